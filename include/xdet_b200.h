@@ -1,0 +1,88 @@
+/* xdet_b200.h -- C-ABI of the B200-native Light-Head R-CNN hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, `extern "C"`, no C++/torch/TF
+ * types.  Every entry point names the reference interface it replaces (paths relative to
+ * HiKapok/X-Detector @ 1b19e15).  All `d_` pointers are DEVICE pointers on the current CUDA
+ * device; all calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
+ * legacy default stream) unless the name ends in `_host`.  The library never frees or keeps a
+ * caller pointer.  Return value: 0 on success, negative XDET_E* on error, with a message
+ * retrievable (per thread) from xdet_last_error().  Nothing here ever calls exit()
+ * (the reference does on a launch failure: cpp/PSROIPooling/ps_roi_align_op.cu:150-155).
+ */
+#ifndef XDET_B200_H_
+#define XDET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XDET_OK 0
+#define XDET_EINVAL (-1) /* shape / attribute violation (the reference's errors::InvalidArgument) */
+#define XDET_ECUDA (-2)  /* CUDA runtime / launch error */
+#define XDET_ENOMEM (-3)
+
+/* Message of the last failing call made by this thread ("" if none). */
+const char* xdet_last_error(void);
+/* "xdet_b200 <version> sm_100a" */
+const char* xdet_version(void);
+/* Number of kernels launched by this library in this process (bench.py's gpu_launches). */
+long long xdet_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * PsRoiAlign forward.
+ * Replaces: TF op "PsRoiAlign" -- REGISTER_OP cpp/PSROIPooling/ps_roi_align_op.cc:38-76,
+ *           PSROIAlignOp::Compute :220-244, functor seam PSROIAlignFunctor<Device,T>::operator()
+ *           cpp/PSROIPooling/ps_roi_align_op.h:40-57 (same flat pointers + dims tuple),
+ *           CUDA kernel cpp/PSROIPooling/ps_roi_align_op.cu:37-156.
+ *   d_inputs  [N,C,H,W] f32 (NCHW, as the reference requires)
+ *   d_rois    [N,R,4]   f32 (center_y, center_x, h, w), normalised to [0,1]
+ *   d_pooled  [N,R,gw*gh,C/(gw*gh)] f32   (out)
+ *   d_index   [N,R,gw*gh,C/(gw*gh)] i32   (out; arg-max sample id for 'max', 0 for 'mean')
+ *   use_max   1 = pool_method contains "max", 0 = "mean"
+ * Errors (XDET_EINVAL): gw,gh <= 0, C % (gw*gh) != 0 (shape fn :68-70), negative sizes.
+ * Results are bit-identical to the reference's CPU functor (:94-193); the two documented
+ * deviations (degenerate RoIs write index 0; out-of-contract samples are clamped) are listed
+ * in DESIGN.md.
+ */
+int xdet_psroi_align_fwd(const float* d_inputs, const float* d_rois, float* d_pooled, int32_t* d_index,
+                         int N, int C, int H, int W, int R, int gw, int gh, int use_max, void* stream);
+
+/* Same, with an explicit kernel variant (tests and benchmarks):
+ *   XDET_PSROI_AUTO   pick by shape
+ *   XDET_PSROI_GATHER one thread per output element, taps gathered from global memory (any shape)
+ *   XDET_PSROI_PLANES channel-slice planes staged in shared memory, RoIs streamed past them
+ *                     (needs (C/(gw*gh))*H*W*4 B <= ~200 KB) */
+#define XDET_PSROI_AUTO 0
+#define XDET_PSROI_GATHER 1
+#define XDET_PSROI_PLANES 2
+int xdet_psroi_align_fwd_ex(const float* d_inputs, const float* d_rois, float* d_pooled, int32_t* d_index,
+                            int N, int C, int H, int W, int R, int gw, int gh, int use_max, int variant,
+                            void* stream);
+
+/* PsRoiAlign backward.
+ * Replaces: TF op "PsRoiAlignGrad" -- cpp/PSROIPooling/ps_roi_align_grad_op.cc:39-57,326-373,
+ *           CPU functor :187-322, CUDA kernel ps_roi_align_grad_op.cu:37-165; registered as the
+ *           gradient of PsRoiAlign at light_head_rfcn_train.py:201-213.
+ *   d_rois [N,R,4], d_pooled_grad [N,R,G,C/G] f32, d_index [N,R,G,C/G] i32 -> d_grad [N,C,H,W] f32
+ * d_grad is fully overwritten (the reference zero-fills first, :197).  Deterministic: each map
+ * cell accumulates its contributions in the reference CPU functor's order (roi-major), so the
+ * result is bit-identical to it and run-to-run reproducible (the reference's GPU kernel uses
+ * float atomics and is not).
+ */
+int xdet_psroi_align_bwd(const float* d_rois, const float* d_pooled_grad, const int32_t* d_index, float* d_grad,
+                         int N, int C, int H, int W, int R, int gw, int gh, int use_max, void* stream);
+
+/* Host-buffer convenience forms (what a framework without device tensors would bind):
+ * copy in, run, copy out, synchronise.  h_ pointers are host memory (pinned or pageable). */
+int xdet_psroi_align_fwd_host(const float* h_inputs, const float* h_rois, float* h_pooled, int32_t* h_index,
+                              int N, int C, int H, int W, int R, int gw, int gh, int use_max);
+int xdet_psroi_align_bwd_host(const float* h_rois, const float* h_pooled_grad, const int32_t* h_index,
+                              float* h_grad, int N, int C, int H, int W, int R, int gw, int gh, int use_max);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XDET_B200_H_ */

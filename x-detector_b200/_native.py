@@ -1,0 +1,81 @@
+"""Loader / builder for the native library (``csrc/libxdet_b200.so``) and ctypes prototypes of
+the C-ABI in ``include/xdet_b200.h``."""
+import ctypes
+import glob
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libxdet_b200.so")
+INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    # bit-exact parity with the reference's CPU arithmetic needs separate mul/add roundings
+    "-fmad=false",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def build(force=False, verbose=False):
+    """Compile every ``csrc/*.cu`` for sm_100a into ``csrc/libxdet_b200.so`` (in-tree)."""
+    srcs = sources()
+    deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
+    if not force and os.path.exists(LIB_PATH):
+        if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(p) for p in deps):
+            return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", LIB_PATH]
+    subprocess.check_call(cmd, cwd=CSRC)
+    return LIB_PATH
+
+
+_lib = None
+_F32P = ctypes.POINTER(ctypes.c_float)
+_I32P = ctypes.POINTER(ctypes.c_int32)
+
+
+def _declare(lib):
+    c_int, c_void_p = ctypes.c_int, ctypes.c_void_p
+    lib.xdet_last_error.restype = ctypes.c_char_p
+    lib.xdet_version.restype = ctypes.c_char_p
+    lib.xdet_launch_count.restype = ctypes.c_longlong
+    lib.xdet_psroi_align_fwd.argtypes = [c_void_p] * 4 + [c_int] * 8 + [c_void_p]
+    lib.xdet_psroi_align_fwd_ex.argtypes = [c_void_p] * 4 + [c_int] * 9 + [c_void_p]
+    lib.xdet_psroi_align_bwd.argtypes = [c_void_p] * 4 + [c_int] * 8 + [c_void_p]
+    lib.xdet_psroi_align_fwd_host.argtypes = [c_void_p] * 4 + [c_int] * 8
+    lib.xdet_psroi_align_bwd_host.argtypes = [c_void_p] * 4 + [c_int] * 8
+
+
+def lib():
+    """The loaded C-ABI library.  Raises loudly if it has not been built: no fallback exists."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryMissing(
+                "%s not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). xdet_b200 has no CPU or PyTorch fallback." % LIB_PATH)
+        _lib = ctypes.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().xdet_last_error().decode()
+        if rc == -1:
+            raise ValueError(msg)
+        raise RuntimeError("xdet_b200 native error %d: %s" % (rc, msg))
+
+
+def launch_count():
+    return int(lib().xdet_launch_count())
