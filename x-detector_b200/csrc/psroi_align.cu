@@ -14,6 +14,7 @@
 //     and one fp32 divide.
 // No tensor cores: this is irregular, HBM/L1-bound gather work.
 #include <cfloat>
+#include <climits>
 #include <cstdint>
 
 #include "common.cuh"
@@ -84,7 +85,8 @@ struct Tap {
 };
 
 // Per-sample weights, shared by every channel of a bin (ps_roi_align_op.cc:166-176).
-__device__ __forceinline__ void sample_weights(float x, float y, int H, int W, int stride_row, Tap& t) {
+__device__ __forceinline__ void sample_weights(float x, float y, int H, int W, int stride_row, int stride_col,
+                                               Tap& t) {
   int ix = __float2int_rz(x), iy = __float2int_rz(y);
   const float fx = __fsub_rn(x, (float)ix), fy = __fsub_rn(y, (float)iy);
   const int ix1 = min(ix + 1, W - 1), iy1 = min(iy + 1, H - 1);
@@ -92,10 +94,10 @@ __device__ __forceinline__ void sample_weights(float x, float y, int H, int W, i
   iy = min(iy, H - 1);
   ix = max(ix, 0);
   iy = max(iy, 0);
-  t.o00 = iy * stride_row + ix;
-  t.o01 = iy1 * stride_row + ix;
-  t.o10 = iy * stride_row + ix1;
-  t.o11 = iy1 * stride_row + ix1;
+  t.o00 = iy * stride_row + ix * stride_col;
+  t.o01 = iy1 * stride_row + ix * stride_col;
+  t.o10 = iy * stride_row + ix1 * stride_col;
+  t.o11 = iy1 * stride_row + ix1 * stride_col;
   const double dfx = (double)fx, dfy = (double)fy;
   const double ax = __dsub_rn(1.0, dfx), ay = __dsub_rn(1.0, dfy);
   t.w00 = __dmul_rn(ax, ay);
@@ -113,10 +115,11 @@ __device__ __forceinline__ float blend(const Tap& t, float p00, float p01, float
 }
 
 // Pool one output element: `plane` points at the (image, channel) plane (global or shared),
-// with `stride_row` elements between rows.
+// with `stride_row` / `stride_col` elements between rows / columns.
 template <bool kMax>
-__device__ __forceinline__ void pool_one(const float* __restrict__ plane, int stride_row, const RoiGeom& g, float x0,
-                                         float y0, int H, int W, float& out_v, int& out_i) {
+__device__ __forceinline__ void pool_one(const float* __restrict__ plane, int stride_row, int stride_col,
+                                         const RoiGeom& g, float x0, float y0, int H, int W, float& out_v,
+                                         int& out_i) {
   float acc = kMax ? -FLT_MAX : 0.f;
   int arg = 0;
   for (int hi = 0; hi < g.nh; ++hi) {
@@ -124,7 +127,7 @@ __device__ __forceinline__ void pool_one(const float* __restrict__ plane, int st
     for (int wi = 0; wi < g.nw; ++wi) {
       const float x = sample_coord(x0, g.step_w, wi);
       Tap t;
-      sample_weights(x, y, H, W, stride_row, t);
+      sample_weights(x, y, H, W, stride_row, stride_col, t);
       const float v = blend(t, plane[t.o00], plane[t.o01], plane[t.o10], plane[t.o11]);
       if (kMax) {
         if (acc < v) {
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(256) psroi_fwd_gather_kernel(const float* __re
       const float x0 = __fadd_rn(g.xmin, __fmul_rn(g.bin_w, (float)col));
       const float y0 = __fadd_rn(g.ymin, __fmul_rn(g.bin_h, (float)row));
       const float* plane = inputs + ((long long)img * C + c) * H * W;
-      pool_one<kMax>(plane, W, g, x0, y0, H, W, v, a);
+      pool_one<kMax>(plane, W, 1, g, x0, y0, H, W, v, a);
     }
     pooled[e] = v;
     index[e] = a;
@@ -175,77 +178,282 @@ __global__ void __launch_bounds__(256) psroi_fwd_gather_kernel(const float* __re
 }
 
 // ------------------------------------------------------------------------------------------
-// Variant PLANES: the feature map of a detector head is tiny (490x30x30 fp32 = 1.76 MB) and
-// lives in L2; what the op really moves is its OUTPUT (8 B per element).  Each CTA therefore
-// pins a channel slice (whole bins: `bins_per_cta * bank` planes) in shared memory once and
-// streams a range of RoIs past it, so every tap is a shared-memory read and HBM sees only the
-// map once plus the output stream.
-//   grid = (slices, roi_splits, N); block = 256 threads
-//   smem = slice planes [cs][H*W + pad] fp32 (odd plane pitch -> conflict-free across channels)
-//          + double-buffered per-RoI geometry for a chunk of kChunk RoIs
-// Inside a chunk the work items (roi, channel) are laid out channel-fastest so that a warp's
-// stores are contiguous runs of `cs` floats per RoI.
+// Variant PLANES.  The feature map of a detector head is tiny (490x30x30 fp32 = 1.76 MB) and
+// lives in L2; what the op really moves is its OUTPUT (8 B per element).  Measured on B200
+// (tools/ubench_pipes.cu): F2F (float<->double) issues at 16 lanes/clk/SM, FP64 arithmetic at 64,
+// fp32 at 128 -- the bit-exact fp64 blend is conversion- and issue-bound, so the design minimises
+// F2Fs and instructions per (sample, channel):
+//
+//   prep kernel (1 CTA / image): RoI geometry once per RoI -> workspace, plus a permutation that
+//       groups RoIs by their sample grid (nh, nw), heavy classes first, so that the lanes of a warp
+//       run the same trip counts and the tap-reuse branches below are (almost) warp-uniform.
+//   main kernel: grid = (channel slices, splits, N).  A CTA pins its slice (whole bins) in shared
+//       memory once, CHANNEL-MINOR [H*W][pitch]; after that its warps are independent (no CTA
+//       barrier): each warp takes rounds of <= 8 (RoI, bin) pairs round-robin.  Per round it first
+//       tabulates in its private table, per pair and axis, the sample coordinates as
+//       {pixel, fraction f32, fraction f64} (one F2F per table entry instead of one per thread and
+//       sample); then one thread per (pair, group of VEC channels) pools: one vector LDS fetches a
+//       tap for VEC channels, the weights (DADD/DMUL from the tables) are shared by those channels,
+//       and a column that the previous sample of the row already loaded and widened slides over
+//       instead of being re-read (consecutive samples are < 1 px apart).
+//   Output stores: consecutive lanes = consecutive channel groups of one RoI -> vector stores
+//       forming contiguous runs of the slice's channels.
 // ------------------------------------------------------------------------------------------
-constexpr int kPlanesThreads = 256;
-constexpr int kChunk = 32;
+constexpr int kPlanesThreads = 384;
+constexpr int kPairsPerWarp = 8;  // (RoI, bin) pairs per warp round (<= 32 / groups-per-bin)
+constexpr int kTMax = 8;    // table depth per axis; RoIs with more samples per bin take the generic path
+constexpr int kClassDim = 8;
+constexpr int kNumClasses = kClassDim * kClassDim + 1;
+constexpr int kPrepThreads = 1024;
 
-template <bool kMax>
-__global__ void __launch_bounds__(kPlanesThreads) psroi_fwd_planes_kernel(
-    const float* __restrict__ inputs, const float* __restrict__ rois, float* __restrict__ pooled,
-    int32_t* __restrict__ index, int C, int H, int W, int R, int gw, int gh, int bins_per_cta, int plane_pitch,
-    int rois_per_split) {
+struct AxisEntry {
+  double fd;  // fractional part, widened once
+  float ff;   // fractional part (fp32, for the all-float fourth term)
+  int i;      // integer pixel (unclamped)
+};
+struct PairMeta {
+  int r, nh, nw, bl;
+};
+
+__device__ __forceinline__ int roi_class(const RoiGeom& g) {
+  if (g.nh <= 0) return kNumClasses - 1;  // degenerate: lightest
+  const int a = min(g.nh, kClassDim) - 1, b = min(g.nw, kClassDim) - 1;
+  return (kClassDim - 1 - a) * kClassDim + (kClassDim - 1 - b);  // heavy first
+}
+
+__global__ void __launch_bounds__(kPrepThreads) psroi_prep_kernel(const float* __restrict__ rois,
+                                                                  RoiGeom* __restrict__ geom, int* __restrict__ perm,
+                                                                  int R, int H, int W, int gw, int gh) {
+  __shared__ int hist[kNumClasses];
+  __shared__ int base[kNumClasses];
+  const int img = blockIdx.x;
+  for (int i = threadIdx.x; i < kNumClasses; i += kPrepThreads) hist[i] = 0;
+  __syncthreads();
+  for (int r = threadIdx.x; r < R; r += kPrepThreads) {
+    const RoiGeom g = roi_geometry(rois + ((long long)img * R + r) * 4, H, W, gw, gh);
+    geom[(long long)img * R + r] = g;
+    atomicAdd(&hist[roi_class(g)], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int i = 0; i < kNumClasses; ++i) {
+      base[i] = run;
+      run += hist[i];
+    }
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < R; r += kPrepThreads) {
+    const RoiGeom g = geom[(long long)img * R + r];
+    const int pos = atomicAdd(&base[roi_class(g)], 1);
+    perm[(long long)img * R + pos] = r;  // order inside a class is arbitrary: outputs are independent
+  }
+}
+
+template <int VEC>
+struct VecLoad;
+template <>
+struct VecLoad<4> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  static __device__ __forceinline__ void st(int32_t* p, const int (&v)[4]) {
+    *reinterpret_cast<int4*>(p) = make_int4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct VecLoad<2> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[2]) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    v[0] = t.x; v[1] = t.y;
+  }
+  static __device__ __forceinline__ void st(float* p, const float (&v)[2]) {
+    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+  }
+  static __device__ __forceinline__ void st(int32_t* p, const int (&v)[2]) {
+    *reinterpret_cast<int2*>(p) = make_int2(v[0], v[1]);
+  }
+};
+template <>
+struct VecLoad<1> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[1]) { v[0] = *p; }
+  static __device__ __forceinline__ void st(float* p, const float (&v)[1]) { *p = v[0]; }
+  static __device__ __forceinline__ void st(int32_t* p, const int (&v)[1]) { *p = v[0]; }
+};
+
+template <bool kMax, int VEC>
+__global__ void __launch_bounds__(kPlanesThreads, 2) psroi_fwd_planes_kernel(
+    const float* __restrict__ inputs, const RoiGeom* __restrict__ geom, const int* __restrict__ perm,
+    float* __restrict__ pooled, int32_t* __restrict__ index, int C, int H, int W, int R, int gw, int gh,
+    int bins_per_cta, int pitch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int kWarps = kPlanesThreads / 32;
   const int G = gw * gh, bank = C / G, HW = H * W;
   const int bin0 = blockIdx.x * bins_per_cta;
   const int nbins = min(bins_per_cta, G - bin0);
-  const int cs = nbins * bank;  // channels in this CTA's slice
+  const int cs = nbins * bank;
   const int c0 = bin0 * bank;
   const int img = blockIdx.z;
-  const int r_begin = blockIdx.y * rois_per_split;
-  const int r_end = min(R, r_begin + rois_per_split);
+  const int gpb = bank / VEC;                      // channel groups per bin
+  const int ppw = min(kPairsPerWarp, 32 / gpb > 0 ? 32 / gpb : 1);  // (RoI, bin) pairs per warp round
+  const long long npairs_total = (long long)R * nbins;
+  const int nrounds = (int)((npairs_total + ppw - 1) / ppw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  float* planes = reinterpret_cast<float*>(smem_raw);
-  RoiGeom* geom = reinterpret_cast<RoiGeom*>(smem_raw + (size_t)bins_per_cta * bank * plane_pitch * sizeof(float));
+  // per-warp private tables: no CTA-wide barrier after the slice is staged
+  AxisEntry* xt = reinterpret_cast<AxisEntry*>(smem_raw) + warp * (2 * kPairsPerWarp * kTMax);
+  AxisEntry* yt = xt + kPairsPerWarp * kTMax;
+  PairMeta* meta = reinterpret_cast<PairMeta*>(reinterpret_cast<AxisEntry*>(smem_raw) +
+                                               kWarps * 2 * kPairsPerWarp * kTMax) + warp * kPairsPerWarp;
+  float* planes = reinterpret_cast<float*>(reinterpret_cast<PairMeta*>(
+      reinterpret_cast<AxisEntry*>(smem_raw) + kWarps * 2 * kPairsPerWarp * kTMax) + kWarps * kPairsPerWarp);
 
-  // Stage the slice: global [cs][HW] contiguous -> shared [cs][plane_pitch].
-  {
+  {  // stage the slice, transposing to channel-minor [HW][pitch]
     const float* src = inputs + ((long long)img * C + c0) * HW;
     const int n = cs * HW;
     for (int i = threadIdx.x; i < n; i += kPlanesThreads) {
       const int ch = i / HW, p = i - ch * HW;
-      planes[ch * plane_pitch + p] = __ldg(src + i);
+      planes[p * pitch + ch] = __ldg(src + i);
     }
   }
+  __syncthreads();
 
-  const int items = kChunk * cs;
-  int buf = 0;
-  for (int rc = r_begin; rc < r_end; rc += kChunk, buf ^= 1) {
-    RoiGeom* gbuf = geom + buf * kChunk;
-    if (threadIdx.x < kChunk) {
-      const int r = rc + threadIdx.x;
-      if (r < r_end) gbuf[threadIdx.x] = roi_geometry(rois + ((long long)img * R + r) * 4, H, W, gw, gh);
+  const RoiGeom* geom_img = geom + (long long)img * R;
+  const int* perm_img = perm + (long long)img * R;
+  const int round_stride = gridDim.y * kWarps;
+  for (int round = blockIdx.y * kWarps + warp; round < nrounds; round += round_stride) {
+    const long long q0 = (long long)round * ppw;
+    const int npairs = (int)min((long long)ppw, npairs_total - q0);
+    // ---- tabulate the sample coordinates of this round's (RoI, bin) pairs ---------------------
+    for (int e = lane; e < ppw * 2 * kTMax; e += 32) {
+      const int pl = e / (2 * kTMax), axis = (e / kTMax) & 1, s = e & (kTMax - 1);
+      if (pl < npairs) {
+        const long long q = q0 + pl;
+        const int pos = (int)(q / nbins), bl = (int)(q - (long long)pos * nbins);
+        const int r = perm_img[pos];
+        const RoiGeom g = geom_img[r];
+        if ((e & (2 * kTMax - 1)) == 0) meta[pl] = PairMeta{r, g.nh, g.nw, bl};
+        const int n = axis ? g.nh : g.nw;
+        if (s < n && n <= kTMax) {
+          const int bin = bin0 + bl;
+          const int row = bin / gw, col = bin - row * gw;
+          const float start = axis ? __fadd_rn(g.ymin, __fmul_rn(g.bin_h, (float)row))
+                                   : __fadd_rn(g.xmin, __fmul_rn(g.bin_w, (float)col));
+          const float x = sample_coord(start, axis ? g.step_h : g.step_w, s);
+          const int i = __float2int_rz(x);
+          const float f = __fsub_rn(x, (float)i);
+          (axis ? yt : xt)[pl * kTMax + s] = AxisEntry{(double)f, f, i};
+        }
+      }
     }
-    __syncthreads();  // geometry visible (and, first time round, the staged planes)
-    for (int it = threadIdx.x; it < items; it += kPlanesThreads) {
-      const int rl = it / cs, ch = it - rl * cs;
-      const int r = rc + rl;
-      if (r >= r_end) break;
-      const RoiGeom g = gbuf[rl];
-      const int bin = bin0 + ch / bank;
-      const int row = bin / gw, col = bin - row * gw;
-      float v = 0.f;
-      int a = 0;
-      if (g.nh > 0) {
+    __syncwarp();
+    // ---- pool: one lane per (pair, group of VEC channels) --------------------------------------
+    if (lane < npairs * gpb) {
+      const int pl = lane / gpb, gi = lane - pl * gpb;
+      const PairMeta m = meta[pl];
+      const int ch0 = m.bl * bank + gi * VEC;  // first channel of this lane inside the slice
+      const float* pbase = planes + ch0;
+      float acc[VEC];
+      int arg[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        acc[k] = kMax ? -FLT_MAX : 0.f;
+        arg[k] = 0;
+      }
+      if (m.nh <= 0) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+      } else if (m.nh <= kTMax && m.nw <= kTMax) {
+        const AxisEntry* xr = xt + pl * kTMax;
+        const AxisEntry* yr = yt + pl * kTMax;
+        const int row_pitch = W * pitch;
+        for (int hi = 0; hi < m.nh; ++hi) {
+          const AxisEntry ey = yr[hi];
+          const int iy = max(min(ey.i, H - 1), 0), iy1 = min(ey.i + 1, H - 1);
+          const double ay = __dsub_rn(1.0, ey.fd);
+          const float* ra = pbase + iy * row_pitch;
+          const float* rb = pbase + iy1 * row_pitch;
+          int cur = INT_MIN;
+          double p00[VEC], p01[VEC], p10[VEC];
+          float p11[VEC];
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            p00[k] = p01[k] = p10[k] = 0.;
+            p11[k] = 0.f;
+          }
+          for (int wi = 0; wi < m.nw; ++wi) {
+            const AxisEntry ex = xr[wi];
+            if (ex.i != cur) {
+              const int ix1 = min(ex.i + 1, W - 1);
+              if (ex.i == cur + 1) {  // slide: the right column becomes the left one
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                  p00[k] = p10[k];
+                  p01[k] = (double)p11[k];
+                }
+              } else {
+                const int ix = max(min(ex.i, W - 1), 0);
+                float ta[VEC], tb[VEC];
+                VecLoad<VEC>::ld(ra + ix * pitch, ta);
+                VecLoad<VEC>::ld(rb + ix * pitch, tb);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                  p00[k] = (double)ta[k];
+                  p01[k] = (double)tb[k];
+                }
+              }
+              float tc[VEC];
+              VecLoad<VEC>::ld(ra + ix1 * pitch, tc);
+              VecLoad<VEC>::ld(rb + ix1 * pitch, p11);
+#pragma unroll
+              for (int k = 0; k < VEC; ++k) p10[k] = (double)tc[k];
+              cur = ex.i;
+            }
+            const double ax = __dsub_rn(1.0, ex.fd);
+            const double w00 = __dmul_rn(ax, ay), w01 = __dmul_rn(ax, ey.fd), w10 = __dmul_rn(ex.fd, ay);
+            const float w11 = __fmul_rn(ex.ff, ey.ff);
+            const int sid = m.nw * hi + wi;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              double sum = __dmul_rn(w00, p00[k]);
+              sum = __dadd_rn(sum, __dmul_rn(w01, p01[k]));
+              sum = __dadd_rn(sum, __dmul_rn(w10, p10[k]));
+              sum = __dadd_rn(sum, (double)__fmul_rn(w11, p11[k]));
+              const float v = __double2float_rn(sum);
+              if (kMax) {
+                if (acc[k] < v) {
+                  acc[k] = v;
+                  arg[k] = sid;
+                }
+              } else {
+                acc[k] = __fadd_rn(acc[k], v);
+              }
+            }
+          }
+        }
+        if (!kMax) {
+          const float cnt = (float)(m.nh * m.nw);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) acc[k] = __fdiv_rn(acc[k], cnt);
+        }
+      } else {  // more than kTMax samples per bin axis: generic per-channel path
+        const RoiGeom g = geom_img[m.r];
+        const int bin = bin0 + m.bl;
+        const int row = bin / gw, col = bin - row * gw;
         const float x0 = __fadd_rn(g.xmin, __fmul_rn(g.bin_w, (float)col));
         const float y0 = __fadd_rn(g.ymin, __fmul_rn(g.bin_h, (float)row));
-        pool_one<kMax>(planes + ch * plane_pitch, W, g, x0, y0, H, W, v, a);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) pool_one<kMax>(pbase + k, W * pitch, pitch, g, x0, y0, H, W, acc[k], arg[k]);
       }
-      const long long o = ((long long)img * R + r) * C + c0 + ch;
-      pooled[o] = v;
-      index[o] = a;
+      const long long o = ((long long)img * R + m.r) * C + c0 + ch0;
+      VecLoad<VEC>::st(pooled + o, acc);
+      VecLoad<VEC>::st(index + o, arg);
     }
-    // no second barrier: the next chunk writes the other geometry buffer, and a thread can only
-    // reach the chunk after that (overwriting this buffer) by passing the next __syncthreads().
+    __syncwarp();  // the next round overwrites this warp's tables
   }
 }
 
@@ -354,21 +562,65 @@ int validate(int N, int C, int H, int W, int R, int gw, int gh) {
 
 constexpr size_t kMaxSmem = 227 * 1024;
 
-// Largest number of whole bins whose planes (+geometry buffers) fit in shared memory; 0 if none.
+size_t planes_fixed_smem() {
+  constexpr size_t warps = kPlanesThreads / 32;
+  return warps * (2 * (size_t)kPairsPerWarp * kTMax * sizeof(AxisEntry) + (size_t)kPairsPerWarp * sizeof(PairMeta));
+}
+
+int planes_vec(int bank) { return (bank % 4 == 0 && bank >= 16) ? 4 : ((bank % 2 == 0 && bank >= 8) ? 2 : 1); }
+
+// Whole bins per CTA for the PLANES variant (0 = a single bin does not fit shared memory).
+// Two CTAs per SM are wanted (latency hiding), so a slice aims at <= ~half of the SM's shared
+// memory; small banks are grouped up to ~32 channels so that a RoI's stores form longer runs.
 int planes_bins_per_cta(int bank, int H, int W, int G, int* pitch_out, size_t* smem_out) {
-  const int HW = H * W;
-  const int pitch = (HW % 2 == 0) ? HW + 1 : HW;  // odd pitch: channels land in distinct banks
-  const size_t geom_bytes = 2 * kChunk * sizeof(RoiGeom);
-  const size_t per_bin = (size_t)bank * pitch * sizeof(float);
-  if (per_bin + geom_bytes > kMaxSmem) return 0;
-  // One bin per CTA keeps the slice small (more CTAs per SM, more slices to spread over the 148
-  // SMs); tiny banks (15x15 grids: bank 4) are grouped until a slice is at least ~32 channels so
-  // that a RoI's output run stays a reasonable store width.
-  int bins = 1;
-  while (bins < G && (bins * bank) < 32 && (size_t)(bins + 1) * per_bin + geom_bytes <= kMaxSmem) ++bins;
-  *pitch_out = pitch;
-  *smem_out = (size_t)bins * per_bin + geom_bytes;
-  return bins;
+  const int HW = H * W, vec = planes_vec(bank);
+  const size_t fixed = planes_fixed_smem();
+  const size_t target = kMaxSmem / 2 - 1024;
+  int best = 0, best_pitch = 0;
+  for (int bins = 1; bins <= G; ++bins) {
+    int pitch = (bins * bank + vec - 1) / vec * vec;
+    if ((pitch / vec) % 2 == 0) pitch += vec;  // odd number of vector slots per pixel: spreads banks
+    const size_t need = (size_t)HW * pitch * sizeof(float) + fixed;
+    if (need > kMaxSmem) break;
+    if (bins > 1 && (need > target || (bins - 1) * bank >= 32)) break;
+    best = bins;
+    best_pitch = pitch;
+  }
+  if (best == 0) return 0;
+  *pitch_out = best_pitch;
+  *smem_out = (size_t)HW * best_pitch * sizeof(float) + fixed;
+  return best;
+}
+
+struct WorkspacePoolInit {
+  WorkspacePoolInit() {
+    // keep stream-ordered allocations cached instead of returning them to the OS at every sync
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) return;
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+};
+
+template <bool kMax, int VEC>
+int launch_planes(const float* in, const RoiGeom* geom, const int* perm, float* pooled, int32_t* index, int N, int C,
+                  int H, int W, int R, int gw, int gh, int bins, int pitch, size_t smem, cudaStream_t st) {
+  const int G = gw * gh;
+  const int slices = (G + bins - 1) / bins;
+  const int ctas_per_sm = (2 * smem <= kMaxSmem) ? 2 : 1;
+  // exactly one wave: every CTA is resident, warps stride over the (class-sorted) pair rounds
+  int splits = (kNumSMs * ctas_per_sm) / (slices * N);
+  const long long max_useful = ((long long)R * bins + kPairsPerWarp - 1) / kPairsPerWarp;
+  if (splits > max_useful) splits = (int)max_useful;
+  if (splits < 1) splits = 1;
+  auto kern = psroi_fwd_planes_kernel<kMax, VEC>;
+  XDET_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                      "cudaFuncSetAttribute(psroi_fwd_planes)"));
+  dim3 grid(slices, splits, N);
+  kern<<<grid, kPlanesThreads, smem, st>>>(in, geom, perm, pooled, index, C, H, W, R, gw, gh, bins, pitch);
+  return after_launch("psroi_fwd_planes_kernel");
 }
 
 template <bool kMax>
@@ -379,29 +631,38 @@ int launch_fwd(const float* in, const float* rois, float* pooled, int32_t* index
   const int G = gw * gh, bank = C / G;
   int pitch = 0;
   size_t smem = 0;
-  const int bins = (bank > 0 && H > 0 && W > 0) ? planes_bins_per_cta(bank, H, W, G, &pitch, &smem) : 0;
+  // a warp round maps one lane to each (pair, channel group): needs bank / VEC <= 32
+  const bool planes_ok = bank > 0 && H > 0 && W > 0 && bank / planes_vec(bank) <= 32;
+  const int bins = planes_ok ? planes_bins_per_cta(bank, H, W, G, &pitch, &smem) : 0;
   if (variant == XDET_PSROI_PLANES && bins == 0)
-    return fail(XDET_EINVAL, "PLANES variant needs bank*H*W*4 B (=%zu) to fit shared memory",
+    return fail(XDET_EINVAL, "PLANES variant needs bank*H*W*4 B (=%zu) to fit shared memory and bank/VEC <= 32",
                 (size_t)bank * H * W * 4);
-  if (variant == XDET_PSROI_AUTO) variant = (bins > 0 && (long long)R * N >= 64) ? XDET_PSROI_PLANES : XDET_PSROI_GATHER;
+  if (variant == XDET_PSROI_AUTO)
+    // measured on B200 (profiles/psroi_sweep_r1.md): the staged variant wins once there are a few million
+    // outputs and the bank allows vector channel groups; tiny banks (15x15 bins) stay on the gather kernel
+    variant = (bins > 0 && planes_vec(bank) >= 2 && total >= (3ll << 19)) ? XDET_PSROI_PLANES : XDET_PSROI_GATHER;
 
   if (variant == XDET_PSROI_PLANES) {
-    const int slices = (G + bins - 1) / bins;
-    // Enough RoI splits to give every SM ~2 CTAs, but never fewer than kChunk RoIs per split.
-    const int ctas_per_sm = (int)(kMaxSmem / smem) >= 2 ? 2 : 1;
-    int splits = (kNumSMs * ctas_per_sm + slices * N - 1) / (slices * N);
-    const int max_splits = (R + kChunk - 1) / kChunk;
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
-    int per = (R + splits - 1) / splits;
-    per = (per + kChunk - 1) / kChunk * kChunk;
-    splits = (R + per - 1) / per;
-    auto kern = psroi_fwd_planes_kernel<kMax>;
-    XDET_TRY(check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                        "cudaFuncSetAttribute(psroi_fwd_planes)"));
-    dim3 grid(slices, splits, N);
-    kern<<<grid, kPlanesThreads, smem, st>>>(in, rois, pooled, index, C, H, W, R, gw, gh, bins, pitch, per);
-    return after_launch("psroi_fwd_planes_kernel");
+    static WorkspacePoolInit pool_init;
+    // workspace: per-RoI geometry + class-sorted permutation (stream-ordered allocation)
+    const size_t ws_geom = (size_t)N * R * sizeof(RoiGeom), ws_perm = (size_t)N * R * sizeof(int);
+    void* ws = nullptr;
+    XDET_TRY(check_cuda(cudaMallocAsync(&ws, ws_geom + ws_perm, st), "cudaMallocAsync(psroi workspace)"));
+    RoiGeom* geom = reinterpret_cast<RoiGeom*>(ws);
+    int* perm = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ws) + ws_geom);
+    psroi_prep_kernel<<<N, kPrepThreads, 0, st>>>(rois, geom, perm, R, H, W, gw, gh);
+    int rc = after_launch("psroi_prep_kernel");
+    if (rc == XDET_OK) {
+      const int vec = planes_vec(bank);
+      if (vec == 4)
+        rc = launch_planes<kMax, 4>(in, geom, perm, pooled, index, N, C, H, W, R, gw, gh, bins, pitch, smem, st);
+      else if (vec == 2)
+        rc = launch_planes<kMax, 2>(in, geom, perm, pooled, index, N, C, H, W, R, gw, gh, bins, pitch, smem, st);
+      else
+        rc = launch_planes<kMax, 1>(in, geom, perm, pooled, index, N, C, H, W, R, gw, gh, bins, pitch, smem, st);
+    }
+    cudaFreeAsync(ws, st);
+    return rc;
   }
   if (variant != XDET_PSROI_GATHER) return fail(XDET_EINVAL, "unknown PsRoiAlign variant %d", variant);
   long long blocks = (total + 255) / 256;
