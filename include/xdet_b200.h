@@ -82,6 +82,41 @@ int xdet_psroi_align_fwd_host(const float* h_inputs, const float* h_rois, float*
 int xdet_psroi_align_bwd_host(const float* h_rois, const float* h_pooled_grad, const int32_t* h_index,
                               float* h_grad, int N, int C, int H, int W, int R, int gw, int gh, int use_max);
 
+
+/* ---------------------------------------------------------------------------------------
+ * Stride-1 convolution / GEMM on the tcgen05 tensor cores (bf16 operands, fp32 accumulate).
+ * Replaces: the cuDNN / cuBLAS kernels TensorFlow runs for tf.layers.conv2d / tf.layers.dense on
+ *   the path -- conv2d_fixed_padding net/resnet_v2.py:89-100 (stride-1 cases), dilate_conv2d
+ *   net/xdet_body.py:28-37, get_rpn net/xception_body.py:381-400, large_sep_kernel :450-475,
+ *   the pointwise half of tf.layers.separable_conv2d :224-233, get_head's dense layers :540-558.
+ * Input  : NHWC bf16, pixel (n,y,x) at d_in + ((n*H + y)*W + x)*in_cs, in_cs % 8 == 0.
+ * Weights: [Cout][KH*KW][ceil(Cin/64)*64] bf16, tap-major, input channels zero-padded to 64.
+ * Output : out(n,y,x,c) at out + n*out_sn + y*out_sy + x*out_sx + c*out_sc (elements), bf16 or fp32:
+ *            v    = acc*scale[c] + bias[c]  (+ residual(n,y,x,c), bf16, laid out like `out`)  (ReLU if relu)
+ *            out  = v ;  out2 = ReLU(v*scale2[c] + bias2[c])  (optional, bf16, laid out like `out`)
+ *          with acc(n,y,x,c) = sum_{kh,kw,ci} in(n, y + kh*dil_h - pad_top, x + kw*dil_w - pad_left, ci) * w
+ *          (reads outside the image are zero: TF 'SAME' padding = pad_top/left = floor(total/2)).
+ * A plain GEMM D[M,Nc] = A[M,K] * W[Nc,K]^T is the case N=1, H=1, W=M, Cin=K, KH=KW=1.
+ */
+typedef struct {
+  int N, H, W, Cin, in_cs;
+  int Cout, KH, KW, dil_h, dil_w, pad_top, pad_left;
+  int Hout, Wout;
+  const void* weights;
+  const float* scale; /* per-Cout multiplier (folded batch-norm), NULL = 1 */
+  const float* bias;  /* per-Cout addend (conv bias / folded batch-norm), NULL = 0 */
+  int relu;
+  const void* residual; /* bf16 or NULL */
+  void* out;
+  int out_fp32; /* 0: bf16, 1: fp32 */
+  long long out_sn, out_sy, out_sx, out_sc;
+  void* out2; /* bf16 or NULL */
+  const float* scale2;
+  const float* bias2;
+  int block_n; /* 0 = auto; otherwise the N tile (multiple of 16, <= 256) */
+} xdet_conv_desc;
+int xdet_conv2d_bf16(const void* d_in, const xdet_conv_desc* desc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

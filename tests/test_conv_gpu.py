@@ -1,0 +1,97 @@
+"""GPU: tcgen05 implicit-GEMM convolution vs a plain PyTorch fp32 reference of the same op on the
+same bf16-rounded operands (fp32 accumulation on both sides).  Tolerance: the only differences are
+fp32 summation order and the final bf16 rounding of the output."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available()
+    import xdet_b200  # noqa: F401
+    from xdet_b200 import ops
+    return ops
+
+
+def ref_conv(x_nhwc, w_oihw, dil, pad_tl, out_hw):
+    """fp32 conv with explicit TF-style (asymmetric) padding on bf16-rounded operands."""
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    w = w_oihw.to(torch.bfloat16).float()
+    kh, kw = w.shape[2:]
+    Ho, Wo = out_hw
+    pt, pl = pad_tl
+    need_h = Ho + (kh - 1) * dil[0]
+    need_w = Wo + (kw - 1) * dil[1]
+    pb, pr = need_h - x.shape[2] - pt, need_w - x.shape[3] - pl
+    x = F.pad(x, (pl, max(pr, 0), pt, max(pb, 0)))
+    return F.conv2d(x, w, dilation=dil)[:, :, :Ho, :Wo]
+
+
+CASES = [
+    # N, H, W, Cin, Cout, KH, KW, dil
+    (2, 30, 30, 64, 128, 1, 1, 1),
+    (1, 30, 30, 256, 64, 3, 3, 1),
+    (2, 30, 30, 128, 256, 3, 3, 2),     # dilated (layer4 / xception exit flow)
+    (1, 30, 30, 192, 256, 15, 1, 1),    # large separable, vertical
+    (1, 30, 30, 256, 496, 1, 15, 1),    # large separable, horizontal, Cout not a multiple of 128
+    (1, 60, 60, 128, 128, 3, 3, 1),
+    (1, 120, 120, 64, 64, 3, 3, 1),
+    (1, 50, 50, 728, 728, 1, 1, 1),     # Cin not a multiple of 64
+    (3, 17, 23, 72, 40, 3, 3, 1),       # ragged everything
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv_matches_fp32_reference(ops, case):
+    N, H, W, Cin, Cout, KH, KW, dil = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case))
+    x = torch.randn((N, H, W, Cin), generator=g, device="cuda").to(torch.bfloat16)
+    w = torch.randn((Cout, Cin, KH, KW), generator=g, device="cuda") / (Cin * KH * KW) ** 0.5
+    wp = ops.pack_conv_weight(w)
+    y = ops.conv2d_nhwc(x, wp, Cout, KH, KW, dilation=(dil, dil), out_layout="nhwc_f32")
+    torch.cuda.synchronize()
+    ref = ref_conv(x, w, (dil, dil), (ops.same_pad(H, KH, dil), ops.same_pad(W, KW, dil)), (H, W)).permute(0, 2, 3, 1)
+    err = (y - ref).abs().max().item()
+    assert err < 2e-3, err
+
+
+def test_epilogue_scale_bias_relu_residual_dual_output(ops):
+    N, H, W, Cin, Cout = 2, 30, 30, 256, 256
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn((N, H, W, Cin), generator=g, device="cuda").to(torch.bfloat16)
+    w = torch.randn((Cout, Cin, 1, 1), generator=g, device="cuda") / Cin ** 0.5
+    scale = torch.rand(Cout, generator=g, device="cuda") + 0.5
+    bias = torch.randn(Cout, generator=g, device="cuda")
+    scale2 = torch.rand(Cout, generator=g, device="cuda") + 0.5
+    bias2 = torch.randn(Cout, generator=g, device="cuda")
+    res = torch.randn((N, H, W, Cout), generator=g, device="cuda").to(torch.bfloat16)
+    out2 = torch.empty((N, H, W, Cout), dtype=torch.bfloat16, device="cuda")
+    y = ops.conv2d_nhwc(x, ops.pack_conv_weight(w), Cout, 1, 1, scale=scale, bias=bias, residual=res, out2=out2,
+                        scale2=scale2, bias2=bias2)
+    torch.cuda.synchronize()
+    acc = ref_conv(x, w, (1, 1), (0, 0), (H, W)).permute(0, 2, 3, 1)
+    v = acc * scale + bias + res.float()
+    assert (y.float() - v).abs().max().item() < 0.05  # bf16 output rounding (|v| up to ~6)
+    v2 = torch.relu(v * scale2 + bias2)
+    assert (out2.float() - v2).abs().max().item() < 0.06
+    y3 = ops.conv2d_nhwc(x, ops.pack_conv_weight(w), Cout, 1, 1, bias=bias, relu=True, out_layout="nchw_f32")
+    torch.cuda.synchronize()
+    assert (y3 - torch.relu(acc + bias).permute(0, 3, 1, 2)).abs().max().item() < 2e-3
+
+
+def test_valid_padding_and_linear(ops):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn((1, 20, 20, 64), generator=g, device="cuda").to(torch.bfloat16)
+    w = torch.randn((64, 64, 3, 3), generator=g, device="cuda") / 24.0
+    y = ops.conv2d_nhwc(x, ops.pack_conv_weight(w), 64, 3, 3, padding="VALID", out_layout="nhwc_f32")
+    ref = ref_conv(x, w, (1, 1), (0, 0), (18, 18)).permute(0, 2, 3, 1)
+    assert y.shape == (1, 18, 18, 64) and (y - ref).abs().max().item() < 2e-3
+    a = torch.randn((1000, 496), generator=g, device="cuda").to(torch.bfloat16)
+    wl = torch.randn((2048, 496), generator=g, device="cuda") / 22.0
+    yl = ops.linear(a, ops.pack_conv_weight(wl.reshape(2048, 496, 1, 1)), 2048, out_layout="nhwc_f32")
+    refl = a.float() @ wl.to(torch.bfloat16).float().t()
+    assert (yl.reshape(1000, 2048) - refl).abs().max().item() < 2e-3
+

@@ -54,6 +54,7 @@ def _declare(lib):
     lib.xdet_psroi_align_bwd.argtypes = [c_void_p] * 4 + [c_int] * 8 + [c_void_p]
     lib.xdet_psroi_align_fwd_host.argtypes = [c_void_p] * 4 + [c_int] * 8
     lib.xdet_psroi_align_bwd_host.argtypes = [c_void_p] * 4 + [c_int] * 8
+    lib.xdet_conv2d_bf16.argtypes = [c_void_p, c_void_p, c_void_p]
 
 
 def lib():

@@ -1,0 +1,96 @@
+"""Host side of the tensor-core convolution / GEMM (``csrc/conv_gemm.cu`` through
+``xdet_conv2d_bf16``).  Tensors are NHWC bf16 CUDA torch tensors (container only).
+
+TensorFlow layers this stands in for on the Light-Head R-CNN path: ``tf.layers.conv2d`` with
+``padding='SAME'|'VALID'``, ``strides=1`` and optional ``dilation_rate`` (net/resnet_v2.py:89-100,
+net/xdet_body.py:28-37, net/xception_body.py:381-400,450-475), and ``tf.layers.dense``
+(net/xception_body.py:540-558).  Batch-norm (inference form) and ReLU are folded into the epilogue.
+"""
+import ctypes
+
+import torch
+
+from .. import _native
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [
+        ("N", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int), ("Cin", ctypes.c_int), ("in_cs", ctypes.c_int),
+        ("Cout", ctypes.c_int), ("KH", ctypes.c_int), ("KW", ctypes.c_int), ("dil_h", ctypes.c_int),
+        ("dil_w", ctypes.c_int), ("pad_top", ctypes.c_int), ("pad_left", ctypes.c_int),
+        ("Hout", ctypes.c_int), ("Wout", ctypes.c_int),
+        ("weights", ctypes.c_void_p), ("scale", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("relu", ctypes.c_int),
+        ("residual", ctypes.c_void_p), ("out", ctypes.c_void_p), ("out_fp32", ctypes.c_int),
+        ("out_sn", ctypes.c_longlong), ("out_sy", ctypes.c_longlong), ("out_sx", ctypes.c_longlong),
+        ("out_sc", ctypes.c_longlong),
+        ("out2", ctypes.c_void_p), ("scale2", ctypes.c_void_p), ("bias2", ctypes.c_void_p), ("block_n", ctypes.c_int),
+    ]
+
+
+def pack_conv_weight(w_oihw):
+    """[Cout, Cin, KH, KW] float -> bf16 [Cout, KH*KW*ceil(Cin/64)*64] (tap-major, channels zero-padded)."""
+    cout, cin, kh, kw = w_oihw.shape
+    cpad = (cin + 63) // 64 * 64
+    w = torch.zeros((cout, kh * kw, cpad), dtype=torch.float32, device=w_oihw.device)
+    w[:, :, :cin] = w_oihw.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin).float()
+    return w.reshape(cout, kh * kw * cpad).to(torch.bfloat16).contiguous()
+
+
+def same_pad(n, k, dil=1, stride=1):
+    """TF 'SAME' low-side padding for extent n: total = max((ceil(n/s)-1)*s + k_eff - n, 0), low = total//2."""
+    k_eff = (k - 1) * dil + 1
+    out = -(-n // stride)
+    total = max((out - 1) * stride + k_eff - n, 0)
+    return total // 2
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def conv2d_nhwc(x, w_packed, cout, kh, kw, *, dilation=(1, 1), padding="SAME", scale=None, bias=None, relu=False,
+                residual=None, out=None, out_layout="nhwc_bf16", out2=None, scale2=None, bias2=None, cin=None,
+                block_n=0):
+    """x: [N,H,W,C] bf16 (channel stride may be padded: pass the true ``cin``).  Returns the output tensor
+    ([N,Ho,Wo,Cout] bf16 for 'nhwc_bf16', [N,Cout,Ho,Wo] fp32 for 'nchw_f32', [N,Ho,Wo,Cout] fp32 for 'nhwc_f32')."""
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4
+    N, H, W, cs = x.shape
+    assert x.stride(3) == 1 and x.stride(2) == cs and x.stride(1) == W * cs and x.stride(0) == H * W * cs
+    cin = cs if cin is None else cin
+    dh, dw = dilation
+    if padding == "SAME":
+        pt, pl = same_pad(H, kh, dh), same_pad(W, kw, dw)
+        Ho, Wo = H, W
+    elif padding == "VALID":
+        pt = pl = 0
+        Ho, Wo = H - (kh - 1) * dh, W - (kw - 1) * dw
+    else:
+        pt, pl, Ho, Wo = padding  # explicit (pad_top, pad_left, Hout, Wout)
+    dev = x.device
+    if out is None:
+        if out_layout == "nhwc_bf16":
+            out = torch.empty((N, Ho, Wo, cout), dtype=torch.bfloat16, device=dev)
+        elif out_layout == "nhwc_f32":
+            out = torch.empty((N, Ho, Wo, cout), dtype=torch.float32, device=dev)
+        elif out_layout == "nchw_f32":
+            out = torch.empty((N, cout, Ho, Wo), dtype=torch.float32, device=dev)
+        else:
+            raise ValueError(out_layout)
+    if out_layout == "nchw_f32":
+        sn, sc, sy, sx = out.stride()
+    else:
+        sn, sy, sx, sc = out.stride()
+    d = ConvDesc(N, H, W, cin, cs, cout, kh, kw, dh, dw, pt, pl, Ho, Wo, w_packed.data_ptr(), _ptr(scale), _ptr(bias),
+                 1 if relu else 0, _ptr(residual), out.data_ptr(), 0 if out.dtype == torch.bfloat16 else 1,
+                 sn, sy, sx, sc, _ptr(out2), _ptr(scale2), _ptr(bias2), block_n)
+    with torch.cuda.device(dev):
+        rc = _native.lib().xdet_conv2d_bf16(x.data_ptr(), ctypes.byref(d), torch.cuda.current_stream().cuda_stream)
+    _native.check(rc)
+    return out
+
+
+def linear(x2d, w_packed, cout, **kw):
+    """[M,K] bf16 @ W[cout,K]^T -> [M,cout]: the dense layers of get_head (net/xception_body.py:540-558)."""
+    M, K = x2d.shape
+    out = conv2d_nhwc(x2d.reshape(1, 1, M, K), w_packed, cout, 1, 1, **kw)
+    return out.reshape(M, cout) if out.dim() == 4 and out.shape[1] == 1 else out
