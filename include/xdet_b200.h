@@ -117,6 +117,57 @@ typedef struct {
 } xdet_conv_desc;
 int xdet_conv2d_bf16(const void* d_in, const xdet_conv_desc* desc, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Bandwidth helpers around the tensor-core convolutions (bf16 NHWC tensors).
+ * xdet_im2col_bf16      patch gather that turns the STRIDED convolutions of the ResNet-v2 stem / stage heads
+ *                       (conv2d_fixed_padding with strides > 1: net/resnet_v2.py:62-100) into GEMMs:
+ *                       dst[n,yo,xo, (kh*KW+kw)*C + c] = src(n, yo*stride+kh-pad_top, xo*stride+kw-pad_left, c)
+ *                       (0 outside); src is NHWC bf16 (pixel pitch in_cs) or NCHW fp32 (the input image);
+ *                       dst pixel pitch out_cs >= KH*KW*C, the tail is zero-filled.
+ * xdet_maxpool3x3s2_bf16  tf.layers.max_pooling2d(3, 2, 'SAME') (net/resnet_v2.py:326-328); optional second
+ *                       output ReLU(pooled*scale2 + bias2) = the first block's pre-activation (resnet_v2.py:163-164).
+ * xdet_affine_relu_bf16 inference batch_norm (+ReLU): y = x*scale[c] + bias[c] (net/resnet_v2.py:41-50).
+ * xdet_f32_to_bf16_rows [rows, cols] fp32 -> [rows, dst_pitch] bf16, zero tail (PsRoIAlign output -> dense operand).
+ */
+int xdet_im2col_bf16(const void* d_src, int src_is_nchw_f32, void* d_dst, int N, int H, int W, int C, int in_cs,
+                     int KH, int KW, int stride, int pad_top, int pad_left, int Ho, int Wo, int out_cs, void* stream);
+int xdet_maxpool3x3s2_bf16(const void* d_src, void* d_dst, void* d_dst2, const float* d_scale2, const float* d_bias2,
+                           int N, int H, int W, int C, int Ho, int Wo, int pad_top, int pad_left, void* stream);
+int xdet_affine_relu_bf16(const void* d_src, void* d_dst, const float* d_scale, const float* d_bias, long long pixels,
+                          int C, int relu, void* stream);
+int xdet_f32_to_bf16_rows(const float* d_src, void* d_dst, long long rows, int cols, int dst_pitch, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * RPN proposals.
+ * xdet_rpn_decode  Replaces: score/loc reshaping + softmax light_head_rfcn_eval.py:389-397 (train :295-305) and
+ *   AnchorEncoder.decode_all_anchors preprocessing/anchor_manipulator.py:641-669 (prior_scaling = 1).
+ *   d_rpn_out [N,fh,fw,ch_stride] fp32: class logits at channel cls_off + a*2 + {0,1}, box deltas at
+ *   box_off + a*4 + {cy,cx,h,w}; anchors yref/xref [fh*fw], href/wref [A] (AnchorCreator, :698-743).
+ *   -> d_scores [N, fh*fw*A], d_boxes [N, fh*fw*A, 4] (ymin,xmin,ymax,xmax); anchor order (y, x, a).
+ * xdet_rpn_select  Replaces: get_proposals (inference branch) net/xception_body.py:402-444 =
+ *   _bboxes_clip :173-194 -> _filter_and_sort_boxes :133-158 (tf.nn.top_k) -> _bboxes_nms :57-67
+ *   (tf.image.non_max_suppression) -> _upsample_rois :196-213, plus _point2center :215-218.
+ *   d_shuffle_keys [N, post_nms_top_n] fp32 or NULL: stands in for tf.random_shuffle (stable argsort of the
+ *   first n keys; NULL = identity).  Outputs: d_rois [N,post,4] (ymin,xmin,ymax,xmax), d_rois_yxhw [N,post,4]
+ *   (cy,cx,h,w; may be NULL), d_roi_scores [N,post] (may be NULL), d_nms_keep_idx [N,post] positions of the NMS
+ *   survivors in the sorted top-k list, -1 padded (may be NULL; for tests).
+ */
+int xdet_rpn_decode(const float* d_rpn_out, int ch_stride, int cls_off, int box_off, const float* d_yref,
+                    const float* d_xref, const float* d_href, const float* d_wref, int N, int fh, int fw, int A,
+                    float* d_scores, float* d_boxes, void* stream);
+size_t xdet_rpn_select_workspace_bytes(int N, int A_tot, int pre_nms_top_n);
+int xdet_rpn_select(const float* d_scores, const float* d_boxes, int N, int A_tot, int pre_nms_top_n,
+                    int post_nms_top_n, float nms_threshold, float min_size, const float* d_shuffle_keys,
+                    float* d_rois, float* d_rois_yxhw, float* d_roi_scores, int* d_nms_keep_idx, void* d_workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* Head post-processing.  Replaces: tf.nn.softmax(cls_score) and AnchorEncoder.ext_decode_rois
+ * (light_head_rfcn_eval.py:406-410, preprocessing/anchor_manipulator.py:671-683; head_prior_scaling = 1).
+ * d_rois [M,4] (ymin,xmin,ymax,xmax); d_head_out [M,ch_stride] fp32 with class scores at cls_off.. and the
+ * 4 box deltas (cy,cx,h,w) at loc_off..  ->  d_probs [M,num_classes], d_boxes [M,4]. */
+int xdet_head_decode(const float* d_rois, const float* d_head_out, int ch_stride, int cls_off, int num_classes,
+                     int loc_off, long long M, float* d_probs, float* d_boxes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

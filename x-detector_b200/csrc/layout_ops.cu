@@ -1,0 +1,240 @@
+// Bandwidth kernels around the tensor-core convolutions (all HBM-bound, no tensor cores):
+//   * patch gather ("im2col") for the few STRIDED convolutions of the ResNet-v2 stem/stage heads
+//     (7x7/s2 initial conv, 3x3/s2 and 1x1/s2 of the first block of block_layer2/3;
+//     net/resnet_v2.py:62-100,320-343): writes [N,Ho,Wo,KH*KW*C] bf16 so that the strided conv
+//     becomes a plain GEMM for conv_gemm.cu.  `fixed_padding` (resnet_v2.py:62-86) is the zero
+//     border the gather produces on the fly.
+//   * 3x3/s2 'SAME' max pooling (resnet_v2.py:326-328) with an optional fused second output
+//     relu(x*scale+bias): the pre-activation BN+ReLU of the first bottleneck (resnet_v2.py:163-164).
+//   * per-channel affine + ReLU (inference batch_norm_relu, resnet_v2.py:41-50) for the places where
+//     one tensor feeds two different batch-norms.
+//   * fp32 -> bf16 row repack with a padded row pitch (PsRoIAlign output -> dense-layer operand).
+#include <cuda_bf16.h>
+
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace xdet {
+namespace {
+
+// src_kind: 0 = NHWC bf16 (pixel pitch in_cs), 1 = NCHW fp32
+template <int SRC>
+__global__ void __launch_bounds__(256) im2col_kernel(const void* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                     int N, int H, int W, int C, int in_cs, int Ho, int Wo, int KH,
+                                                     int KW, int stride, int pad_top, int pad_left, int out_cs,
+                                                     long long total) {
+  const int K = KH * KW * C;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
+    const int k = (int)(e % out_cs);
+    const long long pix = e / out_cs;
+    float v = 0.f;
+    if (k < K) {
+      const int c = k % C, tap = k / C;
+      const int kw = tap % KW, kh = tap / KW;
+      const int xo = (int)(pix % Wo);
+      const int yo = (int)((pix / Wo) % Ho);
+      const int n = (int)(pix / ((long long)Wo * Ho));
+      const int yi = yo * stride + kh - pad_top, xi = xo * stride + kw - pad_left;
+      if (yi >= 0 && yi < H && xi >= 0 && xi < W) {
+        if (SRC == 0)
+          v = __bfloat162float(
+              reinterpret_cast<const __nv_bfloat16*>(src)[(((long long)n * H + yi) * W + xi) * in_cs + c]);
+        else
+          v = __ldg(reinterpret_cast<const float*>(src) + (((long long)n * C + c) * H + yi) * W + xi);
+      }
+    }
+    dst[e] = __float2bfloat16_rn(v);
+  }
+}
+
+// 16-byte vector version for NHWC bf16 with C % 8 == 0 and out_cs == KH*KW*C.
+__global__ void __launch_bounds__(256) im2col_vec8_kernel(const __nv_bfloat16* __restrict__ src,
+                                                          __nv_bfloat16* __restrict__ dst, int N, int H, int W, int C,
+                                                          int in_cs, int Ho, int Wo, int KH, int KW, int stride,
+                                                          int pad_top, int pad_left, long long total_vec) {
+  const int C8 = C / 8, K8 = KH * KW * C8;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total_vec; e += step) {
+    const int k8 = (int)(e % K8);
+    const long long pix = e / K8;
+    const int c8 = k8 % C8, tap = k8 / C8;
+    const int kw = tap % KW, kh = tap / KW;
+    const int xo = (int)(pix % Wo);
+    const int yo = (int)((pix / Wo) % Ho);
+    const int n = (int)(pix / ((long long)Wo * Ho));
+    const int yi = yo * stride + kh - pad_top, xi = xo * stride + kw - pad_left;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (yi >= 0 && yi < H && xi >= 0 && xi < W)
+      v = __ldg(reinterpret_cast<const uint4*>(src + (((long long)n * H + yi) * W + xi) * in_cs) + c8);
+    reinterpret_cast<uint4*>(dst)[e] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ src,
+                                                           __nv_bfloat16* __restrict__ dst,
+                                                           __nv_bfloat16* __restrict__ dst2,
+                                                           const float* __restrict__ scale2,
+                                                           const float* __restrict__ bias2, int N, int H, int W, int C,
+                                                           int Ho, int Wo, int pad_top, int pad_left,
+                                                           long long total_vec) {
+  const int C8 = C / 8;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total_vec; e += step) {
+    const int c8 = (int)(e % C8);
+    const long long pix = e / C8;
+    const int xo = (int)(pix % Wo);
+    const int yo = (int)((pix / Wo) % Ho);
+    const int n = (int)(pix / ((long long)Wo * Ho));
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -FLT_MAX;
+    for (int kh = 0; kh < 3; ++kh) {
+      const int yi = yo * 2 + kh - pad_top;
+      if (yi < 0 || yi >= H) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int xi = xo * 2 + kw - pad_left;
+        if (xi < 0 || xi >= W) continue;
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (((long long)n * H + yi) * W + xi) * C) + c8);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __bfloat1622float2(h[q]);
+          m[2 * q] = fmaxf(m[2 * q], f.x);
+          m[2 * q + 1] = fmaxf(m[2 * q + 1], f.y);
+        }
+      }
+    }
+    uint4 o;
+    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ho[q] = __floats2bfloat162_rn(m[2 * q], m[2 * q + 1]);
+    reinterpret_cast<uint4*>(dst)[e] = o;
+    if (dst2) {
+      uint4 o2;
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&o2);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = c8 * 8 + 2 * q;
+        // the second output normalises the ROUNDED pooled value (what the unfused graph would read back)
+        const float2 r = __bfloat1622float2(ho[q]);
+        h2[q] = __floats2bfloat162_rn(fmaxf(fmaf(r.x, __ldg(scale2 + c), __ldg(bias2 + c)), 0.f),
+                                      fmaxf(fmaf(r.y, __ldg(scale2 + c + 1), __ldg(bias2 + c + 1)), 0.f));
+      }
+      reinterpret_cast<uint4*>(dst2)[e] = o2;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) affine_relu_kernel(const __nv_bfloat16* __restrict__ src,
+                                                          __nv_bfloat16* __restrict__ dst,
+                                                          const float* __restrict__ scale,
+                                                          const float* __restrict__ bias, int C, int relu,
+                                                          long long total_vec) {
+  const int C8 = C / 8;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total_vec; e += step) {
+    const int c8 = (int)(e % C8);
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + e);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    uint4 o;
+    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = c8 * 8 + 2 * q;
+      const float2 f = __bfloat1622float2(h[q]);
+      float a = fmaf(f.x, __ldg(scale + c), __ldg(bias + c));
+      float b = fmaf(f.y, __ldg(scale + c + 1), __ldg(bias + c + 1));
+      if (relu) {
+        a = fmaxf(a, 0.f);
+        b = fmaxf(b, 0.f);
+      }
+      ho[q] = __floats2bfloat162_rn(a, b);
+    }
+    reinterpret_cast<uint4*>(dst)[e] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256) f32_to_bf16_rows_kernel(const float* __restrict__ src,
+                                                               __nv_bfloat16* __restrict__ dst, long long rows,
+                                                               int cols, int dst_pitch) {
+  const long long total = rows * dst_pitch;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
+    const int c = (int)(e % dst_pitch);
+    const long long r = e / dst_pitch;
+    dst[e] = __float2bfloat16_rn(c < cols ? __ldg(src + r * cols + c) : 0.f);
+  }
+}
+
+unsigned grid_for(long long total, int threads = 256) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = (long long)kNumSMs * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace
+}  // namespace xdet
+
+using namespace xdet;
+
+extern "C" int xdet_im2col_bf16(const void* d_src, int src_is_nchw_f32, void* d_dst, int N, int H, int W, int C,
+                                int in_cs, int KH, int KW, int stride, int pad_top, int pad_left, int Ho, int Wo,
+                                int out_cs, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || KH <= 0 || KW <= 0 || stride <= 0 || Ho <= 0 || Wo <= 0)
+    return fail(XDET_EINVAL, "im2col: non-positive dimension");
+  if (out_cs < KH * KW * C) return fail(XDET_EINVAL, "im2col: out_cs (%d) < KH*KW*C (%d)", out_cs, KH * KW * C);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long pixels = (long long)N * Ho * Wo;
+  if (!src_is_nchw_f32 && C % 8 == 0 && in_cs % 8 == 0 && out_cs == KH * KW * C) {
+    const long long tv = pixels * (out_cs / 8);
+    im2col_vec8_kernel<<<grid_for(tv), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(d_src),
+                                                     reinterpret_cast<__nv_bfloat16*>(d_dst), N, H, W, C, in_cs, Ho,
+                                                     Wo, KH, KW, stride, pad_top, pad_left, tv);
+    return after_launch("im2col_vec8_kernel");
+  }
+  const long long total = pixels * out_cs;
+  if (src_is_nchw_f32)
+    im2col_kernel<1><<<grid_for(total), 256, 0, st>>>(d_src, reinterpret_cast<__nv_bfloat16*>(d_dst), N, H, W, C,
+                                                      in_cs, Ho, Wo, KH, KW, stride, pad_top, pad_left, out_cs, total);
+  else
+    im2col_kernel<0><<<grid_for(total), 256, 0, st>>>(d_src, reinterpret_cast<__nv_bfloat16*>(d_dst), N, H, W, C,
+                                                      in_cs, Ho, Wo, KH, KW, stride, pad_top, pad_left, out_cs, total);
+  return after_launch("im2col_kernel");
+}
+
+extern "C" int xdet_maxpool3x3s2_bf16(const void* d_src, void* d_dst, void* d_dst2, const float* d_scale2,
+                                      const float* d_bias2, int N, int H, int W, int C, int Ho, int Wo, int pad_top,
+                                      int pad_left, void* stream) {
+  if (C % 8 != 0) return fail(XDET_EINVAL, "maxpool: C (%d) must be a multiple of 8", C);
+  if (d_dst2 && (!d_scale2 || !d_bias2)) return fail(XDET_EINVAL, "maxpool: second output needs scale2/bias2");
+  const long long tv = (long long)N * Ho * Wo * (C / 8);
+  if (tv <= 0) return XDET_OK;
+  maxpool3x3s2_kernel<<<grid_for(tv), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d_src), reinterpret_cast<__nv_bfloat16*>(d_dst),
+      reinterpret_cast<__nv_bfloat16*>(d_dst2), d_scale2, d_bias2, N, H, W, C, Ho, Wo, pad_top, pad_left, tv);
+  return after_launch("maxpool3x3s2_kernel");
+}
+
+extern "C" int xdet_affine_relu_bf16(const void* d_src, void* d_dst, const float* d_scale, const float* d_bias,
+                                     long long pixels, int C, int relu, void* stream) {
+  if (C % 8 != 0) return fail(XDET_EINVAL, "affine_relu: C (%d) must be a multiple of 8", C);
+  const long long tv = pixels * (C / 8);
+  if (tv <= 0) return XDET_OK;
+  affine_relu_kernel<<<grid_for(tv), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_src),
+                                                                     reinterpret_cast<__nv_bfloat16*>(d_dst), d_scale,
+                                                                     d_bias, C, relu, tv);
+  return after_launch("affine_relu_kernel");
+}
+
+extern "C" int xdet_f32_to_bf16_rows(const float* d_src, void* d_dst, long long rows, int cols, int dst_pitch,
+                                     void* stream) {
+  if (dst_pitch < cols) return fail(XDET_EINVAL, "f32_to_bf16_rows: dst_pitch < cols");
+  if (rows <= 0) return XDET_OK;
+  f32_to_bf16_rows_kernel<<<grid_for(rows * dst_pitch), 256, 0, (cudaStream_t)stream>>>(
+      d_src, reinterpret_cast<__nv_bfloat16*>(d_dst), rows, cols, dst_pitch);
+  return after_launch("f32_to_bf16_rows_kernel");
+}

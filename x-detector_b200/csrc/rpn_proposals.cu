@@ -1,0 +1,453 @@
+// RPN proposal generation on the GPU (the reference pins this whole stage to /cpu:0,
+// net/xception_body.py:425, and it is the largest stall of its step: ~100 ms/img).
+//
+//   xdet_rpn_decode   rpn head outputs -> objectness + decoded boxes
+//                       (light_head_rfcn_eval.py:389-399, preprocessing/anchor_manipulator.py:641-669)
+//   xdet_rpn_select   clip -> filter -> top-k -> NMS -> upsample -> RoIs (+ their (cy,cx,h,w) form)
+//                       (net/xception_body.py:402-444 with _bboxes_clip :173-194, _filter_and_sort_boxes
+//                        :133-158, _bboxes_nms :57-67, _upsample_rois :196-213, _point2center :215-218)
+//
+// The selection stage is integer/compare work on fp32 values with one rounding per operation (this
+// file is built without FMA contraction and uses explicit _rn intrinsics), so that, given the same
+// scores and boxes, the selected set is bit-identical to the CPU restatement (oracle/proposals.py):
+//   * top-k: 64-bit keys (score bits << 32 | ~index) -> descending order, ties to the lower index
+//     (tf.nn.top_k); radix-select of the k-th key, compaction into shared memory, bitonic sort;
+//   * NMS (TF r1.6 NonMaxSuppressionV2): IoU on min/max-normalised corners, 0 if an area <= 0,
+//     suppress iff IoU > threshold; all-pairs suppression bit-matrix spread over the whole GPU, then
+//     one CTA per image resolves 64 candidates at a time (sequential only inside the 64x64 diagonal
+//     block, survivors' rows OR-reduced in parallel);
+//   * upsample: tile + "random" remainder, with tf.random_shuffle replaced by an injected key array
+//     (stable argsort of the first n keys) so that both sides can be driven identically.
+// Neither HBM- nor tensor-bound: latency / dependency bound, reported as us per image.
+#include <cfloat>
+#include <cstdint>
+
+#include "common.cuh"
+
+namespace xdet {
+namespace {
+
+constexpr int kSelThreads = 1024;
+
+// ---- decode ------------------------------------------------------------------------------------
+// rpn_out: [N, h, w, ch_stride] fp32 with the 2A class logits at channel cls_off + a*2 + {0,1} and the
+// 4A box deltas at channel box_off + a*4 + {cy,cx,h,w}.  Anchor order is (y, x, a), a fastest.
+__global__ void __launch_bounds__(256) rpn_decode_kernel(const float* __restrict__ rpn_out, int ch_stride, int cls_off,
+                                                         int box_off, const float* __restrict__ yref,
+                                                         const float* __restrict__ xref,
+                                                         const float* __restrict__ href,
+                                                         const float* __restrict__ wref, int hw, int A,
+                                                         float* __restrict__ scores, float* __restrict__ boxes,
+                                                         long long total) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int a = (int)(e % A);
+  const long long cell = e / A;  // n*hw + (y*w + x)
+  const int pos = (int)(cell % hw);
+  const float* px = rpn_out + cell * ch_stride;
+  const float z0 = __ldg(px + cls_off + a * 2), z1 = __ldg(px + cls_off + a * 2 + 1);
+  // tf.nn.softmax(...)[:, -1]: exp(z - max) / sum
+  const float m = fmaxf(z0, z1);
+  const float e0 = expf(__fsub_rn(z0, m)), e1 = expf(__fsub_rn(z1, m));
+  scores[e] = __fdiv_rn(e1, __fadd_rn(e0, e1));
+  const float t0 = __ldg(px + box_off + a * 4), t1 = __ldg(px + box_off + a * 4 + 1);
+  const float t2 = __ldg(px + box_off + a * 4 + 2), t3 = __ldg(px + box_off + a * 4 + 3);
+  const float ha = __ldg(href + a), wa = __ldg(wref + a);
+  const float ph = __fmul_rn(expf(t2), ha), pw = __fmul_rn(expf(t3), wa);
+  const float cy = __fadd_rn(__fmul_rn(t0, ha), __ldg(yref + pos));
+  const float cx = __fadd_rn(__fmul_rn(t1, wa), __ldg(xref + pos));
+  const float hh = __fmul_rn(ph, 0.5f), hw2 = __fmul_rn(pw, 0.5f);  // x / 2. is exact halving
+  float4 b;
+  b.x = __fsub_rn(cy, hh);
+  b.y = __fsub_rn(cx, hw2);
+  b.z = __fadd_rn(cy, hh);
+  b.w = __fadd_rn(cx, hw2);
+  reinterpret_cast<float4*>(boxes)[e] = b;
+}
+
+// ---- clip + filter -------------------------------------------------------------------------------
+__device__ __forceinline__ float4 clip_box(float4 b) {  // _bboxes_clip against [0,0,1,1]
+  float ymin = fmaxf(b.x, 0.f), xmin = fmaxf(b.y, 0.f);
+  const float ymax = fminf(b.z, 1.f), xmax = fminf(b.w, 1.f);
+  ymin = fminf(ymin, ymax);
+  xmin = fminf(xmin, xmax);
+  return make_float4(ymin, xmin, ymax, xmax);
+}
+
+__device__ __forceinline__ bool keep_box(float4 c, float min_size) {  // _filter_and_sort_boxes mask
+  const float ws = __fsub_rn(c.w, c.y), hs = __fsub_rn(c.z, c.x);
+  const float xc = __fadd_rn(c.y, __fmul_rn(ws, 0.5f)), yc = __fadd_rn(c.x, __fmul_rn(hs, 0.5f));
+  return ws > min_size && hs > min_size && xc > 0.f && yc > 0.f && xc < 1.f && yc < 1.f;
+}
+
+// One CTA per image: keys -> radix-select the K-th largest -> compact -> bitonic sort -> sorted outputs.
+__global__ void __launch_bounds__(kSelThreads) rpn_topk_kernel(const float* __restrict__ scores,
+                                                               const float* __restrict__ boxes, int A_tot, int K,
+                                                               int P /* pow2 >= K */, float min_size,
+                                                               unsigned long long* __restrict__ keys_ws,
+                                                               float* __restrict__ top_scores,
+                                                               float* __restrict__ top_boxes) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* sk = reinterpret_cast<unsigned long long*>(smem_raw);  // [P]
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_remaining, s_count, s_nvalid;
+  const int img = blockIdx.x, tid = threadIdx.x;
+  const float* sc = scores + (long long)img * A_tot;
+  const float4* bx = reinterpret_cast<const float4*>(boxes) + (long long)img * A_tot;
+  unsigned long long* keys = keys_ws + (long long)img * A_tot;
+
+  if (tid == 0) s_nvalid = 0;
+  __syncthreads();
+  int local_valid = 0;
+  for (int i = tid; i < A_tot; i += kSelThreads) {
+    const float4 c = clip_box(bx[i]);
+    const float s = sc[i];
+    unsigned long long key = 0ull;
+    if (keep_box(c, min_size) && s > 0.f) {  // a non-positive score can never outlive _upsample_rois
+      key = ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+      ++local_valid;
+    }
+    keys[i] = key;
+  }
+  atomicAdd(&s_nvalid, local_valid);
+  __syncthreads();
+  const int keff = min(K, s_nvalid);
+
+  // radix select: find the keff-th largest key (keys are unique, 0 = filtered out)
+  unsigned long long thr = ~0ull;  // nothing selected when keff == 0
+  if (keff > 0) {
+    if (tid == 0) {
+      s_prefix = 0ull;
+      s_remaining = keff;
+    }
+    for (int pass = 0; pass < 8; ++pass) {
+      const int shift = 56 - 8 * pass;
+      for (int i = tid; i < 256; i += kSelThreads) hist[i] = 0;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      for (int i = tid; i < A_tot; i += kSelThreads) {
+        const unsigned long long k = keys[i];
+        const bool match = (pass == 0) || ((k >> (shift + 8)) == (prefix >> (shift + 8)));
+        if (match && k != 0ull) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int rem = s_remaining;
+        int b = 255;
+        for (; b > 0; --b) {
+          if ((int)hist[b] >= rem) break;
+          rem -= (int)hist[b];
+        }
+        s_prefix = prefix | ((unsigned long long)b << shift);
+        s_remaining = rem;
+      }
+      __syncthreads();
+    }
+    thr = s_prefix;
+  }
+
+  // compact the selected keys into shared memory, pad with zeros, sort descending
+  if (tid == 0) s_count = 0;
+  for (int i = tid; i < P; i += kSelThreads) sk[i] = 0ull;
+  __syncthreads();
+  if (keff > 0) {
+    for (int i = tid; i < A_tot; i += kSelThreads) {
+      const unsigned long long k = keys[i];
+      if (k != 0ull && k >= thr) sk[atomicAdd(&s_count, 1)] = k;
+    }
+  }
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (P >> 1); t += kSelThreads) {
+        const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);  // first half of each `size` block descending
+        const unsigned long long a = sk[lo], b = sk[hi];
+        if ((a < b) == desc) {
+          sk[lo] = b;
+          sk[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // sorted outputs (zero padded to K, as _pad_axis does)
+  for (int j = tid; j < K; j += kSelThreads) {
+    const unsigned long long k = sk[j];
+    float s = 0.f;
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k != 0ull) {
+      const unsigned idx = 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull);
+      s = __uint_as_float((unsigned)(k >> 32));
+      c = clip_box(bx[idx]);
+    }
+    top_scores[(long long)img * K + j] = s;
+    reinterpret_cast<float4*>(top_boxes)[(long long)img * K + j] = c;
+  }
+}
+
+// ---- NMS -------------------------------------------------------------------------------------------
+struct NBox {
+  float ymin, xmin, ymax, xmax, area;
+};
+__device__ __forceinline__ NBox norm_box(float4 b) {
+  NBox n;
+  n.ymin = fminf(b.x, b.z);
+  n.xmin = fminf(b.y, b.w);
+  n.ymax = fmaxf(b.x, b.z);
+  n.xmax = fmaxf(b.y, b.w);
+  n.area = __fmul_rn(__fsub_rn(n.ymax, n.ymin), __fsub_rn(n.xmax, n.xmin));
+  return n;
+}
+__device__ __forceinline__ bool iou_greater(const NBox& a, const NBox& b, float thr) {
+  if (a.area <= 0.f || b.area <= 0.f) return false;
+  const float iy0 = fmaxf(a.ymin, b.ymin), ix0 = fmaxf(a.xmin, b.xmin);
+  const float iy1 = fminf(a.ymax, b.ymax), ix1 = fminf(a.xmax, b.xmax);
+  const float inter = __fmul_rn(fmaxf(__fsub_rn(iy1, iy0), 0.f), fmaxf(__fsub_rn(ix1, ix0), 0.f));
+  const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(a.area, b.area), inter));
+  return iou > thr;
+}
+
+// grid (col blocks, row blocks, N), 64 threads: word (row i, col block) of the suppression matrix,
+// bit j set iff box (cb*64+j) with j-index > i overlaps box i above the threshold.
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ top_boxes, int K, int words,
+                                                      float thr, unsigned long long* __restrict__ mask) {
+  const int cb = blockIdx.x, rb = blockIdx.y, img = blockIdx.z;
+  if (cb < rb) return;  // only j > i matters
+  __shared__ NBox cols[64];
+  const float4* bx = reinterpret_cast<const float4*>(top_boxes) + (long long)img * K;
+  const int cj = cb * 64 + threadIdx.x;
+  if (cj < K) cols[threadIdx.x] = norm_box(bx[cj]);
+  __syncthreads();
+  const int i = rb * 64 + threadIdx.x;
+  if (i >= K) return;
+  const NBox me = norm_box(bx[i]);
+  unsigned long long w = 0ull;
+  const int ncol = min(64, K - cb * 64);
+  for (int j = 0; j < ncol; ++j) {
+    if (cb * 64 + j > i && iou_greater(cols[j], me, thr)) w |= (1ull << j);
+  }
+  mask[((long long)img * K + i) * words + cb] = w;
+}
+
+// One CTA per image: greedy scan in score order, then _upsample_rois and _point2center.
+__global__ void __launch_bounds__(kSelThreads) nms_scan_kernel(
+    const float* __restrict__ top_scores, const float* __restrict__ top_boxes,
+    const unsigned long long* __restrict__ mask, int K, int words, int keep_n,
+    const float* __restrict__ shuffle_keys /* [N, keep_n] or NULL */, float* __restrict__ rois /* [N,keep_n,4] */,
+    float* __restrict__ rois_yxhw /* [N,keep_n,4] or NULL */, float* __restrict__ roi_scores /* [N,keep_n] or NULL */,
+    int* __restrict__ nms_keep_idx /* [N,keep_n] positions in the sorted list, -1 padded, or NULL */) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* removed = reinterpret_cast<unsigned long long*>(smem_raw);  // [words]
+  int* kept = reinterpret_cast<int*>(removed + words);                            // [keep_n]
+  int* shuf = kept + keep_n;                                                      // [keep_n]
+  __shared__ unsigned long long s_surv;
+  const int img = blockIdx.x, tid = threadIdx.x;
+  const unsigned long long* m = mask + (long long)img * K * words;
+  const float* sc = top_scores + (long long)img * K;
+  const float4* bx = reinterpret_cast<const float4*>(top_boxes) + (long long)img * K;
+
+  for (int i = tid; i < words; i += kSelThreads) removed[i] = 0ull;
+  __syncthreads();
+  const int out_size = min(keep_n, K);
+  int nk = 0;  // every thread tracks the kept count in a register (no shared read/write race)
+  for (int cb = 0; cb < words && nk < out_size; ++cb) {
+    if (tid == 0) {
+      // sequential resolution inside the 64-candidate block (diagonal words of the matrix)
+      unsigned long long rem = removed[cb], surv = 0ull;
+      int k = nk;
+      const int n_in = min(64, K - cb * 64);
+      for (int j = 0; j < n_in && k < out_size; ++j) {
+        if (!((rem >> j) & 1ull)) {
+          surv |= (1ull << j);
+          kept[k++] = cb * 64 + j;
+          rem |= m[((long long)(cb * 64 + j)) * words + cb];
+        }
+      }
+      s_surv = surv;
+    }
+    __syncthreads();
+    // OR the survivors' rows into `removed` for all later blocks, in parallel
+    const unsigned long long surv = s_surv;
+    nk += __popcll(surv);
+    if (surv) {
+      for (int w = cb + 1 + tid; w < words; w += kSelThreads) {
+        unsigned long long acc = removed[w];
+        unsigned long long s = surv;
+        while (s) {
+          const int j = __ffsll((long long)s) - 1;
+          s &= s - 1;
+          acc |= m[((long long)(cb * 64 + j)) * words + w];
+        }
+        removed[w] = acc;
+      }
+    }
+    __syncthreads();
+  }
+  if (nms_keep_idx)
+    for (int j = tid; j < keep_n; j += kSelThreads) nms_keep_idx[(long long)img * keep_n + j] = j < nk ? kept[j] : -1;
+
+  // _upsample_rois: drop paddings (score <= 0).  The kept list is in descending score order, so the
+  // positive-score entries are a prefix and their count is its length.
+  __shared__ int s_n;
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  {
+    int c = 0;
+    for (int j = tid; j < nk; j += kSelThreads) c += (sc[kept[j]] > 0.f) ? 1 : 0;
+    if (c) atomicAdd(&s_n, c);
+  }
+  __syncthreads();
+  const int n = s_n;
+  float* out = rois + (long long)img * keep_n * 4;
+  if (n == 0) {
+    for (int j = tid; j < keep_n; j += kSelThreads) {
+      reinterpret_cast<float4*>(out)[j] = make_float4(0.2f, 0.2f, 0.8f, 0.8f);
+      if (roi_scores) roi_scores[(long long)img * keep_n + j] = 1.f;
+    }
+  } else {
+    const int left = keep_n - n;  // n <= keep_n always
+    const int rem_cnt = left > 0 ? left % n : 0;
+    if (rem_cnt > 0) {
+      // tf.random_shuffle(range(n))[:rem_cnt] := first rem_cnt of the stable argsort of keys[:n]
+      const float* keys = shuffle_keys ? shuffle_keys + (long long)img * keep_n : nullptr;
+      for (int i = tid; i < n; i += kSelThreads) {
+        int rank = i;
+        if (keys) {
+          const float ki = keys[i];
+          rank = 0;
+          for (int j = 0; j < n; ++j) {
+            const float kj = keys[j];
+            rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+          }
+        }
+        if (rank < keep_n) shuf[rank] = i;
+      }
+    }
+    __syncthreads();
+    const int tiled = left > 0 ? n * (left / n + 1) : keep_n;
+    for (int j = tid; j < keep_n; j += kSelThreads) {
+      const int src = (j < tiled) ? (j % n) : shuf[j - tiled];
+      const int pos = kept[src];
+      reinterpret_cast<float4*>(out)[j] = bx[pos];
+      if (roi_scores) roi_scores[(long long)img * keep_n + j] = sc[pos];
+    }
+  }
+  __syncthreads();
+  if (rois_yxhw) {  // _point2center
+    for (int j = tid; j < keep_n; j += kSelThreads) {
+      const float4 b = reinterpret_cast<const float4*>(out)[j];
+      const float h = __fsub_rn(b.z, b.x), w = __fsub_rn(b.w, b.y);
+      reinterpret_cast<float4*>(rois_yxhw + (long long)img * keep_n * 4)[j] =
+          make_float4(__fadd_rn(b.x, __fmul_rn(h, 0.5f)), __fadd_rn(b.y, __fmul_rn(w, 0.5f)), h, w);
+    }
+  }
+}
+
+// ---- head post-processing ------------------------------------------------------------------------
+// softmax over the class scores and ext_decode_rois (preprocessing/anchor_manipulator.py:671-683,
+// light_head_rfcn_eval.py:406-410): one thread per RoI.
+__global__ void __launch_bounds__(256) head_decode_kernel(const float* __restrict__ rois,
+                                                          const float* __restrict__ head_out, int ch_stride,
+                                                          int cls_off, int num_classes, int loc_off,
+                                                          float* __restrict__ probs, float* __restrict__ boxes,
+                                                          long long M) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const float* h = head_out + i * ch_stride;
+  float mx = -FLT_MAX;
+  for (int c = 0; c < num_classes; ++c) mx = fmaxf(mx, __ldg(h + cls_off + c));
+  float sum = 0.f;
+  for (int c = 0; c < num_classes; ++c) sum = __fadd_rn(sum, expf(__fsub_rn(__ldg(h + cls_off + c), mx)));
+  for (int c = 0; c < num_classes; ++c)
+    probs[i * num_classes + c] = __fdiv_rn(expf(__fsub_rn(__ldg(h + cls_off + c), mx)), sum);
+  const float4 r = reinterpret_cast<const float4*>(rois)[i];
+  const float href = __fsub_rn(r.z, r.x), wref = __fsub_rn(r.w, r.y);
+  const float yref = __fadd_rn(r.x, __fmul_rn(href, 0.5f)), xref = __fadd_rn(r.y, __fmul_rn(wref, 0.5f));
+  const float t0 = __ldg(h + loc_off), t1 = __ldg(h + loc_off + 1), t2 = __ldg(h + loc_off + 2),
+              t3 = __ldg(h + loc_off + 3);
+  const float ph = __fmul_rn(expf(t2), href), pw = __fmul_rn(expf(t3), wref);
+  const float cy = __fadd_rn(__fmul_rn(t0, href), yref), cx = __fadd_rn(__fmul_rn(t1, wref), xref);
+  reinterpret_cast<float4*>(boxes)[i] = make_float4(__fsub_rn(cy, __fmul_rn(ph, 0.5f)), __fsub_rn(cx, __fmul_rn(pw, 0.5f)),
+                                                    __fadd_rn(cy, __fmul_rn(ph, 0.5f)), __fadd_rn(cx, __fmul_rn(pw, 0.5f)));
+}
+
+int next_pow2(int n) {
+  int p = 1;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+}  // namespace
+}  // namespace xdet
+
+using namespace xdet;
+
+extern "C" int xdet_rpn_decode(const float* d_rpn_out, int ch_stride, int cls_off, int box_off, const float* d_yref,
+                               const float* d_xref, const float* d_href, const float* d_wref, int N, int fh, int fw,
+                               int A, float* d_scores, float* d_boxes, void* stream) {
+  if (N <= 0 || fh <= 0 || fw <= 0 || A <= 0) return fail(XDET_EINVAL, "rpn_decode: non-positive dimension");
+  const long long total = (long long)N * fh * fw * A;
+  rpn_decode_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      d_rpn_out, ch_stride, cls_off, box_off, d_yref, d_xref, d_href, d_wref, fh * fw, A, d_scores, d_boxes, total);
+  return after_launch("rpn_decode_kernel");
+}
+
+extern "C" size_t xdet_rpn_select_workspace_bytes(int N, int A_tot, int pre_nms_top_n) {
+  const size_t words = (size_t)(pre_nms_top_n + 63) / 64;
+  return (size_t)N * A_tot * 8 + (size_t)N * pre_nms_top_n * (4 + 16) + (size_t)N * pre_nms_top_n * words * 8 + 256;
+}
+
+extern "C" int xdet_rpn_select(const float* d_scores, const float* d_boxes, int N, int A_tot, int pre_nms_top_n,
+                               int post_nms_top_n, float nms_threshold, float min_size, const float* d_shuffle_keys,
+                               float* d_rois, float* d_rois_yxhw, float* d_roi_scores, int* d_nms_keep_idx,
+                               void* d_workspace, size_t workspace_bytes, void* stream) {
+  if (N <= 0 || A_tot <= 0 || pre_nms_top_n <= 0 || post_nms_top_n <= 0)
+    return fail(XDET_EINVAL, "rpn_select: non-positive dimension");
+  const int K = pre_nms_top_n, keep = post_nms_top_n;
+  if (workspace_bytes < xdet_rpn_select_workspace_bytes(N, A_tot, K))
+    return fail(XDET_EINVAL, "rpn_select: workspace too small (%zu < %zu)", workspace_bytes,
+                xdet_rpn_select_workspace_bytes(N, A_tot, K));
+  if ((reinterpret_cast<uintptr_t>(d_workspace) & 15) != 0) return fail(XDET_EINVAL, "rpn_select: workspace alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int words = (K + 63) / 64;
+  unsigned char* ws = reinterpret_cast<unsigned char*>(d_workspace);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws);
+  ws += (size_t)N * A_tot * 8;
+  float* top_boxes = reinterpret_cast<float*>(ws);
+  ws += (size_t)N * K * 16;
+  float* top_scores = reinterpret_cast<float*>(ws);
+  ws += (size_t)N * K * 4;
+  ws += (16 - (reinterpret_cast<uintptr_t>(ws) & 15)) & 15;
+  unsigned long long* mask = reinterpret_cast<unsigned long long*>(ws);
+
+  const int P = next_pow2(K);
+  const size_t smem_topk = (size_t)P * 8;
+  if (smem_topk > 200 * 1024) return fail(XDET_EINVAL, "rpn_select: pre_nms_top_n %d too large for the in-CTA sort", K);
+  XDET_TRY(check_cuda(cudaFuncSetAttribute(rpn_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_topk),
+                      "cudaFuncSetAttribute(rpn_topk)"));
+  rpn_topk_kernel<<<N, kSelThreads, smem_topk, st>>>(d_scores, d_boxes, A_tot, K, P, min_size, keys, top_scores,
+                                                     top_boxes);
+  XDET_TRY(after_launch("rpn_topk_kernel"));
+  // (the lower triangle of the matrix is never written and never read)
+  nms_mask_kernel<<<dim3(words, words, N), 64, 0, st>>>(top_boxes, K, words, nms_threshold, mask);
+  XDET_TRY(after_launch("nms_mask_kernel"));
+  const size_t smem_scan = (size_t)words * 8 + (size_t)keep * 8;
+  XDET_TRY(check_cuda(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan),
+                      "cudaFuncSetAttribute(nms_scan)"));
+  nms_scan_kernel<<<N, kSelThreads, smem_scan, st>>>(top_scores, top_boxes, mask, K, words, keep, d_shuffle_keys,
+                                                     d_rois, d_rois_yxhw, d_roi_scores, d_nms_keep_idx);
+  return after_launch("nms_scan_kernel");
+}
+
+extern "C" int xdet_head_decode(const float* d_rois, const float* d_head_out, int ch_stride, int cls_off,
+                                int num_classes, int loc_off, long long M, float* d_probs, float* d_boxes,
+                                void* stream) {
+  if (M <= 0) return XDET_OK;
+  if (num_classes <= 0) return fail(XDET_EINVAL, "head_decode: num_classes must be positive");
+  head_decode_kernel<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      d_rois, d_head_out, ch_stride, cls_off, num_classes, loc_off, d_probs, d_boxes, M);
+  return after_launch("head_decode_kernel");
+}

@@ -1,0 +1,218 @@
+"""ResNet-v2 (pre-activation) builders -- the API of the reference's ``net/resnet_v2.py``.
+
+Same names and argument order (``batch_norm_relu``, ``fixed_padding``, ``conv2d_fixed_padding``,
+``bottleneck_block``, ``block_layer``, ``imagenet_resnet_v2_generator``, ``imagenet_resnet_v2``), with one extra
+trailing argument: the ``VariableStore`` that plays the role of TF's variable scope.  Tensors are NHWC bf16
+CUDA tensors (the reference's ``data_format='channels_last'``); inference only here (``is_training=False``:
+batch-norm uses its moving statistics, net/resnet_v2.py:41-50).
+
+Compute: every convolution is ``ops.conv2d_nhwc`` (tcgen05 implicit GEMM); batch-norm + ReLU are folded into
+the epilogue of the convolution that PRODUCES the tensor wherever the graph allows it:
+  conv1x1 -> BN -> ReLU and conv3x3 -> BN -> ReLU inside a block are one kernel each;
+  ``conv1x1 + shortcut`` writes the sum AND the next block's pre-activation ``relu(bn(sum))`` (second output).
+Strided convolutions (``conv2d_fixed_padding`` with strides > 1, :89-100) gather their patches first
+(``ops.im2col``, which also materialises ``fixed_padding``, :62-86) and then run as GEMMs.
+
+``lighthead_resnet50_body`` is the Light-Head composition SURVEY 8(a3) defines from these builders plus the
+reference's own dilation pattern (net/xdet_body.py:28-121): block_layer1-3 as-is (stride 16) ->
+batch_norm_relu -> RPN feature [N,h,w,1024]; block_layer4 with stride 1 and dilation 2 -> batch_norm_relu ->
+[N,h,w,2048] for ``large_sep_kernel``.
+"""
+import torch
+
+from .. import ops
+
+_BATCH_NORM_DECAY = 0.997
+_BATCH_NORM_EPSILON = 1e-5
+
+
+def _bn(store, channels):
+    return store.batch_norm(store.auto_name("batch_normalization"), channels)
+
+
+def batch_norm_relu(inputs, is_training, data_format, store=None, bn=None):
+    """Performs a batch normalization followed by a ReLU (net/resnet_v2.py:41-50)."""
+    assert not is_training, "training-mode batch norm is not part of this build (see DESIGN.md)"
+    assert data_format == "channels_last"
+    bn = bn or _bn(store, inputs.shape[-1])
+    scale, bias = store.folded_bn(bn, _BATCH_NORM_EPSILON)
+    return ops.affine_relu(inputs, scale, bias, relu=True)
+
+
+def fixed_padding(inputs, kernel_size, data_format):
+    """Pads the input along the spatial dimensions independently of input size (net/resnet_v2.py:62-86)."""
+    assert data_format == "channels_last"
+    pad_total = kernel_size - 1
+    pad_beg = pad_total // 2
+    pad_end = pad_total - pad_beg
+    return torch.nn.functional.pad(inputs, (0, 0, pad_beg, pad_end, pad_beg, pad_end))
+
+
+def _conv_kernel(store, cin, filters, kernel_size, init=None):
+    name = store.auto_name("conv2d")
+    with store.scope(name):
+        return store.get("kernel", (kernel_size, kernel_size, cin, filters), init or store.variance_scaling)
+
+
+def _packed(store, kern, mode="conv"):
+    """bf16 GEMM weight of a TF conv kernel [KH,KW,Cin,Cout]: 'conv' = tap-major with per-tap channel padding
+    (stride-1 implicit GEMM), 'patch' = one K axis of KH*KW*Cin (for im2col'ed strided convs)."""
+    key = ("w", kern[0], mode)
+    if key not in store.derived:
+        w = kern[1]
+        kh, kw, cin, cout = w.shape
+        if mode == "conv":
+            store.derived[key] = ops.pack_conv_weight(w.permute(3, 2, 0, 1))
+        else:
+            store.derived[key] = ops.pack_conv_weight(w.reshape(kh * kw * cin, cout).t().reshape(cout, kh * kw * cin, 1, 1))
+    return store.derived[key]
+
+
+def _run_conv(store, x, kern, strides, dilation=1, **epilogue):
+    """conv2d_fixed_padding semantics on NHWC bf16: SAME for stride 1, explicit pad + VALID otherwise."""
+    kh, kw, cin, cout = kern[1].shape
+    if strides == 1:
+        return ops.conv2d_nhwc(x, _packed(store, kern), cout, kh, kw, dilation=(dilation, dilation), padding="SAME",
+                               cin=cin, **epilogue)
+    N, H, W, _ = x.shape
+    pad = (kh - 1) // 2
+    Ho = (H + (kh - 1) - kh) // strides + 1
+    Wo = (W + (kw - 1) - kw) // strides + 1
+    patches = ops.im2col(x, kh, kw, strides, pad, pad, Ho, Wo, cin=cin)
+    K = patches.shape[-1]
+    y = ops.conv2d_nhwc(patches.reshape(1, 1, N * Ho * Wo, K), _packed(store, kern, "patch"), cout, 1, 1,
+                        cin=kh * kw * cin, **_flat(epilogue, N * Ho * Wo))
+    return _unflat(y, N, Ho, Wo)
+
+
+def _flat(ep, M):
+    out = dict(ep)
+    for k in ("residual", "out2"):
+        if out.get(k) is not None:
+            out[k] = out[k].reshape(1, 1, M, -1)
+    return out
+
+
+def _unflat(y, N, Ho, Wo):
+    return y.reshape(N, Ho, Wo, y.shape[-1])
+
+
+def conv2d_fixed_padding(inputs, filters, kernel_size, strides, data_format, kernel_initializer=None, store=None,
+                         **epilogue):
+    """Strided 2-D convolution with explicit padding (net/resnet_v2.py:89-100)."""
+    assert data_format == "channels_last"
+    kern = _conv_kernel(store, inputs.shape[-1], filters, kernel_size, kernel_initializer)
+    return _run_conv(store, inputs, kern, strides, **epilogue)
+
+
+def bottleneck_block(inputs, filters, is_training, projection_shortcut, strides, data_format, store=None,
+                     dilation_rate=1, preact=None, next_bn=None):
+    """Bottleneck block variant for residual networks with BN before convolutions (net/resnet_v2.py:142-184;
+    with ``dilation_rate`` > 1 the 3x3 is the dilated SAME conv of xdet_bottleneck_block, net/xdet_body.py:39-81).
+
+    ``preact``: relu(bn(inputs)) if the producer of ``inputs`` already computed it; ``next_bn``: batch-norm of the
+    consumer block, to be fused as a second output.  Returns (sum, fused_next_preact_or_None).
+    """
+    assert not is_training and data_format == "channels_last"
+    shortcut = inputs
+    bn1 = _bn(store, inputs.shape[-1])
+    if preact is None:
+        preact = batch_norm_relu(inputs, is_training, data_format, store, bn=bn1)
+    if projection_shortcut is not None:
+        shortcut = projection_shortcut(preact)
+    k1 = _conv_kernel(store, preact.shape[-1], filters, 1)
+    bn2 = _bn(store, filters)
+    s2, b2 = store.folded_bn(bn2, _BATCH_NORM_EPSILON)
+    t = _run_conv(store, preact, k1, 1, scale=s2, bias=b2, relu=True)
+    k2 = _conv_kernel(store, filters, filters, 3)
+    bn3 = _bn(store, filters)
+    s3, b3 = store.folded_bn(bn3, _BATCH_NORM_EPSILON)
+    t = _run_conv(store, t, k2, strides if dilation_rate == 1 else 1, dilation=dilation_rate, scale=s3, bias=b3,
+                  relu=True)
+    k3 = _conv_kernel(store, filters, 4 * filters, 1)
+    out2 = None
+    ep = {"residual": shortcut}
+    if next_bn is not None:
+        sn, bnb = store.folded_bn(next_bn, _BATCH_NORM_EPSILON)
+        out2 = torch.empty_like(shortcut)
+        ep.update(out2=out2, scale2=sn, bias2=bnb)
+    y = _run_conv(store, t, k3, 1, **ep)
+    return y, out2
+
+
+def block_layer(inputs, filters, block_fn, blocks, strides, is_training, name, data_format, store=None,
+                dilation_rate=1, preact=None):
+    """Creates one layer of blocks for the ResNet model (net/resnet_v2.py:187-223; dilated form
+    net/xdet_body.py:84-121).  Returns the layer output (sum of the last block)."""
+    filters_out = 4 * filters
+
+    def projection_shortcut(x):
+        kern = _conv_kernel(store, x.shape[-1], filters_out, 1)
+        return _run_conv(store, x, kern, strides if dilation_rate == 1 else 1)
+
+    x, pre = inputs, preact
+    for i in range(blocks):
+        # the consumer's first batch-norm is created by the consumer itself; peek its name to fuse it
+        x, pre = block_fn(x, filters, is_training, projection_shortcut if i == 0 else None,
+                          strides if i == 0 else 1, data_format, store=store, dilation_rate=dilation_rate, preact=pre,
+                          next_bn=_peek_next_bn(store, filters_out) if i + 1 < blocks else None)
+    return x
+
+
+def _peek_next_bn(store, channels):
+    """Batch-norm variables the NEXT layer call will create (same automatic name), created now so that they
+    can be fused into the producing convolution."""
+    c = store._counters[-1]
+    i = c.get("batch_normalization", 0)
+    name = "batch_normalization" if i == 0 else "batch_normalization_%d" % i
+    return store.batch_norm(name, channels)  # does not advance the counter
+
+
+def imagenet_resnet_v2_generator(block_fn, layers, num_classes, data_format=None, store=None):
+    """Generator for ImageNet ResNet v2 models (net/resnet_v2.py:290-356), truncated after block_layer4 + the
+    final batch_norm_relu: the classification head (avg-pool + dense) is not on the detector path."""
+    data_format = data_format or "channels_last"
+
+    def model(inputs, is_training):
+        x = stem(inputs, store)
+        x = block_layer(x, 64, block_fn, layers[0], 1, is_training, "block_layer1", data_format, store)
+        x = block_layer(x, 128, block_fn, layers[1], 2, is_training, "block_layer2", data_format, store)
+        x = block_layer(x, 256, block_fn, layers[2], 2, is_training, "block_layer3", data_format, store)
+        x = block_layer(x, 512, block_fn, layers[3], 2, is_training, "block_layer4", data_format, store)
+        return batch_norm_relu(x, is_training, data_format, store)
+
+    return model
+
+
+def imagenet_resnet_v2(resnet_size, num_classes, data_format=None, store=None):
+    """Returns the ResNet model for a given size (net/resnet_v2.py:359-375); bottleneck sizes only."""
+    model_params = {50: [3, 4, 6, 3], 101: [3, 4, 23, 3], 152: [3, 8, 36, 3], 200: [3, 24, 36, 3]}
+    if resnet_size not in model_params:
+        raise ValueError("Not a valid resnet_size:", resnet_size)
+    return imagenet_resnet_v2_generator(bottleneck_block, model_params[resnet_size], num_classes, data_format, store)
+
+
+def stem(image_nchw_f32, store):
+    """7x7/s2 initial conv with fixed padding + 3x3/s2 SAME max-pool (net/resnet_v2.py:320-328) on the
+    fp32 NCHW image the input pipeline delivers; returns NHWC bf16."""
+    N, C, H, W = image_nchw_f32.shape
+    kern = _conv_kernel(store, C, 64, 7)
+    Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    patches = ops.im2col(image_nchw_f32.contiguous(), 7, 7, 2, 3, 3, Ho, Wo, nchw_f32=True)
+    K = patches.shape[-1]
+    y = ops.conv2d_nhwc(patches.reshape(1, 1, N * Ho * Wo, K), _packed(store, kern, "patch"), 64, 1, 1, cin=49 * C)
+    return ops.maxpool3x3s2_same(y.reshape(N, Ho, Wo, 64))
+
+
+def lighthead_resnet50_body(image_nchw_f32, is_training, store, layers=(3, 4, 6, 3)):
+    """Light-Head R-CNN backbone on ResNet-50 v2 (composition).
+    -> (rpn_feature [N,h,w,1024], backbone_feature [N,h,w,2048]) NHWC bf16, both after batch_norm_relu."""
+    df = "channels_last"
+    x = stem(image_nchw_f32, store)
+    x = block_layer(x, 64, bottleneck_block, layers[0], 1, is_training, "block_layer1", df, store)
+    x = block_layer(x, 128, bottleneck_block, layers[1], 2, is_training, "block_layer2", df, store)
+    x = block_layer(x, 256, bottleneck_block, layers[2], 2, is_training, "block_layer3", df, store)
+    rpn_feat = batch_norm_relu(x, is_training, df, store)
+    x = block_layer(x, 512, bottleneck_block, layers[3], 1, is_training, "block_layer4", df, store, dilation_rate=2)
+    backbone = batch_norm_relu(x, is_training, df, store)
+    return rpn_feat, backbone

@@ -1,0 +1,62 @@
+"""Host wrappers of the bandwidth helpers in ``csrc/layout_ops.cu`` (bf16 NHWC tensors)."""
+import torch
+
+from .. import _native
+from .conv import same_pad
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def im2col(x, kh, kw, stride, pad_top, pad_left, Ho, Wo, *, nchw_f32=False, cin=None, out_cs=None):
+    """x: NHWC bf16 [N,H,W,cs] (or NCHW fp32 [N,C,H,W] with nchw_f32=True) -> [N,Ho,Wo,out_cs] bf16 patches,
+    channel order (kh, kw, c).  See xdet_im2col_bf16."""
+    if nchw_f32:
+        N, C, H, W = x.shape
+        cs = C
+        assert x.dtype == torch.float32 and x.is_contiguous()
+    else:
+        N, H, W, cs = x.shape
+        C = cs if cin is None else cin
+        assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    K = kh * kw * C
+    out_cs = (K + 7) // 8 * 8 if out_cs is None else out_cs
+    out = torch.empty((N, Ho, Wo, out_cs), dtype=torch.bfloat16, device=x.device)
+    rc = _native.lib().xdet_im2col_bf16(x.data_ptr(), 1 if nchw_f32 else 0, out.data_ptr(), N, H, W, C, cs, kh, kw,
+                                        stride, pad_top, pad_left, Ho, Wo, out_cs, _st())
+    _native.check(rc)
+    return out
+
+
+def maxpool3x3s2_same(x, scale2=None, bias2=None):
+    """tf.layers.max_pooling2d(3, 2, 'SAME') on NHWC bf16; optionally also returns relu(y*scale2+bias2)."""
+    N, H, W, C = x.shape
+    Ho, Wo = -(-H // 2), -(-W // 2)
+    pt, pl = same_pad(H, 3, 1, 2), same_pad(W, 3, 1, 2)
+    out = torch.empty((N, Ho, Wo, C), dtype=torch.bfloat16, device=x.device)
+    out2 = torch.empty_like(out) if scale2 is not None else None
+    rc = _native.lib().xdet_maxpool3x3s2_bf16(x.data_ptr(), out.data_ptr(), None if out2 is None else out2.data_ptr(),
+                                              None if scale2 is None else scale2.data_ptr(),
+                                              None if bias2 is None else bias2.data_ptr(), N, H, W, C, Ho, Wo, pt, pl,
+                                              _st())
+    _native.check(rc)
+    return (out, out2) if out2 is not None else out
+
+
+def affine_relu(x, scale, bias, relu=True):
+    """Inference batch-norm (+ReLU) on NHWC bf16: y = x*scale[c] + bias[c]."""
+    C = x.shape[-1]
+    out = torch.empty_like(x)
+    rc = _native.lib().xdet_affine_relu_bf16(x.data_ptr(), out.data_ptr(), scale.data_ptr(), bias.data_ptr(),
+                                             x.numel() // C, C, 1 if relu else 0, _st())
+    _native.check(rc)
+    return out
+
+
+def f32_to_bf16_rows(x2d, pitch):
+    rows, cols = x2d.shape
+    out = torch.empty((rows, pitch), dtype=torch.bfloat16, device=x2d.device)
+    rc = _native.lib().xdet_f32_to_bf16_rows(x2d.data_ptr(), out.data_ptr(), rows, cols, pitch, _st())
+    _native.check(rc)
+    return out
