@@ -1,0 +1,148 @@
+"""Light-Head R-CNN inference entry point -- the surface of the reference's ``light_head_rfcn_eval.py``.
+
+* ``FLAGS`` carries the reference's flag names and defaults (light_head_rfcn_eval.py:41-139).
+* ``lighr_head_model_fn(features, labels, mode, params)`` (reference :364-445, spelling kept) runs the graph
+  up to ``head_bboxes_pred`` / ``head_cls_score`` -- backbone -> get_rpn -> large_sep_kernel -> objectness /
+  decode_all_anchors -> get_proposals -> get_head -> ext_decode_rois + softmax -- entirely on the GPU (the
+  reference bounces through /cpu:0 for proposals).  Per-class NMS / VOC mAP (``bboxes_eval``, :263-362) are the
+  "next" rows of SURVEY 8(f) and are not built.
+* ``main`` runs the model on synthetic VOC-shaped tensors (no dataset / checkpoint exists offline).
+
+Batch size: the reference evaluates one image at a time (:212); nothing here depends on that, N images are
+processed per call (BASELINE configs 2/3 use 8 and 32).
+"""
+import argparse
+import types
+
+import torch
+
+from . import ops
+from .net import resnet_v2, xception_body
+from .net.variables import VariableStore
+from .preprocessing import anchor_manipulator
+
+# flag name -> default (light_head_rfcn_eval.py:41-139; data/summary/checkpoint flags kept for completeness)
+_DEFAULTS = dict(
+    num_readers=8, num_preprocessing_threads=24, num_cpu_threads=0, gpu_memory_fraction=1.,
+    data_dir='../PASCAL/VOC_TF/VOC2007TEST_TF/', dataset_name='pascalvoc_2007', num_classes=21,
+    model_dir='./logs_light/', log_every_n_steps=10, save_summary_steps=500, dataset_split_name='test',
+    debug_dir='./Debug_light', train_image_size=480, resnet_size=50, data_format='channels_last',
+    select_threshold=0.01, min_size=4., nms_threshold=0.3, nms_topk_percls=200, nms_topk=200, fg_ratio=0.25,
+    match_threshold=0.53, neg_threshold_high=0.5, neg_threshold_low=0., rpn_anchors_per_image=256,
+    rpn_pre_nms_top_n=5000, rpn_post_nms_top_n=1000, rpn_min_size=16 * 1. / 480, rpn_nms_thres=0.7,
+    rpn_fg_ratio=0.5, rpn_match_threshold=0.7, rpn_neg_threshold=0.3, weight_decay=0.0002,
+    checkpoint_path='./model/xception', model_scope='xception_lighthead', run_on_cloud=True,
+    cloud_checkpoint_path='xception_model/xception_model.ckpt',
+    # not a reference flag: which backbone builder to use (the reference always builds XceptionBody)
+    backbone='resnet50',
+)
+FLAGS = types.SimpleNamespace(**_DEFAULTS)
+pool_method = 'max'  # light_head_rfcn_eval.py:172
+
+
+def make_params(**overrides):
+    p = dict(_DEFAULTS)
+    p.update(overrides)
+    return p
+
+
+def input_pipeline(params, device="cuda"):
+    """Anchor side of the reference's input_pipeline (:174-226): AnchorCreator over the stride-16 map,
+    scales .2...8 + extra .1, ratios 1/2/.5, and the decode closures the model_fn receives through ``labels``."""
+    size = params['train_image_size']
+    fmap = size // 16
+    creator = anchor_manipulator.AnchorCreator([size] * 2, layers_shapes=[(fmap, fmap)],
+                                               anchor_scales=[[0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8]],
+                                               extra_anchor_scales=[[0.1]], anchor_ratios=[[1., 2., .5]],
+                                               layer_steps=[16])
+    all_anchors, num_anchors_list = creator.get_all_anchors()
+    enc = anchor_manipulator.AnchorEncoder(all_anchors, num_classes=params['num_classes'], allowed_borders=[0.],
+                                           positive_threshold=params['rpn_match_threshold'],
+                                           ignore_threshold=params['rpn_neg_threshold'],
+                                           prior_scaling=[1., 1., 1., 1.], rpn_fg_thres=params['match_threshold'],
+                                           rpn_bg_high_thres=params['neg_threshold_high'],
+                                           rpn_bg_low_thres=params['neg_threshold_low'], device=device)
+    return {'rpn_decode_fn': lambda pred: enc.decode_all_anchors([pred], squeeze_inner=True)[0],
+            'head_decode_fn': lambda rois, pred: enc.ext_decode_rois(rois, pred, head_prior_scaling=[1., 1., 1., 1.]),
+            'num_anchors_list': num_anchors_list, 'anchor_encoder': enc}
+
+
+def lighr_head_model_fn(features, labels, mode, params, store=None, shuffle_keys=None):
+    """features: images [N,3,H,W] fp32 CUDA (whitened, as light_head_preprocess_for_eval delivers them).
+    Returns the ``predictions`` of the reference's model_fn plus the intermediate tensors tests compare."""
+    assert mode in ("eval", "predict", "infer"), 'This script only support predict mode!'
+    num_anchors = labels['num_anchors_list'][0]
+    enc = labels['anchor_encoder']
+    df = 'channels_last'
+    with store.scope(params['model_scope']):
+        if params.get('backbone', 'resnet50') == 'resnet50':
+            rpn_feat_map, backbone_feat = resnet_v2.lighthead_resnet50_body(features, False, store)
+        else:
+            raise NotImplementedError("XceptionBody is not built yet (DESIGN.md: next rows)")
+        rpn_out = xception_body.get_rpn(rpn_feat_map, num_anchors, False, df, 'rpn_head', store)
+        large_sep_feature = xception_body.large_sep_kernel(backbone_feat, 256, 10 * 7 * 7, False, df,
+                                                           'large_sep_feature', store)
+        # softmax[:, -1] + decode_all_anchors in one kernel (reference :389-399)
+        rpn_object_score, rpn_bboxes_pred = ops.rpn_decode(rpn_out, 0, 2 * num_anchors, enc.device_anchors(0),
+                                                           num_anchors)
+        proposals_bboxes, yxhw, _ = ops.rpn_select(rpn_object_score, rpn_bboxes_pred, params['rpn_pre_nms_top_n'],
+                                                   params['rpn_post_nms_top_n'], params['rpn_nms_thres'],
+                                                   params['rpn_min_size'], shuffle_keys)
+        cls_score, bboxes_reg = xception_body.get_head(
+            large_sep_feature, lambda input_, bboxes_, gw_, gh_: ops.ps_roi_align(input_, bboxes_, gw_, gh_, pool_method),
+            7, 7, None, proposals_bboxes, params['num_classes'], False, False, 0, df, 'final_head', store,
+            yxhw_bboxes=yxhw)
+        N, R = proposals_bboxes.shape[:2]
+        head = torch.cat([cls_score, bboxes_reg], dim=-1).reshape(N * R, -1).contiguous()
+        head_cls_score, head_bboxes_pred = ops.head_decode(proposals_bboxes.reshape(-1, 4), head, 0,
+                                                           params['num_classes'], params['num_classes'])
+    return {
+        'classes': head_cls_score.argmax(dim=-1), 'probabilities': head_cls_score.max(dim=-1).values,
+        'bboxes_predict': head_bboxes_pred, 'head_cls_score': head_cls_score,
+        # intermediates (not in the reference's predictions dict; used by the parity tests)
+        'rpn_feat_map': rpn_feat_map, 'backbone_feat': backbone_feat, 'rpn_out': rpn_out,
+        'large_sep_feature': large_sep_feature, 'rpn_object_score': rpn_object_score,
+        'rpn_bboxes_pred': rpn_bboxes_pred, 'proposals_bboxes': proposals_bboxes, 'cls_score': cls_score,
+        'bboxes_reg': bboxes_reg,
+    }
+
+
+class LightHeadRFCN(object):
+    """Convenience wrapper: variables + anchors + one call per batch (what ``tf.estimator.Estimator.predict``
+    drives in the reference, :447-503)."""
+
+    def __init__(self, params=None, seed=0, device="cuda", state_dict=None):
+        self.params = params or make_params()
+        self.store = VariableStore(device=device, seed=seed, state_dict=state_dict)
+        self.labels = input_pipeline(self.params, device=device)
+
+    def __call__(self, images, shuffle_keys=None):
+        # a fresh naming pass per call: variables are looked up by the same automatic names every time
+        self.store._counters = [{}]
+        return lighr_head_model_fn(images, self.labels, "eval", self.params, store=self.store,
+                                   shuffle_keys=shuffle_keys)
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description="Light-Head R-CNN inference on synthetic VOC-shaped tensors")
+    for k, v in _DEFAULTS.items():
+        if isinstance(v, bool):
+            ap.add_argument("--" + k, type=lambda s: s.lower() in ("1", "true", "yes"), default=v)
+        else:
+            ap.add_argument("--" + k, type=type(v), default=v)
+    ap.add_argument("--batch_size", type=int, default=8)
+    args = ap.parse_args(argv)
+    params = make_params(**{k: getattr(args, k) for k in _DEFAULTS})
+    model = LightHeadRFCN(params)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    size = params['train_image_size']
+    images = torch.rand((args.batch_size, 3, size, size), generator=g, device="cuda") * 2 - 1
+    out = model(images)
+    torch.cuda.synchronize()
+    print("classes", out['classes'][:10].tolist())
+    print("probabilities", [round(float(p), 4) for p in out['probabilities'][:10]])
+    print("bboxes_predict", out['bboxes_predict'][:3].tolist())
+
+
+if __name__ == '__main__':
+    main()

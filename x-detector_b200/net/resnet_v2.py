@@ -159,11 +159,12 @@ def block_layer(inputs, filters, block_fn, blocks, strides, is_training, name, d
     return x
 
 
-def _peek_next_bn(store, channels):
-    """Batch-norm variables the NEXT layer call will create (same automatic name), created now so that they
-    can be fused into the producing convolution."""
+def _peek_next_bn(store, channels, ahead=3):
+    """Batch-norm variables the NEXT block will create first, created now (same automatic name) so that they can
+    be fused into the convolution that produces its input.  A bottleneck block creates exactly three
+    batch-norms, so seen from before a block the next block's first one is ``ahead`` = 3 names further."""
     c = store._counters[-1]
-    i = c.get("batch_normalization", 0)
+    i = c.get("batch_normalization", 0) + ahead
     name = "batch_normalization" if i == 0 else "batch_normalization_%d" % i
     return store.batch_norm(name, channels)  # does not advance the counter
 

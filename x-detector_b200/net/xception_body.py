@@ -1,0 +1,130 @@
+"""Light-Head R-CNN head builders -- the API of the reference's ``net/xception_body.py``
+(``get_rpn`` :381-400, ``get_proposals`` :402-448, ``large_sep_kernel`` :450-475, ``get_head`` :477-560),
+same names and argument order plus a trailing ``VariableStore``.  NHWC bf16 tensors in, inference only.
+
+Fusions relative to the reference graph (all exact re-associations of the same linear algebra):
+  * get_rpn: the two 1x1 heads (2A class logits, 4A box deltas) are ONE GEMM with 6A output channels;
+  * large_sep_kernel: the two branches read the same input, so the two 15x1 convs are one conv to 2*mid
+    channels and ``branch_0b + branch_1b`` is one 1x15 conv over the concatenated 2*mid channels (K = 15*2*mid);
+    the trailing batch_norm_relu is folded into its epilogue, which writes fp32 NCHW -- the layout and dtype
+    PsRoIAlign's contract requires;
+  * get_head: fc_cls and fc_loc are one GEMM with num_classes + 4 outputs.
+``XceptionBody`` (the Xception-65 backbone, :236-379) is not built yet.
+"""
+import torch
+
+from .. import ops
+from . import resnet_v2
+
+USE_FUSED_BN = True
+BN_EPSILON = 0.0001
+BN_MOMENTUM = 0.99
+
+
+def _conv_vars(store, cin, filters, kh, kw, init=None, use_bias=True):
+    name = store.auto_name("conv2d")
+    with store.scope(name):
+        k = store.get("kernel", (kh, kw, cin, filters), init or store.glorot_normal)
+        b = store.get("bias", (filters,), store.zeros) if use_bias else None
+    return k, b
+
+
+def _dense_vars(store, name, cin, units):
+    with store.scope(name):
+        k = store.get("kernel", (cin, units), store.glorot_normal)
+        b = store.get("bias", (units,), store.zeros)
+    return k, b
+
+
+def _derived(store, key, fn):
+    if key not in store.derived:
+        store.derived[key] = fn()
+    return store.derived[key]
+
+
+def get_rpn(net_input, num_anchors, is_training, data_format, var_scope, store=None):
+    """3x3 SAME conv -> 512 + bias + ReLU, then two 1x1 convs -> 2A / 4A (+bias) (reference :381-400).
+    Returns ONE fp32 NHWC tensor [N,h,w,6A]: class logits in channels [0,2A), box deltas in [2A,6A)
+    (``rpn_cls_score, rpn_bbox_pred`` are its two channel slices)."""
+    assert data_format == "channels_last"
+    cin = net_input.shape[-1]
+    with store.scope(var_scope):
+        k0, b0 = _conv_vars(store, cin, 512, 3, 3)
+        k1, b1 = _conv_vars(store, 512, 2 * num_anchors, 1, 1)
+        k2, b2 = _conv_vars(store, 512, 4 * num_anchors, 1, 1)
+    w0 = _derived(store, ("w", k0[0]), lambda: ops.pack_conv_weight(k0[1].permute(3, 2, 0, 1)))
+    rpn_relu = ops.conv2d_nhwc(net_input, w0, 512, 3, 3, bias=b0[1], relu=True)
+    w12 = _derived(store, ("w", k1[0], k2[0]),
+                   lambda: ops.pack_conv_weight(torch.cat([k1[1], k2[1]], dim=3).permute(3, 2, 0, 1)))
+    b12 = _derived(store, ("b", b1[0], b2[0]), lambda: torch.cat([b1[1], b2[1]]).contiguous())
+    return ops.conv2d_nhwc(rpn_relu, w12, 6 * num_anchors, 1, 1, bias=b12, out_layout="nhwc_f32")
+
+
+def get_proposals(object_score, bboxes_pred, encode_fn, rpn_pre_nms_top_n, rpn_post_nms_top_n, nms_threshold,
+                  rpn_min_size, is_training, data_format, shuffle_keys=None):
+    """clip -> filter/top-k -> NMS -> upsample (reference :402-448), on the GPU instead of /cpu:0.
+    object_score [N,A], bboxes_pred [N,A,4].  Inference: returns the proposal boxes [N,post,4]."""
+    if is_training:
+        raise NotImplementedError("proposal target assignment (ext_encode_rois) is not part of this build")
+    rois, _, _ = ops.rpn_select(object_score, bboxes_pred, rpn_pre_nms_top_n, rpn_post_nms_top_n, nms_threshold,
+                                rpn_min_size, shuffle_keys)
+    return rois
+
+
+def large_sep_kernel(net_input, depth_mid, depth_output, is_training, data_format, var_scope, store=None):
+    """Two branches of (15x1 conv -> depth_mid, 1x15 conv -> depth_output), summed, batch_norm_relu
+    (reference :450-475).  Returns the thin feature map as fp32 NCHW [N,depth_output,h,w]."""
+    assert data_format == "channels_last" and not is_training
+    cin = net_input.shape[-1]
+    with store.scope(var_scope):
+        with store.scope("Branch_0"):
+            a0k, a0b = _conv_vars(store, cin, depth_mid, 15, 1)
+            b0k, b0b = _conv_vars(store, depth_mid, depth_output, 1, 15)
+        with store.scope("Branch_1"):
+            a1k, a1b = _conv_vars(store, cin, depth_mid, 15, 1)
+            b1k, b1b = _conv_vars(store, depth_mid, depth_output, 1, 15)
+        bn = store.batch_norm(store.auto_name("batch_normalization"), depth_output)
+    wa = _derived(store, ("w", a0k[0], a1k[0]),
+                  lambda: ops.pack_conv_weight(torch.cat([a0k[1], a1k[1]], dim=3).permute(3, 2, 0, 1)))
+    ba = _derived(store, ("b", a0b[0], a1b[0]), lambda: torch.cat([a0b[1], a1b[1]]).contiguous())
+    mid = ops.conv2d_nhwc(net_input, wa, 2 * depth_mid, 15, 1, bias=ba)
+    wb = _derived(store, ("w", b0k[0], b1k[0]),
+                  lambda: ops.pack_conv_weight(torch.cat([b0k[1], b1k[1]], dim=2).permute(3, 2, 0, 1)))
+    scale, shift = store.folded_bn(bn, resnet_v2._BATCH_NORM_EPSILON)
+    bb = _derived(store, ("b", b0b[0], b1b[0], "bn"), lambda: ((b0b[1] + b1b[1]) * scale + shift).contiguous())
+    return ops.conv2d_nhwc(mid, wb, depth_output, 1, 15, scale=scale, bias=bb, relu=True, out_layout="nchw_f32")
+
+
+def _point2center(proposals_bboxes):
+    ymin, xmin, ymax, xmax = (proposals_bboxes[:, :, 0], proposals_bboxes[:, :, 1], proposals_bboxes[:, :, 2],
+                              proposals_bboxes[:, :, 3])
+    height, width = (ymax - ymin), (xmax - xmin)
+    return torch.stack([ymin + height / 2., xmin + width / 2., height, width], dim=-1)
+
+
+def get_head(net_input, pooling_op, grid_width, grid_height, loss_func, proposals_bboxes, num_classes, is_training,
+             using_ohem, ohem_roi_one_image, data_format, var_scope, store=None, yxhw_bboxes=None):
+    """PS-RoI pooling + fc 2048 (ReLU) + fc_cls / fc_loc (reference :477-560), inference branch.
+    net_input: thin feature map, fp32 NCHW (PsRoiAlign's contract).  Returns (cls_score [N,R,num_classes],
+    bboxes_reg [N,R,4]) fp32."""
+    if is_training or using_ohem:
+        raise NotImplementedError("training / OHEM branch of get_head is not part of this build")
+    if yxhw_bboxes is None:
+        yxhw_bboxes = _point2center(proposals_bboxes)  # fp32 elementwise, same op order as the reference
+    psroipooled_rois, _ = pooling_op(net_input, yxhw_bboxes.contiguous(), grid_width, grid_height)
+    N, R = psroipooled_rois.shape[:2]
+    feat = psroipooled_rois.reshape(N * R, -1)  # tf.reshape(pooled_feat, [-1, 10*gw*gh]) (:499)
+    cin = feat.shape[1]
+    with store.scope(var_scope):
+        k1, b1 = _dense_vars(store, "subnet_fc", cin, 2048)
+        kc, bc = _dense_vars(store, "fc_cls", 2048, num_classes)
+        kl, bl = _dense_vars(store, "fc_loc", 2048, 4)
+    pitch = (cin + 7) // 8 * 8  # TMA rows must be 16-byte multiples
+    a = ops.f32_to_bf16_rows(feat, pitch)
+    w1 = _derived(store, ("w", k1[0]), lambda: ops.pack_conv_weight(k1[1].t().reshape(2048, cin, 1, 1)))
+    h = ops.conv2d_nhwc(a.reshape(1, 1, N * R, pitch), w1, 2048, 1, 1, bias=b1[1], relu=True, cin=cin)
+    w2 = _derived(store, ("w", kc[0], kl[0]),
+                  lambda: ops.pack_conv_weight(torch.cat([kc[1], kl[1]], dim=1).t().reshape(num_classes + 4, 2048, 1, 1)))
+    b2 = _derived(store, ("b", bc[0], bl[0]), lambda: torch.cat([bc[1], bl[1]]).contiguous())
+    out = ops.conv2d_nhwc(h, w2, num_classes + 4, 1, 1, bias=b2, out_layout="nhwc_f32").reshape(N, R, num_classes + 4)
+    return out[..., :num_classes], out[..., num_classes:]
