@@ -2,10 +2,13 @@
 """bench.py -- measurement contract of the driver.
 
     python bench.py --gpus N --steps K --warmup W            (own arm, CUDA)
-    python bench.py --impl reference --gpus N --steps K ...  (reference CPU arm)
+    python bench.py --impl reference --gpus N --steps K ...  (reference-semantics CPU arm)
 
 One "step" = one pass of the hot path over one batch of synthetic input.  Prints ONE JSON line.
-The workload is selected with --workload (default: see WORKLOADS / DEFAULT_WORKLOAD).
+
+Default workload (BASELINE.json configs[1]): Light-Head R-CNN, ResNet-50 backbone, inference, batch 8 per
+GPU, 480x480 synthetic images; metric = images/s.  `--workload psroi_sweep_top` measures the PsRoIAlign
+operator alone (BASELINE configs[4] top point) as GB/s against the HBM roofline.
 """
 import argparse
 import json
@@ -57,7 +60,7 @@ class ClockSampler(threading.Thread):
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.02)
+                time.sleep(0.01)
         except Exception as e:  # NVML missing: report, do not fail the bench
             self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
 
@@ -69,9 +72,230 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-# ----------------------------------------------------------------------------------------------
-# Workload: PsRoIAlign forward, top of the BASELINE config-5 sweep.
-# ----------------------------------------------------------------------------------------------
+def dist_env():
+    return int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+# ==============================================================================================
+# Workload 1 (default): Light-Head R-CNN ResNet-50 inference, batch 8/GPU, 480x480
+# ==============================================================================================
+class LightHeadResnet50:
+    name = "Light-Head R-CNN ResNet-50 inference, batch=8 per GPU, 480x480 synthetic"
+    metric, unit, dtype = "images_per_sec_480x480", "images/s", "bf16"
+    batch, size = 8, 480
+
+    def images(self, rank):
+        rng = np.random.default_rng(1 + 1000 * rank)  # U(-1,1): img*2 - mean/127.5 (common_preprocessing.py:391-392)
+        return (rng.random((self.batch, 3, self.size, self.size), dtype=np.float32) * 2 - 1).astype(np.float32)
+
+    def run_own(self, args):
+        import torch
+        import torch.distributed as dist
+
+        import xdet_b200  # noqa: F401
+        from xdet_b200 import _native
+        from xdet_b200 import light_head_rfcn_eval as lh
+        from xdet_b200.ops import conv as conv_ops
+
+        world, rank, local = dist_env()
+        assert torch.cuda.is_available(), "bench.py (own arm) needs a GPU; there is no CPU fallback"
+        torch.cuda.set_device(local)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        _native.lib()
+        peaks = load_peaks()
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        params = lh.make_params(train_image_size=self.size)
+        model = lh.LightHeadRFCN(params, seed=0)
+        imgs_h = torch.from_numpy(self.images(rank)).pin_memory()
+        imgs_d = imgs_h.cuda()
+        R = params["rpn_post_nms_top_n"]
+        probs_h = torch.empty((self.batch * R, params["num_classes"]), dtype=torch.float32).pin_memory()
+        boxes_h = torch.empty((self.batch * R, 4), dtype=torch.float32).pin_memory()
+
+        # ---- build: one eager pass creates the variables / packed weights, then the whole forward is
+        # captured into a CUDA graph (launch-bound otherwise: ~90 kernels per step) ------------------
+        static_in = torch.empty_like(imgs_d)
+        static_in.copy_(imgs_d)
+        out = model(static_in)
+        torch.cuda.synchronize()
+        graph = None
+        if not args.no_graph:
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        out = model(static_in)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out = model(static_in)
+                torch.cuda.synchronize()
+            except Exception as e:  # report and fall back to eager launches
+                sys.stderr.write("CUDA graph capture failed (%s: %s); timing eager launches\n" % (type(e).__name__, e))
+                graph = None
+                out = model(static_in)
+                torch.cuda.synchronize()
+
+        launches_per_step = None
+
+        def step():
+            if graph is not None:
+                graph.replay()
+                return out
+            return model(static_in)
+
+        l0 = _native.launch_count()
+        model(static_in)
+        torch.cuda.synchronize()
+        launches_per_step = _native.launch_count() - l0
+
+        # ---- device-resident throughput (value) ---------------------------------------------------
+        for _ in range(max(3, args.warmup)):
+            step()
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+        step_ms = e0.elapsed_time(e1) / args.steps
+
+        # ---- end to end with HOST buffers: H2D of the images, D2H of the detections ----------------
+        def e2e_step():
+            static_in.copy_(imgs_h, non_blocking=True)
+            o = step()
+            probs_h.copy_(o["head_cls_score"], non_blocking=True)
+            boxes_h.copy_(o["bboxes_predict"], non_blocking=True)
+            torch.cuda.synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+        clocks = sampler.finish()
+
+        # ---- dominant kernel (conv_gemm_kernel): live per-launch CUDA-event timing, eager pass ------
+        conv_ops.PROFILE = []
+        for _ in range(3):
+            conv_ops.PROFILE.clear()
+            model(static_in)
+            torch.cuda.synchronize()
+        prof = conv_ops.PROFILE
+        conv_ops.PROFILE = None
+        conv_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
+        conv_flops = sum(f for _, _, f, _ in prof)
+        n_conv = len(prof)
+
+        t = torch.tensor([step_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms, e2e_ms = float(t[0]), float(t[1])
+        value = world * self.batch / (step_ms * 1e-3)
+        e2e_value = world * self.batch / (e2e_ms * 1e-3)
+        achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
+                    "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM), %d launches per step" % n_conv,
+                    "algorithmic_flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms,
+                    "kernel_share_of_step": conv_ms / step_ms if graph is None else None,
+                    "note": "per-launch CUDA-event times from an eager pass (events between launches); "
+                            "flops = 2*MACs of every conv/dense layer (bias/BN/ReLU excluded)"}
+
+        cpu = None
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_network_baseline(self, params, model.store.state_dict(), reps=1)
+
+        if rank == 0:
+            print(json.dumps({
+                "metric": self.metric, "value": value, "unit": self.unit, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": self.dtype, "data": "synthetic",
+                "config": {"workload": self.name, "global_batch": world * self.batch,
+                           "l2": "working set per step (activations ~0.6 GB) exceeds the 126 MB L2",
+                           "sharding": "images partitioned across ranks, no collective (inference)",
+                           "cuda_graph": graph is not None,
+                           "proposals": "pre_nms_top_n=5000 post_nms_top_n=1000 nms=0.7 (eval flags)"},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": self.unit, "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": int(imgs_h.numel() * 4),
+                        "d2h_bytes_per_step": int(probs_h.numel() * 4 + boxes_h.numel() * 4)},
+                "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
+                "roofline": roofline, "cpu_baseline": cpu,
+            }))
+        if world > 1:
+            dist.destroy_process_group()
+
+    def run_reference(self, args):
+        world, rank, _ = dist_env()
+        if rank != 0:
+            return
+        import torch
+
+        # eval flags of the reference (light_head_rfcn_eval.py:95-115); variables are created on demand by the
+        # oracle with the reference's shapes (random: no checkpoint exists offline)
+        params = {"model_scope": "xception_lighthead", "num_classes": 21, "rpn_pre_nms_top_n": 5000,
+                  "rpn_post_nms_top_n": 1000, "rpn_nms_thres": 0.7, "rpn_min_size": 16.0 / self.size}
+        sd = {}
+        base = cpu_network_baseline(self, params, sd, reps=max(1, args.steps), warmup=1 if args.warmup else 0)
+        print(json.dumps({
+            "impl": "reference", "metric": self.metric, "value": base["value"], "unit": self.unit, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / base["value"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": self.name, "sample": base["sample"]},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": self.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        del torch
+
+
+def cpu_network_baseline(wl, params, sd, reps=1, warmup=0):
+    """The reference-semantics CPU path (oracle/net.py, PyTorch CPU fp32 -- TF1 itself is not installable) on a
+    bounded sample: ONE 480x480 image per step, all host threads."""
+    import torch
+
+    from oracle import net as onet
+    from oracle import proposals as op
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    fmap = wl.size // 16
+    anchors = op.layer_anchors((wl.size, wl.size), (fmap, fmap), [0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8], [0.1],
+                               [1., 2., .5], 16)
+    img = wl.images(0)[:1]
+    sd = dict(sd)
+    onet.model(img[:, :, :64, :64], sd, dict(params, rpn_pre_nms_top_n=50, rpn_post_nms_top_n=10),
+               op.layer_anchors((64, 64), (4, 4), [0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8], [0.1], [1., 2., .5], 16),
+               create_seed=0)  # creates any missing variable (tiny input), untimed
+    for _ in range(warmup):
+        onet.model(img, sd, params, anchors)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        onet.model(img, sd, params, anchors)
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": 1.0 / dt, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": "1 image of the batch per step (whole graph incl. proposals/NMS and PsRoIAlign C oracle), "
+                      "PyTorch-CPU fp32 restatement, %d threads, %d rep(s)" % (cores, reps)}
+
+
+# ==============================================================================================
+# Workload 2: PsRoIAlign forward, top of the BASELINE config-5 sweep
+# ==============================================================================================
 class PsroiSweepTop:
     """PsRoIAlign forward, R=16384 RoIs x 7x7 bins over a 980-channel 30x30 thin feature map
     (BASELINE.json configs[4] top point; 1024 channels is rejected by the op)."""
@@ -82,175 +306,140 @@ class PsroiSweepTop:
 
     def algorithmic_bytes(self, R=None):
         R = self.R if R is None else R
-        # features out + index out + rois in + map read once
         return 4 * self.N * R * self.C * 2 + 16 * self.N * R + 4 * self.N * self.C * self.H * self.W
 
     def host_inputs(self, rank):
         from tests import workloads
-        x = workloads.make_map(self.N, self.C, self.H, self.W, seed=4 + 100 * rank)
-        rois = workloads.make_rois(self.N, self.R, seed=5 + 100 * rank)
-        return x, rois
+        return (workloads.make_map(self.N, self.C, self.H, self.W, seed=4 + 100 * rank),
+                workloads.make_rois(self.N, self.R, seed=5 + 100 * rank))
 
-
-WORKLOADS = {"psroi_sweep_top": PsroiSweepTop}
-DEFAULT_WORKLOAD = "psroi_sweep_top"
-
-
-def run_reference(args, wl):
-    """Reference arm: the reference's own CPU implementation (oracle/_ref when it was compiled in
-    the build container, else the C port) on all host cores, on a bounded sample per step."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    from oracle import psroi
-    kind = "reference" if psroi.have_ref() else "port"
-    impl = "ref" if kind == "reference" else "oracle"
-    cores = os.cpu_count() or 1
-    x, rois = wl.host_inputs(0)
-    Rs = wl.cpu_sample_rois
-    rois_s = np.ascontiguousarray(rois[:, :Rs])
-    for _ in range(max(1, args.warmup)):
-        psroi.psroi_align_fwd(x, rois_s, wl.gw, wl.gh, "max", threads=cores, impl=impl)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        psroi.psroi_align_fwd(x, rois_s, wl.gw, wl.gh, "max", threads=cores, impl=impl)
-    dt = (time.perf_counter() - t0) / args.steps
-    val = wl.algorithmic_bytes(Rs) / dt / 1e9
-    sample = "first %d of %d RoIs per step, all %d host threads" % (Rs, wl.R, cores)
-    print(json.dumps({
-        "impl": "reference", "metric": wl.metric, "value": val, "unit": wl.unit, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-        "config": {"workload": wl.name, "sample": sample},
-        "cpu_baseline": {"value": val, "unit": wl.unit, "cores": cores, "kind": kind, "sample": sample},
-        "e2e": {"value": val, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
-
-
-def run_own(args, wl):
-    import torch
-    import torch.distributed as dist
-
-    import xdet_b200  # noqa: F401
-    from xdet_b200 import _native, ops
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py (own arm) needs a GPU; there is no CPU fallback"
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    _native.lib()
-    peaks = load_peaks()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    x_h, rois_h = wl.host_inputs(rank)
-    x_pin = torch.from_numpy(x_h).pin_memory()
-    rois_pin = torch.from_numpy(rois_h).pin_memory()
-    x = x_pin.cuda()
-    rois = rois_pin.cuda()
-    G = wl.gw * wl.gh
-    out_pin = torch.empty((wl.N, wl.R, G, wl.C // G), dtype=torch.float32).pin_memory()
-    idx_pin = torch.empty((wl.N, wl.R, G, wl.C // G), dtype=torch.int32).pin_memory()
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-
-    def step():
-        return ops.ps_roi_align(x, rois, wl.gw, wl.gh, "max")
-
-    # ---- device-resident throughput (value) + per-launch kernel time (roofline) -------------
-    for _ in range(max(3, args.warmup)):
-        flush.zero_()
-        step()
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    launches0 = _native.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    t_wall0 = time.perf_counter()
-    for a, b in ev:
-        flush.zero_()  # evict the previous step's output / the map from L2 (not timed)
-        a.record()
-        step()
-        b.record()
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    launches = _native.launch_count() - launches0
-    kernel_ms = [a.elapsed_time(b) for a, b in ev]
-    step_ms = sum(kernel_ms) / len(kernel_ms)
-
-    # ---- end-to-end through the operator with HOST buffers (e2e) -----------------------------
-    def e2e_step():
-        xd = x_pin.cuda(non_blocking=True)
-        rd = rois_pin.cuda(non_blocking=True)
-        p, i = ops.ps_roi_align(xd, rd, wl.gw, wl.gh, "max")
-        out_pin.copy_(p, non_blocking=True)
-        idx_pin.copy_(i, non_blocking=True)
-        torch.cuda.synchronize()
-
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
-    clocks = sampler.finish()
-
-    # max over ranks
-    t = torch.tensor([step_ms, e2e_ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    step_ms, e2e_ms = float(t[0]), float(t[1])
-
-    bytes_step = wl.algorithmic_bytes()
-    value = world * bytes_step / (step_ms * 1e-3) / 1e9
-    e2e_value = world * bytes_step / (e2e_ms * 1e-3) / 1e9
-    achieved = bytes_step / (step_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
-                "kernel": "psroi_fwd_planes_kernel<max>", "algorithmic_bytes_per_launch": bytes_step,
-                "kernel_ms": step_ms}
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    def cpu(self, x_h, rois_h, reps):
         from oracle import psroi
         kind = "reference" if psroi.have_ref() else "port"
+        impl = "ref" if kind == "reference" else "oracle"
         cores = os.cpu_count() or 1
-        Rs = wl.cpu_sample_rois
-        rs = np.ascontiguousarray(rois_h[:, :Rs])
-        psroi.psroi_align_fwd(x_h, rs, wl.gw, wl.gh, "max", threads=cores, impl="ref" if kind == "reference" else "oracle")
+        rs = np.ascontiguousarray(rois_h[:, :self.cpu_sample_rois])
+        psroi.psroi_align_fwd(x_h, rs, self.gw, self.gh, "max", threads=cores, impl=impl)
         t0 = time.perf_counter()
-        reps = 3
         for _ in range(reps):
-            psroi.psroi_align_fwd(x_h, rs, wl.gw, wl.gh, "max", threads=cores,
-                                  impl="ref" if kind == "reference" else "oracle")
+            psroi.psroi_align_fwd(x_h, rs, self.gw, self.gh, "max", threads=cores, impl=impl)
         dt = (time.perf_counter() - t0) / reps
-        cpu = {"value": wl.algorithmic_bytes(Rs) / dt / 1e9, "unit": wl.unit, "cores": cores, "kind": kind,
-               "sample": "first %d of %d RoIs, best-effort all host threads, %d reps" % (Rs, wl.R, reps)}
+        return {"value": self.algorithmic_bytes(self.cpu_sample_rois) / dt / 1e9, "unit": self.unit, "cores": cores,
+                "kind": kind, "sample": "first %d of %d RoIs per step, %d host threads, %d reps" %
+                (self.cpu_sample_rois, self.R, cores, reps)}, dt
 
-    if rank == 0:
+    def run_reference(self, args):
+        if dist_env()[1] != 0:
+            return
+        x, rois = self.host_inputs(0)
+        base, dt = self.cpu(x, rois, max(1, args.steps))
         print(json.dumps({
-            "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-            "config": {"workload": wl.name, "l2": "flushed between timed iterations (256 MB memset)",
-                       "sharding": "independent RoI batches per rank, no collective"},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": wl.unit, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(x_h.nbytes + rois_h.nbytes),
-                    "d2h_bytes_per_step": int(out_pin.numel() * 4 + idx_pin.numel() * 4)},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "wall_s_timed_region": t_wall,
+            "impl": "reference", "metric": self.metric, "value": base["value"], "unit": self.unit, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": self.dtype, "data": "synthetic",
+            "config": {"workload": self.name, "sample": base["sample"]}, "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": self.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
-    if world > 1:
-        dist.destroy_process_group()
+
+    def run_own(self, args):
+        import torch
+        import torch.distributed as dist
+
+        import xdet_b200  # noqa: F401
+        from xdet_b200 import _native, ops
+
+        world, rank, local = dist_env()
+        assert torch.cuda.is_available(), "bench.py (own arm) needs a GPU; there is no CPU fallback"
+        torch.cuda.set_device(local)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        _native.lib()
+        peaks = load_peaks()
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        x_h, rois_h = self.host_inputs(rank)
+        x_pin, rois_pin = torch.from_numpy(x_h).pin_memory(), torch.from_numpy(rois_h).pin_memory()
+        x, rois = x_pin.cuda(), rois_pin.cuda()
+        G = self.gw * self.gh
+        out_pin = torch.empty((self.N, self.R, G, self.C // G), dtype=torch.float32).pin_memory()
+        idx_pin = torch.empty((self.N, self.R, G, self.C // G), dtype=torch.int32).pin_memory()
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+        def step():
+            return ops.ps_roi_align(x, rois, self.gw, self.gh, "max")
+
+        for _ in range(max(3, args.warmup)):
+            flush.zero_()
+            step()
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        launches0 = _native.launch_count()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        for a, b in ev:
+            flush.zero_()  # evict the previous step's output / the map from L2 (not timed)
+            a.record()
+            step()
+            b.record()
+        barrier()
+        launches = _native.launch_count() - launches0
+        step_ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+
+        def e2e_step():
+            xd = x_pin.cuda(non_blocking=True)
+            rd = rois_pin.cuda(non_blocking=True)
+            p, i = ops.ps_roi_align(xd, rd, self.gw, self.gh, "max")
+            out_pin.copy_(p, non_blocking=True)
+            idx_pin.copy_(i, non_blocking=True)
+            torch.cuda.synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+        clocks = sampler.finish()
+        t = torch.tensor([step_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms, e2e_ms = float(t[0]), float(t[1])
+        nbytes = self.algorithmic_bytes()
+        achieved = nbytes / (step_ms * 1e-3) / 1e9
+        cpu = None
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            cpu, _ = self.cpu(x_h, rois_h, 3)
+        if rank == 0:
+            print(json.dumps({
+                "metric": self.metric, "value": world * achieved, "unit": self.unit, "n_gpus": world,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": step_ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": self.dtype, "data": "synthetic",
+                "config": {"workload": self.name, "l2": "flushed between timed iterations (256 MB memset)",
+                           "sharding": "independent RoI batches per rank, no collective"},
+                "clocks": clocks,
+                "e2e": {"value": world * nbytes / (e2e_ms * 1e-3) / 1e9, "unit": self.unit, "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": int(x_h.nbytes + rois_h.nbytes),
+                        "d2h_bytes_per_step": int(out_pin.numel() * 4 + idx_pin.numel() * 4)},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                             "kernel": "psroi_prep_kernel + psroi_fwd_planes_kernel<max,4>",
+                             "algorithmic_bytes_per_launch": nbytes, "kernel_ms": step_ms},
+                "cpu_baseline": cpu,
+            }))
+        if world > 1:
+            dist.destroy_process_group()
+
+
+WORKLOADS = {"lighthead_resnet50": LightHeadResnet50, "psroi_sweep_top": PsroiSweepTop}
+DEFAULT_WORKLOAD = "lighthead_resnet50"
 
 
 def main():
@@ -261,12 +450,15 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph replay")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]()
     if args.impl == "reference":
-        run_reference(args, wl)
+        if args.workload == "lighthead_resnet50" and args.steps > 3:
+            args.steps = 3  # each CPU step is a whole image through the fp32 graph: keep the arm to a few minutes
+        wl.run_reference(args)
     else:
-        run_own(args, wl)
+        wl.run_own(args)
 
 
 if __name__ == "__main__":

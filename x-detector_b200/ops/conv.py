@@ -48,6 +48,11 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+# When set to a list, every launch appends (start_event, end_event, algorithmic_flops, shape tuple):
+# bench.py uses it to time the conv/GEMM kernel live and to count algorithmic FLOPs (2*MACs).
+PROFILE = None
+
+
 def conv2d_nhwc(x, w_packed, cout, kh, kw, *, dilation=(1, 1), padding="SAME", scale=None, bias=None, relu=False,
                 residual=None, out=None, out_layout="nhwc_bf16", out2=None, scale2=None, bias2=None, cin=None,
                 block_n=0):
@@ -84,7 +89,13 @@ def conv2d_nhwc(x, w_packed, cout, kh, kw, *, dilation=(1, 1), padding="SAME", s
                  1 if relu else 0, _ptr(residual), out.data_ptr(), 0 if out.dtype == torch.bfloat16 else 1,
                  sn, sy, sx, sc, _ptr(out2), _ptr(scale2), _ptr(bias2), block_n)
     with torch.cuda.device(dev):
+        if PROFILE is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         rc = _native.lib().xdet_conv2d_bf16(x.data_ptr(), ctypes.byref(d), torch.cuda.current_stream().cuda_stream)
+        if PROFILE is not None:
+            e1.record()
+            PROFILE.append((e0, e1, 2.0 * N * Ho * Wo * cout * cin * kh * kw, (N, H, W, cin, cout, kh, kw)))
     _native.check(rc)
     return out
 
