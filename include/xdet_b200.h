@@ -84,9 +84,9 @@ int xdet_psroi_align_bwd_host(const float* h_rois, const float* h_pooled_grad, c
 
 
 /* ---------------------------------------------------------------------------------------
- * Stride-1 convolution / GEMM on the tcgen05 tensor cores (bf16 operands, fp32 accumulate).
+ * Convolution (stride 1 or 2, dilated) / GEMM on the tcgen05 tensor cores (bf16 operands, fp32 accumulate).
  * Replaces: the cuDNN / cuBLAS kernels TensorFlow runs for tf.layers.conv2d / tf.layers.dense on
- *   the path -- conv2d_fixed_padding net/resnet_v2.py:89-100 (stride-1 cases), dilate_conv2d
+ *   the path -- conv2d_fixed_padding net/resnet_v2.py:89-100 and the 7x7/s2 stem :320-325, dilate_conv2d
  *   net/xdet_body.py:28-37, get_rpn net/xception_body.py:381-400, large_sep_kernel :450-475,
  *   the pointwise half of tf.layers.separable_conv2d :224-233, get_head's dense layers :540-558.
  * Input  : NHWC bf16, pixel (n,y,x) at d_in + ((n*H + y)*W + x)*in_cs, in_cs % 8 == 0.
@@ -94,14 +94,22 @@ int xdet_psroi_align_bwd_host(const float* h_rois, const float* h_pooled_grad, c
  * Output : out(n,y,x,c) at out + n*out_sn + y*out_sy + x*out_sx + c*out_sc (elements), bf16 or fp32:
  *            v    = acc*scale[c] + bias[c]  (+ residual(n,y,x,c), bf16, laid out like `out`)  (ReLU if relu)
  *            out  = v ;  out2 = ReLU(v*scale2[c] + bias2[c])  (optional, bf16, laid out like `out`)
- *          with acc(n,y,x,c) = sum_{kh,kw,ci} in(n, y + kh*dil_h - pad_top, x + kw*dil_w - pad_left, ci) * w
- *          (reads outside the image are zero: TF 'SAME' padding = pad_top/left = floor(total/2)).
+ *          with acc(n,y,x,c) = sum_{kh,kw,ci} in(n, y*stride_h + kh*dil_h - pad_top, x*stride_w + kw*dil_w - pad_left, ci) * w
+ *          (reads outside the image are zero: TF 'SAME' padding = pad_top/left = floor(total/2); explicit
+ *          fixed_padding = pad_top/left = (k-1)/2).
+ * residual / out2 require a bf16 `out` with unit channel stride and pixel strides that are multiples of 8.
  * A plain GEMM D[M,Nc] = A[M,K] * W[Nc,K]^T is the case N=1, H=1, W=M, Cin=K, KH=KW=1.
+ * fold_w != 0 (few-channel inputs such as the 3-channel image of the stem): the KW taps of a filter row and the
+ *   in_cs (= 8) padded channels form ONE K chunk of KW*in_cs <= 64 contiguous elements.  The caller pads the rows
+ *   horizontally: pixel (n,y,x) lives at d_in + ((n*H + y)*in_wp + x + pad_left)*in_cs with zeros in the padding
+ *   and in_wp >= (Wout-1)*stride_w + 64/in_cs.  Weights are then [Cout][KH][64] with element kw*in_cs + ci.
  */
 typedef struct {
   int N, H, W, Cin, in_cs;
   int Cout, KH, KW, dil_h, dil_w, pad_top, pad_left;
   int Hout, Wout;
+  int stride_h, stride_w; /* 1 or 2 (0 = 1) */
+  int fold_w, in_wp;      /* see above; in_wp is only read when fold_w != 0 */
   const void* weights;
   const float* scale; /* per-Cout multiplier (folded batch-norm), NULL = 1 */
   const float* bias;  /* per-Cout addend (conv bias / folded batch-norm), NULL = 0 */
@@ -128,6 +136,10 @@ int xdet_conv2d_bf16(const void* d_in, const xdet_conv_desc* desc, void* stream)
  *                       output ReLU(pooled*scale2 + bias2) = the first block's pre-activation (resnet_v2.py:163-164).
  * xdet_affine_relu_bf16 inference batch_norm (+ReLU): y = x*scale[c] + bias[c] (net/resnet_v2.py:41-50).
  * xdet_f32_to_bf16_rows [rows, cols] fp32 -> [rows, dst_pitch] bf16, zero tail (PsRoIAlign output -> dense operand).
+ * xdet_image_to_nhwc8_bf16  the input image [N,C<=8,H,W] fp32 NCHW (what light_head_preprocess_for_eval delivers,
+ *                       transposed by the model_fn) -> [N,H,Wp,8] bf16 with `pad_left` zero pixels in front of every
+ *                       row, zero channels C..7 and zero pixels up to Wp: the layout xdet_conv2d_bf16's fold_w mode reads
+ *                       (the 7x7/s2 stem, net/resnet_v2.py:320-325; block1_conv1 of XceptionBody, xception_body.py:243).
  */
 int xdet_im2col_bf16(const void* d_src, int src_is_nchw_f32, void* d_dst, int N, int H, int W, int C, int in_cs,
                      int KH, int KW, int stride, int pad_top, int pad_left, int Ho, int Wo, int out_cs, void* stream);
@@ -136,6 +148,8 @@ int xdet_maxpool3x3s2_bf16(const void* d_src, void* d_dst, void* d_dst2, const f
 int xdet_affine_relu_bf16(const void* d_src, void* d_dst, const float* d_scale, const float* d_bias, long long pixels,
                           int C, int relu, void* stream);
 int xdet_f32_to_bf16_rows(const float* d_src, void* d_dst, long long rows, int cols, int dst_pitch, void* stream);
+int xdet_image_to_nhwc8_bf16(const float* d_src, void* d_dst, int N, int C, int H, int W, int Wp, int pad_left,
+                             void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * RPN proposals.

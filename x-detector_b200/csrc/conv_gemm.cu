@@ -3,29 +3,38 @@
 //   D[m, n] = sum_{tap, c} A[m shifted by tap, c] * Wt[n, tap, c]      (bf16 x bf16 -> fp32 in TMEM)
 //
 // Replaces the cuDNN / cuBLAS calls TensorFlow makes for every tf.layers.conv2d / dense on the
-// Light-Head R-CNN path (net/resnet_v2.py:89-100, net/xception_body.py:243-376,381-400,450-475,
-// 540-558).  One kernel covers 1x1 / 3x3 / 15x1 / 1x15 (dilated) stride-1 convolutions and plain
-// GEMMs (dense layers, 1x1 convs flattened to [N*H*W, C]):
+// Light-Head R-CNN path (net/resnet_v2.py:89-100,320-325, net/xception_body.py:243-376,381-400,450-475,
+// 540-558).  One PERSISTENT kernel covers 1x1 / 3x3 / 7x7 / 15x1 / 1x15 convolutions (dilated, stride 1
+// or 2) and plain GEMMs (dense layers; 1x1 convs are flattened to [N*H*W, C]):
 //
 //   * activations are NHWC bf16; a tile of 128 output pixels is a BH x BW patch of one image.  For
 //     each filter tap the A operand is ONE TMA 4-D box load {64 ch, BW, BH, 1} at the tap's shifted
 //     coordinates -- out-of-bounds rows/columns/channels are zero-filled by TMA, which implements
-//     SAME padding and channel tails without any im2col buffer;
+//     SAME padding and channel tails without any im2col buffer; stride-2 convolutions use the tensor
+//     map's element strides (every 2nd pixel of a 2*BW x 2*BH box);
+//   * "fold_w" mode (the 3-channel 7x7/s2 stem): the KW taps of one filter row and the <= 8 padded input
+//     channels are one contiguous run of KW*in_cs <= 64 elements, so a K chunk is a whole filter row and
+//     the tensor map's pixel stride is stride_w*in_cs elements (overlapping windows);
 //   * weights are [Cout][tap][Cin padded to 64] bf16 (K-major), loaded as 2-D boxes {64, BN};
 //   * both operands land in shared memory in the 128-byte-swizzled K-major layout tcgen05 consumes
 //     directly through shared-memory matrix descriptors;
-//   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread, tcgen05.mma cta_group::1,
-//     M=128, N=BN, K=16) and TMEM owner, warps 2-5 = epilogue (tcgen05.ld 32x32b, each warp its own
-//     32-lane TMEM quadrant); full/empty mbarrier ring of `stages` smem slots, tcgen05.commit frees
-//     a slot / publishes the accumulator;
-//   * epilogue: y = acc*scale[c] + bias[c] (+ residual) (ReLU), written as bf16 or fp32 with arbitrary
-//     element strides (NHWC bf16 for the next layer, NCHW fp32 for PsRoIAlign / the RPN decode), and
-//     optionally a second output relu(y*scale2[c]+bias2[c]) (the next pre-activation BN+ReLU of a
-//     ResNet-v2 block, net/resnet_v2.py:163-164) so that no separate normalisation pass exists.
+//   * each CTA (one per SM) walks tiles blockIdx.x, +gridDim.x, ...: warp 0 = TMA producer, warp 1 = MMA
+//     issuer (one elected thread, tcgen05.mma cta_group::1, M=128, N=BN<=256, K=16) and TMEM owner,
+//     warps 2-5 = epilogue (tcgen05.ld 32x32b, each warp its own 32-lane TMEM quadrant).  Three
+//     pipelines: a full/empty mbarrier ring of shared-memory stages (TMA <-> MMA), TWO accumulator
+//     buffers in TMEM with full/empty barriers (MMA <-> epilogue: the epilogue of tile i overlaps the
+//     main loop of tile i+1), and the epilogue's own double-buffered staging tiles;
+//   * epilogue: y = acc*scale[c] + bias[c] (+ residual) (ReLU), and optionally a second output
+//     relu(y*scale2[c]+bias2[c]) (the next pre-activation BN+ReLU of a ResNet-v2 block,
+//     net/resnet_v2.py:163-164) so that no separate normalisation pass exists.  bf16 NHWC outputs go
+//     registers -> swizzled shared memory -> TMA tile store (coalesced, edges clipped by TMA) and the
+//     residual tile arrives by TMA load, prefetched two 64-channel chunks ahead; fp32 / strided outputs
+//     (NCHW fp32 for PsRoIAlign, fp32 NHWC for the RPN decode) are written directly from registers.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "common.cuh"
@@ -38,57 +47,80 @@ constexpr int kBM = 128;          // rows (output pixels) per tile
 constexpr int kBK = 64;           // K per stage: 64 bf16 = one 128-byte swizzle atom
 constexpr int kUmmaK = 16;        // K per tcgen05.mma for 16-bit inputs
 constexpr int kGemmThreads = 192; // 6 warps: TMA, MMA, 4x epilogue
+constexpr int kEpiThreads = 128;
 constexpr int kMaxStages = 8;
+constexpr int kMaxBN = 256;
+constexpr uint32_t kChunkBytes = kBM * 64 * 2;  // one 128 x 64-channel bf16 staging tile
 
 struct ConvGemmArgs {
-  int tiles_x, tiles_y, n_img;  // spatial tiling of the output (tiles_x * tiles_y * n_img M-tiles)
-  int BW, BH;                   // tile shape, BW*BH == 128
+  int tiles_x, tiles_y, n_tiles_n, total_tiles;
+  int BW, BH;
   int Hout, Wout, Cout;
-  int taps_w, dil_h, dil_w, pad_top, pad_left;
+  int taps_w, dil_h, dil_w, pad_top, pad_left, mul_x, mul_y;
   int k_chunks_per_tap, num_k_blocks;
-  int BN, stages, tmem_cols;
+  int BN, bn_pad, stages, tmem_cols;
   const float* scale;
   const float* bias;
   int relu;
-  const __nv_bfloat16* residual;
+  int tma_epilogue, has_res, has_out2;
   void* out;
   int out_fp32;
   long long out_sn, out_sy, out_sx, out_sc;
-  __nv_bfloat16* out2;
   const float* scale2;
   const float* bias2;
 };
 
+struct TileCoord {
+  int x0, y0, img, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvGemmArgs& p, int t) {
+  TileCoord c;
+  const int nt = t % p.n_tiles_n;
+  int mt = t / p.n_tiles_n;
+  c.n0 = nt * p.BN;
+  c.x0 = (mt % p.tiles_x) * p.BW;
+  mt /= p.tiles_x;
+  c.y0 = (mt % p.tiles_y) * p.BH;
+  c.img = mt / p.tiles_y;
+  return c;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const ConvGemmArgs p) {
+                 const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
+                 const __grid_constant__ CUtensorMap map_out2, const ConvGemmArgs p) {
   extern __shared__ unsigned char smem_raw[];
-  // 128-byte-swizzled operand tiles need 1024-byte aligned bases: align manually (the launch adds slack)
+  // 128-byte-swizzled tiles need 1024-byte aligned bases: align manually (the launch adds slack)
   unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  // carve: [stages][A 16 KB][B BN*128 B] | barriers | tmem ptr
+  // carve: [stages][A 16 KB][B BN*128 B] | epilogue staging (out x2, out2 x2, residual x2) | scale/bias | barriers
   const uint32_t a_bytes = kBM * kBK * 2;
   const uint32_t b_bytes = (uint32_t)p.BN * kBK * 2;
   const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
   unsigned char* tiles = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  unsigned char* cbuf = smem + (size_t)p.stages * stage_bytes;
+  unsigned char* c2buf = cbuf + (p.tma_epilogue ? 2 * kChunkBytes : 0);
+  unsigned char* rbuf = c2buf + (p.has_out2 ? 2 * kChunkBytes : 0);
+  float* sbuf = reinterpret_cast<float*>(rbuf + (p.has_res ? 2 * kChunkBytes : 0));  // [4][kMaxBN]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sbuf + 4 * kMaxBN);
   uint64_t* empty_bar = full_bar + kMaxStages;
-  uint64_t* tmem_full_bar = empty_bar + kMaxStages;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + kMaxStages;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint64_t* res_full_bar = tmem_empty_bar + 2;       // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // tile coordinates
-  int t = blockIdx.x;
-  const int tx = t % p.tiles_x;
-  t /= p.tiles_x;
-  const int ty = t % p.tiles_y;
-  const int img = t / p.tiles_y;
-  const int x0 = tx * p.BW, y0 = ty * p.BH;
-  const int n0 = blockIdx.y * p.BN;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&map_a);
     ptx::prefetch_tmap(&map_b);
+    if (p.tma_epilogue) ptx::prefetch_tmap(&map_out);
+    if (p.has_res) ptx::prefetch_tmap(&map_res);
+    if (p.has_out2) ptx::prefetch_tmap(&map_out2);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -96,7 +128,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         ptx::mbar_init(&full_bar[s], 1);
         ptx::mbar_init(&empty_bar[s], 1);
       }
-      ptx::mbar_init(tmem_full_bar, 1);
+      for (int s = 0; s < 2; ++s) {
+        ptx::mbar_init(&tmem_full_bar[s], 1);
+        ptx::mbar_init(&tmem_empty_bar[s], 4);  // one arrival per epilogue warp
+        ptx::mbar_init(&res_full_bar[s], 1);
+      }
       ptx::fence_mbar_init();
     }
     __syncwarp();
@@ -110,146 +146,235 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (ptx::elect_one()) {
+    if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-        const int tap = kb / p.k_chunks_per_tap, cc = kb - tap * p.k_chunks_per_tap;
-        const int kh = tap / p.taps_w, kw = tap - kh * p.taps_w;
-        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-        unsigned char* sa = tiles + (size_t)stage * stage_bytes;
-        unsigned char* sb = sa + a_bytes;
-        ptx::mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-        ptx::tma_load_4d(sa, &map_a, &full_bar[stage], cc * kBK, x0 + kw * p.dil_w - p.pad_left,
-                         y0 + kh * p.dil_h - p.pad_top, img);
-        ptx::tma_load_2d(sb, &map_b, &full_bar[stage], kb * kBK, n0);
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        const int ax = tc.x0 * p.mul_x - p.pad_left, ay = tc.y0 * p.mul_y - p.pad_top;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          const int tap = kb / p.k_chunks_per_tap, cc = kb - tap * p.k_chunks_per_tap;
+          const int kh = tap / p.taps_w, kw = tap - kh * p.taps_w;
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* sa = tiles + (size_t)stage * stage_bytes;
+          unsigned char* sb = sa + a_bytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+          ptx::tma_load_4d(sa, &map_a, &full_bar[stage], cc * kBK, ax + kw * p.dil_w, ay + kh * p.dil_h, tc.img);
+          ptx::tma_load_2d(sb, &map_b, &full_bar[stage], kb * kBK, tc.n0);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const uint32_t idesc = ptx::make_idesc_bf16(kBM, p.BN);
     int stage = 0;
     uint32_t phase = 0;
-    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-      ptx::mbar_wait(&full_bar[stage], phase);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);  // epilogue has drained this accumulator buffer
       ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-        const uint32_t sa = ptx::smem_u32(tiles + (size_t)stage * stage_bytes);
-        const uint32_t sb = sa + a_bytes;
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.bn_pad);
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = ptx::smem_u32(tiles + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + a_bytes;
 #pragma unroll
-        for (int k = 0; k < kBK / kUmmaK; ++k) {
-          const uint64_t da = ptx::make_smem_desc_sw128(sa + k * kUmmaK * 2);
-          const uint64_t db = ptx::make_smem_desc_sw128(sb + k * kUmmaK * 2);
-          ptx::mma_bf16_ss(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint64_t da = ptx::make_smem_desc_sw128(sa + k * kUmmaK * 2);
+            const uint64_t db = ptx::make_smem_desc_sw128(sb + k * kUmmaK * 2);
+            ptx::mma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::mma_commit(&empty_bar[stage]);                                 // slot reusable once these MMAs retire
+          if (kb == p.num_k_blocks - 1) ptx::mma_commit(&tmem_full_bar[as]);  // accumulator complete
         }
-        ptx::mma_commit(&empty_bar[stage]);                           // slot reusable once these MMAs retire
-        if (kb == p.num_k_blocks - 1) ptx::mma_commit(tmem_full_bar);  // accumulator complete
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
-      __syncwarp();
-      if (++stage == p.stages) {
-        stage = 0;
-        phase ^= 1;
-      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM quadrant = warp % 4 =====
     const int quad = warp & 3;
     const int m = quad * 32 + lane;  // row of the tile == TMEM lane
-    const int py = y0 + m / p.BW, px = x0 + m % p.BW;
-    const bool row_ok = (py < p.Hout) && (px < p.Wout);
-    const long long pix_off = (long long)img * p.out_sn + (long long)py * p.out_sy + (long long)px * p.out_sx;
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tc_fence_after();
-    const int ncols = min(p.BN, p.Cout - n0);
-    for (int c0 = 0; c0 < ncols; c0 += 32) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
-      ptx::tmem_ld_wait();
-      if (!row_ok) continue;
-      const int cbase = n0 + c0;
-      const int nv = min(32, ncols - c0);
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int c = cbase + j;
-        float a = __uint_as_float(r[j]);
-        if (j < nv) {
-          const float sc = p.scale ? __ldg(p.scale + c) : 1.f;
-          const float bi = p.bias ? __ldg(p.bias + c) : 0.f;
-          a = fmaf(a, sc, bi);
+    const int e = threadIdx.x - 64;  // 0..127
+    const bool leader = (e == 0);    // issues the epilogue's TMA loads / stores
+    const int nchunks = (p.BN + 63) / 64;
+    const uint32_t swz = (uint32_t)(m & 7);
+    int as = 0;
+    uint32_t aphase = 0;
+    int g = 0;  // running 64-channel chunk counter of this CTA (staging buffer = g & 1)
+
+    // coordinates of the residual chunk with running index gq (may belong to a later tile of this CTA)
+    auto issue_residual = [&](int gq) {
+      const int ti = gq / nchunks, c = gq - ti * nchunks;
+      const long long t = (long long)blockIdx.x + (long long)ti * gridDim.x;
+      if (t >= p.total_tiles) return;
+      const TileCoord tc = decode_tile(p, (int)t);
+      if (tc.n0 + c * 64 >= p.Cout) return;  // chunk fully outside: the consumer skips it as well
+      const int b = gq & 1;
+      ptx::mbar_arrive_expect_tx(&res_full_bar[b], kChunkBytes);
+      ptx::tma_load_4d(rbuf + (size_t)b * kChunkBytes, &map_res, &res_full_bar[b], tc.n0 + c * 64, tc.x0, tc.y0,
+                       tc.img);
+    };
+    if (p.has_res && leader) {
+      issue_residual(0);
+      issue_residual(1);
+    }
+    uint32_t res_phase = 0;  // bit b = parity of the next fill of residual buffer b
+
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t);
+      // per-tile scale / bias vectors -> shared memory (previous tile's readers passed their last barrier)
+      for (int i = e; i < p.BN; i += kEpiThreads) {
+        const int c = tc.n0 + i;
+        const bool ok = c < p.Cout;
+        sbuf[i] = (ok && p.scale) ? __ldg(p.scale + c) : 1.f;
+        sbuf[kMaxBN + i] = (ok && p.bias) ? __ldg(p.bias + c) : 0.f;
+        if (p.has_out2) {
+          sbuf[2 * kMaxBN + i] = ok ? __ldg(p.scale2 + c) : 1.f;
+          sbuf[3 * kMaxBN + i] = ok ? __ldg(p.bias2 + c) : 0.f;
         }
-        v[j] = a;
       }
-      const bool vec_ok = (p.out_sc == 1) && !p.out_fp32 && (nv == 32) && ((p.out_sx & 7) == 0) &&
-                          ((p.out_sy & 7) == 0) && ((p.out_sn & 7) == 0) && ((cbase & 7) == 0);
-      if (p.residual) {
-        const __nv_bfloat16* rp = p.residual + pix_off + cbase;
-        if (vec_ok) {
+      ptx::named_bar_sync(1, kEpiThreads);
+      ptx::mbar_wait(&tmem_full_bar[as], aphase);
+      ptx::tc_fence_after();
+      const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * p.bn_pad);
+      const int ncols = min(p.BN, p.Cout - tc.n0);
+
+      if (p.tma_epilogue) {
+        for (int c = 0; c < nchunks; ++c, ++g) {
+          const int col0 = c * 64;
+          if (col0 >= ncols) {  // whole chunk beyond Cout (only when BN > remaining channels)
+            if (c == nchunks - 1) {
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+            }
+            if (p.has_res && leader) issue_residual(g + 2);  // keep the prefetch chain going
+            continue;
+          }
+          const int b = g & 1;
+          if (leader) ptx::bulk_wait_read<1>();  // the store issued two chunks ago has finished reading buffer b
+          ptx::named_bar_sync(1, kEpiThreads);
+          uint32_t r0[32], r1[32];
+          ptx::tmem_ld_32x32(t_acc + (uint32_t)col0, r0);
+          ptx::tmem_ld_32x32(t_acc + (uint32_t)col0 + 32u, r1);
+          ptx::tmem_ld_wait();
+          if (c == nchunks - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+          }
+          if (p.has_res) {
+            ptx::mbar_wait(&res_full_bar[b], (res_phase >> b) & 1u);
+            res_phase ^= (1u << b);
+          }
+          unsigned char* crow = cbuf + (size_t)b * kChunkBytes + (size_t)m * 128;
+          unsigned char* c2row = c2buf + (size_t)b * kChunkBytes + (size_t)m * 128;
+          const unsigned char* rrow = rbuf + (size_t)b * kChunkBytes + (size_t)m * 128;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + q);
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+          for (int q = 0; q < 8; ++q) {  // 8 channels = one 16-byte unit of the swizzled row
+            float v[8];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __bfloat1622float2(h[e]);
-              v[q * 8 + e * 2] += f.x;
-              v[q * 8 + e * 2 + 1] += f.y;
+            for (int j = 0; j < 8; ++j) {
+              const int cj = q * 8 + j;
+              const float acc = __uint_as_float(cj < 32 ? r0[cj & 31] : r1[cj & 31]);
+              v[j] = fmaf(acc, sbuf[col0 + cj], sbuf[kMaxBN + col0 + cj]);
+            }
+            const uint32_t off = ((uint32_t)q ^ swz) << 4;
+            if (p.has_res) {
+              const uint4 u = *reinterpret_cast<const uint4*>(rrow + off);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(h[j]);
+                v[2 * j] += f.x;
+                v[2 * j + 1] += f.y;
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            *reinterpret_cast<uint4*>(crow + off) =
+                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            if (p.has_out2) {
+              float w[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int cj = q * 8 + j;
+                w[j] = fmaxf(fmaf(v[j], sbuf[2 * kMaxBN + col0 + cj], sbuf[3 * kMaxBN + col0 + cj]), 0.f);
+              }
+              *reinterpret_cast<uint4*>(c2row + off) = make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]),
+                                                                  pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
             }
           }
-        } else {
-          for (int j = 0; j < nv; ++j) v[j] += __bfloat162float(rp[(long long)j * p.out_sc]);
+          ptx::fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async proxy)
+          ptx::named_bar_sync(1, kEpiThreads);
+          if (leader) {
+            ptx::tma_store_4d(&map_out, cbuf + (size_t)b * kChunkBytes, tc.n0 + col0, tc.x0, tc.y0, tc.img);
+            if (p.has_out2)
+              ptx::tma_store_4d(&map_out2, c2buf + (size_t)b * kChunkBytes, tc.n0 + col0, tc.x0, tc.y0, tc.img);
+            ptx::bulk_commit();
+            if (p.has_res) issue_residual(g + 2);  // everyone has consumed residual buffer b
+          }
         }
-      }
-      if (p.relu) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-      }
-      if (p.out_fp32) {
-        float* op = reinterpret_cast<float*>(p.out) + pix_off + (long long)cbase * p.out_sc;
-        for (int j = 0; j < nv; ++j) op[(long long)j * p.out_sc] = v[j];
       } else {
-        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix_off + (long long)cbase * p.out_sc;
-        if (vec_ok) {
+        // direct register -> global path (fp32 and/or strided outputs)
+        const int py = tc.y0 + m / p.BW, px = tc.x0 + m % p.BW;
+        const bool row_ok = (py < p.Hout) && (px < p.Wout);
+        const long long pix_off =
+            (long long)tc.img * p.out_sn + (long long)py * p.out_sy + (long long)px * p.out_sx;
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(t_acc + (uint32_t)c0, r);
+          ptx::tmem_ld_wait();
+          if (!row_ok) continue;
+          const int nv = min(32, ncols - c0);
+          const long long cbase = tc.n0 + c0;
+          if (p.out_fp32) {
+            float* op = reinterpret_cast<float*>(p.out) + pix_off + cbase * p.out_sc;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 u;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+            for (int j = 0; j < 32; ++j) {
+              if (j < nv) {
+                float a = fmaf(__uint_as_float(r[j]), sbuf[c0 + j], sbuf[kMaxBN + c0 + j]);
+                if (p.relu) a = fmaxf(a, 0.f);
+                op[(long long)j * p.out_sc] = a;
+              }
+            }
+          } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix_off + cbase * p.out_sc;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[q * 8 + e * 2], v[q * 8 + e * 2 + 1]);
-            reinterpret_cast<uint4*>(op)[q] = u;
+            for (int j = 0; j < 32; ++j) {
+              if (j < nv) {
+                float a = fmaf(__uint_as_float(r[j]), sbuf[c0 + j], sbuf[kMaxBN + c0 + j]);
+                if (p.relu) a = fmaxf(a, 0.f);
+                op[(long long)j * p.out_sc] = __float2bfloat16_rn(a);
+              }
+            }
           }
-        } else {
-          for (int j = 0; j < nv; ++j) op[(long long)j * p.out_sc] = __float2bfloat16_rn(v[j]);
         }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+        ptx::named_bar_sync(1, kEpiThreads);  // sbuf is rewritten at the top of the next tile
       }
-      if (p.out2) {
-        __nv_bfloat16* op2 = p.out2 + pix_off + (long long)cbase * p.out_sc;
-        float w[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int c = cbase + j;
-          float a = v[j];
-          if (j < nv) a = fmaxf(fmaf(a, __ldg(p.scale2 + c), __ldg(p.bias2 + c)), 0.f);
-          w[j] = a;
-        }
-        if (vec_ok) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 u;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(w[q * 8 + e * 2], w[q * 8 + e * 2 + 1]);
-            reinterpret_cast<uint4*>(op2)[q] = u;
-          }
-        } else {
-          for (int j = 0; j < nv; ++j) op2[(long long)j * p.out_sc] = __float2bfloat16_rn(w[j]);
-        }
-      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
     }
+    if (p.tma_epilogue && leader) ptx::bulk_wait_all();  // staging tiles must outlive their stores
   }
 
   ptx::tc_fence_before();
@@ -272,12 +397,12 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-               const cuuint32_t* box) {
+               const cuuint32_t* box, const cuuint32_t* estr = nullptr) {
   auto fn = get_encode_fn();
   if (!fn) return fail(XDET_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
-                  strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  strides_bytes, box, estr ? estr : ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(XDET_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return XDET_OK;
@@ -289,6 +414,30 @@ int next_pow2_cols(int n) {
   return c;
 }
 
+// N-tile heuristic: estimated clocks of the busiest SM = waves * (k-blocks * per-block time + epilogue).
+// Per k-block the tile is bound by the MMA (2*BN clocks for 128 x BN x 64 at 8192 MAC-flops/clk/SM) or by
+// the operand traffic from L2 ((16 KB + BN*128 B) at ~kL2BytesPerClk per SM with every SM pulling).
+constexpr double kL2BytesPerClk = 56.0;
+int pick_block_n(int cout, long long m_tiles, int num_k_blocks, bool multiples_of_64) {
+  int cands[4] = {256, 128, 64, 0};
+  if (!multiples_of_64 && cout < 256) cands[3] = ((cout + 15) / 16) * 16;  // exact fit
+  int best = 0;
+  double best_cost = 0;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    if (bn == 0) continue;
+    const long long tiles = m_tiles * ((cout + bn - 1) / bn);
+    const long long waves = (tiles + kNumSMs - 1) / kNumSMs;
+    const double per_kb = std::max(2.0 * bn, (16384.0 + bn * 128.0) / kL2BytesPerClk);
+    const double cost = (double)waves * (num_k_blocks * per_kb + 6.0 * bn + 600.0);
+    if (best == 0 || cost < best_cost * 0.98) {
+      best = bn;
+      best_cost = cost;
+    }
+  }
+  return best;
+}
+
 }  // namespace
 }  // namespace xdet
 
@@ -298,70 +447,119 @@ extern "C" int xdet_conv2d_bf16(const void* d_in, const xdet_conv_desc* d, void*
   if (!d || !d_in) return fail(XDET_EINVAL, "null argument");
   if (d->N <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0 || d->KH <= 0 || d->KW <= 0)
     return fail(XDET_EINVAL, "conv2d: non-positive dimension");
+  if (d->Hout <= 0 || d->Wout <= 0) return fail(XDET_EINVAL, "conv2d: non-positive output size");
   if (d->in_cs < d->Cin || (d->in_cs % 8) != 0)
     return fail(XDET_EINVAL, "conv2d: input channel stride (%d) must be >= Cin and a multiple of 8 (TMA 16-byte strides)",
                 d->in_cs);
   if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d->weights) & 15))
     return fail(XDET_EINVAL, "conv2d: input and weights must be 16-byte aligned");
-  const int kcpt = (d->Cin + kBK - 1) / kBK;
-  const int ktot = d->KH * d->KW * kcpt * kBK;
+  const int sh = d->stride_h <= 0 ? 1 : d->stride_h, sw = d->stride_w <= 0 ? 1 : d->stride_w;
+  if (sh > 2 || sw > 2) return fail(XDET_EINVAL, "conv2d: strides 1 and 2 are supported");
+  const int dil_h = d->dil_h <= 0 ? 1 : d->dil_h, dil_w = d->dil_w <= 0 ? 1 : d->dil_w;
+  const bool fold = d->fold_w != 0;
+  if (fold && (d->KW * d->in_cs > kBK || dil_w != 1 || d->in_wp < (d->Wout - 1) * sw + kBK / d->in_cs))
+    return fail(XDET_EINVAL, "conv2d: fold_w needs KW*in_cs <= 64, dil_w == 1 and in_wp >= (Wout-1)*stride_w + 64/in_cs");
+
+  // geometry seen by the kernel (1x1 stride-1 convolutions over dense tensors flatten to one long row)
+  int N = d->N, H = d->H, W = d->W, Hout = d->Hout, Wout = d->Wout;
+  long long out_sn = d->out_sn, out_sy = d->out_sy, out_sx = d->out_sx;
+  const bool pointwise = !fold && d->KH == 1 && d->KW == 1 && sh == 1 && sw == 1 && d->pad_top == 0 && d->pad_left == 0 &&
+                         Hout == H && Wout == W;
+  if (pointwise && out_sy == out_sx * W && out_sn == out_sy * H && (long long)N * H * W < (1ll << 31)) {
+    W = Wout = N * H * W;
+    H = Hout = 1;
+    N = 1;
+    out_sy = out_sn = out_sx * W;
+  }
+
+  const int kcpt = fold ? 1 : (d->Cin + kBK - 1) / kBK;
+  const int taps = fold ? d->KH : d->KH * d->KW;
+  const int ktot = taps * kcpt * kBK;
 
   ConvGemmArgs a{};
-  // tile shape: widest power-of-two row segment that covers the output row, up to 128
+  // tile shape: widest power-of-two row segment that covers the output row, up to 128 (<= 128/stride so that the
+  // strided box stays within TMA's 256-element limit)
   int BW = 8;
-  while (BW < d->Wout && BW < kBM) BW <<= 1;
+  while (BW < Wout && BW < kBM) BW <<= 1;
   a.BW = BW;
   a.BH = kBM / BW;
-  a.tiles_x = (d->Wout + a.BW - 1) / a.BW;
-  a.tiles_y = (d->Hout + a.BH - 1) / a.BH;
-  a.n_img = d->N;
-  a.Hout = d->Hout;
-  a.Wout = d->Wout;
+  a.tiles_x = (Wout + a.BW - 1) / a.BW;
+  a.tiles_y = (Hout + a.BH - 1) / a.BH;
+  const long long m_tiles = (long long)a.tiles_x * a.tiles_y * N;
+  a.Hout = Hout;
+  a.Wout = Wout;
   a.Cout = d->Cout;
-  a.taps_w = d->KW;
-  a.dil_h = d->dil_h;
-  a.dil_w = d->dil_w;
+  a.taps_w = fold ? 1 : d->KW;
+  a.dil_h = dil_h;
+  a.dil_w = fold ? 0 : dil_w;
   a.pad_top = d->pad_top;
-  a.pad_left = d->pad_left;
+  a.pad_left = fold ? 0 : d->pad_left;
+  a.mul_x = fold ? 1 : sw;
+  a.mul_y = sh;
   a.k_chunks_per_tap = kcpt;
-  a.num_k_blocks = d->KH * d->KW * kcpt;
-  // N tile: 128 by default, the whole (16-aligned) Cout when it is smaller, 256 never (TMEM/epilogue balance)
-  int BN = d->Cout >= 128 ? 128 : ((d->Cout + 15) / 16) * 16;
-  if (d->block_n > 0) BN = d->block_n;
-  if (BN % 16 != 0 || BN < 16 || BN > 256) return fail(XDET_EINVAL, "conv2d: block_n must be a multiple of 16 in [16,256]");
+  a.num_k_blocks = taps * kcpt;
+
+  // epilogue mode
+  const bool out_bf16_nhwc = !d->out_fp32 && d->out_sc == 1 && (out_sx % 8) == 0 && (out_sy % 8) == 0 &&
+                             (out_sn % 8) == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0 && d->Cout >= 8;
+  a.tma_epilogue = out_bf16_nhwc ? 1 : 0;
+  a.has_res = d->residual ? 1 : 0;
+  a.has_out2 = d->out2 ? 1 : 0;
+  if (a.has_out2 && (!d->scale2 || !d->bias2)) return fail(XDET_EINVAL, "conv2d: out2 needs scale2 and bias2");
+  if ((a.has_res || a.has_out2) && !a.tma_epilogue)
+    return fail(XDET_EINVAL, "conv2d: residual / second output need a bf16 NHWC `out` (unit channel stride, 16-byte aligned "
+                             "pixel strides); they share its layout");
+  if ((a.has_res && (reinterpret_cast<uintptr_t>(d->residual) & 15)) || (a.has_out2 && (reinterpret_cast<uintptr_t>(d->out2) & 15)))
+    return fail(XDET_EINVAL, "conv2d: residual / out2 must be 16-byte aligned");
+
+  // shared memory budget and N tile
+  const size_t epi_bytes = (size_t)kChunkBytes * 2 * ((a.tma_epilogue ? 1 : 0) + a.has_out2 + a.has_res);
+  const size_t tail = 4 * kMaxBN * sizeof(float) + (2 * kMaxStages + 6) * sizeof(uint64_t) + 64;
+  const size_t budget = 227 * 1024 - 1024 - tail - epi_bytes;
+  int BN = d->block_n > 0 ? d->block_n : pick_block_n(d->Cout, m_tiles, a.num_k_blocks, a.tma_epilogue != 0);
+  if (BN % 16 != 0 || BN < 16 || BN > kMaxBN) return fail(XDET_EINVAL, "conv2d: block_n must be a multiple of 16 in [16,256]");
+  if (a.tma_epilogue && BN % 64 != 0) return fail(XDET_EINVAL, "conv2d: block_n must be a multiple of 64 for bf16 NHWC outputs");
   a.BN = BN;
-  a.tmem_cols = next_pow2_cols(((BN + 31) / 32) * 32);
+  a.bn_pad = ((BN + 31) / 32) * 32;
+  a.tmem_cols = next_pow2_cols(2 * a.bn_pad);
+  a.n_tiles_n = (d->Cout + BN - 1) / BN;
+  const long long total = m_tiles * a.n_tiles_n;
+  if (total >= (1ll << 31)) return fail(XDET_EINVAL, "conv2d: too many tiles");
+  a.total_tiles = (int)total;
   const size_t stage_bytes = (size_t)kBM * kBK * 2 + (((size_t)BN * kBK * 2 + 1023) & ~(size_t)1023);
-  const size_t tail = 3 * kMaxStages * sizeof(uint64_t) + 64;
-  int stages = (int)((227 * 1024 - tail - 1024) / stage_bytes);
+  int stages = (int)(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages > a.num_k_blocks) stages = a.num_k_blocks < 2 ? 2 : a.num_k_blocks;
   if (stages < 2) return fail(XDET_EINVAL, "conv2d: tile does not fit shared memory");
   a.stages = stages;
   a.scale = d->scale;
   a.bias = d->bias;
   a.relu = d->relu;
-  a.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
   a.out = d->out;
   a.out_fp32 = d->out_fp32;
-  a.out_sn = d->out_sn;
-  a.out_sy = d->out_sy;
-  a.out_sx = d->out_sx;
+  a.out_sn = out_sn;
+  a.out_sy = out_sy;
+  a.out_sx = out_sx;
   a.out_sc = d->out_sc;
-  a.out2 = reinterpret_cast<__nv_bfloat16*>(d->out2);
   a.scale2 = d->scale2;
   a.bias2 = d->bias2;
-  if (a.out2 && (!a.scale2 || !a.bias2)) return fail(XDET_EINVAL, "conv2d: out2 needs scale2 and bias2");
-  if ((a.residual || a.out2) && d->out_fp32)
-    return fail(XDET_EINVAL, "conv2d: residual / second output share the (bf16) layout of `out`");
 
-  CUtensorMap map_a, map_b;
-  {
-    const cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
-    const cuuint64_t strides[3] = {(cuuint64_t)d->in_cs * 2, (cuuint64_t)d->in_cs * 2 * d->W,
-                                   (cuuint64_t)d->in_cs * 2 * d->W * d->H};
-    const cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)a.BW, (cuuint32_t)a.BH, 1};
-    XDET_TRY(encode_map(&map_a, d_in, 4, dims, strides, box));
+  CUtensorMap map_a, map_b, map_out, map_res, map_out2;
+  if (fold) {
+    // dims {64-element window, Wout windows (stride_w pixels apart, overlapping), H rows, N images}
+    const cuuint64_t dims[4] = {(cuuint64_t)kBK, (cuuint64_t)Wout, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)sw * d->in_cs * 2, (cuuint64_t)d->in_wp * d->in_cs * 2,
+                                   (cuuint64_t)d->in_wp * d->in_cs * 2 * H};
+    const cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)a.BW, (cuuint32_t)(a.BH * sh), 1};
+    const cuuint32_t estr[4] = {1, 1, (cuuint32_t)sh, 1};
+    XDET_TRY(encode_map(&map_a, d_in, 4, dims, strides, box, estr));
+  } else {
+    if (a.BW * sw > 256 || a.BH * sh > 256) return fail(XDET_EINVAL, "conv2d: strided tile exceeds the TMA box limit");
+    const cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)d->in_cs * 2, (cuuint64_t)d->in_cs * 2 * W,
+                                   (cuuint64_t)d->in_cs * 2 * W * H};
+    const cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)(a.BW * sw), (cuuint32_t)(a.BH * sh), 1};
+    const cuuint32_t estr[4] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1};
+    XDET_TRY(encode_map(&map_a, d_in, 4, dims, strides, box, estr));
   }
   {
     const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)d->Cout};
@@ -369,10 +567,21 @@ extern "C" int xdet_conv2d_bf16(const void* d_in, const xdet_conv_desc* d, void*
     const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)BN};
     XDET_TRY(encode_map(&map_b, d->weights, 2, dims, strides, box));
   }
-  const size_t smem = (size_t)stages * stage_bytes + tail + 1024;  // +1024: manual alignment slack
-  XDET_TRY(check_cuda(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+  map_out = map_a;  // placeholders when unused (never dereferenced by the kernel)
+  map_res = map_a;
+  map_out2 = map_a;
+  if (a.tma_epilogue) {
+    const cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)Wout, (cuuint64_t)Hout, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)out_sx * 2, (cuuint64_t)out_sy * 2, (cuuint64_t)out_sn * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)a.BW, (cuuint32_t)a.BH, 1};
+    XDET_TRY(encode_map(&map_out, d->out, 4, dims, strides, box));
+    if (a.has_res) XDET_TRY(encode_map(&map_res, d->residual, 4, dims, strides, box));
+    if (a.has_out2) XDET_TRY(encode_map(&map_out2, d->out2, 4, dims, strides, box));
+  }
+  const size_t smem = (size_t)stages * stage_bytes + epi_bytes + tail + 1024;  // +1024: manual alignment slack
+  XDET_TRY(check_cuda(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
                       "cudaFuncSetAttribute(conv_gemm)"));
-  dim3 grid((unsigned)(a.tiles_x * a.tiles_y * a.n_img), (unsigned)((d->Cout + BN - 1) / BN));
-  conv_gemm_kernel<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, a);
+  const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
+  conv_gemm_kernel<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, map_out, map_res, map_out2, a);
   return after_launch("conv_gemm_kernel");
 }

@@ -168,6 +168,34 @@ __global__ void __launch_bounds__(256) f32_to_bf16_rows_kernel(const float* __re
   }
 }
 
+// NCHW fp32 image -> row-padded NHWC bf16 with the channels zero-padded to `cs` (8): the input layout of the
+// fold_w convolution (conv_gemm.cu) that runs the 7x7/s2 stem.  dst[n][y][pad_left + x][c], zeros elsewhere.
+__global__ void __launch_bounds__(256) image_to_nhwc8_kernel(const float* __restrict__ src,
+                                                             __nv_bfloat16* __restrict__ dst, int N, int C, int H,
+                                                             int W, int Wp, int pad_left, long long total) {
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
+    const int xp = (int)(e % Wp);
+    const long long row = e / Wp;  // n*H + y
+    const int y = (int)(row % H);
+    const int n = (int)(row / H);
+    const int x = xp - pad_left;
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = 0.f;
+    if (x >= 0 && x < W) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c < C) v[c] = __ldg(src + (((long long)n * C + c) * H + y) * W + x);
+    }
+    uint4 o;
+    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ho[q] = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+    reinterpret_cast<uint4*>(dst)[e] = o;
+  }
+}
+
 unsigned grid_for(long long total, int threads = 256) {
   long long b = (total + threads - 1) / threads;
   const long long cap = (long long)kNumSMs * 16;
@@ -237,4 +265,14 @@ extern "C" int xdet_f32_to_bf16_rows(const float* d_src, void* d_dst, long long 
   f32_to_bf16_rows_kernel<<<grid_for(rows * dst_pitch), 256, 0, (cudaStream_t)stream>>>(
       d_src, reinterpret_cast<__nv_bfloat16*>(d_dst), rows, cols, dst_pitch);
   return after_launch("f32_to_bf16_rows_kernel");
+}
+
+extern "C" int xdet_image_to_nhwc8_bf16(const float* d_src, void* d_dst, int N, int C, int H, int W, int Wp,
+                                        int pad_left, void* stream) {
+  if (N <= 0 || C <= 0 || C > 8 || H <= 0 || W <= 0) return fail(XDET_EINVAL, "image_to_nhwc8: need 1 <= C <= 8 and positive sizes");
+  if (pad_left < 0 || Wp < W + pad_left) return fail(XDET_EINVAL, "image_to_nhwc8: Wp (%d) < W + pad_left", Wp);
+  const long long total = (long long)N * H * Wp;
+  image_to_nhwc8_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+      d_src, reinterpret_cast<__nv_bfloat16*>(d_dst), N, C, H, W, Wp, pad_left, total);
+  return after_launch("image_to_nhwc8_kernel");
 }

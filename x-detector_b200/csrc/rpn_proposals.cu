@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(kSelThreads) nms_scan_kernel(
   int* kept = reinterpret_cast<int*>(removed + words);                            // [keep_n]
   int* shuf = kept + keep_n;                                                      // [keep_n]
   __shared__ unsigned long long s_surv;
+  __shared__ unsigned long long s_diag[64];
   const int img = blockIdx.x, tid = threadIdx.x;
   const unsigned long long* m = mask + (long long)img * K * words;
   const float* sc = top_scores + (long long)img * K;
@@ -254,8 +255,14 @@ __global__ void __launch_bounds__(kSelThreads) nms_scan_kernel(
   const int out_size = min(keep_n, K);
   int nk = 0;  // every thread tracks the kept count in a register (no shared read/write race)
   for (int cb = 0; cb < words && nk < out_size; ++cb) {
+    // stage the 64 diagonal words of this block (one coalesced-ish parallel fetch instead of 64 dependent ones)
+    if (tid < 64) {
+      const int r = cb * 64 + tid;
+      s_diag[tid] = r < K ? m[(long long)r * words + cb] : 0ull;
+    }
+    __syncthreads();
     if (tid == 0) {
-      // sequential resolution inside the 64-candidate block (diagonal words of the matrix)
+      // sequential resolution inside the 64-candidate block (registers / shared memory only)
       unsigned long long rem = removed[cb], surv = 0ull;
       int k = nk;
       const int n_in = min(64, K - cb * 64);
@@ -263,25 +270,36 @@ __global__ void __launch_bounds__(kSelThreads) nms_scan_kernel(
         if (!((rem >> j) & 1ull)) {
           surv |= (1ull << j);
           kept[k++] = cb * 64 + j;
-          rem |= m[((long long)(cb * 64 + j)) * words + cb];
+          rem |= s_diag[j];
         }
       }
       s_surv = surv;
     }
     __syncthreads();
-    // OR the survivors' rows into `removed` for all later blocks, in parallel
+    // OR the survivors' rows into `removed` for all later blocks: (candidate j, word w) pairs spread over the
+    // whole CTA, four independent loads in flight per thread
     const unsigned long long surv = s_surv;
     nk += __popcll(surv);
-    if (surv) {
-      for (int w = cb + 1 + tid; w < words; w += kSelThreads) {
-        unsigned long long acc = removed[w];
-        unsigned long long s = surv;
-        while (s) {
-          const int j = __ffsll((long long)s) - 1;
-          s &= s - 1;
-          acc |= m[((long long)(cb * 64 + j)) * words + w];
+    const int nw = words - cb - 1;
+    if (surv && nw > 0 && nk < out_size) {
+      const int total = 64 * nw;
+      for (int base = tid; base < total; base += 4 * kSelThreads) {
+        unsigned long long v[4];
+        int ww[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + u * kSelThreads;
+          v[u] = 0ull;
+          ww[u] = 0;
+          if (idx < total) {
+            const int j = idx / nw;
+            ww[u] = cb + 1 + (idx - j * nw);
+            if ((surv >> j) & 1ull) v[u] = m[((long long)(cb * 64 + j)) * words + ww[u]];
+          }
         }
-        removed[w] = acc;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (v[u]) atomicOr(&removed[ww[u]], v[u]);
       }
     }
     __syncthreads();

@@ -10,8 +10,9 @@ Compute: every convolution is ``ops.conv2d_nhwc`` (tcgen05 implicit GEMM); batch
 the epilogue of the convolution that PRODUCES the tensor wherever the graph allows it:
   conv1x1 -> BN -> ReLU and conv3x3 -> BN -> ReLU inside a block are one kernel each;
   ``conv1x1 + shortcut`` writes the sum AND the next block's pre-activation ``relu(bn(sum))`` (second output).
-Strided convolutions (``conv2d_fixed_padding`` with strides > 1, :89-100) gather their patches first
-(``ops.im2col``, which also materialises ``fixed_padding``, :62-86) and then run as GEMMs.
+Strided convolutions (``conv2d_fixed_padding`` with strides > 1, :89-100) are implicit GEMMs as well: the
+tensor map reads every 2nd pixel and its out-of-bounds zero fill is ``fixed_padding`` (:62-86); the 3-channel
+7x7/s2 stem runs in the kernel's fold_w mode on a row-padded NHWC8 copy of the image.
 
 ``lighthead_resnet50_body`` is the Light-Head composition SURVEY 8(a3) defines from these builders plus the
 reference's own dilation pattern (net/xdet_body.py:28-121): block_layer1-3 as-is (stride 16) ->
@@ -69,32 +70,18 @@ def _packed(store, kern, mode="conv"):
 
 
 def _run_conv(store, x, kern, strides, dilation=1, **epilogue):
-    """conv2d_fixed_padding semantics on NHWC bf16: SAME for stride 1, explicit pad + VALID otherwise."""
+    """conv2d_fixed_padding semantics on NHWC bf16: SAME for stride 1, explicit pad + VALID otherwise
+    (net/resnet_v2.py:89-100).  Strided convolutions read every 2nd pixel through the tensor map (no im2col)."""
     kh, kw, cin, cout = kern[1].shape
     if strides == 1:
         return ops.conv2d_nhwc(x, _packed(store, kern), cout, kh, kw, dilation=(dilation, dilation), padding="SAME",
                                cin=cin, **epilogue)
     N, H, W, _ = x.shape
-    pad = (kh - 1) // 2
+    pad = (kh - 1) // 2  # fixed_padding: pad_beg = (k-1)//2, then VALID
     Ho = (H + (kh - 1) - kh) // strides + 1
     Wo = (W + (kw - 1) - kw) // strides + 1
-    patches = ops.im2col(x, kh, kw, strides, pad, pad, Ho, Wo, cin=cin)
-    K = patches.shape[-1]
-    y = ops.conv2d_nhwc(patches.reshape(1, 1, N * Ho * Wo, K), _packed(store, kern, "patch"), cout, 1, 1,
-                        cin=kh * kw * cin, **_flat(epilogue, N * Ho * Wo))
-    return _unflat(y, N, Ho, Wo)
-
-
-def _flat(ep, M):
-    out = dict(ep)
-    for k in ("residual", "out2"):
-        if out.get(k) is not None:
-            out[k] = out[k].reshape(1, 1, M, -1)
-    return out
-
-
-def _unflat(y, N, Ho, Wo):
-    return y.reshape(N, Ho, Wo, y.shape[-1])
+    return ops.conv2d_nhwc(x, _packed(store, kern), cout, kh, kw, padding=(pad, pad, Ho, Wo),
+                           strides=(strides, strides), cin=cin, **epilogue)
 
 
 def conv2d_fixed_padding(inputs, filters, kernel_size, strides, data_format, kernel_initializer=None, store=None,
@@ -198,11 +185,11 @@ def stem(image_nchw_f32, store):
     fp32 NCHW image the input pipeline delivers; returns NHWC bf16."""
     N, C, H, W = image_nchw_f32.shape
     kern = _conv_kernel(store, C, 64, 7)
-    Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
-    patches = ops.im2col(image_nchw_f32.contiguous(), 7, 7, 2, 3, 3, Ho, Wo, nchw_f32=True)
-    K = patches.shape[-1]
-    y = ops.conv2d_nhwc(patches.reshape(1, 1, N * Ho * Wo, K), _packed(store, kern, "patch"), 64, 1, 1, cin=49 * C)
-    return ops.maxpool3x3s2_same(y.reshape(N, Ho, Wo, 64))
+    key = ("w", kern[0], "fold")
+    if key not in store.derived:
+        store.derived[key] = ops.pack_fold_weight(kern[1].permute(3, 2, 0, 1))
+    y = ops.conv2d_image_fold(image_nchw_f32.contiguous(), store.derived[key], 64, 7, 7, 2, 3)
+    return ops.maxpool3x3s2_same(y)
 
 
 def lighthead_resnet50_body(image_nchw_f32, is_training, store, layers=(3, 4, 6, 3)):

@@ -19,6 +19,7 @@ class ConvDesc(ctypes.Structure):
         ("Cout", ctypes.c_int), ("KH", ctypes.c_int), ("KW", ctypes.c_int), ("dil_h", ctypes.c_int),
         ("dil_w", ctypes.c_int), ("pad_top", ctypes.c_int), ("pad_left", ctypes.c_int),
         ("Hout", ctypes.c_int), ("Wout", ctypes.c_int),
+        ("stride_h", ctypes.c_int), ("stride_w", ctypes.c_int), ("fold_w", ctypes.c_int), ("in_wp", ctypes.c_int),
         ("weights", ctypes.c_void_p), ("scale", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("relu", ctypes.c_int),
         ("residual", ctypes.c_void_p), ("out", ctypes.c_void_p), ("out_fp32", ctypes.c_int),
         ("out_sn", ctypes.c_longlong), ("out_sy", ctypes.c_longlong), ("out_sx", ctypes.c_longlong),
@@ -34,6 +35,15 @@ def pack_conv_weight(w_oihw):
     w = torch.zeros((cout, kh * kw, cpad), dtype=torch.float32, device=w_oihw.device)
     w[:, :, :cin] = w_oihw.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin).float()
     return w.reshape(cout, kh * kw * cpad).to(torch.bfloat16).contiguous()
+
+
+def pack_fold_weight(w_oihw, cs=8):
+    """[Cout, Cin<=cs, KH, KW] float -> bf16 [Cout, KH*64] for the fold_w mode: element kw*cs + ci of filter row kh."""
+    cout, cin, kh, kw = w_oihw.shape
+    assert cin <= cs and kw * cs <= 64
+    w = torch.zeros((cout, kh, 64), dtype=torch.float32, device=w_oihw.device)
+    w[:, :, :kw * cs].view(cout, kh, kw, cs)[..., :cin] = w_oihw.permute(0, 2, 3, 1).float()
+    return w.reshape(cout, kh * 64).to(torch.bfloat16).contiguous()
 
 
 def same_pad(n, k, dil=1, stride=1):
@@ -55,22 +65,30 @@ PROFILE = None
 
 def conv2d_nhwc(x, w_packed, cout, kh, kw, *, dilation=(1, 1), padding="SAME", scale=None, bias=None, relu=False,
                 residual=None, out=None, out_layout="nhwc_bf16", out2=None, scale2=None, bias2=None, cin=None,
-                block_n=0):
+                block_n=0, strides=(1, 1), fold_w=None):
     """x: [N,H,W,C] bf16 (channel stride may be padded: pass the true ``cin``).  Returns the output tensor
     ([N,Ho,Wo,Cout] bf16 for 'nhwc_bf16', [N,Cout,Ho,Wo] fp32 for 'nchw_f32', [N,Ho,Wo,Cout] fp32 for 'nhwc_f32')."""
     assert x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4
     N, H, W, cs = x.shape
-    assert x.stride(3) == 1 and x.stride(2) == cs and x.stride(1) == W * cs and x.stride(0) == H * W * cs
+    assert x.is_contiguous()
     cin = cs if cin is None else cin
     dh, dw = dilation
+    sh, sw = strides
+    in_wp = 0
+    if fold_w is not None:
+        # x is the horizontally padded few-channel image [N,H,in_wp,cs]; fold_w = (true width, pad_left)
+        in_wp = W
+        W = fold_w[0]
     if padding == "SAME":
-        pt, pl = same_pad(H, kh, dh), same_pad(W, kw, dw)
-        Ho, Wo = H, W
+        pt, pl = same_pad(H, kh, dh, sh), same_pad(W, kw, dw, sw)
+        Ho, Wo = -(-H // sh), -(-W // sw)
     elif padding == "VALID":
         pt = pl = 0
-        Ho, Wo = H - (kh - 1) * dh, W - (kw - 1) * dw
+        Ho, Wo = (H - (kh - 1) * dh - 1) // sh + 1, (W - (kw - 1) * dw - 1) // sw + 1
     else:
         pt, pl, Ho, Wo = padding  # explicit (pad_top, pad_left, Hout, Wout)
+    if fold_w is not None:
+        assert pl == fold_w[1], "the materialised left padding must equal the convolution's"
     dev = x.device
     if out is None:
         if out_layout == "nhwc_bf16":
@@ -85,7 +103,8 @@ def conv2d_nhwc(x, w_packed, cout, kh, kw, *, dilation=(1, 1), padding="SAME", s
         sn, sc, sy, sx = out.stride()
     else:
         sn, sy, sx, sc = out.stride()
-    d = ConvDesc(N, H, W, cin, cs, cout, kh, kw, dh, dw, pt, pl, Ho, Wo, w_packed.data_ptr(), _ptr(scale), _ptr(bias),
+    d = ConvDesc(N, H, W, cin, cs, cout, kh, kw, dh, dw, pt, pl, Ho, Wo, sh, sw, 0 if fold_w is None else 1, in_wp,
+                 w_packed.data_ptr(), _ptr(scale), _ptr(bias),
                  1 if relu else 0, _ptr(residual), out.data_ptr(), 0 if out.dtype == torch.bfloat16 else 1,
                  sn, sy, sx, sc, _ptr(out2), _ptr(scale2), _ptr(bias2), block_n)
     with torch.cuda.device(dev):
@@ -105,3 +124,18 @@ def linear(x2d, w_packed, cout, **kw):
     M, K = x2d.shape
     out = conv2d_nhwc(x2d.reshape(1, 1, M, K), w_packed, cout, 1, 1, **kw)
     return out.reshape(M, cout) if out.dim() == 4 and out.shape[1] == 1 else out
+
+
+def conv2d_image_fold(image_nchw_f32, w_fold, cout, kh, kw, stride, pad, **kw_args):
+    """Few-channel strided convolution of the fp32 NCHW input image (the 7x7/s2 ResNet stem with explicit
+    ``fixed_padding`` = ``pad`` on both sides, or Xception's 3x3/s2 VALID block1_conv1 with pad 0): one layout
+    pass (image -> row-padded NHWC8 bf16) + the fold_w implicit GEMM.  Returns NHWC bf16 [N,Ho,Wo,cout]."""
+    from .layout import image_to_nhwc8
+    N, C, H, W = image_nchw_f32.shape
+    Ho = (H + 2 * pad - kh) // stride + 1
+    Wo = (W + 2 * pad - kw) // stride + 1
+    wp = max((Wo - 1) * stride + 8, W + pad)
+    wp = (wp + 7) // 8 * 8
+    x8 = image_to_nhwc8(image_nchw_f32, pad, wp)
+    return conv2d_nhwc(x8, w_fold, cout, kh, kw, padding=(pad, pad, Ho, Wo), strides=(stride, stride), cin=C,
+                       fold_w=(W, pad), **kw_args)

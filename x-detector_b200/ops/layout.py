@@ -60,3 +60,14 @@ def f32_to_bf16_rows(x2d, pitch):
     rc = _native.lib().xdet_f32_to_bf16_rows(x2d.data_ptr(), out.data_ptr(), rows, cols, pitch, _st())
     _native.check(rc)
     return out
+
+
+def image_to_nhwc8(image_nchw_f32, pad_left, wp):
+    """[N,C<=8,H,W] fp32 NCHW -> [N,H,wp,8] bf16, `pad_left` zero pixels in front of each row (fold_w conv input)."""
+    N, C, H, W = image_nchw_f32.shape
+    assert image_nchw_f32.dtype == torch.float32 and image_nchw_f32.is_contiguous()
+    out = torch.empty((N, H, wp, 8), dtype=torch.bfloat16, device=image_nchw_f32.device)
+    rc = _native.lib().xdet_image_to_nhwc8_bf16(image_nchw_f32.data_ptr(), out.data_ptr(), N, C, H, W, wp, pad_left,
+                                                _st())
+    _native.check(rc)
+    return out
