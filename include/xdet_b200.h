@@ -115,13 +115,14 @@ typedef struct {
   const float* bias;  /* per-Cout addend (conv bias / folded batch-norm), NULL = 0 */
   int relu;
   const void* residual; /* bf16 or NULL */
-  void* out;
+  void* out; /* may be NULL when out2 is given: only the second output is stored */
   int out_fp32; /* 0: bf16, 1: fp32 */
   long long out_sn, out_sy, out_sx, out_sc;
   void* out2; /* bf16 or NULL */
   const float* scale2;
   const float* bias2;
-  int block_n; /* 0 = auto; otherwise the N tile (multiple of 16, <= 256) */
+  int block_n;  /* 0 = auto; otherwise the N tile (multiple of 16, <= 256; of 64 for bf16 NHWC outputs) */
+  int max_ctas; /* 0 = one persistent CTA per SM; otherwise an upper bound (leaves SMs to a concurrent stream) */
 } xdet_conv_desc;
 int xdet_conv2d_bf16(const void* d_in, const xdet_conv_desc* desc, void* stream);
 

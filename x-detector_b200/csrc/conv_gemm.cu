@@ -51,6 +51,9 @@ constexpr int kEpiThreads = 128;
 constexpr int kMaxStages = 8;
 constexpr int kMaxBN = 256;
 constexpr uint32_t kChunkBytes = kBM * 64 * 2;  // one 128 x 64-channel bf16 staging tile
+// dynamic shared memory per CTA: leaves ~16 KB of the SM for small CTAs of concurrent kernels (the NMS
+// bit-matrix kernel of the proposal stream runs beside the backbone convolutions)
+constexpr size_t kSmemCap = 211 * 1024;
 
 struct ConvGemmArgs {
   int tiles_x, tiles_y, n_tiles_n, total_tiles;
@@ -62,7 +65,7 @@ struct ConvGemmArgs {
   const float* scale;
   const float* bias;
   int relu;
-  int tma_epilogue, has_res, has_out2;
+  int tma_epilogue, has_res, has_out2, skip_out;
   void* out;
   int out_fp32;
   long long out_sn, out_sy, out_sx, out_sc;
@@ -308,8 +311,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
             }
-            *reinterpret_cast<uint4*>(crow + off) =
-                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            if (!p.skip_out)
+              *reinterpret_cast<uint4*>(crow + off) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                                                                 pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
             if (p.has_out2) {
               float w[8];
 #pragma unroll
@@ -324,7 +328,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           ptx::fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async proxy)
           ptx::named_bar_sync(1, kEpiThreads);
           if (leader) {
-            ptx::tma_store_4d(&map_out, cbuf + (size_t)b * kChunkBytes, tc.n0 + col0, tc.x0, tc.y0, tc.img);
+            if (!p.skip_out)
+              ptx::tma_store_4d(&map_out, cbuf + (size_t)b * kChunkBytes, tc.n0 + col0, tc.x0, tc.y0, tc.img);
             if (p.has_out2)
               ptx::tma_store_4d(&map_out2, c2buf + (size_t)b * kChunkBytes, tc.n0 + col0, tc.x0, tc.y0, tc.img);
             ptx::bulk_commit();
@@ -500,6 +505,8 @@ extern "C" int xdet_conv2d_bf16(const void* d_in, const xdet_conv_desc* d, void*
   a.num_k_blocks = taps * kcpt;
 
   // epilogue mode
+  if (!d->out && !d->out2) return fail(XDET_EINVAL, "conv2d: no output");
+  a.skip_out = d->out ? 0 : 1;  // only the second output is wanted (its producer's raw value has no other reader)
   const bool out_bf16_nhwc = !d->out_fp32 && d->out_sc == 1 && (out_sx % 8) == 0 && (out_sy % 8) == 0 &&
                              (out_sn % 8) == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0 && d->Cout >= 8;
   a.tma_epilogue = out_bf16_nhwc ? 1 : 0;
@@ -515,7 +522,7 @@ extern "C" int xdet_conv2d_bf16(const void* d_in, const xdet_conv_desc* d, void*
   // shared memory budget and N tile
   const size_t epi_bytes = (size_t)kChunkBytes * 2 * ((a.tma_epilogue ? 1 : 0) + a.has_out2 + a.has_res);
   const size_t tail = 4 * kMaxBN * sizeof(float) + (2 * kMaxStages + 6) * sizeof(uint64_t) + 64;
-  const size_t budget = 227 * 1024 - 1024 - tail - epi_bytes;
+  const size_t budget = kSmemCap - 1024 - tail - epi_bytes;
   int BN = d->block_n > 0 ? d->block_n : pick_block_n(d->Cout, m_tiles, a.num_k_blocks, a.tma_epilogue != 0);
   if (BN % 16 != 0 || BN < 16 || BN > kMaxBN) return fail(XDET_EINVAL, "conv2d: block_n must be a multiple of 16 in [16,256]");
   if (a.tma_epilogue && BN % 64 != 0) return fail(XDET_EINVAL, "conv2d: block_n must be a multiple of 64 for bf16 NHWC outputs");
@@ -574,14 +581,16 @@ extern "C" int xdet_conv2d_bf16(const void* d_in, const xdet_conv_desc* d, void*
     const cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)Wout, (cuuint64_t)Hout, (cuuint64_t)N};
     const cuuint64_t strides[3] = {(cuuint64_t)out_sx * 2, (cuuint64_t)out_sy * 2, (cuuint64_t)out_sn * 2};
     const cuuint32_t box[4] = {64, (cuuint32_t)a.BW, (cuuint32_t)a.BH, 1};
-    XDET_TRY(encode_map(&map_out, d->out, 4, dims, strides, box));
+    XDET_TRY(encode_map(&map_out, d->out ? d->out : d->out2, 4, dims, strides, box));
     if (a.has_res) XDET_TRY(encode_map(&map_res, d->residual, 4, dims, strides, box));
     if (a.has_out2) XDET_TRY(encode_map(&map_out2, d->out2, 4, dims, strides, box));
   }
   const size_t smem = (size_t)stages * stage_bytes + epi_bytes + tail + 1024;  // +1024: manual alignment slack
   XDET_TRY(check_cuda(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
                       "cudaFuncSetAttribute(conv_gemm)"));
-  const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
+  int sms = kNumSMs;
+  if (d->max_ctas > 0 && d->max_ctas < sms) sms = d->max_ctas;  // leave SMs to a concurrent stream
+  const int grid = a.total_tiles < sms ? a.total_tiles : sms;
   conv_gemm_kernel<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, map_out, map_res, map_out2, a);
   return after_launch("conv_gemm_kernel");
 }

@@ -201,13 +201,22 @@ __device__ __forceinline__ NBox norm_box(float4 b) {
   n.area = __fmul_rn(__fsub_rn(n.ymax, n.ymin), __fsub_rn(n.xmax, n.xmin));
   return n;
 }
+// iou > thr with the reference's roundings (TF r1.6 NonMaxSuppressionV2: one fp32 division, then the compare).
+// The division is only executed when the cheap bracket inter vs thr*union*(1 +- 1e-6) cannot decide: fl(a/b)
+// differs from a/b by <= 2^-24 relative and fl(thr*union) likewise, so outside the bracket the two tests agree.
 __device__ __forceinline__ bool iou_greater(const NBox& a, const NBox& b, float thr) {
   if (a.area <= 0.f || b.area <= 0.f) return false;
   const float iy0 = fmaxf(a.ymin, b.ymin), ix0 = fmaxf(a.xmin, b.xmin);
   const float iy1 = fminf(a.ymax, b.ymax), ix1 = fminf(a.xmax, b.xmax);
   const float inter = __fmul_rn(fmaxf(__fsub_rn(iy1, iy0), 0.f), fmaxf(__fsub_rn(ix1, ix0), 0.f));
-  const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(a.area, b.area), inter));
-  return iou > thr;
+  const float uni = __fsub_rn(__fadd_rn(a.area, b.area), inter);
+  if (thr >= 0.f && uni > 0.f) {
+    if (inter <= 0.f) return false;  // iou == 0
+    const float t = __fmul_rn(thr, uni);
+    if (inter > __fmul_rn(t, 1.000001f)) return true;
+    if (inter < __fmul_rn(t, 0.999999f)) return false;
+  }
+  return __fdiv_rn(inter, uni) > thr;
 }
 
 // grid (col blocks, row blocks, N), 64 threads: word (row i, col block) of the suppression matrix,

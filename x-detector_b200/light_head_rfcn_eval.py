@@ -17,6 +17,7 @@ import types
 import torch
 
 from . import ops
+from .ops import conv as conv_ops
 from .net import resnet_v2, xception_body
 from .net.variables import VariableStore
 from .preprocessing import anchor_manipulator
@@ -67,6 +68,16 @@ def input_pipeline(params, device="cuda"):
             'num_anchors_list': num_anchors_list, 'anchor_encoder': enc}
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 def lighr_head_model_fn(features, labels, mode, params, store=None, shuffle_keys=None):
     """features: images [N,3,H,W] fp32 CUDA (whitened, as light_head_preprocess_for_eval delivers them).
     Returns the ``predictions`` of the reference's model_fn plus the intermediate tensors tests compare."""
@@ -74,26 +85,47 @@ def lighr_head_model_fn(features, labels, mode, params, store=None, shuffle_keys
     num_anchors = labels['num_anchors_list'][0]
     enc = labels['anchor_encoder']
     df = 'channels_last'
+    main = torch.cuda.current_stream()
+    side = _side_stream(features.device)
+    st = {}
+
+    def after_rpn_feat(rpn_feat_map):
+        # RPN head on the main stream, then FORK: objectness/decode -> clip/filter/top-k -> NMS -> upsample run on
+        # a second stream beside block_layer4 + large_sep_kernel (they only meet again at PsRoIAlign).  The
+        # proposal kernels are one CTA per image, so the backbone convolutions leave that many SMs free meanwhile.
+        st['rpn_out'] = xception_body.get_rpn(rpn_feat_map, num_anchors, False, df, 'rpn_head', store)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            # softmax[:, -1] + decode_all_anchors in one kernel (reference :389-399)
+            st['score'], st['boxes'] = ops.rpn_decode(st['rpn_out'], 0, 2 * num_anchors, enc.device_anchors(0),
+                                                      num_anchors)
+            st['rois'], st['yxhw'], _ = ops.rpn_select(st['score'], st['boxes'], params['rpn_pre_nms_top_n'],
+                                                       params['rpn_post_nms_top_n'], params['rpn_nms_thres'],
+                                                       params['rpn_min_size'], shuffle_keys)
+        conv_ops.MAX_CTAS = 148 - min(int(features.shape[0]), 16)
+
     with store.scope(params['model_scope']):
-        if params.get('backbone', 'resnet50') == 'resnet50':
-            rpn_feat_map, backbone_feat = resnet_v2.lighthead_resnet50_body(features, False, store)
-        else:
-            raise NotImplementedError("XceptionBody is not built yet (DESIGN.md: next rows)")
-        rpn_out = xception_body.get_rpn(rpn_feat_map, num_anchors, False, df, 'rpn_head', store)
-        large_sep_feature = xception_body.large_sep_kernel(backbone_feat, 256, 10 * 7 * 7, False, df,
-                                                           'large_sep_feature', store)
-        # softmax[:, -1] + decode_all_anchors in one kernel (reference :389-399)
-        rpn_object_score, rpn_bboxes_pred = ops.rpn_decode(rpn_out, 0, 2 * num_anchors, enc.device_anchors(0),
-                                                           num_anchors)
-        proposals_bboxes, yxhw, _ = ops.rpn_select(rpn_object_score, rpn_bboxes_pred, params['rpn_pre_nms_top_n'],
-                                                   params['rpn_post_nms_top_n'], params['rpn_nms_thres'],
-                                                   params['rpn_min_size'], shuffle_keys)
-        cls_score, bboxes_reg = xception_body.get_head(
+        try:
+            if params.get('backbone', 'resnet50') == 'resnet50':
+                rpn_feat_map, backbone_feat = resnet_v2.lighthead_resnet50_body(features, False, store,
+                                                                                after_rpn_feat=after_rpn_feat)
+            else:
+                raise NotImplementedError("XceptionBody is not built yet (DESIGN.md: next rows)")
+            large_sep_feature = xception_body.large_sep_kernel(backbone_feat, 256, 10 * 7 * 7, False, df,
+                                                               'large_sep_feature', store)
+        finally:
+            conv_ops.MAX_CTAS = 0
+        main.wait_stream(side)  # JOIN
+        rpn_out, rpn_object_score, rpn_bboxes_pred = st['rpn_out'], st['score'], st['boxes']
+        proposals_bboxes, yxhw = st['rois'], st['yxhw']
+        for t in (rpn_object_score, rpn_bboxes_pred, proposals_bboxes, yxhw):
+            t.record_stream(main)
+        cls_score, bboxes_reg, head = xception_body.get_head(
             large_sep_feature, lambda input_, bboxes_, gw_, gh_: ops.ps_roi_align(input_, bboxes_, gw_, gh_, pool_method),
             7, 7, None, proposals_bboxes, params['num_classes'], False, False, 0, df, 'final_head', store,
-            yxhw_bboxes=yxhw)
+            yxhw_bboxes=yxhw, return_fused=True)
         N, R = proposals_bboxes.shape[:2]
-        head = torch.cat([cls_score, bboxes_reg], dim=-1).reshape(N * R, -1).contiguous()
+        head = head.reshape(N * R, -1)
         head_cls_score, head_bboxes_pred = ops.head_decode(proposals_bboxes.reshape(-1, 4), head, 0,
                                                            params['num_classes'], params['num_classes'])
     return {

@@ -93,16 +93,17 @@ def conv2d_fixed_padding(inputs, filters, kernel_size, strides, data_format, ker
 
 
 def bottleneck_block(inputs, filters, is_training, projection_shortcut, strides, data_format, store=None,
-                     dilation_rate=1, preact=None, next_bn=None):
+                     dilation_rate=1, preact=None, next_bn=None, sum_unused=False):
     """Bottleneck block variant for residual networks with BN before convolutions (net/resnet_v2.py:142-184;
     with ``dilation_rate`` > 1 the 3x3 is the dilated SAME conv of xdet_bottleneck_block, net/xdet_body.py:39-81).
 
     ``preact``: relu(bn(inputs)) if the producer of ``inputs`` already computed it; ``next_bn``: batch-norm of the
-    consumer block, to be fused as a second output.  Returns (sum, fused_next_preact_or_None).
+    consumer, to be fused as a second output; ``sum_unused``: nothing reads the raw sum (the consumer only takes
+    relu(bn(sum))), so it is not stored.  Returns (sum_or_None, fused_next_preact_or_None).
     """
     assert not is_training and data_format == "channels_last"
     shortcut = inputs
-    bn1 = _bn(store, inputs.shape[-1])
+    bn1 = _bn(store, preact.shape[-1] if inputs is None else inputs.shape[-1])
     if preact is None:
         preact = batch_norm_relu(inputs, is_training, data_format, store, bn=bn1)
     if projection_shortcut is not None:
@@ -122,15 +123,18 @@ def bottleneck_block(inputs, filters, is_training, projection_shortcut, strides,
     if next_bn is not None:
         sn, bnb = store.folded_bn(next_bn, _BATCH_NORM_EPSILON)
         out2 = torch.empty_like(shortcut)
-        ep.update(out2=out2, scale2=sn, bias2=bnb)
+        ep.update(out2=out2, scale2=sn, bias2=bnb, skip_out=bool(sum_unused))
     y = _run_conv(store, t, k3, 1, **ep)
     return y, out2
 
 
 def block_layer(inputs, filters, block_fn, blocks, strides, is_training, name, data_format, store=None,
-                dilation_rate=1, preact=None):
+                dilation_rate=1, preact=None, fuse_next=False, sum_unused=False):
     """Creates one layer of blocks for the ResNet model (net/resnet_v2.py:187-223; dilated form
-    net/xdet_body.py:84-121).  Returns the layer output (sum of the last block)."""
+    net/xdet_body.py:84-121).  Returns the layer output (sum of the last block); with ``fuse_next`` the
+    batch-norm that follows this layer in creation order (the next layer's first pre-activation, or a trailing
+    batch_norm_relu) is fused into the last convolution and (sum, relu(bn(sum))) is returned; ``sum_unused``
+    then drops the raw sum (None is returned in its place)."""
     filters_out = 4 * filters
 
     def projection_shortcut(x):
@@ -139,11 +143,13 @@ def block_layer(inputs, filters, block_fn, blocks, strides, is_training, name, d
 
     x, pre = inputs, preact
     for i in range(blocks):
+        last = i + 1 == blocks
         # the consumer's first batch-norm is created by the consumer itself; peek its name to fuse it
         x, pre = block_fn(x, filters, is_training, projection_shortcut if i == 0 else None,
                           strides if i == 0 else 1, data_format, store=store, dilation_rate=dilation_rate, preact=pre,
-                          next_bn=_peek_next_bn(store, filters_out) if i + 1 < blocks else None)
-    return x
+                          next_bn=_peek_next_bn(store, filters_out) if (not last or fuse_next) else None,
+                          sum_unused=last and fuse_next and sum_unused)
+    return (x, pre) if fuse_next else x
 
 
 def _peek_next_bn(store, channels, ahead=3):
@@ -180,27 +186,42 @@ def imagenet_resnet_v2(resnet_size, num_classes, data_format=None, store=None):
     return imagenet_resnet_v2_generator(bottleneck_block, model_params[resnet_size], num_classes, data_format, store)
 
 
-def stem(image_nchw_f32, store):
+def stem(image_nchw_f32, store, fuse_next=False):
     """7x7/s2 initial conv with fixed padding + 3x3/s2 SAME max-pool (net/resnet_v2.py:320-328) on the
-    fp32 NCHW image the input pipeline delivers; returns NHWC bf16."""
+    fp32 NCHW image the input pipeline delivers; returns NHWC bf16 (with ``fuse_next`` also relu(bn(.)) of the
+    first block's batch-norm, computed by the pooling kernel)."""
     N, C, H, W = image_nchw_f32.shape
     kern = _conv_kernel(store, C, 64, 7)
     key = ("w", kern[0], "fold")
     if key not in store.derived:
         store.derived[key] = ops.pack_fold_weight(kern[1].permute(3, 2, 0, 1))
     y = ops.conv2d_image_fold(image_nchw_f32.contiguous(), store.derived[key], 64, 7, 7, 2, 3)
-    return ops.maxpool3x3s2_same(y)
+    if not fuse_next:
+        return ops.maxpool3x3s2_same(y)
+    s1, b1 = store.folded_bn(_peek_next_bn(store, 64, ahead=0), _BATCH_NORM_EPSILON)
+    return ops.maxpool3x3s2_same(y, s1, b1)
 
 
-def lighthead_resnet50_body(image_nchw_f32, is_training, store, layers=(3, 4, 6, 3)):
+def lighthead_resnet50_body(image_nchw_f32, is_training, store, layers=(3, 4, 6, 3), after_rpn_feat=None):
     """Light-Head R-CNN backbone on ResNet-50 v2 (composition).
-    -> (rpn_feature [N,h,w,1024], backbone_feature [N,h,w,2048]) NHWC bf16, both after batch_norm_relu."""
+    -> (rpn_feature [N,h,w,1024], backbone_feature [N,h,w,2048]) NHWC bf16, both after batch_norm_relu.
+    Every batch_norm_relu between layers is produced by the convolution (or pooling) kernel that writes its
+    input; raw sums nobody else reads are never stored.  ``after_rpn_feat(rpn_feature)`` is called as soon as
+    the RPN feature exists (the model_fn launches the RPN head and forks the proposal stream there)."""
     df = "channels_last"
-    x = stem(image_nchw_f32, store)
-    x = block_layer(x, 64, bottleneck_block, layers[0], 1, is_training, "block_layer1", df, store)
-    x = block_layer(x, 128, bottleneck_block, layers[1], 2, is_training, "block_layer2", df, store)
-    x = block_layer(x, 256, bottleneck_block, layers[2], 2, is_training, "block_layer3", df, store)
-    rpn_feat = batch_norm_relu(x, is_training, df, store)
-    x = block_layer(x, 512, bottleneck_block, layers[3], 1, is_training, "block_layer4", df, store, dilation_rate=2)
-    backbone = batch_norm_relu(x, is_training, df, store)
+    x, pre = stem(image_nchw_f32, store, fuse_next=True)
+    # layers 2 and 3 start with a projection shortcut that reads relu(bn(x)): the raw x of layers 1 and 2 is unused
+    _, pre = block_layer(x, 64, bottleneck_block, layers[0], 1, is_training, "block_layer1", df, store, preact=pre,
+                         fuse_next=True, sum_unused=True)
+    _, pre = block_layer(None, 128, bottleneck_block, layers[1], 2, is_training, "block_layer2", df, store,
+                         preact=pre, fuse_next=True, sum_unused=True)
+    # after layer 3 the next batch-norm in creation order is the RPN feature's batch_norm_relu
+    x, rpn_feat = block_layer(None, 256, bottleneck_block, layers[2], 2, is_training, "block_layer3", df, store,
+                              preact=pre, fuse_next=True)
+    store.auto_name("batch_normalization")  # consumed by the fused second output above
+    if after_rpn_feat is not None:
+        after_rpn_feat(rpn_feat)
+    _, backbone = block_layer(x, 512, bottleneck_block, layers[3], 1, is_training, "block_layer4", df, store,
+                              dilation_rate=2, fuse_next=True, sum_unused=True)
+    store.auto_name("batch_normalization")
     return rpn_feat, backbone

@@ -103,7 +103,8 @@ def _point2center(proposals_bboxes):
 
 
 def get_head(net_input, pooling_op, grid_width, grid_height, loss_func, proposals_bboxes, num_classes, is_training,
-             using_ohem, ohem_roi_one_image, data_format, var_scope, store=None, yxhw_bboxes=None):
+             using_ohem, ohem_roi_one_image, data_format, var_scope, store=None, yxhw_bboxes=None,
+             return_fused=False):
     """PS-RoI pooling + fc 2048 (ReLU) + fc_cls / fc_loc (reference :477-560), inference branch.
     net_input: thin feature map, fp32 NCHW (PsRoiAlign's contract).  Returns (cls_score [N,R,num_classes],
     bboxes_reg [N,R,4]) fp32."""
@@ -127,4 +128,6 @@ def get_head(net_input, pooling_op, grid_width, grid_height, loss_func, proposal
                   lambda: ops.pack_conv_weight(torch.cat([kc[1], kl[1]], dim=1).t().reshape(num_classes + 4, 2048, 1, 1)))
     b2 = _derived(store, ("b", bc[0], bl[0]), lambda: torch.cat([bc[1], bl[1]]).contiguous())
     out = ops.conv2d_nhwc(h, w2, num_classes + 4, 1, 1, bias=b2, out_layout="nhwc_f32").reshape(N, R, num_classes + 4)
+    if return_fused:  # also the [N,R,num_classes+4] tensor both results are views of
+        return out[..., :num_classes], out[..., num_classes:], out
     return out[..., :num_classes], out[..., num_classes:]

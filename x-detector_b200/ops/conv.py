@@ -25,6 +25,7 @@ class ConvDesc(ctypes.Structure):
         ("out_sn", ctypes.c_longlong), ("out_sy", ctypes.c_longlong), ("out_sx", ctypes.c_longlong),
         ("out_sc", ctypes.c_longlong),
         ("out2", ctypes.c_void_p), ("scale2", ctypes.c_void_p), ("bias2", ctypes.c_void_p), ("block_n", ctypes.c_int),
+        ("max_ctas", ctypes.c_int),
     ]
 
 
@@ -62,10 +63,27 @@ def _ptr(t):
 # bench.py uses it to time the conv/GEMM kernel live and to count algorithmic FLOPs (2*MACs).
 PROFILE = None
 
+# Upper bound on the persistent CTAs of every convolution launched while set (0 = one per SM): the model_fn
+# lowers it while the proposal stream runs beside the backbone so that its one-CTA-per-image kernels find free SMs.
+MAX_CTAS = 0
+
+
+class cta_limit(object):
+    def __init__(self, n):
+        self.n = n
+
+    def __enter__(self):
+        global MAX_CTAS
+        self.prev, MAX_CTAS = MAX_CTAS, self.n
+
+    def __exit__(self, *exc):
+        global MAX_CTAS
+        MAX_CTAS = self.prev
+
 
 def conv2d_nhwc(x, w_packed, cout, kh, kw, *, dilation=(1, 1), padding="SAME", scale=None, bias=None, relu=False,
                 residual=None, out=None, out_layout="nhwc_bf16", out2=None, scale2=None, bias2=None, cin=None,
-                block_n=0, strides=(1, 1), fold_w=None):
+                block_n=0, strides=(1, 1), fold_w=None, skip_out=False):
     """x: [N,H,W,C] bf16 (channel stride may be padded: pass the true ``cin``).  Returns the output tensor
     ([N,Ho,Wo,Cout] bf16 for 'nhwc_bf16', [N,Cout,Ho,Wo] fp32 for 'nchw_f32', [N,Ho,Wo,Cout] fp32 for 'nhwc_f32')."""
     assert x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4
@@ -90,6 +108,9 @@ def conv2d_nhwc(x, w_packed, cout, kh, kw, *, dilation=(1, 1), padding="SAME", s
     if fold_w is not None:
         assert pl == fold_w[1], "the materialised left padding must equal the convolution's"
     dev = x.device
+    if skip_out:
+        assert out2 is not None and out is None and out_layout == "nhwc_bf16"
+        out = out2  # geometry only; the kernel stores nothing through `out`
     if out is None:
         if out_layout == "nhwc_bf16":
             out = torch.empty((N, Ho, Wo, cout), dtype=torch.bfloat16, device=dev)
@@ -105,8 +126,9 @@ def conv2d_nhwc(x, w_packed, cout, kh, kw, *, dilation=(1, 1), padding="SAME", s
         sn, sy, sx, sc = out.stride()
     d = ConvDesc(N, H, W, cin, cs, cout, kh, kw, dh, dw, pt, pl, Ho, Wo, sh, sw, 0 if fold_w is None else 1, in_wp,
                  w_packed.data_ptr(), _ptr(scale), _ptr(bias),
-                 1 if relu else 0, _ptr(residual), out.data_ptr(), 0 if out.dtype == torch.bfloat16 else 1,
-                 sn, sy, sx, sc, _ptr(out2), _ptr(scale2), _ptr(bias2), block_n)
+                 1 if relu else 0, _ptr(residual), None if skip_out else out.data_ptr(),
+                 0 if out.dtype == torch.bfloat16 else 1, sn, sy, sx, sc, _ptr(out2), _ptr(scale2), _ptr(bias2),
+                 block_n, MAX_CTAS)
     with torch.cuda.device(dev):
         if PROFILE is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -116,7 +138,7 @@ def conv2d_nhwc(x, w_packed, cout, kh, kw, *, dilation=(1, 1), padding="SAME", s
             e1.record()
             PROFILE.append((e0, e1, 2.0 * N * Ho * Wo * cout * cin * kh * kw, (N, H, W, cin, cout, kh, kw)))
     _native.check(rc)
-    return out
+    return None if skip_out else out
 
 
 def linear(x2d, w_packed, cout, **kw):
