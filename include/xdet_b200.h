@@ -146,6 +146,17 @@ int xdet_im2col_bf16(const void* d_src, int src_is_nchw_f32, void* d_dst, int N,
                      int KH, int KW, int stride, int pad_top, int pad_left, int Ho, int Wo, int out_cs, void* stream);
 int xdet_maxpool3x3s2_bf16(const void* d_src, void* d_dst, void* d_dst2, const float* d_scale2, const float* d_bias2,
                            int N, int H, int W, int C, int Ho, int Wo, int pad_top, int pad_left, void* stream);
+/* same as xdet_maxpool3x3s2_bf16 plus tf.add(pooled, residual) (Xception entry flow, net/xception_body.py:283-289);
+ * d_residual [N,Ho,Wo,C] bf16 or NULL. */
+int xdet_maxpool3x3s2_add_bf16(const void* d_src, void* d_dst, void* d_dst2, const float* d_scale2, const float* d_bias2,
+                               const void* d_residual, int N, int H, int W, int C, int Ho, int Wo, int pad_top,
+                               int pad_left, void* stream);
+/* Depthwise 3x3 'SAME' stride-1 convolution, depth multiplier 1, dilation >= 1: the depthwise half of
+ * tf.layers.separable_conv2d (net/xception_body.py:224-233,264-272,351-376; its pointwise half is xdet_conv2d_bf16).
+ * d_src/d_dst [N,H,W,C] bf16 NHWC (C % 8 == 0), d_weights [3*3][C] fp32 (TF depthwise_kernel [3,3,C,1] flattened),
+ * relu_in != 0 applies the tf.nn.relu that precedes the layer in relu_separable_bn_block (:223) while loading. */
+int xdet_depthwise3x3_bf16(const void* d_src, const float* d_weights, void* d_dst, int N, int H, int W, int C,
+                           int dilation, int relu_in, void* stream);
 int xdet_affine_relu_bf16(const void* d_src, void* d_dst, const float* d_scale, const float* d_bias, long long pixels,
                           int C, int relu, void* stream);
 int xdet_f32_to_bf16_rows(const float* d_src, void* d_dst, long long rows, int cols, int dst_pitch, void* stream);

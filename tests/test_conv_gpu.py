@@ -189,3 +189,31 @@ def test_deep_k_and_wide_n(ops):
     y2 = ops.conv2d_nhwc(x, ops.pack_conv_weight(w2), 132, 1, 1, out_layout="nhwc_f32")
     ref2 = ref_conv(x, w2, (1, 1), (0, 0), (30, 30)).permute(0, 2, 3, 1)
     assert (y2 - ref2).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("case", [(2, 30, 30, 728, 1, True), (1, 77, 77, 64, 1, False), (2, 25, 31, 1024, 2, False),
+                                  (1, 39, 39, 256, 1, True)])
+def test_depthwise3x3(ops, case):
+    """Depthwise half of tf.layers.separable_conv2d (SAME, depth multiplier 1) vs F.conv2d(groups=C) in fp32."""
+    N, H, W, C, dil, relu_in = case
+    g = torch.Generator(device="cuda").manual_seed(sum(map(int, case)))
+    x = torch.randn((N, H, W, C), generator=g, device="cuda").to(torch.bfloat16)
+    w = torch.randn((3, 3, C), generator=g, device="cuda") / 3.0
+    y = ops.depthwise3x3(x, w.reshape(9, C).contiguous(), dilation=dil, relu_in=relu_in)
+    torch.cuda.synchronize()
+    xi = x.float().permute(0, 3, 1, 2)
+    if relu_in:
+        xi = torch.relu(xi)
+    ref = F.conv2d(xi, w.permute(2, 0, 1).unsqueeze(1), padding=dil, dilation=dil, groups=C).permute(0, 2, 3, 1)
+    assert (y.float() - ref).abs().max().item() < 0.03  # bf16 output rounding
+
+
+def test_maxpool_add(ops):
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn((2, 77, 77, 128), generator=g, device="cuda").to(torch.bfloat16)
+    r = torch.randn((2, 39, 39, 128), generator=g, device="cuda").to(torch.bfloat16)
+    y = ops.maxpool3x3s2_same(x, residual=r)
+    torch.cuda.synchronize()
+    xp = F.pad(x.float().permute(0, 3, 1, 2), (1, 1, 1, 1), value=float("-inf"))  # 77 -> 39: pad (1,1)
+    ref = F.max_pool2d(xp, 3, 2).permute(0, 2, 3, 1) + r.float()
+    assert (y.float() - ref).abs().max().item() < 0.03

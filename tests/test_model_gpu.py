@@ -92,3 +92,51 @@ def test_predictions_are_well_formed(setup):
     assert out["bboxes_predict"].shape == (200, 4) and out["head_cls_score"].shape == (200, 21)
     assert torch.isfinite(out["bboxes_predict"]).all() and torch.isfinite(out["head_cls_score"]).all()
     assert torch.allclose(out["head_cls_score"].sum(-1), torch.ones(200, device="cuda"), atol=1e-4)
+
+
+# ---- Xception backbone (the reference's own XceptionBody) -----------------------------------------------------
+@pytest.fixture(scope="module")
+def setup_xception():
+    assert torch.cuda.is_available()
+    import xdet_b200  # noqa: F401
+    from xdet_b200 import light_head_rfcn_eval as lh
+    params = lh.make_params(train_image_size=160, rpn_pre_nms_top_n=600, rpn_post_nms_top_n=100,
+                            rpn_min_size=16.0 / 160, backbone="xception")
+    model = lh.LightHeadRFCN(params, seed=5)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    images = torch.rand((2, 3, 160, 160), generator=g, device="cuda") * 2 - 1
+    keys = torch.rand((2, 100), generator=g, device="cuda")
+    out = model(images, shuffle_keys=keys)
+    torch.cuda.synchronize()
+    # 160 -> valid 3x3/s2 -> 79 -> valid 3x3 -> 77 -> 39 -> 20 -> 10 ('valid' shifts the sizes)
+    fm = out["rpn_feat_map"].shape[1]
+    anchors = op.layer_anchors((160, 160), (fm, fm), [0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8], [0.1], [1., 2., .5], 16)
+    return model, params, images, keys, out, anchors
+
+
+def test_xception_variable_names(setup_xception):
+    names = set(setup_xception[0].store.state_dict())
+    for n in ["xception_lighthead/block1_conv1/kernel", "xception_lighthead/block1_conv1_bn/gamma",
+              "xception_lighthead/conv2d_1/kernel", "xception_lighthead/batch_normalization_1/moving_mean",
+              "xception_lighthead/block2_sepconv1/depthwise_kernel", "xception_lighthead/block2_sepconv2/pointwise_kernel",
+              "xception_lighthead/block5_sepconv1_bn/beta", "xception_lighthead/block12_sepconv3/depthwise_kernel",
+              "xception_lighthead/conv2d_4/kernel", "xception_lighthead/block13_sepconv2_bn/gamma",
+              "xception_lighthead/block14_sepconv2/pointwise_kernel", "xception_lighthead/rpn_head/conv2d/kernel"]:
+        assert n in names, n
+    assert sum(1 for n in names if n.endswith("depthwise_kernel")) == 34  # 2+2+2 entry, 24 middle, 2+2 exit
+
+
+def test_xception_stagewise_parity(setup_xception):
+    model, params, images, keys, out, anchors = setup_xception
+    sd = model.store.state_dict()
+    assert out["rpn_feat_map"].shape == (2, 10, 10, 728) and out["backbone_feat"].shape == (2, 10, 10, 2048)
+    ref = onet.model(images.cpu().numpy(), sd, params, anchors, shuffle_keys=keys.cpu().numpy())
+    assert rel(out["rpn_feat_map"].float().permute(0, 3, 1, 2).cpu().numpy(), ref["rpn_feat_map"]) < 0.05
+    assert rel(out["backbone_feat"].float().permute(0, 3, 1, 2).cpu().numpy(), ref["backbone_feat"]) < 0.05
+    assert rel(out["large_sep_feature"].cpu().numpy(), ref["large_sep_feature"]) < 0.05
+    inj = {"rpn_object_score": out["rpn_object_score"].cpu().numpy(),
+           "rpn_bboxes_pred": out["rpn_bboxes_pred"].cpu().numpy(),
+           "large_sep_feature": out["large_sep_feature"].cpu().numpy()}
+    ref2 = onet.model(images.cpu().numpy(), sd, params, anchors, shuffle_keys=keys.cpu().numpy(), inject=inj)
+    assert np.array_equal(out["proposals_bboxes"].cpu().numpy().view(np.int32), ref2["proposals_bboxes"].view(np.int32))
+    assert rel(out["cls_score"].cpu().numpy().reshape(-1, 21), ref2["cls_score"]) < 0.03

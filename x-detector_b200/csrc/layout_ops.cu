@@ -76,8 +76,9 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* 
                                                            __nv_bfloat16* __restrict__ dst,
                                                            __nv_bfloat16* __restrict__ dst2,
                                                            const float* __restrict__ scale2,
-                                                           const float* __restrict__ bias2, int N, int H, int W, int C,
-                                                           int Ho, int Wo, int pad_top, int pad_left,
+                                                           const float* __restrict__ bias2,
+                                                           const __nv_bfloat16* __restrict__ residual, int N, int H,
+                                                           int W, int C, int Ho, int Wo, int pad_top, int pad_left,
                                                            long long total_vec) {
   const int C8 = C / 8;
   const long long step = (long long)gridDim.x * blockDim.x;
@@ -104,6 +105,16 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* 
           m[2 * q] = fmaxf(m[2 * q], f.x);
           m[2 * q + 1] = fmaxf(m[2 * q + 1], f.y);
         }
+      }
+    }
+    if (residual) {  // Xception entry flow: tf.add(max_pool(x), residual) (net/xception_body.py:283-289)
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(residual) + e);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(h[q]);
+        m[2 * q] += f.x;
+        m[2 * q + 1] += f.y;
       }
     }
     uint4 o;
@@ -165,6 +176,100 @@ __global__ void __launch_bounds__(256) f32_to_bf16_rows_kernel(const float* __re
     const int c = (int)(e % dst_pitch);
     const long long r = e / dst_pitch;
     dst[e] = __float2bfloat16_rn(c < cols ? __ldg(src + r * cols + c) : 0.f);
+  }
+}
+
+// Depthwise 3x3 'SAME' stride-1 convolution (dilation 1 or 2), depth multiplier 1: the first half of
+// tf.layers.separable_conv2d (net/xception_body.py:224-233,264-272,351-376).  NHWC bf16 in/out, fp32 taps and
+// accumulation, optional ReLU on the input (the tf.nn.relu in front of relu_separable_bn_block, :223).
+// One thread = 8 channels of PX adjacent output pixels of a row (the 3 x (PX+2) input window is loaded once).
+template <int PX>
+__global__ void __launch_bounds__(256) depthwise3x3_kernel(const __nv_bfloat16* __restrict__ src,
+                                                           const float* __restrict__ w /* [9][C] */,
+                                                           __nv_bfloat16* __restrict__ dst, int N, int H, int W, int C,
+                                                           int dil, int relu_in, long long total) {
+  const int C8 = C / 8;
+  const int WX = (W + PX - 1) / PX;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
+    const int c8 = (int)(e % C8);
+    long long t = e / C8;
+    const int xg = (int)(t % WX);
+    t /= WX;
+    const int y = (int)(t % H);
+    const int n = (int)(t / H);
+    const int x0 = xg * PX;
+    float wt[9][8];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(w + (long long)k * C + c8 * 8));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(w + (long long)k * C + c8 * 8) + 1);
+      wt[k][0] = a.x; wt[k][1] = a.y; wt[k][2] = a.z; wt[k][3] = a.w;
+      wt[k][4] = b.x; wt[k][5] = b.y; wt[k][6] = b.z; wt[k][7] = b.w;
+    }
+    float acc[PX][8];
+#pragma unroll
+    for (int p = 0; p < PX; ++p)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int yi = y + (kh - 1) * dil;
+      if (yi < 0 || yi >= H) continue;
+      const __nv_bfloat16* row = src + ((long long)n * H + yi) * W * C + c8 * 8;
+      if (dil == 1) {
+        // contiguous window of PX + 2 pixels
+#pragma unroll
+        for (int i = 0; i < PX + 2; ++i) {
+          const int xi = x0 + i - 1;
+          if (xi < 0 || xi >= W) continue;
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(row + (long long)xi * C));
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = __bfloat1622float2(h[q]);
+            v[2 * q] = relu_in ? fmaxf(f.x, 0.f) : f.x;
+            v[2 * q + 1] = relu_in ? fmaxf(f.y, 0.f) : f.y;
+          }
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int p = i - kw;  // output pixel this input feeds through tap kw
+            if (p >= 0 && p < PX) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(v[j], wt[kh * 3 + kw][j], acc[p][j]);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int xi = x0 + p + (kw - 1) * dil;
+            if (xi < 0 || xi >= W || x0 + p >= W) continue;
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(row + (long long)xi * C));
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 f = __bfloat1622float2(h[q]);
+              const float a = relu_in ? fmaxf(f.x, 0.f) : f.x, b = relu_in ? fmaxf(f.y, 0.f) : f.y;
+              acc[p][2 * q] = fmaf(a, wt[kh * 3 + kw][2 * q], acc[p][2 * q]);
+              acc[p][2 * q + 1] = fmaf(b, wt[kh * 3 + kw][2 * q + 1], acc[p][2 * q + 1]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      if (x0 + p >= W) continue;
+      uint4 o;
+      __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ho[q] = __floats2bfloat162_rn(acc[p][2 * q], acc[p][2 * q + 1]);
+      *reinterpret_cast<uint4*>(dst + (((long long)n * H + y) * W + x0 + p) * C + c8 * 8) = o;
+    }
   }
 }
 
@@ -237,13 +342,21 @@ extern "C" int xdet_im2col_bf16(const void* d_src, int src_is_nchw_f32, void* d_
 extern "C" int xdet_maxpool3x3s2_bf16(const void* d_src, void* d_dst, void* d_dst2, const float* d_scale2,
                                       const float* d_bias2, int N, int H, int W, int C, int Ho, int Wo, int pad_top,
                                       int pad_left, void* stream) {
+  return xdet_maxpool3x3s2_add_bf16(d_src, d_dst, d_dst2, d_scale2, d_bias2, nullptr, N, H, W, C, Ho, Wo, pad_top,
+                                    pad_left, stream);
+}
+
+extern "C" int xdet_maxpool3x3s2_add_bf16(const void* d_src, void* d_dst, void* d_dst2, const float* d_scale2,
+                                          const float* d_bias2, const void* d_residual, int N, int H, int W, int C,
+                                          int Ho, int Wo, int pad_top, int pad_left, void* stream) {
   if (C % 8 != 0) return fail(XDET_EINVAL, "maxpool: C (%d) must be a multiple of 8", C);
   if (d_dst2 && (!d_scale2 || !d_bias2)) return fail(XDET_EINVAL, "maxpool: second output needs scale2/bias2");
   const long long tv = (long long)N * Ho * Wo * (C / 8);
   if (tv <= 0) return XDET_OK;
   maxpool3x3s2_kernel<<<grid_for(tv), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(d_src), reinterpret_cast<__nv_bfloat16*>(d_dst),
-      reinterpret_cast<__nv_bfloat16*>(d_dst2), d_scale2, d_bias2, N, H, W, C, Ho, Wo, pad_top, pad_left, tv);
+      reinterpret_cast<__nv_bfloat16*>(d_dst2), d_scale2, d_bias2, reinterpret_cast<const __nv_bfloat16*>(d_residual),
+      N, H, W, C, Ho, Wo, pad_top, pad_left, tv);
   return after_launch("maxpool3x3s2_kernel");
 }
 
@@ -275,4 +388,17 @@ extern "C" int xdet_image_to_nhwc8_bf16(const float* d_src, void* d_dst, int N, 
   image_to_nhwc8_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
       d_src, reinterpret_cast<__nv_bfloat16*>(d_dst), N, C, H, W, Wp, pad_left, total);
   return after_launch("image_to_nhwc8_kernel");
+}
+
+extern "C" int xdet_depthwise3x3_bf16(const void* d_src, const float* d_weights, void* d_dst, int N, int H, int W, int C,
+                                      int dilation, int relu_in, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0) return fail(XDET_EINVAL, "depthwise3x3: non-positive dimension");
+  if (C % 8 != 0) return fail(XDET_EINVAL, "depthwise3x3: C (%d) must be a multiple of 8", C);
+  if (dilation < 1) return fail(XDET_EINVAL, "depthwise3x3: dilation must be >= 1");
+  constexpr int PX = 4;
+  const long long total = (long long)N * H * ((W + PX - 1) / PX) * (C / 8);
+  depthwise3x3_kernel<PX><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d_src), d_weights, reinterpret_cast<__nv_bfloat16*>(d_dst), N, H, W, C,
+      dilation, relu_in, total);
+  return after_launch("depthwise3x3_kernel");
 }

@@ -34,7 +34,8 @@ _DEFAULTS = dict(
     rpn_fg_ratio=0.5, rpn_match_threshold=0.7, rpn_neg_threshold=0.3, weight_decay=0.0002,
     checkpoint_path='./model/xception', model_scope='xception_lighthead', run_on_cloud=True,
     cloud_checkpoint_path='xception_model/xception_model.ckpt',
-    # not a reference flag: which backbone builder to use (the reference always builds XceptionBody)
+    # not a reference flag: which backbone builder to use ('xception' = the reference's XceptionBody,
+    # 'resnet50' = the ResNet-50 v2 light-head composition of BASELINE configs 2/4)
     backbone='resnet50',
 )
 FLAGS = types.SimpleNamespace(**_DEFAULTS)
@@ -109,8 +110,9 @@ def lighr_head_model_fn(features, labels, mode, params, store=None, shuffle_keys
             if params.get('backbone', 'resnet50') == 'resnet50':
                 rpn_feat_map, backbone_feat = resnet_v2.lighthead_resnet50_body(features, False, store,
                                                                                 after_rpn_feat=after_rpn_feat)
-            else:
-                raise NotImplementedError("XceptionBody is not built yet (DESIGN.md: next rows)")
+            else:  # the reference's own backbone (light_head_rfcn_eval.py:383)
+                rpn_feat_map, backbone_feat = xception_body.XceptionBody(features, params['num_classes'], False, df,
+                                                                         store, after_mid=after_rpn_feat)
             large_sep_feature = xception_body.large_sep_kernel(backbone_feat, 256, 10 * 7 * 7, False, df,
                                                                'large_sep_feature', store)
         finally:

@@ -9,7 +9,9 @@ Fusions relative to the reference graph (all exact re-associations of the same l
     the trailing batch_norm_relu is folded into its epilogue, which writes fp32 NCHW -- the layout and dtype
     PsRoIAlign's contract requires;
   * get_head: fc_cls and fc_loc are one GEMM with num_classes + 4 outputs.
-``XceptionBody`` (the Xception-65 backbone, :236-379) is not built yet.
+``XceptionBody`` (:236-379) runs every separable convolution as a depthwise bandwidth kernel (its leading ReLU
+applied while loading) + a pointwise tcgen05 GEMM whose epilogue carries the batch-norm, the block's residual
+add and, where the graph wants it, a ReLU'd second output; the entry flow's ``max_pool + residual`` is one kernel.
 """
 import torch
 
@@ -40,6 +42,106 @@ def _derived(store, key, fn):
     if key not in store.derived:
         store.derived[key] = fn()
     return store.derived[key]
+
+
+def _bn_named(store, name, channels):
+    return store.folded_bn(store.batch_norm(name, channels), BN_EPSILON)
+
+
+def _conv_named(store, name, cin, filters, k):
+    with store.scope(name):
+        return store.get("kernel", (k, k, cin, filters), store.glorot_normal)
+
+
+def _sep_vars(store, name, cin, filters):
+    with store.scope(name):
+        dw = store.get("depthwise_kernel", (3, 3, cin, 1), store.glorot_normal)
+        pw = store.get("pointwise_kernel", (1, 1, cin, filters), store.glorot_normal)
+    return dw, pw
+
+
+def _separable(store, x, name, filters, relu_in, dilation=1, bn_name=None, **epilogue):
+    """tf.layers.separable_conv2d(3x3, SAME, use_bias=False) + batch_normalization ``name + '_bn'``
+    (reference :220-234): depthwise kernel (ReLU on load when ``relu_in``) -> pointwise GEMM with the BN folded
+    into the epilogue (plus whatever ``epilogue`` adds: relu / residual / out2 ...)."""
+    cin = x.shape[-1]
+    dw, pw = _sep_vars(store, name, cin, filters)
+    w9 = _derived(store, ("dw", dw[0]), lambda: dw[1].reshape(9, cin).float().contiguous())
+    wp = _derived(store, ("w", pw[0]), lambda: ops.pack_conv_weight(pw[1].permute(3, 2, 0, 1)))
+    scale, bias = _bn_named(store, bn_name or (name + "_bn"), filters)
+    t = ops.depthwise3x3(x, w9, dilation=dilation, relu_in=relu_in)
+    return ops.conv2d_nhwc(t, wp, filters, 1, 1, scale=scale, bias=bias, cin=cin, **epilogue)
+
+
+def relu_separable_bn_block(inputs, filters, name_prefix, is_training, data_format, store=None, **epilogue):
+    """relu -> separable_conv2d -> batch_normalization (reference :220-234)."""
+    assert data_format == "channels_last" and not is_training
+    return _separable(store, inputs, name_prefix, filters, relu_in=True, **epilogue)
+
+
+def XceptionBody(input_image, num_classes, is_training=False, data_format='channels_last', store=None,
+                 after_mid=None):
+    """Xception backbone at stride 16 with the last two separable convs atrous (reference :236-379).
+    ``input_image``: fp32 NCHW [N,3,H,W] (what the input pipeline delivers).  Returns
+    (mid_outputs [N,h,w,728], outputs [N,h,w,2048]) NHWC bf16, both ReLU'd as in the reference.
+    ``after_mid(mid_outputs)`` is called as soon as the RPN feature exists (the model_fn forks there)."""
+    assert data_format == "channels_last" and not is_training
+    df = data_format
+    # ---- entry flow: two VALID 3x3 convs (the first strided, on the 3-channel image: fold_w mode) ----
+    k = _conv_named(store, "block1_conv1", input_image.shape[1], 32, 3)
+    wf = _derived(store, ("w", k[0], "fold"), lambda: ops.pack_fold_weight(k[1].permute(3, 2, 0, 1)))
+    sc, bi = _bn_named(store, "block1_conv1_bn", 32)
+    x = ops.conv2d_image_fold(input_image.contiguous(), wf, 32, 3, 3, 2, 0, scale=sc, bias=bi, relu=True)
+    k = _conv_named(store, "block1_conv2", 32, 64, 3)
+    w = _derived(store, ("w", k[0]), lambda: ops.pack_conv_weight(k[1].permute(3, 2, 0, 1)))
+    sc, bi = _bn_named(store, "block1_conv2_bn", 64)
+    x = ops.conv2d_nhwc(x, w, 64, 3, 3, padding="VALID", scale=sc, bias=bi, relu=True)
+
+    def strided_residual(x, idx, filters):
+        """1x1 / stride 2 'same' conv + batch-norm on the block input (:262-266, :291-296, :311-316)."""
+        k = _conv_named(store, "conv2d_%d" % idx, x.shape[-1], filters, 1)
+        w = _derived(store, ("w", k[0]), lambda: ops.pack_conv_weight(k[1].permute(3, 2, 0, 1)))
+        sc, bi = _bn_named(store, "batch_normalization_%d" % idx, filters)
+        N, H, W, _ = x.shape
+        return ops.conv2d_nhwc(x, w, filters, 1, 1, padding=(0, 0, -(-H // 2), -(-W // 2)), strides=(2, 2), scale=sc,
+                               bias=bi)
+
+    residual = strided_residual(x, 1, 128)
+    x = _separable(store, x, "block2_sepconv1", 128, relu_in=False)  # its input is already ReLU'd (:268)
+    x = relu_separable_bn_block(x, 128, "block2_sepconv2", is_training, df, store)
+    x = ops.maxpool3x3s2_same(x, residual=residual)  # block2_pool + residual_add_0
+    for blk, idx, filters in ((3, 2, 256), (4, 3, 728)):
+        residual = strided_residual(x, idx, filters)
+        x = relu_separable_bn_block(x, filters, "block%d_sepconv1" % blk, is_training, df, store)
+        x = relu_separable_bn_block(x, filters, "block%d_sepconv2" % blk, is_training, df, store)
+        x = ops.maxpool3x3s2_same(x, residual=residual)
+    # ---- middle flow: 8 x (3 x relu-sepconv-bn) + identity (:325-334) ----
+    mid_outputs = None
+    for index in range(8):
+        prefix = "block%d" % (index + 5)
+        residual = x
+        t = relu_separable_bn_block(x, 728, prefix + "_sepconv1", is_training, df, store)
+        t = relu_separable_bn_block(t, 728, prefix + "_sepconv2", is_training, df, store)
+        if index < 7:
+            x = relu_separable_bn_block(t, 728, prefix + "_sepconv3", is_training, df, store, residual=residual)
+        else:  # the last sum is also needed ReLU'd: mid_outputs = relu(x) (before_block13_act, :336)
+            mid_outputs = torch.empty_like(residual)
+            one, zero = _derived(store, ("unit", 728), lambda: (torch.ones(728, device=x.device),
+                                                                  torch.zeros(728, device=x.device)))
+            x = relu_separable_bn_block(t, 728, prefix + "_sepconv3", is_training, df, store, residual=residual,
+                                        out2=mid_outputs, scale2=one, bias2=zero)
+    if after_mid is not None:
+        after_mid(mid_outputs)
+    # ---- exit flow with the stride removed and dilation 2 in block14 (:337-376) ----
+    k = _conv_named(store, "conv2d_4", 728, 1024, 1)
+    w = _derived(store, ("w", k[0]), lambda: ops.pack_conv_weight(k[1].permute(3, 2, 0, 1)))
+    sc, bi = _bn_named(store, "batch_normalization_4", 1024)
+    residual = ops.conv2d_nhwc(x, w, 1024, 1, 1, scale=sc, bias=bi)
+    t = relu_separable_bn_block(x, 728, "block13_sepconv1", is_training, df, store)
+    x = relu_separable_bn_block(t, 1024, "block13_sepconv2", is_training, df, store, residual=residual)
+    x = _separable(store, x, "block14_sepconv1", 1536, relu_in=False, dilation=2, relu=True)
+    outputs = _separable(store, x, "block14_sepconv2", 2048, relu_in=False, dilation=2, relu=True)
+    return mid_outputs, outputs
 
 
 def get_rpn(net_input, num_anchors, is_training, data_format, var_scope, store=None):

@@ -29,19 +29,33 @@ def im2col(x, kh, kw, stride, pad_top, pad_left, Ho, Wo, *, nchw_f32=False, cin=
     return out
 
 
-def maxpool3x3s2_same(x, scale2=None, bias2=None):
-    """tf.layers.max_pooling2d(3, 2, 'SAME') on NHWC bf16; optionally also returns relu(y*scale2+bias2)."""
+def maxpool3x3s2_same(x, scale2=None, bias2=None, residual=None):
+    """tf.layers.max_pooling2d(3, 2, 'SAME') on NHWC bf16 (+ ``residual`` added to the pooled value); optionally
+    also returns relu(y*scale2+bias2)."""
     N, H, W, C = x.shape
     Ho, Wo = -(-H // 2), -(-W // 2)
     pt, pl = same_pad(H, 3, 1, 2), same_pad(W, 3, 1, 2)
     out = torch.empty((N, Ho, Wo, C), dtype=torch.bfloat16, device=x.device)
     out2 = torch.empty_like(out) if scale2 is not None else None
-    rc = _native.lib().xdet_maxpool3x3s2_bf16(x.data_ptr(), out.data_ptr(), None if out2 is None else out2.data_ptr(),
-                                              None if scale2 is None else scale2.data_ptr(),
-                                              None if bias2 is None else bias2.data_ptr(), N, H, W, C, Ho, Wo, pt, pl,
-                                              _st())
+    if residual is not None:
+        assert residual.shape == out.shape and residual.dtype == torch.bfloat16 and residual.is_contiguous()
+    rc = _native.lib().xdet_maxpool3x3s2_add_bf16(
+        x.data_ptr(), out.data_ptr(), None if out2 is None else out2.data_ptr(),
+        None if scale2 is None else scale2.data_ptr(), None if bias2 is None else bias2.data_ptr(),
+        None if residual is None else residual.data_ptr(), N, H, W, C, Ho, Wo, pt, pl, _st())
     _native.check(rc)
     return (out, out2) if out2 is not None else out
+
+
+def depthwise3x3(x, w9c, dilation=1, relu_in=False):
+    """Depthwise 3x3 SAME conv (depth multiplier 1) on NHWC bf16; ``w9c`` = [9, C] fp32 taps (kh-major)."""
+    N, H, W, C = x.shape
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and w9c.dtype == torch.float32 and w9c.shape == (9, C)
+    out = torch.empty_like(x)
+    rc = _native.lib().xdet_depthwise3x3_bf16(x.data_ptr(), w9c.data_ptr(), out.data_ptr(), N, H, W, C, dilation,
+                                              1 if relu_in else 0, _st())
+    _native.check(rc)
+    return out
 
 
 def affine_relu(x, scale, bias, relu=True):
