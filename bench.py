@@ -82,7 +82,7 @@ def dist_env():
 class LightHeadResnet50:
     name = "Light-Head R-CNN ResNet-50 inference, batch=8 per GPU, 480x480 synthetic"
     metric, unit, dtype = "images_per_sec_480x480", "images/s", "bf16"
-    batch, size = 8, 480
+    batch, size, backbone = 8, 480, "resnet50"
 
     def images(self, rank):
         rng = np.random.default_rng(1 + 1000 * rank)  # U(-1,1): img*2 - mean/127.5 (common_preprocessing.py:391-392)
@@ -110,7 +110,7 @@ class LightHeadResnet50:
                 dist.barrier()
             torch.cuda.synchronize()
 
-        params = lh.make_params(train_image_size=self.size)
+        params = lh.make_params(train_image_size=self.size, backbone=self.backbone, rpn_min_size=16.0 / self.size)
         model = lh.LightHeadRFCN(params, seed=0)
         imgs_h = torch.from_numpy(self.images(rank)).pin_memory()
         imgs_d = imgs_h.cuda()
@@ -251,7 +251,8 @@ class LightHeadResnet50:
         # eval flags of the reference (light_head_rfcn_eval.py:95-115); variables are created on demand by the
         # oracle with the reference's shapes (random: no checkpoint exists offline)
         params = {"model_scope": "xception_lighthead", "num_classes": 21, "rpn_pre_nms_top_n": 5000,
-                  "rpn_post_nms_top_n": 1000, "rpn_nms_thres": 0.7, "rpn_min_size": 16.0 / self.size}
+                  "rpn_post_nms_top_n": 1000, "rpn_nms_thres": 0.7, "rpn_min_size": 16.0 / self.size,
+                  "backbone": self.backbone}
         sd = {}
         base = cpu_network_baseline(self, params, sd, reps=max(1, args.steps), warmup=1 if args.warmup else 0)
         print(json.dumps({
@@ -438,7 +439,20 @@ class PsroiSweepTop:
             dist.destroy_process_group()
 
 
-WORKLOADS = {"lighthead_resnet50": LightHeadResnet50, "psroi_sweep_top": PsroiSweepTop}
+class LightHeadXception800(LightHeadResnet50):
+    """BASELINE.json configs[2]: the reference's own backbone (XceptionBody), batch 32, 800x800."""
+    name = "Light-Head R-CNN Xception inference, batch=32 per GPU, 800x800 synthetic"
+    metric = "images_per_sec_800x800"
+    batch, size, backbone = 32, 800, "xception"
+
+
+class LightHeadXception480(LightHeadResnet50):
+    name = "Light-Head R-CNN Xception inference, batch=8 per GPU, 480x480 synthetic"
+    batch, size, backbone = 8, 480, "xception"
+
+
+WORKLOADS = {"lighthead_resnet50": LightHeadResnet50, "lighthead_xception_800": LightHeadXception800,
+             "lighthead_xception_480": LightHeadXception480, "psroi_sweep_top": PsroiSweepTop}
 DEFAULT_WORKLOAD = "lighthead_resnet50"
 
 
@@ -454,8 +468,6 @@ def main():
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]()
     if args.impl == "reference":
-        if args.workload == "lighthead_resnet50" and args.steps > 3:
-            args.steps = 3  # each CPU step is a whole image through the fp32 graph: keep the arm to a few minutes
         wl.run_reference(args)
     else:
         wl.run_own(args)

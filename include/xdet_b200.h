@@ -151,7 +151,7 @@ int xdet_maxpool3x3s2_bf16(const void* d_src, void* d_dst, void* d_dst2, const f
 int xdet_maxpool3x3s2_add_bf16(const void* d_src, void* d_dst, void* d_dst2, const float* d_scale2, const float* d_bias2,
                                const void* d_residual, int N, int H, int W, int C, int Ho, int Wo, int pad_top,
                                int pad_left, void* stream);
-/* Depthwise 3x3 'SAME' stride-1 convolution, depth multiplier 1, dilation >= 1: the depthwise half of
+/* Depthwise 3x3 'SAME' stride-1 convolution, depth multiplier 1, dilation 1 or 2: the depthwise half of
  * tf.layers.separable_conv2d (net/xception_body.py:224-233,264-272,351-376; its pointwise half is xdet_conv2d_bf16).
  * d_src/d_dst [N,H,W,C] bf16 NHWC (C % 8 == 0), d_weights [3*3][C] fp32 (TF depthwise_kernel [3,3,C,1] flattened),
  * relu_in != 0 applies the tf.nn.relu that precedes the layer in relu_separable_bn_block (:223) while loading. */

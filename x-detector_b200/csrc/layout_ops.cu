@@ -88,23 +88,33 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* 
     const int xo = (int)(pix % Wo);
     const int yo = (int)((pix / Wo) % Ho);
     const int n = (int)(pix / ((long long)Wo * Ho));
+    // all nine window loads first (independent, in flight together), then the reduction
+    uint4 win[9];
+    bool ok[9];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int yi = yo * 2 + kh - pad_top;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int xi = xo * 2 + kw - pad_left;
+        ok[kh * 3 + kw] = yi >= 0 && yi < H && xi >= 0 && xi < W;
+        win[kh * 3 + kw] = ok[kh * 3 + kw]
+                               ? __ldg(reinterpret_cast<const uint4*>(src + (((long long)n * H + yi) * W + xi) * C) + c8)
+                               : make_uint4(0, 0, 0, 0);
+      }
+    }
     float m[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) m[j] = -FLT_MAX;
-    for (int kh = 0; kh < 3; ++kh) {
-      const int yi = yo * 2 + kh - pad_top;
-      if (yi < 0 || yi >= H) continue;
-      for (int kw = 0; kw < 3; ++kw) {
-        const int xi = xo * 2 + kw - pad_left;
-        if (xi < 0 || xi >= W) continue;
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (((long long)n * H + yi) * W + xi) * C) + c8);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 f = __bfloat1622float2(h[q]);
-          m[2 * q] = fmaxf(m[2 * q], f.x);
-          m[2 * q + 1] = fmaxf(m[2 * q + 1], f.y);
-        }
+    for (int k = 0; k < 9; ++k) {
+      if (!ok[k]) continue;
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&win[k]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(h[q]);
+        m[2 * q] = fmaxf(m[2 * q], f.x);
+        m[2 * q + 1] = fmaxf(m[2 * q + 1], f.y);
       }
     }
     if (residual) {  // Xception entry flow: tf.add(max_pool(x), residual) (net/xception_body.py:283-289)
@@ -182,93 +192,71 @@ __global__ void __launch_bounds__(256) f32_to_bf16_rows_kernel(const float* __re
 // Depthwise 3x3 'SAME' stride-1 convolution (dilation 1 or 2), depth multiplier 1: the first half of
 // tf.layers.separable_conv2d (net/xception_body.py:224-233,264-272,351-376).  NHWC bf16 in/out, fp32 taps and
 // accumulation, optional ReLU on the input (the tf.nn.relu in front of relu_separable_bn_block, :223).
-// One thread = 8 channels of PX adjacent output pixels of a row (the 3 x (PX+2) input window is loaded once).
-template <int PX>
-__global__ void __launch_bounds__(256) depthwise3x3_kernel(const __nv_bfloat16* __restrict__ src,
+// HBM/L2-bandwidth work: one thread = ONE channel pair (4 bytes) of PX adjacent output pixels of a row, so a warp
+// reads/writes 128 contiguous bytes per pixel; the whole 3 x (PX + 2*DIL) input window is fetched up front
+// (30-36 independent 4-byte loads in flight per thread), then consumed from registers.
+template <int PX, int DIL>
+__global__ void __launch_bounds__(256, 3) depthwise3x3_kernel(const __nv_bfloat16* __restrict__ src,
                                                            const float* __restrict__ w /* [9][C] */,
                                                            __nv_bfloat16* __restrict__ dst, int N, int H, int W, int C,
-                                                           int dil, int relu_in, long long total) {
-  const int C8 = C / 8;
+                                                           int relu_in, long long total) {
+  constexpr int WIN = PX + 2 * DIL;
+  const int C2 = C / 2;
   const int WX = (W + PX - 1) / PX;
   const long long step = (long long)gridDim.x * blockDim.x;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
-    const int c8 = (int)(e % C8);
-    long long t = e / C8;
+    const int c2 = (int)(e % C2);
+    long long t = e / C2;
     const int xg = (int)(t % WX);
     t /= WX;
     const int y = (int)(t % H);
     const int n = (int)(t / H);
     const int x0 = xg * PX;
-    float wt[9][8];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(w + (long long)k * C + c8 * 8));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(w + (long long)k * C + c8 * 8) + 1);
-      wt[k][0] = a.x; wt[k][1] = a.y; wt[k][2] = a.z; wt[k][3] = a.w;
-      wt[k][4] = b.x; wt[k][5] = b.y; wt[k][6] = b.z; wt[k][7] = b.w;
-    }
-    float acc[PX][8];
-#pragma unroll
-    for (int p = 0; p < PX; ++p)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(src) + c2;
+    uint32_t in[3][WIN];
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
-      const int yi = y + (kh - 1) * dil;
-      if (yi < 0 || yi >= H) continue;
-      const __nv_bfloat16* row = src + ((long long)n * H + yi) * W * C + c8 * 8;
-      if (dil == 1) {
-        // contiguous window of PX + 2 pixels
+      const int yi = y + (kh - 1) * DIL;
+      const bool row_ok = yi >= 0 && yi < H;
+      const long long roff = ((long long)n * H + (row_ok ? yi : 0)) * W;
 #pragma unroll
-        for (int i = 0; i < PX + 2; ++i) {
-          const int xi = x0 + i - 1;
-          if (xi < 0 || xi >= W) continue;
-          const uint4 u = __ldg(reinterpret_cast<const uint4*>(row + (long long)xi * C));
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-          float v[8];
+      for (int i = 0; i < WIN; ++i) {
+        const int xi = x0 + i - DIL;
+        in[kh][i] = (row_ok && xi >= 0 && xi < W) ? __ldg(base + (roff + xi) * C2) : 0u;
+      }
+    }
+    float2 wt[9];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float2 f = __bfloat1622float2(h[q]);
-            v[2 * q] = relu_in ? fmaxf(f.x, 0.f) : f.x;
-            v[2 * q + 1] = relu_in ? fmaxf(f.y, 0.f) : f.y;
-          }
+    for (int k = 0; k < 9; ++k) wt[k] = __ldg(reinterpret_cast<const float2*>(w + (long long)k * C) + c2);
+    float2 acc[PX];
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const int p = i - kw;  // output pixel this input feeds through tap kw
-            if (p >= 0 && p < PX) {
+    for (int p = 0; p < PX; ++p) acc[p] = make_float2(0.f, 0.f);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(v[j], wt[kh * 3 + kw][j], acc[p][j]);
-            }
-          }
+    for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+      for (int i = 0; i < WIN; ++i) {
+        float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&in[kh][i]));
+        if (relu_in) {
+          v.x = fmaxf(v.x, 0.f);
+          v.y = fmaxf(v.y, 0.f);
         }
-      } else {
 #pragma unroll
-        for (int p = 0; p < PX; ++p) {
-#pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const int xi = x0 + p + (kw - 1) * dil;
-            if (xi < 0 || xi >= W || x0 + p >= W) continue;
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(row + (long long)xi * C));
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float2 f = __bfloat1622float2(h[q]);
-              const float a = relu_in ? fmaxf(f.x, 0.f) : f.x, b = relu_in ? fmaxf(f.y, 0.f) : f.y;
-              acc[p][2 * q] = fmaf(a, wt[kh * 3 + kw][2 * q], acc[p][2 * q]);
-              acc[p][2 * q + 1] = fmaf(b, wt[kh * 3 + kw][2 * q + 1], acc[p][2 * q + 1]);
-            }
+        for (int kw = 0; kw < 3; ++kw) {
+          const int p = i - kw * DIL;  // output pixel fed by this input through tap kw
+          if (p >= 0 && p < PX) {
+            acc[p].x = fmaf(v.x, wt[kh * 3 + kw].x, acc[p].x);
+            acc[p].y = fmaf(v.y, wt[kh * 3 + kw].y, acc[p].y);
           }
         }
       }
     }
+    uint32_t* orow = reinterpret_cast<uint32_t*>(dst) + (((long long)n * H + y) * W + x0) * C2 + c2;
 #pragma unroll
     for (int p = 0; p < PX; ++p) {
-      if (x0 + p >= W) continue;
-      uint4 o;
-      __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) ho[q] = __floats2bfloat162_rn(acc[p][2 * q], acc[p][2 * q + 1]);
-      *reinterpret_cast<uint4*>(dst + (((long long)n * H + y) * W + x0 + p) * C + c8 * 8) = o;
+      if (x0 + p < W) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(acc[p].x, acc[p].y);
+        orow[(long long)p * C2] = *reinterpret_cast<const uint32_t*>(&h);
+      }
     }
   }
 }
@@ -394,11 +382,15 @@ extern "C" int xdet_depthwise3x3_bf16(const void* d_src, const float* d_weights,
                                       int dilation, int relu_in, void* stream) {
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0) return fail(XDET_EINVAL, "depthwise3x3: non-positive dimension");
   if (C % 8 != 0) return fail(XDET_EINVAL, "depthwise3x3: C (%d) must be a multiple of 8", C);
-  if (dilation < 1) return fail(XDET_EINVAL, "depthwise3x3: dilation must be >= 1");
-  constexpr int PX = 4;
-  const long long total = (long long)N * H * ((W + PX - 1) / PX) * (C / 8);
-  depthwise3x3_kernel<PX><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(d_src), d_weights, reinterpret_cast<__nv_bfloat16*>(d_dst), N, H, W, C,
-      dilation, relu_in, total);
+  if (dilation != 1 && dilation != 2) return fail(XDET_EINVAL, "depthwise3x3: dilation must be 1 or 2");
+  constexpr int PX = 8;
+  const long long total = (long long)N * H * ((W + PX - 1) / PX) * (C / 2);
+  const unsigned grid = grid_for(total);
+  const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(d_src);
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(d_dst);
+  if (dilation == 1)
+    depthwise3x3_kernel<PX, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(src, d_weights, dst, N, H, W, C, relu_in, total);
+  else
+    depthwise3x3_kernel<PX, 2><<<grid, 256, 0, (cudaStream_t)stream>>>(src, d_weights, dst, N, H, W, C, relu_in, total);
   return after_launch("depthwise3x3_kernel");
 }
