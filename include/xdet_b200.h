@@ -122,6 +122,7 @@ typedef struct {
   const float* scale2;
   const float* bias2;
   int block_n;  /* 0 = auto; otherwise the N tile (multiple of 16, <= 256; of 64 for bf16 NHWC outputs) */
+  int epi_groups; /* 0 = auto; 1 or 2 epilogue warpgroups (tuning / tests) */
   int max_ctas; /* 0 = one persistent CTA per SM; otherwise an upper bound (leaves SMs to a concurrent stream) */
 } xdet_conv_desc;
 int xdet_conv2d_bf16(const void* d_in, const xdet_conv_desc* desc, void* stream);

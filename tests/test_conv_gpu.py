@@ -144,8 +144,9 @@ def test_image_fold_conv(ops, shape):
     assert (y - ref).abs().max().item() < 2e-3
 
 
+@pytest.mark.parametrize("epi_groups", [1, 2])
 @pytest.mark.parametrize("block_n", [0, 64, 128, 256])
-def test_persistent_many_tiles_residual_chain(ops, block_n):
+def test_persistent_many_tiles_residual_chain(ops, block_n, epi_groups):
     """More tiles than SMs (each CTA walks several tiles): accumulator double buffering, the residual prefetch
     chain across tiles, clipped channel tail (728 = 11*64 + 24), every N-tile width."""
     N, H, W, Cin, Cout = 8, 60, 60, 128, 728
@@ -159,17 +160,27 @@ def test_persistent_many_tiles_residual_chain(ops, block_n):
     res = torch.randn((N, H, W, Cout), generator=g, device="cuda").to(torch.bfloat16)
     out2 = torch.full((N, H, W, Cout), 7.0, dtype=torch.bfloat16, device="cuda")
     y = ops.conv2d_nhwc(x, ops.pack_conv_weight(w), Cout, 1, 1, scale=scale, bias=bias, residual=res, out2=out2,
-                        scale2=scale2, bias2=bias2, block_n=block_n)
+                        scale2=scale2, bias2=bias2, block_n=block_n, epi_groups=epi_groups)
     torch.cuda.synchronize()
     acc = ref_conv(x, w, (1, 1), (0, 0), (H, W)).permute(0, 2, 3, 1)
     v = acc * scale + bias + res.float()
     assert (y.float() - v).abs().max().item() < 0.05
     assert (out2.float() - torch.relu(v * scale2 + bias2)).abs().max().item() < 0.06
+    # second output only (raw sum not stored), and plain (no residual) with two groups
+    o2 = torch.full((N, H, W, Cout), 7.0, dtype=torch.bfloat16, device="cuda")
+    ops.conv2d_nhwc(x, ops.pack_conv_weight(w), Cout, 1, 1, scale=scale, bias=bias, residual=res, out2=o2,
+                    scale2=scale2, bias2=bias2, block_n=block_n, epi_groups=epi_groups, skip_out=True)
+    yp = ops.conv2d_nhwc(x, ops.pack_conv_weight(w), Cout, 1, 1, scale=scale, bias=bias, relu=True, block_n=block_n,
+                         epi_groups=epi_groups)
+    torch.cuda.synchronize()
+    assert torch.equal(o2, out2)
+    assert (yp.float() - torch.relu(acc * scale + bias)).abs().max().item() < 0.05
     # spatial (non-flattened) tiles with ragged edges + residual: 3x3 on 30x30
     w3 = torch.randn((256, Cin, 3, 3), generator=g, device="cuda") / (9 * Cin) ** 0.5
     x3 = x[:, :30, :30].contiguous()
     r3 = torch.randn((N, 30, 30, 256), generator=g, device="cuda").to(torch.bfloat16)
-    y3 = ops.conv2d_nhwc(x3, ops.pack_conv_weight(w3), 256, 3, 3, residual=r3, relu=True, block_n=block_n)
+    y3 = ops.conv2d_nhwc(x3, ops.pack_conv_weight(w3), 256, 3, 3, residual=r3, relu=True, block_n=block_n,
+                         epi_groups=epi_groups)
     torch.cuda.synchronize()
     ref3 = torch.relu(ref_conv(x3, w3, (1, 1), (1, 1), (30, 30)).permute(0, 2, 3, 1) + r3.float())
     assert (y3.float() - ref3).abs().max().item() < 0.05

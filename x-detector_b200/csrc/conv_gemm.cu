@@ -46,14 +46,16 @@ namespace {
 constexpr int kBM = 128;          // rows (output pixels) per tile
 constexpr int kBK = 64;           // K per stage: 64 bf16 = one 128-byte swizzle atom
 constexpr int kUmmaK = 16;        // K per tcgen05.mma for 16-bit inputs
-constexpr int kGemmThreads = 192; // 6 warps: TMA, MMA, 4x epilogue
+constexpr int kGemmThreads = 320; // 10 warps: TMA, MMA, 2 epilogue groups x 4
 constexpr int kEpiThreads = 128;
 constexpr int kMaxStages = 8;
 constexpr int kMaxBN = 256;
+constexpr int kMaxSlots = 3;
 constexpr uint32_t kChunkBytes = kBM * 64 * 2;  // one 128 x 64-channel bf16 staging tile
 // dynamic shared memory per CTA: leaves ~16 KB of the SM for small CTAs of concurrent kernels (the NMS
 // bit-matrix kernel of the proposal stream runs beside the backbone convolutions)
-constexpr size_t kSmemCap = 211 * 1024;
+constexpr size_t kSmemCapShared = 211 * 1024;  // while another stream runs beside the convolutions (max_ctas set)
+constexpr size_t kSmemCapAlone = 227 * 1024;
 
 struct ConvGemmArgs {
   int tiles_x, tiles_y, n_tiles_n, total_tiles;
@@ -66,6 +68,7 @@ struct ConvGemmArgs {
   const float* bias;
   int relu;
   int tma_epilogue, has_res, has_out2, skip_out;
+  int epi_groups, n_slots, n_out2;  // epilogue warpgroups; staging slots / second-output buffers per group
   void* out;
   int out_fp32;
   long long out_sn, out_sy, out_sx, out_sc;
@@ -105,16 +108,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t b_bytes = (uint32_t)p.BN * kBK * 2;
   const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
   unsigned char* tiles = smem;
-  unsigned char* cbuf = smem + (size_t)p.stages * stage_bytes;
-  unsigned char* c2buf = cbuf + (p.tma_epilogue ? 2 * kChunkBytes : 0);
-  unsigned char* rbuf = c2buf + (p.has_out2 ? 2 * kChunkBytes : 0);
-  float* sbuf = reinterpret_cast<float*>(rbuf + (p.has_res ? 2 * kChunkBytes : 0));  // [4][kMaxBN]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sbuf + 4 * kMaxBN);
+  unsigned char* ebuf = smem + (size_t)p.stages * stage_bytes;  // [groups][n_slots + n_out2][16 KB]
+  float* sbuf = reinterpret_cast<float*>(ebuf + (size_t)p.epi_groups * (p.n_slots + p.n_out2) * kChunkBytes);  // [2][4][kMaxBN]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sbuf + 2 * 4 * kMaxBN);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full_bar = empty_bar + kMaxStages;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
-  uint64_t* res_full_bar = tmem_empty_bar + 2;       // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full_bar + 2);
+  uint64_t* res_full_bar = tmem_empty_bar + 2;       // [2 groups][kMaxSlots]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full_bar + 2 * kMaxSlots);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -133,9 +134,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       for (int s = 0; s < 2; ++s) {
         ptx::mbar_init(&tmem_full_bar[s], 1);
-        ptx::mbar_init(&tmem_empty_bar[s], 4);  // one arrival per epilogue warp
-        ptx::mbar_init(&res_full_bar[s], 1);
+        ptx::mbar_init(&tmem_empty_bar[s], 4 * p.epi_groups);  // one arrival per epilogue warp
       }
+      for (int s = 0; s < 2 * kMaxSlots; ++s) ptx::mbar_init(&res_full_bar[s], 1);
       ptx::fence_mbar_init();
     }
     __syncwarp();
@@ -207,109 +208,128 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
-  } else {
-    // ===== epilogue: warps 2..5, TMEM quadrant = warp % 4 =====
+  } else if (((warp - 2) >> 2) < p.epi_groups) {
+    // ===== epilogue: warps 2..5 (group 0) and 6..9 (group 1), TMEM quadrant = warp % 4 =====
+    // The 64-channel chunks of the tile sequence are dealt round-robin to the groups; each group owns its
+    // staging slots, scale/bias vectors, named barrier and TMA store/load stream.
+    const int grp = (warp - 2) >> 2;
     const int quad = warp & 3;
-    const int m = quad * 32 + lane;  // row of the tile == TMEM lane
-    const int e = threadIdx.x - 64;  // 0..127
-    const bool leader = (e == 0);    // issues the epilogue's TMA loads / stores
+    const int m = quad * 32 + lane;                        // row of the tile == TMEM lane
+    const int e = (warp - 2 - grp * 4) * 32 + lane;        // 0..127 inside the group
+    const bool leader = (e == 0);                          // issues the group's TMA loads / stores
+    const uint32_t bar_id = 1u + (uint32_t)grp;
     const int nchunks = (p.BN + 63) / 64;
+    const int G = p.epi_groups;
     const uint32_t swz = (uint32_t)(m & 7);
+    unsigned char* gbase = ebuf + (size_t)grp * (size_t)(p.n_slots + p.n_out2) * kChunkBytes;
+    float* sb = sbuf + grp * 4 * kMaxBN;
+    uint64_t* res_bar = res_full_bar + grp * kMaxSlots;
     int as = 0;
     uint32_t aphase = 0;
-    int g = 0;  // running 64-channel chunk counter of this CTA (staging buffer = g & 1)
+    int q = 0;               // chunks this group has processed (slot = q % n_slots)
+    uint32_t res_phase = 0;  // bit s = parity of the next fill of residual slot s
 
-    // coordinates of the residual chunk with running index gq (may belong to a later tile of this CTA)
-    auto issue_residual = [&](int gq) {
-      const int ti = gq / nchunks, c = gq - ti * nchunks;
+    // residual tile of this group's qq-th chunk (running chunk index j = qq*G + grp over the CTA's tile sequence)
+    auto issue_residual = [&](int qq) {
+      const int j = qq * G + grp;
+      const int ti = j / nchunks, c = j - ti * nchunks;
       const long long t = (long long)blockIdx.x + (long long)ti * gridDim.x;
       if (t >= p.total_tiles) return;
       const TileCoord tc = decode_tile(p, (int)t);
       if (tc.n0 + c * 64 >= p.Cout) return;  // chunk fully outside: the consumer skips it as well
-      const int b = gq & 1;
-      ptx::mbar_arrive_expect_tx(&res_full_bar[b], kChunkBytes);
-      ptx::tma_load_4d(rbuf + (size_t)b * kChunkBytes, &map_res, &res_full_bar[b], tc.n0 + c * 64, tc.x0, tc.y0,
-                       tc.img);
+      const int sl = qq % p.n_slots;
+      ptx::mbar_arrive_expect_tx(&res_bar[sl], kChunkBytes);
+      ptx::tma_load_4d(gbase + (size_t)sl * kChunkBytes, &map_res, &res_bar[sl], tc.n0 + c * 64, tc.x0, tc.y0, tc.img);
     };
     if (p.has_res && leader) {
       issue_residual(0);
       issue_residual(1);
     }
-    uint32_t res_phase = 0;  // bit b = parity of the next fill of residual buffer b
 
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    int ti = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
       const TileCoord tc = decode_tile(p, t);
-      // per-tile scale / bias vectors -> shared memory (previous tile's readers passed their last barrier)
-      for (int i = e; i < p.BN; i += kEpiThreads) {
-        const int c = tc.n0 + i;
-        const bool ok = c < p.Cout;
-        sbuf[i] = (ok && p.scale) ? __ldg(p.scale + c) : 1.f;
-        sbuf[kMaxBN + i] = (ok && p.bias) ? __ldg(p.bias + c) : 0.f;
-        if (p.has_out2) {
-          sbuf[2 * kMaxBN + i] = ok ? __ldg(p.scale2 + c) : 1.f;
-          sbuf[3 * kMaxBN + i] = ok ? __ldg(p.bias2 + c) : 0.f;
+      const int ncols = min(p.BN, p.Cout - tc.n0);
+      // this group's chunks of the tile: c = c_first, c_first + G, ...
+      int c_first = (grp - (ti * nchunks) % G + G) % G;
+      const bool mine = c_first < nchunks;
+      if (mine) {
+        // per-tile scale / bias vectors -> shared memory (this group's previous readers passed their last barrier)
+        for (int i = e; i < p.BN; i += kEpiThreads) {
+          const int c = tc.n0 + i;
+          const bool ok = c < p.Cout;
+          sb[i] = (ok && p.scale) ? __ldg(p.scale + c) : 1.f;
+          sb[kMaxBN + i] = (ok && p.bias) ? __ldg(p.bias + c) : 0.f;
+          if (p.has_out2) {
+            sb[2 * kMaxBN + i] = ok ? __ldg(p.scale2 + c) : 1.f;
+            sb[3 * kMaxBN + i] = ok ? __ldg(p.bias2 + c) : 0.f;
+          }
         }
+        ptx::named_bar_sync(bar_id, kEpiThreads);
       }
-      ptx::named_bar_sync(1, kEpiThreads);
       ptx::mbar_wait(&tmem_full_bar[as], aphase);
       ptx::tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * p.bn_pad);
-      const int ncols = min(p.BN, p.Cout - tc.n0);
+      bool released = false;
+      auto release_tmem = [&]() {  // accumulator fully read by this warp: hand the buffer back to the MMA warp
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+        released = true;
+      };
 
       if (p.tma_epilogue) {
-        for (int c = 0; c < nchunks; ++c, ++g) {
+        for (int c = c_first; c < nchunks; c += G, ++q) {
           const int col0 = c * 64;
+          const bool last = c + G >= nchunks;
           if (col0 >= ncols) {  // whole chunk beyond Cout (only when BN > remaining channels)
-            if (c == nchunks - 1) {
-              ptx::tc_fence_before();
-              __syncwarp();
-              if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
+            if (p.has_res && leader) {
+              ptx::bulk_wait_read<0>();  // no store of its own follows: every earlier one must be done
+              issue_residual(q + 2);     // keep the prefetch chain going
             }
-            if (p.has_res && leader) issue_residual(g + 2);  // keep the prefetch chain going
             continue;
           }
-          const int b = g & 1;
-          if (leader) ptx::bulk_wait_read<1>();  // the store issued two chunks ago has finished reading buffer b
-          ptx::named_bar_sync(1, kEpiThreads);
+          const int sl = q % p.n_slots;
+          unsigned char* obuf = gbase + (size_t)sl * kChunkBytes;
+          unsigned char* o2buf = gbase + (size_t)(p.n_slots + (q % max(p.n_out2, 1))) * kChunkBytes;
+          if (leader) {  // the stores that last read the buffers written below have finished reading them
+            if (p.n_out2 == 1) ptx::bulk_wait_read<0>(); else ptx::bulk_wait_read<1>();
+          }
+          ptx::named_bar_sync(bar_id, kEpiThreads);
           uint32_t r0[32], r1[32];
           ptx::tmem_ld_32x32(t_acc + (uint32_t)col0, r0);
           ptx::tmem_ld_32x32(t_acc + (uint32_t)col0 + 32u, r1);
           ptx::tmem_ld_wait();
-          if (c == nchunks - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
-          }
+          if (last) release_tmem();
           if (p.has_res) {
-            ptx::mbar_wait(&res_full_bar[b], (res_phase >> b) & 1u);
-            res_phase ^= (1u << b);
+            ptx::mbar_wait(&res_bar[sl], (res_phase >> sl) & 1u);
+            res_phase ^= (1u << sl);
           }
-          unsigned char* crow = cbuf + (size_t)b * kChunkBytes + (size_t)m * 128;
-          unsigned char* c2row = c2buf + (size_t)b * kChunkBytes + (size_t)m * 128;
-          const unsigned char* rrow = rbuf + (size_t)b * kChunkBytes + (size_t)m * 128;
+          unsigned char* crow = obuf + (size_t)m * 128;   // residual in, result out: same 16-byte units, same thread
+          unsigned char* c2row = o2buf + (size_t)m * 128;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {  // 8 channels = one 16-byte unit of the swizzled row
+          for (int u = 0; u < 8; ++u) {  // 8 channels = one 16-byte unit of the swizzled row
             float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int cj = q * 8 + j;
+            for (int jj = 0; jj < 8; ++jj) {
+              const int cj = u * 8 + jj;
               const float acc = __uint_as_float(cj < 32 ? r0[cj & 31] : r1[cj & 31]);
-              v[j] = fmaf(acc, sbuf[col0 + cj], sbuf[kMaxBN + col0 + cj]);
+              v[jj] = fmaf(acc, sb[col0 + cj], sb[kMaxBN + col0 + cj]);
             }
-            const uint32_t off = ((uint32_t)q ^ swz) << 4;
+            const uint32_t off = ((uint32_t)u ^ swz) << 4;
             if (p.has_res) {
-              const uint4 u = *reinterpret_cast<const uint4*>(rrow + off);
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+              const uint4 rr = *reinterpret_cast<const uint4*>(crow + off);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rr);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = __bfloat1622float2(h[j]);
-                v[2 * j] += f.x;
-                v[2 * j + 1] += f.y;
+              for (int jj = 0; jj < 4; ++jj) {
+                const float2 f = __bfloat1622float2(h[jj]);
+                v[2 * jj] += f.x;
+                v[2 * jj + 1] += f.y;
               }
             }
             if (p.relu) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+              for (int jj = 0; jj < 8; ++jj) v[jj] = fmaxf(v[jj], 0.f);
             }
             if (!p.skip_out)
               *reinterpret_cast<uint4*>(crow + off) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
@@ -317,27 +337,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             if (p.has_out2) {
               float w[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int cj = q * 8 + j;
-                w[j] = fmaxf(fmaf(v[j], sbuf[2 * kMaxBN + col0 + cj], sbuf[3 * kMaxBN + col0 + cj]), 0.f);
+              for (int jj = 0; jj < 8; ++jj) {
+                const int cj = u * 8 + jj;
+                w[jj] = fmaxf(fmaf(v[jj], sb[2 * kMaxBN + col0 + cj], sb[3 * kMaxBN + col0 + cj]), 0.f);
               }
               *reinterpret_cast<uint4*>(c2row + off) = make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]),
                                                                   pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
             }
           }
           ptx::fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async proxy)
-          ptx::named_bar_sync(1, kEpiThreads);
+          ptx::named_bar_sync(bar_id, kEpiThreads);
           if (leader) {
-            if (!p.skip_out)
-              ptx::tma_store_4d(&map_out, cbuf + (size_t)b * kChunkBytes, tc.n0 + col0, tc.x0, tc.y0, tc.img);
-            if (p.has_out2)
-              ptx::tma_store_4d(&map_out2, c2buf + (size_t)b * kChunkBytes, tc.n0 + col0, tc.x0, tc.y0, tc.img);
+            if (!p.skip_out) ptx::tma_store_4d(&map_out, obuf, tc.n0 + col0, tc.x0, tc.y0, tc.img);
+            if (p.has_out2) ptx::tma_store_4d(&map_out2, o2buf, tc.n0 + col0, tc.x0, tc.y0, tc.img);
             ptx::bulk_commit();
-            if (p.has_res) issue_residual(g + 2);  // everyone has consumed residual buffer b
+            if (p.has_res) {
+              // slot (q+2) % 3 was last read by the store of chunk q-1: all but the newest store must be done
+              ptx::bulk_wait_read<1>();
+              issue_residual(q + 2);
+            }
           }
         }
+        if (!released) release_tmem();  // no chunk of this tile (or only skipped ones) was this group's
       } else {
-        // direct register -> global path (fp32 and/or strided outputs)
+        // direct register -> global path (fp32 and/or strided outputs); single group
         const int py = tc.y0 + m / p.BW, px = tc.x0 + m % p.BW;
         const bool row_ok = (py < p.Hout) && (px < p.Wout);
         const long long pix_off =
@@ -354,7 +377,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               if (j < nv) {
-                float a = fmaf(__uint_as_float(r[j]), sbuf[c0 + j], sbuf[kMaxBN + c0 + j]);
+                float a = fmaf(__uint_as_float(r[j]), sb[c0 + j], sb[kMaxBN + c0 + j]);
                 if (p.relu) a = fmaxf(a, 0.f);
                 op[(long long)j * p.out_sc] = a;
               }
@@ -364,17 +387,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               if (j < nv) {
-                float a = fmaf(__uint_as_float(r[j]), sbuf[c0 + j], sbuf[kMaxBN + c0 + j]);
+                float a = fmaf(__uint_as_float(r[j]), sb[c0 + j], sb[kMaxBN + c0 + j]);
                 if (p.relu) a = fmaxf(a, 0.f);
                 op[(long long)j * p.out_sc] = __float2bfloat16_rn(a);
               }
             }
           }
         }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
-        ptx::named_bar_sync(1, kEpiThreads);  // sbuf is rewritten at the top of the next tile
+        release_tmem();
+        ptx::named_bar_sync(bar_id, kEpiThreads);  // sb is rewritten at the top of the next tile
       }
       as ^= 1;
       if (as == 0) aphase ^= 1;
@@ -519,13 +540,35 @@ extern "C" int xdet_conv2d_bf16(const void* d_in, const xdet_conv_desc* d, void*
   if ((a.has_res && (reinterpret_cast<uintptr_t>(d->residual) & 15)) || (a.has_out2 && (reinterpret_cast<uintptr_t>(d->out2) & 15)))
     return fail(XDET_EINVAL, "conv2d: residual / out2 must be 16-byte aligned");
 
-  // shared memory budget and N tile
-  const size_t epi_bytes = (size_t)kChunkBytes * 2 * ((a.tma_epilogue ? 1 : 0) + a.has_out2 + a.has_res);
-  const size_t tail = 4 * kMaxBN * sizeof(float) + (2 * kMaxStages + 6) * sizeof(uint64_t) + 64;
-  const size_t budget = kSmemCap - 1024 - tail - epi_bytes;
+  // epilogue staging: memory-bound layers (few k-blocks per tile) get two epilogue warpgroups; a residual is
+  // prefetched two chunks ahead into a third slot and overwritten in place by the result
+  a.epi_groups = (a.tma_epilogue && a.num_k_blocks <= 12) ? 2 : 1;
+  if (d->epi_groups == 1 || d->epi_groups == 2) a.epi_groups = a.tma_epilogue ? d->epi_groups : 1;
+  a.n_slots = a.tma_epilogue ? (a.has_res ? 3 : 2) : 0;
+  a.n_out2 = a.has_out2 ? (a.has_res ? 1 : 2) : 0;
+  const size_t tail = 2 * 4 * kMaxBN * sizeof(float) + (2 * kMaxStages + 4 + 2 * kMaxSlots) * sizeof(uint64_t) + 64;
   int BN = d->block_n > 0 ? d->block_n : pick_block_n(d->Cout, m_tiles, a.num_k_blocks, a.tma_epilogue != 0);
   if (BN % 16 != 0 || BN < 16 || BN > kMaxBN) return fail(XDET_EINVAL, "conv2d: block_n must be a multiple of 16 in [16,256]");
   if (a.tma_epilogue && BN % 64 != 0) return fail(XDET_EINVAL, "conv2d: block_n must be a multiple of 64 for bf16 NHWC outputs");
+  // shared memory: [stages][A + B] + epilogue staging must fit; want >= 3 stages (>= 2 at the very least).
+  // Shrink in this order: N tile 256 -> 128 (auto only), then one epilogue group instead of two.
+  const size_t kSmemCap = d->max_ctas > 0 ? kSmemCapShared : kSmemCapAlone;
+  size_t epi_bytes = 0, stage_bytes = 0;
+  int stages = 0;
+  for (;;) {
+    epi_bytes = (size_t)kChunkBytes * a.epi_groups * (a.n_slots + a.n_out2);
+    stage_bytes = (size_t)kBM * kBK * 2 + (((size_t)BN * kBK * 2 + 1023) & ~(size_t)1023);
+    const size_t fixed = 1024 + tail + epi_bytes;
+    stages = fixed < kSmemCap ? (int)((kSmemCap - fixed) / stage_bytes) : 0;
+    const int want = a.num_k_blocks >= 3 ? 3 : 2;
+    if (stages >= want) break;
+    if (d->block_n <= 0 && BN > 128) { BN = 128; continue; }
+    if (a.epi_groups == 2) { a.epi_groups = 1; continue; }
+    if (stages >= 2) break;
+    if (d->block_n <= 0 && BN > 64) { BN = 64; continue; }
+    return fail(XDET_EINVAL, "conv2d: tile does not fit shared memory");
+  }
+  if (stages > kMaxStages) stages = kMaxStages;
   a.BN = BN;
   a.bn_pad = ((BN + 31) / 32) * 32;
   a.tmem_cols = next_pow2_cols(2 * a.bn_pad);
@@ -533,10 +576,6 @@ extern "C" int xdet_conv2d_bf16(const void* d_in, const xdet_conv_desc* d, void*
   const long long total = m_tiles * a.n_tiles_n;
   if (total >= (1ll << 31)) return fail(XDET_EINVAL, "conv2d: too many tiles");
   a.total_tiles = (int)total;
-  const size_t stage_bytes = (size_t)kBM * kBK * 2 + (((size_t)BN * kBK * 2 + 1023) & ~(size_t)1023);
-  int stages = (int)(budget / stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) return fail(XDET_EINVAL, "conv2d: tile does not fit shared memory");
   a.stages = stages;
   a.scale = d->scale;
   a.bias = d->bias;

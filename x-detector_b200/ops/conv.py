@@ -25,7 +25,7 @@ class ConvDesc(ctypes.Structure):
         ("out_sn", ctypes.c_longlong), ("out_sy", ctypes.c_longlong), ("out_sx", ctypes.c_longlong),
         ("out_sc", ctypes.c_longlong),
         ("out2", ctypes.c_void_p), ("scale2", ctypes.c_void_p), ("bias2", ctypes.c_void_p), ("block_n", ctypes.c_int),
-        ("max_ctas", ctypes.c_int),
+        ("epi_groups", ctypes.c_int), ("max_ctas", ctypes.c_int),
     ]
 
 
@@ -83,7 +83,7 @@ class cta_limit(object):
 
 def conv2d_nhwc(x, w_packed, cout, kh, kw, *, dilation=(1, 1), padding="SAME", scale=None, bias=None, relu=False,
                 residual=None, out=None, out_layout="nhwc_bf16", out2=None, scale2=None, bias2=None, cin=None,
-                block_n=0, strides=(1, 1), fold_w=None, skip_out=False):
+                block_n=0, strides=(1, 1), fold_w=None, skip_out=False, epi_groups=0):
     """x: [N,H,W,C] bf16 (channel stride may be padded: pass the true ``cin``).  Returns the output tensor
     ([N,Ho,Wo,Cout] bf16 for 'nhwc_bf16', [N,Cout,Ho,Wo] fp32 for 'nchw_f32', [N,Ho,Wo,Cout] fp32 for 'nhwc_f32')."""
     assert x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4
@@ -128,7 +128,7 @@ def conv2d_nhwc(x, w_packed, cout, kh, kw, *, dilation=(1, 1), padding="SAME", s
                  w_packed.data_ptr(), _ptr(scale), _ptr(bias),
                  1 if relu else 0, _ptr(residual), None if skip_out else out.data_ptr(),
                  0 if out.dtype == torch.bfloat16 else 1, sn, sy, sx, sc, _ptr(out2), _ptr(scale2), _ptr(bias2),
-                 block_n, MAX_CTAS)
+                 block_n, epi_groups, MAX_CTAS)
     with torch.cuda.device(dev):
         if PROFILE is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
