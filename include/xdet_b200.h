@@ -127,6 +127,24 @@ typedef struct {
 } xdet_conv_desc;
 int xdet_conv2d_bf16(const void* d_in, const xdet_conv_desc* desc, void* stream);
 
+/* Weight gradient of the same convolutions (training; replaces TensorFlow's Conv2DBackpropFilter behind
+ * `optimizer.minimize`, light_head_rfcn_train.py:426-441):
+ *   dw[co][kh*KW+kw][ci] += sum_{n,y,x} dy(n,y,x,co) * x(n, y*stride_h + kh*dil_h - pad_top, x*stride_w + kw*dil_w - pad_left, ci)
+ * d_x  [N,H,W,in_cs] bf16 (the forward input), d_dy [N,Hout,Wout,dy_cs] bf16 (gradient of the forward output),
+ * dw   [Cout][KH*KW][ceil(Cin/64)*64] fp32 -- the packed weight layout of xdet_conv2d_bf16 -- ACCUMULATED into
+ *      (the caller zero-fills it; pixel splits of one tile meet through fp32 atomics, so the summation order and
+ *      hence the last bits are not run-to-run reproducible).
+ * The input gradient needs no entry point of its own: it is xdet_conv2d_bf16 on dy with the filter flipped and
+ * its channel axes swapped (ops/conv.py:pack_dgrad_weight), on a zero-stuffed dy for stride-2 layers. */
+typedef struct {
+  int N, H, W, Cin, in_cs;
+  int Cout, KH, KW, dil_h, dil_w, pad_top, pad_left, stride_h, stride_w;
+  int Hout, Wout, dy_cs;
+  float* dw;
+  int splits; /* 0 = auto: enough pixel splits to fill the GPU */
+} xdet_wgrad_desc;
+int xdet_conv2d_wgrad_bf16(const void* d_x, const void* d_dy, const xdet_wgrad_desc* desc, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Bandwidth helpers around the tensor-core convolutions (bf16 NHWC tensors).
  * xdet_im2col_bf16      patch gather that turns the STRIDED convolutions of the ResNet-v2 stem / stage heads

@@ -55,6 +55,7 @@ def _declare(lib):
     lib.xdet_psroi_align_fwd_host.argtypes = [c_void_p] * 4 + [c_int] * 8
     lib.xdet_psroi_align_bwd_host.argtypes = [c_void_p] * 4 + [c_int] * 8
     lib.xdet_conv2d_bf16.argtypes = [c_void_p, c_void_p, c_void_p]
+    lib.xdet_conv2d_wgrad_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
     c_ll, c_float, c_size_t = ctypes.c_longlong, ctypes.c_float, ctypes.c_size_t
     lib.xdet_im2col_bf16.argtypes = [c_void_p, c_int, c_void_p] + [c_int] * 13 + [c_void_p]
     lib.xdet_maxpool3x3s2_bf16.argtypes = [c_void_p] * 5 + [c_int] * 8 + [c_void_p]

@@ -161,3 +161,65 @@ def conv2d_image_fold(image_nchw_f32, w_fold, cout, kh, kw, stride, pad, **kw_ar
     x8 = image_to_nhwc8(image_nchw_f32, pad, wp)
     return conv2d_nhwc(x8, w_fold, cout, kh, kw, padding=(pad, pad, Ho, Wo), strides=(stride, stride), cin=C,
                        fold_w=(W, pad), **kw_args)
+
+
+# ---- training: gradients of the convolution -----------------------------------------------------------------
+class WgradDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ("N", "H", "W", "Cin", "in_cs", "Cout", "KH", "KW", "dil_h", "dil_w",
+                                            "pad_top", "pad_left", "stride_h", "stride_w", "Hout", "Wout", "dy_cs")] + \
+               [("dw", ctypes.c_void_p), ("splits", ctypes.c_int)]
+
+
+def conv2d_wgrad(x, dy, kh, kw, *, dilation=(1, 1), padding="SAME", strides=(1, 1), cin=None, cout=None, dw=None,
+                 splits=0):
+    """dW of ``conv2d_nhwc(x, w, ...) -> y`` given ``dy`` (both NHWC bf16): fp32 [Cout, kh*kw, ceil(Cin/64)*64], the
+    packed layout of the forward weights.  ``dw`` (zero-filled, or holding a partial sum) is accumulated into."""
+    assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and x.is_contiguous() and dy.is_contiguous()
+    N, H, W, cs = x.shape
+    _, Ho, Wo, dcs = dy.shape
+    cin = cs if cin is None else cin
+    cout = dcs if cout is None else cout
+    dh, dw_ = dilation
+    sh, sw = strides
+    if padding == "SAME":
+        pt, pl = same_pad(H, kh, dh, sh), same_pad(W, kw, dw_, sw)
+    elif padding == "VALID":
+        pt = pl = 0
+    else:
+        pt, pl = padding[:2]
+    cpad = (cin + 63) // 64 * 64
+    if dw is None:
+        dw = torch.zeros((cout, kh * kw, cpad), dtype=torch.float32, device=x.device)
+    d = WgradDesc(N, H, W, cin, cs, cout, kh, kw, dh, dw_, pt, pl, sh, sw, Ho, Wo, dcs, dw.data_ptr(), splits)
+    with torch.cuda.device(x.device):
+        rc = _native.lib().xdet_conv2d_wgrad_bf16(x.data_ptr(), dy.data_ptr(), ctypes.byref(d),
+                                                  torch.cuda.current_stream().cuda_stream)
+    _native.check(rc)
+    return dw
+
+
+def pack_dgrad_weight(w_oihw):
+    """Packed weights of the INPUT-gradient convolution: dX = conv(dY, flip(W) with in/out channels swapped).
+    [Cout, Cin, KH, KW] -> bf16 [Cin, KH*KW*ceil(Cout/64)*64]."""
+    return pack_conv_weight(torch.flip(w_oihw, dims=(2, 3)).permute(1, 0, 2, 3))
+
+
+def conv2d_dgrad(dy, w_dgrad, cin, kh, kw, in_hw, *, dilation=(1, 1), padding="SAME", strides=(1, 1), cout=None, **kws):
+    """dX of ``conv2d_nhwc`` (NHWC bf16): the forward kernel on ``dy`` with ``pack_dgrad_weight`` weights and the
+    mirrored padding; stride-2 layers first zero-stuff ``dy`` to the input grid."""
+    H, W = in_hw
+    dh, dw_ = dilation
+    sh, sw = strides
+    if padding == "SAME":
+        pt, pl = same_pad(H, kh, dh, sh), same_pad(W, kw, dw_, sw)
+    elif padding == "VALID":
+        pt = pl = 0
+    else:
+        pt, pl = padding[:2]
+    if (sh, sw) != (1, 1):
+        N, Ho, Wo, C = dy.shape
+        up = torch.zeros((N, Ho * sh, Wo * sw, C), dtype=dy.dtype, device=dy.device)
+        up[:, ::sh, ::sw] = dy  # plumbing (6 layers of the net); a fused scatter store is the obvious next step
+        dy = up
+    return conv2d_nhwc(dy, w_dgrad, cin, kh, kw, dilation=dilation,
+                       padding=((kh - 1) * dh - pt, (kw - 1) * dw_ - pl, H, W), cin=cout, **kws)
