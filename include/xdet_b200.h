@@ -213,6 +213,63 @@ int xdet_rpn_select(const float* d_scores, const float* d_boxes, int N, int A_to
 int xdet_head_decode(const float* d_rois, const float* d_head_out, int ch_stride, int cls_off, int num_classes,
                      int loc_off, long long M, float* d_probs, float* d_boxes, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Training-step kernels (csrc/train_ops.cu).  Replace the TF ops/gradients of the training graph
+ * (light_head_rfcn_train.py:277-451) that are not convolutions.
+ *
+ * Batch norm, training mode (tf.layers.batch_normalization(training=True, fused=True), net/resnet_v2.py:41-50):
+ *   xdet_col_stats_bf16   d_sums[0..C) += column sums of x [rows, cs] bf16 (and d_sums[C..2C) += sums of squares);
+ *                         also the bias gradient of a convolution (column sums of dy).
+ *   xdet_bn_finalize      batch mean / biased variance -> scale = gamma/sqrt(var+eps), shift = beta - mean*scale
+ *                         (what xdet_affine_relu_bf16 / the conv epilogue apply), mean, invstd (saved for backward);
+ *                         moving_mean/var <- decay*moving + (1-decay)*batch (unbiased variance), NULL = no update.
+ *   xdet_bn_relu_bwd_bf16 gradient of y = relu(x*scale+shift) w.r.t. x (two passes: reduce, apply), + d_add_in
+ *                         (a gradient arriving over the identity shortcut); d_sums[0..C) = dbeta, [C..2C) = dgamma.
+ * xdet_maxpool3x3s2_bwd_bf16  gradient of tf.layers.max_pooling2d(3,2,'SAME') (first maximum of each window).
+ * xdet_nchw_f32_to_nhwc_bf16 / xdet_affine_relu_to_nchw_f32  repacks around the fp32 NCHW thin feature map.
+ * xdet_softmax_ce     tf.nn.sparse_softmax_cross_entropy_with_logits: loss_row[r] and
+ *                     dlogits[r,c] = w_all * row_w[r] * (softmax - onehot) (light_head_rfcn_train.py:361,385).
+ * xdet_smooth_l1      modified_smooth_l1 (:257-275, sigma 1) summed over the 4 coordinates, times row_w; gradient.
+ * xdet_sgd_momentum_* tf.train.MomentumOptimizer (:436-441) on fp32 masters in TF layout with the L2 term of :420
+ *                     (grad + wd*w); the conv form reads dw in the packed layout of xdet_conv2d_wgrad_bf16 and
+ *                     rewrites the bf16 forward / input-gradient packs (slices of fused packs via the offsets).
+ * xdet_match_encode   iou_matrix + do_dual_max_match + target encoding (preprocessing/anchor_manipulator.py:40-94,
+ *                     118-171 for anchors: box_img_stride 0 + d_ref_yxhw; :345-392 for RoIs): labels (class, 0 bg,
+ *                     -1 ignore), targets [.,4], matched overlap scores.  gt labels <= 0 are padding.
+ * xdet_sample_fg_bg   fg/bg sampling with up-sampling (:394-432; light_head_rfcn_train.py:321-358); the three
+ *                     tf.random_shuffle calls are stable argsorts of the injected key arrays (keys >= 0).
+ */
+int xdet_col_stats_bf16(const void* d_x, long long rows, int C, int cs, int with_squares, float* d_sums, void* stream);
+int xdet_bn_finalize(const float* d_sums, const float* d_gamma, const float* d_beta, long long rows, int C, float eps,
+                     float decay, float* d_moving_mean, float* d_moving_var, float* d_scale, float* d_shift,
+                     float* d_mean, float* d_invstd, void* stream);
+int xdet_bn_relu_bwd_bf16(const void* d_dy, const void* d_x, const float* d_scale, const float* d_shift,
+                          const float* d_mean, const float* d_invstd, long long rows, int C, int relu,
+                          const void* d_add_in, float* d_sums, void* d_dx, void* stream);
+int xdet_maxpool3x3s2_bwd_bf16(const void* d_x, const void* d_dy, void* d_dx, int N, int H, int W, int C, int Ho, int Wo,
+                               int pad_top, int pad_left, void* stream);
+int xdet_nchw_f32_to_nhwc_bf16(const float* d_src, void* d_dst, int N, int C, int HW, void* stream);
+int xdet_affine_relu_to_nchw_f32(const void* d_src, const float* d_scale, const float* d_shift, float* d_dst, int N,
+                                 int C, int HW, int relu, void* stream);
+int xdet_softmax_ce(const float* d_logits, int ld, int C, const int* d_labels, const float* d_row_w, float w_all,
+                    long long M, float* d_loss_row, float* d_dlogits, int dld, void* stream);
+int xdet_smooth_l1(const float* d_pred, int ld, const float* d_target, const float* d_row_w, float w_all, long long M,
+                   float* d_loss_row, float* d_dpred, int dld, void* stream);
+int xdet_sgd_momentum_conv(const float* d_dw, float* d_w, float* d_mom, void* d_w_pack, void* d_w_dgrad_pack, int Cout,
+                           int KH, int KW, int Cin, int pack_co_off, int pack_ci_off, int pack_cin_pad,
+                           int pack_cout_pad, int fold, float lr, float momentum, float wd, float grad_scale,
+                           void* stream);
+int xdet_sgd_momentum_vec(const float* d_g, float* d_w, float* d_mom, long long n, float lr, float momentum, float wd,
+                          float grad_scale, void* stream);
+size_t xdet_match_workspace_bytes(int N, int G);
+int xdet_match_encode(const float* d_boxes, long long box_img_stride, const float* d_ref_yxhw, const float* d_gt,
+                      const int* d_gt_labels, int N, int A, int G, float allowed_border, float high_thres,
+                      float low_thres, const float* prior_scaling4, int* d_labels, float* d_targets, float* d_scores,
+                      void* d_workspace, void* stream);
+int xdet_sample_fg_bg(const int* d_labels, const float* d_scores, float bg_low, int groups, int n, int exp_fg, int total,
+                      const float* d_keys_fg, const float* d_keys_bg, const float* d_keys_up, int* d_workspace,
+                      int* d_out, int* d_counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

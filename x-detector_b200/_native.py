@@ -72,6 +72,27 @@ def _declare(lib):
                                     [c_size_t, c_void_p])
 
 
+def _declare_train(lib):
+    c_int, c_void_p, c_ll, c_float, c_size_t = (ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_float,
+                                                 ctypes.c_size_t)
+    lib.xdet_col_stats_bf16.argtypes = [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p]
+    lib.xdet_bn_finalize.argtypes = [c_void_p] * 3 + [c_ll, c_int, c_float, c_float] + [c_void_p] * 7
+    lib.xdet_bn_relu_bwd_bf16.argtypes = [c_void_p] * 6 + [c_ll, c_int, c_int] + [c_void_p] * 4
+    lib.xdet_maxpool3x3s2_bwd_bf16.argtypes = [c_void_p] * 3 + [c_int] * 8 + [c_void_p]
+    lib.xdet_nchw_f32_to_nhwc_bf16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
+    lib.xdet_affine_relu_to_nchw_f32.argtypes = [c_void_p] * 4 + [c_int] * 4 + [c_void_p]
+    lib.xdet_softmax_ce.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_ll, c_void_p, c_void_p, c_int,
+                                    c_void_p]
+    lib.xdet_smooth_l1.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_float, c_ll, c_void_p, c_void_p, c_int, c_void_p]
+    lib.xdet_sgd_momentum_conv.argtypes = [c_void_p] * 5 + [c_int] * 9 + [c_float] * 4 + [c_void_p]
+    lib.xdet_sgd_momentum_vec.argtypes = [c_void_p] * 3 + [c_ll] + [c_float] * 4 + [c_void_p]
+    lib.xdet_match_workspace_bytes.argtypes = [c_int, c_int]
+    lib.xdet_match_workspace_bytes.restype = c_size_t
+    lib.xdet_match_encode.argtypes = ([c_void_p, c_ll] + [c_void_p] * 3 + [c_int] * 3 + [c_float] * 3 +
+                                      [ctypes.POINTER(c_float)] + [c_void_p] * 5)
+    lib.xdet_sample_fg_bg.argtypes = [c_void_p, c_void_p, c_float] + [c_int] * 4 + [c_void_p] * 7
+
+
 def lib():
     """The loaded C-ABI library.  Raises loudly if it has not been built: no fallback exists."""
     global _lib
@@ -82,6 +103,7 @@ def lib():
                 "(nvcc, sm_100a). xdet_b200 has no CPU or PyTorch fallback." % LIB_PATH)
         _lib = ctypes.CDLL(LIB_PATH)
         _declare(_lib)
+        _declare_train(_lib)
     return _lib
 
 

@@ -1,0 +1,798 @@
+// Training-step kernels around the tensor-core convolutions (all bandwidth / latency work, no tensor cores):
+//   * batch-norm in training mode (tf.layers.batch_normalization(training=True, fused=True),
+//     net/resnet_v2.py:41-50): per-channel batch statistics, finalisation (+ moving-average update), and the
+//     two-pass backward of BN+ReLU;
+//   * max-pool backward, bias gradient (column sums), NCHW fp32 <-> NHWC bf16 repacks for the thin feature map;
+//   * losses of light_head_rfcn_train.py:257-275,361-413: sparse softmax cross-entropy and modified_smooth_l1,
+//     forward value and gradient in one pass;
+//   * MomentumOptimizer step (light_head_rfcn_train.py:426-441) with the L2 term of :420 folded in, writing the
+//     bf16 forward / input-gradient weight packs of the next step as it goes;
+//   * target assignment: iou_matrix + do_dual_max_match + box encoding (preprocessing/anchor_manipulator.py:
+//     40-94,118-171,337-392) and the fg/bg sampling with up-sampling of :394-432 and
+//     light_head_rfcn_train.py:321-358, tf.random_shuffle replaced by injected key arrays.
+#include <cuda_bf16.h>
+
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace xdet {
+namespace {
+
+unsigned blocks_for(long long total, int threads = 256, int per_sm = 8) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = (long long)kNumSMs * per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+// ---- column sums of a [rows, cs] bf16 matrix: sum (and sum of squares) per channel --------------------------
+// block = 256 threads = 32 channel-groups of 8 x 8 row lanes; grid.x over channel groups of 256, grid.y over row slabs
+template <bool SQ>
+__global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C,
+                                                        int cs, float* __restrict__ sums /* [2][C] or [C] */) {
+  __shared__ float s_sum[8][256 + 8], s_sq[8][256 + 8];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;  // 32 groups of 8 channels, 8 row lanes
+  const int c0 = blockIdx.x * 256 + cg * 8;
+  float a[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = q[j] = 0.f;
+  if (c0 < C) {
+    for (long long r = (long long)blockIdx.y * 8 + rl; r < rows; r += (long long)gridDim.y * 8) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + r * cs + c0));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(h[k]);
+        a[2 * k] += f.x;
+        a[2 * k + 1] += f.y;
+        if (SQ) {
+          q[2 * k] = fmaf(f.x, f.x, q[2 * k]);
+          q[2 * k + 1] = fmaf(f.y, f.y, q[2 * k + 1]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s_sum[rl][cg * 8 + j] = a[j];
+    if (SQ) s_sq[rl][cg * 8 + j] = q[j];
+  }
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < C) {
+    float t = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      t += s_sum[r][threadIdx.x];
+      if (SQ) t2 += s_sq[r][threadIdx.x];
+    }
+    atomicAdd(sums + c, t);
+    if (SQ) atomicAdd(sums + C + c, t2);
+  }
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, long long rows, int C, float eps, float decay,
+                                   float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = (double)sums[c] / (double)rows;
+  double var = (double)sums[C + c] / (double)rows - m * m;  // biased (what normalises the batch)
+  if (var < 0.0) var = 0.0;
+  const double inv = 1.0 / sqrt(var + (double)eps);
+  const float sc = (float)((double)gamma[c] * inv);
+  scale[c] = sc;
+  shift[c] = (float)((double)beta[c] - m * (double)gamma[c] * inv);
+  mean_out[c] = (float)m;
+  invstd_out[c] = (float)inv;
+  if (moving_mean) {  // fused batch norm feeds the UNBIASED variance to the moving average
+    const double unb = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
+    moving_mean[c] = moving_mean[c] * decay + (1.f - decay) * (float)m;
+    moving_var[c] = moving_var[c] * decay + (1.f - decay) * (float)unb;
+  }
+}
+
+// g = dy * [x*scale+shift > 0] (ReLU mask recomputed from the saved pre-BN tensor); sums: [0,C) = sum g,
+// [C,2C) = sum g * xhat, xhat = (x - mean) * invstd.
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                            const __nv_bfloat16* __restrict__ x,
+                                                            const float* __restrict__ scale,
+                                                            const float* __restrict__ shift,
+                                                            const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd, long long rows, int C,
+                                                            int relu, float* __restrict__ sums) {
+  __shared__ float s_a[8][256 + 8], s_b[8][256 + 8];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + cg * 8;
+  float a[8], b[8], sc[8], sh[8], mu[8], is[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
+  if (c0 < C) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = scale[c0 + j];
+      sh[j] = shift[c0 + j];
+      mu[j] = mean[c0 + j];
+      is[j] = invstd[c0 + j];
+    }
+    for (long long r = (long long)blockIdx.y * 8 + rl; r < rows; r += (long long)gridDim.y * 8) {
+      const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + r * C + c0));
+      const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x + r * C + c0));
+      const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&ud);
+      const __nv_bfloat162* hx = reinterpret_cast<const __nv_bfloat162*>(&ux);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 fd = __bfloat1622float2(hd[k]), fx = __bfloat1622float2(hx[k]);
+        const float g0 = (!relu || fmaf(fx.x, sc[2 * k], sh[2 * k]) > 0.f) ? fd.x : 0.f;
+        const float g1 = (!relu || fmaf(fx.y, sc[2 * k + 1], sh[2 * k + 1]) > 0.f) ? fd.y : 0.f;
+        a[2 * k] += g0;
+        a[2 * k + 1] += g1;
+        b[2 * k] = fmaf(g0, (fx.x - mu[2 * k]) * is[2 * k], b[2 * k]);
+        b[2 * k + 1] = fmaf(g1, (fx.y - mu[2 * k + 1]) * is[2 * k + 1], b[2 * k + 1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s_a[rl][cg * 8 + j] = a[j];
+    s_b[rl][cg * 8 + j] = b[j];
+  }
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < C) {
+    float t = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      t += s_a[r][threadIdx.x];
+      t2 += s_b[r][threadIdx.x];
+    }
+    atomicAdd(sums + c, t);
+    atomicAdd(sums + C + c, t2);
+  }
+}
+
+// dx = scale * (g - sum_g/M - xhat * sum_gx/M) (+ add_in); scale = gamma * invstd.
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                           const __nv_bfloat16* __restrict__ x,
+                                                           const float* __restrict__ scale,
+                                                           const float* __restrict__ shift,
+                                                           const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd,
+                                                           const float* __restrict__ sums,
+                                                           const __nv_bfloat16* __restrict__ add_in, long long rows,
+                                                           int C, int relu, __nv_bfloat16* __restrict__ dx) {
+  const int C8 = C / 8;
+  const long long total = rows * C8;
+  const float inv_m = 1.f / (float)rows;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
+    const int c0 = (int)(e % C8) * 8;
+    const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy) + e);
+    const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x) + e);
+    uint4 ua = make_uint4(0, 0, 0, 0);
+    if (add_in) ua = __ldg(reinterpret_cast<const uint4*>(add_in) + e);
+    const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&ud);
+    const __nv_bfloat162* hx = reinterpret_cast<const __nv_bfloat162*>(&ux);
+    const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&ua);
+    uint4 o;
+    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fd = __bfloat1622float2(hd[k]), fx = __bfloat1622float2(hx[k]), fa = __bfloat1622float2(ha[k]);
+      float r[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int c = c0 + 2 * k + t;
+        const float xv = t ? fx.y : fx.x, dv = t ? fd.y : fd.x;
+        const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+        const float g = (!relu || fmaf(xv, sc, sh) > 0.f) ? dv : 0.f;
+        const float xh = (xv - __ldg(mean + c)) * __ldg(invstd + c);
+        r[t] = sc * (g - __ldg(sums + c) * inv_m - xh * __ldg(sums + C + c) * inv_m) + (t ? fa.y : fa.x);
+      }
+      ho[k] = __floats2bfloat162_rn(r[0], r[1]);
+    }
+    reinterpret_cast<uint4*>(dx)[e] = o;
+  }
+}
+
+// dx of tf.layers.max_pooling2d(3, 2, 'SAME'): every input pixel gathers dy from the (<= 4) windows that cover it
+// and whose FIRST maximum (row-major window order) it is.
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                          const __nv_bfloat16* __restrict__ dy,
+                                                          __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C,
+                                                          int Ho, int Wo, int pad_top, int pad_left, long long total) {
+  const int C2 = C / 2;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
+    const int c2 = (int)(e % C2);
+    long long t = e / C2;
+    const int xi = (int)(t % W);
+    t /= W;
+    const int yi = (int)(t % H);
+    const int n = (int)(t / H);
+    const uint32_t* xs = reinterpret_cast<const uint32_t*>(x) + c2;
+    const uint32_t me_u = __ldg(xs + (((long long)n * H + yi) * W + xi) * C2);
+    const float2 me = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&me_u));
+    float2 acc = make_float2(0.f, 0.f);
+    // windows (yo, xo) with yo*2 - pad_top <= yi <= yo*2 - pad_top + 2
+    const int yo_lo = max(0, (yi + pad_top - 2 + 1) / 2), yo_hi = min(Ho - 1, (yi + pad_top) / 2);
+    const int xo_lo = max(0, (xi + pad_left - 2 + 1) / 2), xo_hi = min(Wo - 1, (xi + pad_left) / 2);
+    for (int yo = yo_lo; yo <= yo_hi; ++yo) {
+      for (int xo = xo_lo; xo <= xo_hi; ++xo) {
+        // am I the first maximum of this window? (strictly greater than everything before me, >= everything after)
+        bool first0 = true, first1 = true;
+        for (int kh = 0; kh < 3; ++kh) {
+          const int yy = yo * 2 + kh - pad_top;
+          if (yy < 0 || yy >= H) continue;
+          for (int kw = 0; kw < 3; ++kw) {
+            const int xx = xo * 2 + kw - pad_left;
+            if (xx < 0 || xx >= W || (yy == yi && xx == xi)) continue;
+            const uint32_t u = __ldg(xs + (((long long)n * H + yy) * W + xx) * C2);
+            const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+            const bool before = (yy < yi) || (yy == yi && xx < xi);
+            first0 = first0 && (before ? (me.x > v.x) : (me.x >= v.x));
+            first1 = first1 && (before ? (me.y > v.y) : (me.y >= v.y));
+          }
+        }
+        const uint32_t du = __ldg(reinterpret_cast<const uint32_t*>(dy) + (((long long)n * Ho + yo) * Wo + xo) * C2 + c2);
+        const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&du));
+        if (first0) acc.x += d.x;
+        if (first1) acc.y += d.y;
+      }
+    }
+    const __nv_bfloat162 o = __floats2bfloat162_rn(acc.x, acc.y);
+    reinterpret_cast<uint32_t*>(dx)[e] = *reinterpret_cast<const uint32_t*>(&o);
+  }
+}
+
+// [N,C,H,W] fp32 -> [N,H,W,C] bf16 and [N,H,W,C] bf16 -> relu(x*scale+shift) as [N,C,H,W] fp32 (thin feature map)
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int C,
+                                             int HW, long long total) {
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
+    const int c = (int)(e % C);
+    const long long p = e / C;  // n*HW + hw
+    const long long n = p / HW, hw = p % HW;
+    dst[e] = __float2bfloat16_rn(__ldg(src + (n * C + c) * HW + hw));
+  }
+}
+__global__ void affine_relu_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ src, const float* __restrict__ scale,
+                                               const float* __restrict__ shift, float* __restrict__ dst, int N, int C,
+                                               int HW, int relu, long long total) {
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
+    const long long hw = e % HW;
+    const long long t = e / HW;
+    const int c = (int)(t % C);
+    const long long n = t / C;
+    float v = fmaf(__bfloat162float(src[(n * HW + hw) * C + c]), __ldg(scale + c), __ldg(shift + c));
+    if (relu) v = fmaxf(v, 0.f);
+    dst[e] = v;
+  }
+}
+
+// ---- losses ------------------------------------------------------------------------------------------------
+// tf.nn.sparse_softmax_cross_entropy_with_logits per row; dlogits = row_w * (softmax - onehot).
+__global__ void softmax_ce_kernel(const float* __restrict__ logits, int ld, int C, const int* __restrict__ labels,
+                                  const float* __restrict__ row_w, float w_all, long long M, float* __restrict__ loss_row,
+                                  float* __restrict__ dlogits, int dld) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= M) return;
+  const float* z = logits + r * ld;
+  float mx = -FLT_MAX;
+  for (int c = 0; c < C; ++c) mx = fmaxf(mx, z[c]);
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) s += expf(z[c] - mx);
+  const int y = labels[r];
+  const float lse = logf(s) + mx;
+  if (loss_row) loss_row[r] = lse - z[y];
+  if (dlogits) {
+    const float w = w_all * (row_w ? row_w[r] : 1.f);
+    for (int c = 0; c < C; ++c) dlogits[r * dld + c] = w * (expf(z[c] - lse) - (c == y ? 1.f : 0.f));
+  }
+}
+
+// modified_smooth_l1 (sigma = 1) summed over the 4 coordinates of a row, times row_w; dpred = w_all*row_w*clip(d,-1,1).
+__global__ void smooth_l1_kernel(const float* __restrict__ pred, int ld, const float* __restrict__ target,
+                                 const float* __restrict__ row_w, float w_all, long long M, float* __restrict__ loss_row,
+                                 float* __restrict__ dpred, int dld) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= M) return;
+  const float rw = row_w ? row_w[r] : 1.f;
+  float tot = 0.f;
+  for (int j = 0; j < 4; ++j) {
+    const float d = pred[r * ld + j] - target[r * 4 + j];
+    const float ad = fabsf(d);
+    tot += (ad < 1.f) ? 0.5f * d * d : ad - 0.5f;
+    if (dpred) dpred[r * dld + j] = w_all * rw * ((ad < 1.f) ? d : (d > 0.f ? 1.f : -1.f));
+  }
+  if (loss_row) loss_row[r] = tot * rw;
+}
+
+// ---- optimizer -----------------------------------------------------------------------------------------------
+// MomentumOptimizer: accum = momentum*accum + (g + wd*w); w -= lr*accum.  The master weights keep TF's layout
+// [KH*KW][Cin][Cout]; dw arrives in the packed layout [Cout][KH*KW][cin_pad]; the bf16 packs of the next step
+// (forward [Cout][tap][cin_pad] and input-gradient [Cin][flipped tap][cout_pad]) are rewritten on the fly.
+// fold != 0: the stem layout, packed element kw*8 + ci of filter row kh.
+__global__ void sgd_conv_kernel(const float* __restrict__ dw, float* __restrict__ w, float* __restrict__ mom,
+                                __nv_bfloat16* __restrict__ wp, __nv_bfloat16* __restrict__ wd_pack, int Cout, int KH,
+                                int KW, int Cin, int cin_pad, int cout_pad, int fold, float lr, float momentum, float wd,
+                                float gscale, long long total) {
+  const int taps = KH * KW;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
+    const int co = (int)(e % Cout);
+    long long t = e / Cout;
+    const int ci = (int)(t % Cin);
+    const int tap = (int)(t / Cin);  // e indexes the master [tap][ci][co]
+    long long pidx;
+    if (fold) {
+      const int kh = tap / KW, kw = tap - kh * KW;
+      pidx = ((long long)co * KH + kh) * 64 + kw * 8 + ci;
+    } else {
+      pidx = ((long long)co * taps + tap) * cin_pad + ci;
+    }
+    const float wv = w[e];
+    const float g = dw[pidx] * gscale + wd * wv;
+    const float a = momentum * mom[e] + g;
+    mom[e] = a;
+    const float nw = wv - lr * a;
+    w[e] = nw;
+    const __nv_bfloat16 b = __float2bfloat16_rn(nw);
+    wp[pidx] = b;
+    if (wd_pack) wd_pack[((long long)ci * taps + (taps - 1 - tap)) * cout_pad + co] = b;
+  }
+}
+__global__ void sgd_vec_kernel(const float* __restrict__ g, float* __restrict__ w, float* __restrict__ mom, long long n,
+                               float lr, float momentum, float wd, float gscale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float wv = w[i];
+  const float a = momentum * mom[i] + g[i] * gscale + wd * wv;
+  mom[i] = a;
+  w[i] = wv - lr * a;
+}
+
+// ---- target assignment ---------------------------------------------------------------------------------------
+// boxes [N,A,4] (ymin,xmin,ymax,xmax); gt [N,G,4], gt_labels [N,G] (<= 0: padding, ignored).
+__device__ __forceinline__ float iou_ref(const float4 g, const float4 b) {  // iou_matrix, :20-46
+  const float iy0 = fmaxf(g.x, b.x), ix0 = fmaxf(g.y, b.y), iy1 = fminf(g.z, b.z), ix1 = fminf(g.w, b.w);
+  const float inter = __fmul_rn(fmaxf(__fsub_rn(iy1, iy0), 0.f), fmaxf(__fsub_rn(ix1, ix0), 0.f));
+  const float ag = __fmul_rn(__fsub_rn(g.z, g.x), __fsub_rn(g.w, g.y));
+  const float ab = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  const float uni = __fsub_rn(__fadd_rn(ag, ab), inter);
+  return uni == 0.f ? 0.f : __fdiv_rn(inter, uni);
+}
+__device__ __forceinline__ bool inside_ok(const float4 b, float border) {
+  return b.x >= -border && b.y >= -border && b.z < 1.f + border && b.w < 1.f + border;
+}
+// pass 1: per ground truth the best box (first maximum): 64-bit atomicMax on (iou bits << 32 | ~index)
+__global__ void match_gt_argmax_kernel(const float* __restrict__ boxes, const float* __restrict__ gt,
+                                       const int* __restrict__ gt_labels, int A, int G, float border,
+                                       unsigned long long* __restrict__ best /* [N,G], zero-filled */) {
+  const int img = blockIdx.y;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= A) return;
+  const float4 b = reinterpret_cast<const float4*>(boxes)[(long long)img * A + a];
+  const bool in = inside_ok(b, border);
+  for (int g = 0; g < G; ++g) {
+    if (gt_labels[img * G + g] <= 0) continue;
+    const float ov = in ? iou_ref(reinterpret_cast<const float4*>(gt)[img * G + g], b) : 0.f;
+    const unsigned long long key = ((unsigned long long)__float_as_uint(ov) << 32) | (0xFFFFFFFFu - (unsigned)a);
+    atomicMax(best + img * G + g, key);
+  }
+}
+// pass 2: do_dual_max_match + encode.  labels_out: matched class (> 0), 0 = background, -1 = ignore.
+// ref_yxhw: optional [A,4] (cy,cx,h,w) reference boxes used for the encoding (the anchors' own centre form,
+// encode_anchor :118-171); NULL = point2center of the box itself (ext_encode_rois :374-378).
+__global__ void match_encode_kernel(const float* __restrict__ boxes, long long box_img_stride,
+                                    const float* __restrict__ ref_yxhw, const float* __restrict__ gt,
+                                    const int* __restrict__ gt_labels, const unsigned long long* __restrict__ best, int A,
+                                    int G, float border, float high, float low, float p0, float p1, float p2, float p3,
+                                    int* __restrict__ labels_out, float* __restrict__ targets_out,
+                                    float* __restrict__ scores_out) {
+  const int img = blockIdx.y;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= A) return;
+  const float4 b = reinterpret_cast<const float4*>(boxes + (long long)img * box_img_stride)[a];
+  const bool in = inside_ok(b, border);
+  float mv = -1.f, forced_val = -1.f;
+  int a2g = -1, forced_g = -1;
+  bool has = false;
+  for (int g = 0; g < G; ++g) {
+    if (gt_labels[img * G + g] <= 0) continue;  // tf.boolean_mask(_labels > 0): order of the valid ones is kept
+    const float ov = in ? iou_ref(reinterpret_cast<const float4*>(gt)[img * G + g], b) : 0.f;
+    if (ov > mv) {  // anchors_to_gt: first maximum
+      mv = ov;
+      a2g = g;
+    }
+    const unsigned bi = 0xFFFFFFFFu - (unsigned)(best[img * G + g] & 0xFFFFFFFFull);
+    const bool picked = (bi == (unsigned)a);  // left_gt_to_anchors_mask[g, a]
+    has = has || picked;
+    const float lv = picked ? ov : 0.f;  // left_gt_to_anchors_scores
+    if (lv > forced_val) {               // argmax over ALL valid g, first maximum
+      forced_val = lv;
+      forced_g = g;
+    }
+  }
+  const long long o = (long long)img * A + a;
+  if (a2g < 0) {  // no ground truth at all
+    labels_out[o] = 0;
+    scores_out[o] = 0.f;
+    reinterpret_cast<float4*>(targets_out)[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  int match;  // >= 0: gt index, -1 negative, -2 ignore
+  if (has) {
+    match = forced_g;
+  } else {
+    match = a2g;
+    if (mv < low) match = -1;
+    if (mv < high && mv >= low) match = -2;
+  }
+  const int gsel = has ? forced_g : a2g;
+  scores_out[o] = in ? iou_ref(reinterpret_cast<const float4*>(gt)[img * G + gsel], b) : 0.f;
+  labels_out[o] = match >= 0 ? gt_labels[img * G + match] : (match == -2 ? -1 : 0);
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (match >= 0) {
+    const float4 gb = reinterpret_cast<const float4*>(gt)[img * G + match];
+    float yref, xref, h, w;
+    if (ref_yxhw) {
+      const float4 r = reinterpret_cast<const float4*>(ref_yxhw)[a];
+      yref = r.x; xref = r.y; h = r.z; w = r.w;
+    } else {
+      h = __fsub_rn(b.z, b.x);
+      w = __fsub_rn(b.w, b.y);
+      yref = __fadd_rn(b.x, __fmul_rn(h, 0.5f));
+      xref = __fadd_rn(b.y, __fmul_rn(w, 0.5f));
+    }
+    const float gcy = __fmul_rn(__fadd_rn(gb.z, gb.x), 0.5f), gcx = __fmul_rn(__fadd_rn(gb.w, gb.y), 0.5f);
+    const float gh = __fsub_rn(gb.z, gb.x), gw = __fsub_rn(gb.w, gb.y);
+    t.x = __fdiv_rn(__fdiv_rn(__fsub_rn(gcy, yref), h), p0);
+    t.y = __fdiv_rn(__fdiv_rn(__fsub_rn(gcx, xref), w), p1);
+    t.z = __fdiv_rn(logf(__fdiv_rn(gh, h)), p2);
+    t.w = __fdiv_rn(logf(__fdiv_rn(gw, w)), p3);
+  }
+  reinterpret_cast<float4*>(targets_out)[o] = t;
+}
+
+// ---- fg / bg sampling with up-sampling (anchor_manipulator.py:394-432, light_head_rfcn_train.py:321-358) --------
+constexpr int kSampThreads = 1024;
+
+// out[0..k) = indices of the k smallest keys[0..n) in ascending (key, index) order -- the first k entries of the
+// stable argsort that stands in for tf.random_shuffle(tf.range(n)).  keys >= 0.  Whole CTA; sk = smem [P], P >= k.
+__device__ void select_smallest(const float* __restrict__ keys, int n, int k, int* out, unsigned long long* sk, int P,
+                                unsigned int* hist, unsigned long long* s_prefix, int* s_remaining, int* s_count) {
+  const int tid = threadIdx.x;
+  auto key64 = [&](int i) {  // larger = smaller (key, index)
+    return ~(((unsigned long long)__float_as_uint(keys[i]) << 32) | (unsigned long long)(unsigned)i);
+  };
+  if (k <= 0) return;
+  if (tid == 0) {
+    *s_prefix = 0ull;
+    *s_remaining = k;
+  }
+  __syncthreads();
+  for (int pass = 0; pass < 8; ++pass) {
+    const int shift = 56 - 8 * pass;
+    for (int i = tid; i < 256; i += kSampThreads) hist[i] = 0;
+    __syncthreads();
+    const unsigned long long prefix = *s_prefix;
+    for (int i = tid; i < n; i += kSampThreads) {
+      const unsigned long long kk = key64(i);
+      const bool match = (pass == 0) || ((kk >> (shift + 8)) == (prefix >> (shift + 8)));
+      if (match) atomicAdd(&hist[(unsigned)(kk >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int rem = *s_remaining;
+      int b = 255;
+      for (; b > 0; --b) {
+        if ((int)hist[b] >= rem) break;
+        rem -= (int)hist[b];
+      }
+      *s_prefix = prefix | ((unsigned long long)b << shift);
+      *s_remaining = rem;
+    }
+    __syncthreads();
+  }
+  const unsigned long long thr = *s_prefix;
+  if (tid == 0) *s_count = 0;
+  for (int i = tid; i < P; i += kSampThreads) sk[i] = 0ull;
+  __syncthreads();
+  for (int i = tid; i < n; i += kSampThreads) {
+    const unsigned long long kk = key64(i);
+    if (kk >= thr) sk[atomicAdd(s_count, 1)] = kk;
+  }
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (P >> 1); t += kSampThreads) {
+        const int lo = ((t / stride) * (stride << 1)) + (t % stride), hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long a = sk[lo], b = sk[hi];
+        if ((a < b) == desc) {
+          sk[lo] = b;
+          sk[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int j = tid; j < k; j += kSampThreads) out[j] = (int)((~sk[j]) & 0xFFFFFFFFull);
+  __syncthreads();
+}
+
+// One CTA per group (an image for RoIs; the whole flattened batch for RPN anchors).
+__global__ void __launch_bounds__(kSampThreads) sample_fg_bg_kernel(
+    const int* __restrict__ labels, const float* __restrict__ scores /* or NULL */, float bg_low, int n, int exp_fg,
+    int total, int P, const float* __restrict__ keys_fg, const float* __restrict__ keys_bg,
+    const float* __restrict__ keys_up, int* __restrict__ ws /* [groups][2n] */, int* __restrict__ out /* [groups][total] */,
+    int* __restrict__ counts /* [groups][3]: n_pos, n_neg, n_keep (may be NULL) */) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* sk = reinterpret_cast<unsigned long long*>(smem_raw);  // [P]
+  int* keep = reinterpret_cast<int*>(sk + P);                                // [total]
+  int* sel = keep + total;                                                   // [total]
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_remaining, s_count;
+  __shared__ int s_pos[kSampThreads + 1], s_neg[kSampThreads + 1];
+  const int grp = blockIdx.x, tid = threadIdx.x;
+  labels += (long long)grp * n;
+  if (scores) scores += (long long)grp * n;
+  keys_fg += (long long)grp * n;
+  keys_bg += (long long)grp * n;
+  keys_up += (long long)grp * total;
+  int* pos_list = ws + (long long)grp * 2 * n;
+  int* neg_list = pos_list + n;
+  out += (long long)grp * total;
+
+  // ordered compaction of positives / negatives
+  const int chunk = (n + kSampThreads - 1) / kSampThreads;
+  const int i0 = min(n, tid * chunk), i1 = min(n, i0 + chunk);
+  int cp = 0, cn = 0;
+  for (int i = i0; i < i1; ++i) {
+    const int l = labels[i];
+    cp += l > 0;
+    cn += (l == 0) && (!scores || scores[i] > bg_low);
+  }
+  s_pos[tid + 1] = cp;
+  s_neg[tid + 1] = cn;
+  __syncthreads();
+  if (tid == 0) {
+    s_pos[0] = s_neg[0] = 0;
+    for (int t = 1; t <= kSampThreads; ++t) {
+      s_pos[t] += s_pos[t - 1];
+      s_neg[t] += s_neg[t - 1];
+    }
+  }
+  __syncthreads();
+  {
+    int op = s_pos[tid], on = s_neg[tid];
+    for (int i = i0; i < i1; ++i) {
+      const int l = labels[i];
+      if (l > 0) pos_list[op++] = i;
+      if ((l == 0) && (!scores || scores[i] > bg_low)) neg_list[on++] = i;
+    }
+  }
+  __syncthreads();
+  const int n_pos = s_pos[kSampThreads], n_neg = s_neg[kSampThreads];
+  int n_fg;
+  if (n_pos < exp_fg) {
+    n_fg = n_pos;
+    for (int j = tid; j < n_fg; j += kSampThreads) keep[j] = pos_list[j];
+  } else {
+    n_fg = exp_fg;
+    select_smallest(keys_fg, n_pos, n_fg, sel, sk, P, hist, &s_prefix, &s_remaining, &s_count);
+    for (int j = tid; j < n_fg; j += kSampThreads) keep[j] = pos_list[sel[j]];
+  }
+  __syncthreads();
+  const int exp_bg = total - min(n_pos, exp_fg);
+  int n_bg;
+  if (n_neg < exp_bg) {
+    n_bg = n_neg;
+    for (int j = tid; j < n_bg; j += kSampThreads) keep[n_fg + j] = neg_list[j];
+  } else {
+    n_bg = exp_bg;
+    select_smallest(keys_bg, n_neg, n_bg, sel, sk, P, hist, &s_prefix, &s_remaining, &s_count);
+    for (int j = tid; j < n_bg; j += kSampThreads) keep[n_fg + j] = neg_list[sel[j]];
+  }
+  __syncthreads();
+  const int n_keep = n_fg + n_bg;
+  if (counts && tid == 0) {
+    counts[grp * 3] = n_pos;
+    counts[grp * 3 + 1] = n_neg;
+    counts[grp * 3 + 2] = n_keep;
+  }
+  if (n_keep == 0) {
+    for (int j = tid; j < total; j += kSampThreads) out[j] = 0;
+    return;
+  }
+  if (n_keep >= total) {
+    for (int j = tid; j < total; j += kSampThreads) out[j] = keep[j];
+    return;
+  }
+  const int left = total - n_keep;
+  const int rem = left % n_keep;
+  const int tiled = n_keep * (left / n_keep + 1);
+  select_smallest(keys_up, n_keep, rem, sel, sk, P, hist, &s_prefix, &s_remaining, &s_count);
+  __syncthreads();
+  for (int j = tid; j < total; j += kSampThreads) out[j] = keep[j < tiled ? (j % n_keep) : sel[j - tiled]];
+}
+
+}  // namespace
+}  // namespace xdet
+
+using namespace xdet;
+
+extern "C" int xdet_col_stats_bf16(const void* d_x, long long rows, int C, int cs, int with_squares, float* d_sums,
+                                   void* stream) {
+  if (rows <= 0 || C <= 0) return XDET_OK;
+  if (C % 8 || cs % 8 || cs < C) return fail(XDET_EINVAL, "col_stats: C and the row pitch must be multiples of 8");
+  long long slabs = (rows + 63) / 64;
+  const long long cap = (long long)kNumSMs * 8 / ((C + 255) / 256);
+  if (slabs > cap) slabs = cap < 1 ? 1 : cap;
+  dim3 grid((unsigned)((C + 255) / 256), (unsigned)slabs);
+  if (with_squares)
+    col_stats_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_x), rows, C, cs, d_sums);
+  else
+    col_stats_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_x), rows, C, cs, d_sums);
+  return after_launch("col_stats_kernel");
+}
+
+extern "C" int xdet_bn_finalize(const float* d_sums, const float* d_gamma, const float* d_beta, long long rows, int C,
+                                float eps, float decay, float* d_moving_mean, float* d_moving_var, float* d_scale,
+                                float* d_shift, float* d_mean, float* d_invstd, void* stream) {
+  if (C <= 0 || rows <= 0) return fail(XDET_EINVAL, "bn_finalize: empty");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_sums, d_gamma, d_beta, rows, C, eps, decay,
+                                                                        d_moving_mean, d_moving_var, d_scale, d_shift,
+                                                                        d_mean, d_invstd);
+  return after_launch("bn_finalize_kernel");
+}
+
+extern "C" int xdet_bn_relu_bwd_bf16(const void* d_dy, const void* d_x, const float* d_scale, const float* d_shift,
+                                     const float* d_mean, const float* d_invstd, long long rows, int C, int relu,
+                                     const void* d_add_in, float* d_sums, void* d_dx, void* stream) {
+  if (rows <= 0 || C <= 0) return XDET_OK;
+  if (C % 8) return fail(XDET_EINVAL, "bn_relu_bwd: C must be a multiple of 8");
+  cudaStream_t st = (cudaStream_t)stream;
+  XDET_TRY(check_cuda(cudaMemsetAsync(d_sums, 0, sizeof(float) * 2 * C, st), "memset(bn sums)"));
+  long long slabs = (rows + 63) / 64;
+  const long long cap = (long long)kNumSMs * 8 / ((C + 255) / 256);
+  if (slabs > cap) slabs = cap < 1 ? 1 : cap;
+  dim3 grid((unsigned)((C + 255) / 256), (unsigned)slabs);
+  bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(d_dy),
+                                             reinterpret_cast<const __nv_bfloat16*>(d_x), d_scale, d_shift, d_mean,
+                                             d_invstd, rows, C, relu, d_sums);
+  XDET_TRY(after_launch("bn_bwd_reduce_kernel"));
+  bn_bwd_apply_kernel<<<blocks_for(rows * (C / 8)), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d_dy), reinterpret_cast<const __nv_bfloat16*>(d_x), d_scale, d_shift, d_mean,
+      d_invstd, d_sums, reinterpret_cast<const __nv_bfloat16*>(d_add_in), rows, C, relu,
+      reinterpret_cast<__nv_bfloat16*>(d_dx));
+  return after_launch("bn_bwd_apply_kernel");
+}
+
+extern "C" int xdet_maxpool3x3s2_bwd_bf16(const void* d_x, const void* d_dy, void* d_dx, int N, int H, int W, int C,
+                                          int Ho, int Wo, int pad_top, int pad_left, void* stream) {
+  if (C % 2) return fail(XDET_EINVAL, "maxpool_bwd: C must be even");
+  const long long total = (long long)N * H * W * (C / 2);
+  if (total <= 0) return XDET_OK;
+  maxpool_bwd_kernel<<<blocks_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d_x), reinterpret_cast<const __nv_bfloat16*>(d_dy),
+      reinterpret_cast<__nv_bfloat16*>(d_dx), N, H, W, C, Ho, Wo, pad_top, pad_left, total);
+  return after_launch("maxpool_bwd_kernel");
+}
+
+extern "C" int xdet_nchw_f32_to_nhwc_bf16(const float* d_src, void* d_dst, int N, int C, int HW, void* stream) {
+  const long long total = (long long)N * C * HW;
+  if (total <= 0) return XDET_OK;
+  nchw_f32_to_nhwc_bf16_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(
+      d_src, reinterpret_cast<__nv_bfloat16*>(d_dst), N, C, HW, total);
+  return after_launch("nchw_f32_to_nhwc_bf16_kernel");
+}
+
+extern "C" int xdet_affine_relu_to_nchw_f32(const void* d_src, const float* d_scale, const float* d_shift, float* d_dst,
+                                            int N, int C, int HW, int relu, void* stream) {
+  const long long total = (long long)N * C * HW;
+  if (total <= 0) return XDET_OK;
+  affine_relu_to_nchw_f32_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d_src), d_scale, d_shift, d_dst, N, C, HW, relu, total);
+  return after_launch("affine_relu_to_nchw_f32_kernel");
+}
+
+extern "C" int xdet_softmax_ce(const float* d_logits, int ld, int C, const int* d_labels, const float* d_row_w,
+                               float w_all, long long M, float* d_loss_row, float* d_dlogits, int dld, void* stream) {
+  if (M <= 0) return XDET_OK;
+  if (C <= 0 || ld < C || (d_dlogits && dld < C)) return fail(XDET_EINVAL, "softmax_ce: bad class count / pitch");
+  softmax_ce_kernel<<<(unsigned)((M + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_logits, ld, C, d_labels, d_row_w,
+                                                                                  w_all, M, d_loss_row, d_dlogits, dld);
+  return after_launch("softmax_ce_kernel");
+}
+
+extern "C" int xdet_smooth_l1(const float* d_pred, int ld, const float* d_target, const float* d_row_w, float w_all,
+                              long long M, float* d_loss_row, float* d_dpred, int dld, void* stream) {
+  if (M <= 0) return XDET_OK;
+  if (ld < 4 || (d_dpred && dld < 4)) return fail(XDET_EINVAL, "smooth_l1: pitch < 4");
+  smooth_l1_kernel<<<(unsigned)((M + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_pred, ld, d_target, d_row_w, w_all, M,
+                                                                                 d_loss_row, d_dpred, dld);
+  return after_launch("smooth_l1_kernel");
+}
+
+extern "C" int xdet_sgd_momentum_conv(const float* d_dw, float* d_w, float* d_mom, void* d_w_pack, void* d_w_dgrad_pack,
+                                      int Cout, int KH, int KW, int Cin, int pack_co_off, int pack_ci_off,
+                                      int pack_cin_pad, int pack_cout_pad, int fold, float lr, float momentum, float wd,
+                                      float grad_scale, void* stream) {
+  const long long total = (long long)Cout * KH * KW * Cin;
+  if (total <= 0) return XDET_OK;
+  if (fold && (KW * 8 > 64 || Cin > 8)) return fail(XDET_EINVAL, "sgd_conv: bad fold geometry");
+  const long long taps = (long long)KH * KW;
+  // offsets select this variable's slice of a fused (concatenated) pack
+  const float* dw = d_dw + ((long long)pack_co_off * taps) * (fold ? 64 : pack_cin_pad) + (fold ? 0 : pack_ci_off);
+  __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(d_w_pack) +
+                      ((long long)pack_co_off * taps) * (fold ? 64 : pack_cin_pad) + (fold ? 0 : pack_ci_off);
+  __nv_bfloat16* wdp = d_w_dgrad_pack ? reinterpret_cast<__nv_bfloat16*>(d_w_dgrad_pack) +
+                                            ((long long)pack_ci_off * taps) * pack_cout_pad + pack_co_off
+                                      : nullptr;
+  sgd_conv_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(dw, d_w, d_mom, wp, wdp, Cout, KH, KW, Cin,
+                                                                      pack_cin_pad, pack_cout_pad, fold, lr, momentum, wd,
+                                                                      grad_scale, total);
+  return after_launch("sgd_conv_kernel");
+}
+
+extern "C" int xdet_sgd_momentum_vec(const float* d_g, float* d_w, float* d_mom, long long n, float lr, float momentum,
+                                     float wd, float grad_scale, void* stream) {
+  if (n <= 0) return XDET_OK;
+  sgd_vec_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_g, d_w, d_mom, n, lr, momentum, wd,
+                                                                               grad_scale);
+  return after_launch("sgd_vec_kernel");
+}
+
+extern "C" size_t xdet_match_workspace_bytes(int N, int G) { return sizeof(unsigned long long) * (size_t)N * (size_t)G; }
+
+extern "C" int xdet_match_encode(const float* d_boxes, long long box_img_stride, const float* d_ref_yxhw,
+                                 const float* d_gt, const int* d_gt_labels, int N, int A, int G, float allowed_border,
+                                 float high_thres, float low_thres, const float* prior_scaling4, int* d_labels,
+                                 float* d_targets, float* d_scores, void* d_workspace, void* stream) {
+  if (N <= 0 || A <= 0 || G <= 0) return fail(XDET_EINVAL, "match_encode: empty");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* best = reinterpret_cast<unsigned long long*>(d_workspace);
+  XDET_TRY(check_cuda(cudaMemsetAsync(best, 0, sizeof(unsigned long long) * (size_t)N * G, st), "memset(match)"));
+  dim3 grid((unsigned)((A + 255) / 256), (unsigned)N);
+  // pass 1 reads boxes with the same per-image stride
+  if (box_img_stride == 0) {
+    // shared boxes: one launch per image keeps the kernel simple (N is small)
+    for (int i = 0; i < N; ++i) {
+      match_gt_argmax_kernel<<<dim3(grid.x, 1), 256, 0, st>>>(d_boxes, d_gt + (long long)i * G * 4, d_gt_labels + (long long)i * G,
+                                                              A, G, allowed_border, best + (long long)i * G);
+      XDET_TRY(after_launch("match_gt_argmax_kernel"));
+    }
+  } else {
+    if (box_img_stride != (long long)A * 4) return fail(XDET_EINVAL, "match_encode: box_img_stride must be 0 or A*4");
+    match_gt_argmax_kernel<<<grid, 256, 0, st>>>(d_boxes, d_gt, d_gt_labels, A, G, allowed_border, best);
+    XDET_TRY(after_launch("match_gt_argmax_kernel"));
+  }
+  match_encode_kernel<<<grid, 256, 0, st>>>(d_boxes, box_img_stride, d_ref_yxhw, d_gt, d_gt_labels, best, A, G,
+                                            allowed_border, high_thres, low_thres, prior_scaling4[0], prior_scaling4[1],
+                                            prior_scaling4[2], prior_scaling4[3], d_labels, d_targets, d_scores);
+  return after_launch("match_encode_kernel");
+}
+
+extern "C" int xdet_sample_fg_bg(const int* d_labels, const float* d_scores, float bg_low, int groups, int n, int exp_fg,
+                                 int total, const float* d_keys_fg, const float* d_keys_bg, const float* d_keys_up,
+                                 int* d_workspace /* [groups][2n] */, int* d_out, int* d_counts, void* stream) {
+  if (groups <= 0 || n <= 0 || total <= 0) return fail(XDET_EINVAL, "sample_fg_bg: empty");
+  if (total > 4096) return fail(XDET_EINVAL, "sample_fg_bg: at most 4096 samples per group");
+  int P = 2;
+  while (P < total) P <<= 1;
+  const size_t smem = sizeof(unsigned long long) * P + sizeof(int) * 2 * (size_t)total;
+  XDET_TRY(check_cuda(cudaFuncSetAttribute(sample_fg_bg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024),
+                      "cudaFuncSetAttribute(sample)"));
+  sample_fg_bg_kernel<<<groups, kSampThreads, smem, (cudaStream_t)stream>>>(d_labels, d_scores, bg_low, n, exp_fg, total, P,
+                                                                           d_keys_fg, d_keys_bg, d_keys_up, d_workspace,
+                                                                           d_out, d_counts);
+  return after_launch("sample_fg_bg_kernel");
+}

@@ -1,0 +1,168 @@
+"""Host wrappers of the training-step kernels (``csrc/train_ops.cu``): batch-norm with batch statistics and
+its backward, pooling backward, losses, the momentum step, target assignment and sampling.  Torch tensors are
+the container only."""
+import ctypes
+
+import torch
+
+from .. import _native
+from .conv import same_pad
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def col_stats(x2d, with_squares=True, C=None):
+    """x2d [rows, cs] bf16 -> fp32 [2*C] (sums, sums of squares) or [C]."""
+    rows, cs = x2d.shape
+    C = cs if C is None else C
+    sums = torch.zeros((2 if with_squares else 1) * C, dtype=torch.float32, device=x2d.device)
+    _native.check(_native.lib().xdet_col_stats_bf16(x2d.data_ptr(), rows, C, cs, 1 if with_squares else 0,
+                                                    sums.data_ptr(), _st()))
+    return sums
+
+
+class BNState(object):
+    """What the backward of one training-mode batch-norm needs."""
+    __slots__ = ("scale", "shift", "mean", "invstd", "rows")
+
+
+def bn_train(x, gamma, beta, eps, decay=None, moving_mean=None, moving_var=None):
+    """Batch statistics of x [..., C] bf16 -> BNState (scale/shift normalise with the BATCH mean/variance)."""
+    C = x.shape[-1]
+    x2 = x.reshape(-1, C)
+    sums = col_stats(x2, True)
+    st = BNState()
+    st.rows = x2.shape[0]
+    st.scale, st.shift, st.mean, st.invstd = (torch.empty(C, dtype=torch.float32, device=x.device) for _ in range(4))
+    _native.check(_native.lib().xdet_bn_finalize(sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), st.rows, C, eps,
+                                                 0.0 if decay is None else decay, _p(moving_mean), _p(moving_var),
+                                                 st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(),
+                                                 st.invstd.data_ptr(), _st()))
+    return st
+
+
+def bn_relu_bwd(dy, x, st, relu=True, add_in=None):
+    """-> (dx bf16 like x, dgamma [C], dbeta [C]) for y = relu(x*scale+shift) with batch statistics."""
+    C = x.shape[-1]
+    assert dy.shape == x.shape and dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16
+    assert dy.is_contiguous() and x.is_contiguous() and (add_in is None or add_in.is_contiguous())
+    sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+    dx = torch.empty_like(x)
+    _native.check(_native.lib().xdet_bn_relu_bwd_bf16(dy.data_ptr(), x.data_ptr(), st.scale.data_ptr(),
+                                                      st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
+                                                      st.rows, C, 1 if relu else 0, _p(add_in), sums.data_ptr(),
+                                                      dx.data_ptr(), _st()))
+    return dx, sums[C:], sums[:C]
+
+
+def maxpool3x3s2_bwd(x, dy):
+    N, H, W, C = x.shape
+    _, Ho, Wo, _ = dy.shape
+    dx = torch.empty_like(x)
+    _native.check(_native.lib().xdet_maxpool3x3s2_bwd_bf16(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), N, H, W, C, Ho, Wo,
+                                                           same_pad(H, 3, 1, 2), same_pad(W, 3, 1, 2), _st()))
+    return dx
+
+
+def nchw_f32_to_nhwc_bf16(x):
+    N, C, H, W = x.shape
+    out = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=x.device)
+    _native.check(_native.lib().xdet_nchw_f32_to_nhwc_bf16(x.data_ptr(), out.data_ptr(), N, C, H * W, _st()))
+    return out
+
+
+def affine_relu_to_nchw_f32(x, scale, shift, relu=True):
+    N, H, W, C = x.shape
+    out = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
+    _native.check(_native.lib().xdet_affine_relu_to_nchw_f32(x.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                                             out.data_ptr(), N, C, H * W, 1 if relu else 0, _st()))
+    return out
+
+
+def softmax_ce(logits, labels, num_classes, row_w=None, w_all=1.0, dlogits=None):
+    """logits [M, ld] fp32 (classes in the first num_classes columns), labels [M] int32 ->
+    (loss_row [M], dlogits [M, dld] = w_all*row_w*(softmax-onehot), written into ``dlogits`` if given)."""
+    M, ld = logits.shape
+    loss = torch.empty(M, dtype=torch.float32, device=logits.device)
+    if dlogits is None:
+        dlogits = torch.zeros((M, ld), dtype=torch.float32, device=logits.device)
+    _native.check(_native.lib().xdet_softmax_ce(logits.data_ptr(), logits.stride(0), num_classes, labels.data_ptr(),
+                                                _p(row_w), w_all, M, loss.data_ptr(), dlogits.data_ptr(),
+                                                dlogits.stride(0), _st()))
+    return loss, dlogits
+
+
+def smooth_l1(pred, target, row_w=None, w_all=1.0, dpred=None):
+    """pred [M, >=4] fp32 view (row stride arbitrary), target [M,4] -> (loss_row [M], dpred)."""
+    M = pred.shape[0]
+    loss = torch.empty(M, dtype=torch.float32, device=pred.device)
+    if dpred is None:
+        dpred = torch.zeros((M, 4), dtype=torch.float32, device=pred.device)
+    assert target.is_contiguous() and target.shape == (M, 4)
+    _native.check(_native.lib().xdet_smooth_l1(pred.data_ptr(), pred.stride(0), target.data_ptr(), _p(row_w), w_all, M,
+                                               loss.data_ptr(), dpred.data_ptr(), dpred.stride(0), _st()))
+    return loss, dpred
+
+
+def sgd_momentum_conv(dw, w, mom, w_pack, w_dgrad_pack, lr, momentum, wd, grad_scale=1.0, co_off=0, ci_off=0,
+                      fold=False):
+    """w/mom: fp32 master + accumulator in TF layout [kh,kw,cin,cout] (or [cin,units] for dense); dw: packed fp32
+    gradient [Cout_total, taps, cin_pad]; w_pack / w_dgrad_pack: the bf16 packs to refresh."""
+    if w.dim() == 2:
+        kh = kw = 1
+        cin, cout = w.shape
+    else:
+        kh, kw, cin, cout = w.shape
+    cin_pad = dw.shape[-1]
+    cout_pad = 0 if w_dgrad_pack is None else w_dgrad_pack.shape[-1] // (kh * kw)
+    _native.check(_native.lib().xdet_sgd_momentum_conv(dw.data_ptr(), w.data_ptr(), mom.data_ptr(), w_pack.data_ptr(),
+                                                       _p(w_dgrad_pack), cout, kh, kw, cin, co_off, ci_off, cin_pad,
+                                                       cout_pad, 1 if fold else 0, lr, momentum, wd, grad_scale, _st()))
+
+
+def sgd_momentum_vec(g, w, mom, lr, momentum, wd=0.0, grad_scale=1.0):
+    _native.check(_native.lib().xdet_sgd_momentum_vec(g.data_ptr(), w.data_ptr(), mom.data_ptr(), w.numel(), lr,
+                                                      momentum, wd, grad_scale, _st()))
+
+
+def match_encode(boxes, gt, gt_labels, allowed_border, high_thres, low_thres, prior_scaling=(1., 1., 1., 1.),
+                 ref_yxhw=None):
+    """boxes [A,4] (shared by all images; pass ref_yxhw [A,4] = the anchors' centre form) or [N,A,4];
+    gt [N,G,4] fp32, gt_labels [N,G] int32 (<= 0: padding) -> labels [N,A] int32, targets [N,A,4], scores [N,A]."""
+    N, G = gt_labels.shape
+    shared = boxes.dim() == 2
+    A = boxes.shape[-2]
+    dev = gt.device
+    labels = torch.empty((N, A), dtype=torch.int32, device=dev)
+    targets = torch.empty((N, A, 4), dtype=torch.float32, device=dev)
+    scores = torch.empty((N, A), dtype=torch.float32, device=dev)
+    lib = _native.lib()
+    ws = torch.empty(max(8, lib.xdet_match_workspace_bytes(N, G)), dtype=torch.uint8, device=dev)
+    ps = (ctypes.c_float * 4)(*prior_scaling)
+    assert boxes.is_contiguous() and gt.is_contiguous() and gt_labels.dtype == torch.int32 and gt_labels.is_contiguous()
+    _native.check(lib.xdet_match_encode(boxes.data_ptr(), 0 if shared else A * 4, _p(ref_yxhw), gt.data_ptr(),
+                                        gt_labels.data_ptr(), N, A, G, allowed_border, high_thres, low_thres, ps,
+                                        labels.data_ptr(), targets.data_ptr(), scores.data_ptr(), ws.data_ptr(), _st()))
+    return labels, targets, scores
+
+
+def sample_fg_bg(labels, scores, bg_low, exp_fg, total, keys_fg, keys_bg, keys_up):
+    """labels [groups, n] int32 (scores [groups, n] or None) -> (indices [groups, total] int32, counts [groups, 3])."""
+    groups, n = labels.shape
+    dev = labels.device
+    out = torch.empty((groups, total), dtype=torch.int32, device=dev)
+    counts = torch.empty((groups, 3), dtype=torch.int32, device=dev)
+    ws = torch.empty((groups, 2 * n), dtype=torch.int32, device=dev)
+    for k in (keys_fg, keys_bg):
+        assert k.shape == (groups, n) and k.dtype == torch.float32 and k.is_contiguous()
+    assert keys_up.shape == (groups, total) and keys_up.is_contiguous()
+    _native.check(_native.lib().xdet_sample_fg_bg(labels.data_ptr(), _p(scores), bg_low, groups, n, exp_fg, total,
+                                                  keys_fg.data_ptr(), keys_bg.data_ptr(), keys_up.data_ptr(),
+                                                  ws.data_ptr(), out.data_ptr(), counts.data_ptr(), _st()))
+    return out, counts
