@@ -142,6 +142,7 @@ typedef struct {
   int Hout, Wout, dy_cs;
   float* dw;
   int splits; /* 0 = auto: enough pixel splits to fill the GPU */
+  int fold_w, in_wp; /* as in xdet_conv_desc (the stem); dw is then [Cout][KH][64] with element kw*in_cs + ci */
 } xdet_wgrad_desc;
 int xdet_conv2d_wgrad_bf16(const void* d_x, const void* d_dy, const xdet_wgrad_desc* desc, void* stream);
 
@@ -226,7 +227,8 @@ int xdet_head_decode(const float* d_rois, const float* d_head_out, int ch_stride
  *   xdet_bn_relu_bwd_bf16 gradient of y = relu(x*scale+shift) w.r.t. x (two passes: reduce, apply), + d_add_in
  *                         (a gradient arriving over the identity shortcut); d_sums[0..C) = dbeta, [C..2C) = dgamma.
  * xdet_maxpool3x3s2_bwd_bf16  gradient of tf.layers.max_pooling2d(3,2,'SAME') (first maximum of each window).
- * xdet_nchw_f32_to_nhwc_bf16 / xdet_affine_relu_to_nchw_f32  repacks around the fp32 NCHW thin feature map.
+ * xdet_nchw_f32_to_nhwc_bf16 / xdet_affine_relu_to_nchw_f32  repacks around the fp32 NCHW thin feature map; the
+ *                     NHWC side has a channel pitch (490 channels live in rows of 496, zero tail).
  * xdet_softmax_ce     tf.nn.sparse_softmax_cross_entropy_with_logits: loss_row[r] and
  *                     dlogits[r,c] = w_all * row_w[r] * (softmax - onehot) (light_head_rfcn_train.py:361,385).
  * xdet_smooth_l1      modified_smooth_l1 (:257-275, sigma 1) summed over the 4 coordinates, times row_w; gradient.
@@ -246,11 +248,14 @@ int xdet_bn_finalize(const float* d_sums, const float* d_gamma, const float* d_b
 int xdet_bn_relu_bwd_bf16(const void* d_dy, const void* d_x, const float* d_scale, const float* d_shift,
                           const float* d_mean, const float* d_invstd, long long rows, int C, int relu,
                           const void* d_add_in, float* d_sums, void* d_dx, void* stream);
+/* dx = dy where y > 0 else 0 (gradient of a ReLU fused into a convolution epilogue); bf16, n elements (n % 8 == 0) */
+int xdet_relu_bwd_bf16(const void* d_dy, const void* d_y, void* d_dx, long long n, void* stream);
+/* fp32 [rows, cols] -> bf16 [rows, dst_pitch] is xdet_f32_to_bf16_rows above */
 int xdet_maxpool3x3s2_bwd_bf16(const void* d_x, const void* d_dy, void* d_dx, int N, int H, int W, int C, int Ho, int Wo,
                                int pad_top, int pad_left, void* stream);
-int xdet_nchw_f32_to_nhwc_bf16(const float* d_src, void* d_dst, int N, int C, int HW, void* stream);
+int xdet_nchw_f32_to_nhwc_bf16(const float* d_src, void* d_dst, int N, int C, int dst_cs, int HW, void* stream);
 int xdet_affine_relu_to_nchw_f32(const void* d_src, const float* d_scale, const float* d_shift, float* d_dst, int N,
-                                 int C, int HW, int relu, void* stream);
+                                 int C, int src_cs, int HW, int relu, void* stream);
 int xdet_softmax_ce(const float* d_logits, int ld, int C, const int* d_labels, const float* d_row_w, float w_all,
                     long long M, float* d_loss_row, float* d_dlogits, int dld, void* stream);
 int xdet_smooth_l1(const float* d_pred, int ld, const float* d_target, const float* d_row_w, float w_all, long long M,

@@ -70,3 +70,22 @@ def test_wgrad_accumulates_and_splits_agree(ops):
     torch.cuda.synchronize()
     assert (a - b).abs().max().item() < 1e-3 * a.abs().max().item()
     assert (c - 2 * a).abs().max().item() < 1e-3 * a.abs().max().item()
+
+
+def test_stem_fold_wgrad(ops):
+    """dW of the 7x7/s2 stem on the 3-channel image (fold_w operand: a K chunk = one filter row of the padded NHWC8 image)."""
+    g = torch.Generator(device="cuda").manual_seed(8)
+    N, H, W = 2, 96, 96
+    img = torch.rand((N, 3, H, W), generator=g, device="cuda") * 2 - 1
+    w = torch.randn((64, 3, 7, 7), generator=g, device="cuda") / 147 ** 0.5
+    Ho = Wo = 48
+    wp = (max((Wo - 1) * 2 + 8, W + 3) + 7) // 8 * 8
+    x8 = ops.image_to_nhwc8(img, 3, wp)
+    dy = torch.randn((N, Ho, Wo, 64), generator=g, device="cuda").to(torch.bfloat16)
+    dw = ops.conv2d_wgrad(x8, dy, 7, 7, padding=(3, 3, Ho, Wo), strides=(2, 2), cin=3, cout=64, fold_w=(W, 3))
+    torch.cuda.synchronize()
+    xf = img.to(torch.bfloat16).float()
+    wf = w.clone().requires_grad_(True)
+    F.conv2d(xf, wf, stride=2, padding=3).backward(dy.float().permute(0, 3, 1, 2))
+    got = dw.reshape(64, 7, 8, 8)[:, :, :7, :3].permute(0, 3, 1, 2)  # [co][kh][kw][c] -> [co][c][kh][kw]
+    assert (got - wf.grad).abs().max().item() < 2e-3 * max(1.0, wf.grad.abs().max().item())

@@ -1,0 +1,130 @@
+"""GPU: one Light-Head R-CNN training step (forward in training mode, losses, explicit backward, momentum step)
+against the PyTorch-CPU fp32 autograd restatement (oracle/net_train.py) on the same variables, with the discrete
+selections of the GPU step injected into the oracle (they are checked exactly elsewhere).  The tensor-core path
+computes in bf16: losses agree to ~1e-2 relative, gradients are compared by cosine similarity and norm ratio."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import net_train as ont
+from oracle import proposals as op
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(layers):
+    assert torch.cuda.is_available()
+    import xdet_b200  # noqa: F401
+    from xdet_b200 import light_head_rfcn_train as lt
+    params = lt.make_params(train_image_size=160, batch_size=2, rpn_pre_nms_top_n=600, rpn_post_nms_top_n=200,
+                            rpn_min_size=16.0 / 160, rpn_anchors_per_image=64, roi_one_image=32, ohem_roi_one_image=16,
+                            resnet_layers=layers)
+    tr = lt.LightHeadTrainer(params, seed=7)
+    sd0 = {k: v.detach().clone() for k, v in tr.store.state_dict().items()}
+    batch = lt.synthetic_batch(params, 2, seed=3)
+    out = tr.step(*batch, apply_update=False)
+    torch.cuda.synchronize()
+    return lt, params, tr, sd0, batch, out
+
+
+@pytest.fixture(scope="module")
+def run():
+    """The full ResNet-50 depth (3,4,6,3)."""
+    return _run((3, 4, 6, 3))
+
+
+@pytest.fixture(scope="module")
+def run_shallow():
+    """One bottleneck per block_layer: every layer type / gradient path of the step, but shallow enough that the
+    bf16-vs-fp32 rounding noise is not amplified by 16 randomly initialised blocks with batch statistics."""
+    return _run((1, 1, 1, 1))
+
+
+def test_variable_names_match_the_inference_model(run):
+    lt, params, tr, sd0, batch, out = run
+    from xdet_b200 import light_head_rfcn_eval as lh
+    m = lh.LightHeadRFCN(lh.make_params(train_image_size=160), seed=1)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    m(torch.rand((1, 3, 160, 160), generator=g, device="cuda"))
+    assert set(m.store.state_dict()) == set(sd0)
+    for k, v in m.store.state_dict().items():
+        assert tuple(v.shape) == tuple(sd0[k].shape), k
+
+
+@pytest.mark.parametrize("depth", ["shallow", "resnet50"])
+def test_losses_and_gradients_vs_autograd_oracle(run, run_shallow, depth):
+    lt, params, tr, sd0, batch, out = run_shallow if depth == "shallow" else run
+    # shallow: tight; full depth at random init: the forward already differs by ~30 % RMS at block_layer4 (measured
+    # layer by layer with tools/train_fwd_check.py: 0.9 % after the first block, x1.1-1.3 per block), so only the
+    # gradient norms and a loose direction bound are asserted there
+    cos_min, cos_vec_min, n_min = (0.93, 0.9, 20) if depth == "shallow" else (0.3, 0.15, 60)
+    images, gt, gl, keys = batch
+    anchors = op.layer_anchors((160, 160), (10, 10), [0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8], [0.1], [1., 2., .5], 16)
+    inject = {k: out[k].cpu().numpy() for k in ("rpn_idx", "rois_all", "roi_idx", "ohem_idx")}
+    losses, grads, mid = ont.train_step(images.cpu().numpy(), gt.cpu().numpy(), gl.cpu().numpy(), sd0, params, anchors,
+                                        inject)
+    # discrete targets are exact
+    assert np.array_equal(out["glabels"].cpu().numpy().reshape(-1), mid["glabels"])
+    assert np.array_equal(out["roi_labels"].cpu().numpy(), mid["roi_labels"])
+    for k in ("rpn_cross_entropy_loss", "rpn_location_loss", "head_loss"):
+        a, b = float(out[k]), losses[k]
+        assert abs(a - b) < 5e-2 * max(1.0, abs(b)), (k, a, b)
+
+    def tf_layout(cp, i):
+        key, t, co, ci = cp.masters[i]
+        kh, kw = cp.kh, cp.kw
+        if t.dim() == 2:
+            cin, cout = t.shape
+        else:
+            cin, cout = t.shape[2], t.shape[3]
+        if cp.fold:
+            d = cp.dw.reshape(cp.cout, kh, 8, 8)[:, :, :kw, :cin]  # [co][kh][kw][c]
+            return key, d.permute(1, 2, 3, 0)
+        d = cp.dw[co:co + cout, :, ci:ci + cin].reshape(cout, kh, kw, cin).permute(1, 2, 3, 0)
+        return key, d.reshape(t.shape)
+
+    cos_bad, checked = [], 0
+    for cp in tr.convs:
+        for i in range(len(cp.masters)):
+            key, d = tf_layout(cp, i)
+            ref = grads[key].reshape(d.shape)
+            a, b = d.float().cpu().flatten(), ref.flatten()
+            if b.norm() < 1e-8:
+                continue
+            cos = float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-20))
+            ratio = float(a.norm() / b.norm())
+            checked += 1
+            if cos < cos_min or not (0.85 < ratio < 1.15):
+                cos_bad.append((key, round(cos, 4), round(ratio, 4)))
+    assert checked >= n_min
+    assert not cos_bad, cos_bad[:10]
+    # vectors: batch-norm gamma/beta and biases
+    vec_bad = []
+    for v in tr.vecs:
+        for i, t in enumerate(v.tensors):
+            key = [k for k, val in tr.store.vars.items() if val.data_ptr() == t.data_ptr() and val.numel() == t.numel()]
+            if not key:
+                continue  # fused bias views are checked through their parts below
+            ref = grads[key[0]].flatten()
+            a = v.grad[i * v.seg:i * v.seg + t.numel()].cpu()
+            if ref.norm() < 1e-4:  # e.g. a bias in front of a training-mode batch-norm: its true gradient is 0
+                assert a.norm() < 1e-2, key[0]
+                continue
+            cos = float(torch.dot(a, ref) / (a.norm() * ref.norm() + 1e-20))
+            if cos < cos_vec_min:
+                vec_bad.append((key[0], round(cos, 4)))
+    assert not vec_bad, vec_bad[:10]
+
+
+def test_update_moves_the_weights_and_the_loss(run):
+    lt, params, tr, sd0, batch, out = run
+    l0 = sum(float(out[k]) for k in ("rpn_cross_entropy_loss", "rpn_location_loss", "head_loss"))
+    inj = {k: out[k] for k in ("rpn_idx", "rois_all", "roi_idx", "ohem_idx")}
+    tr.params = dict(tr.params, learning_rate=0.02)
+    for _ in range(3):
+        o = tr.step(*batch, inject=inj)
+    l1 = sum(float(o[k]) for k in ("rpn_cross_entropy_loss", "rpn_location_loss", "head_loss"))
+    assert np.isfinite(l1) and l1 < l0, (l0, l1)
+    moved = sum(1 for k, v in tr.store.state_dict().items() if not torch.equal(v, sd0[k]))
+    assert moved > 150
+    assert tr.global_step == 3

@@ -78,9 +78,10 @@ def _declare_train(lib):
     lib.xdet_col_stats_bf16.argtypes = [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p]
     lib.xdet_bn_finalize.argtypes = [c_void_p] * 3 + [c_ll, c_int, c_float, c_float] + [c_void_p] * 7
     lib.xdet_bn_relu_bwd_bf16.argtypes = [c_void_p] * 6 + [c_ll, c_int, c_int] + [c_void_p] * 4
+    lib.xdet_relu_bwd_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_ll, c_void_p]
     lib.xdet_maxpool3x3s2_bwd_bf16.argtypes = [c_void_p] * 3 + [c_int] * 8 + [c_void_p]
-    lib.xdet_nchw_f32_to_nhwc_bf16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
-    lib.xdet_affine_relu_to_nchw_f32.argtypes = [c_void_p] * 4 + [c_int] * 4 + [c_void_p]
+    lib.xdet_nchw_f32_to_nhwc_bf16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+    lib.xdet_affine_relu_to_nchw_f32.argtypes = [c_void_p] * 4 + [c_int] * 5 + [c_void_p]
     lib.xdet_softmax_ce.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_ll, c_void_p, c_void_p, c_int,
                                     c_void_p]
     lib.xdet_smooth_l1.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_float, c_ll, c_void_p, c_void_p, c_int, c_void_p]

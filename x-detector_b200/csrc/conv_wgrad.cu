@@ -241,10 +241,13 @@ extern "C" int xdet_conv2d_wgrad_bf16(const void* d_x, const void* d_dy, const x
   const int sh = d->stride_h <= 0 ? 1 : d->stride_h, sw = d->stride_w <= 0 ? 1 : d->stride_w;
   if (sh > 2 || sw > 2) return fail(XDET_EINVAL, "wgrad: strides 1 and 2 are supported");
   const int dil_h = d->dil_h <= 0 ? 1 : d->dil_h, dil_w = d->dil_w <= 0 ? 1 : d->dil_w;
+  const bool fold = d->fold_w != 0;  // the stem: x is the row-padded NHWC8 image, a K chunk = one filter row
+  if (fold && (d->KW * d->in_cs > 64 || dil_w != 1 || d->in_wp < (d->Wout - 1) * sw + 64 / d->in_cs))
+    return fail(XDET_EINVAL, "wgrad: fold_w needs KW*in_cs <= 64, dil_w == 1 and in_wp >= (Wout-1)*stride_w + 64/in_cs");
 
   // 1x1 stride-1 convolutions flatten to one long pixel row (no ragged tiles)
   int N = d->N, H = d->H, W = d->W, Hout = d->Hout, Wout = d->Wout;
-  if (d->KH == 1 && d->KW == 1 && sh == 1 && sw == 1 && d->pad_top == 0 && d->pad_left == 0 && Hout == H && Wout == W &&
+  if (!fold && d->KH == 1 && d->KW == 1 && sh == 1 && sw == 1 && d->pad_top == 0 && d->pad_left == 0 && Hout == H && Wout == W &&
       (long long)N * H * W < (1ll << 31)) {
     W = Wout = N * H * W;
     H = Hout = 1;
@@ -260,16 +263,16 @@ extern "C" int xdet_conv2d_wgrad_bf16(const void* d_x, const void* d_dy, const x
   a.tiles_y = (Hout + a.BH - 1) / a.BH;
   a.n_img = N;
   a.pix_tiles = a.tiles_x * a.tiles_y * N;
-  a.taps_w = d->KW;
-  a.taps = d->KH * d->KW;
+  a.taps_w = fold ? 1 : d->KW;
+  a.taps = fold ? d->KH : d->KH * d->KW;
   a.dil_h = dil_h;
-  a.dil_w = dil_w;
+  a.dil_w = fold ? 0 : dil_w;
   a.pad_top = d->pad_top;
-  a.pad_left = d->pad_left;
-  a.mul_x = sw;
+  a.pad_left = fold ? 0 : d->pad_left;
+  a.mul_x = fold ? 1 : sw;
   a.mul_y = sh;
   a.Cout = d->Cout;
-  a.cin_pad = (d->Cin + 63) / 64 * 64;
+  a.cin_pad = fold ? 64 : (d->Cin + 63) / 64 * 64;
   a.co_tiles = (d->Cout + 127) / 128;
   a.BN = a.cin_pad >= 256 ? 256 : (a.cin_pad >= 128 ? 128 : 64);
   a.ci_tiles = (a.cin_pad + a.BN - 1) / a.BN;
@@ -299,7 +302,14 @@ extern "C" int xdet_conv2d_wgrad_bf16(const void* d_x, const void* d_dy, const x
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     XDET_TRY(wg_encode(&map_dy, d_dy, dims, strides, box, estr));
   }
-  {
+  if (fold) {
+    const cuuint64_t dims[4] = {64, (cuuint64_t)Wout, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)sw * d->in_cs * 2, (cuuint64_t)d->in_wp * d->in_cs * 2,
+                                   (cuuint64_t)d->in_wp * d->in_cs * 2 * H};
+    const cuuint32_t box[4] = {64, (cuuint32_t)a.BW, (cuuint32_t)(a.BH * sh), 1};
+    const cuuint32_t estr[4] = {1, 1, (cuuint32_t)sh, 1};
+    XDET_TRY(wg_encode(&map_x, d_x, dims, strides, box, estr));
+  } else {
     const cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t strides[3] = {(cuuint64_t)d->in_cs * 2, (cuuint64_t)d->in_cs * 2 * W,
                                    (cuuint64_t)d->in_cs * 2 * W * H};

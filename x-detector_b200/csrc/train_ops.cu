@@ -249,27 +249,45 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
   }
 }
 
+__global__ void relu_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, uint4* __restrict__ dx,
+                                long long n8) {
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n8; e += step) {
+    const uint4 d = __ldg(dy + e), v = __ldg(y + e);
+    const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&d);
+    const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&v);
+    uint4 o;
+    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fd = __bfloat1622float2(hd[k]), fv = __bfloat1622float2(hv[k]);
+      ho[k] = __floats2bfloat162_rn(fv.x > 0.f ? fd.x : 0.f, fv.y > 0.f ? fd.y : 0.f);
+    }
+    dx[e] = o;
+  }
+}
+
 // [N,C,H,W] fp32 -> [N,H,W,C] bf16 and [N,H,W,C] bf16 -> relu(x*scale+shift) as [N,C,H,W] fp32 (thin feature map)
 __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int C,
-                                             int HW, long long total) {
+                                             int cs, int HW, long long total) {
   const long long step = (long long)gridDim.x * blockDim.x;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
-    const int c = (int)(e % C);
-    const long long p = e / C;  // n*HW + hw
+    const int c = (int)(e % cs);
+    const long long p = e / cs;  // n*HW + hw
     const long long n = p / HW, hw = p % HW;
-    dst[e] = __float2bfloat16_rn(__ldg(src + (n * C + c) * HW + hw));
+    dst[e] = __float2bfloat16_rn(c < C ? __ldg(src + (n * C + c) * HW + hw) : 0.f);  // zero channel tail
   }
 }
 __global__ void affine_relu_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ src, const float* __restrict__ scale,
                                                const float* __restrict__ shift, float* __restrict__ dst, int N, int C,
-                                               int HW, int relu, long long total) {
+                                               int cs, int HW, int relu, long long total) {
   const long long step = (long long)gridDim.x * blockDim.x;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
     const long long hw = e % HW;
     const long long t = e / HW;
     const int c = (int)(t % C);
     const long long n = t / C;
-    float v = fmaf(__bfloat162float(src[(n * HW + hw) * C + c]), __ldg(scale + c), __ldg(shift + c));
+    float v = fmaf(__bfloat162float(src[(n * HW + hw) * cs + c]), __ldg(scale + c), __ldg(shift + c));
     if (relu) v = fmaxf(v, 0.f);
     dst[e] = v;
   }
@@ -676,6 +694,14 @@ extern "C" int xdet_bn_relu_bwd_bf16(const void* d_dy, const void* d_x, const fl
   return after_launch("bn_bwd_apply_kernel");
 }
 
+extern "C" int xdet_relu_bwd_bf16(const void* d_dy, const void* d_y, void* d_dx, long long n, void* stream) {
+  if (n <= 0) return XDET_OK;
+  if (n % 8) return fail(XDET_EINVAL, "relu_bwd: n must be a multiple of 8");
+  relu_bwd_kernel<<<blocks_for(n / 8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(d_dy), reinterpret_cast<const uint4*>(d_y), reinterpret_cast<uint4*>(d_dx), n / 8);
+  return after_launch("relu_bwd_kernel");
+}
+
 extern "C" int xdet_maxpool3x3s2_bwd_bf16(const void* d_x, const void* d_dy, void* d_dx, int N, int H, int W, int C,
                                           int Ho, int Wo, int pad_top, int pad_left, void* stream) {
   if (C % 2) return fail(XDET_EINVAL, "maxpool_bwd: C must be even");
@@ -687,20 +713,23 @@ extern "C" int xdet_maxpool3x3s2_bwd_bf16(const void* d_x, const void* d_dy, voi
   return after_launch("maxpool_bwd_kernel");
 }
 
-extern "C" int xdet_nchw_f32_to_nhwc_bf16(const float* d_src, void* d_dst, int N, int C, int HW, void* stream) {
-  const long long total = (long long)N * C * HW;
+extern "C" int xdet_nchw_f32_to_nhwc_bf16(const float* d_src, void* d_dst, int N, int C, int dst_cs, int HW,
+                                          void* stream) {
+  if (dst_cs < C) return fail(XDET_EINVAL, "nchw_f32_to_nhwc_bf16: dst_cs < C");
+  const long long total = (long long)N * dst_cs * HW;
   if (total <= 0) return XDET_OK;
   nchw_f32_to_nhwc_bf16_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(
-      d_src, reinterpret_cast<__nv_bfloat16*>(d_dst), N, C, HW, total);
+      d_src, reinterpret_cast<__nv_bfloat16*>(d_dst), N, C, dst_cs, HW, total);
   return after_launch("nchw_f32_to_nhwc_bf16_kernel");
 }
 
 extern "C" int xdet_affine_relu_to_nchw_f32(const void* d_src, const float* d_scale, const float* d_shift, float* d_dst,
-                                            int N, int C, int HW, int relu, void* stream) {
+                                            int N, int C, int src_cs, int HW, int relu, void* stream) {
+  if (src_cs < C) return fail(XDET_EINVAL, "affine_relu_to_nchw_f32: src_cs < C");
   const long long total = (long long)N * C * HW;
   if (total <= 0) return XDET_OK;
   affine_relu_to_nchw_f32_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(d_src), d_scale, d_shift, d_dst, N, C, HW, relu, total);
+      reinterpret_cast<const __nv_bfloat16*>(d_src), d_scale, d_shift, d_dst, N, C, src_cs, HW, relu, total);
   return after_launch("affine_relu_to_nchw_f32_kernel");
 }
 

@@ -1,0 +1,650 @@
+"""Light-Head R-CNN training step -- the surface of the reference's ``light_head_rfcn_train.py``.
+
+* ``FLAGS`` / ``make_params`` carry the reference's flag names and defaults (light_head_rfcn_train.py:38-170).
+* ``LightHeadTrainer.step(images, gt_boxes, gt_labels, keys)`` is one ``train_op`` of ``lighr_head_model_fn``
+  (:277-451): forward in training mode (batch-norm with batch statistics), RPN losses on sampled anchors
+  (:321-378), proposals (K=10000 -> NMS 0.7 -> 1800) + ``ext_encode_rois`` (64 RoIs/image @ 25 % fg), PsRoIAlign +
+  fc head with OHEM (top-32 of the per-RoI loss, get_head net/xception_body.py:504-560), L2 on the non-BN
+  variables (:420), backward through everything, momentum-SGD with the piecewise learning rate (:426-441).
+  The backbone is the ResNet-50 v2 light-head composition of BASELINE configs 2/4.
+* Data parallel: images shard across ranks; the only exchange is ONE all-reduce (sum) of the flat fp32 gradient
+  buffer per step (``torch.distributed``: NCCL on GPUs), divided by the world size inside the optimizer kernel.
+  Batch-norm statistics stay local to each rank, exactly like TF tower replication (SURVEY 8 e).
+
+TensorFlow's autodiff is replaced by an explicit backward: every forward layer object below saves what its
+gradient needs and ``bwd`` launches the gradient kernels (``ops.conv2d_wgrad`` / ``ops.conv2d_dgrad`` on the
+tensor cores, ``ops.train.*`` for batch-norm, pooling, losses).  ``tf.random_shuffle`` calls (select_samples,
+_upsample_rois, ext_encode_rois) consume injected uniform key arrays so that the CPU oracle can be driven
+identically.  One reference quirk is kept on purpose: with OHEM, ``tf.gather(psroipooled_rois, select_indices,
+axis=1)`` (net/xception_body.py:533) applies EVERY image's top-k index row to EVERY image, so the head runs on
+N*N*k RoI rows and the loss is their mean.
+"""
+import math
+import types
+
+import torch
+
+from . import _native, ops
+from .net.variables import VariableStore
+from .ops import train as T
+from .preprocessing import anchor_manipulator
+
+# flag name -> default (light_head_rfcn_train.py:38-170; data/summary/checkpoint flags omitted)
+_DEFAULTS = dict(
+    num_classes=21, batch_size=8, data_format='channels_last', train_image_size=480, resnet_size=50,
+    match_threshold=0.53, neg_threshold_high=0.5, neg_threshold_low=0., fg_ratio=0.25, roi_one_image=64,
+    rpn_anchors_per_image=256, rpn_pre_nms_top_n=10000, rpn_post_nms_top_n=1800, rpn_min_size=16 * 1. / 480,
+    rpn_nms_thres=0.7, rpn_fg_ratio=0.5, rpn_match_threshold=0.7, rpn_neg_threshold=0.3, using_ohem=True,
+    ohem_roi_one_image=32, weight_decay=0.0002, momentum=0.9, learning_rate=1e-3, end_learning_rate=1e-4,
+    decay_boundaries='60000, 80000', lr_decay_factors='1, 0.8, 0.1', model_scope='xception_lighthead',
+    backbone='resnet50',
+    # not a reference flag: blocks per block_layer of the ResNet v2 composition (resnet_size 50 = 3,4,6,3)
+    resnet_layers=(3, 4, 6, 3),
+)
+FLAGS = types.SimpleNamespace(**_DEFAULTS)
+pool_method = 'max'  # light_head_rfcn_train.py:199
+_BN_DECAY, _BN_EPS = 0.997, 1e-5  # net/resnet_v2.py:37-38
+
+
+def make_params(**overrides):
+    p = dict(_DEFAULTS)
+    p.update(overrides)
+    return p
+
+
+def learning_rate(params, global_step):
+    """tf.train.piecewise_constant + the end_learning_rate floor (light_head_rfcn_train.py:426-432)."""
+    bounds = [int(b) for b in str(params['decay_boundaries']).split(',')]
+    factors = [float(f) for f in str(params['lr_decay_factors']).split(',')]
+    lr = params['learning_rate'] * factors[sum(1 for b in bounds if global_step > b)]
+    return max(lr, params['end_learning_rate'])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# parameters: fp32 masters under the reference's variable names + momentum + bf16 packs + gradient views
+# ---------------------------------------------------------------------------------------------------------------
+class _Registry(object):
+    """Collects gradient-buffer requests, then carves ONE flat fp32 buffer (the all-reduce payload)."""
+
+    def __init__(self, device):
+        self.device, self.requests, self.flat = device, [], None
+
+    def request(self, numel, setter):
+        self.requests.append((numel, setter))
+
+    def finalize(self):
+        total = sum((n + 3) // 4 * 4 for n, _ in self.requests)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=self.device)
+        off = 0
+        for n, setter in self.requests:
+            setter(self.flat[off:off + n])
+            off += (n + 3) // 4 * 4
+
+
+class ConvParams(object):
+    """One (possibly fused) convolution / dense weight: masters ``[(key, tensor, co_off, ci_off)]`` in TF layout,
+    bf16 packs for the forward and input-gradient kernels, packed fp32 gradient ``dw``."""
+
+    def __init__(self, reg, masters, kh, kw, cin, cout, fold=False, need_dgrad=True):
+        self.masters, self.kh, self.kw, self.cin, self.cout, self.fold = masters, kh, kw, cin, cout, fold
+        dev = masters[0][1].device
+        self.mom = [torch.zeros_like(m[1]) for m in masters]
+        w = torch.zeros((cout, cin, kh, kw), dtype=torch.float32, device=dev)
+        for _, t, co, ci in masters:
+            t4 = t if t.dim() == 4 else t.reshape(1, 1, *t.shape)
+            w[co:co + t4.shape[3], ci:ci + t4.shape[2]] = t4.permute(3, 2, 0, 1)
+        if fold:
+            self.pack = ops.pack_fold_weight(w)
+            self.cin_pad, shape = 64, (cout, kh, 64)
+        else:
+            self.pack = ops.pack_conv_weight(w)
+            self.cin_pad = (cin + 63) // 64 * 64
+            shape = (cout, kh * kw, self.cin_pad)
+        self.dpack = ops.pack_dgrad_weight(w) if need_dgrad else None
+        self.dw = None
+        reg.request(shape[0] * shape[1] * shape[2], lambda v: setattr(self, 'dw', v.view(shape)))
+
+    def update(self, lr, momentum, wd, gscale):
+        for (_, t, co, ci), m in zip(self.masters, self.mom):
+            T.sgd_momentum_conv(self.dw, t, m, self.pack, self.dpack, lr, momentum, wd, gscale, co, ci, self.fold)
+
+
+class VecParam(object):
+    """A bias (weight-decayed) or a batch-norm (beta, gamma) pair (not decayed).  The gradient view holds one
+    segment of ``seg`` floats per tensor (``seg`` = the channel pitch of the tensor the gradient kernel reduces,
+    i.e. the length rounded up to 8): the kernels write it directly, the optimizer reads the leading part."""
+
+    def __init__(self, reg, tensors, decayed):
+        self.tensors, self.decayed = tensors, decayed
+        self.seg = (tensors[0].numel() + 7) // 8 * 8
+        self.mom = [torch.zeros_like(t) for t in tensors]
+        self.grad = None
+        reg.request(self.seg * len(tensors), lambda v: setattr(self, 'grad', v))
+
+    def update(self, lr, momentum, wd, gscale):
+        for i, (t, m) in enumerate(zip(self.tensors, self.mom)):
+            T.sgd_momentum_vec(self.grad[i * self.seg:i * self.seg + t.numel()], t, m, lr, momentum,
+                               wd if self.decayed else 0.0, gscale)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# layers with explicit backward
+# ---------------------------------------------------------------------------------------------------------------
+class Conv(object):
+    def __init__(self, params, stride=1, dilation=1, padding="SAME", bias=None):
+        self.p, self.stride, self.dil, self.padding, self.bias = params, stride, dilation, padding, bias
+
+    def _geom(self, H, W):
+        p, s = self.p, self.stride
+        if self.padding == "SAME":
+            return "SAME"
+        if self.padding == "FIXED":  # conv2d_fixed_padding with strides > 1 (net/resnet_v2.py:89-100)
+            pad = (p.kh - 1) // 2
+            return (pad, pad, (H + 2 * pad - p.kh) // s + 1, (W + 2 * pad - p.kw) // s + 1)
+        return self.padding
+
+    def fwd(self, x, bias_tensor=None, **epilogue):
+        p = self.p
+        self.x = x
+        self.in_hw = x.shape[1:3]
+        self.geom = self._geom(*self.in_hw)
+        b = bias_tensor if bias_tensor is not None else (self.bias.tensors[0] if self.bias is not None else None)
+        self.y = ops.conv2d_nhwc(x, p.pack, p.cout, p.kh, p.kw, dilation=(self.dil, self.dil), padding=self.geom,
+                                 strides=(self.stride, self.stride), cin=p.cin, bias=b, **epilogue)
+        return self.y
+
+    def bwd(self, dy, need_dx=True, dx_residual=None, dx_layout="nhwc_bf16"):
+        """dy: NHWC bf16 (channel pitch a multiple of 8, >= cout).  Accumulates dW (and dbias); returns dX."""
+        p = self.p
+        ops.conv2d_wgrad(self.x, dy, p.kh, p.kw, dilation=(self.dil, self.dil), padding=self.geom,
+                         strides=(self.stride, self.stride), cin=p.cin, cout=p.cout, dw=p.dw)
+        if self.bias is not None:  # dbias = column sums of dy, accumulated straight into the flat gradient buffer
+            dy2 = dy.reshape(-1, dy.shape[-1])
+            assert dy2.shape[1] == self.bias.seg, (dy2.shape, self.bias.seg)
+            _native.check(_native.lib().xdet_col_stats_bf16(dy2.data_ptr(), dy2.shape[0], dy2.shape[1], dy2.shape[1], 0,
+                                                            self.bias.grad.data_ptr(),
+                                                            torch.cuda.current_stream().cuda_stream))
+        if not need_dx:
+            return None
+        return ops.conv2d_dgrad(dy, p.dpack, p.cin, p.kh, p.kw, self.in_hw, dilation=(self.dil, self.dil),
+                                padding=self.geom, strides=(self.stride, self.stride), cout=p.cout,
+                                residual=dx_residual, out_layout=dx_layout)
+
+
+class BNRelu(object):
+    """tf.layers.batch_normalization(training=True) + ReLU (net/resnet_v2.py:41-50) on NHWC bf16.  When the tensor's
+    channel pitch exceeds the variable length (490 channels in rows of 496) gamma/beta are zero-extended."""
+
+    def __init__(self, vec, moving, eps=_BN_EPS, decay=_BN_DECAY):
+        self.vec, self.moving, self.eps, self.decay = vec, moving, eps, decay  # vec.tensors = (beta, gamma)
+
+    def stats(self, x):
+        beta, gamma = self.vec.tensors
+        C, cs = beta.numel(), x.shape[-1]
+        self.x = x
+        if cs == C:
+            self.st = T.bn_train(x, gamma, beta, self.eps, self.decay, self.moving[0], self.moving[1])
+        else:  # zero tail: statistics of the padding channels are (0, 0) and never reach the variables
+            pad = (0, cs - C)
+            mm, mv = (torch.nn.functional.pad(t, pad) for t in self.moving)
+            self.st = T.bn_train(x, torch.nn.functional.pad(gamma, pad), torch.nn.functional.pad(beta, pad), self.eps,
+                                 self.decay, mm, mv)
+            self.moving[0].copy_(mm[:C])
+            self.moving[1].copy_(mv[:C])
+        return self.st
+
+    def fwd(self, x):
+        st = self.stats(x)
+        return ops.affine_relu(x, st.scale, st.shift, relu=True)
+
+    def bwd(self, dy, add_in=None):
+        cs = self.x.shape[-1]
+        assert cs == self.vec.seg and dy.shape == self.x.shape and dy.is_contiguous()
+        dx = torch.empty_like(self.x)
+        st = self.st
+        # the kernel's sums ARE the gradient: [0,cs) = dbeta, [cs,2cs) = dgamma, written into the flat buffer
+        _native.check(_native.lib().xdet_bn_relu_bwd_bf16(dy.data_ptr(), self.x.data_ptr(), st.scale.data_ptr(),
+                                                          st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
+                                                          st.rows, cs, 1, None if add_in is None else add_in.data_ptr(),
+                                                          self.vec.grad.data_ptr(), dx.data_ptr(),
+                                                          torch.cuda.current_stream().cuda_stream))
+        return dx
+
+
+class Bottleneck(object):
+    """Pre-activation bottleneck (net/resnet_v2.py:142-184; dilated 3x3 as net/xdet_body.py:39-81)."""
+
+    def __init__(self, bn1, proj, c1, bn2, c2, bn3, c3):
+        self.bn1, self.proj, self.c1, self.bn2, self.c2, self.bn3, self.c3 = bn1, proj, c1, bn2, c2, bn3, c3
+
+    def fwd(self, x):
+        a = self.bn1.fwd(x)
+        sc = self.proj.fwd(a) if self.proj is not None else x
+        b = self.bn2.fwd(self.c1.fwd(a))
+        c = self.bn3.fwd(self.c2.fwd(b))
+        return self.c3.fwd(c, residual=sc)
+
+    def bwd(self, dy, extra_dx=None):
+        """dy: gradient of the block output.  Returns the gradient of the block input (+ ``extra_dx``)."""
+        dc = self.c3.bwd(dy)
+        db = self.c2.bwd(self.bn3.bwd(dc))
+        dc1 = self.bn2.bwd(db)
+        if self.proj is not None:
+            da_p = self.proj.bwd(dy)
+            da = self.c1.bwd(dc1, dx_residual=da_p)
+            return self.bn1.bwd(da, add_in=extra_dx)
+        da = self.c1.bwd(dc1)
+        assert extra_dx is None
+        return self.bn1.bwd(da, add_in=dy)  # identity shortcut
+
+
+def allreduce_gradients(flat, group=None):
+    """The ONE exchange of a data-parallel step: sum the flat fp32 gradient buffer over the ranks (NCCL on GPUs,
+    gloo in the CPU tests).  Returns the world size; the optimizer kernels divide by it (grad_scale = 1/world)."""
+    if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        return 1
+    world = torch.distributed.get_world_size(group)
+    if world > 1:
+        torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM, group=group)
+    return world
+
+
+def shard_batch(global_batch, world, rank):
+    """Images partition across ranks: rank r owns [r*B/world, (r+1)*B/world)."""
+    if global_batch % world:
+        raise ValueError("global batch %d does not divide over %d ranks" % (global_batch, world))
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class LightHeadTrainer(object):
+    def __init__(self, params=None, seed=0, device="cuda", state_dict=None, process_group=None):
+        self.params = p = params or make_params()
+        assert p['backbone'] == 'resnet50', "the training step is built for the ResNet-50 composition (config 4)"
+        self.device = torch.device(device)
+        self.store = store = VariableStore(device=device, seed=seed, state_dict=state_dict)
+        self.pg = process_group
+        self.global_step = 0
+        self.reg = reg = _Registry(self.device)
+        self.convs, self.vecs = [], []
+        size = p['train_image_size']
+        self.fmap = size // 16
+        creator = anchor_manipulator.AnchorCreator([size] * 2, layers_shapes=[(self.fmap, self.fmap)],
+                                                   anchor_scales=[[0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8]],
+                                                   extra_anchor_scales=[[0.1]], anchor_ratios=[[1., 2., .5]],
+                                                   layer_steps=[16])
+        all_anchors, num_anchors_list = creator.get_all_anchors()
+        self.A = num_anchors_list[0]
+        self.enc = anchor_manipulator.AnchorEncoder(all_anchors, num_classes=p['num_classes'], allowed_borders=[0.],
+                                                    positive_threshold=p['rpn_match_threshold'],
+                                                    ignore_threshold=p['rpn_neg_threshold'],
+                                                    prior_scaling=[1., 1., 1., 1.], device=device)
+        # anchors in centre form [A_tot,4] and point form (center2point, preprocessing/anchor_manipulator.py:111-112)
+        yref, xref, href, wref = self.enc.device_anchors(0)
+        fm, A = self.fmap, self.A
+        cy = yref.reshape(fm * fm, 1).expand(fm * fm, A).reshape(-1)
+        cx = xref.reshape(fm * fm, 1).expand(fm * fm, A).reshape(-1)
+        hh = href.reshape(1, A).expand(fm * fm, A).reshape(-1)
+        ww = wref.reshape(1, A).expand(fm * fm, A).reshape(-1)
+        self.anchors_yxhw = torch.stack([cy, cx, hh, ww], -1).contiguous()
+        self.anchors_pt = torch.stack([cy - hh / 2., cx - ww / 2., cy + hh / 2., cx + ww / 2.], -1).contiguous()
+        self._build()
+        reg.finalize()
+        self.grads = reg.flat
+
+    # ---- variable creation in the reference's naming order --------------------------------------------------
+    def _conv(self, cin, cout, k, stride=1, dil=1, fold=False, need_dgrad=True, init=None):
+        s = self.store
+        name = s.auto_name("conv2d")
+        with s.scope(name):
+            key, t = s.get("kernel", (k, k, cin, cout), init or s.variance_scaling)
+        cp = ConvParams(self.reg, [(key, t, 0, 0)], k, k, cin, cout, fold=fold, need_dgrad=need_dgrad)
+        self.convs.append(cp)
+        padding = "SAME" if stride == 1 else "FIXED"
+        return Conv(cp, stride=stride, dilation=dil, padding=padding)
+
+    def _bn(self, channels, name=None):
+        s = self.store
+        bn = s.batch_norm(name or s.auto_name("batch_normalization"), channels)
+        vec = VecParam(self.reg, [bn["beta"][1], bn["gamma"][1]], decayed=False)
+        self.vecs.append(vec)
+        return BNRelu(vec, (bn["mean"][1], bn["var"][1]))
+
+    def _bias(self, tensors):
+        vec = VecParam(self.reg, tensors, decayed=True)
+        self.vecs.append(vec)
+        return vec
+
+    def _block(self, cin, filters, project, stride, dil):
+        bn1 = self._bn(cin)
+        proj = self._conv(cin, 4 * filters, 1, stride=stride if dil == 1 else 1) if project else None
+        c1 = self._conv(cin, filters, 1)
+        bn2 = self._bn(filters)
+        c2 = self._conv(filters, filters, 3, stride=stride if dil == 1 else 1, dil=dil)
+        bn3 = self._bn(filters)
+        c3 = self._conv(filters, 4 * filters, 1)
+        return Bottleneck(bn1, proj, c1, bn2, c2, bn3, c3)
+
+    def _build(self):
+        s, p = self.store, self.params
+        nc, A = p['num_classes'], self.A
+        with s.scope(p['model_scope']):
+            self.stem = self._conv(3, 64, 7, stride=2, fold=True, need_dgrad=False)
+            self.layers = []
+            cin = 64
+            nb = p['resnet_layers']
+            for filters, blocks, stride, dil in ((64, nb[0], 1, 1), (128, nb[1], 2, 1), (256, nb[2], 2, 1), (512, nb[3], 2, 2)):
+                layer = []
+                for i in range(blocks):
+                    layer.append(self._block(cin, filters, i == 0, stride if i == 0 else 1, dil))
+                    cin = 4 * filters
+                self.layers.append(layer)
+                if len(self.layers) == 3:
+                    self.bn_rpn = self._bn(cin)  # batch_norm_relu -> RPN feature (created before block_layer4)
+            self.bn_final = self._bn(cin)
+
+            def named_conv(kh, kw, cin_, cout_, init=None):
+                name = s.auto_name("conv2d")
+                with s.scope(name):
+                    k = s.get("kernel", (kh, kw, cin_, cout_), init or s.glorot_normal)
+                    b = s.get("bias", (cout_,), s.zeros)
+                return k, b
+
+            def fuse_bias(pairs):
+                """Re-home separate bias variables as views of ONE tensor (the fused convolution's bias)."""
+                fused = torch.cat([t for _, t in pairs]).contiguous()
+                off, views = 0, []
+                for key, t in pairs:
+                    v = fused[off:off + t.numel()]
+                    s.vars[key] = v
+                    views.append(v)
+                    off += t.numel()
+                return fused, views
+
+            with s.scope('rpn_head'):
+                k0, b0 = named_conv(3, 3, 1024, 512)
+                k1, b1 = named_conv(1, 1, 512, 2 * A)
+                k2, b2 = named_conv(1, 1, 512, 4 * A)
+            cp0 = ConvParams(self.reg, [(k0[0], k0[1], 0, 0)], 3, 3, 1024, 512)
+            cp12 = ConvParams(self.reg, [(k1[0], k1[1], 0, 0), (k2[0], k2[1], 2 * A, 0)], 1, 1, 512, 6 * A)
+            self.convs += [cp0, cp12]
+            self.rpn_conv = Conv(cp0, bias=self._bias([b0[1]]))
+            fused12, _ = fuse_bias([b1, b2])
+            self.rpn_out = Conv(cp12, bias=self._bias([fused12]))
+
+            with s.scope('large_sep_feature'):
+                with s.scope("Branch_0"):
+                    a0k, a0b = named_conv(15, 1, 2048, 256)
+                    b0k, b0b = named_conv(1, 15, 256, 490)
+                with s.scope("Branch_1"):
+                    a1k, a1b = named_conv(15, 1, 2048, 256)
+                    b1k, b1b = named_conv(1, 15, 256, 490)
+                self.bn_sep = self._bn(490, name=s.auto_name("batch_normalization"))
+            cpa = ConvParams(self.reg, [(a0k[0], a0k[1], 0, 0), (a1k[0], a1k[1], 256, 0)], 15, 1, 2048, 512)
+            cpa.kh, cpa.kw = 15, 1
+            cpb = ConvParams(self.reg, [(b0k[0], b0k[1], 0, 0), (b1k[0], b1k[1], 0, 256)], 1, 15, 512, 490)
+            self.convs += [cpa, cpb]
+            fused_a, _ = fuse_bias([a0b, a1b])
+            self.sep_a = Conv(cpa, bias=self._bias([fused_a]))
+            # the 1x15 biases of the two branches both receive the summed-output gradient; forward adds their sum
+            self.sep_b_biases = (b0b[1], b1b[1])
+            self.sep_b_bias_vec = self._bias([b0b[1]])       # gradient view shared by both (identical gradients)
+            self.sep_b_bias_mom2 = torch.zeros_like(b1b[1])
+            self.sep_b = Conv(cpb, bias=None)
+
+            with s.scope('final_head'):
+                with s.scope("subnet_fc"):
+                    f1k = s.get("kernel", (490, 2048), s.glorot_normal)
+                    f1b = s.get("bias", (2048,), s.zeros)
+                with s.scope("fc_cls"):
+                    fck = s.get("kernel", (2048, nc), s.glorot_normal)
+                    fcb = s.get("bias", (nc,), s.zeros)
+                with s.scope("fc_loc"):
+                    flk = s.get("kernel", (2048, 4), s.glorot_normal)
+                    flb = s.get("bias", (4,), s.zeros)
+            cpf1 = ConvParams(self.reg, [(f1k[0], f1k[1], 0, 0)], 1, 1, 490, 2048)
+            cpf2 = ConvParams(self.reg, [(fck[0], fck[1], 0, 0), (flk[0], flk[1], nc, 0)], 1, 1, 2048, nc + 4)
+            self.convs += [cpf1, cpf2]
+            self.fc1 = Conv(cpf1, bias=self._bias([f1b[1]]))
+            fused_f2, _ = fuse_bias([fcb, flb])
+            self.fc2 = Conv(cpf2, bias=self._bias([fused_f2]))
+
+    # ---- forward pieces ----------------------------------------------------------------------------------------
+    def _head_fwd(self, feat_bf16):
+        """feat [M, 496] bf16 -> (h [1,1,M,2048] bf16 ReLU'd, out [M, nc+4] fp32)."""
+        M = feat_bf16.shape[0]
+        h = self.fc1.fwd(feat_bf16.reshape(1, 1, M, -1), relu=True)
+        out = self.fc2.fwd(h, out_layout="nhwc_f32")
+        return h, out.reshape(M, -1)
+
+    def _head_loss(self, out, labels_i32, targets, w_rows):
+        """Per-row loss of head_loss_func (:381-399): CE + smooth-L1 * [label>0] / fg_ratio, and its gradient
+        w.r.t. ``out`` with every row weighted by ``w_rows`` (1/M for the mean)."""
+        nc = self.params['num_classes']
+        pos = (labels_i32 > 0).float() / self.params['fg_ratio']
+        dout = torch.zeros_like(out)
+        ce, _ = T.softmax_ce(out, labels_i32, nc, w_all=w_rows, dlogits=dout)
+        l1, _ = T.smooth_l1(out[:, nc:], targets, row_w=pos, w_all=w_rows, dpred=dout[:, nc:])
+        return ce + l1, dout
+
+    # ---- one training step ------------------------------------------------------------------------------------
+    def step(self, images, gt_boxes, gt_labels, keys, apply_update=True, inject=None):
+        """images [N,3,H,W] fp32; gt_boxes [N,G,4] fp32 (ymin,xmin,ymax,xmax in [0,1]); gt_labels [N,G] int32
+        (0 = padding); keys: dict of uniform [0,1) fp32 arrays standing in for tf.random_shuffle:
+        'rpn_fg','rpn_bg' [1, N*A_tot], 'rpn_up' [1, N*256], 'prop' [N, 1800], 'roi_fg','roi_bg' [N, 1800+G],
+        'roi_up' [N, 64].  ``inject`` (tests): {'rois_all','roi_idx','rpn_idx','ohem_idx'} override the discrete
+        selections.  Returns a dict of scalar losses (device tensors) and the selections."""
+        p, nc, A = self.params, self.params['num_classes'], self.A
+        inject = inject or {}
+        N = images.shape[0]
+        fm = self.fmap
+        self.grads.zero_()
+
+        # ---------------- forward: backbone ----------------
+        Wimg = images.shape[3]
+        Wo = (Wimg + 6 - 7) // 2 + 1
+        wp = (max((Wo - 1) * 2 + 8, Wimg + 3) + 7) // 8 * 8
+        x8 = ops.image_to_nhwc8(images.contiguous(), 3, wp)
+        Ho = (images.shape[2] + 6 - 7) // 2 + 1
+        self.stem.x = x8
+        y0 = ops.conv2d_nhwc(x8, self.stem.p.pack, 64, 7, 7, padding=(3, 3, Ho, Wo), strides=(2, 2), cin=3,
+                             fold_w=(Wimg, 3))
+        x = ops.maxpool3x3s2_same(y0)
+        for li, layer in enumerate(self.layers):
+            for blk in layer:
+                x = blk.fwd(x)
+            if li == 2:
+                x3 = x
+                rpn_feat = self.bn_rpn.fwd(x3)
+        backbone = self.bn_final.fwd(x)
+
+        # ---------------- forward: RPN head, losses on sampled anchors ----------------
+        r = self.rpn_conv.fwd(rpn_feat, relu=True)
+        rpn_out = self.rpn_out.fwd(r, out_layout="nhwc_f32")  # [N,fm,fm,6A]: logits [0,2A), deltas [2A,6A)
+        score, boxes = ops.rpn_decode(rpn_out, 0, 2 * A, self.enc.device_anchors(0), A)
+        glabels, gtargets, gscores = T.match_encode(self.anchors_pt, gt_boxes, gt_labels, 0.0,
+                                                    p['rpn_match_threshold'], p['rpn_neg_threshold'],
+                                                    ref_yxhw=self.anchors_yxhw)
+        n_rpn = N * p['rpn_anchors_per_image']
+        exp_fg = int(round(n_rpn * p['rpn_fg_ratio']))
+        if 'rpn_idx' in inject:
+            rpn_idx = inject['rpn_idx']
+        else:
+            rpn_idx, _ = T.sample_fg_bg(glabels.reshape(1, -1), None, 0.0, exp_fg, n_rpn, keys['rpn_fg'], keys['rpn_bg'],
+                                        keys['rpn_up'])
+            rpn_idx = rpn_idx.reshape(-1).long()
+        cls_all = rpn_out[..., :2 * A].reshape(-1, 2)   # plumbing: [N*A_tot, 2] copies of the two channel groups
+        loc_all = rpn_out[..., 2 * A:].reshape(-1, 4)
+        s_cls, s_loc = cls_all.index_select(0, rpn_idx), loc_all.index_select(0, rpn_idx)
+        s_lab = (glabels.reshape(-1).index_select(0, rpn_idx) > 0).to(torch.int32)
+        s_tgt = gtargets.reshape(-1, 4).index_select(0, rpn_idx).contiguous()
+        rpn_ce_rows, d_s_cls = T.softmax_ce(s_cls, s_lab, 2, w_all=1.0 / n_rpn)
+        posm = s_lab.float()
+        npos = posm.sum().clamp(min=1.0)
+        row_w = posm / (npos * p['rpn_fg_ratio'])
+        rpn_l1_rows, d_s_loc = T.smooth_l1(s_loc, s_tgt, row_w=row_w, w_all=1.0)
+        rpn_ce, rpn_loc = rpn_ce_rows.mean(), rpn_l1_rows.sum()
+
+        # ---------------- forward: proposals + RoI targets (the reference pins this to /cpu:0) ----------------
+        if 'rois_all' in inject:
+            rois_all = inject['rois_all']
+        else:
+            props, _, _ = ops.rpn_select(score, boxes, p['rpn_pre_nms_top_n'], p['rpn_post_nms_top_n'],
+                                         p['rpn_nms_thres'], p['rpn_min_size'], keys['prop'])
+            rois_all = torch.cat([props, gt_boxes * (gt_labels > 0).unsqueeze(-1).float()], dim=1).contiguous()
+        rlab, rtgt, rsc = T.match_encode(rois_all, gt_boxes, gt_labels, 0.1, p['match_threshold'],
+                                         p['neg_threshold_high'])
+        R = p['roi_one_image']
+        if 'roi_idx' in inject:
+            roi_idx = inject['roi_idx']
+        else:
+            roi_idx, _ = T.sample_fg_bg(rlab, rsc, p['neg_threshold_low'], int(round(R * p['fg_ratio'])), R,
+                                        keys['roi_fg'], keys['roi_bg'], keys['roi_up'])
+            roi_idx = roi_idx.long()
+        rois = torch.gather(rois_all, 1, roi_idx.unsqueeze(-1).expand(N, R, 4)).contiguous()
+        roi_tgt = torch.gather(rtgt, 1, roi_idx.unsqueeze(-1).expand(N, R, 4)).contiguous()
+        roi_lab = torch.gather(rlab, 1, roi_idx).contiguous()
+
+        # ---------------- forward: thin feature map ----------------
+        mid = self.sep_a.fwd(backbone)
+        bias_b = self.sep_b_biases[0] + self.sep_b_biases[1]
+        # 490 channels live in rows of 496 (16-byte pixel strides for TMA and the vector kernels), zero tail
+        o_buf = torch.zeros((N, fm, fm, 496), dtype=torch.bfloat16, device=self.device)
+        self.sep_b.fwd(mid, bias_tensor=bias_b, out=o_buf[..., :490])
+        st_sep = self.bn_sep.stats(o_buf)
+        thin = T.affine_relu_to_nchw_f32(o_buf, st_sep.scale, st_sep.shift, relu=True, C=490)
+
+        # ---------------- forward: PsRoIAlign + head with OHEM ----------------
+        h_, w_ = rois[..., 2] - rois[..., 0], rois[..., 3] - rois[..., 1]
+        yxhw = torch.stack([rois[..., 0] + h_ / 2., rois[..., 1] + w_ / 2., h_, w_], dim=-1).contiguous()  # _point2center
+        pooled, pindex = ops.ps_roi_align(thin, yxhw, 7, 7, pool_method)
+        feat = pooled.reshape(N * R, -1)
+        cin = feat.shape[1]
+        pitch = (cin + 7) // 8 * 8
+        lab_flat, tgt_flat = roi_lab.reshape(-1), roi_tgt.reshape(-1, 4)
+        if p['using_ohem']:
+            k = min(p['ohem_roi_one_image'], R)
+            if 'ohem_idx' in inject:
+                sel = inject['ohem_idx']
+            else:
+                _, out1 = self._head_fwd(ops.f32_to_bf16_rows(feat, pitch))
+                loss1, _ = self._head_loss(out1, lab_flat, tgt_flat, 1.0)
+                sel = torch.topk(loss1.reshape(N, R), k, dim=1).indices  # selection only (tf.nn.top_k, :529)
+            # tf.gather(x, select_indices, axis=1) with a [N,k] index: every image gets every image's rows
+            flat_sel = (torch.arange(N, device=self.device).view(N, 1, 1) * R + sel.view(1, N, k)).reshape(-1)
+            feat2 = feat.index_select(0, flat_sel)
+            lab2 = roi_lab.index_select(1, sel.reshape(-1)).reshape(-1).contiguous()
+            tgt2 = roi_tgt.index_select(1, sel.reshape(-1)).reshape(-1, 4).contiguous()
+        else:
+            sel, flat_sel, feat2, lab2, tgt2 = None, None, feat, lab_flat, tgt_flat
+        M2 = feat2.shape[0]
+        a2 = ops.f32_to_bf16_rows(feat2.contiguous(), pitch)
+        h2, out2 = self._head_fwd(a2)
+        head_rows, dout2 = self._head_loss(out2, lab2, tgt2, 1.0 / M2)
+        head_loss = head_rows.mean()
+
+        # ================= backward =================
+        # ---- head ----
+        dpitch = (nc + 4 + 7) // 8 * 8
+        d_out_b = ops.f32_to_bf16_rows(dout2, dpitch).reshape(1, 1, M2, dpitch)
+        dh = self.fc2.bwd(d_out_b)
+        dh = T.relu_bwd(dh, h2)
+        dfeat2 = self.fc1.bwd(dh, dx_layout="nhwc_f32").reshape(M2, cin)
+        if flat_sel is not None:
+            dfeat = torch.zeros_like(feat).index_add_(0, flat_sel, dfeat2)
+        else:
+            dfeat = dfeat2
+        d_thin = ops.ps_roi_align_grad(thin, yxhw, dfeat.reshape(pooled.shape).contiguous(), pindex, 7, 7, pool_method)
+        # ---- thin feature map ----
+        do = self.bn_sep.bwd(T.nchw_f32_to_nhwc_bf16(d_thin, pitch=496))
+        # biases of the two 1x15 convs: both get the column sums of `do` (one gradient view, two variables)
+        _native.check(_native.lib().xdet_col_stats_bf16(do.data_ptr(), N * fm * fm, 496, 496, 0,
+                                                        self.sep_b_bias_vec.grad.data_ptr(),
+                                                        torch.cuda.current_stream().cuda_stream))
+        dmid = self.sep_b.bwd(do)
+        dbackbone = self.sep_a.bwd(dmid)
+        # ---- RPN head ----
+        d_cls = torch.zeros_like(cls_all).index_add_(0, rpn_idx, d_s_cls)
+        d_loc = torch.zeros_like(loc_all).index_add_(0, rpn_idx, d_s_loc)
+        cpitch = (6 * A + 7) // 8 * 8
+        d_rpn = torch.zeros((N, fm, fm, cpitch), dtype=torch.bfloat16, device=self.device)
+        d_rpn[..., :2 * A] = d_cls.reshape(N, fm, fm, 2 * A)
+        d_rpn[..., 2 * A:6 * A] = d_loc.reshape(N, fm, fm, 4 * A)
+        dr = T.relu_bwd(self.rpn_out.bwd(d_rpn), r)
+        d_rpn_feat = self.rpn_conv.bwd(dr)
+        # ---- backbone ----
+        dx = self.bn_final.bwd(dbackbone)
+        for li in (3, 2, 1, 0):
+            layer = self.layers[li]
+            if li == 2:  # x3 also feeds the RPN feature's batch_norm_relu
+                dx = self.bn_rpn.bwd(d_rpn_feat, add_in=dx)
+            for bi in range(len(layer) - 1, -1, -1):
+                blk = layer[bi]
+                dx = blk.bwd(dx)
+        dy0 = T.maxpool3x3s2_bwd(y0, dx)
+        ops.conv2d_wgrad(x8, dy0, 7, 7, padding=(3, 3, Ho, Wo), strides=(2, 2), cin=3, cout=64, dw=self.stem.p.dw,
+                         fold_w=(Wimg, 3))
+
+        # ================= all-reduce + optimizer =================
+        world = allreduce_gradients(self.grads, self.pg)
+        if apply_update:
+            lr = learning_rate(p, self.global_step)
+            gs = 1.0 / world
+            for c in self.convs:
+                c.update(lr, p['momentum'], p['weight_decay'], gs)
+            for v in self.vecs:
+                v.update(lr, p['momentum'], p['weight_decay'], gs)
+            # second 1x15 bias: same gradient as the first
+            T.sgd_momentum_vec(self.sep_b_bias_vec.grad, self.sep_b_biases[1], self.sep_b_bias_mom2, lr, p['momentum'],
+                               p['weight_decay'], gs)
+            self.global_step += 1
+        return {'rpn_cross_entropy_loss': rpn_ce, 'rpn_location_loss': rpn_loc, 'head_loss': head_loss,
+                'rpn_idx': rpn_idx, 'rois_all': rois_all, 'roi_idx': roi_idx, 'ohem_idx': sel,
+                'rois': rois, 'roi_labels': roi_lab, 'roi_targets': roi_tgt, 'glabels': glabels,
+                'rpn_out': rpn_out, 'large_sep_feature': thin}
+
+
+def synthetic_batch(params, batch, seed, device="cuda", max_gt=6):
+    """VOC-shaped synthetic tensors: images U(-1,1); 1..6 boxes per image with side >= 0.1,
+    labels 1..20; the uniform key arrays that stand in for tf.random_shuffle."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    size = params['train_image_size']
+    images = torch.rand((batch, 3, size, size), generator=g) * 2 - 1
+    gt = torch.zeros((batch, max_gt, 4))
+    gl = torch.zeros((batch, max_gt), dtype=torch.int32)
+    for n in range(batch):
+        k = int(torch.randint(1, max_gt + 1, (1,), generator=g))
+        cy, cx = torch.rand(k, generator=g) * 0.6 + 0.2, torch.rand(k, generator=g) * 0.6 + 0.2
+        h, w = torch.rand(k, generator=g) * 0.4 + 0.1, torch.rand(k, generator=g) * 0.4 + 0.1
+        gt[n, :k] = torch.stack([cy - h / 2, cx - w / 2, cy + h / 2, cx + w / 2], -1).clamp(0, 1)
+        gl[n, :k] = torch.randint(1, params['num_classes'], (k,), generator=g).to(torch.int32)
+    fm = size // 16
+    a_tot = fm * fm * 22
+    R0 = params['rpn_post_nms_top_n']
+    keys = {'rpn_fg': torch.rand((1, batch * a_tot), generator=g), 'rpn_bg': torch.rand((1, batch * a_tot), generator=g),
+            'rpn_up': torch.rand((1, batch * params['rpn_anchors_per_image']), generator=g),
+            'prop': torch.rand((batch, R0), generator=g), 'roi_fg': torch.rand((batch, R0 + max_gt), generator=g),
+            'roi_bg': torch.rand((batch, R0 + max_gt), generator=g),
+            'roi_up': torch.rand((batch, params['roi_one_image']), generator=g)}
+    to = lambda t: t.to(device).contiguous()
+    return to(images), to(gt), to(gl), {k: to(v) for k, v in keys.items()}
+
+
+def main(argv=None):
+    import argparse
+    ap = argparse.ArgumentParser(description="Light-Head R-CNN training steps on synthetic VOC-shaped tensors")
+    ap.add_argument("--batch_size", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=3)
+    args = ap.parse_args(argv)
+    params = make_params(batch_size=args.batch_size)
+    tr = LightHeadTrainer(params)
+    batch = synthetic_batch(params, args.batch_size, seed=3)
+    for i in range(args.steps):
+        out = tr.step(*batch)
+        print("step %d  rpn_ce %.4f  rpn_loc %.4f  head %.4f" % (i, float(out['rpn_cross_entropy_loss']),
+                                                                 float(out['rpn_location_loss']), float(out['head_loss'])))
+
+
+if __name__ == '__main__':
+    main()

@@ -167,15 +167,18 @@ def conv2d_image_fold(image_nchw_f32, w_fold, cout, kh, kw, stride, pad, **kw_ar
 class WgradDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in ("N", "H", "W", "Cin", "in_cs", "Cout", "KH", "KW", "dil_h", "dil_w",
                                             "pad_top", "pad_left", "stride_h", "stride_w", "Hout", "Wout", "dy_cs")] + \
-               [("dw", ctypes.c_void_p), ("splits", ctypes.c_int)]
+               [("dw", ctypes.c_void_p), ("splits", ctypes.c_int), ("fold_w", ctypes.c_int), ("in_wp", ctypes.c_int)]
 
 
 def conv2d_wgrad(x, dy, kh, kw, *, dilation=(1, 1), padding="SAME", strides=(1, 1), cin=None, cout=None, dw=None,
-                 splits=0):
+                 splits=0, fold_w=None):
     """dW of ``conv2d_nhwc(x, w, ...) -> y`` given ``dy`` (both NHWC bf16): fp32 [Cout, kh*kw, ceil(Cin/64)*64], the
     packed layout of the forward weights.  ``dw`` (zero-filled, or holding a partial sum) is accumulated into."""
     assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and x.is_contiguous() and dy.is_contiguous()
     N, H, W, cs = x.shape
+    in_wp = 0
+    if fold_w is not None:  # x = row-padded NHWC8 image [N,H,in_wp,8]; fold_w = (true width, pad_left)
+        in_wp, W = W, fold_w[0]
     _, Ho, Wo, dcs = dy.shape
     cin = cs if cin is None else cin
     cout = dcs if cout is None else cout
@@ -189,8 +192,10 @@ def conv2d_wgrad(x, dy, kh, kw, *, dilation=(1, 1), padding="SAME", strides=(1, 
         pt, pl = padding[:2]
     cpad = (cin + 63) // 64 * 64
     if dw is None:
-        dw = torch.zeros((cout, kh * kw, cpad), dtype=torch.float32, device=x.device)
-    d = WgradDesc(N, H, W, cin, cs, cout, kh, kw, dh, dw_, pt, pl, sh, sw, Ho, Wo, dcs, dw.data_ptr(), splits)
+        dw = torch.zeros((cout, kh, 64) if fold_w is not None else (cout, kh * kw, cpad), dtype=torch.float32,
+                         device=x.device)
+    d = WgradDesc(N, H, W, cin, cs, cout, kh, kw, dh, dw_, pt, pl, sh, sw, Ho, Wo, dcs, dw.data_ptr(), splits,
+                  0 if fold_w is None else 1, in_wp)
     with torch.cuda.device(x.device):
         rc = _native.lib().xdet_conv2d_wgrad_bf16(x.data_ptr(), dy.data_ptr(), ctypes.byref(d),
                                                   torch.cuda.current_stream().cuda_stream)

@@ -61,6 +61,13 @@ def bn_relu_bwd(dy, x, st, relu=True, add_in=None):
     return dx, sums[C:], sums[:C]
 
 
+def relu_bwd(dy, y):
+    assert dy.shape == y.shape and dy.is_contiguous() and y.is_contiguous() and dy.dtype == torch.bfloat16
+    dx = torch.empty_like(dy)
+    _native.check(_native.lib().xdet_relu_bwd_bf16(dy.data_ptr(), y.data_ptr(), dx.data_ptr(), dy.numel(), _st()))
+    return dx
+
+
 def maxpool3x3s2_bwd(x, dy):
     N, H, W, C = x.shape
     _, Ho, Wo, _ = dy.shape
@@ -70,18 +77,22 @@ def maxpool3x3s2_bwd(x, dy):
     return dx
 
 
-def nchw_f32_to_nhwc_bf16(x):
+def nchw_f32_to_nhwc_bf16(x, pitch=None):
+    """[N,C,H,W] fp32 -> [N,H,W,pitch] bf16 (channels C..pitch-1 zero)."""
     N, C, H, W = x.shape
-    out = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=x.device)
-    _native.check(_native.lib().xdet_nchw_f32_to_nhwc_bf16(x.data_ptr(), out.data_ptr(), N, C, H * W, _st()))
+    pitch = C if pitch is None else pitch
+    out = torch.empty((N, H, W, pitch), dtype=torch.bfloat16, device=x.device)
+    _native.check(_native.lib().xdet_nchw_f32_to_nhwc_bf16(x.data_ptr(), out.data_ptr(), N, C, pitch, H * W, _st()))
     return out
 
 
-def affine_relu_to_nchw_f32(x, scale, shift, relu=True):
-    N, H, W, C = x.shape
+def affine_relu_to_nchw_f32(x, scale, shift, relu=True, C=None):
+    """relu(x*scale+shift) of the first C channels of x [N,H,W,cs] bf16 -> [N,C,H,W] fp32."""
+    N, H, W, cs = x.shape
+    C = cs if C is None else C
     out = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
     _native.check(_native.lib().xdet_affine_relu_to_nchw_f32(x.data_ptr(), scale.data_ptr(), shift.data_ptr(),
-                                                             out.data_ptr(), N, C, H * W, 1 if relu else 0, _st()))
+                                                             out.data_ptr(), N, C, cs, H * W, 1 if relu else 0, _st()))
     return out
 
 
