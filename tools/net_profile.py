@@ -21,11 +21,20 @@ def main():
     ap.add_argument("--backbone", default="resnet50")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--list", action="store_true", help="also print every launch of the last step in order")
+    ap.add_argument("--train", action="store_true", help="profile the training step instead of inference")
     args = ap.parse_args()
-    params = lh.make_params(train_image_size=args.size, backbone=args.backbone)
-    model = lh.LightHeadRFCN(params, seed=0)
-    g = torch.Generator(device="cuda").manual_seed(1)
-    images = torch.rand((args.batch, 3, args.size, args.size), generator=g, device="cuda") * 2 - 1
+    if args.train:
+        from xdet_b200 import light_head_rfcn_train as lt
+        tparams = lt.make_params(train_image_size=args.size, batch_size=args.batch)
+        trainer = lt.LightHeadTrainer(tparams, seed=0)
+        tb = lt.synthetic_batch(tparams, args.batch, seed=3)
+        model = lambda _images: trainer.step(*tb)  # noqa: E731
+        images = None
+    else:
+        params = lh.make_params(train_image_size=args.size, backbone=args.backbone)
+        model = lh.LightHeadRFCN(params, seed=0)
+        g = torch.Generator(device="cuda").manual_seed(1)
+        images = torch.rand((args.batch, 3, args.size, args.size), generator=g, device="cuda") * 2 - 1
     for _ in range(3):
         model(images)
     torch.cuda.synchronize()

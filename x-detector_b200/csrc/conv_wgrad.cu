@@ -39,7 +39,7 @@ struct WgradArgs {
   int taps_w, dil_h, dil_w, pad_top, pad_left, mul_x, mul_y;
   int Cout, cin_pad, taps;
   int co_tiles, ci_tiles, BN, a_boxes, b_boxes;
-  int splits, items, stages, tmem_cols;
+  int splits, items, stages, tmem_cols, overwrite;
   float* dw;
   long long ld_dw;  // taps * cin_pad
 };
@@ -184,10 +184,20 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
         ptx::tmem_ld_wait();
-        if (co < p.Cout) {
+        if (co < p.Cout) {  // ncols is a multiple of 64: whole 16-byte groups
+          float4* dst = reinterpret_cast<float4*>(row + c0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < ncols) atomicAdd(row + c0 + j, __uint_as_float(r[j]));
+          for (int j = 0; j < 8; ++j) {
+            const float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                         __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            if (p.splits == 1 && p.overwrite) {
+              dst[j] = v;  // the only contribution to this tile: plain vector store
+            } else {
+              asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v.x), "f"(v.y),
+                           "f"(v.z), "f"(v.w)
+                           : "memory");
+            }
+          }
         }
       }
       ptx::tc_fence_before();
@@ -279,9 +289,13 @@ extern "C" int xdet_conv2d_wgrad_bf16(const void* d_x, const void* d_dy, const x
   a.a_boxes = 2;
   a.b_boxes = a.BN / 64;
   const int units = a.taps * a.co_tiles * a.ci_tiles;
-  int splits = d->splits > 0 ? d->splits : (2 * kNumSMs + units - 1) / units;
+  // pixel splits: just enough to put one item on every SM (each extra split costs a full tile of fp32 atomics),
+  // none when the (tap, Cout tile, Cin tile) units already fill the GPU, and at least 4 pixel tiles per item
+  int splits = d->splits > 0 ? d->splits : (units >= 100 ? 1 : (kNumSMs + units - 1) / units);
+  if (d->splits <= 0 && splits > a.pix_tiles / 4) splits = a.pix_tiles / 4;
   if (splits > a.pix_tiles) splits = a.pix_tiles;
   if (splits < 1) splits = 1;
+  a.overwrite = 0;  // dw is accumulated into (a caller-zeroed buffer or a partial sum)
   a.splits = splits;
   a.items = units * splits;
   const size_t stage_bytes = (size_t)(a.a_boxes + a.b_boxes) * kBoxBytes;

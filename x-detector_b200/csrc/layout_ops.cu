@@ -148,32 +148,40 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* 
   }
 }
 
+// y = x*scale[c] + bias[c] (ReLU): a thread owns 8 channels (constants in registers) and strides over the rows;
+// 256 threads = cgb channel groups x 256/cgb row lanes.
 __global__ void __launch_bounds__(256) affine_relu_kernel(const __nv_bfloat16* __restrict__ src,
                                                           __nv_bfloat16* __restrict__ dst,
                                                           const float* __restrict__ scale,
-                                                          const float* __restrict__ bias, int C, int relu,
-                                                          long long total_vec) {
-  const int C8 = C / 8;
-  const long long step = (long long)gridDim.x * blockDim.x;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total_vec; e += step) {
-    const int c8 = (int)(e % C8);
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + e);
+                                                          const float* __restrict__ bias, int C, int relu, int cgb,
+                                                          long long rows) {
+  const int rl = 256 / cgb;
+  const int cg = threadIdx.x % cgb, lane_row = threadIdx.x / cgb;
+  const int c0 = (blockIdx.x * cgb + cg) * 8;
+  if (c0 >= C) return;
+  float sc[8], bi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[c0 + j];
+    bi[j] = bias[c0 + j];
+  }
+  for (long long r = (long long)blockIdx.y * rl + lane_row; r < rows; r += (long long)gridDim.y * rl) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + r * C + c0));
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
     uint4 o;
     __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int c = c8 * 8 + 2 * q;
       const float2 f = __bfloat1622float2(h[q]);
-      float a = fmaf(f.x, __ldg(scale + c), __ldg(bias + c));
-      float b = fmaf(f.y, __ldg(scale + c + 1), __ldg(bias + c + 1));
+      float a = fmaf(f.x, sc[2 * q], bi[2 * q]);
+      float b = fmaf(f.y, sc[2 * q + 1], bi[2 * q + 1]);
       if (relu) {
         a = fmaxf(a, 0.f);
         b = fmaxf(b, 0.f);
       }
       ho[q] = __floats2bfloat162_rn(a, b);
     }
-    reinterpret_cast<uint4*>(dst)[e] = o;
+    *reinterpret_cast<uint4*>(dst + r * C + c0) = o;
   }
 }
 
@@ -351,11 +359,16 @@ extern "C" int xdet_maxpool3x3s2_add_bf16(const void* d_src, void* d_dst, void* 
 extern "C" int xdet_affine_relu_bf16(const void* d_src, void* d_dst, const float* d_scale, const float* d_bias,
                                      long long pixels, int C, int relu, void* stream) {
   if (C % 8 != 0) return fail(XDET_EINVAL, "affine_relu: C (%d) must be a multiple of 8", C);
-  const long long tv = pixels * (C / 8);
-  if (tv <= 0) return XDET_OK;
-  affine_relu_kernel<<<grid_for(tv), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_src),
-                                                                     reinterpret_cast<__nv_bfloat16*>(d_dst), d_scale,
-                                                                     d_bias, C, relu, tv);
+  if (pixels <= 0) return XDET_OK;
+  int cgb = 1;
+  while (cgb * 2 <= 32 && cgb * 2 <= C / 8) cgb *= 2;
+  const int gx = (C / 8 + cgb - 1) / cgb, rl = 256 / cgb;
+  long long slabs = (pixels + (long long)rl * 4 - 1) / ((long long)rl * 4);
+  const long long cap = (long long)kNumSMs * 8 / gx < 1 ? 1 : (long long)kNumSMs * 8 / gx;
+  if (slabs > cap) slabs = cap;
+  affine_relu_kernel<<<dim3((unsigned)gx, (unsigned)slabs), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d_src), reinterpret_cast<__nv_bfloat16*>(d_dst), d_scale, d_bias, C, relu, cgb,
+      pixels);
   return after_launch("affine_relu_kernel");
 }
 

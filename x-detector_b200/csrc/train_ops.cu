@@ -12,6 +12,7 @@
 //     light_head_rfcn_train.py:321-358, tf.random_shuffle replaced by injected key arrays.
 #include <cuda_bf16.h>
 
+#include <algorithm>
 #include <cfloat>
 
 #include "common.cuh"
@@ -28,19 +29,56 @@ unsigned blocks_for(long long total, int threads = 256, int per_sm = 8) {
 }
 
 // ---- column sums of a [rows, cs] bf16 matrix: sum (and sum of squares) per channel --------------------------
-// block = 256 threads = 32 channel-groups of 8 x 8 row lanes; grid.x over channel groups of 256, grid.y over row slabs
+// A block of 256 threads = CGB channel groups (8 channels = 16 bytes each) x RL = 256/CGB row lanes; a thread owns
+// its 8 channels for the whole kernel (per-channel constants live in registers) and strides over the rows.
+// CGB = min(32, C/8) rounded down to a power of two, so narrow tensors (C = 64) still use every thread.
+struct ColMap {
+  int cgb, rl, cg, lane_row, c0;
+  __device__ __forceinline__ ColMap(int cgb_) {
+    cgb = cgb_;
+    rl = 256 / cgb;
+    cg = threadIdx.x % cgb;
+    lane_row = threadIdx.x / cgb;
+    c0 = (blockIdx.x * cgb + cg) * 8;
+  }
+};
+__device__ __forceinline__ void block_col_reduce(float (*s)[8], const ColMap& m, int C, const float* a, const float* q,
+                                                 bool sq, float* sums) {
+  // s: [256][8] floats of shared memory per quantity, laid out [row lane][channel group][8]
+  __shared__ float s_a[256][8], s_q[256][8];
+  (void)s;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s_a[threadIdx.x][j] = a[j];
+    if (sq) s_q[threadIdx.x][j] = q[j];
+  }
+  __syncthreads();
+  const int nch = m.cgb * 8;  // channels of this block
+  if ((int)threadIdx.x < nch) {
+    const int cg = threadIdx.x / 8, j = threadIdx.x % 8;
+    const int c = (blockIdx.x * m.cgb + cg) * 8 + j;
+    if (c < C) {
+      float t = 0.f, t2 = 0.f;
+      for (int r = 0; r < m.rl; ++r) {
+        t += s_a[r * m.cgb + cg][j];
+        if (sq) t2 += s_q[r * m.cgb + cg][j];
+      }
+      atomicAdd(sums + c, t);
+      if (sq) atomicAdd(sums + C + c, t2);
+    }
+  }
+}
+
 template <bool SQ>
 __global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C,
-                                                        int cs, float* __restrict__ sums /* [2][C] or [C] */) {
-  __shared__ float s_sum[8][256 + 8], s_sq[8][256 + 8];
-  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;  // 32 groups of 8 channels, 8 row lanes
-  const int c0 = blockIdx.x * 256 + cg * 8;
+                                                        int cs, int cgb, float* __restrict__ sums /* [2][C] or [C] */) {
+  const ColMap m(cgb);
   float a[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = q[j] = 0.f;
-  if (c0 < C) {
-    for (long long r = (long long)blockIdx.y * 8 + rl; r < rows; r += (long long)gridDim.y * 8) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + r * cs + c0));
+  if (m.c0 < C) {
+    for (long long r = (long long)blockIdx.y * m.rl + m.lane_row; r < rows; r += (long long)gridDim.y * m.rl) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + r * cs + m.c0));
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -54,23 +92,7 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* __r
       }
     }
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    s_sum[rl][cg * 8 + j] = a[j];
-    if (SQ) s_sq[rl][cg * 8 + j] = q[j];
-  }
-  __syncthreads();
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c < C) {
-    float t = 0.f, t2 = 0.f;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      t += s_sum[r][threadIdx.x];
-      if (SQ) t2 += s_sq[r][threadIdx.x];
-    }
-    atomicAdd(sums + c, t);
-    if (SQ) atomicAdd(sums + C + c, t2);
-  }
+  block_col_reduce(nullptr, m, C, a, q, SQ, sums);
 }
 
 __global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ gamma,
@@ -104,24 +126,22 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ shift,
                                                             const float* __restrict__ mean,
                                                             const float* __restrict__ invstd, long long rows, int C,
-                                                            int relu, float* __restrict__ sums) {
-  __shared__ float s_a[8][256 + 8], s_b[8][256 + 8];
-  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
-  const int c0 = blockIdx.x * 256 + cg * 8;
+                                                            int relu, int cgb, float* __restrict__ sums) {
+  const ColMap m(cgb);
   float a[8], b[8], sc[8], sh[8], mu[8], is[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
-  if (c0 < C) {
+  if (m.c0 < C) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      sc[j] = scale[c0 + j];
-      sh[j] = shift[c0 + j];
-      mu[j] = mean[c0 + j];
-      is[j] = invstd[c0 + j];
+      sc[j] = scale[m.c0 + j];
+      sh[j] = shift[m.c0 + j];
+      mu[j] = mean[m.c0 + j];
+      is[j] = invstd[m.c0 + j];
     }
-    for (long long r = (long long)blockIdx.y * 8 + rl; r < rows; r += (long long)gridDim.y * 8) {
-      const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + r * C + c0));
-      const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x + r * C + c0));
+    for (long long r = (long long)blockIdx.y * m.rl + m.lane_row; r < rows; r += (long long)gridDim.y * m.rl) {
+      const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + r * C + m.c0));
+      const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x + r * C + m.c0));
       const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&ud);
       const __nv_bfloat162* hx = reinterpret_cast<const __nv_bfloat162*>(&ux);
 #pragma unroll
@@ -136,26 +156,11 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
       }
     }
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    s_a[rl][cg * 8 + j] = a[j];
-    s_b[rl][cg * 8 + j] = b[j];
-  }
-  __syncthreads();
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c < C) {
-    float t = 0.f, t2 = 0.f;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      t += s_a[r][threadIdx.x];
-      t2 += s_b[r][threadIdx.x];
-    }
-    atomicAdd(sums + c, t);
-    atomicAdd(sums + C + c, t2);
-  }
+  block_col_reduce(nullptr, m, C, a, b, true, sums);
 }
 
-// dx = scale * (g - sum_g/M - xhat * sum_gx/M) (+ add_in); scale = gamma * invstd.
+// dx = scale * (g - sum_g/M - xhat * sum_gx/M) (+ add_in) = scale*g + B*x + D with per-channel constants
+//   B = -scale*invstd*sum_gx/M,  D = scale*(mean*invstd*sum_gx - sum_g)/M   (scale = gamma * invstd).
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
                                                            const __nv_bfloat16* __restrict__ x,
                                                            const float* __restrict__ scale,
@@ -164,17 +169,26 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
                                                            const float* __restrict__ invstd,
                                                            const float* __restrict__ sums,
                                                            const __nv_bfloat16* __restrict__ add_in, long long rows,
-                                                           int C, int relu, __nv_bfloat16* __restrict__ dx) {
-  const int C8 = C / 8;
-  const long long total = rows * C8;
+                                                           int C, int relu, int cgb, __nv_bfloat16* __restrict__ dx) {
+  const ColMap m(cgb);
+  if (m.c0 >= C) return;
   const float inv_m = 1.f / (float)rows;
-  const long long step = (long long)gridDim.x * blockDim.x;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
-    const int c0 = (int)(e % C8) * 8;
-    const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy) + e);
-    const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x) + e);
+  float sc[8], sh[8], B[8], D[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = m.c0 + j;
+    sc[j] = scale[c];
+    sh[j] = shift[c];
+    const float is = invstd[c], s0 = sums[c], s1 = sums[C + c];
+    B[j] = -sc[j] * is * s1 * inv_m;
+    D[j] = sc[j] * (mean[c] * is * s1 - s0) * inv_m;
+  }
+  for (long long r = (long long)blockIdx.y * m.rl + m.lane_row; r < rows; r += (long long)gridDim.y * m.rl) {
+    const long long off = r * C + m.c0;
+    const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + off));
+    const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x + off));
     uint4 ua = make_uint4(0, 0, 0, 0);
-    if (add_in) ua = __ldg(reinterpret_cast<const uint4*>(add_in) + e);
+    if (add_in) ua = __ldg(reinterpret_cast<const uint4*>(add_in + off));
     const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&ud);
     const __nv_bfloat162* hx = reinterpret_cast<const __nv_bfloat162*>(&ux);
     const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&ua);
@@ -183,19 +197,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float2 fd = __bfloat1622float2(hd[k]), fx = __bfloat1622float2(hx[k]), fa = __bfloat1622float2(ha[k]);
-      float r[2];
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int c = c0 + 2 * k + t;
-        const float xv = t ? fx.y : fx.x, dv = t ? fd.y : fd.x;
-        const float sc = __ldg(scale + c), sh = __ldg(shift + c);
-        const float g = (!relu || fmaf(xv, sc, sh) > 0.f) ? dv : 0.f;
-        const float xh = (xv - __ldg(mean + c)) * __ldg(invstd + c);
-        r[t] = sc * (g - __ldg(sums + c) * inv_m - xh * __ldg(sums + C + c) * inv_m) + (t ? fa.y : fa.x);
-      }
-      ho[k] = __floats2bfloat162_rn(r[0], r[1]);
+      const float g0 = (!relu || fmaf(fx.x, sc[2 * k], sh[2 * k]) > 0.f) ? fd.x : 0.f;
+      const float g1 = (!relu || fmaf(fx.y, sc[2 * k + 1], sh[2 * k + 1]) > 0.f) ? fd.y : 0.f;
+      ho[k] = __floats2bfloat162_rn(fmaf(sc[2 * k], g0, fmaf(B[2 * k], fx.x, D[2 * k])) + fa.x,
+                                    fmaf(sc[2 * k + 1], g1, fmaf(B[2 * k + 1], fx.y, D[2 * k + 1])) + fa.y);
     }
-    reinterpret_cast<uint4*>(dx)[e] = o;
+    *reinterpret_cast<uint4*>(dx + off) = o;
   }
 }
 
@@ -365,6 +372,43 @@ __global__ void sgd_conv_kernel(const float* __restrict__ dw, float* __restrict_
     if (wd_pack) wd_pack[((long long)ci * taps + (taps - 1 - tap)) * cout_pad + co] = b;
   }
 }
+// Tiled form for the regular layout: a block owns a 32 (ci) x 32 (co) tile of one tap and transposes through shared
+// memory, so the packed arrays (ci fastest) and the TF-layout masters (co fastest) are BOTH accessed coalesced.
+__global__ void __launch_bounds__(256) sgd_conv_tiled_kernel(const float* __restrict__ dw, float* __restrict__ w,
+                                                             float* __restrict__ mom, __nv_bfloat16* __restrict__ wp,
+                                                             __nv_bfloat16* __restrict__ wd_pack, int Cout, int taps,
+                                                             int Cin, int cin_pad, int cout_pad, float lr, float momentum,
+                                                             float wd, float gscale) {
+  __shared__ float s_g[32][33];
+  __shared__ __nv_bfloat16 s_w[32][34];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32, tap = blockIdx.z;
+  for (int l = ty; l < 32; l += 8) {
+    const int co = co0 + l, ci = ci0 + tx;
+    s_g[l][tx] = (co < Cout && ci < Cin) ? dw[((long long)co * taps + tap) * cin_pad + ci] : 0.f;
+  }
+  __syncthreads();
+  for (int l = ty; l < 32; l += 8) {
+    const int ci = ci0 + l, co = co0 + tx;
+    if (ci < Cin && co < Cout) {
+      const long long e = ((long long)tap * Cin + ci) * Cout + co;
+      const float wv = w[e];
+      const float a = momentum * mom[e] + (s_g[tx][l] * gscale + wd * wv);
+      mom[e] = a;
+      const float nw = wv - lr * a;
+      w[e] = nw;
+      const __nv_bfloat16 b = __float2bfloat16_rn(nw);
+      s_w[tx][l] = b;
+      if (wd_pack) wd_pack[((long long)ci * taps + (taps - 1 - tap)) * cout_pad + co] = b;
+    }
+  }
+  __syncthreads();
+  for (int l = ty; l < 32; l += 8) {
+    const int co = co0 + l, ci = ci0 + tx;
+    if (co < Cout && ci < Cin) wp[((long long)co * taps + tap) * cin_pad + ci] = s_w[l][tx];
+  }
+}
+
 __global__ void sgd_vec_kernel(const float* __restrict__ g, float* __restrict__ w, float* __restrict__ mom, long long n,
                                float lr, float momentum, float wd, float gscale) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -647,18 +691,32 @@ __global__ void __launch_bounds__(kSampThreads) sample_fg_bg_kernel(
 
 using namespace xdet;
 
+// channel groups per block (power of two <= min(32, C/8)) and the launch grid of the column-owner kernels
+static int col_cgb(int C) {
+  int g = 1;
+  while (g * 2 <= 32 && g * 2 <= C / 8) g *= 2;
+  return g;
+}
+static dim3 col_grid(long long rows, int C, int cgb) {
+  const int gx = (C / 8 + cgb - 1) / cgb;
+  const int rl = 256 / cgb;
+  long long slabs = (rows + (long long)rl * 8 - 1) / ((long long)rl * 8);  // >= 8 rows per thread
+  const long long cap = std::max(1LL, (long long)kNumSMs * 8 / gx);
+  if (slabs > cap) slabs = cap;
+  if (slabs < 1) slabs = 1;
+  return dim3((unsigned)gx, (unsigned)slabs);
+}
+
 extern "C" int xdet_col_stats_bf16(const void* d_x, long long rows, int C, int cs, int with_squares, float* d_sums,
                                    void* stream) {
   if (rows <= 0 || C <= 0) return XDET_OK;
   if (C % 8 || cs % 8 || cs < C) return fail(XDET_EINVAL, "col_stats: C and the row pitch must be multiples of 8");
-  long long slabs = (rows + 63) / 64;
-  const long long cap = (long long)kNumSMs * 8 / ((C + 255) / 256);
-  if (slabs > cap) slabs = cap < 1 ? 1 : cap;
-  dim3 grid((unsigned)((C + 255) / 256), (unsigned)slabs);
+  const int cgb = col_cgb(C);
+  const dim3 grid = col_grid(rows, C, cgb);
   if (with_squares)
-    col_stats_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_x), rows, C, cs, d_sums);
+    col_stats_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_x), rows, C, cs, cgb, d_sums);
   else
-    col_stats_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_x), rows, C, cs, d_sums);
+    col_stats_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_x), rows, C, cs, cgb, d_sums);
   return after_launch("col_stats_kernel");
 }
 
@@ -679,17 +737,15 @@ extern "C" int xdet_bn_relu_bwd_bf16(const void* d_dy, const void* d_x, const fl
   if (C % 8) return fail(XDET_EINVAL, "bn_relu_bwd: C must be a multiple of 8");
   cudaStream_t st = (cudaStream_t)stream;
   XDET_TRY(check_cuda(cudaMemsetAsync(d_sums, 0, sizeof(float) * 2 * C, st), "memset(bn sums)"));
-  long long slabs = (rows + 63) / 64;
-  const long long cap = (long long)kNumSMs * 8 / ((C + 255) / 256);
-  if (slabs > cap) slabs = cap < 1 ? 1 : cap;
-  dim3 grid((unsigned)((C + 255) / 256), (unsigned)slabs);
+  const int cgb = col_cgb(C);
+  const dim3 grid = col_grid(rows, C, cgb);
   bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(d_dy),
                                              reinterpret_cast<const __nv_bfloat16*>(d_x), d_scale, d_shift, d_mean,
-                                             d_invstd, rows, C, relu, d_sums);
+                                             d_invstd, rows, C, relu, cgb, d_sums);
   XDET_TRY(after_launch("bn_bwd_reduce_kernel"));
-  bn_bwd_apply_kernel<<<blocks_for(rows * (C / 8)), 256, 0, st>>>(
+  bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(d_dy), reinterpret_cast<const __nv_bfloat16*>(d_x), d_scale, d_shift, d_mean,
-      d_invstd, d_sums, reinterpret_cast<const __nv_bfloat16*>(d_add_in), rows, C, relu,
+      d_invstd, d_sums, reinterpret_cast<const __nv_bfloat16*>(d_add_in), rows, C, relu, cgb,
       reinterpret_cast<__nv_bfloat16*>(d_dx));
   return after_launch("bn_bwd_apply_kernel");
 }
@@ -766,6 +822,12 @@ extern "C" int xdet_sgd_momentum_conv(const float* d_dw, float* d_w, float* d_mo
   __nv_bfloat16* wdp = d_w_dgrad_pack ? reinterpret_cast<__nv_bfloat16*>(d_w_dgrad_pack) +
                                             ((long long)pack_ci_off * taps) * pack_cout_pad + pack_co_off
                                       : nullptr;
+  if (!fold) {
+    dim3 grid((unsigned)((Cin + 31) / 32), (unsigned)((Cout + 31) / 32), (unsigned)taps);
+    sgd_conv_tiled_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dw, d_w, d_mom, wp, wdp, Cout, (int)taps, Cin,
+                                                                 pack_cin_pad, pack_cout_pad, lr, momentum, wd, grad_scale);
+    return after_launch("sgd_conv_tiled_kernel");
+  }
   sgd_conv_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(dw, d_w, d_mom, wp, wdp, Cout, KH, KW, Cin,
                                                                       pack_cin_pad, pack_cout_pad, fold, lr, momentum, wd,
                                                                       grad_scale, total);

@@ -197,8 +197,14 @@ def conv2d_wgrad(x, dy, kh, kw, *, dilation=(1, 1), padding="SAME", strides=(1, 
     d = WgradDesc(N, H, W, cin, cs, cout, kh, kw, dh, dw_, pt, pl, sh, sw, Ho, Wo, dcs, dw.data_ptr(), splits,
                   0 if fold_w is None else 1, in_wp)
     with torch.cuda.device(x.device):
+        if PROFILE is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         rc = _native.lib().xdet_conv2d_wgrad_bf16(x.data_ptr(), dy.data_ptr(), ctypes.byref(d),
                                                   torch.cuda.current_stream().cuda_stream)
+        if PROFILE is not None:
+            e1.record()
+            PROFILE.append((e0, e1, 2.0 * N * Ho * Wo * cout * cin * kh * kw, ("wgrad", N, H, W, cin, cout, kh, kw)))
     _native.check(rc)
     return dw
 
