@@ -76,6 +76,31 @@ def dist_env():
     return int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
+def dist_init(local):
+    """NCCL process group for the ranks torchrun started.  NCCL's own banner ("NCCL version ...") goes to stdout
+    when NCCL_DEBUG=VERSION/INFO is inherited: stdout must carry exactly ONE JSON line, so keep it at WARN."""
+    import torch
+    import torch.distributed as dist
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+
+def dist_finish(world):
+    """Leave without tearing NCCL down under live CUDA graphs (destroy_process_group can hang there): flush, meet at a
+    barrier, and exit the process directly."""
+    import torch
+    import torch.distributed as dist
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
+
+
 # ==============================================================================================
 # Workload 1 (default): Light-Head R-CNN ResNet-50 inference, batch 8/GPU, 480x480
 # ==============================================================================================
@@ -101,7 +126,7 @@ class LightHeadResnet50:
         assert torch.cuda.is_available(), "bench.py (own arm) needs a GPU; there is no CPU fallback"
         torch.cuda.set_device(local)
         if world > 1:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist_init(local)
         _native.lib()
         peaks = load_peaks()
 
@@ -239,8 +264,7 @@ class LightHeadResnet50:
                 "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
                 "roofline": roofline, "cpu_baseline": cpu,
             }))
-        if world > 1:
-            dist.destroy_process_group()
+        dist_finish(world)
 
     def run_reference(self, args):
         world, rank, _ = dist_env()
@@ -353,7 +377,7 @@ class PsroiSweepTop:
         assert torch.cuda.is_available(), "bench.py (own arm) needs a GPU; there is no CPU fallback"
         torch.cuda.set_device(local)
         if world > 1:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist_init(local)
         _native.lib()
         peaks = load_peaks()
 
@@ -435,8 +459,7 @@ class PsroiSweepTop:
                              "algorithmic_bytes_per_launch": nbytes, "kernel_ms": step_ms},
                 "cpu_baseline": cpu,
             }))
-        if world > 1:
-            dist.destroy_process_group()
+        dist_finish(world)
 
 
 class LightHeadResnet50Train:
@@ -459,7 +482,7 @@ class LightHeadResnet50Train:
         assert torch.cuda.is_available(), "bench.py (own arm) needs a GPU; there is no CPU fallback"
         torch.cuda.set_device(local)
         if world > 1:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist_init(local)
         _native.lib()
         peaks = load_peaks()
 
@@ -588,8 +611,7 @@ class LightHeadResnet50Train:
                 "cpu_baseline": None,
                 "losses": {k: float(out[k]) for k in ("rpn_cross_entropy_loss", "rpn_location_loss", "head_loss")},
             }))
-        if world > 1:
-            dist.destroy_process_group()
+        dist_finish(world)
 
     def run_reference(self, args):
         world, rank, _ = dist_env()
