@@ -126,6 +126,9 @@ typedef struct {
   int max_ctas; /* 0 = one persistent CTA per SM; otherwise an upper bound (leaves SMs to a concurrent stream) */
 } xdet_conv_desc;
 int xdet_conv2d_bf16(const void* d_in, const xdet_conv_desc* desc, void* stream);
+/* Convolutions are launched with programmatic stream serialization (their prologue overlaps the predecessor's tail;
+ * the kernel executes griddepcontrol.wait before touching tensor data).  0 turns that off (debugging). */
+void xdet_set_conv_pdl(int enabled);
 
 /* Weight gradient of the same convolutions (training; replaces TensorFlow's Conv2DBackpropFilter behind
  * `optimizer.minimize`, light_head_rfcn_train.py:426-441):

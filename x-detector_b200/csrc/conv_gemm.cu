@@ -147,6 +147,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // Programmatic dependent launch: this kernel may have started while its predecessor was still draining (its
+  // prologue above touches no tensor data).  Let OUR successor start its prologue as SMs free up, and make every
+  // thread that reads upstream tensors (the TMA producer, the residual loaders, the epilogue's scale/bias reads of
+  // batch-norm statistics) wait for the predecessor's memory first.
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -469,6 +475,9 @@ int pick_block_n(int cout, long long m_tiles, int num_k_blocks, bool multiples_o
 
 using namespace xdet;
 
+static int g_conv_pdl = 1;
+extern "C" void xdet_set_conv_pdl(int enabled) { g_conv_pdl = enabled ? 1 : 0; }
+
 extern "C" int xdet_conv2d_bf16(const void* d_in, const xdet_conv_desc* d, void* stream) {
   if (!d || !d_in) return fail(XDET_EINVAL, "null argument");
   if (d->N <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0 || d->KH <= 0 || d->KW <= 0)
@@ -630,6 +639,18 @@ extern "C" int xdet_conv2d_bf16(const void* d_in, const xdet_conv_desc* d, void*
   int sms = kNumSMs;
   if (d->max_ctas > 0 && d->max_ctas < sms) sms = d->max_ctas;  // leave SMs to a concurrent stream
   const int grid = a.total_tiles < sms ? a.total_tiles : sms;
-  conv_gemm_kernel<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(map_a, map_b, map_out, map_res, map_out2, a);
-  return after_launch("conv_gemm_kernel");
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  // not while another stream shares the GPU (max_ctas set): early-launched CTAs would sit on the SMs left free for it
+  cfg.numAttrs = (g_conv_pdl && d->max_ctas <= 0) ? 1 : 0;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, conv_gemm_kernel, map_a, map_b, map_out, map_res, map_out2, a);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_cuda(le != cudaSuccess ? le : cudaGetLastError(), "conv_gemm_kernel");
 }
