@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(256) affine_relu_kernel(const __nv_bfloat16* _
     sc[j] = scale[c0 + j];
     bi[j] = bias[c0 + j];
   }
+#pragma unroll 4
   for (long long r = (long long)blockIdx.y * rl + lane_row; r < rows; r += (long long)gridDim.y * rl) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + r * C + c0));
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);

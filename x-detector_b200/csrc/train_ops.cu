@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* __r
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = q[j] = 0.f;
   if (m.c0 < C) {
+#pragma unroll 4
     for (long long r = (long long)blockIdx.y * m.rl + m.lane_row; r < rows; r += (long long)gridDim.y * m.rl) {
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + r * cs + m.c0));
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
       mu[j] = mean[m.c0 + j];
       is[j] = invstd[m.c0 + j];
     }
+#pragma unroll 4
     for (long long r = (long long)blockIdx.y * m.rl + m.lane_row; r < rows; r += (long long)gridDim.y * m.rl) {
       const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + r * C + m.c0));
       const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x + r * C + m.c0));
@@ -183,6 +185,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
     B[j] = -sc[j] * is * s1 * inv_m;
     D[j] = sc[j] * (mean[c] * is * s1 - s0) * inv_m;
   }
+#pragma unroll 4
   for (long long r = (long long)blockIdx.y * m.rl + m.lane_row; r < rows; r += (long long)gridDim.y * m.rl) {
     const long long off = r * C + m.c0;
     const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + off));

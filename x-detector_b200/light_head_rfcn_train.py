@@ -26,6 +26,7 @@ import torch
 
 from . import _native, ops
 from .net.variables import VariableStore
+from .ops import conv as conv_ops
 from .ops import train as T
 from .preprocessing import anchor_manipulator
 
@@ -289,6 +290,7 @@ class LightHeadTrainer(object):
         ww = wref.reshape(1, A).expand(fm * fm, A).reshape(-1)
         self.anchors_yxhw = torch.stack([cy, cx, hh, ww], -1).contiguous()
         self.anchors_pt = torch.stack([cy - hh / 2., cx - ww / 2., cy + hh / 2., cx + ww / 2.], -1).contiguous()
+        self.side = torch.cuda.Stream(device=self.device)
         self._build()
         reg.finalize()
         self.grads = reg.flat
@@ -451,73 +453,95 @@ class LightHeadTrainer(object):
         y0 = ops.conv2d_nhwc(x8, self.stem.p.pack, 64, 7, 7, padding=(3, 3, Ho, Wo), strides=(2, 2), cin=3,
                              fold_w=(Wimg, 3))
         x = ops.maxpool3x3s2_same(y0)
-        for li, layer in enumerate(self.layers):
-            for blk in layer:
+        for li in range(3):
+            for blk in self.layers[li]:
                 x = blk.fwd(x)
-            if li == 2:
-                x3 = x
-                rpn_feat = self.bn_rpn.fwd(x3)
-        backbone = self.bn_final.fwd(x)
-
-        # ---------------- forward: RPN head, losses on sampled anchors ----------------
+        x3 = x
+        rpn_feat = self.bn_rpn.fwd(x3)
         r = self.rpn_conv.fwd(rpn_feat, relu=True)
         rpn_out = self.rpn_out.fwd(r, out_layout="nhwc_f32")  # [N,fm,fm,6A]: logits [0,2A), deltas [2A,6A)
-        score, boxes = ops.rpn_decode(rpn_out, 0, 2 * A, self.enc.device_anchors(0), A)
-        glabels, gtargets, gscores = T.match_encode(self.anchors_pt, gt_boxes, gt_labels, 0.0,
-                                                    p['rpn_match_threshold'], p['rpn_neg_threshold'],
-                                                    ref_yxhw=self.anchors_yxhw)
-        n_rpn = N * p['rpn_anchors_per_image']
-        exp_fg = int(round(n_rpn * p['rpn_fg_ratio']))
-        if 'rpn_idx' in inject:
-            rpn_idx = inject['rpn_idx']
-        else:
-            rpn_idx, _ = T.sample_fg_bg(glabels.reshape(1, -1), None, 0.0, exp_fg, n_rpn, keys['rpn_fg'], keys['rpn_bg'],
-                                        keys['rpn_up'])
-            rpn_idx = rpn_idx.reshape(-1).long()
-        cls_all = rpn_out[..., :2 * A].reshape(-1, 2)   # plumbing: [N*A_tot, 2] copies of the two channel groups
-        loc_all = rpn_out[..., 2 * A:].reshape(-1, 4)
-        s_cls, s_loc = cls_all.index_select(0, rpn_idx), loc_all.index_select(0, rpn_idx)
-        s_lab = (glabels.reshape(-1).index_select(0, rpn_idx) > 0).to(torch.int32)
-        s_tgt = gtargets.reshape(-1, 4).index_select(0, rpn_idx).contiguous()
-        rpn_ce_rows, d_s_cls = T.softmax_ce(s_cls, s_lab, 2, w_all=1.0 / n_rpn)
-        posm = s_lab.float()
-        npos = posm.sum().clamp(min=1.0)
-        row_w = posm / (npos * p['rpn_fg_ratio'])
-        rpn_l1_rows, d_s_loc = T.smooth_l1(s_loc, s_tgt, row_w=row_w, w_all=1.0)
-        rpn_ce, rpn_loc = rpn_ce_rows.mean(), rpn_l1_rows.sum()
 
-        # ---------------- forward: proposals + RoI targets (the reference pins this to /cpu:0) ----------------
-        if 'rois_all' in inject:
-            rois_all = inject['rois_all']
-        else:
-            props, _, _ = ops.rpn_select(score, boxes, p['rpn_pre_nms_top_n'], p['rpn_post_nms_top_n'],
-                                         p['rpn_nms_thres'], p['rpn_min_size'], keys['prop'])
-            rois_all = torch.cat([props, gt_boxes * (gt_labels > 0).unsqueeze(-1).float()], dim=1).contiguous()
-        rlab, rtgt, rsc = T.match_encode(rois_all, gt_boxes, gt_labels, 0.1, p['match_threshold'],
-                                         p['neg_threshold_high'])
-        R = p['roi_one_image']
-        if 'roi_idx' in inject:
-            roi_idx = inject['roi_idx']
-        else:
-            roi_idx, _ = T.sample_fg_bg(rlab, rsc, p['neg_threshold_low'], int(round(R * p['fg_ratio'])), R,
-                                        keys['roi_fg'], keys['roi_bg'], keys['roi_up'])
-            roi_idx = roi_idx.long()
-        rois = torch.gather(rois_all, 1, roi_idx.unsqueeze(-1).expand(N, R, 4)).contiguous()
-        roi_tgt = torch.gather(rtgt, 1, roi_idx.unsqueeze(-1).expand(N, R, 4)).contiguous()
-        roi_lab = torch.gather(rlab, 1, roi_idx).contiguous()
+        # ---------------- FORK: RPN losses, proposals and RoI targets on a second stream -----------------------
+        # (the reference pins proposals / ext_encode_rois to /cpu:0; here they run beside block_layer4 +
+        # large_sep_kernel, whose convolutions leave a few SMs to the one-CTA-per-image kernels meanwhile)
+        main = torch.cuda.current_stream()
+        side = self.side
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            score, boxes = ops.rpn_decode(rpn_out, 0, 2 * A, self.enc.device_anchors(0), A)
+            glabels, gtargets, gscores = T.match_encode(self.anchors_pt, gt_boxes, gt_labels, 0.0,
+                                                        p['rpn_match_threshold'], p['rpn_neg_threshold'],
+                                                        ref_yxhw=self.anchors_yxhw)
+            n_rpn = N * p['rpn_anchors_per_image']
+            exp_fg = int(round(n_rpn * p['rpn_fg_ratio']))
+            if 'rpn_idx' in inject:
+                rpn_idx = inject['rpn_idx']
+            else:
+                rpn_idx, _ = T.sample_fg_bg(glabels.reshape(1, -1), None, 0.0, exp_fg, n_rpn, keys['rpn_fg'],
+                                            keys['rpn_bg'], keys['rpn_up'])
+                rpn_idx = rpn_idx.reshape(-1).long()
+            cls_all = rpn_out[..., :2 * A].reshape(-1, 2)   # plumbing: [N*A_tot, 2] copies of the two channel groups
+            loc_all = rpn_out[..., 2 * A:].reshape(-1, 4)
+            s_cls, s_loc = cls_all.index_select(0, rpn_idx), loc_all.index_select(0, rpn_idx)
+            s_lab = (glabels.reshape(-1).index_select(0, rpn_idx) > 0).to(torch.int32)
+            s_tgt = gtargets.reshape(-1, 4).index_select(0, rpn_idx).contiguous()
+            rpn_ce_rows, d_s_cls = T.softmax_ce(s_cls, s_lab, 2, w_all=1.0 / n_rpn)
+            posm = s_lab.float()
+            npos = posm.sum().clamp(min=1.0)
+            row_w = posm / (npos * p['rpn_fg_ratio'])
+            rpn_l1_rows, d_s_loc = T.smooth_l1(s_loc, s_tgt, row_w=row_w, w_all=1.0)
+            rpn_ce, rpn_loc = rpn_ce_rows.mean(), rpn_l1_rows.sum()
+            # gradient of the RPN losses w.r.t. the head output, scattered back to the dense [N,fm,fm,6A] tensor
+            d_cls = torch.zeros_like(cls_all).index_add_(0, rpn_idx, d_s_cls)
+            d_loc = torch.zeros_like(loc_all).index_add_(0, rpn_idx, d_s_loc)
+            cpitch = (6 * A + 7) // 8 * 8
+            d_rpn = torch.zeros((N, fm, fm, cpitch), dtype=torch.bfloat16, device=self.device)
+            d_rpn[..., :2 * A] = d_cls.reshape(N, fm, fm, 2 * A)
+            d_rpn[..., 2 * A:6 * A] = d_loc.reshape(N, fm, fm, 4 * A)
 
-        # ---------------- forward: thin feature map ----------------
-        mid = self.sep_a.fwd(backbone)
-        bias_b = self.sep_b_biases[0] + self.sep_b_biases[1]
-        # 490 channels live in rows of 496 (16-byte pixel strides for TMA and the vector kernels), zero tail
-        o_buf = torch.zeros((N, fm, fm, 496), dtype=torch.bfloat16, device=self.device)
-        self.sep_b.fwd(mid, bias_tensor=bias_b, out=o_buf[..., :490])
+            # proposals + RoI targets
+            if 'rois_all' in inject:
+                rois_all = inject['rois_all']
+            else:
+                props, _, _ = ops.rpn_select(score, boxes, p['rpn_pre_nms_top_n'], p['rpn_post_nms_top_n'],
+                                             p['rpn_nms_thres'], p['rpn_min_size'], keys['prop'])
+                rois_all = torch.cat([props, gt_boxes * (gt_labels > 0).unsqueeze(-1).float()], dim=1).contiguous()
+            rlab, rtgt, rsc = T.match_encode(rois_all, gt_boxes, gt_labels, 0.1, p['match_threshold'],
+                                             p['neg_threshold_high'])
+            R = p['roi_one_image']
+            if 'roi_idx' in inject:
+                roi_idx = inject['roi_idx']
+            else:
+                roi_idx, _ = T.sample_fg_bg(rlab, rsc, p['neg_threshold_low'], int(round(R * p['fg_ratio'])), R,
+                                            keys['roi_fg'], keys['roi_bg'], keys['roi_up'])
+                roi_idx = roi_idx.long()
+            rois = torch.gather(rois_all, 1, roi_idx.unsqueeze(-1).expand(N, R, 4)).contiguous()
+            roi_tgt = torch.gather(rtgt, 1, roi_idx.unsqueeze(-1).expand(N, R, 4)).contiguous()
+            roi_lab = torch.gather(rlab, 1, roi_idx).contiguous()
+            h_, w_ = rois[..., 2] - rois[..., 0], rois[..., 3] - rois[..., 1]
+            yxhw = torch.stack([rois[..., 0] + h_ / 2., rois[..., 1] + w_ / 2., h_, w_], dim=-1).contiguous()  # _point2center
+
+        # ---------------- main stream meanwhile: block_layer4, thin feature map ----------------
+        conv_ops.MAX_CTAS = 148 - 12
+        try:
+            for blk in self.layers[3]:
+                x = blk.fwd(x)
+            backbone = self.bn_final.fwd(x)
+            mid = self.sep_a.fwd(backbone)
+            bias_b = self.sep_b_biases[0] + self.sep_b_biases[1]
+            # 490 channels live in rows of 496 (16-byte pixel strides for TMA and the vector kernels), zero tail
+            o_buf = torch.zeros((N, fm, fm, 496), dtype=torch.bfloat16, device=self.device)
+            self.sep_b.fwd(mid, bias_tensor=bias_b, out=o_buf[..., :490])
+        finally:
+            conv_ops.MAX_CTAS = 0
         st_sep = self.bn_sep.stats(o_buf)
         thin = T.affine_relu_to_nchw_f32(o_buf, st_sep.scale, st_sep.shift, relu=True, C=490)
+        main.wait_stream(side)  # JOIN
+        for t_ in (score, boxes, glabels, gtargets, rpn_idx, d_rpn, rois_all, rlab, rtgt, rsc, roi_idx, rois, roi_tgt,
+                   roi_lab, yxhw, rpn_ce, rpn_loc):
+            t_.record_stream(main)
 
         # ---------------- forward: PsRoIAlign + head with OHEM ----------------
-        h_, w_ = rois[..., 2] - rois[..., 0], rois[..., 3] - rois[..., 1]
-        yxhw = torch.stack([rois[..., 0] + h_ / 2., rois[..., 1] + w_ / 2., h_, w_], dim=-1).contiguous()  # _point2center
         pooled, pindex = ops.ps_roi_align(thin, yxhw, 7, 7, pool_method)
         feat = pooled.reshape(N * R, -1)
         cin = feat.shape[1]
@@ -565,12 +589,6 @@ class LightHeadTrainer(object):
         dmid = self.sep_b.bwd(do)
         dbackbone = self.sep_a.bwd(dmid)
         # ---- RPN head ----
-        d_cls = torch.zeros_like(cls_all).index_add_(0, rpn_idx, d_s_cls)
-        d_loc = torch.zeros_like(loc_all).index_add_(0, rpn_idx, d_s_loc)
-        cpitch = (6 * A + 7) // 8 * 8
-        d_rpn = torch.zeros((N, fm, fm, cpitch), dtype=torch.bfloat16, device=self.device)
-        d_rpn[..., :2 * A] = d_cls.reshape(N, fm, fm, 2 * A)
-        d_rpn[..., 2 * A:6 * A] = d_loc.reshape(N, fm, fm, 4 * A)
         dr = T.relu_bwd(self.rpn_out.bwd(d_rpn), r)
         d_rpn_feat = self.rpn_conv.bwd(dr)
         # ---- backbone ----
