@@ -180,6 +180,9 @@ int xdet_maxpool3x3s2_add_bf16(const void* d_src, void* d_dst, void* d_dst2, con
  * relu_in != 0 applies the tf.nn.relu that precedes the layer in relu_separable_bn_block (:223) while loading. */
 int xdet_depthwise3x3_bf16(const void* d_src, const float* d_weights, void* d_dst, int N, int H, int W, int C,
                            int dilation, int relu_in, void* stream);
+/* training-mode forward of the same pooling: also writes d_argmax [N,Ho,Wo,C] uint8 (see xdet_maxpool3x3s2_bwd_bf16) */
+int xdet_maxpool3x3s2_argmax_bf16(const void* d_src, void* d_dst, void* d_argmax, int N, int H, int W, int C, int Ho,
+                                  int Wo, int pad_top, int pad_left, void* stream);
 int xdet_affine_relu_bf16(const void* d_src, void* d_dst, const float* d_scale, const float* d_bias, long long pixels,
                           int C, int relu, void* stream);
 int xdet_f32_to_bf16_rows(const float* d_src, void* d_dst, long long rows, int cols, int dst_pitch, void* stream);
@@ -229,7 +232,8 @@ int xdet_head_decode(const float* d_rois, const float* d_head_out, int ch_stride
  *                         moving_mean/var <- decay*moving + (1-decay)*batch (unbiased variance), NULL = no update.
  *   xdet_bn_relu_bwd_bf16 gradient of y = relu(x*scale+shift) w.r.t. x (two passes: reduce, apply), + d_add_in
  *                         (a gradient arriving over the identity shortcut); d_sums[0..C) = dbeta, [C..2C) = dgamma.
- * xdet_maxpool3x3s2_bwd_bf16  gradient of tf.layers.max_pooling2d(3,2,'SAME') (first maximum of each window).
+ * xdet_maxpool3x3s2_bwd_bf16  gradient of tf.layers.max_pooling2d(3,2,'SAME'): dy goes to the first maximum of each
+ *                     window, whose position (kh*3+kw, one byte per output element) xdet_maxpool3x3s2_argmax_bf16 recorded.
  * xdet_nchw_f32_to_nhwc_bf16 / xdet_affine_relu_to_nchw_f32  repacks around the fp32 NCHW thin feature map; the
  *                     NHWC side has a channel pitch (490 channels live in rows of 496, zero tail).
  * xdet_softmax_ce     tf.nn.sparse_softmax_cross_entropy_with_logits: loss_row[r] and
@@ -254,8 +258,8 @@ int xdet_bn_relu_bwd_bf16(const void* d_dy, const void* d_x, const float* d_scal
 /* dx = dy where y > 0 else 0 (gradient of a ReLU fused into a convolution epilogue); bf16, n elements (n % 8 == 0) */
 int xdet_relu_bwd_bf16(const void* d_dy, const void* d_y, void* d_dx, long long n, void* stream);
 /* fp32 [rows, cols] -> bf16 [rows, dst_pitch] is xdet_f32_to_bf16_rows above */
-int xdet_maxpool3x3s2_bwd_bf16(const void* d_x, const void* d_dy, void* d_dx, int N, int H, int W, int C, int Ho, int Wo,
-                               int pad_top, int pad_left, void* stream);
+int xdet_maxpool3x3s2_bwd_bf16(const void* d_argmax, const void* d_dy, void* d_dx, int N, int H, int W, int C, int Ho,
+                               int Wo, int pad_top, int pad_left, void* stream);
 int xdet_nchw_f32_to_nhwc_bf16(const float* d_src, void* d_dst, int N, int C, int dst_cs, int HW, void* stream);
 int xdet_affine_relu_to_nchw_f32(const void* d_src, const float* d_scale, const float* d_shift, float* d_dst, int N,
                                  int C, int src_cs, int HW, int relu, void* stream);

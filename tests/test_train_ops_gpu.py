@@ -125,9 +125,10 @@ def test_maxpool_backward(T):
     import xdet_b200.ops as ops
     g = torch.Generator(device="cuda").manual_seed(2)
     x = torch.randn((2, 60, 60, 64), generator=g, device="cuda").to(torch.bfloat16)
-    y = ops.maxpool3x3s2_same(x)
+    y, arg = T.maxpool3x3s2_fwd_train(x)
+    assert torch.equal(y, ops.maxpool3x3s2_same(x))
     dy = torch.randn(y.shape, generator=g, device="cuda").to(torch.bfloat16)
-    dx = T.maxpool3x3s2_bwd(x, dy)
+    dx = T.maxpool3x3s2_bwd(arg, dy, x.shape[1:3])
     xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
     yr = F.max_pool2d(F.pad(xr, (0, 1, 0, 1), value=float("-inf")), 3, 2)  # 60 -> 30: SAME pads (0,1)
     assert torch.equal(yr.permute(0, 2, 3, 1), y.float())

@@ -60,6 +60,7 @@ def _declare(lib):
     lib.xdet_im2col_bf16.argtypes = [c_void_p, c_int, c_void_p] + [c_int] * 13 + [c_void_p]
     lib.xdet_maxpool3x3s2_bf16.argtypes = [c_void_p] * 5 + [c_int] * 8 + [c_void_p]
     lib.xdet_maxpool3x3s2_add_bf16.argtypes = [c_void_p] * 6 + [c_int] * 8 + [c_void_p]
+    lib.xdet_maxpool3x3s2_argmax_bf16.argtypes = [c_void_p] * 3 + [c_int] * 8 + [c_void_p]
     lib.xdet_depthwise3x3_bf16.argtypes = [c_void_p] * 3 + [c_int] * 6 + [c_void_p]
     lib.xdet_affine_relu_bf16.argtypes = [c_void_p] * 4 + [c_ll, c_int, c_int, c_void_p]
     lib.xdet_f32_to_bf16_rows.argtypes = [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p]

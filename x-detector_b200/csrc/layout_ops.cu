@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* 
                                                            __nv_bfloat16* __restrict__ dst2,
                                                            const float* __restrict__ scale2,
                                                            const float* __restrict__ bias2,
-                                                           const __nv_bfloat16* __restrict__ residual, int N, int H,
+                                                           const __nv_bfloat16* __restrict__ residual,
+                                                           unsigned char* __restrict__ argmax, int N, int H,
                                                            int W, int C, int Ho, int Wo, int pad_top, int pad_left,
                                                            long long total_vec) {
   const int C8 = C / 8;
@@ -104,8 +105,12 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* 
       }
     }
     float m[8];
+    unsigned am[8];  // window position (kh*3 + kw) of the FIRST maximum: where the gradient goes
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = -FLT_MAX;
+    for (int j = 0; j < 8; ++j) {
+      m[j] = -FLT_MAX;
+      am[j] = 0;
+    }
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
       if (!ok[k]) continue;
@@ -113,9 +118,21 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* 
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float2 f = __bfloat1622float2(h[q]);
-        m[2 * q] = fmaxf(m[2 * q], f.x);
-        m[2 * q + 1] = fmaxf(m[2 * q + 1], f.y);
+        if (f.x > m[2 * q]) {
+          m[2 * q] = f.x;
+          am[2 * q] = k;
+        }
+        if (f.y > m[2 * q + 1]) {
+          m[2 * q + 1] = f.y;
+          am[2 * q + 1] = k;
+        }
       }
+    }
+    if (argmax) {
+      uint2 a;
+      a.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
+      a.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
+      reinterpret_cast<uint2*>(argmax)[e] = a;
     }
     if (residual) {  // Xception entry flow: tf.add(max_pool(x), residual) (net/xception_body.py:283-289)
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(residual) + e);
@@ -343,6 +360,17 @@ extern "C" int xdet_maxpool3x3s2_bf16(const void* d_src, void* d_dst, void* d_ds
                                     pad_left, stream);
 }
 
+extern "C" int xdet_maxpool3x3s2_argmax_bf16(const void* d_src, void* d_dst, void* d_argmax, int N, int H, int W, int C,
+                                             int Ho, int Wo, int pad_top, int pad_left, void* stream) {
+  if (C % 8 != 0) return fail(XDET_EINVAL, "maxpool: C (%d) must be a multiple of 8", C);
+  const long long tv = (long long)N * Ho * Wo * (C / 8);
+  if (tv <= 0) return XDET_OK;
+  maxpool3x3s2_kernel<<<grid_for(tv), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d_src), reinterpret_cast<__nv_bfloat16*>(d_dst), nullptr, nullptr, nullptr,
+      nullptr, reinterpret_cast<unsigned char*>(d_argmax), N, H, W, C, Ho, Wo, pad_top, pad_left, tv);
+  return after_launch("maxpool3x3s2_kernel");
+}
+
 extern "C" int xdet_maxpool3x3s2_add_bf16(const void* d_src, void* d_dst, void* d_dst2, const float* d_scale2,
                                           const float* d_bias2, const void* d_residual, int N, int H, int W, int C,
                                           int Ho, int Wo, int pad_top, int pad_left, void* stream) {
@@ -353,7 +381,7 @@ extern "C" int xdet_maxpool3x3s2_add_bf16(const void* d_src, void* d_dst, void* 
   maxpool3x3s2_kernel<<<grid_for(tv), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(d_src), reinterpret_cast<__nv_bfloat16*>(d_dst),
       reinterpret_cast<__nv_bfloat16*>(d_dst2), d_scale2, d_bias2, reinterpret_cast<const __nv_bfloat16*>(d_residual),
-      N, H, W, C, Ho, Wo, pad_top, pad_left, tv);
+      nullptr, N, H, W, C, Ho, Wo, pad_top, pad_left, tv);
   return after_launch("maxpool3x3s2_kernel");
 }
 

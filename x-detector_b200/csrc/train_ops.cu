@@ -210,52 +210,52 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
 }
 
 // dx of tf.layers.max_pooling2d(3, 2, 'SAME'): every input pixel gathers dy from the (<= 4) windows that cover it
-// and whose FIRST maximum (row-major window order) it is.
-__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x,
+// and whose FIRST maximum it is -- the forward kernel recorded that position (kh*3 + kw) per output element.
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const unsigned char* __restrict__ argmax,
                                                           const __nv_bfloat16* __restrict__ dy,
                                                           __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C,
                                                           int Ho, int Wo, int pad_top, int pad_left, long long total) {
-  const int C2 = C / 2;
+  const int C8 = C / 8;
   const long long step = (long long)gridDim.x * blockDim.x;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
-    const int c2 = (int)(e % C2);
-    long long t = e / C2;
+    const int c8 = (int)(e % C8);
+    long long t = e / C8;
     const int xi = (int)(t % W);
     t /= W;
     const int yi = (int)(t % H);
     const int n = (int)(t / H);
-    const uint32_t* xs = reinterpret_cast<const uint32_t*>(x) + c2;
-    const uint32_t me_u = __ldg(xs + (((long long)n * H + yi) * W + xi) * C2);
-    const float2 me = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&me_u));
-    float2 acc = make_float2(0.f, 0.f);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     // windows (yo, xo) with yo*2 - pad_top <= yi <= yo*2 - pad_top + 2
-    const int yo_lo = max(0, (yi + pad_top - 2 + 1) / 2), yo_hi = min(Ho - 1, (yi + pad_top) / 2);
-    const int xo_lo = max(0, (xi + pad_left - 2 + 1) / 2), xo_hi = min(Wo - 1, (xi + pad_left) / 2);
+    const int yo_lo = max(0, (yi + pad_top - 1) / 2), yo_hi = min(Ho - 1, (yi + pad_top) / 2);
+    const int xo_lo = max(0, (xi + pad_left - 1) / 2), xo_hi = min(Wo - 1, (xi + pad_left) / 2);
     for (int yo = yo_lo; yo <= yo_hi; ++yo) {
+      const int kh = yi - (yo * 2 - pad_top);
+      if (kh < 0 || kh > 2) continue;
       for (int xo = xo_lo; xo <= xo_hi; ++xo) {
-        // am I the first maximum of this window? (strictly greater than everything before me, >= everything after)
-        bool first0 = true, first1 = true;
-        for (int kh = 0; kh < 3; ++kh) {
-          const int yy = yo * 2 + kh - pad_top;
-          if (yy < 0 || yy >= H) continue;
-          for (int kw = 0; kw < 3; ++kw) {
-            const int xx = xo * 2 + kw - pad_left;
-            if (xx < 0 || xx >= W || (yy == yi && xx == xi)) continue;
-            const uint32_t u = __ldg(xs + (((long long)n * H + yy) * W + xx) * C2);
-            const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
-            const bool before = (yy < yi) || (yy == yi && xx < xi);
-            first0 = first0 && (before ? (me.x > v.x) : (me.x >= v.x));
-            first1 = first1 && (before ? (me.y > v.y) : (me.y >= v.y));
-          }
+        const int kw = xi - (xo * 2 - pad_left);
+        if (kw < 0 || kw > 2) continue;
+        const unsigned code = (unsigned)(kh * 3 + kw);
+        const long long o = (((long long)n * Ho + yo) * Wo + xo) * C8 + c8;
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(argmax) + o);
+        const uint4 d = __ldg(reinterpret_cast<const uint4*>(dy) + o);
+        const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&d);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __bfloat1622float2(hd[q]);
+          const unsigned w = (q < 2) ? a.x : a.y;
+          const unsigned a0 = (w >> ((2 * q & 3) * 8)) & 255u, a1 = (w >> (((2 * q + 1) & 3) * 8)) & 255u;
+          if (a0 == code) acc[2 * q] += f.x;
+          if (a1 == code) acc[2 * q + 1] += f.y;
         }
-        const uint32_t du = __ldg(reinterpret_cast<const uint32_t*>(dy) + (((long long)n * Ho + yo) * Wo + xo) * C2 + c2);
-        const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&du));
-        if (first0) acc.x += d.x;
-        if (first1) acc.y += d.y;
       }
     }
-    const __nv_bfloat162 o = __floats2bfloat162_rn(acc.x, acc.y);
-    reinterpret_cast<uint32_t*>(dx)[e] = *reinterpret_cast<const uint32_t*>(&o);
+    uint4 o4;
+    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o4);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ho[q] = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
+    reinterpret_cast<uint4*>(dx)[e] = o4;
   }
 }
 
@@ -761,13 +761,13 @@ extern "C" int xdet_relu_bwd_bf16(const void* d_dy, const void* d_y, void* d_dx,
   return after_launch("relu_bwd_kernel");
 }
 
-extern "C" int xdet_maxpool3x3s2_bwd_bf16(const void* d_x, const void* d_dy, void* d_dx, int N, int H, int W, int C,
+extern "C" int xdet_maxpool3x3s2_bwd_bf16(const void* d_argmax, const void* d_dy, void* d_dx, int N, int H, int W, int C,
                                           int Ho, int Wo, int pad_top, int pad_left, void* stream) {
-  if (C % 2) return fail(XDET_EINVAL, "maxpool_bwd: C must be even");
-  const long long total = (long long)N * H * W * (C / 2);
+  if (C % 8) return fail(XDET_EINVAL, "maxpool_bwd: C must be a multiple of 8");
+  const long long total = (long long)N * H * W * (C / 8);
   if (total <= 0) return XDET_OK;
   maxpool_bwd_kernel<<<blocks_for(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(d_x), reinterpret_cast<const __nv_bfloat16*>(d_dy),
+      reinterpret_cast<const unsigned char*>(d_argmax), reinterpret_cast<const __nv_bfloat16*>(d_dy),
       reinterpret_cast<__nv_bfloat16*>(d_dx), N, H, W, C, Ho, Wo, pad_top, pad_left, total);
   return after_launch("maxpool_bwd_kernel");
 }

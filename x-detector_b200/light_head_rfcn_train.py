@@ -452,7 +452,7 @@ class LightHeadTrainer(object):
         self.stem.x = x8
         y0 = ops.conv2d_nhwc(x8, self.stem.p.pack, 64, 7, 7, padding=(3, 3, Ho, Wo), strides=(2, 2), cin=3,
                              fold_w=(Wimg, 3))
-        x = ops.maxpool3x3s2_same(y0)
+        x, pool_arg = T.maxpool3x3s2_fwd_train(y0)
         for li in range(3):
             for blk in self.layers[li]:
                 x = blk.fwd(x)
@@ -600,7 +600,7 @@ class LightHeadTrainer(object):
             for bi in range(len(layer) - 1, -1, -1):
                 blk = layer[bi]
                 dx = blk.bwd(dx)
-        dy0 = T.maxpool3x3s2_bwd(y0, dx)
+        dy0 = T.maxpool3x3s2_bwd(pool_arg, dx, y0.shape[1:3])
         ops.conv2d_wgrad(x8, dy0, 7, 7, padding=(3, 3, Ho, Wo), strides=(2, 2), cin=3, cout=64, dw=self.stem.p.dw,
                          fold_w=(Wimg, 3))
 

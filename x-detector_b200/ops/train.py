@@ -68,12 +68,24 @@ def relu_bwd(dy, y):
     return dx
 
 
-def maxpool3x3s2_bwd(x, dy):
+def maxpool3x3s2_fwd_train(x):
+    """tf.layers.max_pooling2d(3, 2, 'SAME') on NHWC bf16 -> (pooled, argmax uint8 [N,Ho,Wo,C])."""
     N, H, W, C = x.shape
-    _, Ho, Wo, _ = dy.shape
-    dx = torch.empty_like(x)
-    _native.check(_native.lib().xdet_maxpool3x3s2_bwd_bf16(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), N, H, W, C, Ho, Wo,
-                                                           same_pad(H, 3, 1, 2), same_pad(W, 3, 1, 2), _st()))
+    Ho, Wo = -(-H // 2), -(-W // 2)
+    out = torch.empty((N, Ho, Wo, C), dtype=torch.bfloat16, device=x.device)
+    arg = torch.empty((N, Ho, Wo, C), dtype=torch.uint8, device=x.device)
+    _native.check(_native.lib().xdet_maxpool3x3s2_argmax_bf16(x.data_ptr(), out.data_ptr(), arg.data_ptr(), N, H, W, C, Ho,
+                                                              Wo, same_pad(H, 3, 1, 2), same_pad(W, 3, 1, 2), _st()))
+    return out, arg
+
+
+def maxpool3x3s2_bwd(argmax, dy, in_hw):
+    """dx [N,H,W,C] of the pooling above from its recorded argmax."""
+    N, Ho, Wo, C = dy.shape
+    H, W = in_hw
+    dx = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=dy.device)
+    _native.check(_native.lib().xdet_maxpool3x3s2_bwd_bf16(argmax.data_ptr(), dy.data_ptr(), dx.data_ptr(), N, H, W, C, Ho,
+                                                           Wo, same_pad(H, 3, 1, 2), same_pad(W, 3, 1, 2), _st()))
     return dx
 
 
