@@ -476,7 +476,7 @@ class PsroiSweepTop:
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
-                             "kernel": "psroi_prep_kernel + psroi_fwd_planes_kernel<max,4>",
+                             "kernel": "psroi_prep_geom_kernel + psroi_prep_perm_kernel + psroi_fwd_select_kernel<4>",
                              "algorithmic_bytes_per_launch": nbytes, "kernel_ms": step_ms},
                 "cpu_baseline": cpu,
             }))

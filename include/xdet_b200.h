@@ -54,10 +54,13 @@ int xdet_psroi_align_fwd(const float* d_inputs, const float* d_rois, float* d_po
  *   XDET_PSROI_AUTO   pick by shape
  *   XDET_PSROI_GATHER one thread per output element, taps gathered from global memory (any shape)
  *   XDET_PSROI_PLANES channel-slice planes staged in shared memory, RoIs streamed past them
- *                     (needs (C/(gw*gh))*H*W*4 B <= ~200 KB) */
+ *                     (needs (C/(gw*gh))*H*W*4 B <= ~200 KB)
+ *   XDET_PSROI_SELECT PLANES staging; max pooling only: an fp32 pass selects the arg-max sample when that is provable
+ *                     (else the exact loop runs), the fp64 blend is evaluated for the selected sample only */
 #define XDET_PSROI_AUTO 0
 #define XDET_PSROI_GATHER 1
 #define XDET_PSROI_PLANES 2
+#define XDET_PSROI_SELECT 3
 int xdet_psroi_align_fwd_ex(const float* d_inputs, const float* d_rois, float* d_pooled, int32_t* d_index,
                             int N, int C, int H, int W, int R, int gw, int gh, int use_max, int variant,
                             void* stream);
@@ -188,6 +191,31 @@ int xdet_affine_relu_bf16(const void* d_src, void* d_dst, const float* d_scale, 
 int xdet_f32_to_bf16_rows(const float* d_src, void* d_dst, long long rows, int cols, int dst_pitch, void* stream);
 int xdet_image_to_nhwc8_bf16(const float* d_src, void* d_dst, int N, int C, int H, int W, int Wp, int pad_left,
                              void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * fp32-accurate PARITY MODE ("fp32x3", csrc/parity_ops.cu; not on the throughput path).
+ * The reference computes every convolution / dense layer in fp32 (tf.layers.conv2d/dense, net/resnet_v2.py:89-100,
+ * net/xception_body.py:224-233,381-400,450-475,540-558); north_star asks for box/score deltas within 1e-4 of it.
+ * xdet_conv2d_bf16 reaches fp32-level error when both operands are split into three bf16 pieces and the six
+ * significant cross products are summed in its fp32 accumulator: activations [mid|lo|hi|mid|hi|hi] (blocks of C
+ * channels, written by xdet_split3_bf16) against weights [mid|hi|lo|hi|mid|hi] (packed by the host).
+ * xdet_split3_bf16      d_src fp32, element (n,y,x,c) at n*sn + y*sy + x*sx + c*sc -> d_dst [N,H,W,out_cs] bf16,
+ *                       out_cs >= 6*C, out_cs % 8 == 0, zero tail.
+ * xdet_f32_post         v = x (+ residual) (ReLU if relu); out = v (NULL = not stored); out2 = v*scale2[c]+bias2[c]
+ *                       (ReLU if relu2) (NULL = none): the fp32 form of the conv epilogue's residual / second-output
+ *                       stages and of batch_norm_relu (net/resnet_v2.py:41-50).  [rows, C] fp32.
+ * xdet_maxpool3x3s2_f32 tf.layers.max_pooling2d(3,2,'SAME') (+ residual, + second output) on NHWC fp32.
+ * xdet_depthwise3x3_f32 depthwise half of tf.layers.separable_conv2d (net/xception_body.py:224-233) on NHWC fp32.
+ */
+int xdet_split3_bf16(const float* d_src, long long sn, long long sy, long long sx, long long sc, int N, int H, int W,
+                     int C, void* d_dst, int out_cs, void* stream);
+int xdet_f32_post(const float* d_x, const float* d_residual, int relu, float* d_out, const float* d_scale2,
+                  const float* d_bias2, int relu2, float* d_out2, long long rows, int C, void* stream);
+int xdet_maxpool3x3s2_f32(const float* d_src, float* d_dst, float* d_dst2, const float* d_scale2, const float* d_bias2,
+                          const float* d_residual, int N, int H, int W, int C, int Ho, int Wo, int pad_top, int pad_left,
+                          void* stream);
+int xdet_depthwise3x3_f32(const float* d_src, const float* d_weights, float* d_dst, int N, int H, int W, int C,
+                          int dilation, int relu_in, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * RPN proposals.

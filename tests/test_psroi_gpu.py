@@ -46,9 +46,16 @@ def run_bwd(ops, shape, rois, g, idx, gw, gh, method):
     return out.cpu().numpy()
 
 
-@pytest.mark.parametrize("variant", ["gather", "planes", "auto"])
+def variants_for(method):
+    """SELECT (fp32 selection + exact fp64 blend of the selected sample) exists for max pooling only."""
+    return ("gather", "planes", "select") if method == "max" else ("gather", "planes")
+
+
+@pytest.mark.parametrize("variant", ["gather", "planes", "select", "auto"])
 @pytest.mark.parametrize("method", ["mean", "max"])
 def test_reference_fixture(ops, method, variant):
+    if variant == "select" and method != "max":
+        pytest.skip("SELECT is max-only")
     x, rois = GOLD["fix_inputs"], GOLD["fix_rois"]
     p, i = run_fwd(ops, x, rois, 2, 2, method, variant)
     assert np.array_equal(bits(p), bits(GOLD["fix_%s_pooled" % method]))
@@ -57,9 +64,11 @@ def test_reference_fixture(ops, method, variant):
     assert np.array_equal(bits(g), bits(GOLD["fix_%s_grad" % method]))
 
 
-@pytest.mark.parametrize("variant", ["gather", "planes"])
+@pytest.mark.parametrize("variant", ["gather", "planes", "select"])
 @pytest.mark.parametrize("method", ["mean", "max"])
 def test_small_golden(ops, method, variant):
+    if variant == "select" and method != "max":
+        pytest.skip("SELECT is max-only")
     x = workloads.make_map(2, 98, 30, 30, seed=10)
     rois = workloads.make_rois(2, 28, seed=11, edge_cases=True)
     p, i = run_fwd(ops, x, rois, 7, 7, method, variant)
@@ -70,11 +79,13 @@ def test_small_golden(ops, method, variant):
     assert np.array_equal(bits(g), bits(GOLD["small_%s_grad" % method]))
 
 
-@pytest.mark.parametrize("variant", ["gather", "planes"])
+@pytest.mark.parametrize("variant", ["gather", "planes", "select"])
 @pytest.mark.parametrize("method", ["mean", "max"])
 def test_config1_model_shape_digest(ops, method, variant):
     """BASELINE config 1 (S-model): 1x490x30x30 + 300 RoIs (+4 edge cases), 7x7; pinned to digests
     of the reference's own output."""
+    if variant == "select" and method != "max":
+        pytest.skip("SELECT is max-only")
     x = workloads.make_map(1, 490, 30, 30, seed=0)
     rois = workloads.make_rois(1, 300, seed=0, edge_cases=True)
     p, i = run_fwd(ops, x, rois, 7, 7, method, variant)
@@ -102,7 +113,7 @@ def test_fwd_bwd_vs_oracle(ops, oracle_built, shape, method):
     x = workloads.make_map(N, C, H, W, seed=sum(shape))
     rois = workloads.make_rois(N, R, seed=sum(shape) + 1, min_side=0.02, edge_cases=R > 0)
     po, io = oracle_built.psroi_align_fwd(x, rois, gw, gh, method)
-    for variant in ("gather", "planes"):
+    for variant in variants_for(method):
         p, i = run_fwd(ops, x, rois, gw, gh, method, variant)
         assert np.array_equal(bits(p), bits(po)), variant
         assert np.array_equal(i, io), variant
@@ -110,6 +121,54 @@ def test_fwd_bwd_vs_oracle(ops, oracle_built, shape, method):
     g = run_bwd(ops, x.shape, rois, gup, io, gw, gh, method)
     go = oracle_built.psroi_align_bwd(x.shape, rois, gup, io, gw, gh, method)
     assert np.array_equal(bits(g), bits(go))
+
+
+def _adversarial_maps():
+    """Planes built to defeat an approximate arg-max: exact ties, near-ties, zeros, huge and tiny magnitudes,
+    non-finite values.  SELECT must fall back to the exact loop wherever the fp32 pass cannot prove the winner."""
+    rng = np.random.default_rng(99)
+    base = rng.standard_normal((1, 98, 30, 30), dtype=np.float32)
+    relu = np.maximum(base, 0)                                   # ~50 % exact zeros (the model's thin map is post-ReLU)
+    sparse = np.where(rng.random(base.shape) < 0.9, 0, base).astype(np.float32)
+    const = np.full_like(base, 0.7)                              # every sample ties
+    negzero = np.where(rng.random(base.shape) < 0.5, -0.0, 0.0).astype(np.float32)
+    quant = np.round(base * 2).astype(np.float32) / 2            # few distinct values: many exact ties
+    near = (1.0 + rng.integers(0, 4, base.shape) * np.float32(2.0 ** -23)).astype(np.float32)  # 1-ulp steps
+    huge = (base * np.float32(1e30)).astype(np.float32)
+    tiny = (base * np.float32(1e-38)).astype(np.float32)         # subnormal products
+    mixed = base.copy()
+    mixed[:, ::7] *= np.float32(1e20)
+    nonfin = base.copy()
+    nonfin[0, 3, 4, 5] = np.nan
+    nonfin[0, 10, 20, 11] = np.inf
+    nonfin[0, 11, 2, 7] = -np.inf
+    ramp = np.broadcast_to(np.arange(30, dtype=np.float32)[None, None, None, :], base.shape).copy()  # affine in x
+    return {"relu": relu, "sparse": sparse, "const": const, "negzero": negzero, "quant": quant, "near": near,
+            "huge": huge, "tiny": tiny, "mixed": mixed, "nonfinite": nonfin, "ramp": ramp}
+
+
+@pytest.mark.parametrize("name", sorted(_adversarial_maps()))
+def test_select_adversarial_planes(ops, oracle_built, name):
+    x = _adversarial_maps()[name]
+    rois = workloads.make_rois(1, 96, seed=123, min_side=0.02, edge_cases=True)
+    with np.errstate(all="ignore"):
+        po, io = oracle_built.psroi_align_fwd(x, rois, 7, 7, "max")
+    nan = np.isnan(po)   # NaN payloads differ between x86 and the GPU (0xFFC00000 vs 0x7FFFFFFF): compare positions
+    for variant in ("select", "planes", "gather"):
+        p, i = run_fwd(ops, x, rois, 7, 7, "max", variant)
+        assert np.array_equal(np.isnan(p), nan), (name, variant)
+        assert np.array_equal(bits(p)[~nan], bits(po)[~nan]), (name, variant)
+        assert np.array_equal(i, io), (name, variant)
+
+
+def test_select_many_samples_per_bin(ops, oracle_built):
+    """Big RoIs on a 50x50 map with 2x2 bins: up to 26 samples per bin axis, beyond the 8-deep sample tables
+    (generic path inside SELECT), mixed with small RoIs that use the tables."""
+    x = workloads.make_map(1, 64, 50, 50, seed=31)
+    rois = workloads.make_rois(1, 64, seed=32, min_side=0.02, max_side=1.0, edge_cases=True)
+    po, io = oracle_built.psroi_align_fwd(x, rois, 2, 2, "max")
+    p, i = run_fwd(ops, x, rois, 2, 2, "max", "select")
+    assert np.array_equal(bits(p), bits(po)) and np.array_equal(i, io)
 
 
 def test_config1_literal_480_map(ops, oracle_built):
@@ -132,6 +191,8 @@ def test_sweep_top_properties(ops):
     pa, ia = run_fwd(ops, x, rois, 7, 7, "max", "planes")
     pb, ib = run_fwd(ops, x, rois, 7, 7, "max", "gather")
     assert np.array_equal(bits(pa), bits(pb)) and np.array_equal(ia, ib)
+    ps, is_ = run_fwd(ops, x, rois, 7, 7, "max", "select")   # 16 M outputs: the near-tie fallback is exercised
+    assert np.array_equal(bits(ps), bits(pa)) and np.array_equal(is_, ia)
     perm = np.random.default_rng(6).permutation(16384)
     pp, ip = run_fwd(ops, x, np.ascontiguousarray(rois[:, perm]), 7, 7, "max", "planes")
     assert np.array_equal(bits(pp), bits(pa[:, perm])) and np.array_equal(ip, ia[:, perm])

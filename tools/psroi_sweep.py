@@ -36,7 +36,8 @@ def time_op(fn, flush, iters=10):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "psroi_sweep.json"))
-    ap.add_argument("--variants", default="planes,gather")
+    ap.add_argument("--variants", default="select,planes,gather")
+    ap.add_argument("--quick", action="store_true", help="R in {1024, 4096, 16384} only")
     ap.add_argument("--methods", default="max")
     args = ap.parse_args()
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
@@ -45,7 +46,7 @@ def main():
     rows = []
     for (C, g, hw) in [(980, 7, 30), (900, 15, 30), (490, 7, 30), (980, 7, 50), (900, 15, 50)]:
         x = torch.from_numpy(workloads.make_map(1, C, hw, hw, seed=4)).cuda()
-        for R in [128, 256, 512, 1024, 2048, 4096, 8192, 16384]:
+        for R in ([1024, 4096, 16384] if args.quick else [128, 256, 512, 1024, 2048, 4096, 8192, 16384]):
             rois = torch.from_numpy(workloads.make_rois(1, R, seed=5)).cuda()
             nbytes = 8 * R * C + 16 * R + 4 * C * hw * hw
             for method in args.methods.split(","):

@@ -65,6 +65,11 @@ def _declare(lib):
     lib.xdet_affine_relu_bf16.argtypes = [c_void_p] * 4 + [c_ll, c_int, c_int, c_void_p]
     lib.xdet_f32_to_bf16_rows.argtypes = [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p]
     lib.xdet_image_to_nhwc8_bf16.argtypes = [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]
+    lib.xdet_split3_bf16.argtypes = [c_void_p] + [c_ll] * 4 + [c_int] * 4 + [c_void_p, c_int, c_void_p]
+    lib.xdet_f32_post.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_int,
+                                  c_void_p]
+    lib.xdet_maxpool3x3s2_f32.argtypes = [c_void_p] * 6 + [c_int] * 8 + [c_void_p]
+    lib.xdet_depthwise3x3_f32.argtypes = [c_void_p] * 3 + [c_int] * 6 + [c_void_p]
     lib.xdet_rpn_decode.argtypes = [c_void_p, c_int, c_int, c_int] + [c_void_p] * 4 + [c_int] * 4 + [c_void_p] * 3
     lib.xdet_head_decode.argtypes = [c_void_p, c_void_p] + [c_int] * 4 + [c_ll, c_void_p, c_void_p, c_void_p]
     lib.xdet_rpn_select_workspace_bytes.argtypes = [c_int, c_int, c_int]

@@ -37,6 +37,9 @@ _DEFAULTS = dict(
     # not a reference flag: which backbone builder to use ('xception' = the reference's XceptionBody,
     # 'resnet50' = the ResNet-50 v2 light-head composition of BASELINE configs 2/4)
     backbone='resnet50',
+    # not a reference flag: 'bf16' = the throughput path; 'fp32x3' = parity mode (fp32 activations, split-operand
+    # tensor-core convolutions with fp32-level error, ~8x slower; see ops/conv.py and csrc/parity_ops.cu)
+    precision='bf16',
 )
 FLAGS = types.SimpleNamespace(**_DEFAULTS)
 pool_method = 'max'  # light_head_rfcn_eval.py:172
@@ -153,8 +156,9 @@ class LightHeadRFCN(object):
     def __call__(self, images, shuffle_keys=None):
         # a fresh naming pass per call: variables are looked up by the same automatic names every time
         self.store._counters = [{}]
-        return lighr_head_model_fn(images, self.labels, "eval", self.params, store=self.store,
-                                   shuffle_keys=shuffle_keys)
+        with conv_ops.precision(self.params.get('precision', 'bf16')):
+            return lighr_head_model_fn(images, self.labels, "eval", self.params, store=self.store,
+                                       shuffle_keys=shuffle_keys)
 
 
 def main(argv=None):

@@ -222,10 +222,13 @@ def get_head(net_input, pooling_op, grid_width, grid_height, loss_func, proposal
         k1, b1 = _dense_vars(store, "subnet_fc", cin, 2048)
         kc, bc = _dense_vars(store, "fc_cls", 2048, num_classes)
         kl, bl = _dense_vars(store, "fc_loc", 2048, 4)
-    pitch = (cin + 7) // 8 * 8  # TMA rows must be 16-byte multiples
-    a = ops.f32_to_bf16_rows(feat, pitch)
     w1 = _derived(store, ("w", k1[0]), lambda: ops.pack_conv_weight(k1[1].t().reshape(2048, cin, 1, 1)))
-    h = ops.conv2d_nhwc(a.reshape(1, 1, N * R, pitch), w1, 2048, 1, 1, bias=b1[1], relu=True, cin=cin)
+    if ops.conv.PRECISION == "fp32x3":  # parity mode: the pooled features stay fp32 (split inside conv2d_nhwc)
+        h = ops.conv2d_nhwc(feat.reshape(1, 1, N * R, cin), w1, 2048, 1, 1, bias=b1[1], relu=True)
+    else:
+        pitch = (cin + 7) // 8 * 8  # TMA rows must be 16-byte multiples
+        a = ops.f32_to_bf16_rows(feat, pitch)
+        h = ops.conv2d_nhwc(a.reshape(1, 1, N * R, pitch), w1, 2048, 1, 1, bias=b1[1], relu=True, cin=cin)
     w2 = _derived(store, ("w", kc[0], kl[0]),
                   lambda: ops.pack_conv_weight(torch.cat([kc[1], kl[1]], dim=1).t().reshape(num_classes + 4, 2048, 1, 1)))
     b2 = _derived(store, ("b", bc[0], bl[0]), lambda: torch.cat([bc[1], bl[1]]).contiguous())

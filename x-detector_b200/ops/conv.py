@@ -29,8 +29,48 @@ class ConvDesc(ctypes.Structure):
     ]
 
 
+# Arithmetic of the convolutions / dense layers:
+#   "bf16"   (default, the throughput path) bf16 operands, fp32 accumulate;
+#   "fp32x3" PARITY MODE (csrc/parity_ops.cu): activations stay fp32 between layers and every operand is split
+#            into three bf16 pieces; one convolution over 6*Cin channels sums the six significant cross products
+#            in the fp32 accumulator -> fp32-level error, for the end-to-end 1e-4 parity tests.  ~8x slower.
+PRECISION = "bf16"
+
+
+class precision(object):
+    """``with precision("fp32x3"): ...`` -- weights packed and convolutions issued inside use that arithmetic.
+    A VariableStore caches packed weights, so use one store (one model object) per precision."""
+
+    def __init__(self, mode):
+        assert mode in ("bf16", "fp32x3"), mode
+        self.mode = mode
+
+    def __enter__(self):
+        global PRECISION
+        self.prev, PRECISION = PRECISION, self.mode
+
+    def __exit__(self, *exc):
+        global PRECISION
+        PRECISION = self.prev
+
+
+def split3_values(w):
+    """fp32 tensor -> (hi, mid, lo): bf16-representable fp32 tensors with hi + mid + lo == w up to 2^-24 |w|."""
+    w = w.float()
+    hi = w.to(torch.bfloat16).float()
+    r = w - hi  # exact
+    mid = r.to(torch.bfloat16).float()
+    lo = (r - mid).to(torch.bfloat16).float()
+    return hi, mid, lo
+
+
 def pack_conv_weight(w_oihw):
-    """[Cout, Cin, KH, KW] float -> bf16 [Cout, KH*KW*ceil(Cin/64)*64] (tap-major, channels zero-padded)."""
+    """[Cout, Cin, KH, KW] float -> bf16 [Cout, KH*KW*ceil(Cin/64)*64] (tap-major, channels zero-padded).
+    In "fp32x3" precision the input-channel axis becomes the six blocks [mid|hi|lo|hi|mid|hi] that pair with the
+    activation blocks [mid|lo|hi|mid|hi|hi] written by ``split3``."""
+    if PRECISION == "fp32x3":
+        hi, mid, lo = split3_values(w_oihw)
+        w_oihw = torch.cat([mid, hi, lo, hi, mid, hi], dim=1)
     cout, cin, kh, kw = w_oihw.shape
     cpad = (cin + 63) // 64 * 64
     w = torch.zeros((cout, kh * kw, cpad), dtype=torch.float32, device=w_oihw.device)
@@ -39,7 +79,11 @@ def pack_conv_weight(w_oihw):
 
 
 def pack_fold_weight(w_oihw, cs=8):
-    """[Cout, Cin<=cs, KH, KW] float -> bf16 [Cout, KH*64] for the fold_w mode: element kw*cs + ci of filter row kh."""
+    """[Cout, Cin<=cs, KH, KW] float -> bf16 [Cout, KH*64] for the fold_w mode: element kw*cs + ci of filter row kh.
+    ("fp32x3" precision has no fold mode: the generic split pack is returned and ``conv2d_image_fold`` runs the
+    generic strided convolution.)"""
+    if PRECISION == "fp32x3":
+        return pack_conv_weight(w_oihw)
     cout, cin, kh, kw = w_oihw.shape
     assert cin <= cs and kw * cs <= 64
     w = torch.zeros((cout, kh, 64), dtype=torch.float32, device=w_oihw.device)
@@ -86,6 +130,10 @@ def conv2d_nhwc(x, w_packed, cout, kh, kw, *, dilation=(1, 1), padding="SAME", s
                 block_n=0, strides=(1, 1), fold_w=None, skip_out=False, epi_groups=0):
     """x: [N,H,W,C] bf16 (channel stride may be padded: pass the true ``cin``).  Returns the output tensor
     ([N,Ho,Wo,Cout] bf16 for 'nhwc_bf16', [N,Cout,Ho,Wo] fp32 for 'nchw_f32', [N,Ho,Wo,Cout] fp32 for 'nhwc_f32')."""
+    if x.dtype == torch.float32:  # parity mode: fp32 activations
+        return _conv2d_fp32x3(x, w_packed, cout, kh, kw, dilation=dilation, padding=padding, scale=scale, bias=bias,
+                              relu=relu, residual=residual, out=out, out_layout=out_layout, out2=out2, scale2=scale2,
+                              bias2=bias2, cin=cin, block_n=block_n, strides=strides, skip_out=skip_out)
     assert x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4
     N, H, W, cs = x.shape
     assert x.is_contiguous()
@@ -141,6 +189,60 @@ def conv2d_nhwc(x, w_packed, cout, kh, kw, *, dilation=(1, 1), padding="SAME", s
     return None if skip_out else out
 
 
+def split3(x, cin=None):
+    """fp32 [N,H,W,C] (any strides) -> bf16 [N,H,W,ceil8(6*C)]: blocks [mid|lo|hi|mid|hi|hi] of the three bf16 pieces of
+    every value (csrc/parity_ops.cu)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+    N, H, W, C = x.shape
+    cin = C if cin is None else cin
+    out_cs = (6 * cin + 7) // 8 * 8
+    out = torch.empty((N, H, W, out_cs), dtype=torch.bfloat16, device=x.device)
+    sn, sy, sx, sc = x.stride()
+    with torch.cuda.device(x.device):
+        rc = _native.lib().xdet_split3_bf16(x.data_ptr(), sn, sy, sx, sc, N, H, W, cin, out.data_ptr(), out_cs,
+                                            torch.cuda.current_stream().cuda_stream)
+    _native.check(rc)
+    return out
+
+
+def f32_post(x, residual=None, relu=False, out=None, scale2=None, bias2=None, out2=None, relu2=True, store_out=True):
+    """fp32 elementwise tail of a parity-mode layer: v = x (+ residual) (ReLU) -> ``out`` (allocated unless
+    ``store_out`` is False); ``out2`` = ReLU(v*scale2 + bias2) when scale2 is given.  Returns (out, out2)."""
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    C = x.shape[-1]
+    if store_out and out is None:
+        out = torch.empty_like(x)
+    if scale2 is not None and out2 is None:
+        out2 = torch.empty_like(x)
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.is_contiguous() and residual.shape == x.shape
+    with torch.cuda.device(x.device):
+        rc = _native.lib().xdet_f32_post(x.data_ptr(), _ptr(residual), 1 if relu else 0, _ptr(out) if store_out else None,
+                                         _ptr(scale2), _ptr(bias2), 1 if relu2 else 0, _ptr(out2), x.numel() // C, C,
+                                         torch.cuda.current_stream().cuda_stream)
+    _native.check(rc)
+    return (out if store_out else None), out2
+
+
+def _conv2d_fp32x3(x, w_packed, cout, kh, kw, *, dilation, padding, scale, bias, relu, residual, out, out_layout, out2,
+                   scale2, bias2, cin, block_n, strides, skip_out):
+    """``conv2d_nhwc`` in "fp32x3" precision: split the fp32 input, run the bf16 kernel over 6*Cin channels with an
+    fp32 output, then (residual / second output) the fp32 elementwise tail.  Outputs are fp32."""
+    cin = x.shape[-1] if cin is None else cin
+    xs = split3(x, cin)
+    layout = "nhwc_f32" if out_layout == "nhwc_bf16" else out_layout
+    tail = residual is not None or out2 is not None or scale2 is not None
+    assert not tail or layout == "nhwc_f32"
+    raw = conv2d_nhwc(xs, w_packed, cout, kh, kw, dilation=dilation, padding=padding, scale=scale, bias=bias,
+                      relu=relu and residual is None, out=None if tail else out, out_layout=layout, cin=6 * cin,
+                      block_n=block_n, strides=strides)
+    if not tail:
+        return raw
+    y, _ = f32_post(raw, residual=residual, relu=relu, out=raw if out is None else out, scale2=scale2, bias2=bias2,
+                    out2=out2, store_out=not skip_out)
+    return y
+
+
 def linear(x2d, w_packed, cout, **kw):
     """[M,K] bf16 @ W[cout,K]^T -> [M,cout]: the dense layers of get_head (net/xception_body.py:540-558)."""
     M, K = x2d.shape
@@ -156,6 +258,9 @@ def conv2d_image_fold(image_nchw_f32, w_fold, cout, kh, kw, stride, pad, **kw_ar
     N, C, H, W = image_nchw_f32.shape
     Ho = (H + 2 * pad - kh) // stride + 1
     Wo = (W + 2 * pad - kw) // stride + 1
+    if PRECISION == "fp32x3":  # generic strided convolution on the NHWC view of the fp32 image
+        return conv2d_nhwc(image_nchw_f32.permute(0, 2, 3, 1), w_fold, cout, kh, kw, padding=(pad, pad, Ho, Wo),
+                           strides=(stride, stride), cin=C, **kw_args)
     wp = max((Wo - 1) * stride + 8, W + pad)
     wp = (wp + 7) // 8 * 8
     x8 = image_to_nhwc8(image_nchw_f32, pad, wp)

@@ -35,6 +35,18 @@ def maxpool3x3s2_same(x, scale2=None, bias2=None, residual=None):
     N, H, W, C = x.shape
     Ho, Wo = -(-H // 2), -(-W // 2)
     pt, pl = same_pad(H, 3, 1, 2), same_pad(W, 3, 1, 2)
+    if x.dtype == torch.float32:  # parity mode (csrc/parity_ops.cu)
+        assert x.is_contiguous()
+        out = torch.empty((N, Ho, Wo, C), dtype=torch.float32, device=x.device)
+        out2 = torch.empty_like(out) if scale2 is not None else None
+        if residual is not None:
+            assert residual.shape == out.shape and residual.dtype == torch.float32 and residual.is_contiguous()
+        rc = _native.lib().xdet_maxpool3x3s2_f32(
+            x.data_ptr(), out.data_ptr(), None if out2 is None else out2.data_ptr(),
+            None if scale2 is None else scale2.data_ptr(), None if bias2 is None else bias2.data_ptr(),
+            None if residual is None else residual.data_ptr(), N, H, W, C, Ho, Wo, pt, pl, _st())
+        _native.check(rc)
+        return (out, out2) if out2 is not None else out
     out = torch.empty((N, Ho, Wo, C), dtype=torch.bfloat16, device=x.device)
     out2 = torch.empty_like(out) if scale2 is not None else None
     if residual is not None:
@@ -50,6 +62,13 @@ def maxpool3x3s2_same(x, scale2=None, bias2=None, residual=None):
 def depthwise3x3(x, w9c, dilation=1, relu_in=False):
     """Depthwise 3x3 SAME conv (depth multiplier 1) on NHWC bf16; ``w9c`` = [9, C] fp32 taps (kh-major)."""
     N, H, W, C = x.shape
+    if x.dtype == torch.float32:  # parity mode (csrc/parity_ops.cu)
+        assert x.is_contiguous() and w9c.dtype == torch.float32 and w9c.shape == (9, C)
+        out = torch.empty_like(x)
+        rc = _native.lib().xdet_depthwise3x3_f32(x.data_ptr(), w9c.data_ptr(), out.data_ptr(), N, H, W, C, dilation,
+                                                 1 if relu_in else 0, _st())
+        _native.check(rc)
+        return out
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and w9c.dtype == torch.float32 and w9c.shape == (9, C)
     out = torch.empty_like(x)
     rc = _native.lib().xdet_depthwise3x3_bf16(x.data_ptr(), w9c.data_ptr(), out.data_ptr(), N, H, W, C, dilation,
@@ -61,6 +80,9 @@ def depthwise3x3(x, w9c, dilation=1, relu_in=False):
 def affine_relu(x, scale, bias, relu=True):
     """Inference batch-norm (+ReLU) on NHWC bf16: y = x*scale[c] + bias[c]."""
     C = x.shape[-1]
+    if x.dtype == torch.float32:  # parity mode (csrc/parity_ops.cu)
+        from .conv import f32_post
+        return f32_post(x, scale2=scale, bias2=bias, relu2=relu, store_out=False)[1]
     out = torch.empty_like(x)
     rc = _native.lib().xdet_affine_relu_bf16(x.data_ptr(), out.data_ptr(), scale.data_ptr(), bias.data_ptr(),
                                              x.numel() // C, C, 1 if relu else 0, _st())

@@ -15,7 +15,7 @@ import torch
 
 from .. import _native
 
-VARIANTS = {"auto": 0, "gather": 1, "planes": 2}
+VARIANTS = {"auto": 0, "gather": 1, "planes": 2, "select": 3}
 
 
 def _use_max(pool_method):
