@@ -193,6 +193,26 @@ int xdet_image_to_nhwc8_bf16(const float* d_src, void* d_dst, int N, int C, int 
                              void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Detection post-processing.
+ * Replaces: the '/device:CPU:0' block of bboxes_eval light_head_rfcn_eval.py:263-290 up to bboxes_nms_batch =
+ *   eval_helper.tf_bboxes_select utility/eval_helper.py:556-625 (per class c >= 1: score and box times the 0/1 mask of
+ *   score > select_threshold) -> bboxes_clip :365-404 (against bbox_img) -> filter_boxes :278-317 (both sides >
+ *   min_size, centre inside (0,1)) -> bboxes_resize :423-447 -> bboxes_sort :333-361 (tf.nn.top_k, top_k = 2*nms_topk)
+ *   -> bboxes_nms_batch :449-506 (tf.image.non_max_suppression, zero padded to keep_top_k).
+ * The reference handles one image per call (its comment at :261); here N images and all num_classes-1 classes are
+ * one batch of N*(num_classes-1) independent selections.
+ *   d_probs [N,R,num_classes] softmax scores, d_boxes [N,R,4] decoded boxes (ymin,xmin,ymax,xmax),
+ *   d_bbox_img [N,4], d_min_size [N] (= max(0.0001, min_size_ratio * sqrt(image_h*image_w / net_h*net_w)), :295)
+ *   -> d_out_scores [N,num_classes-1,keep_top_k], d_out_boxes [N,num_classes-1,keep_top_k,4], class c at index c-1,
+ *   descending score, zero padded.  Selection is bit-identical to the CPU restatement (oracle/detections.py).
+ */
+size_t xdet_det_postprocess_workspace_bytes(int N, int R, int num_classes, int top_k);
+int xdet_det_postprocess(const float* d_probs, const float* d_boxes, const float* d_bbox_img, const float* d_min_size,
+                         int N, int R, int num_classes, float select_threshold, int top_k, int keep_top_k,
+                         float nms_threshold, float* d_out_scores, float* d_out_boxes, void* d_workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * fp32-accurate PARITY MODE ("fp32x3", csrc/parity_ops.cu; not on the throughput path).
  * The reference computes every convolution / dense layer in fp32 (tf.layers.conv2d/dense, net/resnet_v2.py:89-100,
  * net/xception_body.py:224-233,381-400,450-475,540-558); north_star asks for box/score deltas within 1e-4 of it.

@@ -65,6 +65,10 @@ def _declare(lib):
     lib.xdet_affine_relu_bf16.argtypes = [c_void_p] * 4 + [c_ll, c_int, c_int, c_void_p]
     lib.xdet_f32_to_bf16_rows.argtypes = [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p]
     lib.xdet_image_to_nhwc8_bf16.argtypes = [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]
+    lib.xdet_det_postprocess_workspace_bytes.argtypes = [c_int] * 4
+    lib.xdet_det_postprocess_workspace_bytes.restype = c_size_t
+    lib.xdet_det_postprocess.argtypes = ([c_void_p] * 4 + [c_int] * 3 + [c_float, c_int, c_int, c_float] +
+                                         [c_void_p] * 3 + [c_size_t, c_void_p])
     lib.xdet_split3_bf16.argtypes = [c_void_p] + [c_ll] * 4 + [c_int] * 4 + [c_void_p, c_int, c_void_p]
     lib.xdet_f32_post.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_int,
                                   c_void_p]

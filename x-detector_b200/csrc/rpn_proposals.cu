@@ -84,6 +84,8 @@ __device__ __forceinline__ bool keep_box(float4 c, float min_size) {  // _filter
 __global__ void __launch_bounds__(kSelThreads) rpn_topk_kernel(const float* __restrict__ scores,
                                                                const float* __restrict__ boxes, int A_tot, int K,
                                                                int P /* pow2 >= K */, float min_size,
+                                                               int prefiltered /* 1: candidates are valid iff score > 0,
+                                                                                  boxes are used as they are */,
                                                                unsigned long long* __restrict__ keys_ws,
                                                                float* __restrict__ top_scores,
                                                                float* __restrict__ top_boxes) {
@@ -101,10 +103,10 @@ __global__ void __launch_bounds__(kSelThreads) rpn_topk_kernel(const float* __re
   __syncthreads();
   int local_valid = 0;
   for (int i = tid; i < A_tot; i += kSelThreads) {
-    const float4 c = clip_box(bx[i]);
     const float s = sc[i];
     unsigned long long key = 0ull;
-    if (keep_box(c, min_size) && s > 0.f) {  // a non-positive score can never outlive _upsample_rois
+    // a non-positive score can never outlive _upsample_rois
+    if (s > 0.f && (prefiltered || keep_box(clip_box(bx[i]), min_size))) {
       key = ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
       ++local_valid;
     }
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(kSelThreads) rpn_topk_kernel(const float* __re
     if (k != 0ull) {
       const unsigned idx = 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull);
       s = __uint_as_float((unsigned)(k >> 32));
-      c = clip_box(bx[idx]);
+      c = prefiltered ? bx[idx] : clip_box(bx[idx]);
     }
     top_scores[(long long)img * K + j] = s;
     reinterpret_cast<float4*>(top_boxes)[(long long)img * K + j] = c;
@@ -245,7 +247,8 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(kSelThreads) nms_scan_kernel(
     const float* __restrict__ top_scores, const float* __restrict__ top_boxes,
     const unsigned long long* __restrict__ mask, int K, int words, int keep_n,
-    const float* __restrict__ shuffle_keys /* [N, keep_n] or NULL */, float* __restrict__ rois /* [N,keep_n,4] */,
+    const float* __restrict__ shuffle_keys /* [N, keep_n] or NULL */, int zero_pad /* 1: no _upsample_rois */,
+    float* __restrict__ rois /* [N,keep_n,4] */,
     float* __restrict__ rois_yxhw /* [N,keep_n,4] or NULL */, float* __restrict__ roi_scores /* [N,keep_n] or NULL */,
     int* __restrict__ nms_keep_idx /* [N,keep_n] positions in the sorted list, -1 padded, or NULL */) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -329,7 +332,13 @@ __global__ void __launch_bounds__(kSelThreads) nms_scan_kernel(
   __syncthreads();
   const int n = s_n;
   float* out = rois + (long long)img * keep_n * 4;
-  if (n == 0) {
+  if (zero_pad) {  // bboxes_nms (utility/eval_helper.py:449-472): the selected boxes, zero padded to keep_n
+    for (int j = tid; j < keep_n; j += kSelThreads) {
+      const bool on = j < n;
+      reinterpret_cast<float4*>(out)[j] = on ? bx[kept[j]] : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (roi_scores) roi_scores[(long long)img * keep_n + j] = on ? sc[kept[j]] : 0.f;
+    }
+  } else if (n == 0) {
     for (int j = tid; j < keep_n; j += kSelThreads) {
       reinterpret_cast<float4*>(out)[j] = make_float4(0.2f, 0.2f, 0.8f, 0.8f);
       if (roi_scores) roi_scores[(long long)img * keep_n + j] = 1.f;
@@ -455,7 +464,7 @@ extern "C" int xdet_rpn_select(const float* d_scores, const float* d_boxes, int 
   if (smem_topk > 200 * 1024) return fail(XDET_EINVAL, "rpn_select: pre_nms_top_n %d too large for the in-CTA sort", K);
   XDET_TRY(check_cuda(cudaFuncSetAttribute(rpn_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_topk),
                       "cudaFuncSetAttribute(rpn_topk)"));
-  rpn_topk_kernel<<<N, kSelThreads, smem_topk, st>>>(d_scores, d_boxes, A_tot, K, P, min_size, keys, top_scores,
+  rpn_topk_kernel<<<N, kSelThreads, smem_topk, st>>>(d_scores, d_boxes, A_tot, K, P, min_size, 0, keys, top_scores,
                                                      top_boxes);
   XDET_TRY(after_launch("rpn_topk_kernel"));
   // (the lower triangle of the matrix is never written and never read)
@@ -464,8 +473,111 @@ extern "C" int xdet_rpn_select(const float* d_scores, const float* d_boxes, int 
   const size_t smem_scan = (size_t)words * 8 + (size_t)keep * 8;
   XDET_TRY(check_cuda(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan),
                       "cudaFuncSetAttribute(nms_scan)"));
-  nms_scan_kernel<<<N, kSelThreads, smem_scan, st>>>(top_scores, top_boxes, mask, K, words, keep, d_shuffle_keys,
+  nms_scan_kernel<<<N, kSelThreads, smem_scan, st>>>(top_scores, top_boxes, mask, K, words, keep, d_shuffle_keys, 0,
                                                      d_rois, d_rois_yxhw, d_roi_scores, d_nms_keep_idx);
+  return after_launch("nms_scan_kernel");
+}
+
+// ---- detection post-processing (light_head_rfcn_eval.py:263-290, utility/eval_helper.py) ------------------------
+namespace xdet {
+namespace {
+// One thread per (image, class >= 1, RoI): tf_bboxes_select_layer (eval_helper.py:556-588: score and box times the
+// 0/1 mask of score > select_threshold), bboxes_clip against bbox_img (:365-404), filter_boxes (:278-317) and
+// bboxes_resize (:423-447).  Candidates that are dropped become (score 0, box 0): exactly what the reference's
+// zero padding looks like to bboxes_sort / bboxes_nms.
+__global__ void __launch_bounds__(256) det_prepare_kernel(const float* __restrict__ probs,
+                                                          const float* __restrict__ boxes,
+                                                          const float* __restrict__ bbox_img,
+                                                          const float* __restrict__ min_size, int R, int num_classes,
+                                                          float select_threshold, float* __restrict__ cand_scores,
+                                                          float* __restrict__ cand_boxes, long long total) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int r = (int)(e % R);
+  const int c1 = (int)((e / R) % (num_classes - 1));
+  const int n = (int)(e / ((long long)R * (num_classes - 1)));
+  const float s0 = probs[((long long)n * R + r) * num_classes + c1 + 1];
+  const float fmask = s0 > select_threshold ? 1.f : 0.f;
+  const float s = __fmul_rn(s0, fmask);
+  const float4 b = reinterpret_cast<const float4*>(boxes)[(long long)n * R + r];
+  const float4 ref = reinterpret_cast<const float4*>(bbox_img)[n];
+  float ymin = fmaxf(__fmul_rn(b.x, fmask), ref.x), xmin = fmaxf(__fmul_rn(b.y, fmask), ref.y);
+  const float ymax = fminf(__fmul_rn(b.z, fmask), ref.z), xmax = fminf(__fmul_rn(b.w, fmask), ref.w);
+  ymin = fminf(ymin, ymax);
+  xmin = fminf(xmin, xmax);
+  const float ms = min_size[n];
+  const float ws = __fsub_rn(xmax, xmin), hs = __fsub_rn(ymax, ymin);
+  const float xc = __fadd_rn(xmin, __fmul_rn(ws, 0.5f)), yc = __fadd_rn(ymin, __fmul_rn(hs, 0.5f));
+  const bool keep = ws > ms && hs > ms && xc > 0.f && yc > 0.f && xc < 1.f && yc < 1.f;
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  float so = 0.f;
+  if (keep && s > 0.f) {
+    const float sy = __fsub_rn(ref.z, ref.x), sx = __fsub_rn(ref.w, ref.y);
+    o = make_float4(__fdiv_rn(__fsub_rn(ymin, ref.x), sy), __fdiv_rn(__fsub_rn(xmin, ref.y), sx),
+                    __fdiv_rn(__fsub_rn(ymax, ref.x), sy), __fdiv_rn(__fsub_rn(xmax, ref.y), sx));
+    so = s;
+  }
+  cand_scores[e] = so;
+  reinterpret_cast<float4*>(cand_boxes)[e] = o;
+}
+}  // namespace
+}  // namespace xdet
+
+extern "C" size_t xdet_det_postprocess_workspace_bytes(int N, int R, int num_classes, int top_k) {
+  const size_t M = (size_t)N * (num_classes - 1);
+  return M * R * (4 + 16) + xdet_rpn_select_workspace_bytes((int)M, R, top_k) + 256;
+}
+
+extern "C" int xdet_det_postprocess(const float* d_probs, const float* d_boxes, const float* d_bbox_img,
+                                    const float* d_min_size, int N, int R, int num_classes, float select_threshold,
+                                    int top_k, int keep_top_k, float nms_threshold, float* d_out_scores,
+                                    float* d_out_boxes, void* d_workspace, size_t workspace_bytes, void* stream) {
+  if (N <= 0 || R <= 0 || num_classes < 2 || top_k <= 0 || keep_top_k <= 0)
+    return fail(XDET_EINVAL, "det_postprocess: non-positive dimension");
+  if (workspace_bytes < xdet_det_postprocess_workspace_bytes(N, R, num_classes, top_k))
+    return fail(XDET_EINVAL, "det_postprocess: workspace too small");
+  if ((reinterpret_cast<uintptr_t>(d_workspace) & 15) != 0) return fail(XDET_EINVAL, "det_postprocess: workspace alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = N * (num_classes - 1);
+  // the sorted list is min(#candidates, top_k) long in the reference; entries past the candidates are zero padding
+  const int K = top_k < R ? top_k : R;
+  const int keep = keep_top_k;
+  unsigned char* ws = reinterpret_cast<unsigned char*>(d_workspace);
+  float* cand_boxes = reinterpret_cast<float*>(ws);
+  ws += (size_t)M * R * 16;
+  float* cand_scores = reinterpret_cast<float*>(ws);
+  ws += (size_t)M * R * 4;
+  ws += (16 - (reinterpret_cast<uintptr_t>(ws) & 15)) & 15;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws);
+  ws += (size_t)M * R * 8;
+  float* top_boxes = reinterpret_cast<float*>(ws);
+  ws += (size_t)M * K * 16;
+  float* top_scores = reinterpret_cast<float*>(ws);
+  ws += (size_t)M * K * 4;
+  ws += (16 - (reinterpret_cast<uintptr_t>(ws) & 15)) & 15;
+  unsigned long long* mask = reinterpret_cast<unsigned long long*>(ws);
+
+  const long long total = (long long)M * R;
+  det_prepare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_probs, d_boxes, d_bbox_img, d_min_size, R,
+                                                                      num_classes, select_threshold, cand_scores,
+                                                                      cand_boxes, total);
+  XDET_TRY(after_launch("det_prepare_kernel"));
+  const int words = (K + 63) / 64;
+  const int P = next_pow2(K);
+  const size_t smem_topk = (size_t)P * 8;
+  if (smem_topk > 200 * 1024) return fail(XDET_EINVAL, "det_postprocess: top_k %d too large for the in-CTA sort", K);
+  XDET_TRY(check_cuda(cudaFuncSetAttribute(rpn_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_topk),
+                      "cudaFuncSetAttribute(rpn_topk)"));
+  rpn_topk_kernel<<<M, kSelThreads, smem_topk, st>>>(cand_scores, cand_boxes, R, K, P, 0.f, 1, keys, top_scores,
+                                                     top_boxes);
+  XDET_TRY(after_launch("rpn_topk_kernel"));
+  nms_mask_kernel<<<dim3(words, words, M), 64, 0, st>>>(top_boxes, K, words, nms_threshold, mask);
+  XDET_TRY(after_launch("nms_mask_kernel"));
+  const size_t smem_scan = (size_t)words * 8 + (size_t)keep * 8;
+  XDET_TRY(check_cuda(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan),
+                      "cudaFuncSetAttribute(nms_scan)"));
+  nms_scan_kernel<<<M, kSelThreads, smem_scan, st>>>(top_scores, top_boxes, mask, K, words, keep, nullptr, 1,
+                                                     d_out_boxes, nullptr, d_out_scores, nullptr);
   return after_launch("nms_scan_kernel");
 }
 

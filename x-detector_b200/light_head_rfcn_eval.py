@@ -4,8 +4,9 @@
 * ``lighr_head_model_fn(features, labels, mode, params)`` (reference :364-445, spelling kept) runs the graph
   up to ``head_bboxes_pred`` / ``head_cls_score`` -- backbone -> get_rpn -> large_sep_kernel -> objectness /
   decode_all_anchors -> get_proposals -> get_head -> ext_decode_rois + softmax -- entirely on the GPU (the
-  reference bounces through /cpu:0 for proposals).  Per-class NMS / VOC mAP (``bboxes_eval``, :263-362) are the
-  "next" rows of SURVEY 8(f) and are not built.
+  reference bounces through /cpu:0 for proposals).
+* ``bboxes_eval`` (:263-290): the per-class select / clip / filter / sort / NMS post-processing, one batched GPU
+  selection.  TP/FP matching and VOC mAP (:292-362) are SURVEY 8 f3 and are not built.
 * ``main`` runs the model on synthetic VOC-shaped tensors (no dataset / checkpoint exists offline).
 
 Batch size: the reference evaluates one image at a time (:212); nothing here depends on that, N images are
@@ -70,6 +71,32 @@ def input_pipeline(params, device="cuda"):
     return {'rpn_decode_fn': lambda pred: enc.decode_all_anchors([pred], squeeze_inner=True)[0],
             'head_decode_fn': lambda rois, pred: enc.ext_decode_rois(rois, pred, head_prior_scaling=[1., 1., 1., 1.]),
             'num_anchors_list': num_anchors_list, 'anchor_encoder': enc}
+
+
+def bboxes_eval(image_shape, bbox_img, cls_pred_prob, bboxes_pred, num_classes, params=None):
+    """Detection post-processing of the reference's ``bboxes_eval`` (light_head_rfcn_eval.py:263-290, the
+    '/device:CPU:0' block): per class c >= 1 select (score > select_threshold) -> clip to ``bbox_img`` -> filter
+    (min size 0.03 of the net input, centre inside) -> resize to the original image frame -> top 2*nms_topk ->
+    NMS(nms_threshold) -> nms_topk, zero padded.  On the GPU, batched over images AND classes (the reference handles
+    one image per call on the CPU).
+
+    image_shape [N,2] (h, w of the original images; host ints), bbox_img [N,4], cls_pred_prob [N,R,num_classes]
+    (softmax scores, e.g. ``head_cls_score``), bboxes_pred [N,R,4] (decoded, e.g. ``bboxes_predict``).
+    Returns ({c: scores [N,nms_topk]}, {c: bboxes [N,nms_topk,4]}) -- the reference's per-class dictionaries.
+    TP/FP matching and mAP (``bboxes_matching_batch``, ``metrics``) are SURVEY 8 f3, not built."""
+    import numpy as np
+    p = params or _DEFAULTS
+    N = cls_pred_prob.shape[0]
+    net = np.float32(int(p['train_image_size']) * int(p['train_image_size']))
+    shp = np.asarray(image_shape, dtype=np.int64).reshape(N, 2)
+    # utility/eval_helper.py:295 in fp32: max(0.0001, 0.03 * sqrt(float32(h*w) / (net_h*net_w)))
+    q = (shp[:, 0] * shp[:, 1]).astype(np.float32) / net
+    min_size = np.maximum(np.float32(0.0001), np.float32(0.03) * np.sqrt(q, dtype=np.float32)).astype(np.float32)
+    dev = cls_pred_prob.device
+    scores, boxes = ops.det_postprocess(cls_pred_prob, bboxes_pred, bbox_img.to(dev, torch.float32),
+                                        torch.from_numpy(min_size).to(dev), p['select_threshold'], 2 * p['nms_topk'],
+                                        p['nms_topk'], p['nms_threshold'])
+    return ({c: scores[:, c - 1] for c in range(1, num_classes)}, {c: boxes[:, c - 1] for c in range(1, num_classes)})
 
 
 _SIDE_STREAMS = {}

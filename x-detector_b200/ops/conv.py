@@ -224,18 +224,74 @@ def f32_post(x, residual=None, relu=False, out=None, scale2=None, bias2=None, ou
     return (out if store_out else None), out2
 
 
+# The tensor core's fp32 accumulator truncates instead of rounding, so the error of one launch grows with the number
+# of accumulation steps (K/16).  Parity mode therefore caps the reduction length of a launch at PARITY_MAX_K operand
+# elements (6 * taps * channels): longer reductions run as several launches over channel chunks whose fp32 partial
+# results are added with round-to-nearest by xdet_f32_post.  0 = never chunk.
+PARITY_MAX_K = 768
+_chunk_cache = {}
+
+
+def _weight_chunk(w_packed, cout, taps, cin, c0, c1):
+    """Packed "fp32x3" weights of input channels [c0, c1): the six blocks of the chunk, re-padded to 64 per tap."""
+    key = (w_packed.data_ptr(), c0, c1)
+    hit = _chunk_cache.get(key)
+    if hit is None or hit[0] is not w_packed:
+        cpad = w_packed.shape[1] // taps
+        idx = torch.cat([torch.arange(j * cin + c0, j * cin + c1, device=w_packed.device) for j in range(6)])
+        wv = w_packed.view(cout, taps, cpad)[:, :, idx]
+        n = wv.shape[2]
+        npad = (n + 63) // 64 * 64
+        out = torch.zeros((cout, taps, npad), dtype=w_packed.dtype, device=w_packed.device)
+        out[:, :, :n] = wv
+        hit = (w_packed, out.reshape(cout, taps * npad).contiguous())
+        _chunk_cache[key] = hit
+    return hit[1]
+
+
+def _ones(n, device):
+    key = ("ones", n, str(device))
+    if key not in _chunk_cache:
+        _chunk_cache[key] = torch.ones(n, dtype=torch.float32, device=device)
+    return _chunk_cache[key]
+
+
 def _conv2d_fp32x3(x, w_packed, cout, kh, kw, *, dilation, padding, scale, bias, relu, residual, out, out_layout, out2,
                    scale2, bias2, cin, block_n, strides, skip_out):
     """``conv2d_nhwc`` in "fp32x3" precision: split the fp32 input, run the bf16 kernel over 6*Cin channels with an
     fp32 output, then (residual / second output) the fp32 elementwise tail.  Outputs are fp32."""
     cin = x.shape[-1] if cin is None else cin
-    xs = split3(x, cin)
     layout = "nhwc_f32" if out_layout == "nhwc_bf16" else out_layout
     tail = residual is not None or out2 is not None or scale2 is not None
     assert not tail or layout == "nhwc_f32"
-    raw = conv2d_nhwc(xs, w_packed, cout, kh, kw, dilation=dilation, padding=padding, scale=scale, bias=bias,
-                      relu=relu and residual is None, out=None if tail else out, out_layout=layout, cin=6 * cin,
-                      block_n=block_n, strides=strides)
+    taps = kh * kw
+    c_chunk = cin if PARITY_MAX_K <= 0 else max(8, PARITY_MAX_K // (6 * taps) // 8 * 8)
+    if cin <= c_chunk:
+        raw = conv2d_nhwc(split3(x, cin), w_packed, cout, kh, kw, dilation=dilation, padding=padding, scale=scale,
+                          bias=bias, relu=relu and residual is None, out=None if tail else out, out_layout=layout,
+                          cin=6 * cin, block_n=block_n, strides=strides)
+    else:
+        acc = None
+        for c0 in range(0, cin, c_chunk):
+            c1 = min(cin, c0 + c_chunk)
+            part = conv2d_nhwc(split3(x[..., c0:c1]), _weight_chunk(w_packed, cout, taps, cin, c0, c1), cout, kh, kw,
+                               dilation=dilation, padding=padding, out_layout="nhwc_f32", cin=6 * (c1 - c0),
+                               block_n=block_n, strides=strides)
+            acc = part if acc is None else f32_post(acc, residual=part, out=acc)[0]
+        if scale is not None or bias is not None or relu:
+            sc = scale if scale is not None else _ones(cout, x.device)
+            bi = bias if bias is not None else torch.zeros_like(sc)
+            raw = f32_post(acc, scale2=sc, bias2=bi, relu2=relu and residual is None, out2=acc, store_out=False)[1]
+        else:
+            raw = acc
+        if layout == "nchw_f32":  # layout plumbing of the chunked form only (the single launch stores NCHW itself)
+            raw = raw.permute(0, 3, 1, 2).contiguous()
+            if out is not None:
+                out.copy_(raw)
+                raw = out
+        elif out is not None and not tail:
+            out.copy_(raw)
+            raw = out
     if not tail:
         return raw
     y, _ = f32_post(raw, residual=residual, relu=relu, out=raw if out is None else out, scale2=scale2, bias2=bias2,

@@ -66,3 +66,29 @@ def head_decode(rois, head_out, cls_off, num_classes, loc_off):
                                         probs.data_ptr(), boxes.data_ptr(), _st())
     _native.check(rc)
     return probs, boxes
+
+
+def det_postprocess(probs, boxes, bbox_img, min_size, select_threshold, top_k, keep_top_k, nms_threshold):
+    """probs [N,R,num_classes], boxes [N,R,4], bbox_img [N,4], min_size [N] (fp32 CUDA) -> per-class detections
+    scores [N,num_classes-1,keep_top_k], boxes [N,num_classes-1,keep_top_k,4] (class c at index c-1), descending,
+    zero padded: tf_bboxes_select -> bboxes_clip -> filter_boxes -> bboxes_resize -> bboxes_sort -> bboxes_nms_batch
+    of the reference's bboxes_eval (light_head_rfcn_eval.py:263-290) as one batched GPU selection."""
+    N, R, C = probs.shape
+    assert boxes.shape == (N, R, 4) and bbox_img.shape == (N, 4) and min_size.shape == (N,)
+    for t in (probs, boxes, bbox_img, min_size):
+        assert t.dtype == torch.float32 and t.is_cuda
+    probs, boxes, bbox_img, min_size = probs.contiguous(), boxes.contiguous(), bbox_img.contiguous(), min_size.contiguous()
+    dev = probs.device
+    need = _native.lib().xdet_det_postprocess_workspace_bytes(N, R, C, top_k)
+    key = (dev, torch.cuda.current_stream().cuda_stream, "det")
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        _ws_cache[key] = ws
+    out_s = torch.empty((N, C - 1, keep_top_k), dtype=torch.float32, device=dev)
+    out_b = torch.empty((N, C - 1, keep_top_k, 4), dtype=torch.float32, device=dev)
+    rc = _native.lib().xdet_det_postprocess(probs.data_ptr(), boxes.data_ptr(), bbox_img.data_ptr(), min_size.data_ptr(),
+                                            N, R, C, float(select_threshold), top_k, keep_top_k, float(nms_threshold),
+                                            out_s.data_ptr(), out_b.data_ptr(), ws.data_ptr(), ws.numel(), _st())
+    _native.check(rc)
+    return out_s, out_b
