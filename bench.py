@@ -151,17 +151,22 @@ class LightHeadResnet50:
 
         params = lh.make_params(train_image_size=self.size, backbone=self.backbone, rpn_min_size=16.0 / self.size)
         model = lh.LightHeadRFCN(params, seed=0)
+        conv_ops.AUTOTUNE = not args.no_autotune  # one-time tile-shape tuning per layer shape during the eager pass
         imgs_h = torch.from_numpy(self.images(rank)).pin_memory()
         imgs_d = imgs_h.cuda()
         R = params["rpn_post_nms_top_n"]
-        probs_h = torch.empty((self.batch * R, params["num_classes"]), dtype=torch.float32).pin_memory()
-        boxes_h = torch.empty((self.batch * R, 4), dtype=torch.float32).pin_memory()
+        # the step ends with the per-class detections (bboxes_eval): what the reference's eval loop consumes
+        ncls, ndet = params["num_classes"] - 1, params["nms_topk"]
+        probs_h = torch.empty((self.batch, ncls, ndet), dtype=torch.float32).pin_memory()
+        boxes_h = torch.empty((self.batch, ncls, ndet, 4), dtype=torch.float32).pin_memory()
+        del R
+        run = lambda x: model(x, detections=True)  # noqa: E731
 
         # ---- build: one eager pass creates the variables / packed weights, then the whole forward is
         # captured into a CUDA graph (launch-bound otherwise: ~90 kernels per step) ------------------
         static_in = torch.empty_like(imgs_d)
         static_in.copy_(imgs_d)
-        out = model(static_in)
+        out = run(static_in)
         torch.cuda.synchronize()
         graph = None
         if not args.no_graph:
@@ -170,17 +175,17 @@ class LightHeadResnet50:
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):
                     for _ in range(2):
-                        out = model(static_in)
+                        out = run(static_in)
                 torch.cuda.current_stream().wait_stream(side)
                 torch.cuda.synchronize()
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
-                    out = model(static_in)
+                    out = run(static_in)
                 torch.cuda.synchronize()
             except Exception as e:  # report and fall back to eager launches
                 sys.stderr.write("CUDA graph capture failed (%s: %s); timing eager launches\n" % (type(e).__name__, e))
                 graph = None
-                out = model(static_in)
+                out = run(static_in)
                 torch.cuda.synchronize()
 
         launches_per_step = None
@@ -189,10 +194,10 @@ class LightHeadResnet50:
             if graph is not None:
                 graph.replay()
                 return out
-            return model(static_in)
+            return run(static_in)
 
         l0 = _native.launch_count()
-        model(static_in)
+        run(static_in)
         torch.cuda.synchronize()
         launches_per_step = _native.launch_count() - l0
 
@@ -215,8 +220,8 @@ class LightHeadResnet50:
         def e2e_step():
             static_in.copy_(imgs_h, non_blocking=True)
             o = step()
-            probs_h.copy_(o["head_cls_score"], non_blocking=True)
-            boxes_h.copy_(o["bboxes_predict"], non_blocking=True)
+            probs_h.copy_(o["det_scores"], non_blocking=True)
+            boxes_h.copy_(o["det_bboxes"], non_blocking=True)
             torch.cuda.synchronize()
 
         for _ in range(2):
@@ -236,7 +241,7 @@ class LightHeadResnet50:
         for _ in range(3):
             conv_ops.PROFILE.clear()
             torch.cuda._sleep(40_000_000)
-            model(static_in)
+            run(static_in)
             torch.cuda.synchronize()
         prof = conv_ops.PROFILE
         conv_ops.PROFILE = None
@@ -276,8 +281,9 @@ class LightHeadResnet50:
                 "config": {"workload": self.name, "global_batch": world * self.batch,
                            "l2": "working set per step (activations ~0.6 GB) exceeds the 126 MB L2",
                            "sharding": "images partitioned across ranks, no collective (inference)",
-                           "cuda_graph": graph is not None,
-                           "proposals": "pre_nms_top_n=5000 post_nms_top_n=1000 nms=0.7 (eval flags)"},
+                           "cuda_graph": graph is not None, "conv_autotune": bool(conv_ops.AUTOTUNE),
+                           "proposals": "pre_nms_top_n=5000 post_nms_top_n=1000 nms=0.7 (eval flags)",
+                           "postprocess": "bboxes_eval on the GPU inside the step: 20 classes x top-400 x NMS 0.3 -> 200"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": self.unit, "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": int(imgs_h.numel() * 4),
@@ -328,14 +334,21 @@ def cpu_network_baseline(wl, params, sd, reps=1, warmup=0):
     onet.model(img[:, :, :64, :64], sd, dict(params, rpn_pre_nms_top_n=50, rpn_post_nms_top_n=10),
                op.layer_anchors((64, 64), (4, 4), [0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8], [0.1], [1., 2., .5], 16),
                create_seed=0)  # creates any missing variable (tiny input), untimed
+    from oracle import detections as od
+
+    def one():
+        o = onet.model(img, sd, params, anchors)
+        od.bboxes_eval_select(o["head_cls_score"], o["bboxes_predict"], np.array([0, 0, 1, 1], np.float32),
+                              (wl.size, wl.size), params["num_classes"], train_image_size=wl.size)
+
     for _ in range(warmup):
-        onet.model(img, sd, params, anchors)
+        one()
     t0 = time.perf_counter()
     for _ in range(reps):
-        onet.model(img, sd, params, anchors)
+        one()
     dt = (time.perf_counter() - t0) / reps
     return {"value": 1.0 / dt, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": "1 image of the batch per step (whole graph incl. proposals/NMS and PsRoIAlign C oracle), "
+            "sample": "1 image of the batch per step (whole graph incl. proposals/NMS, PsRoIAlign C oracle, per-class NMS), "
                       "PyTorch-CPU fp32 restatement, %d threads, %d rep(s)" % (cores, reps)}
 
 
@@ -619,7 +632,7 @@ class LightHeadResnet50Train:
                            "l2": "working set per step (saved activations ~2 GB) exceeds the 126 MB L2",
                            "sharding": "images partitioned across ranks; one NCCL all-reduce of the flat fp32 gradient "
                                        "buffer (%.0f MB) per step" % (trainer.grads.numel() * 4 / 1e6),
-                           "cuda_graph": graph is not None,
+                           "cuda_graph": graph is not None, "conv_autotune": bool(conv_ops.AUTOTUNE),
                            "flags": "rpn 10000->1800 @0.7, 64 RoIs/img @25% fg, OHEM 32, 256 RPN samples/img, momentum 0.9"},
                 "clocks": clocks,
                 "e2e": {"value": world * self.batch / (e2e_ms * 1e-3), "unit": self.unit, "ms_per_step": e2e_ms,
@@ -672,6 +685,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph replay")
+    ap.add_argument("--no-autotune", action="store_true", help="keep the heuristic conv tile shapes (no per-shape tuning)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]()
     if args.impl == "reference":

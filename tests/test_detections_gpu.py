@@ -79,3 +79,37 @@ def test_empty_and_saturated_classes(lh):
         assert np.array_equal(bits(d_scores[c][0].cpu().numpy()), bits(ref_s[c]))
         assert np.array_equal(bits(d_boxes[c][0].cpu().numpy()), bits(ref_b[c]))
     assert not d_scores[2].any() and (d_scores[1][0] > 0).sum() == 200
+
+
+def test_model_call_with_detections(lh):
+    """LightHeadRFCN(..., detections=True): the per-class detections of the model's own head outputs equal the
+    oracle chain applied to those outputs (bit-exact selection), also when replayed from a CUDA graph."""
+    params = lh.make_params(train_image_size=160, rpn_pre_nms_top_n=300, rpn_post_nms_top_n=64, rpn_min_size=16.0 / 160,
+                            select_threshold=0.02)
+    model = lh.LightHeadRFCN(params, seed=1)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    images = torch.rand((2, 3, 160, 160), generator=g, device="cuda") * 2 - 1
+    out = model(images, detections=True)
+    torch.cuda.synchronize()
+    assert out["det_scores"].shape == (2, 20, 200) and out["det_bboxes"].shape == (2, 20, 200, 4)
+    probs = out["head_cls_score"].reshape(2, -1, 21).cpu().numpy()
+    boxes = out["bboxes_predict"].reshape(2, -1, 4).cpu().numpy()
+    for i in range(2):
+        ref_s, ref_b = od.bboxes_eval_select(probs[i], boxes[i], np.array([0, 0, 1, 1], np.float32), (160, 160), 21,
+                                             select_threshold=0.02, train_image_size=160)
+        for c in range(1, 21):
+            assert np.array_equal(bits(out["det_scores"][i, c - 1].cpu().numpy()), bits(ref_s[c]))
+            assert np.array_equal(bits(out["det_bboxes"][i, c - 1].cpu().numpy()), bits(ref_b[c]))
+    # graph replay gives the same detections
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        model(images, detections=True)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out2 = model(images, detections=True)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out2["det_scores"], out["det_scores"]) and torch.equal(out2["det_bboxes"], out["det_bboxes"])

@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_parity_mode_gpu.py tests/test_detections_gpu.py tests/test_proposals_gpu.py -q -m gpu > gpurun_out/c6_tests.log 2>&1; echo "rc=$?" >> gpurun_out/c6_tests.log
-grep -n "^E  \|passed\|failed\|rc=\|Error" gpurun_out/c6_tests.log | cut -c1-300 | head -40
+timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_net_tuned.json 2> gpurun_out/bench_net_tuned.err; tail -3 gpurun_out/bench_net_tuned.err; cat gpurun_out/bench_net_tuned.json | cut -c1-400
+timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --no-autotune > gpurun_out/bench_net_untuned.json 2>> gpurun_out/bench_net_tuned.err; cat gpurun_out/bench_net_untuned.json | cut -c1-250
+timeout 600 python -m pytest tests/test_conv_gpu.py tests/test_model_gpu.py -q -m gpu -x 2>&1 | tail -3

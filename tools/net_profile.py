@@ -36,11 +36,11 @@ def main():
         g = torch.Generator(device="cuda").manual_seed(1)
         images = torch.rand((args.batch, 3, args.size, args.size), generator=g, device="cuda") * 2 - 1
     for _ in range(3):
-        model(images)
+        model(images, detections=True)
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for _ in range(args.steps):
-            model(images)
+            model(images, detections=True)
         torch.cuda.synchronize()
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     agg = collections.OrderedDict()

@@ -551,7 +551,7 @@ extern "C" int xdet_conv2d_bf16(const void* d_in, const xdet_conv_desc* d, void*
 
   // epilogue staging: memory-bound layers (few k-blocks per tile) get two epilogue warpgroups; a residual is
   // prefetched two chunks ahead into a third slot and overwritten in place by the result
-  a.epi_groups = (a.tma_epilogue && a.num_k_blocks <= 12) ? 2 : 1;
+  a.epi_groups = (a.tma_epilogue && a.num_k_blocks <= 40) ? 2 : 1;  // measured: tools/conv_floor.py
   if (d->epi_groups == 1 || d->epi_groups == 2) a.epi_groups = a.tma_epilogue ? d->epi_groups : 1;
   a.n_slots = a.tma_epilogue ? (a.has_res ? 3 : 2) : 0;
   a.n_out2 = a.has_out2 ? (a.has_res ? 1 : 2) : 0;

@@ -28,6 +28,7 @@ namespace xdet {
 namespace {
 
 constexpr int kSelThreads = 1024;
+constexpr int kDetThreads = 256;  // CTA size of the per-(image, class) selections of xdet_det_postprocess
 
 // ---- decode ------------------------------------------------------------------------------------
 // rpn_out: [N, h, w, ch_stride] fp32 with the 2A class logits at channel cls_off + a*2 + {0,1} and the
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(kSelThreads) rpn_topk_kernel(const float* __re
   __shared__ unsigned int hist[256];
   __shared__ unsigned long long s_prefix;
   __shared__ int s_remaining, s_count, s_nvalid;
-  const int img = blockIdx.x, tid = threadIdx.x;
+  const int img = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
   const float* sc = scores + (long long)img * A_tot;
   const float4* bx = reinterpret_cast<const float4*>(boxes) + (long long)img * A_tot;
   unsigned long long* keys = keys_ws + (long long)img * A_tot;
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(kSelThreads) rpn_topk_kernel(const float* __re
   if (tid == 0) s_nvalid = 0;
   __syncthreads();
   int local_valid = 0;
-  for (int i = tid; i < A_tot; i += kSelThreads) {
+  for (int i = tid; i < A_tot; i += nthr) {
     const float s = sc[i];
     unsigned long long key = 0ull;
     // a non-positive score can never outlive _upsample_rois
@@ -115,20 +116,29 @@ __global__ void __launch_bounds__(kSelThreads) rpn_topk_kernel(const float* __re
   atomicAdd(&s_nvalid, local_valid);
   __syncthreads();
   const int keff = min(K, s_nvalid);
+  if (keff == 0) {  // nothing to select (e.g. a class without detections): the zero padding is the whole answer
+    for (int j = tid; j < K; j += nthr) {
+      top_scores[(long long)img * K + j] = 0.f;
+      reinterpret_cast<float4*>(top_boxes)[(long long)img * K + j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return;
+  }
 
   // radix select: find the keff-th largest key (keys are unique, 0 = filtered out)
   unsigned long long thr = ~0ull;  // nothing selected when keff == 0
-  if (keff > 0) {
+  if (keff > 0 && s_nvalid <= K) {
+    thr = 1ull;  // every valid key is selected: no selection pass needed
+  } else if (keff > 0) {
     if (tid == 0) {
       s_prefix = 0ull;
       s_remaining = keff;
     }
     for (int pass = 0; pass < 8; ++pass) {
       const int shift = 56 - 8 * pass;
-      for (int i = tid; i < 256; i += kSelThreads) hist[i] = 0;
+      for (int i = tid; i < 256; i += nthr) hist[i] = 0;
       __syncthreads();
       const unsigned long long prefix = s_prefix;
-      for (int i = tid; i < A_tot; i += kSelThreads) {
+      for (int i = tid; i < A_tot; i += nthr) {
         const unsigned long long k = keys[i];
         const bool match = (pass == 0) || ((k >> (shift + 8)) == (prefix >> (shift + 8)));
         if (match && k != 0ull) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
@@ -151,10 +161,10 @@ __global__ void __launch_bounds__(kSelThreads) rpn_topk_kernel(const float* __re
 
   // compact the selected keys into shared memory, pad with zeros, sort descending
   if (tid == 0) s_count = 0;
-  for (int i = tid; i < P; i += kSelThreads) sk[i] = 0ull;
+  for (int i = tid; i < P; i += nthr) sk[i] = 0ull;
   __syncthreads();
   if (keff > 0) {
-    for (int i = tid; i < A_tot; i += kSelThreads) {
+    for (int i = tid; i < A_tot; i += nthr) {
       const unsigned long long k = keys[i];
       if (k != 0ull && k >= thr) sk[atomicAdd(&s_count, 1)] = k;
     }
@@ -162,7 +172,7 @@ __global__ void __launch_bounds__(kSelThreads) rpn_topk_kernel(const float* __re
   __syncthreads();
   for (int size = 2; size <= P; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = tid; t < (P >> 1); t += kSelThreads) {
+      for (int t = tid; t < (P >> 1); t += nthr) {
         const int lo = ((t / stride) * (stride << 1)) + (t % stride);
         const int hi = lo + stride;
         const bool desc = ((lo & size) == 0);  // first half of each `size` block descending
@@ -176,7 +186,7 @@ __global__ void __launch_bounds__(kSelThreads) rpn_topk_kernel(const float* __re
     }
   }
   // sorted outputs (zero padded to K, as _pad_axis does)
-  for (int j = tid; j < K; j += kSelThreads) {
+  for (int j = tid; j < K; j += nthr) {
     const unsigned long long k = sk[j];
     float s = 0.f;
     float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -257,12 +267,12 @@ __global__ void __launch_bounds__(kSelThreads) nms_scan_kernel(
   int* shuf = kept + keep_n;                                                      // [keep_n]
   __shared__ unsigned long long s_surv;
   __shared__ unsigned long long s_diag[64];
-  const int img = blockIdx.x, tid = threadIdx.x;
+  const int img = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
   const unsigned long long* m = mask + (long long)img * K * words;
   const float* sc = top_scores + (long long)img * K;
   const float4* bx = reinterpret_cast<const float4*>(top_boxes) + (long long)img * K;
 
-  for (int i = tid; i < words; i += kSelThreads) removed[i] = 0ull;
+  for (int i = tid; i < words; i += nthr) removed[i] = 0ull;
   __syncthreads();
   const int out_size = min(keep_n, K);
   int nk = 0;  // every thread tracks the kept count in a register (no shared read/write race)
@@ -295,12 +305,12 @@ __global__ void __launch_bounds__(kSelThreads) nms_scan_kernel(
     const int nw = words - cb - 1;
     if (surv && nw > 0 && nk < out_size) {
       const int total = 64 * nw;
-      for (int base = tid; base < total; base += 4 * kSelThreads) {
+      for (int base = tid; base < total; base += 4 * nthr) {
         unsigned long long v[4];
         int ww[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int idx = base + u * kSelThreads;
+          const int idx = base + u * nthr;
           v[u] = 0ull;
           ww[u] = 0;
           if (idx < total) {
@@ -317,7 +327,7 @@ __global__ void __launch_bounds__(kSelThreads) nms_scan_kernel(
     __syncthreads();
   }
   if (nms_keep_idx)
-    for (int j = tid; j < keep_n; j += kSelThreads) nms_keep_idx[(long long)img * keep_n + j] = j < nk ? kept[j] : -1;
+    for (int j = tid; j < keep_n; j += nthr) nms_keep_idx[(long long)img * keep_n + j] = j < nk ? kept[j] : -1;
 
   // _upsample_rois: drop paddings (score <= 0).  The kept list is in descending score order, so the
   // positive-score entries are a prefix and their count is its length.
@@ -326,20 +336,20 @@ __global__ void __launch_bounds__(kSelThreads) nms_scan_kernel(
   __syncthreads();
   {
     int c = 0;
-    for (int j = tid; j < nk; j += kSelThreads) c += (sc[kept[j]] > 0.f) ? 1 : 0;
+    for (int j = tid; j < nk; j += nthr) c += (sc[kept[j]] > 0.f) ? 1 : 0;
     if (c) atomicAdd(&s_n, c);
   }
   __syncthreads();
   const int n = s_n;
   float* out = rois + (long long)img * keep_n * 4;
   if (zero_pad) {  // bboxes_nms (utility/eval_helper.py:449-472): the selected boxes, zero padded to keep_n
-    for (int j = tid; j < keep_n; j += kSelThreads) {
+    for (int j = tid; j < keep_n; j += nthr) {
       const bool on = j < n;
       reinterpret_cast<float4*>(out)[j] = on ? bx[kept[j]] : make_float4(0.f, 0.f, 0.f, 0.f);
       if (roi_scores) roi_scores[(long long)img * keep_n + j] = on ? sc[kept[j]] : 0.f;
     }
   } else if (n == 0) {
-    for (int j = tid; j < keep_n; j += kSelThreads) {
+    for (int j = tid; j < keep_n; j += nthr) {
       reinterpret_cast<float4*>(out)[j] = make_float4(0.2f, 0.2f, 0.8f, 0.8f);
       if (roi_scores) roi_scores[(long long)img * keep_n + j] = 1.f;
     }
@@ -349,7 +359,7 @@ __global__ void __launch_bounds__(kSelThreads) nms_scan_kernel(
     if (rem_cnt > 0) {
       // tf.random_shuffle(range(n))[:rem_cnt] := first rem_cnt of the stable argsort of keys[:n]
       const float* keys = shuffle_keys ? shuffle_keys + (long long)img * keep_n : nullptr;
-      for (int i = tid; i < n; i += kSelThreads) {
+      for (int i = tid; i < n; i += nthr) {
         int rank = i;
         if (keys) {
           const float ki = keys[i];
@@ -364,7 +374,7 @@ __global__ void __launch_bounds__(kSelThreads) nms_scan_kernel(
     }
     __syncthreads();
     const int tiled = left > 0 ? n * (left / n + 1) : keep_n;
-    for (int j = tid; j < keep_n; j += kSelThreads) {
+    for (int j = tid; j < keep_n; j += nthr) {
       const int src = (j < tiled) ? (j % n) : shuf[j - tiled];
       const int pos = kept[src];
       reinterpret_cast<float4*>(out)[j] = bx[pos];
@@ -373,7 +383,7 @@ __global__ void __launch_bounds__(kSelThreads) nms_scan_kernel(
   }
   __syncthreads();
   if (rois_yxhw) {  // _point2center
-    for (int j = tid; j < keep_n; j += kSelThreads) {
+    for (int j = tid; j < keep_n; j += nthr) {
       const float4 b = reinterpret_cast<const float4*>(out)[j];
       const float h = __fsub_rn(b.z, b.x), w = __fsub_rn(b.w, b.y);
       reinterpret_cast<float4*>(rois_yxhw + (long long)img * keep_n * 4)[j] =
@@ -568,7 +578,8 @@ extern "C" int xdet_det_postprocess(const float* d_probs, const float* d_boxes, 
   if (smem_topk > 200 * 1024) return fail(XDET_EINVAL, "det_postprocess: top_k %d too large for the in-CTA sort", K);
   XDET_TRY(check_cuda(cudaFuncSetAttribute(rpn_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_topk),
                       "cudaFuncSetAttribute(rpn_topk)"));
-  rpn_topk_kernel<<<M, kSelThreads, smem_topk, st>>>(cand_scores, cand_boxes, R, K, P, 0.f, 1, keys, top_scores,
+  // many small selections (one per image and class): 256-thread CTAs, several per SM, one wave
+  rpn_topk_kernel<<<M, kDetThreads, smem_topk, st>>>(cand_scores, cand_boxes, R, K, P, 0.f, 1, keys, top_scores,
                                                      top_boxes);
   XDET_TRY(after_launch("rpn_topk_kernel"));
   nms_mask_kernel<<<dim3(words, words, M), 64, 0, st>>>(top_boxes, K, words, nms_threshold, mask);
@@ -576,7 +587,7 @@ extern "C" int xdet_det_postprocess(const float* d_probs, const float* d_boxes, 
   const size_t smem_scan = (size_t)words * 8 + (size_t)keep * 8;
   XDET_TRY(check_cuda(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan),
                       "cudaFuncSetAttribute(nms_scan)"));
-  nms_scan_kernel<<<M, kSelThreads, smem_scan, st>>>(top_scores, top_boxes, mask, K, words, keep, nullptr, 1,
+  nms_scan_kernel<<<M, kDetThreads, smem_scan, st>>>(top_scores, top_boxes, mask, K, words, keep, nullptr, 1,
                                                      d_out_boxes, nullptr, d_out_scores, nullptr);
   return after_launch("nms_scan_kernel");
 }

@@ -73,7 +73,18 @@ def input_pipeline(params, device="cuda"):
             'num_anchors_list': num_anchors_list, 'anchor_encoder': enc}
 
 
-def bboxes_eval(image_shape, bbox_img, cls_pred_prob, bboxes_pred, num_classes, params=None):
+def det_min_size(image_shape, train_image_size, device):
+    """utility/eval_helper.py:295 in fp32 on the host: max(0.0001, 0.03 * sqrt(float32(h*w) / (net_h*net_w))) per
+    image -> fp32 tensor [N] on ``device`` (a host->device copy: build it outside CUDA-graph capture)."""
+    import numpy as np
+    shp = np.asarray(image_shape, dtype=np.int64).reshape(-1, 2)
+    net = np.float32(int(train_image_size) * int(train_image_size))
+    q = (shp[:, 0] * shp[:, 1]).astype(np.float32) / net
+    ms = np.maximum(np.float32(0.0001), np.float32(0.03) * np.sqrt(q, dtype=np.float32)).astype(np.float32)
+    return torch.from_numpy(ms).to(device)
+
+
+def bboxes_eval(image_shape, bbox_img, cls_pred_prob, bboxes_pred, num_classes, params=None, min_size=None):
     """Detection post-processing of the reference's ``bboxes_eval`` (light_head_rfcn_eval.py:263-290, the
     '/device:CPU:0' block): per class c >= 1 select (score > select_threshold) -> clip to ``bbox_img`` -> filter
     (min size 0.03 of the net input, centre inside) -> resize to the original image frame -> top 2*nms_topk ->
@@ -84,18 +95,12 @@ def bboxes_eval(image_shape, bbox_img, cls_pred_prob, bboxes_pred, num_classes, 
     (softmax scores, e.g. ``head_cls_score``), bboxes_pred [N,R,4] (decoded, e.g. ``bboxes_predict``).
     Returns ({c: scores [N,nms_topk]}, {c: bboxes [N,nms_topk,4]}) -- the reference's per-class dictionaries.
     TP/FP matching and mAP (``bboxes_matching_batch``, ``metrics``) are SURVEY 8 f3, not built."""
-    import numpy as np
     p = params or _DEFAULTS
-    N = cls_pred_prob.shape[0]
-    net = np.float32(int(p['train_image_size']) * int(p['train_image_size']))
-    shp = np.asarray(image_shape, dtype=np.int64).reshape(N, 2)
-    # utility/eval_helper.py:295 in fp32: max(0.0001, 0.03 * sqrt(float32(h*w) / (net_h*net_w)))
-    q = (shp[:, 0] * shp[:, 1]).astype(np.float32) / net
-    min_size = np.maximum(np.float32(0.0001), np.float32(0.03) * np.sqrt(q, dtype=np.float32)).astype(np.float32)
     dev = cls_pred_prob.device
-    scores, boxes = ops.det_postprocess(cls_pred_prob, bboxes_pred, bbox_img.to(dev, torch.float32),
-                                        torch.from_numpy(min_size).to(dev), p['select_threshold'], 2 * p['nms_topk'],
-                                        p['nms_topk'], p['nms_threshold'])
+    if min_size is None:  # ``min_size`` [N] fp32 on the device may be passed instead (det_min_size, precomputed)
+        min_size = det_min_size(image_shape, p['train_image_size'], dev)
+    scores, boxes = ops.det_postprocess(cls_pred_prob, bboxes_pred, bbox_img.to(dev, torch.float32), min_size,
+                                        p['select_threshold'], 2 * p['nms_topk'], p['nms_topk'], p['nms_threshold'])
     return ({c: scores[:, c - 1] for c in range(1, num_classes)}, {c: boxes[:, c - 1] for c in range(1, num_classes)})
 
 
@@ -180,12 +185,37 @@ class LightHeadRFCN(object):
         self.store = VariableStore(device=device, seed=seed, state_dict=state_dict)
         self.labels = input_pipeline(self.params, device=device)
 
-    def __call__(self, images, shuffle_keys=None):
+        self._det_consts = {}
+
+    def det_consts(self, n, image_shape=None, bbox_img=None, device="cuda"):
+        """(bbox_img [n,4], min_size [n]) device tensors for the post-processing; cached, so a CUDA-graph capture of
+        ``__call__(..., detections=True)`` finds them already on the device.  Defaults: the whole net input is the
+        image (bbox_img = [0,0,1,1], image_shape = train_image_size squared) -- the synthetic-tensor case."""
+        size = self.params['train_image_size']
+        shp = tuple(map(tuple, image_shape)) if image_shape is not None else ((size, size),) * n
+        ref = tuple(map(tuple, bbox_img)) if bbox_img is not None else ((0., 0., 1., 1.),) * n
+        key = (n, shp, ref, str(device))
+        if key not in self._det_consts:
+            self._det_consts[key] = (torch.tensor(ref, dtype=torch.float32, device=device),
+                                     det_min_size(shp, size, device))
+        return self._det_consts[key]
+
+    def __call__(self, images, shuffle_keys=None, detections=False, image_shape=None, bbox_img=None):
+        """One batch through the model_fn.  ``detections=True`` also runs ``bboxes_eval`` and adds 'det_scores'
+        [N,num_classes-1,nms_topk] and 'det_bboxes' [N,num_classes-1,nms_topk,4] (class c at index c-1)."""
         # a fresh naming pass per call: variables are looked up by the same automatic names every time
         self.store._counters = [{}]
         with conv_ops.precision(self.params.get('precision', 'bf16')):
-            return lighr_head_model_fn(images, self.labels, "eval", self.params, store=self.store,
-                                       shuffle_keys=shuffle_keys)
+            out = lighr_head_model_fn(images, self.labels, "eval", self.params, store=self.store,
+                                      shuffle_keys=shuffle_keys)
+        if detections:
+            N, C = images.shape[0], self.params['num_classes']
+            ref, min_size = self.det_consts(N, image_shape, bbox_img, images.device)
+            p = self.params
+            out['det_scores'], out['det_bboxes'] = ops.det_postprocess(
+                out['head_cls_score'].reshape(N, -1, C), out['bboxes_predict'].reshape(N, -1, 4), ref, min_size,
+                p['select_threshold'], 2 * p['nms_topk'], p['nms_topk'], p['nms_threshold'])
+        return out
 
 
 def main(argv=None):

@@ -112,6 +112,48 @@ PROFILE = None
 MAX_CTAS = 0
 
 
+# One-time tile-shape tuning per distinct layer shape (like cudnn.benchmark): with AUTOTUNE set, the first eager call
+# of a shape times the N-tile widths {heuristic, 64, 128, 256} x {1, 2} epilogue warpgroups (10 back-to-back launches
+# replayed from a CUDA graph each) and later calls -- including CUDA-graph captures -- use the fastest.  The choice
+# does not change results: every output element accumulates its K products in the same order for any tile width.
+AUTOTUNE = False
+_tune_cache = {}
+
+
+def _autotune(x, d, reps=10):
+    lib = _native.lib()
+    cands = [(0, 0)] + [(bn, eg) for bn in (64, 128, 256) for eg in (1, 2) if bn <= max(64, (d.Cout + 63) // 64 * 64)]
+    best, best_t = (0, 0), None
+    cur = torch.cuda.current_stream()
+    side = torch.cuda.Stream(device=x.device)
+    for bn, eg in cands:
+        d.block_n, d.epi_groups = bn, eg
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            if lib.xdet_conv2d_bf16(x.data_ptr(), ctypes.byref(d), side.cuda_stream) != 0:
+                continue  # this tile shape is not available for the layer (shared memory, alignment)
+            side.synchronize()
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    for _ in range(reps):
+                        lib.xdet_conv2d_bf16(x.data_ptr(), ctypes.byref(d), torch.cuda.current_stream().cuda_stream)
+                g.replay()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(side)
+                g.replay()
+                e1.record(side)
+                side.synchronize()
+                t = e0.elapsed_time(e1)
+            except RuntimeError:
+                continue
+        if best_t is None or t < best_t * 0.985:  # prefer earlier candidates (the heuristic) on ties
+            best, best_t = (bn, eg), t
+    cur.wait_stream(side)
+    d.block_n, d.epi_groups = 0, 0
+    return best
+
+
 class cta_limit(object):
     def __init__(self, n):
         self.n = n
@@ -178,6 +220,12 @@ def conv2d_nhwc(x, w_packed, cout, kh, kw, *, dilation=(1, 1), padding="SAME", s
                  0 if out.dtype == torch.bfloat16 else 1, sn, sy, sx, sc, _ptr(out2), _ptr(scale2), _ptr(bias2),
                  block_n, epi_groups, MAX_CTAS)
     with torch.cuda.device(dev):
+        if AUTOTUNE and block_n == 0 and epi_groups == 0:
+            key = (N, H, W, cin, cs, cout, kh, kw, dh, dw, pt, pl, Ho, Wo, sh, sw, fold_w is not None, bool(relu),
+                   residual is not None, out2 is not None, bool(skip_out), out_layout, MAX_CTAS > 0)
+            if key not in _tune_cache and not torch.cuda.is_current_stream_capturing():
+                _tune_cache[key] = _autotune(x, d)
+            d.block_n, d.epi_groups = _tune_cache.get(key, (0, 0))
         if PROFILE is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
