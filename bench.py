@@ -216,20 +216,57 @@ class LightHeadResnet50:
         barrier()
         step_ms = e0.elapsed_time(e1) / args.steps
 
-        # ---- end to end with HOST buffers: H2D of the images, D2H of the detections ----------------
-        def e2e_step():
-            static_in.copy_(imgs_h, non_blocking=True)
-            o = step()
-            probs_h.copy_(o["det_scores"], non_blocking=True)
-            boxes_h.copy_(o["det_bboxes"], non_blocking=True)
+        # ---- end to end with HOST buffers: H2D of the images, D2H of the detections, every step -----------
+        # Double-buffered: the pinned images of step i+1 travel host->device on a copy stream while step i computes,
+        # and the detections of step i travel device->host while step i+1 computes (what a serving loop does).  Every
+        # step's copies are inside the timed region; the host waits for the detections of step i-1 before it
+        # enqueues step i+1 (bounded queue), and for everything at the end.
+        stage_in = [torch.empty_like(imgs_d) for _ in range(2)]
+        det_s_d = [torch.empty((self.batch, ncls, ndet), dtype=torch.float32, device="cuda") for _ in range(2)]
+        det_b_d = [torch.empty((self.batch, ncls, ndet, 4), dtype=torch.float32, device="cuda") for _ in range(2)]
+        probs_hh = [probs_h, torch.empty_like(probs_h).pin_memory()]
+        boxes_hh = [boxes_h, torch.empty_like(boxes_h).pin_memory()]
+        cur = torch.cuda.current_stream()
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        ev_in = [torch.cuda.Event() for _ in range(2)]     # images of slot b are on the device
+        ev_free = [torch.cuda.Event() for _ in range(2)]   # slot b's staging buffer has been consumed
+        ev_det = [torch.cuda.Event() for _ in range(2)]    # detections of slot b are in their device buffer
+        ev_done = [torch.cuda.Event() for _ in range(2)]   # detections of slot b are on the host
+
+        def e2e_run(n):
+            with torch.cuda.stream(s_in):
+                stage_in[0].copy_(imgs_h, non_blocking=True)
+                ev_in[0].record(s_in)
+            for i in range(n):
+                b = i & 1
+                if i + 1 < n:  # next step's images: host -> device, behind the compute of this step
+                    with torch.cuda.stream(s_in):
+                        if i >= 1:
+                            s_in.wait_event(ev_free[b ^ 1])
+                        stage_in[b ^ 1].copy_(imgs_h, non_blocking=True)
+                        ev_in[b ^ 1].record(s_in)
+                cur.wait_event(ev_in[b])
+                static_in.copy_(stage_in[b], non_blocking=True)  # device->device, 7 us
+                ev_free[b].record(cur)
+                o = step()
+                if i >= 2:
+                    cur.wait_event(ev_done[b])  # the D2H that last read these device buffers has finished
+                det_s_d[b].copy_(o["det_scores"], non_blocking=True)
+                det_b_d[b].copy_(o["det_bboxes"], non_blocking=True)
+                ev_det[b].record(cur)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_det[b])
+                    probs_hh[b].copy_(det_s_d[b], non_blocking=True)
+                    boxes_hh[b].copy_(det_b_d[b], non_blocking=True)
+                    ev_done[b].record(s_out)
+                if i >= 1:
+                    ev_done[b ^ 1].synchronize()  # the host consumes the detections of step i-1 here
             torch.cuda.synchronize()
 
-        for _ in range(2):
-            e2e_step()
+        e2e_run(3)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
+        e2e_run(args.steps)
         barrier()
         e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
         clocks = sampler.finish()

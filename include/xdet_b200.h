@@ -212,6 +212,18 @@ int xdet_det_postprocess(const float* d_probs, const float* d_boxes, const float
                          float nms_threshold, float* d_out_scores, float* d_out_boxes, void* d_workspace,
                          size_t workspace_bytes, void* stream);
 
+/* TP / FP matching of the per-class detections against ground truth (GPU half).
+ * Replaces: eval_helper.bboxes_matching_batch utility/eval_helper.py:790-840 = bboxes_matching :700-788 (one
+ *   tf.while_loop per class over the detections in score order) with bboxes_jaccard :671-699.
+ *   d_det_boxes [N,num_classes-1,Kd,4] (xdet_det_postprocess's d_out_boxes), d_glabels [N,G] int32 (0 = padding),
+ *   d_gbboxes [N,G,4], d_gdifficult [N,G] int32 -> d_tp, d_fp [N,num_classes-1,Kd] uint8, d_n_gbboxes
+ *   [N,num_classes-1] int32 (ground-truth boxes of the class that are not 'difficult').
+ * Zero-padded detections are matched like any other (the reference does the same and drops them later by score,
+ * utility/metrics.py:170-176).  G == 0 (the reference would fail in tf.argmax): every detection is a false positive. */
+int xdet_det_match(const float* d_det_boxes, const int* d_glabels, const float* d_gbboxes, const int* d_gdifficult,
+                   int N, int num_classes, int Kd, int G, float matching_threshold, unsigned char* d_tp,
+                   unsigned char* d_fp, int* d_n_gbboxes, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * fp32-accurate PARITY MODE ("fp32x3", csrc/parity_ops.cu; not on the throughput path).
  * The reference computes every convolution / dense layer in fp32 (tf.layers.conv2d/dense, net/resnet_v2.py:89-100,

@@ -28,7 +28,7 @@ def main():
         tparams = lt.make_params(train_image_size=args.size, batch_size=args.batch)
         trainer = lt.LightHeadTrainer(tparams, seed=0)
         tb = lt.synthetic_batch(tparams, args.batch, seed=3)
-        model = lambda _images: trainer.step(*tb)  # noqa: E731
+        model = lambda _images, detections=False: trainer.step(*tb)  # noqa: E731
         images = None
     else:
         params = lh.make_params(train_image_size=args.size, backbone=args.backbone)

@@ -967,9 +967,10 @@ int launch_fwd(const float* in, const float* rois, float* pooled, int32_t* index
     // measured on B200 (profiles/psroi_sweep_r1.md): the staged variant wins once there are a few million
     // outputs and the bank allows vector channel groups; tiny banks (15x15 bins) stay on the gather kernel
     // SELECT amortises its per-sample bookkeeping over the channels of a lane: it wins with 4-channel groups
-    // (bank % 4 == 0, >= 16) and loses to PLANES with 2-channel groups (the model's bank of 10)
+    // (bank % 4 == 0, >= 16); with 2-channel groups (the model's bank of 10) only from ~6 M outputs on
+    // (profiles/psroi_sweep_r1.md)
     variant = (bins > 0 && planes_vec(bank) >= 2 && total >= (3ll << 19))
-                  ? ((kMax && planes_vec(bank) == 4) ? XDET_PSROI_SELECT : XDET_PSROI_PLANES)
+                  ? ((kMax && (planes_vec(bank) == 4 || total >= (6ll << 20))) ? XDET_PSROI_SELECT : XDET_PSROI_PLANES)
                   : XDET_PSROI_GATHER;
 
   if (variant == XDET_PSROI_PLANES || variant == XDET_PSROI_SELECT) {

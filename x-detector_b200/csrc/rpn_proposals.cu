@@ -100,7 +100,10 @@ __global__ void __launch_bounds__(kSelThreads) rpn_topk_kernel(const float* __re
   const float4* bx = reinterpret_cast<const float4*>(boxes) + (long long)img * A_tot;
   unsigned long long* keys = keys_ws + (long long)img * A_tot;
 
+  const bool direct = A_tot <= P;  // few candidates: sort them all in shared memory, no selection pass
   if (tid == 0) s_nvalid = 0;
+  if (direct)
+    for (int i = tid; i < P; i += nthr) sk[i] = 0ull;
   __syncthreads();
   int local_valid = 0;
   for (int i = tid; i < A_tot; i += nthr) {
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(kSelThreads) rpn_topk_kernel(const float* __re
       key = ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
       ++local_valid;
     }
-    keys[i] = key;
+    if (direct) sk[i] = key; else keys[i] = key;
   }
   atomicAdd(&s_nvalid, local_valid);
   __syncthreads();
@@ -124,52 +127,51 @@ __global__ void __launch_bounds__(kSelThreads) rpn_topk_kernel(const float* __re
     return;
   }
 
-  // radix select: find the keff-th largest key (keys are unique, 0 = filtered out)
-  unsigned long long thr = ~0ull;  // nothing selected when keff == 0
-  if (keff > 0 && s_nvalid <= K) {
-    thr = 1ull;  // every valid key is selected: no selection pass needed
-  } else if (keff > 0) {
-    if (tid == 0) {
-      s_prefix = 0ull;
-      s_remaining = keff;
-    }
-    for (int pass = 0; pass < 8; ++pass) {
-      const int shift = 56 - 8 * pass;
-      for (int i = tid; i < 256; i += nthr) hist[i] = 0;
-      __syncthreads();
-      const unsigned long long prefix = s_prefix;
-      for (int i = tid; i < A_tot; i += nthr) {
-        const unsigned long long k = keys[i];
-        const bool match = (pass == 0) || ((k >> (shift + 8)) == (prefix >> (shift + 8)));
-        if (match && k != 0ull) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
-      }
-      __syncthreads();
+  if (!direct) {
+    // radix select: find the keff-th largest key (keys are unique, 0 = filtered out)
+    unsigned long long thr = 1ull;  // s_nvalid <= K: every valid key is selected, no selection pass needed
+    if (s_nvalid > K) {
       if (tid == 0) {
-        int rem = s_remaining;
-        int b = 255;
-        for (; b > 0; --b) {
-          if ((int)hist[b] >= rem) break;
-          rem -= (int)hist[b];
-        }
-        s_prefix = prefix | ((unsigned long long)b << shift);
-        s_remaining = rem;
+        s_prefix = 0ull;
+        s_remaining = keff;
       }
-      __syncthreads();
+      for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 56 - 8 * pass;
+        for (int i = tid; i < 256; i += nthr) hist[i] = 0;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        for (int i = tid; i < A_tot; i += nthr) {
+          const unsigned long long k = keys[i];
+          const bool match = (pass == 0) || ((k >> (shift + 8)) == (prefix >> (shift + 8)));
+          if (match && k != 0ull) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+          int rem = s_remaining;
+          int b = 255;
+          for (; b > 0; --b) {
+            if ((int)hist[b] >= rem) break;
+            rem -= (int)hist[b];
+          }
+          s_prefix = prefix | ((unsigned long long)b << shift);
+          s_remaining = rem;
+        }
+        __syncthreads();
+      }
+      thr = s_prefix;
     }
-    thr = s_prefix;
-  }
 
-  // compact the selected keys into shared memory, pad with zeros, sort descending
-  if (tid == 0) s_count = 0;
-  for (int i = tid; i < P; i += nthr) sk[i] = 0ull;
-  __syncthreads();
-  if (keff > 0) {
+    // compact the selected keys into shared memory, pad with zeros
+    if (tid == 0) s_count = 0;
+    for (int i = tid; i < P; i += nthr) sk[i] = 0ull;
+    __syncthreads();
     for (int i = tid; i < A_tot; i += nthr) {
       const unsigned long long k = keys[i];
       if (k != 0ull && k >= thr) sk[atomicAdd(&s_count, 1)] = k;
     }
+    __syncthreads();
   }
-  __syncthreads();
+  // sort descending
   for (int size = 2; size <= P; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       for (int t = tid; t < (P >> 1); t += nthr) {
@@ -265,8 +267,6 @@ __global__ void __launch_bounds__(kSelThreads) nms_scan_kernel(
   unsigned long long* removed = reinterpret_cast<unsigned long long*>(smem_raw);  // [words]
   int* kept = reinterpret_cast<int*>(removed + words);                            // [keep_n]
   int* shuf = kept + keep_n;                                                      // [keep_n]
-  __shared__ unsigned long long s_surv;
-  __shared__ unsigned long long s_diag[64];
   const int img = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
   const unsigned long long* m = mask + (long long)img * K * words;
   const float* sc = top_scores + (long long)img * K;
@@ -275,56 +275,90 @@ __global__ void __launch_bounds__(kSelThreads) nms_scan_kernel(
   for (int i = tid; i < words; i += nthr) removed[i] = 0ull;
   __syncthreads();
   const int out_size = min(keep_n, K);
-  int nk = 0;  // every thread tracks the kept count in a register (no shared read/write race)
+  // Greedy scan, 64 candidates (one word column "cb") per iteration, software-pipelined over the CTA's warps:
+  //   warp 0 (resolver) settles block cb -- the 64 diagonal words live in its registers (prefetched one block ahead),
+  //     the sequential resolution runs on shuffles -- and at once ORs the survivors' words of column cb+1 into
+  //     removed[cb+1], so that the next block can start;
+  //   the other warps (workers) meanwhile OR the rows of block cb-1's survivors into the columns >= cb+1.
+  // One CTA barrier per block.  removed[cb] is complete when block cb is resolved: block cb-1 contributed through the
+  // resolver in the previous iteration, blocks <= cb-2 through the workers of iterations <= cb-1.
+  const int warp_id = tid >> 5, lane_id = tid & 31;
+  const int nworkers = nthr - 32;
+  __shared__ unsigned long long s_surv2[2];
+  int nk = 0;  // every thread tracks the kept count in a register
+  unsigned long long d0 = 0ull, d1 = 0ull;
+  if (warp_id == 0) {
+    d0 = lane_id < K ? m[(long long)lane_id * words] : 0ull;
+    d1 = lane_id + 32 < K ? m[(long long)(lane_id + 32) * words] : 0ull;
+  }
   for (int cb = 0; cb < words && nk < out_size; ++cb) {
-    // stage the 64 diagonal words of this block (one coalesced-ish parallel fetch instead of 64 dependent ones)
-    if (tid < 64) {
-      const int r = cb * 64 + tid;
-      s_diag[tid] = r < K ? m[(long long)r * words + cb] : 0ull;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      // sequential resolution inside the 64-candidate block (registers / shared memory only)
+    if (warp_id == 0) {
+      // prefetch the next block's diagonal words
+      unsigned long long n0 = 0ull, n1 = 0ull;
+      if (cb + 1 < words) {
+        const int r0 = (cb + 1) * 64 + lane_id, r1 = r0 + 32;
+        if (r0 < K) n0 = m[(long long)r0 * words + cb + 1];
+        if (r1 < K) n1 = m[(long long)r1 * words + cb + 1];
+      }
       unsigned long long rem = removed[cb], surv = 0ull;
       int k = nk;
       const int n_in = min(64, K - cb * 64);
       for (int j = 0; j < n_in && k < out_size; ++j) {
+        const unsigned long long dj = __shfl_sync(0xffffffffu, j < 32 ? d0 : d1, j & 31);
         if (!((rem >> j) & 1ull)) {
           surv |= (1ull << j);
-          kept[k++] = cb * 64 + j;
-          rem |= s_diag[j];
+          ++k;
+          rem |= dj;
         }
       }
-      s_surv = surv;
-    }
-    __syncthreads();
-    // OR the survivors' rows into `removed` for all later blocks: (candidate j, word w) pairs spread over the
-    // whole CTA, four independent loads in flight per thread
-    const unsigned long long surv = s_surv;
-    nk += __popcll(surv);
-    const int nw = words - cb - 1;
-    if (surv && nw > 0 && nk < out_size) {
-      const int total = 64 * nw;
-      for (int base = tid; base < total; base += 4 * nthr) {
-        unsigned long long v[4];
-        int ww[4];
+      // survivors' positions in the kept list, and their words of column cb+1
+      unsigned long long next_word = 0ull;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int idx = base + u * nthr;
-          v[u] = 0ull;
-          ww[u] = 0;
-          if (idx < total) {
-            const int j = idx / nw;
-            ww[u] = cb + 1 + (idx - j * nw);
-            if ((surv >> j) & 1ull) v[u] = m[((long long)(cb * 64 + j)) * words + ww[u]];
+      for (int h = 0; h < 2; ++h) {
+        const int j = lane_id + 32 * h;
+        if ((surv >> j) & 1ull) {
+          kept[nk + __popcll(surv & ((1ull << j) - 1ull))] = cb * 64 + j;
+          if (cb + 1 < words) next_word |= m[(long long)(cb * 64 + j) * words + cb + 1];
+        }
+      }
+      const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)(next_word & 0xffffffffull));
+      const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(next_word >> 32));
+      if (lane_id == 0) {
+        s_surv2[cb & 1] = surv;
+        const unsigned long long v = ((unsigned long long)hi << 32) | lo;
+        if (v) atomicOr(&removed[cb + 1], v);
+      }
+      d0 = n0;
+      d1 = n1;
+    } else if (cb >= 1) {
+      const int pb = cb - 1;  // block whose survivors' rows are applied to the columns >= pb + 2
+      const unsigned long long surv = s_surv2[pb & 1];
+      const int nw = words - pb - 2;
+      if (surv && nw > 0) {
+        const int total = 64 * nw;
+        const int wt = tid - 32;
+        for (int base = wt; base < total; base += 4 * nworkers) {
+          unsigned long long v[4];
+          int ww[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int idx = base + u * nworkers;
+            v[u] = 0ull;
+            ww[u] = 0;
+            if (idx < total) {
+              const int j = idx / nw;
+              ww[u] = pb + 2 + (idx - j * nw);
+              if ((surv >> j) & 1ull) v[u] = m[((long long)(pb * 64 + j)) * words + ww[u]];
+            }
           }
-        }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (v[u]) atomicOr(&removed[ww[u]], v[u]);
+          for (int u = 0; u < 4; ++u)
+            if (v[u]) atomicOr(&removed[ww[u]], v[u]);
+        }
       }
     }
     __syncthreads();
+    nk += __popcll(s_surv2[cb & 1]);
   }
   if (nms_keep_idx)
     for (int j = tid; j < keep_n; j += nthr) nms_keep_idx[(long long)img * keep_n + j] = j < nk ? kept[j] : -1;
@@ -573,7 +607,7 @@ extern "C" int xdet_det_postprocess(const float* d_probs, const float* d_boxes, 
                                                                       cand_boxes, total);
   XDET_TRY(after_launch("det_prepare_kernel"));
   const int words = (K + 63) / 64;
-  const int P = next_pow2(K);
+  const int P = R <= 2048 ? next_pow2(R) : next_pow2(K);  // few candidates per class: sort them all (no radix select)
   const size_t smem_topk = (size_t)P * 8;
   if (smem_topk > 200 * 1024) return fail(XDET_EINVAL, "det_postprocess: top_k %d too large for the in-CTA sort", K);
   XDET_TRY(check_cuda(cudaFuncSetAttribute(rpn_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_topk),
@@ -600,4 +634,92 @@ extern "C" int xdet_head_decode(const float* d_rois, const float* d_head_out, in
   head_decode_kernel<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       d_rois, d_head_out, ch_stride, cls_off, num_classes, loc_off, d_probs, d_boxes, M);
   return after_launch("head_decode_kernel");
+}
+
+// ---- TP / FP matching of detections against ground truth (utility/eval_helper.py:671-788) -------------------
+namespace xdet {
+namespace {
+// One warp per (image, class): the detections are visited in order (they are sorted by score), each one is matched
+// to the ground-truth box of its class with the largest Jaccard score (first maximum, as tf.argmax), exactly as
+// bboxes_matching's tf.while_loop does; the lanes share the ground-truth boxes.
+__global__ void __launch_bounds__(32) det_match_kernel(const float* __restrict__ det_boxes,
+                                                       const int* __restrict__ glabels,
+                                                       const float* __restrict__ gbboxes,
+                                                       const int* __restrict__ gdifficult, int num_fg, int Kd, int G,
+                                                       float thr, unsigned char* __restrict__ tp,
+                                                       unsigned char* __restrict__ fp, int* __restrict__ n_gb) {
+  extern __shared__ unsigned char gmatch[];  // [G]
+  const int n = blockIdx.x / num_fg, c1 = blockIdx.x % num_fg, label = c1 + 1;
+  const int lane = threadIdx.x;
+  const int* gl = glabels + (long long)n * G;
+  const int* gd = gdifficult + (long long)n * G;
+  const float4* gb = reinterpret_cast<const float4*>(gbboxes) + (long long)n * G;
+  int cnt = 0;
+  for (int g = lane; g < G; g += 32) {
+    gmatch[g] = 0;
+    cnt += (gl[g] == label && gd[g] == 0) ? 1 : 0;
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (lane == 0) n_gb[blockIdx.x] = cnt;
+  __syncwarp();
+  const float4* db = reinterpret_cast<const float4*>(det_boxes) + (long long)blockIdx.x * Kd;
+  for (int i = 0; i < Kd; ++i) {
+    const float4 r = db[i];
+    const float rarea = __fmul_rn(__fsub_rn(r.z, r.x), __fsub_rn(r.w, r.y));
+    float best = -1.f;  // Jaccard scores are >= 0, so the first candidate always replaces this
+    int best_g = G;
+    for (int g = lane; g < G; g += 32) {
+      const float4 b = gb[g];
+      const float h = fmaxf(__fsub_rn(fminf(b.z, r.z), fmaxf(b.x, r.x)), 0.f);
+      const float w = fmaxf(__fsub_rn(fminf(b.w, r.w), fmaxf(b.y, r.y)), 0.f);
+      const float inter = __fmul_rn(h, w);
+      const float garea = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+      const float uni = __fadd_rn(__fadd_rn(-inter, garea), rarea);
+      float j = uni > 0.f ? __fdiv_rn(inter, uni) : 0.f;
+      j = __fmul_rn(j, gl[g] == label ? 1.f : 0.f);
+      if (j > best) {  // strict: the first maximum wins inside a lane (g ascending)
+        best = j;
+        best_g = g;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {  // across lanes: larger score, ties -> smaller index
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int og = __shfl_xor_sync(0xffffffffu, best_g, o);
+      if (ob > best || (ob == best && og < best_g)) {
+        best = ob;
+        best_g = og;
+      }
+    }
+    bool t = false, f = true;  // no ground truth at all: a false positive
+    if (best_g < G) {
+      const bool match = best > thr;
+      const bool existing = gmatch[best_g] != 0;
+      const bool nd = gd[best_g] == 0;
+      t = nd && match && !existing;
+      f = nd && (existing || !match);
+      __syncwarp();
+      if (lane == 0 && nd && match) gmatch[best_g] = 1;
+      __syncwarp();
+    }
+    if (lane == 0) {
+      tp[(long long)blockIdx.x * Kd + i] = t ? 1 : 0;
+      fp[(long long)blockIdx.x * Kd + i] = f ? 1 : 0;
+    }
+  }
+}
+}  // namespace
+}  // namespace xdet
+
+extern "C" int xdet_det_match(const float* d_det_boxes, const int* d_glabels, const float* d_gbboxes,
+                              const int* d_gdifficult, int N, int num_classes, int Kd, int G,
+                              float matching_threshold, unsigned char* d_tp, unsigned char* d_fp, int* d_n_gbboxes,
+                              void* stream) {
+  if (N <= 0 || num_classes < 2 || Kd <= 0 || G < 0) return fail(XDET_EINVAL, "det_match: bad dimension");
+  if (G > 48 * 1024) return fail(XDET_EINVAL, "det_match: too many ground-truth boxes per image");
+  const int M = N * (num_classes - 1);
+  det_match_kernel<<<M, 32, (size_t)(G > 0 ? G : 1), (cudaStream_t)stream>>>(d_det_boxes, d_glabels, d_gbboxes,
+                                                                           d_gdifficult, num_classes - 1, Kd, G,
+                                                                           matching_threshold, d_tp, d_fp, d_n_gbboxes);
+  return after_launch("det_match_kernel");
 }
