@@ -113,3 +113,46 @@ def test_model_call_with_detections(lh):
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(out2["det_scores"], out["det_scores"]) and torch.equal(out2["det_bboxes"], out["det_bboxes"])
+
+
+def test_tp_fp_matching_matches_oracle(lh):
+    """xdet_det_match (utility.eval_helper.bboxes_matching_batch) vs the loop restatement of bboxes_matching, then the
+    whole detections -> TP/FP -> VOC AP chain on the same inputs."""
+    from oracle import voc_eval as ov
+    from xdet_b200.utility import eval_helper as eh
+    from xdet_b200.utility import metrics as M
+    num_classes = 21
+    n, r = 2, 600
+    probs, boxes, bbox_img, shapes = make_case(n, r, num_classes, seed=11, sharp=4.0)
+    bbox_img[:] = np.array([0, 0, 1, 1], np.float32)
+    rng = np.random.default_rng(12)
+    G = 9
+    glabels = rng.integers(0, num_classes, (n, G)).astype(np.int64)   # 0 = padding
+    gdiff = (rng.random((n, G)) < 0.2).astype(np.int64)
+    # ground truth built from a few of the predicted boxes (so that there are true positives), jittered
+    pick = rng.integers(0, r, (n, G))
+    gboxes = np.clip(np.take_along_axis(boxes, pick[..., None].repeat(4, -1), axis=1) +
+                     rng.normal(0, 0.01, (n, G, 4)).astype(np.float32), 0, 1).astype(np.float32)
+    d_scores, d_boxes = lh.bboxes_eval(shapes, torch.from_numpy(bbox_img).cuda(), torch.from_numpy(probs).cuda(),
+                                       torch.from_numpy(boxes).cuda(), num_classes)
+    ngb, tp, fp = eh.bboxes_matching_batch(d_scores.keys(), d_scores, d_boxes, torch.from_numpy(glabels),
+                                           torch.from_numpy(gboxes), torch.from_numpy(gdiff))
+    torch.cuda.synchronize()
+    n_tp = 0
+    for c in range(1, num_classes):
+        for i in range(n):
+            ref_n, ref_tp, ref_fp = ov.bboxes_matching(c, d_scores[c][i].cpu().numpy(), d_boxes[c][i].cpu().numpy(),
+                                                       glabels[i], gboxes[i], gdiff[i])
+            assert int(ngb[c][i]) == ref_n
+            assert np.array_equal(tp[c][i].cpu().numpy(), ref_tp), (c, i)
+            assert np.array_equal(fp[c][i].cpu().numpy(), ref_fp), (c, i)
+            n_tp += int(ref_tp.sum())
+    assert n_tp > 0
+    state = M.streaming_tp_fp_arrays(ngb, tp, fp, d_scores)
+    m07, aps = M.voc_map(state, use_07_metric=True)
+    m12, _ = M.voc_map(state, use_07_metric=False)
+    assert 0.0 <= m07 <= 1.0 and 0.0 <= m12 <= 1.0 and len(aps) == num_classes - 1
+    # no ground truth at all: every detection is a false positive, none a true positive
+    _, tp0, fp0 = eh.bboxes_matching_batch(d_scores.keys(), d_scores, d_boxes, torch.zeros((n, 0), dtype=torch.int64),
+                                           torch.zeros((n, 0, 4)), torch.zeros((n, 0), dtype=torch.int64))
+    assert not any(bool(tp0[c].any()) for c in tp0) and all(bool(fp0[c].all()) for c in fp0)

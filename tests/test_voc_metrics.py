@@ -1,0 +1,38 @@
+"""CPU: VOC metric arithmetic (x-detector_b200/utility/metrics.py) against hand-computed cases and the independent
+devkit-style AP of oracle/voc_eval.py."""
+import numpy as np
+
+import xdet_b200  # noqa: F401
+from oracle import voc_eval as ov
+from xdet_b200.utility import metrics as M
+
+
+def test_ap_hand_case():
+    # 4 detections sorted by score: TP, FP, TP, FP with 2 objects -> precision 1, .5, .667, .5; recall .5, .5, 1, 1
+    p, r = M.precision_recall(2, 4, [1, 0, 1, 0], [0, 1, 0, 1], [0.9, 0.8, 0.7, 0.6])
+    assert np.allclose(p, [1, 0.5, 2 / 3, 0.5]) and np.allclose(r, [0.5, 0.5, 1, 1])
+    assert abs(M.average_precision_voc12(p, r) - (0.5 * 1 + 0.5 * 2 / 3)) < 1e-12
+    assert abs(M.average_precision_voc07(p, r) - (6 * 1 + 5 * 2 / 3) / 11) < 1e-12
+
+
+def test_ap_matches_devkit_formula():
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        n = int(rng.integers(1, 200))
+        tp = rng.random(n) < 0.4
+        fp = ~tp
+        scores = rng.random(n).astype(np.float32)
+        nobj = int(tp.sum() + rng.integers(0, 20))
+        p, r = M.precision_recall(nobj, n, tp, fp, scores)
+        assert abs(M.average_precision_voc07(p, r) - ov.voc_ap(r, p, True)) < 1e-12
+        assert abs(M.average_precision_voc12(p, r) - ov.voc_ap(r, p, False)) < 1e-12
+
+
+def test_streaming_accumulation_and_filters():
+    st = M.streaming_tp_fp_arrays({1: [2]}, {1: [[1, 0, 0]]}, {1: [[0, 1, 1]]}, {1: [[0.9, 0.5, 0.0]]})
+    st = M.streaming_tp_fp_arrays({1: [1]}, {1: [[0, 0]]}, {1: [[0, 0]]}, {1: [[0.7, 0.6]]}, state=st)
+    nobj, ndet, tp, fp, sc = st[1].value()
+    # the zero-score FP and the two neither-TP-nor-FP ('difficult') detections are dropped
+    assert (nobj, ndet) == (3, 2) and tp.tolist() == [True, False] and fp.tolist() == [False, True]
+    m, aps = M.voc_map(st)
+    assert 0.0 <= m <= 1.0 and list(aps) == [1]
