@@ -183,6 +183,9 @@ int xdet_maxpool3x3s2_add_bf16(const void* d_src, void* d_dst, void* d_dst2, con
  * relu_in != 0 applies the tf.nn.relu that precedes the layer in relu_separable_bn_block (:223) while loading. */
 int xdet_depthwise3x3_bf16(const void* d_src, const float* d_weights, void* d_dst, int N, int H, int W, int C,
                            int dilation, int relu_in, void* stream);
+/* dilation 1 runs the rolling-rows kernel (a thread walks down a strip of rows with the 3-row window in registers);
+ * 0 selects the older one-row-per-thread kernel (A/B timing, tools/dw_one.py). */
+void xdet_set_depthwise_rows(int enabled);
 /* training-mode forward of the same pooling: also writes d_argmax [N,Ho,Wo,C] uint8 (see xdet_maxpool3x3s2_bwd_bf16) */
 int xdet_maxpool3x3s2_argmax_bf16(const void* d_src, void* d_dst, void* d_argmax, int N, int H, int W, int C, int Ho,
                                   int Wo, int pad_top, int pad_left, void* stream);

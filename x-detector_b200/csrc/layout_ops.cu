@@ -287,6 +287,182 @@ __global__ void __launch_bounds__(256, 3) depthwise3x3_kernel(const __nv_bfloat1
   }
 }
 
+// Depthwise 3x3, dilation 1, "rolling rows" form: one thread = 4 channels (8 bytes) of PX adjacent output columns and
+// walks DOWN a strip of YS rows with the 3 x (PX+2) input window in fp32 registers (rotated by renaming), so every
+// input pixel is loaded and widened once per strip (0.06 load instructions per output element; the one-row-per-
+// thread kernel needs 1.9).  What bounds such a kernel is memory-level parallelism: HBM latency x 6.5 TB/s needs
+// ~35 KB in flight per SM.  The next D rows of every thread are therefore streamed by cp.async into a thread-private
+// shared-memory ring (no registers held by loads in flight: D * 32 B * 512 threads = 64 KB per SM outstanding) and
+// picked up with one 8-byte LDS per pixel.  Measured at 32x100x100x728: 1.7 TB/s (no prefetch) -> 2.9 TB/s (two rows
+// ahead in registers) -> see profiles/ for this version.
+// packed fp32 pairs (Blackwell FFMA2: two fp32 FMAs per issued instruction)
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t ffma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+template <int PX, int D>
+__global__ void __launch_bounds__(256, 2) depthwise3x3_rows_kernel(const __nv_bfloat16* __restrict__ src,
+                                                                   const float* __restrict__ w /* [9][C] */,
+                                                                   __nv_bfloat16* __restrict__ dst, int N, int H, int W,
+                                                                   int C, int relu_in, int YS, long long total) {
+  constexpr int WIN = PX + 2;
+  constexpr int RS = D + 1;  // ring slots: D rows in flight + the one being consumed
+  __shared__ uint2 ring[RS * WIN * 256];
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) e = total - 1;  // surplus threads of the last CTA redo its last item (identical values)
+  const int C4 = C / 4;
+  const int WX = (W + PX - 1) / PX;
+  const int HY = (H + YS - 1) / YS;
+  const int c4 = (int)(e % C4);
+  long long t = e / C4;
+  const int xg = (int)(t % WX);
+  t /= WX;
+  const int ys = (int)(t % HY);
+  const int n = (int)(t / HY);
+  const int x0 = xg * PX, y0 = ys * YS, y1 = min(y0 + YS, H);
+  f32x2_t wt[9][2];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(w + (long long)k * C) + c4);
+    wt[k][0] = pack2(v.x, v.y);
+    wt[k][1] = pack2(v.z, v.w);
+  }
+  // Addressing is incremental: column offsets / validity are fixed for the strip, the row pointers advance by one
+  // row pitch per step, the ring slots by one slot pitch (no multiplies, divisions or 64-bit products in the loop).
+  const long long row_pitch = (long long)W * C4;  // uint2 units
+  const uint2* img = reinterpret_cast<const uint2*>(src) + (long long)n * H * row_pitch + c4;
+  int col_off[WIN], col_sz[WIN];
+  bool col_ok[WIN];
+#pragma unroll
+  for (int i = 0; i < WIN; ++i) {
+    const int xi = x0 + i - 1;
+    col_ok[i] = xi >= 0 && xi < W;
+    col_off[i] = (col_ok[i] ? xi : 0) * C4;
+    col_sz[i] = col_ok[i] ? 8 : 0;  // cp.async source size: 0 = zero fill
+  }
+  const uint32_t ring_sa = (uint32_t)__cvta_generic_to_shared(ring) + threadIdx.x * 8u;
+  constexpr uint32_t kSlotBytes = WIN * 256 * 8;
+  const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+  // queue input row yi (pointer `rowp`) into the ring slot at shared address `sa`; zero-filled where the row /
+  // column is outside the image or below the strip's last halo row
+  auto queue_row = [&](int yi, const uint2* rowp, uint32_t sa) {
+    const bool row_ok = yi >= 0 && yi < H && yi <= y1;
+    const uint2* rp = row_ok ? rowp : img;
+    const int rmask = row_ok ? -1 : 0;
+#pragma unroll
+    for (int i = 0; i < WIN; ++i) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa + (uint32_t)(i * 256 * 8)), "l"(rp + col_off[i]),
+                   "r"(col_sz[i] & rmask)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto widen = [&](uint2 v, f32x2_t (&r)[2]) {
+    if (relu_in) {  // on the packed pairs: one instruction per two values
+      const __nv_bfloat162 a = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&v.x), zero2);
+      const __nv_bfloat162 b2 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&v.y), zero2);
+      v.x = *reinterpret_cast<const uint32_t*>(&a);
+      v.y = *reinterpret_cast<const uint32_t*>(&b2);
+    }
+    r[0] = pack2(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u));
+    r[1] = pack2(__uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
+  };
+  auto take_row = [&](uint32_t sa, f32x2_t (&r)[WIN][2]) {  // oldest queued row -> fp32 registers
+    asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");
+#pragma unroll
+    for (int i = 0; i < WIN; ++i) {
+      uint2 v;
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(sa + (uint32_t)(i * 256 * 8)));
+      widen(v, r[i]);
+    }
+  };
+  auto load_row = [&](int yi, f32x2_t (&r)[WIN][2]) {  // direct (the first two rows of the strip)
+    const bool row_ok = yi >= 0 && yi < H;
+    const uint2* rp = img + (long long)(row_ok ? yi : 0) * row_pitch;
+#pragma unroll
+    for (int i = 0; i < WIN; ++i) {
+      const uint2 v = (row_ok && col_ok[i]) ? __ldg(rp + col_off[i]) : make_uint2(0u, 0u);
+      widen(v, r[i]);
+    }
+  };
+  uint2* orow = reinterpret_cast<uint2*>(dst) + ((long long)n * H + y0) * row_pitch + (long long)x0 * C4 + c4;
+  bool out_ok[PX];
+#pragma unroll
+  for (int p = 0; p < PX; ++p) out_ok[p] = x0 + p < W;
+  auto emit = [&](const f32x2_t (&ra)[WIN][2], const f32x2_t (&rb)[WIN][2], const f32x2_t (&rc)[WIN][2]) {
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      f32x2_t a2[2] = {0ull, 0ull};  // (+0, +0)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) a2[h] = ffma2(ra[p + kw][h], wt[kw][h], a2[h]);
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) a2[h] = ffma2(rb[p + kw][h], wt[3 + kw][h], a2[h]);
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) a2[h] = ffma2(rc[p + kw][h], wt[6 + kw][h], a2[h]);
+      if (out_ok[p]) {
+        float acc[4];
+        unpack2(a2[0], acc[0], acc[1]);
+        unpack2(a2[1], acc[2], acc[3]);
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[0], acc[1]), h1 = __floats2bfloat162_rn(acc[2], acc[3]);
+        orow[p * C4] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+      }
+    }
+    orow += row_pitch;
+  };
+  // rows y0+1 .. y0+D go into slots 0 .. D-1; afterwards the slot consumed one step ago is refilled
+  const uint2* qrow = img + (long long)(y0 + 1) * row_pitch;  // pointer of the next row to queue
+  int qy = y0 + 1;
+  uint32_t q_sa = ring_sa;                                      // its slot
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    queue_row(qy, qrow, q_sa);
+    ++qy;
+    qrow += row_pitch;
+    q_sa += kSlotBytes;
+  }
+  // q_sa now points at slot D (= RS-1): the free one
+  uint32_t t_sa = ring_sa;  // slot of the oldest queued row
+  f32x2_t r0[WIN][2], r1[WIN][2], r2[WIN][2];
+  load_row(y0 - 1, r0);
+  load_row(y0, r1);
+  int y = y0;
+  auto step = [&](f32x2_t (&ra)[WIN][2], f32x2_t (&rb)[WIN][2], f32x2_t (&rc)[WIN][2]) {
+    take_row(t_sa, rc);  // row y+1
+    t_sa = (t_sa == ring_sa + (RS - 1) * kSlotBytes) ? ring_sa : t_sa + kSlotBytes;
+    queue_row(qy, qrow, q_sa);
+    ++qy;
+    qrow += row_pitch;
+    q_sa = (q_sa == ring_sa + (RS - 1) * kSlotBytes) ? ring_sa : q_sa + kSlotBytes;
+    emit(ra, rb, rc);
+    ++y;
+  };
+  while (y < y1) {  // three output rows per trip: the fp32 window rotates by renaming, not by moving registers
+    step(r0, r1, r2);
+    if (y >= y1) break;
+    step(r1, r2, r0);
+    if (y >= y1) break;
+    step(r2, r0, r1);
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // NCHW fp32 image -> row-padded NHWC bf16 with the channels zero-padded to `cs` (8): the input layout of the
 // fold_w convolution (conv_gemm.cu) that runs the 7x7/s2 stem.  dst[n][y][pad_left + x][c], zeros elsewhere.
 __global__ void __launch_bounds__(256) image_to_nhwc8_kernel(const float* __restrict__ src,
@@ -420,6 +596,9 @@ extern "C" int xdet_image_to_nhwc8_bf16(const float* d_src, void* d_dst, int N, 
   return after_launch("image_to_nhwc8_kernel");
 }
 
+static int g_dw_rows = 1;
+extern "C" void xdet_set_depthwise_rows(int enabled) { g_dw_rows = enabled ? 1 : 0; }
+
 extern "C" int xdet_depthwise3x3_bf16(const void* d_src, const float* d_weights, void* d_dst, int N, int H, int W, int C,
                                       int dilation, int relu_in, void* stream) {
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0) return fail(XDET_EINVAL, "depthwise3x3: non-positive dimension");
@@ -430,6 +609,16 @@ extern "C" int xdet_depthwise3x3_bf16(const void* d_src, const float* d_weights,
   const unsigned grid = grid_for(total);
   const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(d_src);
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(d_dst);
+  if (dilation == 1 && g_dw_rows) {
+    constexpr int PXR = 2;
+    // strip height: as tall as keeps >= ~4 CTAs per SM in flight
+    int YS = 16;
+    while (YS > 4 && (long long)N * ((H + YS - 1) / YS) * ((W + PXR - 1) / PXR) * (C / 4) < 4ll * kNumSMs * 256) YS /= 2;
+    const long long tot = (long long)N * ((H + YS - 1) / YS) * ((W + PXR - 1) / PXR) * (C / 4);
+    depthwise3x3_rows_kernel<PXR, 4><<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        src, d_weights, dst, N, H, W, C, relu_in, YS, tot);
+    return after_launch("depthwise3x3_rows_kernel");
+  }
   if (dilation == 1)
     depthwise3x3_kernel<PX, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(src, d_weights, dst, N, H, W, C, relu_in, total);
   else
