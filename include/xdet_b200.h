@@ -252,6 +252,16 @@ int xdet_maxpool3x3s2_f32(const float* d_src, float* d_dst, float* d_dst2, const
 int xdet_depthwise3x3_f32(const float* d_src, const float* d_weights, float* d_dst, int N, int H, int W, int C,
                           int dilation, int relu_in, void* stream);
 
+/* Input pipeline of the eval / test scripts.
+ * Replaces: light_head_preprocess_for_eval / _for_test preprocessing/common_preprocessing.py:383-458 with
+ *   resize = WARP_RESIZE (the scripts' default): convert_image_dtype(uint8 -> float32) * 2, tf_image_whitened
+ *   (:136-152) with the means / 127.5 of :36-38, tf.image.resize_images(BILINEAR, align_corners=False)
+ *   (preprocessing/tf_image.py:307-319), transpose to NCHW.
+ *   d_image [H,W,3] uint8 (RGB) -> d_out [3,Ho,Wo] fp32 (one image of the NCHW batch); h_means3 = host pointer to the
+ *   three per-channel means already divided by 127.5.  fp32 arithmetic with one rounding per operation. */
+int xdet_preprocess_eval_u8(const unsigned char* d_image, int H, int W, int Ho, int Wo, const float* h_means3,
+                            float* d_out, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * RPN proposals.
  * xdet_rpn_decode  Replaces: score/loc reshaping + softmax light_head_rfcn_eval.py:389-397 (train :295-305) and

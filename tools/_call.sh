@@ -1,4 +1,1 @@
-mkdir -p gpurun_out/final
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/final/bench_net_2gpu.json 2> gpurun_out/final/bench_net_2gpu.err; tail -2 gpurun_out/final/bench_net_2gpu.err; cut -c1-260 gpurun_out/final/bench_net_2gpu.json
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 --workload lighthead_resnet50_train > gpurun_out/final/bench_train_2gpu.json 2> gpurun_out/final/bench_train_2gpu.err; tail -2 gpurun_out/final/bench_train_2gpu.err; cut -c1-260 gpurun_out/final/bench_train_2gpu.json
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --impl reference --steps 1 --warmup 0 2>/dev/null | cut -c1-200
+timeout 600 python -m pytest tests/test_preprocess_gpu.py -q -m gpu 2>&1 | tail -5

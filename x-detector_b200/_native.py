@@ -70,6 +70,8 @@ def _declare(lib):
     lib.xdet_det_postprocess.argtypes = ([c_void_p] * 4 + [c_int] * 3 + [c_float, c_int, c_int, c_float] +
                                          [c_void_p] * 3 + [c_size_t, c_void_p])
     lib.xdet_set_depthwise_rows.argtypes = [c_int]
+    lib.xdet_preprocess_eval_u8.argtypes = [c_void_p, c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_float * 3),
+                                            c_void_p, c_void_p]
     lib.xdet_det_match.argtypes = [c_void_p] * 4 + [c_int] * 4 + [c_float] + [c_void_p] * 4
     lib.xdet_split3_bf16.argtypes = [c_void_p] + [c_ll] * 4 + [c_int] * 4 + [c_void_p, c_int, c_void_p]
     lib.xdet_f32_post.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_int,

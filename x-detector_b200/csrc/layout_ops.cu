@@ -625,3 +625,52 @@ extern "C" int xdet_depthwise3x3_bf16(const void* d_src, const float* d_weights,
     depthwise3x3_kernel<PX, 2><<<grid, 256, 0, (cudaStream_t)stream>>>(src, d_weights, dst, N, H, W, C, relu_in, total);
   return after_launch("depthwise3x3_kernel");
 }
+
+// ---- input pipeline: light_head_preprocess_for_eval / _for_test (preprocessing/common_preprocessing.py:383-458) ------
+// uint8 HWC image -> whitened fp32, bilinear WARP_RESIZE to the network input, written as one NCHW plane set:
+//   tf.image.convert_image_dtype(uint8 -> float32) = cast * (1/255)   (:391)
+//   * 2.                                                             (:391)
+//   - [R,G,B mean / 127.5]                                           (tf_image_whitened, :136-152, :392)
+//   tf.image.resize_images(BILINEAR, align_corners=False)            (:428-431): TF r1.6 ResizeBilinear (legacy
+//     sampling, no half-pixel centres): in = out_index * (in_size / out_size), lower = (int)in,
+//     upper = min(lower + 1, in_size - 1), lerp = in - lower;  top = tl + (tr - tl) * xl, bottom likewise,
+//     value = top + (bottom - top) * yl -- all in fp32, one rounding per operation.
+namespace xdet {
+namespace {
+__global__ void __launch_bounds__(256) preprocess_eval_kernel(const unsigned char* __restrict__ img, int H, int W,
+                                                              int Ho, int Wo, float sy, float sx, float m0, float m1,
+                                                              float m2, float* __restrict__ out /* [3,Ho,Wo] */) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= Ho * Wo) return;
+  const int x = e % Wo, y = e / Wo;
+  const float in_y = __fmul_rn((float)y, sy), in_x = __fmul_rn((float)x, sx);
+  const int y0 = (int)in_y, x0 = (int)in_x;
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float yl = __fsub_rn(in_y, (float)y0), xl = __fsub_rn(in_x, (float)x0);
+  const float mean[3] = {m0, m1, m2};
+  const float k255 = 1.0f / 255.0f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    auto px = [&](int yy, int xx) {
+      const float v = (float)img[((long long)yy * W + xx) * 3 + c];
+      return __fsub_rn(__fmul_rn(__fmul_rn(v, k255), 2.0f), mean[c]);
+    };
+    const float tl = px(y0, x0), tr = px(y0, x1), bl = px(y1, x0), br = px(y1, x1);
+    const float top = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), xl));
+    const float bot = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), xl));
+    out[((long long)c * Ho + y) * Wo + x] = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), yl));
+  }
+}
+}  // namespace
+}  // namespace xdet
+
+extern "C" int xdet_preprocess_eval_u8(const unsigned char* d_image, int H, int W, int Ho, int Wo, const float* h_means3,
+                                       float* d_out, void* stream) {
+  if (H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0) return fail(XDET_EINVAL, "preprocess_eval: non-positive size");
+  if (!h_means3) return fail(XDET_EINVAL, "preprocess_eval: means missing");
+  const float sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;  // CalculateResizeScale, align_corners = false
+  const int total = Ho * Wo;
+  preprocess_eval_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_image, H, W, Ho, Wo, sy, sx, h_means3[0],
+                                                                               h_means3[1], h_means3[2], d_out);
+  return after_launch("preprocess_eval_kernel");
+}
