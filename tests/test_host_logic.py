@@ -1,0 +1,73 @@
+"""CPU: host-side logic that needs no GPU -- the fp32x3 operand split / weight packing (ops/conv.py), the
+post-processing constants (light_head_rfcn_eval.det_min_size) and the oracle chain they are checked against."""
+import numpy as np
+import torch
+
+import xdet_b200  # noqa: F401
+from oracle import detections as od
+from xdet_b200.ops import conv as conv_ops
+
+
+def test_split3_values_is_exact_to_fp32():
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn((64, 37), generator=g) * 5
+    hi, mid, lo = conv_ops.split3_values(w)
+    for part in (hi, mid, lo):  # every piece is representable in bf16
+        assert torch.equal(part, part.to(torch.bfloat16).float())
+    err = (hi.double() + mid.double() + lo.double() - w.double()).abs()
+    assert bool((err <= w.double().abs() * 2.0 ** -23).all())
+
+
+def test_fp32x3_packing_pairs_the_six_significant_products():
+    """Emulate one output of the split-operand convolution on the CPU: activation blocks [mid|lo|hi|mid|hi|hi] against
+    the packed weight blocks must equal x.w to fp32 level (dropped products are < 2^-24 of the result)."""
+    g = torch.Generator().manual_seed(1)
+    cin, cout = 40, 8
+    x = torch.randn((cin,), generator=g)
+    w = torch.randn((cout, cin, 1, 1), generator=g)
+    with conv_ops.precision("fp32x3"):
+        wp = conv_ops.pack_conv_weight(w)            # [cout, pad64(6*cin)] bf16
+    assert wp.shape == (cout, 256) and wp.dtype == torch.bfloat16
+    hi, mid, lo = conv_ops.split3_values(x)
+    xs = torch.cat([mid, lo, hi, mid, hi, hi]).double()          # what xdet_split3_bf16 writes
+    got = wp[:, :6 * cin].double() @ xs
+    ref = w.reshape(cout, cin).double() @ x.double()
+    assert float((got - ref).abs().max()) < 1e-6 * float(ref.abs().max() + 1)
+    assert not wp[:, 6 * cin:].float().any()                     # zero padding up to the 64-channel chunk
+    # default precision: plain bf16 pack, one block
+    assert conv_ops.pack_conv_weight(w).shape == (cout, 64)
+
+
+def test_weight_chunk_selects_the_same_channels_in_all_six_blocks():
+    g = torch.Generator().manual_seed(2)
+    cin, cout, taps = 24, 4, 3
+    w = torch.randn((cout, cin, 1, taps), generator=g)
+    with conv_ops.precision("fp32x3"):
+        wp = conv_ops.pack_conv_weight(w)
+        full = wp.view(cout, taps, -1)[:, :, :6 * cin].float().view(cout, taps, 6, cin)
+        chunk = conv_ops._weight_chunk(wp, cout, taps, cin, 8, 16)
+    cv = chunk.view(cout, taps, -1)
+    assert cv.shape[2] == 64
+    assert torch.equal(cv[:, :, :48].float().view(cout, taps, 6, 8), full[:, :, :, 8:16])
+
+
+def test_det_min_size_follows_eval_helper():
+    from xdet_b200 import light_head_rfcn_eval as lh
+    shapes = [(375, 500), (480, 480), (1, 1), (1200, 1600)]
+    ms = lh.det_min_size(shapes, 480, "cpu").numpy()
+    for s, m in zip(shapes, ms):
+        assert m == od.min_size_of(0.03, s, (480, 480))
+    assert ms[2] == np.float32(0.0001)  # the floor of utility/eval_helper.py:295
+
+
+def test_oracle_detection_chain_small_case():
+    """Hand-checkable case: two overlapping boxes of one class (the weaker one is suppressed at IoU 0.3), one box of
+    another class, one below the score threshold."""
+    probs = np.zeros((4, 3), np.float32)
+    probs[:, 0] = 1.0
+    probs[0, 1], probs[1, 1], probs[2, 2], probs[3, 1] = 0.9, 0.8, 0.7, 0.005
+    boxes = np.array([[0.1, 0.1, 0.5, 0.5], [0.12, 0.1, 0.5, 0.52], [0.6, 0.6, 0.9, 0.9], [0.2, 0.2, 0.4, 0.4]], np.float32)
+    s, b = od.bboxes_eval_select(probs, boxes, np.array([0, 0, 1, 1], np.float32), (480, 480), 3)
+    assert s[1][0] == np.float32(0.9) and not s[1][1:].any() and s[1].shape == (200,)
+    assert np.array_equal(b[1][0], boxes[0]) and not b[1][1:].any()
+    assert s[2][0] == np.float32(0.7) and np.array_equal(b[2][0], boxes[2])
