@@ -13,6 +13,10 @@ from xdet_b200 import ops  # noqa: E402
 N, C, R = 8, 490, 1000
 x = torch.from_numpy(workloads.make_map(N, C, 30, 30, seed=4)).cuda()
 rois = torch.from_numpy(workloads.make_rois(N, R, seed=5)).cuda()
+import sys as _sys
+if "--relu" in _sys.argv:  # the model's thin feature map is post-ReLU: ~half of it exact zeros
+    x = torch.relu(x)
+    print("post-ReLU map")
 for variant in ("planes", "select", "gather"):
     for _ in range(3):
         ops.ps_roi_align(x, rois, 7, 7, "max", variant=variant)

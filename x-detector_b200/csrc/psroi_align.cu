@@ -16,6 +16,7 @@
 #include <cfloat>
 #include <climits>
 #include <cstdint>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -487,8 +488,10 @@ __global__ void __launch_bounds__(kPlanesThreads, 2) psroi_fwd_planes_kernel(
 //       alpha = 8 * 2^-24 * (1+2^-22)  (fp32 weights: 2 roundings; column blend 2, sample blend 2; the
 //       reference itself rounds fx*fy*P11 and the sum to fp32; all magnitudes <= sum|w*p| <= (1+2^-22) cm),
 //       beta = 63 * 2^-23 (the overwritten bits), plus 2^-140 for fp32 underflow.
-//       The lane keeps the largest key K_b and dmin, the smallest distance of any key to the running
-//       maximum before it; dmin > T implies K_b - K_s > T for every other sample s.
+//       The lane keeps the largest key K_b and either the smallest distance of any key to the running maximum
+//       before it (dense planes) or the second-largest key (planes with many exact zeros); a distance / gap > T
+//       implies K_b - K_s > T for every other sample s.  Bins whose samples all approximate to +0 on a plane
+//       without negative or tiny values are exactly +0 everywhere: the first sample wins, no fp64 needed.
 //   decision: with T = 2^-19 cm + 1.375 * 2^-16 |K_b| + 2^-119  (>= (2 alpha cm + 2 beta |K_b|)/(1 - beta),
 //       using |K_s| <= |K_b| + (K_b - K_s)),  K_b - K_s > T gives V_b > V_s: the reference's arg-max is
 //       sample b for certain, so
@@ -567,34 +570,57 @@ __global__ void __launch_bounds__(kPlanesThreads, 2) psroi_fwd_select_kernel(
   float* planes = reinterpret_cast<float*>(smem_raw);
   // per-channel max |value| of the slice (bit pattern of a non-negative float; NaN/Inf order above finite)
   unsigned* chan_max = reinterpret_cast<unsigned*>(planes + (size_t)HW * pitch);
-
-  for (int i = threadIdx.x; i < cs; i += kPlanesThreads) chan_max[i] = 0u;
+  // per-channel flag: the plane holds a negative value (sign bit, -0 included) or a non-zero magnitude below 2^-60.
+  // A channel without the flag is "clean": every fp32 sample approximation is >= 0 and is zero iff the reference's
+  // value is exactly +0 (no product can underflow), which settles all-zero bins without the exact loop.
+  unsigned* chan_flag = chan_max + pitch;
+  __shared__ int s_zeros;  // exact zeros in the slice: picks the near-tie test of pass 1 (see below)
+  if (threadIdx.x == 0) s_zeros = 0;
+  for (int i = threadIdx.x; i < cs; i += kPlanesThreads) {
+    chan_max[i] = 0u;
+    chan_flag[i] = 0u;
+  }
   __syncthreads();
+  int zeros_seen = 0;
   {  // stage the slice channel-minor [HW][pitch] and reduce max|.| per channel
     const float* src = inputs + ((long long)img * C + c0) * HW;
     const int n = cs * HW;
     for (int i0 = warp * 32; i0 < n; i0 += kPlanesThreads) {
       const int i = i0 + lane;
-      unsigned mag = 0u;
+      unsigned mag = 0u, flag = 0u;
       int ch = -1;
       if (i < n) {
         ch = i / HW;
         const int p = i - ch * HW;
         const float v = __ldg(src + i);
         planes[p * pitch + ch] = v;
-        mag = __float_as_uint(v) & 0x7fffffffu;
+        const unsigned b = __float_as_uint(v);
+        mag = b & 0x7fffffffu;
+        flag = ((b >> 31) != 0u || (mag != 0u && mag < 0x21800000u)) ? 1u : 0u;  // negative, or 0 < |v| < 2^-60
       }
+      zeros_seen += __popc(__ballot_sync(0xffffffffu, i < n && mag == 0u));
       const int ch_first = i0 / HW;
       const int ch_last = min(i0 + 31, n - 1) / HW;
       if (ch_first == ch_last) {
         const unsigned m = __reduce_max_sync(0xffffffffu, mag);
-        if (lane == 0 && m > chan_max[ch_first]) atomicMax(&chan_max[ch_first], m);
+        const unsigned f = __reduce_or_sync(0xffffffffu, flag);
+        if (lane == 0) {
+          if (m > chan_max[ch_first]) atomicMax(&chan_max[ch_first], m);
+          if (f) chan_flag[ch_first] = 1u;
+        }
       } else if (ch >= 0) {
         atomicMax(&chan_max[ch], mag);
+        if (flag) chan_flag[ch] = 1u;
       }
     }
+    if (lane == 0 && zeros_seen) atomicAdd(&s_zeros, zeros_seen);
   }
   __syncthreads();
+  // Near-tie test of pass 1.  Dense planes: the smallest distance of any key to the running maximum before it
+  // (one FMA-pipe + one ALU instruction per sample and channel; conservative: a tie between two samples that both
+  // lose also triggers the exact loop).  Planes with many exact zeros (post-ReLU maps) would trip that all the time
+  // -- zeros tie with zeros -- so they track the true second-largest key instead (two ALU instructions).
+  const bool dense = (long long)s_zeros * 16 < (long long)cs * HW;
 
   // After staging the warps are independent: a warp takes rounds of `ppw` (RoI, bin) pairs; lane -> (pair slot,
   // group of VEC channels) is fixed.  Each lane derives its pair's sample coordinates itself (a few fp32 ops per
@@ -629,6 +655,10 @@ __global__ void __launch_bounds__(kPlanesThreads, 2) psroi_fwd_select_kernel(
     return p;
   };
 
+  // The round loop is instantiated twice (DENSE known at compile time) so that each near-tie test gets its own
+  // optimised inner loop; the choice is uniform over the CTA.
+  auto run = [&](auto dense_tag) {
+  constexpr bool DENSE = decltype(dense_tag)::value;
   int round = blockIdx.y * kWarps + warp;
   PairSel cur = fetch(round);
   while (round < nrounds) {
@@ -664,17 +694,23 @@ __global__ void __launch_bounds__(kPlanesThreads, 2) psroi_fwd_select_kernel(
           // ---- pass 1: fp32 approximations (separable form) ------------------------------------------------
           // Per sample row a column's two taps are blended once (cv = ay*P[iy] + fy*P[iy1]) and shared by the
           // samples left and right of it; a sample is ax*cv[ix] + fx*cv[ix+1].  The sample id rides in the 6 low
-          // mantissa bits of the value ("key"): one FMNMX tracks the maximum and its position; dmin is the
-          // smallest distance of any key to the running maximum before it: if dmin > 2e' no other sample comes
-          // within 2e' of the final maximum.
-          float dmin[VEC];
+          // mantissa bits of the value ("key"): one FMNMX tracks the maximum and its position; aux tracks the
+          // near-tie evidence (see `dense` above).
+          float aux[VEC];  // DENSE: smallest distance to the running maximum; else: second-largest key
 #pragma unroll
           for (int k = 0; k < VEC; ++k) {
             m1[k] = -FLT_MAX;
-            dmin[k] = FLT_MAX;
+            aux[k] = DENSE ? FLT_MAX : -FLT_MAX;
+          }
+          // a bin with a single sample has nothing to select: its key is sample 0 with an unbeatable margin
+          // (small RoIs -- one sample per bin -- are the bulk of a detector's proposals)
+          const bool single = g.nh == 1 && g.nw == 1;
+          if (single) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) m1[k] = 0.f;  // id bits 0 -> sample (0, 0); aux keeps its 'no rival' value
           }
           float fhi = 0.f;
-          for (int hi = 0; hi < g.nh; ++hi, fhi += 1.0f) {
+          for (int hi = 0; hi < (single ? 0 : g.nh); ++hi, fhi += 1.0f) {
             const float y = __fadd_rn(__fadd_rn(y0, __fmul_rn(g.step_h, fhi)), hsh);
             const int eyi = __float2int_rz(y);
             const float fy = __fsub_rn(y, (float)eyi);
@@ -712,12 +748,22 @@ __global__ void __launch_bounds__(kPlanesThreads, 2) psroi_fwd_select_kernel(
                 cur_ix = exi;
               }
               const float ax = 1.0f - fx;
+              if (DENSE) {
 #pragma unroll
-              for (int k = 0; k < VEC; ++k) {
-                const float a = __fmaf_rn(fx, cr[k], ax * cl[k]);
-                const float key = __uint_as_float((__float_as_uint(a) & 0xffffffc0u) | sid);
-                dmin[k] = fminf(dmin[k], fabsf(key - m1[k]));
-                m1[k] = fmaxf(m1[k], key);
+                for (int k = 0; k < VEC; ++k) {
+                  const float a = __fmaf_rn(fx, cr[k], ax * cl[k]);
+                  const float key = __uint_as_float((__float_as_uint(a) & 0xffffffc0u) | sid);
+                  aux[k] = fminf(aux[k], fabsf(key - m1[k]));
+                  m1[k] = fmaxf(m1[k], key);
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                  const float a = __fmaf_rn(fx, cr[k], ax * cl[k]);
+                  const float key = __uint_as_float((__float_as_uint(a) & 0xffffffc0u) | sid);
+                  aux[k] = fmaxf(aux[k], fminf(key, m1[k]));
+                  m1[k] = fmaxf(m1[k], key);
+                }
               }
             }
           }
@@ -727,7 +773,12 @@ __global__ void __launch_bounds__(kPlanesThreads, 2) psroi_fwd_select_kernel(
             const unsigned cmb = chan_max[ch0 + k];
             // T = 2*alpha*cm + 2*beta*|K_best| with margin (see the kernel header): 2^-19 cm + 1.375 * 2^-16 |m1|
             const float e2 = __fmaf_rn(fabsf(m1[k]), 0x1.6p-16f, __fmaf_rn(__uint_as_float(cmb), 0x1p-19f, 0x1p-119f));
-            const bool sure = (dmin[k] > e2) && (cmb < 0x7f800000u);  // NaN / Inf planes: never
+            bool sure = ((DENSE ? aux[k] : m1[k] - aux[k]) > e2) && (cmb < 0x7f800000u);  // NaN / Inf planes: never
+            // all samples approximate to +0 on a clean plane: every reference value is exactly +0 and the first
+            // sample wins (thin feature maps are post-ReLU: whole bins of zeros are common)
+            const bool zero_all = !sure && (__float_as_uint(m1[k]) & 0xffffffc0u) == 0u && chan_flag[ch0 + k] == 0u &&
+                                  g.step_h >= 0x1p-20f && g.step_w >= 0x1p-20f && (cmb < 0x7f800000u);
+            sure = sure || zero_all;
             all_sure = all_sure && sure;
             const unsigned sidk = __float_as_uint(m1[k]) & 63u;
             const unsigned hi = sidk >> 3, wi = sidk & 7u;
@@ -753,8 +804,8 @@ __global__ void __launch_bounds__(kPlanesThreads, 2) psroi_fwd_select_kernel(
             sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(ax, dfy), (double)q01));
             sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(dfx, ay), (double)q10));
             sum = __dadd_rn(sum, (double)__fmul_rn(__fmul_rn(fx, fy), q11));
-            acc[k] = __double2float_rn(sum);
-            arg[k] = g.nw * (int)hi + (int)wi;
+            acc[k] = zero_all ? 0.f : __double2float_rn(sum);
+            arg[k] = zero_all ? 0 : g.nw * (int)hi + (int)wi;
             if (!sure) m1[k] = __int_as_float(0x7fc00000);  // mark for the exact loop below
           }
         }
@@ -771,6 +822,11 @@ __global__ void __launch_bounds__(kPlanesThreads, 2) psroi_fwd_select_kernel(
     cur = nxt;
     round += round_stride;
   }
+  };
+  if (dense)
+    run(std::true_type{});
+  else
+    run(std::false_type{});
 }
 
 // ------------------------------------------------------------------------------------------
@@ -896,7 +952,7 @@ int planes_bins_per_cta(int bank, int H, int W, int G, int* pitch_out, size_t* s
   for (int bins = 1; bins <= G; ++bins) {
     int pitch = (bins * bank + vec - 1) / vec * vec;
     if ((pitch / vec) % 2 == 0) pitch += vec;  // odd number of vector slots per pixel: spreads banks
-    const size_t need = (size_t)HW * pitch * sizeof(float) + (size_t)pitch * sizeof(unsigned) + fixed;
+    const size_t need = (size_t)HW * pitch * sizeof(float) + 2 * (size_t)pitch * sizeof(unsigned) + fixed;
     if (need > kMaxSmem) break;
     if (bins > 1 && (need > target || (bins - 1) * bank >= 32)) break;
     best = bins;
@@ -904,7 +960,7 @@ int planes_bins_per_cta(int bank, int H, int W, int G, int* pitch_out, size_t* s
   }
   if (best == 0) return 0;
   *pitch_out = best_pitch;
-  *smem_out = (size_t)HW * best_pitch * sizeof(float) + (size_t)best_pitch * sizeof(unsigned) + fixed;
+  *smem_out = (size_t)HW * best_pitch * sizeof(float) + 2 * (size_t)best_pitch * sizeof(unsigned) + fixed;
   return best;
 }
 
@@ -966,11 +1022,10 @@ int launch_fwd(const float* in, const float* rois, float* pooled, int32_t* index
   if (variant == XDET_PSROI_AUTO)
     // measured on B200 (profiles/psroi_sweep_r1.md): the staged variant wins once there are a few million
     // outputs and the bank allows vector channel groups; tiny banks (15x15 bins) stay on the gather kernel
-    // SELECT amortises its per-sample bookkeeping over the channels of a lane: it wins with 4-channel groups
-    // (bank % 4 == 0, >= 16); with 2-channel groups (the model's bank of 10) only from ~6 M outputs on
-    // (profiles/psroi_sweep_r1.md)
+    // max pooling: SELECT (with its single-sample and all-zero fast paths) for every shape the staged kernels
+    // take; mean pooling needs every sample exactly: PLANES
     variant = (bins > 0 && planes_vec(bank) >= 2 && total >= (3ll << 19))
-                  ? ((kMax && (planes_vec(bank) == 4 || total >= (6ll << 20))) ? XDET_PSROI_SELECT : XDET_PSROI_PLANES)
+                  ? (kMax ? XDET_PSROI_SELECT : XDET_PSROI_PLANES)
                   : XDET_PSROI_GATHER;
 
   if (variant == XDET_PSROI_PLANES || variant == XDET_PSROI_SELECT) {
