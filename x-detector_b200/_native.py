@@ -7,7 +7,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libxdet_b200.so")
+# XDET_B200_LIB: load another build of the same library (A/B experiments of tools/); default = the in-tree build
+LIB_PATH = os.environ.get("XDET_B200_LIB") or os.path.join(CSRC, "libxdet_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
 NVCC_FLAGS = [

@@ -598,7 +598,9 @@ __global__ void __launch_bounds__(kPlanesThreads, 2) psroi_fwd_select_kernel(
         mag = b & 0x7fffffffu;
         flag = ((b >> 31) != 0u || (mag != 0u && mag < 0x21800000u)) ? 1u : 0u;  // negative, or 0 < |v| < 2^-60
       }
+#ifndef XDET_SEL_NOSTATS
       zeros_seen += __popc(__ballot_sync(0xffffffffu, i < n && mag == 0u));
+#endif
       const int ch_first = i0 / HW;
       const int ch_last = min(i0 + 31, n - 1) / HW;
       if (ch_first == ch_last) {
@@ -685,7 +687,7 @@ __global__ void __launch_bounds__(kPlanesThreads, 2) psroi_fwd_select_kernel(
         const bool fast = g.nh <= 8 && g.nw <= 8 && g.step_h >= 4.0f * FLT_MIN && g.step_w >= 4.0f * FLT_MIN &&
                           x0 >= 0.f && y0 >= 0.f && x0 < 2097152.f && y0 < 2097152.f && g.step_w < 65536.f &&
                           g.step_h < 65536.f;
-        bool all_sure = fast;
+        unsigned unsure = 0u;  // bit k: channel k's selection is not provable
         float m1[VEC];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) m1[k] = -FLT_MAX;
@@ -773,13 +775,8 @@ __global__ void __launch_bounds__(kPlanesThreads, 2) psroi_fwd_select_kernel(
             const unsigned cmb = chan_max[ch0 + k];
             // T = 2*alpha*cm + 2*beta*|K_best| with margin (see the kernel header): 2^-19 cm + 1.375 * 2^-16 |m1|
             const float e2 = __fmaf_rn(fabsf(m1[k]), 0x1.6p-16f, __fmaf_rn(__uint_as_float(cmb), 0x1p-19f, 0x1p-119f));
-            bool sure = ((DENSE ? aux[k] : m1[k] - aux[k]) > e2) && (cmb < 0x7f800000u);  // NaN / Inf planes: never
-            // all samples approximate to +0 on a clean plane: every reference value is exactly +0 and the first
-            // sample wins (thin feature maps are post-ReLU: whole bins of zeros are common)
-            const bool zero_all = !sure && (__float_as_uint(m1[k]) & 0xffffffc0u) == 0u && chan_flag[ch0 + k] == 0u &&
-                                  g.step_h >= 0x1p-20f && g.step_w >= 0x1p-20f && (cmb < 0x7f800000u);
-            sure = sure || zero_all;
-            all_sure = all_sure && sure;
+            const bool sure = ((DENSE ? aux[k] : m1[k] - aux[k]) > e2) && (cmb < 0x7f800000u);  // NaN / Inf: never
+            if (!sure) unsure |= 1u << k;
             const unsigned sidk = __float_as_uint(m1[k]) & 63u;
             const unsigned hi = sidk >> 3, wi = sidk & 7u;
             // (float)hi, (float)wi for values < 8 without the conversion pipe
@@ -804,15 +801,29 @@ __global__ void __launch_bounds__(kPlanesThreads, 2) psroi_fwd_select_kernel(
             sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(ax, dfy), (double)q01));
             sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(dfx, ay), (double)q10));
             sum = __dadd_rn(sum, (double)__fmul_rn(__fmul_rn(fx, fy), q11));
-            acc[k] = zero_all ? 0.f : __double2float_rn(sum);
-            arg[k] = zero_all ? 0 : g.nw * (int)hi + (int)wi;
-            if (!sure) m1[k] = __int_as_float(0x7fc00000);  // mark for the exact loop below
+            acc[k] = __double2float_rn(sum);
+            arg[k] = g.nw * (int)hi + (int)wi;
           }
         }
-        if (!all_sure) {  // rare: provable selection failed for some channel of this lane (or no fast path)
+        if (!fast || unsure) {  // provable selection failed for some channel of this lane (or no fast path)
+          const bool steps_ok = g.step_h >= 0x1p-20f && g.step_w >= 0x1p-20f;
 #pragma unroll
-          for (int k = 0; k < VEC; ++k)
-            if (!fast || m1[k] != m1[k]) pool_one<true>(pbase + k, row_pitch, pitch, g, x0, y0, H, W, acc[k], arg[k]);
+          for (int k = 0; k < VEC; ++k) {
+            if (!fast) {
+              pool_one<true>(pbase + k, row_pitch, pitch, g, x0, y0, H, W, acc[k], arg[k]);
+            } else if ((unsure >> k) & 1u) {
+              // All samples approximate to +0 on a clean plane (no negative / tiny values, chan_flag): every
+              // reference value is exactly +0 and the first sample wins -- thin feature maps are post-ReLU, whole
+              // bins of zeros are common.  Anything else that is not provable takes the exact loop.
+              if ((__float_as_uint(m1[k]) & 0xffffffc0u) == 0u && chan_flag[ch0 + k] == 0u && steps_ok &&
+                  chan_max[ch0 + k] < 0x7f800000u) {
+                acc[k] = 0.f;
+                arg[k] = 0;
+              } else {
+                pool_one<true>(pbase + k, row_pitch, pitch, g, x0, y0, H, W, acc[k], arg[k]);
+              }
+            }
+          }
         }
       }
       const long long o = ((long long)img * R + cur.r) * C + c0 + ch0;
@@ -823,10 +834,15 @@ __global__ void __launch_bounds__(kPlanesThreads, 2) psroi_fwd_select_kernel(
     round += round_stride;
   }
   };
+#ifdef XDET_SEL_FORCE_DENSE
+  (void)dense;
+  run(std::true_type{});
+#else
   if (dense)
     run(std::true_type{});
   else
     run(std::false_type{});
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
