@@ -292,6 +292,11 @@ int xdet_rpn_select(const float* d_scores, const float* d_boxes, int N, int A_to
  * 4 box deltas (cy,cx,h,w) at loc_off..  ->  d_probs [M,num_classes], d_boxes [M,4]. */
 int xdet_head_decode(const float* d_rois, const float* d_head_out, int ch_stride, int cls_off, int num_classes,
                      int loc_off, long long M, float* d_probs, float* d_boxes, void* stream);
+/* same, plus the 'classes' / 'probabilities' entries of the predictions dict (tf.argmax / tf.reduce_max over the class
+ * axis, light_head_rfcn_eval.py:413-416): d_classes [M] int64 and d_best_prob [M] fp32, either may be NULL. */
+int xdet_head_decode_ex(const float* d_rois, const float* d_head_out, int ch_stride, int cls_off, int num_classes,
+                        int loc_off, long long M, float* d_probs, float* d_boxes, long long* d_classes,
+                        float* d_best_prob, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Training-step kernels (csrc/train_ops.cu).  Replace the TF ops/gradients of the training graph

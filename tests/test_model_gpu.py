@@ -92,6 +92,9 @@ def test_predictions_are_well_formed(setup):
     assert out["bboxes_predict"].shape == (200, 4) and out["head_cls_score"].shape == (200, 21)
     assert torch.isfinite(out["bboxes_predict"]).all() and torch.isfinite(out["head_cls_score"]).all()
     assert torch.allclose(out["head_cls_score"].sum(-1), torch.ones(200, device="cuda"), atol=1e-4)
+    # 'classes' / 'probabilities' of the predictions dict (tf.argmax / tf.reduce_max, light_head_rfcn_eval.py:413-416)
+    assert out["classes"].dtype == torch.int64 and torch.equal(out["probabilities"], out["head_cls_score"].max(-1).values)
+    assert torch.equal(out["head_cls_score"].gather(1, out["classes"][:, None])[:, 0], out["probabilities"])
 
 
 # ---- Xception backbone (the reference's own XceptionBody) -----------------------------------------------------

@@ -81,6 +81,7 @@ def _declare(lib):
     lib.xdet_depthwise3x3_f32.argtypes = [c_void_p] * 3 + [c_int] * 6 + [c_void_p]
     lib.xdet_rpn_decode.argtypes = [c_void_p, c_int, c_int, c_int] + [c_void_p] * 4 + [c_int] * 4 + [c_void_p] * 3
     lib.xdet_head_decode.argtypes = [c_void_p, c_void_p] + [c_int] * 4 + [c_ll, c_void_p, c_void_p, c_void_p]
+    lib.xdet_head_decode_ex.argtypes = [c_void_p, c_void_p] + [c_int] * 4 + [c_ll] + [c_void_p] * 5
     lib.xdet_rpn_select_workspace_bytes.argtypes = [c_int, c_int, c_int]
     lib.xdet_rpn_select_workspace_bytes.restype = c_size_t
     lib.xdet_rpn_select.argtypes = ([c_void_p, c_void_p] + [c_int] * 4 + [c_float, c_float] + [c_void_p] * 6 +

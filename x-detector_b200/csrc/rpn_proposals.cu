@@ -433,7 +433,8 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const float* __restric
                                                           const float* __restrict__ head_out, int ch_stride,
                                                           int cls_off, int num_classes, int loc_off,
                                                           float* __restrict__ probs, float* __restrict__ boxes,
-                                                          long long M) {
+                                                          long long* __restrict__ classes /* or NULL */,
+                                                          float* __restrict__ best_prob /* or NULL */, long long M) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
   const float* h = head_out + i * ch_stride;
@@ -441,8 +442,18 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const float* __restric
   for (int c = 0; c < num_classes; ++c) mx = fmaxf(mx, __ldg(h + cls_off + c));
   float sum = 0.f;
   for (int c = 0; c < num_classes; ++c) sum = __fadd_rn(sum, expf(__fsub_rn(__ldg(h + cls_off + c), mx)));
-  for (int c = 0; c < num_classes; ++c)
-    probs[i * num_classes + c] = __fdiv_rn(expf(__fsub_rn(__ldg(h + cls_off + c), mx)), sum);
+  float pbest = -1.f;
+  int cbest = 0;
+  for (int c = 0; c < num_classes; ++c) {
+    const float pc = __fdiv_rn(expf(__fsub_rn(__ldg(h + cls_off + c), mx)), sum);
+    probs[i * num_classes + c] = pc;
+    if (pc > pbest) {  // tf.argmax / tf.reduce_max over the class axis (light_head_rfcn_eval.py:413-416): first maximum
+      pbest = pc;
+      cbest = c;
+    }
+  }
+  if (classes) classes[i] = cbest;
+  if (best_prob) best_prob[i] = pbest;
   const float4 r = reinterpret_cast<const float4*>(rois)[i];
   const float href = __fsub_rn(r.z, r.x), wref = __fsub_rn(r.w, r.y);
   const float yref = __fadd_rn(r.x, __fmul_rn(href, 0.5f)), xref = __fadd_rn(r.y, __fmul_rn(wref, 0.5f));
@@ -626,14 +637,20 @@ extern "C" int xdet_det_postprocess(const float* d_probs, const float* d_boxes, 
   return after_launch("nms_scan_kernel");
 }
 
-extern "C" int xdet_head_decode(const float* d_rois, const float* d_head_out, int ch_stride, int cls_off,
-                                int num_classes, int loc_off, long long M, float* d_probs, float* d_boxes,
-                                void* stream) {
+extern "C" int xdet_head_decode_ex(const float* d_rois, const float* d_head_out, int ch_stride, int cls_off,
+                                   int num_classes, int loc_off, long long M, float* d_probs, float* d_boxes,
+                                   long long* d_classes, float* d_best_prob, void* stream) {
   if (M <= 0) return XDET_OK;
   if (num_classes <= 0) return fail(XDET_EINVAL, "head_decode: num_classes must be positive");
   head_decode_kernel<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      d_rois, d_head_out, ch_stride, cls_off, num_classes, loc_off, d_probs, d_boxes, M);
+      d_rois, d_head_out, ch_stride, cls_off, num_classes, loc_off, d_probs, d_boxes, d_classes, d_best_prob, M);
   return after_launch("head_decode_kernel");
+}
+
+extern "C" int xdet_head_decode(const float* d_rois, const float* d_head_out, int ch_stride, int cls_off, int num_classes,
+                                int loc_off, long long M, float* d_probs, float* d_boxes, void* stream) {
+  return xdet_head_decode_ex(d_rois, d_head_out, ch_stride, cls_off, num_classes, loc_off, M, d_probs, d_boxes, nullptr,
+                             nullptr, stream);
 }
 
 // ---- TP / FP matching of detections against ground truth (utility/eval_helper.py:671-788) -------------------

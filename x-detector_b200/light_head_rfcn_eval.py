@@ -163,10 +163,10 @@ def lighr_head_model_fn(features, labels, mode, params, store=None, shuffle_keys
             yxhw_bboxes=yxhw, return_fused=True)
         N, R = proposals_bboxes.shape[:2]
         head = head.reshape(N * R, -1)
-        head_cls_score, head_bboxes_pred = ops.head_decode(proposals_bboxes.reshape(-1, 4), head, 0,
-                                                           params['num_classes'], params['num_classes'])
+        head_cls_score, head_bboxes_pred, classes, probabilities = ops.head_decode(
+            proposals_bboxes.reshape(-1, 4), head, 0, params['num_classes'], params['num_classes'], with_classes=True)
     return {
-        'classes': head_cls_score.argmax(dim=-1), 'probabilities': head_cls_score.max(dim=-1).values,
+        'classes': classes, 'probabilities': probabilities,
         'bboxes_predict': head_bboxes_pred, 'head_cls_score': head_cls_score,
         # intermediates (not in the reference's predictions dict; used by the parity tests)
         'rpn_feat_map': rpn_feat_map, 'backbone_feat': backbone_feat, 'rpn_out': rpn_out,

@@ -56,15 +56,23 @@ def rpn_select(scores, boxes, pre_nms_top_n, post_nms_top_n, nms_threshold, min_
     return rois, yxhw, rscore
 
 
-def head_decode(rois, head_out, cls_off, num_classes, loc_off):
-    """rois [M,4], head_out [M,ch] fp32 -> softmax probs [M,num_classes], decoded boxes [M,4]."""
+def head_decode(rois, head_out, cls_off, num_classes, loc_off, with_classes=False):
+    """rois [M,4], head_out [M,ch] fp32 -> softmax probs [M,num_classes], decoded boxes [M,4]
+    (+ with_classes: arg-max class [M] int64 and its probability [M], the predictions dict's 'classes' /
+    'probabilities')."""
     rois, head_out = rois.contiguous(), head_out.contiguous()
     M, ch = head_out.shape
     probs = torch.empty((M, num_classes), dtype=torch.float32, device=head_out.device)
     boxes = torch.empty((M, 4), dtype=torch.float32, device=head_out.device)
-    rc = _native.lib().xdet_head_decode(rois.data_ptr(), head_out.data_ptr(), ch, cls_off, num_classes, loc_off, M,
-                                        probs.data_ptr(), boxes.data_ptr(), _st())
+    classes = torch.empty((M,), dtype=torch.int64, device=head_out.device) if with_classes else None
+    best = torch.empty((M,), dtype=torch.float32, device=head_out.device) if with_classes else None
+    rc = _native.lib().xdet_head_decode_ex(rois.data_ptr(), head_out.data_ptr(), ch, cls_off, num_classes, loc_off, M,
+                                           probs.data_ptr(), boxes.data_ptr(),
+                                           None if classes is None else classes.data_ptr(),
+                                           None if best is None else best.data_ptr(), _st())
     _native.check(rc)
+    if with_classes:
+        return probs, boxes, classes, best
     return probs, boxes
 
 
