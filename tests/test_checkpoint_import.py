@@ -1,0 +1,115 @@
+"""CPU: TF V2 checkpoint import -- the tensor-bundle reader against bundles written by the independent
+fixture writer (tests/bundle_writer.py), the restore-name rules of utility/train_helper.py:13-30, and a model built
+from the imported state dict.  No TensorFlow offline: the format is restated, parity unpinned."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import xdet_b200  # noqa: F401
+from tests import bundle_writer as bw
+from xdet_b200.net.variables import VariableStore
+from xdet_b200.utility import tensor_bundle as tb
+from xdet_b200.utility import train_helper as th
+
+
+def test_crc32c_known_answers():
+    assert tb.crc32c(b"123456789") == 0xE3069283      # the CRC-32C check value
+    assert tb.crc32c(b"") == 0
+    assert tb.crc32c(bytes(32)) == 0x8A9136AA          # RFC 3720 B.4: 32 bytes of zeros
+
+
+def _tensors(rng):
+    t = {"xception_lighthead/conv2d/kernel": rng.standard_normal((7, 7, 3, 64)).astype(np.float32),
+         "xception_lighthead/batch_normalization/gamma": rng.random(64).astype(np.float32),
+         "xception_lighthead/batch_normalization/moving_mean": rng.standard_normal(64).astype(np.float32),
+         "xception_lighthead/final_head/fc_cls/bias": rng.standard_normal(21).astype(np.float32),
+         "global_step": np.array(12345, np.int64)}
+    for i in range(1, 30):  # enough keys for several table blocks and shared key prefixes
+        t["xception_lighthead/conv2d_%d/kernel" % i] = rng.standard_normal((1, 1, 8, 4 + i)).astype(np.float32)
+    return t
+
+
+def test_reader_roundtrip(tmp_path):
+    rng = np.random.default_rng(0)
+    tensors = _tensors(rng)
+    prefix = str(tmp_path / "model.ckpt-7")
+    bw.write_bundle(prefix, tensors)
+    r = tb.TensorBundleReader(prefix)
+    assert set(r.get_variable_to_shape_map()) == set(tensors)
+    for k, v in tensors.items():
+        got = r.get_tensor(k)
+        assert got.dtype == v.dtype and list(got.shape) == list(v.shape) and np.array_equal(got, v), k
+    assert r.has_tensor("global_step") and not r.has_tensor("nope")
+    # corruption is detected
+    with open(prefix + ".data-00000-of-00001", "r+b") as f:
+        f.seek(100)
+        b = f.read(1)
+        f.seek(100)
+        f.write(bytes([b[0] ^ 0xFF]))
+    bad = [k for k in tensors if _raises(lambda: tb.TensorBundleReader(prefix).get_tensor(k))]
+    assert len(bad) == 1
+    with open(prefix + ".index", "r+b") as f:
+        f.seek(-3, os.SEEK_END)
+        f.write(b"\x00")
+    with pytest.raises(ValueError):
+        tb.TensorBundleReader(prefix)
+
+
+def _raises(fn):
+    try:
+        fn()
+        return False
+    except ValueError:
+        return True
+
+
+def test_restore_name_rules():
+    names = ["xception_lighthead/conv2d/kernel", "xception_lighthead/rpn_head/conv2d/kernel",
+             "xception_lighthead/final_head/fc_cls/bias"]
+    assert th.variables_to_restore(names, "xception_lighthead") == {n: n for n in names}
+    m = th.variables_to_restore(names, "xception_lighthead", "xception", "xception_lighthead/final_head, other")
+    assert m == {"xception/conv2d/kernel": names[0], "xception/rpn_head/conv2d/kernel": names[1]}
+    m = th.variables_to_restore(names[:1], "xception_lighthead", " ")   # blank: strip the scope (train_helper.py:27-28)
+    assert m == {" conv2d/kernel": names[0]}
+
+
+def test_load_state_dict_into_store(tmp_path):
+    rng = np.random.default_rng(1)
+    tensors = _tensors(rng)
+    ckpt_dir = tmp_path / "logs"
+    ckpt_dir.mkdir()
+    # the checkpoint uses another scope name, as the published Xception backbone does (--checkpoint_model_scope)
+    renamed = {k.replace("xception_lighthead", "xception"): v for k, v in tensors.items()}
+    bw.write_bundle(str(ckpt_dir / "model.ckpt-9"), renamed)
+    (ckpt_dir / "checkpoint").write_text('model_checkpoint_path: "model.ckpt-9"\nall_model_checkpoint_paths: "model.ckpt-9"\n')
+    assert th.latest_checkpoint(str(ckpt_dir)) == str(ckpt_dir / "model.ckpt-9")
+    want = [k for k in tensors if k != "global_step"] + ["xception_lighthead/not_in_checkpoint/kernel"]
+    with pytest.raises(KeyError):
+        th.load_state_dict(str(ckpt_dir), want, "xception_lighthead", "xception")
+    sd = th.load_state_dict(str(ckpt_dir), want, "xception_lighthead", "xception", ignore_missing_vars=True,
+                            shapes={"xception_lighthead/conv2d/kernel": (7, 7, 3, 64)})
+    assert set(sd) == set(want[:-1])
+    with pytest.raises(ValueError):
+        th.load_state_dict(str(ckpt_dir), want, "xception_lighthead", "xception", ignore_missing_vars=True,
+                           shapes={"xception_lighthead/conv2d/kernel": (3, 3, 3, 64)})
+    store = VariableStore(device="cpu", seed=0, state_dict=sd)
+    with store.scope("xception_lighthead"):
+        with store.scope("conv2d"):
+            key, k = store.get("kernel", (7, 7, 3, 64), store.glorot_normal)   # found, not re-initialised
+    assert key == "xception_lighthead/conv2d/kernel" and torch.equal(k, torch.from_numpy(tensors[key]))
+    assert k.dtype == torch.float32
+
+
+def test_checkpoint_to_state_dict(tmp_path):
+    rng = np.random.default_rng(2)
+    tensors = _tensors(rng)
+    tensors["xception_lighthead/conv2d/kernel/Momentum"] = np.zeros((7, 7, 3, 64), np.float32)
+    renamed = {k.replace("xception_lighthead", "xception"): v for k, v in tensors.items()}
+    renamed["unrelated/weights"] = np.ones(3, np.float32)
+    prefix = str(tmp_path / "m.ckpt")
+    bw.write_bundle(prefix, renamed)
+    sd = th.checkpoint_to_state_dict(prefix, "xception_lighthead", "xception")
+    assert set(sd) == {k for k in tensors if not k.endswith("Momentum") and k != "global_step"}
+    assert np.array_equal(sd["xception_lighthead/final_head/fc_cls/bias"], tensors["xception_lighthead/final_head/fc_cls/bias"])

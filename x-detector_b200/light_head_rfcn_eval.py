@@ -187,6 +187,17 @@ class LightHeadRFCN(object):
 
         self._det_consts = {}
 
+    @classmethod
+    def from_checkpoint(cls, params=None, checkpoint_path=None, checkpoint_model_scope=None, seed=0, device="cuda"):
+        """Build the model from a TensorFlow V2 checkpoint of the reference (``--checkpoint_path`` / ``--model_dir``,
+        light_head_rfcn_eval.py:125-137, :499): variables found in the checkpoint are used, the others keep their
+        seeded initial values (utility/train_helper.py)."""
+        from .utility import train_helper
+        params = params or make_params()
+        sd = train_helper.checkpoint_to_state_dict(checkpoint_path or params['checkpoint_path'], params['model_scope'],
+                                                   checkpoint_model_scope)
+        return cls(params, seed=seed, device=device, state_dict=sd)
+
     def det_consts(self, n, image_shape=None, bbox_img=None, device="cuda"):
         """(bbox_img [n,4], min_size [n]) device tensors for the post-processing; cached, so a CUDA-graph capture of
         ``__call__(..., detections=True)`` finds them already on the device.  Defaults: the whole net input is the

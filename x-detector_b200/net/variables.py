@@ -19,7 +19,10 @@ import torch
 class VariableStore(object):
     def __init__(self, device="cuda", seed=0, state_dict=None):
         self.device = torch.device(device)
-        self.vars = {} if state_dict is None else dict(state_dict)
+        # state_dict: {TF variable name: tensor or numpy array} (e.g. utility.train_helper.load_state_dict of a TF
+        # checkpoint); values become fp32 tensors on the device
+        self.vars = {} if state_dict is None else {
+            k: torch.as_tensor(v, dtype=torch.float32).to(self.device).contiguous() for k, v in state_dict.items()}
         self.derived = {}
         self._gen = torch.Generator(device="cpu").manual_seed(seed)
         self._scope = []
