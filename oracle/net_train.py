@@ -1,5 +1,6 @@
 """CPU restatement of ONE training step of the reference's lighr_head_model_fn (light_head_rfcn_train.py:277-451)
-for the ResNet-50 light-head composition: PyTorch-CPU fp32 graph + autograd.  TEST INFRASTRUCTURE ONLY.
+for the ResNet-50 light-head composition (and, with params['backbone'] = 'xception', the reference's XceptionBody):
+PyTorch-CPU fp32 graph + autograd.  TEST INFRASTRUCTURE ONLY.
 
 The discrete selections (RPN sample indices, sampled RoIs, OHEM indices) can be INJECTED so that gradients are
 compared on identical decisions (they are discontinuous in the bf16-vs-fp32 rounding); the selections themselves
@@ -49,7 +50,11 @@ def train_step(images, gt_boxes, gt_labels, sd, params, anchors, inject):
     onet.BN_TRAINING = True
     try:
         xin = torch.as_tensor(images).float()
-        rpn_feat, backbone = onet.lighthead_resnet50_body(xin, nm, layers=tuple(params.get("resnet_layers", (3, 4, 6, 3))))
+        if params.get("backbone", "resnet50") == "xception":  # the reference's own backbone (net/xception_body.py:236-379)
+            rpn_feat, backbone = onet.xception_body(xin, nm)
+        else:
+            rpn_feat, backbone = onet.lighthead_resnet50_body(xin, nm,
+                                                              layers=tuple(params.get("resnet_layers", (3, 4, 6, 3))))
         cls, box = onet.get_rpn(rpn_feat, nm, "rpn_head", num_anchors=A)
         thin = onet.large_sep_kernel(backbone, nm, "large_sep_feature")
         cls_all = cls.permute(0, 2, 3, 1).reshape(-1, 2)
