@@ -36,3 +36,19 @@ def test_streaming_accumulation_and_filters():
     assert (nobj, ndet) == (3, 2) and tp.tolist() == [True, False] and fp.tolist() == [False, True]
     m, aps = M.voc_map(st)
     assert 0.0 <= m <= 1.0 and list(aps) == [1]
+
+
+def test_ap_matches_the_reference_voc_ap_golden():
+    """Golden vectors minted from the reference's own numpy voc_ap (voc_eval.py:98-130, executed unmodified by
+    tests/golden/make_voc_ap_golden.py): utility/metrics.py's precision/recall + AP07/AP12 reproduce them."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "voc_ap_golden.npz"))
+    for i in range(int(g["n_cases"])):
+        tp = g["tp_%d" % i]
+        n = tp.shape[0]
+        scores = np.linspace(1.0, 0.5, n).astype(np.float32)       # already in score order
+        p, r = M.precision_recall(int(g["npos_%d" % i]), n, tp, ~tp, scores)
+        assert abs(M.average_precision_voc07(p, r) - float(g["ap07_%d" % i])) < 1e-12, i
+        assert abs(M.average_precision_voc12(p, r) - float(g["ap12_%d" % i])) < 1e-12, i
+        assert abs(ov.voc_ap(r, p, True) - float(g["ap07_%d" % i])) < 1e-12
+        assert abs(ov.voc_ap(r, p, False) - float(g["ap12_%d" % i])) < 1e-12
