@@ -1,0 +1,342 @@
+"""A numpy-backed stand-in for the few dozen TensorFlow 1.x graph ops that the reference's *Python* helpers on the
+Light-Head R-CNN path use (preprocessing/anchor_manipulator.py, net/xception_body.py:41-218,402-448,
+utility/eval_helper.py), evaluated eagerly.  TEST INFRASTRUCTURE ONLY (like oracle/ref_shim for the C++ op): with this
+directory first on sys.path, ``import tensorflow as tf`` inside the UNMODIFIED reference modules resolves here, so
+their own code can be run in this container to mint golden vectors (tests/golden/make_tfpath_golden.py).
+
+Semantics kept: float32 arithmetic (python scalars are weak, python float lists become float32, ints int32, as TF's
+convert_to_tensor does), tf.nn.top_k = descending with ties to the lower index, tf.boolean_mask / gather / pad / tile /
+while_loop / TensorArray as documented for TF 1.6.  NOT provided by TensorFlow's own code here: tf.nn.top_k,
+tf.image.non_max_suppression (TF r1.6 NonMaxSuppressionV2, restated in oracle/proposals.py) and tf.random_shuffle
+(replaced by the injected-key order the product uses) -- the goldens pin everything AROUND those three."""
+import contextlib
+import sys
+import types
+
+import numpy as np
+
+float32, float64, int32, int64, bool = np.float32, np.float64, np.int32, np.int64, np.bool_
+uint8 = np.uint8
+
+
+class _Shape(object):
+    def __init__(self, dims):
+        self._d = [int(d) for d in dims]
+
+    def as_list(self):
+        return list(self._d)
+
+    def is_fully_defined(self):
+        return True
+
+    def with_rank(self, rank):
+        assert len(self._d) == rank
+        return self
+
+    @property
+    def ndims(self):
+        return len(self._d)
+
+    def __len__(self):
+        return len(self._d)
+
+    def __getitem__(self, i):
+        return self._d[i]
+
+
+class Tensor(np.ndarray):
+    def get_shape(self):
+        return _Shape(self.shape)
+
+    def set_shape(self, shape):
+        return None
+
+
+def _t(x, dtype=None):
+    """convert_to_tensor: python floats -> float32, python ints -> int32, arrays keep their dtype."""
+    if isinstance(x, np.ndarray):
+        a = x if dtype is None else x.astype(dtype)
+    else:
+        a = np.asarray(x)
+        if dtype is not None:
+            a = a.astype(dtype)
+        elif a.dtype == np.float64:
+            a = a.astype(np.float32)
+        elif a.dtype == np.int64:
+            a = a.astype(np.int32)
+    return np.ascontiguousarray(a).view(Tensor) if a.ndim else np.asarray(a).reshape(()).view(Tensor)
+
+
+def convert_to_tensor(x, dtype=None, name=None):
+    return _t(x, dtype)
+
+
+def constant(value, dtype=None, shape=None, name=None):
+    return _t(value, dtype)
+
+
+def cast(x, dtype, name=None):
+    return _t(np.asarray(_t(x)).astype(dtype))
+
+
+def to_float(x):
+    return cast(x, float32)
+
+
+def to_double(x):
+    return cast(x, float64)
+
+
+def identity(x, name=None):
+    return x
+
+
+def stop_gradient(x, name=None):
+    return x
+
+
+def Print(x, data=None, message=None, summarize=None, name=None):
+    return x
+
+
+@contextlib.contextmanager
+def name_scope(*a, **k):
+    yield
+
+
+@contextlib.contextmanager
+def device(*a, **k):
+    yield
+
+
+variable_scope = name_scope
+
+
+def shape(x, name=None, out_type=None):
+    return _t(np.array(np.shape(x), dtype=np.int32))
+
+
+def size(x, name=None, out_type=None):
+    return np.int32(np.size(x))
+
+
+def reshape(x, shp, name=None):
+    return _t(np.reshape(_t(x), [int(s) for s in np.asarray(shp).reshape(-1)]))
+
+
+def transpose(x, perm=None, name=None):
+    return _t(np.transpose(_t(x), perm))
+
+
+def expand_dims(x, axis=None, name=None, dim=None):
+    return _t(np.expand_dims(_t(x), axis if axis is not None else dim))
+
+
+def stack(values, axis=0, name=None):
+    vals = [_t(v) for v in values]
+    return _t(np.stack(vals, axis=axis))
+
+
+def unstack(x, num=None, axis=0, name=None):
+    x = _t(x)
+    return [_t(np.take(x, i, axis=axis)) for i in range(x.shape[axis])]
+
+
+def concat(values, axis, name=None):
+    if len(values) == 1:  # TF returns identity(values[0]) for a single input, whatever the axis (array_ops.concat)
+        return _t(values[0])
+    return _t(np.concatenate([_t(v) for v in values], axis=axis))
+
+
+def tile(x, multiples, name=None):
+    return _t(np.tile(_t(x), [int(m) for m in np.asarray(multiples).reshape(-1)]))
+
+
+def pad(x, paddings, mode='CONSTANT', name=None):
+    assert mode == 'CONSTANT'
+    p = np.asarray(paddings).astype(np.int64)
+    return _t(np.pad(_t(x), [(int(a), int(b)) for a, b in p], mode='constant'))
+
+
+def slice(x, begin, size, name=None):  # noqa: A001
+    x = _t(x)
+    idx = tuple(np.s_[int(b):(None if int(s) < 0 else int(b) + int(s))] for b, s in zip(begin, size))
+    return _t(x[idx])
+
+
+def gather(params, indices, name=None, axis=0):
+    return _t(np.take(_t(params), np.asarray(indices).astype(np.int64), axis=axis))
+
+
+def boolean_mask(tensor, mask, name=None):
+    return _t(_t(tensor)[np.asarray(mask).astype(np.bool_)])
+
+
+def where(condition, x=None, y=None, name=None):
+    return _t(np.where(np.asarray(condition), _t(x), _t(y)))
+
+
+def range(*args, **kw):  # noqa: A001
+    dtype = kw.get('dtype', np.int32)
+    return _t(np.arange(*[int(a) for a in args]).astype(dtype))
+
+
+def meshgrid(*args, **kw):
+    return [_t(m) for m in np.meshgrid(*[_t(a) for a in args], indexing=kw.get('indexing', 'xy'))]
+
+
+def zeros(shp, dtype=float32, name=None):
+    return _t(np.zeros([int(s) for s in np.asarray(shp).reshape(-1)], dtype=dtype))
+
+
+def zeros_like(x, dtype=None, name=None):
+    return _t(np.zeros_like(_t(x), dtype=dtype))
+
+
+def _binary(fn):
+    def op(a, b, name=None):
+        a, b = _t(a), _t(b)
+        with np.errstate(divide="ignore", invalid="ignore"):  # e.g. safe_divide's 0/0, masked afterwards by tf.where
+            return _t(fn(a, b))
+    return op
+
+
+maximum, minimum = _binary(np.maximum), _binary(np.minimum)
+greater, less, equal = _binary(np.greater), _binary(np.less), _binary(np.equal)
+greater_equal, less_equal = _binary(np.greater_equal), _binary(np.less_equal)
+logical_and, logical_or = _binary(np.logical_and), _binary(np.logical_or)
+divide = _binary(np.true_divide)
+floor_div = _binary(np.floor_divide)
+floormod = _binary(np.mod)
+
+
+def logical_not(x, name=None):
+    return _t(np.logical_not(_t(x)))
+
+
+def exp(x, name=None):
+    return _t(np.exp(_t(x)))
+
+
+def sqrt(x, name=None):
+    return _t(np.sqrt(_t(x)))
+
+
+def reduce_sum(x, axis=None, keepdims=False, name=None):
+    return _t(np.sum(_t(x), axis=axis, keepdims=keepdims))
+
+
+def reduce_max(x, axis=None, keepdims=False, name=None):
+    return _t(np.max(_t(x), axis=axis, keepdims=keepdims))
+
+
+def count_nonzero(x, axis=None, name=None):
+    return np.int64(np.count_nonzero(_t(x), axis=axis))
+
+
+def argmax(x, axis=None, name=None, output_type=np.int64):
+    return np.asarray(np.argmax(_t(x), axis=axis)).astype(output_type)  # first maximum, as TF
+
+
+def cond(pred, true_fn=None, false_fn=None, name=None, **kw):
+    return true_fn() if builtins_bool(pred) else false_fn()
+
+
+def builtins_bool(x):
+    return True if np.asarray(x).reshape(-1)[0] else False
+
+
+MAP_INDEX = 0  # element index of the innermost running tf.map_fn (read by random_shuffle)
+
+
+def map_fn(fn, elems, dtype=None, back_prop=True, infer_shape=True, parallel_iterations=None, name=None):
+    global MAP_INDEX
+    multi = isinstance(elems, (list, tuple))
+    n = len(elems[0]) if multi else len(elems)
+    outs = []
+    saved = MAP_INDEX
+    for i in builtins_range(n):
+        MAP_INDEX = i
+        outs.append(fn(type(elems)(_t(e[i]) for e in elems) if multi else _t(elems[i])))
+    MAP_INDEX = saved
+    if isinstance(outs[0], (list, tuple)):
+        return type(outs[0])(_t(np.stack([np.asarray(o[j]) for o in outs])) for j in builtins_range(len(outs[0])))
+    return _t(np.stack([np.asarray(o) for o in outs]))
+
+
+import builtins as _b  # noqa: E402
+
+builtins_range = _b.range
+
+
+def while_loop(cond_fn, body, loop_vars, parallel_iterations=None, back_prop=False, **kw):
+    v = list(loop_vars)
+    while builtins_bool(cond_fn(*v)):
+        v = list(body(*v))
+    return v
+
+
+class TensorArray(object):
+    def __init__(self, dtype, size=0, dynamic_size=False, infer_shape=True, **kw):
+        self.dtype, self.items = dtype, [None] * int(size)
+
+    def write(self, i, value):
+        self.items[int(i)] = np.asarray(value).astype(self.dtype)
+        return self
+
+    def stack(self):
+        return _t(np.stack(self.items)) if self.items else _t(np.zeros((0,), self.dtype))
+
+
+SHUFFLE_KEYS = None  # [batch, n] float32: tf.random_shuffle(range(n)) := stable argsort of SHUFFLE_KEYS[MAP_INDEX, :n]
+
+
+def random_shuffle(value, seed=None, name=None):
+    v = _t(value)
+    keys = np.arange(len(v), dtype=np.float32) if SHUFFLE_KEYS is None else np.asarray(SHUFFLE_KEYS[MAP_INDEX][:len(v)], np.float32)
+    return _t(v[np.argsort(keys, kind='stable')])
+
+
+class _Any(object):
+    """Attribute sink for module-level references the golden scripts never execute (initialisers, tf.layers, ...)."""
+
+    def __getattr__(self, name):
+        return _Any()
+
+    def __call__(self, *a, **k):
+        return _Any()
+
+
+def __getattr__(name):
+    return _Any()
+
+
+# ---- submodules ------------------------------------------------------------------------------------------------
+nn = types.ModuleType("tensorflow.nn")
+image = types.ModuleType("tensorflow.image")
+
+
+def _top_k(x, k=1, sorted=True, name=None):  # noqa: A002
+    x = _t(x)
+    k = int(np.asarray(k))
+    order = np.lexsort((np.arange(x.shape[0]), -x.astype(np.float64)))[:k]   # descending, ties -> lower index
+    return _t(x[order]), _t(order.astype(np.int32))
+
+
+def _softmax(x, axis=-1, name=None, dim=None):
+    x = _t(x)
+    e = np.exp(x - np.max(x, axis=axis, keepdims=True))
+    return _t((e / np.sum(e, axis=axis, keepdims=True)).astype(x.dtype))
+
+
+def _nms(boxes, scores, max_output_size, iou_threshold=0.5, name=None):
+    from oracle import proposals as P  # the restated TF r1.6 NonMaxSuppressionV2
+    idx = P.non_max_suppression_fast(np.asarray(boxes, np.float32), np.asarray(scores, np.float32), int(np.asarray(max_output_size)),
+                                     float(iou_threshold))
+    return _t(idx.astype(np.int32))
+
+
+nn.top_k, nn.softmax = _top_k, _softmax
+image.non_max_suppression = _nms
+sys.modules.setdefault("tensorflow.nn", nn)
+sys.modules.setdefault("tensorflow.image", image)

@@ -1,0 +1,102 @@
+"""The numpy oracles of the TF graph code on the path, pinned to golden vectors minted from the REFERENCE'S OWN Python
+(preprocessing/anchor_manipulator.py, net/xception_body.py, utility/eval_helper.py) run unmodified under the numpy
+TensorFlow stand-in (tests/golden/make_tfpath_golden.py).  CPU part: oracle == golden, bit for bit.  GPU part: the CUDA
+kernels (through the C-ABI) == golden."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import detections as od
+from oracle import proposals as P
+from oracle import voc_eval as ov
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "tfpath_golden.npz"))
+F = np.float32
+SCALES, EXTRA, RATIOS = [0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8], [0.1], [1., 2., .5]
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=F).view(np.int32)
+
+
+@pytest.mark.parametrize("size,fm", [(480, 30), (800, 50), (160, 10)])
+def test_anchors(size, fm):
+    y, x, h, w = P.layer_anchors((size, size), (fm, fm), SCALES, EXTRA, RATIOS, 16)
+    for k, a in zip("yxhw", (y, x, h, w)):
+        assert np.array_equal(bits(a), bits(G["anchors%d_%s" % (size, k)])), k
+    assert int(G["anchors%d_num" % size]) == 22
+
+
+def test_decode_proposals_point2center_ext_decode():
+    anchors = P.layer_anchors((160, 160), (10, 10), SCALES, EXTRA, RATIOS, 16)
+    boxes = P.decode_all_anchors(G["dec_pred"], anchors)
+    assert np.array_equal(bits(boxes), bits(G["dec_boxes"]))
+    rois, _ = P.get_proposals(G["prop_score"], G["dec_boxes"], 600, 100, 0.7, 16 / 160., G["prop_keys"])
+    assert np.array_equal(bits(rois), bits(G["prop_rois"]))
+    assert np.array_equal(bits(P.point2center(G["prop_rois"].reshape(-1, 4))), bits(G["prop_yxhw"].reshape(-1, 4)))
+    ext = P.ext_decode_rois(G["prop_rois"].reshape(-1, 4), G["ext_deltas"].reshape(-1, 4))
+    assert np.array_equal(bits(ext), bits(G["ext_boxes"].reshape(-1, 4)))
+
+
+def test_detection_chain_and_matching():
+    s, b = od.bboxes_eval_select(G["det_probs"], G["det_boxes"], G["det_bbox_img"], G["det_shape"], 21)
+    for c in range(1, 21):
+        assert np.array_equal(bits(s[c]), bits(G["det_out_scores"][c - 1])), c
+        assert np.array_equal(bits(b[c]), bits(G["det_out_boxes"][c - 1])), c
+        n, tp, fp = ov.bboxes_matching(c, s[c], b[c], G["match_glabels"], G["match_gboxes"], G["match_gdiff"])
+        assert n == int(G["match_n"][c - 1])
+        assert np.array_equal(tp, G["match_tp"][c - 1]) and np.array_equal(fp, G["match_fp"][c - 1])
+    assert int((G["det_out_scores"] > 0).sum()) > 100 and int(G["match_tp"].sum()) > 0
+
+
+# ---- the CUDA path against the same goldens ---------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def cuda():
+    import torch
+    assert torch.cuda.is_available()
+    import xdet_b200  # noqa: F401
+    from xdet_b200 import _native
+    _native.lib()
+    return torch
+
+
+@pytest.mark.gpu
+def test_gpu_anchor_creator(cuda):
+    from xdet_b200.preprocessing import anchor_manipulator as am
+    for size, fm in ((480, 30), (800, 50), (160, 10)):
+        cr = am.AnchorCreator([size, size], layers_shapes=[(fm, fm)], anchor_scales=[SCALES], extra_anchor_scales=[EXTRA],
+                              anchor_ratios=[RATIOS], layer_steps=[16])
+        anchors, num = cr.get_all_anchors()
+        assert num[0] == 22
+        for k, a in zip("yxhw", anchors[0]):
+            assert np.array_equal(bits(np.asarray(a.cpu() if hasattr(a, "cpu") else a)), bits(G["anchors%d_%s" % (size, k)])), k
+
+
+@pytest.mark.gpu
+def test_gpu_proposals(cuda):
+    torch = cuda
+    from xdet_b200 import ops
+    rois, yxhw, _ = ops.rpn_select(torch.from_numpy(G["prop_score"]).cuda(), torch.from_numpy(G["dec_boxes"]).cuda(), 600, 100,
+                                   0.7, 16 / 160., torch.from_numpy(G["prop_keys"]).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(bits(rois.cpu().numpy()), bits(G["prop_rois"]))
+    assert np.array_equal(bits(yxhw.cpu().numpy()), bits(G["prop_yxhw"]))
+
+
+@pytest.mark.gpu
+def test_gpu_detection_chain_and_matching(cuda):
+    torch = cuda
+    from xdet_b200 import light_head_rfcn_eval as lh
+    from xdet_b200.utility import eval_helper as eh
+    d_s, d_b = lh.bboxes_eval([tuple(int(v) for v in G["det_shape"])], torch.from_numpy(G["det_bbox_img"][None]).cuda(),
+                              torch.from_numpy(G["det_probs"][None]).cuda(), torch.from_numpy(G["det_boxes"][None]).cuda(), 21)
+    ngb, tp, fp = eh.bboxes_matching_batch(d_s.keys(), d_s, d_b, torch.from_numpy(G["match_glabels"][None]),
+                                           torch.from_numpy(G["match_gboxes"][None]), torch.from_numpy(G["match_gdiff"][None]))
+    torch.cuda.synchronize()
+    for c in range(1, 21):
+        assert np.array_equal(bits(d_s[c][0].cpu().numpy()), bits(G["det_out_scores"][c - 1])), c
+        assert np.array_equal(bits(d_b[c][0].cpu().numpy()), bits(G["det_out_boxes"][c - 1])), c
+        assert int(ngb[c][0]) == int(G["match_n"][c - 1])
+        assert np.array_equal(tp[c][0].cpu().numpy(), G["match_tp"][c - 1])
+        assert np.array_equal(fp[c][0].cpu().numpy(), G["match_fp"][c - 1])
