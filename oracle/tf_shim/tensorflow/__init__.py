@@ -15,8 +15,33 @@ import types
 
 import numpy as np
 
-float32, float64, int32, int64, bool = np.float32, np.float64, np.int32, np.int64, np.bool_
-uint8 = np.uint8
+class DType(object):
+    """tf.float32 & co.: usable wherever TF takes a dtype, with .max / .min / .as_numpy_dtype."""
+
+    def __init__(self, np_type):
+        self.as_numpy_dtype = np_type
+        self.name = np.dtype(np_type).name
+        if np.issubdtype(np_type, np.integer):
+            self.max, self.min = int(np.iinfo(np_type).max), int(np.iinfo(np_type).min)
+        elif np.issubdtype(np_type, np.floating):
+            self.max, self.min = float(np.finfo(np_type).max), float(np.finfo(np_type).min)
+
+    def __eq__(self, other):
+        return _np(other) == self.as_numpy_dtype if other is not None else False
+
+    def __hash__(self):
+        return hash(self.name)
+
+
+def _np(dtype):
+    """numpy type of a DType / numpy dtype / None."""
+    if dtype is None:
+        return None
+    return dtype.as_numpy_dtype if isinstance(dtype, DType) else np.dtype(dtype).type
+
+
+float32, float64, int32, int64, bool = DType(np.float32), DType(np.float64), DType(np.int32), DType(np.int64), DType(np.bool_)
+uint8 = DType(np.uint8)
 
 
 class _Shape(object):
@@ -54,6 +79,7 @@ class Tensor(np.ndarray):
 
 def _t(x, dtype=None):
     """convert_to_tensor: python floats -> float32, python ints -> int32, arrays keep their dtype."""
+    dtype = _np(dtype)
     if isinstance(x, np.ndarray):
         a = x if dtype is None else x.astype(dtype)
     else:
@@ -76,7 +102,7 @@ def constant(value, dtype=None, shape=None, name=None):
 
 
 def cast(x, dtype, name=None):
-    return _t(np.asarray(_t(x)).astype(dtype))
+    return _t(np.asarray(_t(x)).astype(_np(dtype)))
 
 
 def to_float(x):
@@ -173,11 +199,15 @@ def boolean_mask(tensor, mask, name=None):
 
 
 def where(condition, x=None, y=None, name=None):
+    if x is None and y is None:  # coordinates of the true elements, [n, rank] int64
+        return _t(np.argwhere(np.asarray(condition)).astype(np.int64))
     return _t(np.where(np.asarray(condition), _t(x), _t(y)))
 
 
 def range(*args, **kw):  # noqa: A001
-    dtype = kw.get('dtype', np.int32)
+    dtype = _np(kw.get('dtype', None))
+    if dtype is None:  # dtype of the limits (python ints -> int32, tensors keep theirs), as tf.range infers it
+        dtype = np.result_type(*[np.asarray(_t(a)).dtype for a in args]).type
     return _t(np.arange(*[int(a) for a in args]).astype(dtype))
 
 
@@ -186,11 +216,46 @@ def meshgrid(*args, **kw):
 
 
 def zeros(shp, dtype=float32, name=None):
-    return _t(np.zeros([int(s) for s in np.asarray(shp).reshape(-1)], dtype=dtype))
+    return _t(np.zeros([int(s) for s in np.asarray(shp).reshape(-1)], dtype=_np(dtype)))
 
 
 def zeros_like(x, dtype=None, name=None):
-    return _t(np.zeros_like(_t(x), dtype=dtype))
+    return _t(np.zeros_like(_t(x), dtype=_np(dtype)))
+
+
+def ones_like(x, dtype=None, name=None):
+    return _t(np.ones_like(_t(x), dtype=_np(dtype)))
+
+
+def one_hot(indices, depth, on_value=None, off_value=None, axis=None, dtype=None, name=None):
+    """Negative / out-of-range indices give an all-`off` slice, as in TF."""
+    idx = np.asarray(_t(indices)).astype(np.int64)
+    depth = int(np.asarray(depth))
+    dt = _np(dtype) or (np.asarray(on_value).dtype.type if on_value is not None else np.float32)
+    on = np.asarray(1 if on_value is None else on_value).astype(dt)
+    off = np.asarray(0 if off_value is None else off_value).astype(dt)
+    hot = (idx[..., None] == np.arange(depth)).astype(np.bool_)          # new axis last
+    out = np.where(hot, on, off).astype(dt)
+    ax = -1 if axis is None else axis
+    return _t(np.moveaxis(out, -1, ax if ax >= 0 else out.ndim + ax))
+
+
+def clip_by_value(x, lo, hi, name=None):
+    x = _t(x)
+    return _t(np.clip(x, np.asarray(lo).astype(x.dtype), np.asarray(hi).astype(x.dtype)))
+
+
+def gather_nd(params, indices, name=None):
+    idx = np.asarray(_t(indices)).astype(np.int64)
+    return _t(_t(params)[tuple(idx[..., i] for i in builtins_range(idx.shape[-1]))])
+
+
+def split(value, num_or_size_splits, axis=0, num=None, name=None):
+    return [_t(p) for p in np.split(_t(value), num_or_size_splits, axis=axis)]
+
+
+def squeeze(x, axis=None, name=None, squeeze_dims=None):
+    return _t(np.squeeze(_t(x), axis=axis if axis is not None else squeeze_dims))
 
 
 def _binary(fn):
@@ -206,6 +271,7 @@ greater, less, equal = _binary(np.greater), _binary(np.less), _binary(np.equal)
 greater_equal, less_equal = _binary(np.greater_equal), _binary(np.less_equal)
 logical_and, logical_or = _binary(np.logical_and), _binary(np.logical_or)
 divide = _binary(np.true_divide)
+truediv = _binary(np.true_divide)
 floor_div = _binary(np.floor_divide)
 floormod = _binary(np.mod)
 
@@ -222,20 +288,29 @@ def sqrt(x, name=None):
     return _t(np.sqrt(_t(x)))
 
 
+def log(x, name=None):
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return _t(np.log(_t(x)))
+
+
+def round(x, name=None):  # noqa: A001
+    return _t(np.rint(_t(x)))  # half to even, as tf.round
+
+
 def reduce_sum(x, axis=None, keepdims=False, name=None):
     return _t(np.sum(_t(x), axis=axis, keepdims=keepdims))
 
 
-def reduce_max(x, axis=None, keepdims=False, name=None):
-    return _t(np.max(_t(x), axis=axis, keepdims=keepdims))
+def reduce_max(x, axis=None, keepdims=False, name=None, keep_dims=None):
+    return _t(np.max(_t(x), axis=axis, keepdims=keepdims if keep_dims is None else keep_dims))
 
 
 def count_nonzero(x, axis=None, name=None):
     return np.int64(np.count_nonzero(_t(x), axis=axis))
 
 
-def argmax(x, axis=None, name=None, output_type=np.int64):
-    return np.asarray(np.argmax(_t(x), axis=axis)).astype(output_type)  # first maximum, as TF
+def argmax(x, axis=None, name=None, output_type=None):
+    return _t(np.asarray(np.argmax(_t(x), axis=axis)).astype(_np(output_type) or np.int64))  # first maximum, as TF
 
 
 def cond(pred, true_fn=None, false_fn=None, name=None, **kw):
@@ -278,7 +353,7 @@ def while_loop(cond_fn, body, loop_vars, parallel_iterations=None, back_prop=Fal
 
 class TensorArray(object):
     def __init__(self, dtype, size=0, dynamic_size=False, infer_shape=True, **kw):
-        self.dtype, self.items = dtype, [None] * int(size)
+        self.dtype, self.items = _np(dtype), [None] * int(size)
 
     def write(self, i, value):
         self.items[int(i)] = np.asarray(value).astype(self.dtype)
@@ -288,12 +363,24 @@ class TensorArray(object):
         return _t(np.stack(self.items)) if self.items else _t(np.zeros((0,), self.dtype))
 
 
-SHUFFLE_KEYS = None  # [batch, n] float32: tf.random_shuffle(range(n)) := stable argsort of SHUFFLE_KEYS[MAP_INDEX, :n]
+# tf.random_shuffle(range(n)) := stable argsort of keys[:n] (the injected-key order of the product and the oracles).
+# SHUFFLE_KEYS: [batch, n] float32 used for every call, or a callable (map_index, n, caller_lineno) -> keys [>= n]
+# when a function shuffles for several purposes (ext_encode_rois: fg / bg down-sampling, up-sampling).
+SHUFFLE_KEYS = None
 
 
 def random_shuffle(value, seed=None, name=None):
     v = _t(value)
-    keys = np.arange(len(v), dtype=np.float32) if SHUFFLE_KEYS is None else np.asarray(SHUFFLE_KEYS[MAP_INDEX][:len(v)], np.float32)
+    if SHUFFLE_KEYS is None:
+        keys = np.arange(len(v), dtype=np.float32)
+    elif callable(SHUFFLE_KEYS):
+        frames, f = [], sys._getframe(1)
+        while f is not None and len(frames) < 6:
+            frames.append((f.f_code.co_name, f.f_lineno))
+            f = f.f_back
+        keys = np.asarray(SHUFFLE_KEYS(MAP_INDEX, len(v), frames), np.float32)[:len(v)]
+    else:
+        keys = np.asarray(SHUFFLE_KEYS[MAP_INDEX][:len(v)], np.float32)
     return _t(v[np.argsort(keys, kind='stable')])
 
 

@@ -6,6 +6,8 @@ stand-in oracle/tf_shim (TensorFlow 1.6 itself cannot be installed offline):
                                        (:641-669), ext_decode_rois (:671-683)
   net/xception_body.py                 get_proposals (:402-448) = _bboxes_clip, _filter_and_sort_boxes, _bboxes_nms,
                                        _upsample_rois; _point2center (:215-218)
+                                       AnchorEncoder.encode_all_anchors (:118-171,319-335: iou_matrix, do_dual_max_match,
+                                       target encoding) and ext_encode_rois (:337-432: RoI targets + fg/bg sampling)
   utility/eval_helper.py               tf_bboxes_select, bboxes_clip, filter_boxes, bboxes_resize, bboxes_sort,
                                        bboxes_nms_batch (the chain of light_head_rfcn_eval.py:274-288), bboxes_matching
 
@@ -105,6 +107,53 @@ def main():
         fps.append(np.asarray(fp))
     out["match_glabels"], out["match_gboxes"], out["match_gdiff"] = glabels, gboxes, gdiff
     out["match_n"], out["match_tp"], out["match_fp"] = np.array(ngs, np.int64), np.stack(tps), np.stack(fps)
+    # ---- training targets: anchor matching / encoding, RoI targets + sampling ------------------------------------
+    enc2 = am.AnchorEncoder(anchors, num_classes=21, allowed_borders=[0.], positive_threshold=0.7, ignore_threshold=0.3,
+                            prior_scaling=[1., 1., 1., 1.], rpn_fg_thres=0.5, rpn_bg_high_thres=0.5, rpn_bg_low_thres=0.)
+    N, R, Gn = 2, 60, 4
+    gt = np.zeros((N, Gn, 4), F)
+    gl = np.zeros((N, Gn), np.int64)
+    gt[0, :3] = [[0.1, 0.1, 0.6, 0.7], [0.5, 0.4, 0.95, 0.9], [0.3, 0.05, 0.5, 0.3]]
+    gl[0, :3] = [3, 7, 12]
+    gt[1, :2] = [[0.2, 0.3, 0.8, 0.8], [0.05, 0.5, 0.4, 0.95]]
+    gl[1, :2] = [1, 20]
+    out["tgt_gt"], out["tgt_gl"] = gt, gl
+    with np.errstate(all="ignore"):
+        for n in range(N):
+            valid = gl[n] > 0
+            labels, targets, scores, pts, _ = enc2.encode_all_anchors(tf.constant(gl[n][valid]), tf.constant(gt[n][valid]))
+            out["enc_labels_%d" % n] = np.asarray(labels[0]).reshape(-1)
+            out["enc_targets_%d" % n] = np.asarray(targets[0]).reshape(-1, 4)
+            out["enc_scores_%d" % n] = np.asarray(scores[0]).reshape(-1)
+            out["enc_points_%d" % n] = np.asarray(pts[0])
+    rois_in = np.zeros((N, R, 4), F)
+    for n in range(N):
+        ng = int((gl[n] > 0).sum())
+        for j in range(R):
+            bb = np.clip(gt[n, j % ng] + rng.normal(0, 0.02 * (j // 3), 4).astype(F), 0, 1)
+            rois_in[n, j] = [min(bb[0], bb[2] - 0.05), min(bb[1], bb[3] - 0.05), bb[2], bb[3]]
+    rois_in = np.clip(rois_in, 0, 1).astype(F)
+    per_image, fg_frac = 16, 0.25
+    kfg, kbg = rng.random((N, R + Gn)).astype(F), rng.random((N, R + Gn)).astype(F)
+    kup = rng.random((N, per_image)).astype(F)
+    src = open("/root/reference/preprocessing/anchor_manipulator.py").read().split("\n")
+    line_of = {k: [i + 1 for i, ln in enumerate(src) if ln.strip().startswith(k + " = tf.cond")][0]
+               for k in ("fg_select_indices", "bg_select_indices", "final_keep_indices")}
+
+    def keyfn(mi, n, frames):  # which of ext_encode_rois' three shuffles is running: by the tf.cond line on the stack
+        lines = [ln for _, ln in frames]
+        if line_of["fg_select_indices"] in lines:
+            return kfg[mi]
+        if line_of["bg_select_indices"] in lines:
+            return kbg[mi]
+        assert line_of["final_keep_indices"] in lines
+        return kup[mi]
+
+    tf.SHUFFLE_KEYS = keyfn
+    with np.errstate(all="ignore"):
+        pr, pt, pl, ps = enc2.ext_encode_rois(tf.constant(rois_in), tf.constant(gl), tf.constant(gt), per_image, fg_frac, 0.1)
+    out["roi_in"], out["roi_kfg"], out["roi_kbg"], out["roi_kup"] = rois_in, kfg, kbg, kup
+    out["roi_out"], out["roi_targets"], out["roi_labels"], out["roi_scores"] = (np.asarray(v) for v in (pr, pt, pl, ps))
     path = os.path.join(HERE, "tfpath_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, "%.0f KB" % (os.path.getsize(path) / 1024))

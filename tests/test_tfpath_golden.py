@@ -50,6 +50,39 @@ def test_detection_chain_and_matching():
     assert int((G["det_out_scores"] > 0).sum()) > 100 and int(G["match_tp"].sum()) > 0
 
 
+def test_training_targets_and_roi_sampling():
+    """encode_all_anchors and ext_encode_rois (matching, target encoding, fg/bg sampling with the injected shuffles).
+    Targets of unmatched boxes: the reference multiplies by the 0/1 mask (-0.0 for negative encodings), the oracle
+    and the kernels write +0.0 -- equal as numbers, so values are compared numerically and matched rows bit for bit."""
+    from oracle import train as ot
+    anchors = P.layer_anchors((160, 160), (10, 10), SCALES, EXTRA, RATIOS, 16)
+    y, x, h, w = anchors
+    fm, A = 10, 22
+    cy = np.broadcast_to(y[:, :, None], (fm, fm, A)).reshape(-1).astype(F)
+    cx = np.broadcast_to(x[:, :, None], (fm, fm, A)).reshape(-1).astype(F)
+    hh = np.broadcast_to(h[None, None, :], (fm, fm, A)).reshape(-1).astype(F)
+    ww = np.broadcast_to(w[None, None, :], (fm, fm, A)).reshape(-1).astype(F)
+    ref = np.stack([cy, cx, hh, ww], -1)
+    pts = np.stack([cy - hh / F(2), cx - ww / F(2), cy + hh / F(2), cx + ww / F(2)], -1)
+    gt, gl = G["tgt_gt"], G["tgt_gl"]
+    for n in range(2):
+        assert np.array_equal(bits(pts), bits(G["enc_points_%d" % n]))
+        l0, t0, s0 = ot.match_encode(pts, gt[n], gl[n], 0.0, 0.7, 0.3, ref_yxhw=ref)
+        assert np.array_equal(l0, G["enc_labels_%d" % n]) and (l0 > 0).sum() > 0 and (l0 < 0).sum() > 0
+        assert np.array_equal(bits(s0), bits(G["enc_scores_%d" % n]))
+        assert np.array_equal(t0, G["enc_targets_%d" % n])
+        assert np.array_equal(bits(t0[l0 > 0]), bits(G["enc_targets_%d" % n][l0 > 0]))
+        # RoI targets + sampling: ground-truth boxes are appended to the RoIs first (ext_encode_rois :352)
+        valid = gl[n] > 0
+        allr = np.concatenate([G["roi_in"][n], gt[n][valid]], 0)
+        l1, t1, s1 = ot.match_encode(allr, gt[n], gl[n], 0.1, 0.5, 0.5)
+        keep, _ = ot.sample_fg_bg(l1, s1, 0.0, int(np.rint(F(16) * F(0.25))), 16, G["roi_kfg"][n], G["roi_kbg"][n], G["roi_kup"][n])
+        assert np.array_equal(bits(allr[keep]), bits(G["roi_out"][n]))
+        assert np.array_equal(l1[keep], G["roi_labels"][n]) and (l1[keep] > 0).sum() == 4
+        assert np.array_equal(bits(s1[keep]), bits(G["roi_scores"][n]))
+        assert np.array_equal(t1[keep], G["roi_targets"][n])
+
+
 # ---- the CUDA path against the same goldens ---------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def cuda():
