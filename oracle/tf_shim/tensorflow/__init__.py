@@ -1,6 +1,6 @@
-"""A numpy-backed stand-in for the few dozen TensorFlow 1.x graph ops that the reference's *Python* helpers on the
-Light-Head R-CNN path use (preprocessing/anchor_manipulator.py, net/xception_body.py:41-218,402-448,
-utility/eval_helper.py), evaluated eagerly.  TEST INFRASTRUCTURE ONLY (like oracle/ref_shim for the C++ op): with this
+"""A numpy-backed stand-in for the few dozen TensorFlow 1.x graph ops that the reference's *Python* code on the
+Light-Head R-CNN path uses (preprocessing/anchor_manipulator.py, net/xception_body.py, net/resnet_v2.py,
+net/xdet_body.py, utility/eval_helper.py), evaluated eagerly; tf.variable_scope and tf.layers live in _layers.py.  TEST INFRASTRUCTURE ONLY (like oracle/ref_shim for the C++ op): with this
 directory first on sys.path, ``import tensorflow as tf`` inside the UNMODIFIED reference modules resolves here, so
 their own code can be run in this container to mint golden vectors (tests/golden/make_tfpath_golden.py).
 
@@ -133,9 +133,6 @@ def name_scope(*a, **k):
 @contextlib.contextmanager
 def device(*a, **k):
     yield
-
-
-variable_scope = name_scope
 
 
 def shape(x, name=None, out_type=None):
@@ -388,6 +385,8 @@ class _Any(object):
     """Attribute sink for module-level references the golden scripts never execute (initialisers, tf.layers, ...)."""
 
     def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
         return _Any()
 
     def __call__(self, *a, **k):
@@ -395,6 +394,8 @@ class _Any(object):
 
 
 def __getattr__(name):
+    if name.startswith("__"):
+        raise AttributeError(name)
     return _Any()
 
 
@@ -427,3 +428,53 @@ nn.top_k, nn.softmax = _top_k, _softmax
 image.non_max_suppression = _nms
 sys.modules.setdefault("tensorflow.nn", nn)
 sys.modules.setdefault("tensorflow.image", image)
+
+
+# ---- variable scopes + tf.layers (network builders; see _layers.py) ----------------------------------------------
+import importlib  # noqa: E402
+
+_layers = importlib.import_module(__name__ + "._layers")  # ('from . import' would hit the __getattr__ sink)
+
+layers = types.ModuleType("tensorflow.layers")
+for _n in ("conv2d", "separable_conv2d", "batch_normalization", "max_pooling2d", "dense"):
+    setattr(layers, _n, getattr(_layers, _n))
+sys.modules.setdefault("tensorflow.layers", layers)
+variable_scope, AUTO_REUSE = _layers.variable_scope, _layers.AUTO_REUSE
+add, subtract, multiply = _binary(np.add), _binary(np.subtract), _binary(np.multiply)
+
+
+def reduce_mean(x, axis=None, keepdims=False, name=None):
+    return _t(np.mean(_t(x), axis=axis, keepdims=keepdims, dtype=np.float64).astype(np.float32))
+
+
+def _relu(x, name=None):
+    return _t(np.maximum(_t(x), 0))
+
+
+nn.relu = _relu
+
+
+# ---- any other tensorflow.* import (tensorflow.contrib.framework..., tensorflow.python.ops...) resolves to an empty
+#      package of attribute sinks: modules that merely IMPORT such names at the top (net/depth_conv2d.py) load --------
+import importlib.abc  # noqa: E402
+import importlib.machinery  # noqa: E402
+
+
+class _SinkFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname.startswith("tensorflow."):
+            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        return None
+
+    def exec_module(self, module):
+        def sink(name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return _Any()
+        module.__getattr__ = sink
+
+
+sys.meta_path.append(_SinkFinder())
