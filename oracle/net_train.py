@@ -4,7 +4,13 @@ PyTorch-CPU fp32 graph + autograd.  TEST INFRASTRUCTURE ONLY.
 
 The discrete selections (RPN sample indices, sampled RoIs, OHEM indices) can be INJECTED so that gradients are
 compared on identical decisions (they are discontinuous in the bf16-vs-fp32 rounding); the selections themselves
-are checked separately and exactly (oracle/train.py vs the kernels).  parity unpinned (no TF, no reference tests)."""
+are checked separately and exactly (oracle/train.py vs the kernels).
+
+PINNED (forward) by the reference's own model_fn: tests/golden/make_trainstep_golden.py calls the unmodified
+lighr_head_model_fn in TRAIN mode under the numpy TensorFlow stand-in (oracle/tf_shim; the custom op bound to the
+reference's compiled PsRoIAlign) and tests/test_trainstep_golden.py holds this file to its RPN sample indices, RoI
+selection, OHEM indices and the three loss values.  Gradients are torch autograd over that forward; TensorFlow's own
+gradient code is not available offline, so the backward stays unpinned by the reference."""
 import numpy as np
 import torch
 

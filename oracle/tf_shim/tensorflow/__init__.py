@@ -113,7 +113,13 @@ def to_double(x):
     return cast(x, float64)
 
 
+NAMED = {}        # tf.identity(x, name=...) results by name (how the reference labels its loss tensors)
+GATHER_LOG = None  # a list -> every tf.gather call appends (params.shape, indices, axis)
+
+
 def identity(x, name=None):
+    if name is not None:
+        NAMED[name] = x
     return x
 
 
@@ -188,6 +194,8 @@ def slice(x, begin, size, name=None):  # noqa: A001
 
 
 def gather(params, indices, name=None, axis=0):
+    if GATHER_LOG is not None:
+        GATHER_LOG.append((np.shape(params), np.array(indices), axis))
     return _t(np.take(_t(params), np.asarray(indices).astype(np.int64), axis=axis))
 
 
@@ -372,8 +380,8 @@ def random_shuffle(value, seed=None, name=None):
         keys = np.arange(len(v), dtype=np.float32)
     elif callable(SHUFFLE_KEYS):
         frames, f = [], sys._getframe(1)
-        while f is not None and len(frames) < 6:
-            frames.append((f.f_code.co_name, f.f_lineno))
+        while f is not None and len(frames) < 8:
+            frames.append((f.f_code.co_name, f.f_lineno, f.f_code.co_filename))
             f = f.f_back
         keys = np.asarray(SHUFFLE_KEYS(MAP_INDEX, len(v), frames), np.float32)[:len(v)]
     else:
@@ -407,6 +415,10 @@ image = types.ModuleType("tensorflow.image")
 def _top_k(x, k=1, sorted=True, name=None):  # noqa: A002
     x = _t(x)
     k = int(np.asarray(k))
+    if x.ndim > 1:  # row-wise
+        rows = [_top_k(r, k) for r in x.reshape(-1, x.shape[-1])]
+        return (_t(np.stack([r[0] for r in rows]).reshape(x.shape[:-1] + (k,))),
+                _t(np.stack([r[1] for r in rows]).reshape(x.shape[:-1] + (k,))))
     order = np.lexsort((np.arange(x.shape[0]), -x.astype(np.float64)))[:k]   # descending, ties -> lower index
     return _t(x[order]), _t(order.astype(np.int32))
 
@@ -452,6 +464,112 @@ def _relu(x, name=None):
 
 
 nn.relu = _relu
+
+
+# ---- what the reference's TRAINING model_fn needs beyond the graph builders (light_head_rfcn_train.py:277-451) -----
+control_dependencies = name_scope
+
+
+def abs(x, name=None):  # noqa: A001
+    return _t(np.abs(_t(x)))
+
+
+def add_n(values, name=None):
+    total = _t(values[0])
+    for v in values[1:]:
+        total = _t(total + _t(v))
+    return total
+
+
+class _Variable(object):
+    def __init__(self, name, value):
+        self.name, self.value = name + ":0", value
+
+
+def trainable_variables():
+    return [_Variable(k, v) for k, v in _layers.VARIABLES.items() if not k.rsplit("/", 1)[-1].startswith("moving_")]
+
+
+def _log_softmax(logits):
+    z = np.asarray(logits, np.float64)
+    z = z - z.max(axis=-1, keepdims=True)
+    return z - np.log(np.exp(z).sum(axis=-1, keepdims=True))
+
+
+def _sparse_xent(labels=None, logits=None, name=None, _sentinel=None):
+    lp = _log_softmax(logits)
+    lab = np.asarray(labels).astype(np.int64)
+    return _t((-np.take_along_axis(lp, lab[..., None], axis=-1)[..., 0]).astype(np.float32))
+
+
+def _l2_loss(v, name=None):
+    a = np.asarray(v.value if isinstance(v, _Variable) else v, np.float64)
+    return _t(np.float32((a * a).sum() / 2))
+
+
+nn.sparse_softmax_cross_entropy_with_logits, nn.l2_loss = _sparse_xent, _l2_loss
+
+losses = types.ModuleType("tensorflow.losses")
+# weights = 1, reduction SUM_BY_NONZERO_WEIGHTS: the mean over all elements
+losses.sparse_softmax_cross_entropy = lambda labels, logits, **kw: _t(
+    np.float32(np.asarray(_sparse_xent(labels, logits), np.float64).mean()))
+losses.add_loss = lambda *a, **k: None
+
+estimator = types.ModuleType("tensorflow.estimator")
+
+
+class _ModeKeys(object):
+    TRAIN, EVAL, PREDICT = "train", "eval", "infer"
+
+
+class _EstimatorSpec(object):
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+estimator.ModeKeys, estimator.EstimatorSpec = _ModeKeys, _EstimatorSpec
+
+
+class _Flags(object):
+    """tf.app.flags: DEFINE_* record their defaults; OVERRIDES plays the command line."""
+    OVERRIDES = {}
+
+    class _Values(object):
+        pass
+
+    FLAGS = _Values()
+
+    @classmethod
+    def _define(cls, name, default, doc=None, **kw):
+        setattr(cls.FLAGS, name, cls.OVERRIDES.get(name, default))
+
+    DEFINE_integer = DEFINE_float = DEFINE_string = DEFINE_boolean = DEFINE_bool = _define
+
+
+app = types.ModuleType("tensorflow.app")
+app.flags = _Flags
+train = types.ModuleType("tensorflow.train")
+train.get_or_create_global_step = lambda: _t(np.int64(0))
+train.piecewise_constant = lambda x, boundaries, values, name=None: _t(
+    np.float32(values[int(np.searchsorted(np.asarray(boundaries), np.asarray(x), side="left"))]))
+
+
+def _train_sink(name):
+    if name.startswith("__"):
+        raise AttributeError(name)
+    return _Any()
+
+
+for _m in (train, nn, image, layers, losses, estimator, app):  # PEP 562: names not defined above resolve to sinks
+    _m.__getattr__ = _train_sink
+OP_LIBRARIES = {}  # path suffix -> object standing for the loaded custom-op module (tf.load_op_library)
+
+
+def load_op_library(path):
+    for k, v in OP_LIBRARIES.items():
+        if path.endswith(k):
+            return v
+    return _Any()
 
 
 # ---- any other tensorflow.* import (tensorflow.contrib.framework..., tensorflow.python.ops...) resolves to an empty

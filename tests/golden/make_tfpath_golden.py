@@ -141,7 +141,7 @@ def main():
                for k in ("fg_select_indices", "bg_select_indices", "final_keep_indices")}
 
     def keyfn(mi, n, frames):  # which of ext_encode_rois' three shuffles is running: by the tf.cond line on the stack
-        lines = [ln for _, ln in frames]
+        lines = [f[1] for f in frames]
         if line_of["fg_select_indices"] in lines:
             return kfg[mi]
         if line_of["bg_select_indices"] in lines:
