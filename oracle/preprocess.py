@@ -1,7 +1,10 @@
 """CPU oracle (TEST INFRASTRUCTURE ONLY) of the eval input pipeline: numpy fp32 restatement of
 ``light_head_preprocess_for_test`` (preprocessing/common_preprocessing.py:443-458, WARP_RESIZE) with TF r1.6's
 ResizeBilinear (legacy sampling, align_corners=False; tensorflow/core/kernels/resize_bilinear_op.cc, restated from
-its published algorithm: TF is not installable offline -> parity unpinned)."""
+its published algorithm: TF is not installable offline).  Pinned around that kernel by the reference's own
+preprocessing/common_preprocessing.py run under the numpy TensorFlow stand-in (tests/golden/make_preprocess_golden.py,
+tests/test_preprocess_golden.py): dtype conversion, whitening constants, warp resize, NCHW transpose, difficult-box
+removal, bbox_img; the stand-in's resize is an independent float64 matrix formulation of the same sampling rule."""
 import numpy as np
 
 F = np.float32

@@ -436,6 +436,40 @@ def _nms(boxes, scores, max_output_size, iou_threshold=0.5, name=None):
     return _t(idx.astype(np.int32))
 
 
+def _convert_image_dtype(x, dtype, saturate=False, name=None):
+    """integer -> float: cast, then multiply by 1 / dtype.max (the documented rule)."""
+    x = _t(x)
+    if np.issubdtype(x.dtype, np.integer) and np.issubdtype(_np(dtype), np.floating):
+        return _t((x.astype(np.float64) * (1.0 / np.iinfo(x.dtype).max)).astype(_np(dtype)))
+    return _t(x.astype(_np(dtype)))
+
+
+class _ResizeMethod(object):
+    BILINEAR, NEAREST_NEIGHBOR, BICUBIC, AREA = 0, 1, 2, 3
+
+
+def _lerp_matrix(n_out, n_in):
+    """[n_out, n_in] float64 interpolation matrix of TF r1.6 ResizeBilinear, align_corners=False: output i samples
+    the input at i * (n_in / n_out) (no half-pixel offset), between floor() and min(floor() + 1, n_in - 1)."""
+    m = np.zeros((n_out, n_in))
+    for i in builtins_range(n_out):
+        pos = i * (np.float32(n_in) / np.float32(n_out))
+        lo = int(np.floor(pos))
+        hi = min(lo + 1, n_in - 1)
+        m[i, lo] += 1.0 - (pos - lo)
+        m[i, hi] += pos - lo
+    return m
+
+
+def _resize_images(images, size, method=_ResizeMethod.BILINEAR, align_corners=False):
+    assert method == _ResizeMethod.BILINEAR and not align_corners
+    x = np.asarray(_t(images), np.float64)  # [N,H,W,C]
+    ho, wo = int(np.asarray(size[0])), int(np.asarray(size[1]))
+    ry, rx = _lerp_matrix(ho, x.shape[1]), _lerp_matrix(wo, x.shape[2])
+    return _t(np.einsum("ih,nhwc,jw->nijc", ry, x, rx).astype(np.float32))
+
+
+image.convert_image_dtype, image.resize_images, image.ResizeMethod = _convert_image_dtype, _resize_images, _ResizeMethod
 nn.top_k, nn.softmax = _top_k, _softmax
 image.non_max_suppression = _nms
 sys.modules.setdefault("tensorflow.nn", nn)
