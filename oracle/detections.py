@@ -2,9 +2,11 @@
 post-processing of the reference's ``bboxes_eval`` (light_head_rfcn_eval.py:263-290): a numpy fp32 restatement of the
 ``utility/eval_helper.py`` functions it chains, one function per reference function, operation order kept.
 
-parity unpinned: TF 1.6 is not installable offline and the reference holds no tests / fixtures for these functions;
-``tf.nn.top_k`` (descending, ties -> lower index) and ``tf.image.non_max_suppression`` (TF r1.6 NonMaxSuppressionV2)
-are restated in oracle/proposals.py and reused here.
+Pinned by the reference's own Python: utility/eval_helper.py is run unmodified under the numpy TensorFlow stand-in
+(oracle/tf_shim) to mint tests/golden/tfpath_golden.npz and tests/test_tfpath_golden.py holds this file (and the CUDA
+path) to it bit for bit.  Two TensorFlow-core kernels inside that run are restatements, not TensorFlow's code:
+``tf.nn.top_k`` (descending, ties -> lower index) and ``tf.image.non_max_suppression`` (TF r1.6 NonMaxSuppressionV2),
+both in oracle/proposals.py and reused here -- those two stay unpinned.
 """
 import numpy as np
 

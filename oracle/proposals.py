@@ -1,9 +1,11 @@
 """TEST INFRASTRUCTURE ONLY -- numpy fp32 restatement of the RPN proposal path.
 
-PARITY UNPINNED by reference tests: the reference has no tests for this path and its arithmetic
-lives in TensorFlow 1.6 (not vendored, not installable offline), so this restatement of the graph
-code IS the pin.  Each function cites the reference lines it follows; every operation is done in
-float32 in the reference's order (e.g. ``ymin + h / 2.`` and not ``(ymin + ymax) / 2``).
+Pinned by the reference's own Python: preprocessing/anchor_manipulator.py and net/xception_body.py are run
+unmodified under the numpy TensorFlow stand-in (oracle/tf_shim) to mint tests/golden/tfpath_golden.npz, and
+tests/test_tfpath_golden.py holds this file (and the CUDA path) to it bit for bit.  Not TensorFlow's own code in
+that run, hence still unpinned: tf.nn.top_k, tf.image.non_max_suppression (TF-core kernels, restated below from
+TF r1.6) and tf.random_shuffle (injected keys).  Each function cites the reference lines it follows; every
+operation is done in float32 in the reference's order (e.g. ``ymin + h / 2.`` and not ``(ymin + ymax) / 2``).
 
   AnchorCreator.get_layer_anchors    preprocessing/anchor_manipulator.py:698-743
   AnchorEncoder.decode_all_anchors   preprocessing/anchor_manipulator.py:641-669  (center2point :111-112)

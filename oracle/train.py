@@ -4,8 +4,10 @@ TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.
 Follows preprocessing/anchor_manipulator.py: areas/intersection/iou_matrix :22-46, do_dual_max_match :48-94,
 AnchorEncoder.encode_anchor :118-171, ext_encode_rois :337-432 and light_head_rfcn_train.py select_samples
 :321-358.  tf.random_shuffle(tf.range(n)) is replaced on both sides by the stable argsort of an injected key
-array (keys[:n]).  parity unpinned: the reference holds no tests/fixtures for these functions and TF 1.6 cannot be
-installed here; this restatement is the pin."""
+array (keys[:n]).  Pinned by the reference's own Python run under the numpy TensorFlow stand-in (oracle/tf_shim):
+encode_all_anchors / ext_encode_rois goldens in tests/golden/tfpath_golden.npz, select_samples inside the whole
+training model_fn in tests/golden/trainstep_golden.npz (tests/test_tfpath_golden.py, tests/test_trainstep_golden.py).
+One documented deviation: unmatched boxes get +0.0 targets where the reference's mask multiplication gives -0.0."""
 import numpy as np
 
 f32 = np.float32

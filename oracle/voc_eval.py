@@ -1,7 +1,9 @@
 """CPU oracle (TEST INFRASTRUCTURE ONLY) for the TP/FP matching and the VOC AP arithmetic of the reference's eval
 path: loop-level restatement of ``bboxes_jaccard`` / ``bboxes_matching`` (utility/eval_helper.py:671-788) in numpy
 fp32, and an independent textbook VOC AP (the well-known ``voc_ap`` of the PASCAL devkit / py-faster-rcnn) used to
-cross-check ``utility/metrics.py``'s formulas.  parity unpinned by the reference (no tests / fixtures there)."""
+cross-check ``utility/metrics.py``'s formulas.  Pinned: bboxes_matching by the reference's own eval_helper.py under
+the numpy TensorFlow stand-in (tests/golden/tfpath_golden.npz), the AP arithmetic by the reference's own
+voc_eval.py:98-130 (tests/golden/voc_ap_golden.npz)."""
 import numpy as np
 
 F = np.float32
