@@ -518,10 +518,19 @@ def add_n(values, name=None):
 class _Variable(object):
     def __init__(self, name, value):
         self.name, self.value = name + ":0", value
+        self.op = types.SimpleNamespace(name=name)
 
 
 def trainable_variables():
     return [_Variable(k, v) for k, v in _layers.VARIABLES.items() if not k.rsplit("/", 1)[-1].startswith("moving_")]
+
+
+class GraphKeys(object):
+    TRAINABLE_VARIABLES, UPDATE_OPS, GLOBAL_VARIABLES = "trainable_variables", "update_ops", "variables"
+
+
+def get_collection(key, scope=None):
+    return trainable_variables() if key == GraphKeys.TRAINABLE_VARIABLES else []
 
 
 def _log_softmax(logits):
@@ -584,6 +593,30 @@ app = types.ModuleType("tensorflow.app")
 app.flags = _Flags
 train = types.ModuleType("tensorflow.train")
 train.get_or_create_global_step = lambda: _t(np.int64(0))
+CHECKPOINT_TENSORS = None  # a set of names -> what tf.train.NewCheckpointReader(...).has_tensor answers from
+SAVERS = []                # var_list of every tf.train.Saver constructed
+
+
+class _CheckpointReader(object):
+    def __init__(self, path):
+        self.path = path
+
+    def has_tensor(self, name):
+        return CHECKPOINT_TENSORS is None or name in CHECKPOINT_TENSORS
+
+
+class _Saver(object):
+    def __init__(self, var_list=None, reshape=False, **kw):
+        SAVERS.append(var_list)
+
+    def build(self):
+        return None
+
+
+train.latest_checkpoint = lambda checkpoint_dir, latest_filename=None: None
+train.NewCheckpointReader, train.Saver = _CheckpointReader, _Saver
+gfile = types.ModuleType("tensorflow.gfile")
+gfile.IsDirectory = lambda path: False
 train.piecewise_constant = lambda x, boundaries, values, name=None: _t(
     np.float32(values[int(np.searchsorted(np.asarray(boundaries), np.asarray(x), side="left"))]))
 
@@ -594,7 +627,7 @@ def _train_sink(name):
     return _Any()
 
 
-for _m in (train, nn, image, layers, losses, estimator, app):  # PEP 562: names not defined above resolve to sinks
+for _m in (train, nn, image, layers, losses, estimator, app, gfile):  # PEP 562: names not defined above resolve to sinks
     _m.__getattr__ = _train_sink
 OP_LIBRARIES = {}  # path suffix -> object standing for the loaded custom-op module (tf.load_op_library)
 

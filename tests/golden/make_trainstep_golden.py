@@ -150,6 +150,21 @@ def main():
                  "head_location_loss", "head_loss", "total_loss"):
         out[name] = np.asarray(tf.NAMED[name], np.float64)
     assert float(spec.loss) == float(out["total_loss"])
+    # ---- what get_init_fn_for_scaffold (utility/train_helper.py:5-72) restores for this graph under the train
+    #      script's default flags: the model_fn above already built one Saver through tf.train.Scaffold(init_fn=...);
+    #      a second call with a checkpoint that lacks some tensors exercises ignore_missing_vars -------------------
+    assert len(tf.SAVERS) == 1
+    flags = lt.FLAGS
+    restore_all = {k: v.op.name for k, v in tf.SAVERS[0].items()}
+    present = sorted(restore_all)
+    tf.CHECKPOINT_TENSORS = set(present[::2])
+    lt.train_helper.get_init_fn_for_scaffold(flags)
+    restore_half = {k: v.op.name for k, v in tf.SAVERS[1].items()}
+    out["restore"] = np.array(json.dumps(dict(
+        model_scope=flags.model_scope, checkpoint_model_scope=flags.checkpoint_model_scope,
+        checkpoint_exclude_scopes=flags.checkpoint_exclude_scopes, ignore_missing_vars=flags.ignore_missing_vars,
+        all=restore_all, checkpoint_tensors=sorted(tf.CHECKPOINT_TENSORS), half=restore_half)))
+    print("restore map:", len(restore_all), "variables;", len(restore_half), "with half the checkpoint missing")
     out["meta"] = np.array(json.dumps(dict(
         seed=2018, size=SIZE, feature_map=fm, roi_one_image=ROI_ONE_IMAGE, params=PARAMS, thresholds=THRESHOLDS,
         variables=[[k, list(v.shape)] for k, v in _layers.VARIABLES.items()])))

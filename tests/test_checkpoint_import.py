@@ -113,3 +113,30 @@ def test_checkpoint_to_state_dict(tmp_path):
     sd = th.checkpoint_to_state_dict(prefix, "xception_lighthead", "xception")
     assert set(sd) == {k for k in tensors if not k.endswith("Momentum") and k != "global_step"}
     assert np.array_equal(sd["xception_lighthead/final_head/fc_cls/bias"], tensors["xception_lighthead/final_head/fc_cls/bias"])
+
+
+def test_restore_map_matches_reference_init_fn(tmp_path):
+    """The {checkpoint name: model variable} map that the reference's own get_init_fn_for_scaffold
+    (utility/train_helper.py:5-72) hands to tf.train.Saver for the real Xception graph under the train script's
+    default flags -- captured by running the reference unmodified under the numpy TensorFlow stand-in
+    (tests/golden/make_trainstep_golden.py) -- against the product's rules, including ignore_missing_vars."""
+    import json
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "trainstep_golden.npz"))
+    r = json.loads(str(G["restore"]))
+    meta = json.loads(str(G["meta"]))
+    # the reference restores TRAINABLE variables only (tf.GraphKeys.TRAINABLE_VARIABLES): no moving statistics
+    trainable = [n for n, _ in meta["variables"] if not n.rsplit("/", 1)[-1].startswith("moving_")]
+    m = th.variables_to_restore(trainable, r["model_scope"], r["checkpoint_model_scope"], r["checkpoint_exclude_scopes"])
+    assert m == r["all"] and len(m) == 154
+    assert not any("/rpn_head/" in v or "/large_sep_feature/" in v or "/final_head/" in v for v in m.values())
+    # a checkpoint holding every other tensor: the missing ones are skipped, the rest restored under model names
+    shapes = {n: tuple(s) for n, s in meta["variables"]}
+    rng = np.random.default_rng(4)
+    tensors = {k: rng.standard_normal(shapes[r["all"][k]]).astype(np.float32) for k in r["checkpoint_tensors"]}
+    prefix = str(tmp_path / "xception_model.ckpt")
+    bw.write_bundle(prefix, tensors)
+    sd = th.load_state_dict(prefix, trainable, r["model_scope"], r["checkpoint_model_scope"],
+                            r["checkpoint_exclude_scopes"], ignore_missing_vars=r["ignore_missing_vars"], shapes=shapes)
+    assert set(sd) == set(r["half"].values()) and len(sd) == 77
+    for ck, name in r["half"].items():
+        assert np.array_equal(np.asarray(sd[name]), tensors[ck])
