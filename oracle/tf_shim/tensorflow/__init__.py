@@ -80,7 +80,8 @@ class Tensor(np.ndarray):
 def _t(x, dtype=None):
     """convert_to_tensor: python floats -> float32, python ints -> int32, arrays keep their dtype."""
     dtype = _np(dtype)
-    if isinstance(x, np.ndarray):
+    if isinstance(x, (np.ndarray, np.generic)):  # tensors (and the numpy scalars reductions return) keep their dtype
+        x = np.asarray(x)
         a = x if dtype is None else x.astype(dtype)
     else:
         a = np.asarray(x)
@@ -404,6 +405,8 @@ class _Any(object):
 def __getattr__(name):
     if name.startswith("__"):
         raise AttributeError(name)
+    if name == "tuple":
+        return _tf_tuple
     return _Any()
 
 
@@ -637,6 +640,84 @@ def load_op_library(path):
         if path.endswith(k):
             return v
     return _Any()
+
+
+# ---- tensorflow.python.* internals that utility/metrics.py reaches for: local variables (keyed by scope/name so
+#      that calling streaming_tp_fp_arrays once per batch accumulates, as running its update ops would), assigns,
+#      cumsum / scan / reverse ------------------------------------------------------------------------------------
+LOCAL_VARIABLES = {}
+
+
+class Variable(object):
+    def __new__(cls, initial_value=None, name=None, trainable=True, collections=None, validate_shape=True, **kw):
+        key = _layers._full(name)
+        if key not in LOCAL_VARIABLES:
+            self = object.__new__(cls)
+            self.name, self.value = key, _t(initial_value)
+            LOCAL_VARIABLES[key] = self
+        return LOCAL_VARIABLES[key]
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(self.value) if dtype is None else np.asarray(self.value).astype(dtype)
+
+
+def _assign(ref, value, validate_shape=None, name=None):
+    ref.value = _t(value).astype(ref.value.dtype)
+    return ref.value
+
+
+def _assign_add(ref, value, name=None):
+    ref.value = _t(ref.value + _t(value).astype(ref.value.dtype))
+    return ref.value
+
+
+def cumsum(x, axis=0, name=None):
+    return _t(np.cumsum(_t(x), axis=axis))
+
+
+def reverse(x, axis, name=None):
+    return _t(np.flip(_t(x), axis=tuple(axis)))
+
+
+def scan(fn, elems, initializer=None, **kw):
+    e = _t(elems)
+    acc, outs = (e[0], [e[0]]) if initializer is None else (initializer, [])
+    for v in e[(1 if initializer is None else 0):]:
+        acc = fn(acc, v)
+        outs.append(acc)
+    return _t(np.stack([np.asarray(o) for o in outs]))
+
+
+def _tf_tuple(tensors, name=None):  # tf.tuple: served by the module __getattr__ (keeps the builtin usable here)
+    return list(tensors)
+
+
+def _module(fullname, **attrs):
+    m = types.ModuleType(fullname)
+    m.__dict__.update(attrs)
+    m.__getattr__ = _train_sink
+    m.__path__ = []
+    sys.modules[fullname] = m
+    parent, _, leaf = fullname.rpartition(".")
+    if parent != "tensorflow":
+        setattr(sys.modules[parent], leaf, m)  # 'from parent import leaf' must not fall into the parent's sink
+    return m
+
+
+_this = sys.modules[__name__]
+_module("tensorflow.python")
+_module("tensorflow.python.framework")
+_module("tensorflow.python.ops")
+_module("tensorflow.python.framework.dtypes", float32=float32, float64=float64, int32=int32, int64=int64, bool=bool)
+_module("tensorflow.python.framework.ops", name_scope=name_scope, convert_to_tensor=convert_to_tensor,
+        control_dependencies=control_dependencies, GraphKeys=GraphKeys, add_to_collections=lambda *a, **k: None)
+_module("tensorflow.python.ops.array_ops", zeros=zeros, shape=shape, unstack=unstack)
+_module("tensorflow.python.ops.math_ops", greater=greater, divide=divide,
+        to_int64=lambda x, name=None: cast(x, int64), to_float=lambda x, name=None: cast(x, float32))
+_module("tensorflow.python.ops.state_ops", assign=_assign, assign_add=_assign_add)
+_module("tensorflow.python.ops.variable_scope", variable_scope=variable_scope)
+_module("tensorflow.python.ops.variables", Variable=Variable)
+GraphKeys.LOCAL_VARIABLES = "local_variables"
 
 
 # ---- any other tensorflow.* import (tensorflow.contrib.framework..., tensorflow.python.ops...) resolves to an empty

@@ -52,3 +52,28 @@ def test_ap_matches_the_reference_voc_ap_golden():
         assert abs(M.average_precision_voc12(p, r) - float(g["ap12_%d" % i])) < 1e-12, i
         assert abs(ov.voc_ap(r, p, True) - float(g["ap07_%d" % i])) < 1e-12
         assert abs(ov.voc_ap(r, p, False) - float(g["ap12_%d" % i])) < 1e-12
+
+
+def test_streaming_metrics_match_reference_metrics_py():
+    """Goldens from the reference's own utility/metrics.py run under the numpy TensorFlow stand-in
+    (tests/golden/make_metrics_golden.py), chained as bboxes_eval chains them: accumulate over 7 images and 4 classes
+    (zero-padded scores, sub-threshold scores, neither-TP-nor-FP detections, a never-correct class), then
+    precision / recall, AP07, AP12 per class and the mAPs."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics_golden.npz"))
+    classes = [int(c) for c in G["classes"]]
+    state = None
+    for i in range(int(G["images"])):
+        args = [{c: G["in_%d_%d_%s" % (i, c, k)] for c in classes} for k in ("n", "tp", "fp", "scores")]
+        state = M.streaming_tp_fp_arrays(*args, state=state)
+    for c in classes:
+        nobj, ndet, tp, fp, sc = state[c].value()
+        assert (nobj, ndet) == (int(G["acc_%d_nobjects" % c]), int(G["acc_%d_ndetections" % c]))
+        assert np.array_equal(tp, G["acc_%d_tp" % c]) and np.array_equal(fp, G["acc_%d_fp" % c])
+        assert np.array_equal(sc.view(np.int32), G["acc_%d_scores" % c].view(np.int32))
+        p, r = M.precision_recall(nobj, ndet, tp, fp, sc)
+        assert np.abs(p - G["prec_%d" % c]).max() < 1e-15 and np.abs(r - G["rec_%d" % c]).max() < 1e-15
+        assert abs(M.average_precision_voc07(p, r) - float(G["ap07_%d" % c])) < 1e-12
+        assert abs(M.average_precision_voc12(p, r) - float(G["ap12_%d" % c])) < 1e-12
+    assert abs(M.voc_map(state, True)[0] - float(G["map07"])) < 1e-12
+    assert abs(M.voc_map(state, False)[0] - float(G["map12"])) < 1e-12
