@@ -330,7 +330,7 @@ def builtins_bool(x):
 MAP_INDEX = 0  # element index of the innermost running tf.map_fn (read by random_shuffle)
 
 
-def map_fn(fn, elems, dtype=None, back_prop=True, infer_shape=True, parallel_iterations=None, name=None):
+def map_fn(fn, elems, dtype=None, back_prop=True, infer_shape=True, parallel_iterations=None, name=None, **kw):
     global MAP_INDEX
     multi = isinstance(elems, (list, tuple))
     n = len(elems[0]) if multi else len(elems)
