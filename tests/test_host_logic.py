@@ -71,3 +71,29 @@ def test_oracle_detection_chain_small_case():
     assert s[1][0] == np.float32(0.9) and not s[1][1:].any() and s[1].shape == (200,)
     assert np.array_equal(b[1][0], boxes[0]) and not b[1][1:].any()
     assert s[2][0] == np.float32(0.7) and np.array_equal(b[2][0], boxes[2])
+
+
+def test_flag_names_and_defaults_match_reference_scripts():
+    """tests/golden/flags_golden.json: what tf.app.flags.DEFINE_* record when the reference's train / eval scripts are
+    imported unmodified under the numpy TensorFlow stand-in.  The drop-in contract: same flag names, same
+    defaults.  Deviations, both deliberate: data_format (NHWC is the kernels' native layout; the NCHW contract is kept
+    at the op boundary) and the extra flags backbone / precision / resnet_layers."""
+    import json
+    import os
+    from xdet_b200 import light_head_rfcn_eval as pe
+    from xdet_b200 import light_head_rfcn_train as pt
+    with open(os.path.join(os.path.dirname(__file__), "golden", "flags_golden.json")) as f:
+        gold = json.load(f)
+    for which, mod, extras in (("train", pt, {"backbone", "resnet_layers"}), ("eval", pe, {"backbone", "precision"})):
+        mine, ref = mod.make_params(), gold[which]
+        assert set(mine) - set(ref) == extras, (which, sorted(set(mine) - set(ref)))
+        assert set(ref) - set(mine) == set(), (which, sorted(set(ref) - set(mine)))
+        diff = {k for k in ref if mine[k] != ref[k]}
+        assert diff == {"data_format"}, (which, {k: (mine[k], ref[k]) for k in diff})
+        assert ref["data_format"] == "channels_first" and mine["data_format"] == "channels_last"
+        # ... and the launchers accept every one of them on the command line
+        ap = mod.arg_parser()
+        args = ap.parse_args(["--rpn_nms_thres", "0.6", "--run_on_cloud", "false", "--model_scope", "m"])
+        assert args.rpn_nms_thres == 0.6 and args.run_on_cloud is False and args.model_scope == "m"
+        assert all(hasattr(args, k) for k in ref)
+    assert pt.arg_parser().parse_args(["--resnet_layers", "1,1,1,1", "--train_epochs", "3"]).resnet_layers == (1, 1, 1, 1)

@@ -25,11 +25,12 @@ from .preprocessing import anchor_manipulator
 
 # flag name -> default (light_head_rfcn_eval.py:41-139; data/summary/checkpoint flags kept for completeness)
 _DEFAULTS = dict(
-    num_readers=8, num_preprocessing_threads=24, num_cpu_threads=0, gpu_memory_fraction=1.,
+    num_readers=16, num_preprocessing_threads=48, num_cpu_threads=0, gpu_memory_fraction=1.,
     data_dir='../PASCAL/VOC_TF/VOC2007TEST_TF/', dataset_name='pascalvoc_2007', num_classes=21,
-    model_dir='./logs_light/', log_every_n_steps=10, save_summary_steps=500, dataset_split_name='test',
-    debug_dir='./Debug_light', train_image_size=480, resnet_size=50, data_format='channels_last',
-    select_threshold=0.01, min_size=4., nms_threshold=0.3, nms_topk_percls=200, nms_topk=200, fg_ratio=0.25,
+    model_dir='./logs_light/', log_every_n_steps=10, save_summary_steps=100, dataset_split_name='test',
+    debug_dir='./Debug_light/', train_image_size=480, resnet_size=50, roi_one_image=64,
+    data_format='channels_last',
+    select_threshold=0.01, nms_threshold=0.3, nms_topk_percls=200, nms_topk=200, fg_ratio=0.25,
     match_threshold=0.53, neg_threshold_high=0.5, neg_threshold_low=0., rpn_anchors_per_image=256,
     rpn_pre_nms_top_n=5000, rpn_post_nms_top_n=1000, rpn_min_size=16 * 1. / 480, rpn_nms_thres=0.7,
     rpn_fg_ratio=0.5, rpn_match_threshold=0.7, rpn_neg_threshold=0.3, weight_decay=0.0002,
@@ -229,7 +230,8 @@ class LightHeadRFCN(object):
         return out
 
 
-def main(argv=None):
+def arg_parser():
+    """The reference's flags (light_head_rfcn_eval.py:41-139), same names and defaults, as ``--name value``."""
     ap = argparse.ArgumentParser(description="Light-Head R-CNN inference on synthetic VOC-shaped tensors")
     for k, v in _DEFAULTS.items():
         if isinstance(v, bool):
@@ -237,7 +239,11 @@ def main(argv=None):
         else:
             ap.add_argument("--" + k, type=type(v), default=v)
     ap.add_argument("--batch_size", type=int, default=8)
-    args = ap.parse_args(argv)
+    return ap
+
+
+def main(argv=None):
+    args = arg_parser().parse_args(argv)
     params = make_params(**{k: getattr(args, k) for k in _DEFAULTS})
     model = LightHeadRFCN(params)
     g = torch.Generator(device="cuda").manual_seed(1)

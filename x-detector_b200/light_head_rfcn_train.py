@@ -30,7 +30,7 @@ from .ops import conv as conv_ops
 from .ops import train as T
 from .preprocessing import anchor_manipulator
 
-# flag name -> default (light_head_rfcn_train.py:38-170; data/summary/checkpoint flags omitted)
+# flag name -> default (light_head_rfcn_train.py:38-170)
 _DEFAULTS = dict(
     num_classes=21, batch_size=8, data_format='channels_last', train_image_size=480, resnet_size=50,
     match_threshold=0.53, neg_threshold_high=0.5, neg_threshold_low=0., fg_ratio=0.25, roi_one_image=64,
@@ -38,6 +38,16 @@ _DEFAULTS = dict(
     rpn_nms_thres=0.7, rpn_fg_ratio=0.5, rpn_match_threshold=0.7, rpn_neg_threshold=0.3, using_ohem=True,
     ohem_roi_one_image=32, weight_decay=0.0002, momentum=0.9, learning_rate=1e-3, end_learning_rate=1e-4,
     decay_boundaries='60000, 80000', lr_decay_factors='1, 0.8, 0.1', model_scope='xception_lighthead',
+    # data / summary / checkpoint flags: kept with the reference's defaults (the synthetic-tensor launcher ignores
+    # the data ones; the checkpoint ones feed utility/train_helper.py)
+    num_readers=16, num_preprocessing_threads=48, num_cpu_threads=0, gpu_memory_fraction=1.0,
+    data_dir='../PASCAL/VOC_TF/VOC0712TF/', dataset_name='pascalvoc_0712', dataset_split_name='train',
+    model_dir='./logs_light/', log_every_n_steps=10, save_summary_steps=500, save_checkpoints_secs=7200,
+    train_epochs=None, nms_threshold=0.3, decay_steps=1000, learning_rate_decay_factor=0.96,
+    checkpoint_path='./model/xception', checkpoint_model_scope='',
+    checkpoint_exclude_scopes='xception_lighthead/rpn_head, xception_lighthead/large_sep_feature, xception_lighthead/final_head',
+    ignore_missing_vars=True, run_on_cloud=True, cloud_checkpoint_path='xception_model/xception_model.ckpt',
+    # not a reference flag: which backbone builder to use
     backbone='resnet50',
     # not a reference flag: blocks per block_layer of the ResNet v2 composition (resnet_size 50 = 3,4,6,3)
     resnet_layers=(3, 4, 6, 3),
@@ -649,13 +659,26 @@ def synthetic_batch(params, batch, seed, device="cuda", max_gt=6):
     return to(images), to(gt), to(gl), {k: to(v) for k, v in keys.items()}
 
 
-def main(argv=None):
+def arg_parser():
+    """The reference's flags (light_head_rfcn_train.py:38-168), same names and defaults, as ``--name value``."""
     import argparse
     ap = argparse.ArgumentParser(description="Light-Head R-CNN training steps on synthetic VOC-shaped tensors")
-    ap.add_argument("--batch_size", type=int, default=8)
+    for k, v in _DEFAULTS.items():
+        if isinstance(v, bool):
+            ap.add_argument("--" + k, type=lambda s: s.lower() in ("1", "true", "yes"), default=v)
+        elif isinstance(v, tuple):
+            ap.add_argument("--" + k, type=lambda s: tuple(int(t) for t in s.split(",")), default=v)
+        elif v is None:
+            ap.add_argument("--" + k, type=int, default=None)
+        else:
+            ap.add_argument("--" + k, type=type(v), default=v)
     ap.add_argument("--steps", type=int, default=3)
-    args = ap.parse_args(argv)
-    params = make_params(batch_size=args.batch_size)
+    return ap
+
+
+def main(argv=None):
+    args = arg_parser().parse_args(argv)
+    params = make_params(**{k: getattr(args, k) for k in _DEFAULTS})
     tr = LightHeadTrainer(params)
     batch = synthetic_batch(params, args.batch_size, seed=3)
     for i in range(args.steps):
