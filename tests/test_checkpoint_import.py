@@ -140,3 +140,36 @@ def test_restore_map_matches_reference_init_fn(tmp_path):
     assert set(sd) == set(r["half"].values()) and len(sd) == 77
     for ck, name in r["half"].items():
         assert np.array_equal(np.asarray(sd[name]), tensors[ck])
+
+
+def test_reference_named_entry_points(tmp_path):
+    """get_init_fn_for_scaffold / get_latest_checkpoint_for_evaluate under the reference's names and flag object."""
+    import types
+    rng = np.random.default_rng(2)
+    names = ["xception_lighthead/block1_conv1/kernel", "xception_lighthead/rpn_head/conv2d/kernel"]
+    tensors = {"block1_conv1/kernel": rng.standard_normal((3, 3, 3, 32)).astype(np.float32)}
+    pre = tmp_path / "pretrained"
+    pre.mkdir()
+    bw.write_bundle(str(pre / "xception_model.ckpt"), tensors)
+    logs = tmp_path / "logs"
+    logs.mkdir()
+    flags = types.SimpleNamespace(checkpoint_path=str(pre / "xception_model.ckpt"), run_on_cloud=False, data_dir="",
+                                  cloud_checkpoint_path="", model_dir=str(logs), model_scope="xception_lighthead",
+                                  checkpoint_model_scope="", checkpoint_exclude_scopes="xception_lighthead/rpn_head",
+                                  ignore_missing_vars=True)
+    init_fn = th.get_init_fn_for_scaffold(flags, names, shapes={names[0]: (3, 3, 3, 32)})
+    sd = init_fn(None, None)
+    assert list(sd) == names[:1] and np.array_equal(sd[names[0]], tensors["block1_conv1/kernel"])
+    assert th.get_latest_checkpoint_for_evaluate(flags) == flags.checkpoint_path
+    # the cloud layout: data_dir/cloud_checkpoint_path
+    cloud = types.SimpleNamespace(**dict(vars(flags), run_on_cloud=True, data_dir=str(pre),
+                                         cloud_checkpoint_path="xception_model.ckpt", checkpoint_path="unused"))
+    assert list(th.get_init_fn_for_scaffold(cloud, names)(None, None)) == names[:1]
+    # a checkpoint in model_dir wins: no init_fn, and evaluation leaves the choice to the model_dir
+    bw.write_bundle(str(logs / "model.ckpt-5"), tensors)
+    (logs / "checkpoint").write_text('model_checkpoint_path: "model.ckpt-5"\n')
+    assert th.get_init_fn_for_scaffold(flags, names) is None and th.get_latest_checkpoint_for_evaluate(flags) is None
+    with pytest.raises(ValueError):
+        flags.model_dir = str(tmp_path / "empty")
+        flags.checkpoint_exclude_scopes = "xception_lighthead"
+        th.get_init_fn_for_scaffold(flags, names)

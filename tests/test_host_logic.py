@@ -97,3 +97,51 @@ def test_flag_names_and_defaults_match_reference_scripts():
         assert args.rpn_nms_thres == 0.6 and args.run_on_cloud is False and args.model_scope == "m"
         assert all(hasattr(args, k) for k in ref)
     assert pt.arg_parser().parse_args(["--resnet_layers", "1,1,1,1", "--train_epochs", "3"]).resnet_layers == (1, 1, 1, 1)
+
+
+def test_public_signatures_are_supersets_of_the_reference():
+    """tests/golden/signatures_golden.json: inspect.signature of the reference's functions (imported unmodified under
+    the numpy TensorFlow stand-in).  Every same-named product function must take the reference's parameters under the
+    same names, required ones at the same positions, with the same defaults -- so that reference call sites keep
+    working; the product may add trailing keyword parameters (store=, out=, state=, device=...).  Deliberate default
+    deviations are listed here, nowhere else."""
+    import importlib
+    import inspect
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "signatures_golden.json")) as f:
+        gold = json.load(f)
+    allowed = {
+        # NCHW is what the model_fn consumes and the kernel writes; 'NHWC' returns the permuted view
+        ("preprocessing.common_preprocessing", "light_head_preprocess_for_test", "data_format"),
+        ("preprocessing.common_preprocessing", "light_head_preprocess_for_eval", "data_format"),
+        # numpy float64 in place of tf.float64
+        ("utility.metrics", "precision_recall", "dtype"),
+    }
+    checked = 0
+    for modname, sigs in gold.items():
+        mod = importlib.import_module("xdet_b200." + modname)
+        for qual, ref in sigs.items():
+            obj = mod
+            for part in qual.split("."):
+                obj = getattr(obj, part, None)
+                if obj is None:
+                    break
+            if obj is None or not callable(obj):
+                continue                       # not part of the hot path's surface (other detectors' helpers, ...)
+            params = list(inspect.signature(obj).parameters.items())
+            names = [n for n, _ in params]
+            for pos, (name, dflt) in enumerate(ref):
+                assert name in names, (modname, qual, name)
+                p = dict(params)[name]
+                if dflt is None:               # required in the reference: same position here
+                    assert names.index(name) == pos, (modname, qual, name)
+                    continue
+                assert p.default is not inspect.Parameter.empty, (modname, qual, name)
+                if (modname, qual, name) in allowed:
+                    continue
+                if "value" in dflt:
+                    mine = list(p.default) if isinstance(p.default, (tuple, list)) else p.default
+                    assert mine == dflt["value"], (modname, qual, name, p.default, dflt)
+            checked += 1
+    assert checked >= 25, checked

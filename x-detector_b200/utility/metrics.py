@@ -36,9 +36,11 @@ class StreamingTpFpArrays(object):
         return self.nobjects, self.ndetections, self.tp, self.fp, self.scores
 
 
-def streaming_tp_fp_arrays(num_gbboxes, tp, fp, scores, remove_zero_scores=True, state=None):
+def streaming_tp_fp_arrays(num_gbboxes, tp, fp, scores, remove_zero_scores=True, metrics_collections=None,
+                           updates_collections=None, name=None, state=None):
     """Dictionary form of the reference (:143-157): one ``StreamingTpFpArrays`` per class, updated in place.
-    ``state`` is the dict returned by a previous call (None starts a new accumulation)."""
+    ``state`` is the dict returned by a previous call (None starts a new accumulation); the TF collection / name
+    arguments of the reference signature are accepted and unused."""
     state = {} if state is None else state
     for c in num_gbboxes:
         state.setdefault(c, StreamingTpFpArrays(remove_zero_scores)).update(
@@ -50,7 +52,7 @@ def _np(x):
     return x.detach().cpu().numpy() if hasattr(x, "detach") else np.asarray(x)
 
 
-def precision_recall(num_gbboxes, num_detections, tp, fp, scores, dtype=np.float64):
+def precision_recall(num_gbboxes, num_detections, tp, fp, scores, dtype=np.float64, scope=None):
     """utility/metrics.py:102-132: sort by score (tf.nn.top_k: descending, ties -> lower index), cumulative TP / FP."""
     scores = np.asarray(scores, np.float32)[:num_detections]
     order = np.lexsort((np.arange(scores.shape[0]), -scores.astype(np.float64)))
@@ -62,7 +64,7 @@ def precision_recall(num_gbboxes, num_detections, tp, fp, scores, dtype=np.float
     return precision, recall
 
 
-def average_precision_voc12(precision, recall):
+def average_precision_voc12(precision, recall, name=None):
     """utility/metrics.py:205-227."""
     precision = np.concatenate([[0.], np.asarray(precision, np.float64), [0.]])
     recall = np.concatenate([[0.], np.asarray(recall, np.float64), [1.]])
@@ -70,7 +72,7 @@ def average_precision_voc12(precision, recall):
     return float(np.sum(precision[1:] * (recall[1:] - recall[:-1])))
 
 
-def average_precision_voc07(precision, recall):
+def average_precision_voc07(precision, recall, name=None):
     """utility/metrics.py:230-252: 11-point interpolation."""
     precision = np.concatenate([np.asarray(precision, np.float64), [0.]])
     recall = np.concatenate([np.asarray(recall, np.float64), [np.inf]])

@@ -90,3 +90,36 @@ def checkpoint_to_state_dict(checkpoint_path, model_scope, checkpoint_model_scop
         if t.dtype.kind == 'f':
             out[model_name] = np.asarray(t, dtype=np.float32)
     return out
+
+
+def get_init_fn_for_scaffold(flags, var_names, shapes=None):
+    """utility/train_helper.py:5-72 under the reference's name: None when ``flags.model_dir`` already holds a
+    checkpoint (the Estimator resumes from it and ``--checkpoint_path`` is ignored, :10-12); otherwise a callable that
+    performs the fine-tuning restore and returns ``{model variable name: float32 array}`` -- pass it as
+    ``VariableStore(state_dict=...)`` / ``LightHeadRFCN.from_checkpoint``.  ``var_names`` stands for TF's
+    TRAINABLE_VARIABLES collection (:17): the model's trainable variable names (no moving statistics)."""
+    checkpoint_path = flags.checkpoint_path
+    if flags.run_on_cloud:
+        checkpoint_path = os.path.join(flags.data_dir, flags.cloud_checkpoint_path)
+    if latest_checkpoint(flags.model_dir):
+        return None
+    if not variables_to_restore(var_names, flags.model_scope, flags.checkpoint_model_scope,
+                                flags.checkpoint_exclude_scopes):
+        raise ValueError('variables_to_restore cannot be empty')
+
+    def callback(scaffold=None, session=None):
+        return load_state_dict(checkpoint_path, var_names, flags.model_scope, flags.checkpoint_model_scope,
+                               flags.checkpoint_exclude_scopes, flags.ignore_missing_vars, shapes)
+    return callback
+
+
+def get_latest_checkpoint_for_evaluate(flags):
+    """utility/train_helper.py:74-93: the checkpoint an evaluation should read -- None when ``flags.model_dir`` holds
+    one (the Estimator picks that up by itself), else ``--checkpoint_path`` (``model_dir`` on the cloud) resolved to
+    its latest checkpoint if it is a directory."""
+    checkpoint_path = flags.checkpoint_path
+    if flags.run_on_cloud:
+        checkpoint_path = flags.model_dir
+    if latest_checkpoint(flags.model_dir):
+        return None
+    return resolve_checkpoint_path(checkpoint_path)
