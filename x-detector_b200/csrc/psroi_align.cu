@@ -598,9 +598,7 @@ __global__ void __launch_bounds__(kPlanesThreads, 2) psroi_fwd_select_kernel(
         mag = b & 0x7fffffffu;
         flag = ((b >> 31) != 0u || (mag != 0u && mag < 0x21800000u)) ? 1u : 0u;  // negative, or 0 < |v| < 2^-60
       }
-#ifndef XDET_SEL_NOSTATS
       zeros_seen += __popc(__ballot_sync(0xffffffffu, i < n && mag == 0u));
-#endif
       const int ch_first = i0 / HW;
       const int ch_last = min(i0 + 31, n - 1) / HW;
       if (ch_first == ch_last) {
@@ -834,15 +832,10 @@ __global__ void __launch_bounds__(kPlanesThreads, 2) psroi_fwd_select_kernel(
     round += round_stride;
   }
   };
-#ifdef XDET_SEL_FORCE_DENSE
-  (void)dense;
-  run(std::true_type{});
-#else
   if (dense)
     run(std::true_type{});
   else
     run(std::false_type{});
-#endif
 }
 
 // ------------------------------------------------------------------------------------------
