@@ -94,3 +94,26 @@ def test_oracle_threading_is_order_independent(oracle_built):
     a = oracle_built.psroi_align_fwd(x, rois, 7, 7, "max", threads=1)
     b = oracle_built.psroi_align_fwd(x, rois, 7, 7, "max", threads=5)
     assert np.array_equal(bits(a[0]), bits(b[0])) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not mounted")
+@pytest.mark.parametrize("name", sorted(workloads.adversarial_maps()))
+def test_oracle_vs_compiled_reference_adversarial_planes(oracle_built, name):
+    """The planes the GPU SELECT kernel is attacked with (exact ties, near-ties, zeros, -0.0, huge / subnormal
+    magnitudes, NaN / inf): the C restatement must make the reference's choice on every one of them -- first maximum
+    wins, strict '<', fp64 blend rounded once -- so that 'kernel == oracle' means 'kernel == reference' there too."""
+    x = workloads.adversarial_maps()[name]
+    rois = workloads.make_rois(1, 96, seed=123, min_side=0.02, edge_cases=True)
+    for method in ("max", "mean"):
+        with np.errstate(all="ignore"):
+            p, i = oracle_built.psroi_align_fwd(x, rois, 7, 7, method)
+            pr, ir = oracle_built.psroi_align_fwd(x, rois, 7, 7, method, impl="ref")
+        ir[workloads.degenerate_mask(rois)] = 0
+        nan = np.isnan(pr)
+        assert np.array_equal(np.isnan(p), nan)
+        assert np.array_equal(bits(p)[~nan], bits(pr)[~nan]) and np.array_equal(i, ir)
+        gup = np.random.default_rng(8).standard_normal(p.shape, dtype=np.float32)
+        with np.errstate(all="ignore"):
+            g = oracle_built.psroi_align_bwd(x.shape, rois, gup, i, 7, 7, method)
+            gr = oracle_built.psroi_align_bwd(x.shape, rois, gup, i, 7, 7, method, impl="ref")
+        assert np.array_equal(bits(g), bits(gr))

@@ -36,3 +36,27 @@ def degenerate_mask(rois):
     """True where the reference leaves pooled_index unwritten (ps_roi_align_op.cc:123-126)."""
     tiny = np.finfo(np.float32).tiny
     return (rois[..., 2] < tiny) | (rois[..., 3] < tiny)
+
+
+def adversarial_maps():
+    """Planes built to defeat an approximate arg-max: exact ties, near-ties, zeros, huge and tiny magnitudes,
+    non-finite values.  SELECT must fall back to the exact loop wherever the fp32 pass cannot prove the winner."""
+    rng = np.random.default_rng(99)
+    base = rng.standard_normal((1, 98, 30, 30), dtype=np.float32)
+    relu = np.maximum(base, 0)                                   # ~50 % exact zeros (the model's thin map is post-ReLU)
+    sparse = np.where(rng.random(base.shape) < 0.9, 0, base).astype(np.float32)
+    const = np.full_like(base, 0.7)                              # every sample ties
+    negzero = np.where(rng.random(base.shape) < 0.5, -0.0, 0.0).astype(np.float32)
+    quant = np.round(base * 2).astype(np.float32) / 2            # few distinct values: many exact ties
+    near = (1.0 + rng.integers(0, 4, base.shape) * np.float32(2.0 ** -23)).astype(np.float32)  # 1-ulp steps
+    huge = (base * np.float32(1e30)).astype(np.float32)
+    tiny = (base * np.float32(1e-38)).astype(np.float32)         # subnormal products
+    mixed = base.copy()
+    mixed[:, ::7] *= np.float32(1e20)
+    nonfin = base.copy()
+    nonfin[0, 3, 4, 5] = np.nan
+    nonfin[0, 10, 20, 11] = np.inf
+    nonfin[0, 11, 2, 7] = -np.inf
+    ramp = np.broadcast_to(np.arange(30, dtype=np.float32)[None, None, None, :], base.shape).copy()  # affine in x
+    return {"relu": relu, "sparse": sparse, "const": const, "negzero": negzero, "quant": quant, "near": near,
+            "huge": huge, "tiny": tiny, "mixed": mixed, "nonfinite": nonfin, "ramp": ramp}
