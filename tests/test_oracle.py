@@ -117,3 +117,41 @@ def test_oracle_vs_compiled_reference_adversarial_planes(oracle_built, name):
             g = oracle_built.psroi_align_bwd(x.shape, rois, gup, i, 7, 7, method)
             gr = oracle_built.psroi_align_bwd(x.shape, rois, gup, i, 7, 7, method, impl="ref")
         assert np.array_equal(bits(g), bits(gr))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not mounted")
+def test_oracle_vs_compiled_reference_random_geometries(oracle_built):
+    """Differential sweep over the op's whole argument space inside its documented contract (boxes within the image):
+    ragged maps down to 1x1, non-square grids, banks of 1..4, zero to a dozen RoIs per image, boxes from degenerate
+    (zero height / width) to the full image, several images -- C restatement versus the reference's compiled C++,
+    bit for bit, forward and backward, both pooling methods."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None, derandomize=True)
+    @given(st.integers(1, 3), st.integers(1, 5), st.integers(1, 5), st.integers(1, 4), st.integers(1, 40),
+           st.integers(1, 40), st.integers(0, 12), st.integers(0, 2 ** 31 - 1), st.sampled_from(["max", "mean"]))
+    def run(N, gw, gh, bank, H, W, R, seed, method):
+        rng = np.random.default_rng(seed)
+        C = gw * gh * bank
+        x = rng.standard_normal((N, C, H, W), dtype=np.float32)
+        if seed % 3 == 0:
+            x = np.maximum(x, 0)                                  # post-ReLU planes: exact ties at zero
+        a, b = np.sort(rng.random((N, R, 2, 2), dtype=np.float32), axis=2)[:, :, 0], None
+        b = np.sort(rng.random((N, R, 2, 2), dtype=np.float32), axis=2)[:, :, 1]
+        lo, hi = np.minimum(a, b), np.maximum(a, b)               # ymin,xmin <= ymax,xmax inside [0,1)
+        if R:
+            hi[:, 0] = lo[:, 0]                                   # a degenerate box
+            if R > 1:
+                lo[:, 1], hi[:, 1] = 0.0, 1.0                     # the whole image
+        hw = (hi - lo).astype(np.float32)
+        rois = np.concatenate([lo + hw / np.float32(2), hw], -1).astype(np.float32)   # (cy, cx, h, w)
+        p, i = oracle_built.psroi_align_fwd(x, rois, gw, gh, method)
+        pr, ir = oracle_built.psroi_align_fwd(x, rois, gw, gh, method, impl="ref")
+        ir[workloads.degenerate_mask(rois)] = 0
+        assert np.array_equal(bits(p), bits(pr)) and np.array_equal(i, ir)
+        gup = rng.standard_normal(p.shape, dtype=np.float32)
+        g = oracle_built.psroi_align_bwd(x.shape, rois, gup, i, gw, gh, method)
+        gr = oracle_built.psroi_align_bwd(x.shape, rois, gup, i, gw, gh, method, impl="ref")
+        assert np.array_equal(bits(g), bits(gr))
+
+    run()
