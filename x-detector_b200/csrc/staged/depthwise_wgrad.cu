@@ -1,0 +1,111 @@
+// STAGED FOR ROUND 2 -- NOT part of libxdet_b200.so (the build globs csrc/*.cu only) and NOT yet run on a GPU:
+// it compiles for sm_100a (see staged/README.md) and has a numerics test that is skipped until it is moved into
+// the library.  First missing piece of the Xception TRAINING path (SURVEY 8 row a15 for the reference's own
+// backbone, DESIGN 7 "next steps" item 3).
+//
+// Weight gradient of tf.layers.separable_conv2d's depthwise stage (net/xception_body.py:220-234: 3x3, 'same',
+// stride 1, depth multiplier 1, dilation 1 or 2, input ReLU'd by relu_separable_bn_block):
+//     dW[kh][kw][c] = sum_{n,y,x} in(n, y + (kh-1)*d, x + (kw-1)*d, c) * dY(n, y, x, c)      in = relu(x) if relu_in
+// The input gradient needs no kernel of its own: it is the forward kernel run on dY with the taps flipped
+// (w'[kh][kw] = w[2-kh][2-kw]) and relu_in = 0, followed by the existing relu_bwd.
+//
+// HBM-bound: reads x and dY once (x's 8 neighbours come from L1/L2), writes 9*C floats.  Layout NHWC bf16, one
+// thread per channel PAIR so that a warp covers 64 consecutive channels = 128 contiguous bytes per pixel; the 8 warps
+// of a CTA take different pixels of the same 64-channel chunk, keep 9 fp32x2 partial sums in registers, fold them
+// through shared memory and add ONE value per (tap, channel) and CTA to the fp32 gradient buffer (atomics: the
+// last bits depend on CTA order, like the other weight gradients; DESIGN 7 "determinism").
+#include <cuda_bf16.h>
+
+#include "../common.cuh"
+
+namespace xdet {
+namespace {
+
+constexpr int kWgThreads = 256;
+constexpr int kWgWarps = kWgThreads / 32;
+
+template <int DIL>
+__global__ void __launch_bounds__(kWgThreads) depthwise3x3_wgrad_kernel(
+    const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw /* [9, C] */,
+    int N, int H, int W, int C, int relu_in, int pixels_per_cta) {
+  __shared__ float part[kWgWarps][9][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + lane * 2;          // this thread's channel pair
+  const bool live = c < C;                           // C % 8 == 0, so a pair never straddles the end
+  const long long total = (long long)N * H * W;
+  const long long p_begin = (long long)blockIdx.y * pixels_per_cta;
+  const long long p_end = p_begin + pixels_per_cta < total ? p_begin + pixels_per_cta : total;
+  float2 acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = make_float2(0.f, 0.f);
+  if (live) {
+    for (long long p = p_begin + warp; p < p_end; p += kWgWarps) {
+      const int xo = (int)(p % W);
+      const int yo = (int)((p / W) % H);
+      const long long n = p / ((long long)W * H);
+      const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dy + p * C + c));
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int yi = yo + (kh - 1) * DIL;
+        if (yi < 0 || yi >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int xi = xo + (kw - 1) * DIL;
+          if (xi < 0 || xi >= W) continue;
+          float2 v = __bfloat1622float2(
+              *reinterpret_cast<const __nv_bfloat162*>(x + ((n * H + yi) * W + xi) * C + c));
+          if (relu_in) {
+            v.x = fmaxf(v.x, 0.f);
+            v.y = fmaxf(v.y, 0.f);
+          }
+          acc[kh * 3 + kw].x = __fmaf_rn(v.x, g.x, acc[kh * 3 + kw].x);
+          acc[kh * 3 + kw].y = __fmaf_rn(v.y, g.y, acc[kh * 3 + kw].y);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    part[warp][k][lane * 2] = acc[k].x;
+    part[warp][k][lane * 2 + 1] = acc[k].y;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 9 * 64; e += kWgThreads) {
+    const int k = e / 64, cc = e % 64;
+    if (blockIdx.x * 64 + cc >= C) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWgWarps; ++w) s += part[w][k][cc];
+    atomicAdd(dw + (long long)k * C + blockIdx.x * 64 + cc, s);
+  }
+}
+
+}  // namespace
+}  // namespace xdet
+
+using namespace xdet;
+
+// d_dw [9, C] fp32 is ACCUMULATED into (the caller zeroes the flat gradient buffer once per step).
+extern "C" int xdet_depthwise3x3_wgrad_bf16(const void* d_x, const void* d_dy, float* d_dw, int N, int H, int W, int C,
+                                            int dilation, int relu_in, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0) return fail(XDET_EINVAL, "depthwise3x3_wgrad: non-positive dimension");
+  if (C % 8 != 0) return fail(XDET_EINVAL, "depthwise3x3_wgrad: C (%d) must be a multiple of 8", C);
+  if (dilation != 1 && dilation != 2) return fail(XDET_EINVAL, "depthwise3x3_wgrad: dilation must be 1 or 2");
+  const long long total = (long long)N * H * W;
+  const int chunks = (C + 63) / 64;
+  // enough CTAs to fill the chip ~4x over, but at least 64 pixels per warp so that the fold + atomics amortise
+  long long slabs = (4ll * kNumSMs + chunks - 1) / chunks;
+  const long long max_slabs = (total + 64 * kWgWarps - 1) / (64 * kWgWarps);
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < 1) slabs = 1;
+  if (slabs > 65535) slabs = 65535;
+  const int per = (int)((total + slabs - 1) / slabs);
+  const dim3 grid((unsigned)chunks, (unsigned)((total + per - 1) / per));
+  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(d_x);
+  const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(d_dy);
+  if (dilation == 1)
+    depthwise3x3_wgrad_kernel<1><<<grid, kWgThreads, 0, (cudaStream_t)stream>>>(x, dy, d_dw, N, H, W, C, relu_in, per);
+  else
+    depthwise3x3_wgrad_kernel<2><<<grid, kWgThreads, 0, (cudaStream_t)stream>>>(x, dy, d_dw, N, H, W, C, relu_in, per);
+  return after_launch("depthwise3x3_wgrad_kernel");
+}
