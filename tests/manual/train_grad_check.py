@@ -6,7 +6,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import xdet_b200  # noqa: E402,F401
 from oracle import net_train as ont  # noqa: E402
 from oracle import proposals as op  # noqa: E402

@@ -55,7 +55,7 @@ def test_variable_names_match_the_inference_model(run):
 def test_losses_and_gradients_vs_autograd_oracle(run, run_shallow, depth):
     lt, params, tr, sd0, batch, out = run_shallow if depth == "shallow" else run
     # shallow: tight; full depth at random init: the forward already differs by ~30 % RMS at block_layer4 (measured
-    # layer by layer with tools/train_fwd_check.py: 0.9 % after the first block, x1.1-1.3 per block), so only the
+    # layer by layer with tests/manual/train_fwd_check.py: 0.9 % after the first block, x1.1-1.3 per block), so only the
     # gradient norms and a loose direction bound are asserted there
     cos_min, cos_vec_min, n_min = (0.93, 0.9, 20) if depth == "shallow" else (0.3, 0.15, 60)
     images, gt, gl, keys = batch
