@@ -68,3 +68,31 @@ def test_operator_wrapper_validation(native):
         ps_roi_align(x, torch.zeros(2, 5, 4), 7, 7, "max")
     with pytest.raises(ValueError, match="GPU only"):
         ps_roi_align(x, r, 7, 7, "max")  # CPU tensors: no fallback
+
+
+def test_product_fails_loudly_without_the_cuda_library(tmp_path):
+    """No CPU / PyTorch fallback exists: with the shared library absent an op raises NativeLibraryMissing (the
+    message says how to build it), and ops that validate their arguments first refuse CPU tensors outright -- checked in a fresh interpreter through an op that needs no GPU to reach the
+    library lookup."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "import xdet_b200\n"
+        "from xdet_b200 import _native, ops\n"
+        "assert not __import__('os').path.exists(_native.LIB_PATH)\n"
+        "for call in (lambda: _native.lib(),\n"
+        "             lambda: ops.affine_relu(torch.zeros((1, 2, 2, 8), dtype=torch.bfloat16), torch.ones(8), torch.zeros(8)),\n"
+        "             lambda: ops.ps_roi_align(torch.zeros((1, 4, 5, 5)), torch.zeros((1, 1, 4)), 2, 2, 'max')):\n"
+        "    try:\n"
+        "        call()\n"
+        "    except (_native.NativeLibraryMissing, ValueError) as e:\n"
+        "        assert 'no CPU or PyTorch fallback' in str(e) or 'no CPU fallback' in str(e), e\n"
+        "    else:\n"
+        "        raise SystemExit('an op ran without the CUDA library')\n"
+        "print('LOUD')\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, XDET_B200_LIB=str(tmp_path / "absent" / "libxdet_b200.so"))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "LOUD" in r.stdout, r.stdout + r.stderr
