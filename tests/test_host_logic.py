@@ -145,3 +145,32 @@ def test_public_signatures_are_supersets_of_the_reference():
                     assert mine == dflt["value"], (modname, qual, name, p.default, dflt)
             checked += 1
     assert checked >= 25, checked
+
+
+def test_separation_of_product_oracle_and_reference():
+    """Static guards on the three rules the parity claims rest on:
+    (1) nothing under x-detector_b200/ or tools/ imports or executes oracle/ (test infrastructure only);
+    (2) nothing that runs on the GPU box -- the product, bench.py, __graft_entry__, the -m gpu tests -- reads
+        /root/reference (only the golden-minting scripts and the CPU-only 'reference mounted?' probes mention it);
+    (3) the stand-in TensorFlow (oracle/tf_shim) is imported only by tests/golden/make_*.py: no test and no oracle
+        module does ``import tensorflow``."""
+    import glob
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    product = glob.glob(os.path.join(root, "x-detector_b200", "**", "*.py"), recursive=True)
+    tools = glob.glob(os.path.join(root, "tools", "*.py"))
+    imp = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b|from\s+\.+\s*oracle\b)", re.M)
+    for f in product + tools:
+        src = open(f).read()
+        assert not imp.search(src), f
+        assert "tf_shim" not in src and "/root/reference" not in src, f
+    gpu_side = [os.path.join(root, "bench.py")] + glob.glob(os.path.join(root, "tests", "*_gpu.py"))
+    for f in gpu_side:
+        src = open(f).read()
+        assert "/root/reference" not in src and "tf_shim" not in src, f
+    entry = open(os.path.join(root, "__graft_entry__.py")).read()
+    assert entry.count("/root/reference") == 1 and 'isdir("/root/reference")' in entry   # build(): compile oracle/_ref if present
+    for f in glob.glob(os.path.join(root, "tests", "test_*.py")) + glob.glob(os.path.join(root, "oracle", "*.py")):
+        src = open(f).read()
+        assert not re.search(r"^\s*import tensorflow|^\s*from tensorflow", src, re.M), f
