@@ -40,6 +40,7 @@ F = np.float32
 DF = "channels_first"
 PARAMS = dict(num_classes=21, rpn_pre_nms_top_n=600, rpn_post_nms_top_n=100, rpn_nms_thres=0.7)
 SUBSAMPLE = {"rpn_feat_map": 4, "backbone_feat": 8, "large_sep_feature": 2}
+SUBSAMPLE_SQUARE = {"rpn_feat_map": 16, "backbone_feat": 32, "large_sep_feature": 8}   # the xs / rs runs
 
 
 def image(seed, n, h, w):
@@ -48,7 +49,7 @@ def image(seed, n, h, w):
 
 def put(out, prefix, name, value):
     v = np.asarray(value)
-    step = SUBSAMPLE.get(name, 1)
+    step = (SUBSAMPLE_SQUARE if prefix in ("xs", "rs") else SUBSAMPLE).get(name, 1)
     out["%s_%s" % (prefix, name)] = v[:, ::step] if step > 1 else v
     if step > 1:
         out["%s_%s_sums" % (prefix, name)] = np.array([v.sum(dtype=np.float64), np.abs(v).sum(dtype=np.float64)])
@@ -146,6 +147,9 @@ def main():
     run(out, "xc", "xception", "xception_lighthead", 11, 161, 193)
     run(out, "rn", "resnet50", "resnet_lighthead", 12, 145, 177)
     run_training_forward(out, "rt", "resnet_lighthead", 13, 81, 97)
+    # square 160x160 inputs: a size the product's launchers take (train_image_size), for the CUDA parity-mode test
+    run(out, "xs", "xception", "xception_lighthead", 14, 160, 160)
+    run(out, "rs", "resnet50", "resnet_lighthead", 15, 160, 160)
     path = os.path.join(HERE, "netgraph_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")

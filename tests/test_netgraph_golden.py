@@ -56,6 +56,8 @@ def check(gold, prefix, name, value, tol=1e-5):
         shape = tuple(gold["%s_%s_shape" % (prefix, name)])
         assert v.shape == shape, (name, v.shape, shape)
         step = -(-shape[1] // g.shape[1])
+        while v[:, ::step].shape[1] != g.shape[1]:   # ceil(C / step) is not injective: find the stride that was used
+            step += 1
         sums = gold["%s_%s_sums" % (prefix, name)]
         assert abs(v.sum(dtype=np.float64) - sums[0]) <= 1e-5 * sums[1], name
         assert abs(np.abs(v).sum(dtype=np.float64) - sums[1]) <= 1e-5 * sums[1], name
@@ -63,7 +65,7 @@ def check(gold, prefix, name, value, tol=1e-5):
     assert rel(v, g) < tol, (name, rel(v, g))
 
 
-@pytest.mark.parametrize("prefix", ["xc", "rn"])
+@pytest.mark.parametrize("prefix", ["xc", "rn", "xs", "rs"])
 def test_oracle_graph_matches_reference_builders(gold, prefix):
     meta = json.loads(str(gold["%s_meta" % prefix]))
     sd = state_dict(meta)
@@ -131,3 +133,35 @@ def test_training_mode_forward(gold):
     for name, v in (("rpn_feat_map", rpn_feat), ("backbone_feat", backbone), ("large_sep_feature", thin),
                     ("rpn_cls", cls.permute(0, 2, 3, 1)), ("rpn_box", box.permute(0, 2, 3, 1))):
         check(gold, "rt", name, v.numpy(), 1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.skip(reason="staged: written after the round's GPU budget was spent; un-skip after its first run on a B200")
+@pytest.mark.parametrize("prefix", ["xs", "rs"])
+def test_cuda_parity_mode_matches_reference_builders(gold, prefix):
+    """The CUDA path in fp32x3 parity mode, fed the same name-seeded variables, against the reference's own graph
+    builders (160x160, both backbones): north_star's 1e-4 on boxes / scores, stage tensors at 1e-4 of their magnitude."""
+    import torch
+    import xdet_b200  # noqa: F401
+    from xdet_b200 import light_head_rfcn_eval as lh
+    meta = json.loads(str(gold["%s_meta" % prefix]))
+    sd = {name: torch.from_numpy(onet.seeded_variable(name, tuple(shape))) for name, shape in meta["variables"]}
+    params = lh.make_params(train_image_size=meta["height"], backbone=meta["backbone"], model_scope=meta["scope"],
+                            rpn_pre_nms_top_n=meta["rpn_pre_nms_top_n"], rpn_post_nms_top_n=meta["rpn_post_nms_top_n"],
+                            rpn_nms_thres=meta["rpn_nms_thres"], rpn_min_size=meta["rpn_min_size"], precision="fp32x3")
+    model = lh.LightHeadRFCN(params, seed=0, state_dict=sd)
+    keys = torch.from_numpy(gold["%s_shuffle_keys" % prefix]).cuda()
+    out = model(torch.from_numpy(image(meta)).cuda(), shuffle_keys=keys)
+    torch.cuda.synchronize()
+    check(gold, prefix, "rpn_feat_map", out["rpn_feat_map"].permute(0, 3, 1, 2).cpu().numpy(), 1e-4)
+    check(gold, prefix, "backbone_feat", out["backbone_feat"].permute(0, 3, 1, 2).cpu().numpy(), 1e-4)
+    check(gold, prefix, "large_sep_feature", out["large_sep_feature"].cpu().numpy(), 1e-4)
+    rpn = out["rpn_out"].cpu().numpy()
+    check(gold, prefix, "rpn_cls", rpn[..., :44], 1e-4)
+    check(gold, prefix, "rpn_box", rpn[..., 44:], 1e-4)
+    assert np.abs(out["proposals_bboxes"].cpu().numpy() - gold["%s_proposals_bboxes" % prefix]).max() < 1e-4
+    assert np.abs(out["cls_score"].cpu().numpy().reshape(-1, 21) - gold["%s_cls_score" % prefix]).max() < 1e-4 * max(
+        1.0, np.abs(gold["%s_cls_score" % prefix]).max())
+    assert np.abs(out["bboxes_reg"].cpu().numpy().reshape(-1, 4) - gold["%s_bboxes_reg" % prefix]).max() < 1e-4
+    assert np.abs(out["head_cls_score"].cpu().numpy() - gold["%s_head_cls_score" % prefix]).max() < 1e-4
+    assert np.abs(out["bboxes_predict"].cpu().numpy() - gold["%s_bboxes_predict" % prefix]).max() < 1e-4
