@@ -43,3 +43,26 @@ def test_threshold_is_strict():
         want = tv_ops.nms(torch.from_numpy(boxes), torch.from_numpy(scores), thr).numpy()
         assert len(want) == kept
         assert np.array_equal(np.asarray(P.non_max_suppression(boxes, scores, 10, thr)), want)
+
+
+def test_top_k_tie_rule_against_torch_stable_sort():
+    """tf.nn.top_k (TopKV2, not available offline) is documented as: descending, equal values -> the lower index
+    first.  The oracle states it as a lexsort; torch's stable descending sort is an independent implementation of the
+    same rule (scores with many exact ties, +-0.0 and a few +-inf)."""
+    rng = np.random.default_rng(11)
+    for n, k in ((5000, 600), (64, 64), (7, 3), (1, 1)):
+        s = (rng.integers(0, 50, n) / 50.0).astype(np.float32)          # ~100 copies of each value
+        s[rng.integers(0, n, max(n // 50, 1))] = np.float32(-0.0)
+        if n > 10:
+            s[3], s[n // 2] = np.inf, -np.inf
+        boxes = rng.random((n, 4), dtype=np.float32)
+        order = np.lexsort((np.arange(n), -s.astype(np.float64)))[:k]
+        want = torch.sort(torch.from_numpy(s), descending=True, stable=True).indices.numpy()[:k]
+        assert np.array_equal(order, want)
+        # the same rule inside _filter_and_sort_boxes (everything passes the filter: size 1, centre inside)
+        b = np.tile(np.array([0.25, 0.25, 0.75, 0.75], np.float32), (n, 1)) + boxes * np.float32(1e-3)
+        pos = np.where(np.isfinite(s) & (s > 0), s, np.float32(0.5)).astype(np.float32)
+        ss, bb, sel = P.filter_and_sort_boxes(pos, b, 0.01, k)
+        want = torch.sort(torch.from_numpy(pos), descending=True, stable=True).indices.numpy()[:k]
+        assert np.array_equal(sel, want) and np.array_equal(ss[:len(want)], pos[want])
+        assert np.array_equal(bb[:len(want)], b[want])
