@@ -133,3 +133,33 @@ def test_gpu_detection_chain_and_matching(cuda):
         assert int(ngb[c][0]) == int(G["match_n"][c - 1])
         assert np.array_equal(tp[c][0].cpu().numpy(), G["match_tp"][c - 1])
         assert np.array_equal(fp[c][0].cpu().numpy(), G["match_fp"][c - 1])
+
+
+@pytest.mark.gpu
+@pytest.mark.skip(reason="staged: AnchorEncoder.encode_all_anchors / ext_encode_rois were added as wrappers over the "
+                         "validated match_encode / sample_fg_bg ops after the round's GPU budget was spent; un-skip "
+                         "after their first run on a B200")
+def test_gpu_anchor_encoder_training_targets(cuda):
+    """The reference's method names (preprocessing/anchor_manipulator.py:319-335, :337-432) on the CUDA path against
+    the goldens its own AnchorEncoder produced."""
+    torch = cuda
+    from xdet_b200.preprocessing import anchor_manipulator as am
+    cr = am.AnchorCreator([160, 160], layers_shapes=[(10, 10)], anchor_scales=[SCALES], extra_anchor_scales=[EXTRA],
+                          anchor_ratios=[RATIOS], layer_steps=[16])
+    anchors, _ = cr.get_all_anchors()
+    enc = am.AnchorEncoder(anchors, num_classes=21, allowed_borders=[0.], positive_threshold=0.7, ignore_threshold=0.3,
+                           prior_scaling=[1., 1., 1., 1.], rpn_fg_thres=0.5, rpn_bg_high_thres=0.5, rpn_bg_low_thres=0.)
+    gt, gl = torch.from_numpy(G["tgt_gt"]).cuda(), torch.from_numpy(G["tgt_gl"]).cuda()
+    labels, targets, scores, points, n_layers = enc.encode_all_anchors(gl, gt)
+    assert n_layers == 1
+    for n in range(2):
+        assert np.array_equal(labels[0][n].cpu().numpy(), G["enc_labels_%d" % n])
+        assert np.array_equal(targets[0][n].cpu().numpy(), G["enc_targets_%d" % n])
+        assert np.array_equal(bits(scores[0][n].cpu().numpy()), bits(G["enc_scores_%d" % n]))
+        assert np.array_equal(bits(points[0].cpu().numpy()), bits(G["enc_points_%d" % n]))
+    keys = {"roi_fg": torch.from_numpy(G["roi_kfg"]).cuda(), "roi_bg": torch.from_numpy(G["roi_kbg"]).cuda(),
+            "roi_up": torch.from_numpy(G["roi_kup"]).cuda()}
+    rois, tgt, lab, sc = enc.ext_encode_rois(torch.from_numpy(G["roi_in"]).cuda(), gl, gt, 16, 0.25, 0.1, keys=keys)
+    assert np.array_equal(bits(rois.cpu().numpy()), bits(G["roi_out"]))
+    assert np.array_equal(lab.cpu().numpy(), G["roi_labels"]) and np.array_equal(tgt.cpu().numpy(), G["roi_targets"])
+    assert np.array_equal(bits(sc.cpu().numpy()), bits(G["roi_scores"]))

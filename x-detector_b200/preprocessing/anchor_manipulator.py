@@ -5,7 +5,9 @@
   fp32 constants, computed once on the host exactly as the reference does (python-double sqrt, then cast).
 * ``AnchorEncoder.decode_all_anchors`` (:641-669) and ``ext_decode_rois`` (:671-683): CUDA kernels
   ``xdet_rpn_decode`` / ``xdet_head_decode``.
-* ``encode_all_anchors`` / ``ext_encode_rois`` (training targets, :319-636) are NOT part of this build.
+* ``AnchorEncoder.encode_all_anchors`` (:118-171, :319-335) and ``ext_encode_rois`` (:337-432), the training
+  targets: the reference's method names over the kernels the training step launches directly
+  (``xdet_match_encode``, ``xdet_sample_fg_bg``; ``tf.random_shuffle`` = stable argsort of injected keys).
 """
 import math
 
@@ -103,3 +105,64 @@ class AnchorEncoder(object):
         shape = proposals_roi.shape
         _, boxes = ops.head_decode(proposals_roi.reshape(-1, 4), pred_location.reshape(-1, 4).contiguous(), 0, 4, 0)
         return boxes.reshape(shape)
+
+    # ---- training targets -----------------------------------------------------------------------------------
+    def _flat_anchors(self, index=0):
+        """All anchors of one layer, (y, x, a) order with a fastest: point form [A_tot,4] (center2point) and centre
+        form [A_tot,4]."""
+        yref, xref, href, wref = self._dev_anchors[index]
+        cells, A = yref.numel(), href.numel()
+        cy = yref.reshape(cells, 1).expand(cells, A).reshape(-1)
+        cx = xref.reshape(cells, 1).expand(cells, A).reshape(-1)
+        hh = href.reshape(1, A).expand(cells, A).reshape(-1)
+        ww = wref.reshape(1, A).expand(cells, A).reshape(-1)
+        pt = torch.stack([cy - hh / 2., cx - ww / 2., cy + hh / 2., cx + ww / 2.], -1).contiguous()
+        return pt, torch.stack([cy, cx, hh, ww], -1).contiguous()
+
+    def encode_all_anchors(self, labels, bboxes):
+        """Reference :319-335 (``encode_anchor`` :118-171 per layer): labels [G] / [N,G] (<= 0: padding), bboxes
+        [G,4] / [N,G,4] CUDA tensors -> (ground_labels, anchor_regress_targets, ground_scores, ground_bboxes,
+        n_layers), lists with one entry per feature layer: labels int32 (>0 matched class, 0 background, -1 ignored),
+        targets fp32 [...,4], scores fp32, each over the layer's anchors ([A_tot] or [N,A_tot]); ground_bboxes = the
+        anchors in point form."""
+        from ..ops import train as T
+        single = labels.dim() == 1
+        gl = (labels.reshape(1, -1) if single else labels).to(torch.int32).contiguous()
+        gb = (bboxes.reshape(1, -1, 4) if single else bboxes).to(torch.float32).contiguous()
+        ground_labels, targets, scores, points = [], [], [], []
+        for index in range(len(self._anchors)):
+            pt, yxhw = self._flat_anchors(index)
+            l, t, s = T.match_encode(pt, gb, gl, float(self._allowed_borders[index]), self._positive_threshold,
+                                     self._ignore_threshold, ref_yxhw=yxhw)
+            ground_labels.append(l[0] if single else l)
+            targets.append(t[0] if single else t)
+            scores.append(s[0] if single else s)
+            points.append(pt)
+        return ground_labels, targets, scores, points, len(self._anchors)
+
+    def ext_encode_rois(self, all_rois, all_labels, all_bboxes, rois_per_image, fg_fraction, allowed_border,
+                        head_prior_scaling=[1., 1., 1., 1.], keys=None):
+        """Reference :337-432: append the ground-truth boxes to the RoIs, match (fg >= rpn_fg_thres, bg below
+        rpn_bg_high_thres and above rpn_bg_low_thres), sample ``rois_per_image`` per image at ``fg_fraction``
+        foreground.  all_rois [N,R,4], all_labels [N,G] (<= 0: padding), all_bboxes [N,G,4] -> (rois [N,S,4],
+        targets [N,S,4], labels [N,S] int32, scores [N,S]).  ``keys``: {'roi_fg','roi_bg': [N,R+G], 'roi_up': [N,S]}
+        uniform fp32 arrays standing in for the three tf.random_shuffle calls (drawn here when omitted)."""
+        from ..ops import train as T
+        if any(float(p) != 1.0 for p in head_prior_scaling):
+            raise ValueError("only head_prior_scaling = [1,1,1,1] is built (light_head_rfcn_train.py:252)")
+        N, S = all_rois.shape[0], int(rois_per_image)
+        gl = all_labels.to(torch.int32).contiguous()
+        gb = all_bboxes.to(torch.float32).contiguous()
+        rois_all = torch.cat([all_rois, gb * (gl > 0).unsqueeze(-1).float()], dim=1).contiguous()
+        n = rois_all.shape[1]
+        if keys is None:
+            keys = {'roi_fg': torch.rand((N, n), device=rois_all.device), 'roi_bg': torch.rand((N, n), device=rois_all.device),
+                    'roi_up': torch.rand((N, S), device=rois_all.device)}
+        lab, tgt, sc = T.match_encode(rois_all, gb, gl, float(allowed_border), self._rpn_fg_thres,
+                                      self._rpn_bg_high_thres)
+        idx, _ = T.sample_fg_bg(lab, sc, float(self._rpn_bg_low_thres), int(round(S * fg_fraction)), S,
+                                keys['roi_fg'], keys['roi_bg'], keys['roi_up'])
+        idx = idx.long()
+        gather4 = idx.unsqueeze(-1).expand(N, S, 4)
+        return (torch.gather(rois_all, 1, gather4).contiguous(), torch.gather(tgt, 1, gather4).contiguous(),
+                torch.gather(lab, 1, idx).contiguous(), torch.gather(sc, 1, idx).contiguous())
