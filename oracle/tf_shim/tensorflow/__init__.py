@@ -257,6 +257,8 @@ def gather_nd(params, indices, name=None):
 
 
 def split(value, num_or_size_splits, axis=0, num=None, name=None):
+    if not np.isscalar(num_or_size_splits):   # a list gives the SIZES of the parts (np.split wants the cut points)
+        num_or_size_splits = np.cumsum(np.asarray(num_or_size_splits))[:-1]
     return [_t(p) for p in np.split(_t(value), num_or_size_splits, axis=axis)]
 
 
@@ -359,9 +361,11 @@ def while_loop(cond_fn, body, loop_vars, parallel_iterations=None, back_prop=Fal
 
 class TensorArray(object):
     def __init__(self, dtype, size=0, dynamic_size=False, infer_shape=True, **kw):
-        self.dtype, self.items = _np(dtype), [None] * int(size)
+        self.dtype, self.items, self.dynamic = _np(dtype), [None] * int(size), dynamic_size
 
     def write(self, i, value):
+        if self.dynamic and int(i) >= len(self.items):
+            self.items.extend([None] * (int(i) + 1 - len(self.items)))
         self.items[int(i)] = np.asarray(value).astype(self.dtype)
         return self
 
