@@ -136,7 +136,7 @@ def test_training_mode_forward(gold):
 
 
 @pytest.mark.gpu
-@pytest.mark.skip(reason="staged: written after the round's GPU budget was spent; un-skip after its first run on a B200")
+@pytest.mark.skipif(not os.environ.get("XDET_RUN_STAGED"), reason="staged (XDET_RUN_STAGED=1 runs it): written after the round's GPU budget was spent; un-skip after its first run on a B200")
 @pytest.mark.parametrize("prefix", ["xs", "rs"])
 def test_cuda_parity_mode_matches_reference_builders(gold, prefix):
     """The CUDA path in fp32x3 parity mode, fed the same name-seeded variables, against the reference's own graph

@@ -7,8 +7,12 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
+# XDET_BUILD_STAGED=1: also compile csrc/staged/*.cu (kernels awaiting their first GPU run) into a SEPARATE library,
+# libxdet_b200_staged.so, and load that one -- the default build and library never contain staged code.
+STAGED = os.environ.get("XDET_BUILD_STAGED", "") not in ("", "0")
 # XDET_B200_LIB: load another build of the same library (A/B experiments of tools/); default = the in-tree build
-LIB_PATH = os.environ.get("XDET_B200_LIB") or os.path.join(CSRC, "libxdet_b200.so")
+LIB_PATH = os.environ.get("XDET_B200_LIB") or os.path.join(CSRC, "libxdet_b200_staged.so" if STAGED
+                                                             else "libxdet_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
 NVCC_FLAGS = [
@@ -24,7 +28,8 @@ class NativeLibraryMissing(RuntimeError):
 
 
 def sources():
-    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    return srcs + sorted(glob.glob(os.path.join(CSRC, "staged", "*.cu"))) if STAGED else srcs
 
 
 def build(force=False, verbose=False):
