@@ -1,0 +1,198 @@
+"""STAGED (written after the round's GPU minutes were spent; first run pending -- see csrc/staged/README.md):
+training-mode ``XceptionBody`` (net/xception_body.py:220-379 with is_training=True) on the CUDA kernels, forward tape
++ explicit backward, the device-side twin of the CPU blueprint ``oracle/xception_backward.py`` (which is held to
+autograd for all 154 trainable variables).  Same classes, same order of operations; every method is one or two
+kernel launches:
+
+  Conv.bwd        xdet_conv2d_wgrad_bf16 + xdet_conv2d_dgrad_bf16
+  Depthwise.bwd   xdet_depthwise3x3_wgrad_bf16 (csrc/staged/) + the forward kernel on dY with flipped taps
+                  (+ xdet_relu_bwd_bf16 when the block ReLUs its input)
+  BatchNorm       xdet_col_stats / xdet_bn_finalize forward, xdet_bn_relu_bwd_bf16 backward (relu flag 0 / 1)
+  MaxPool         xdet_maxpool3x3s2_argmax_bf16 / xdet_maxpool3x3s2_bwd_bf16
+
+Not yet wired into ``LightHeadTrainer`` (whose backbone is the ResNet-50 composition): gradients are returned as a
+dict in TF variable layouts so that the first GPU run can be compared tensor by tensor with the blueprint
+(tests/test_staged_xception_train_gpu.py); fusions (BN into the pointwise epilogue, pool + residual) come after that.
+Needs the staged library: XDET_BUILD_STAGED=1.
+"""
+import ctypes
+
+import torch
+
+from .. import _native, ops
+from ..ops import train as T
+
+BN_EPSILON = 0.0001
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Conv(object):
+    """tf.layers.conv2d without bias on NHWC bf16; ``w`` = TF kernel [kh,kw,cin,cout] fp32."""
+
+    def __init__(self, name, w, stride=1, padding="SAME", need_dgrad=True):
+        self.name, self.stride, self.padding = name, stride, padding
+        self.kh, self.kw, self.cin, self.cout = w.shape
+        w4 = w.permute(3, 2, 0, 1).contiguous()
+        self.pack = ops.pack_conv_weight(w4)
+        self.dpack = ops.pack_dgrad_weight(w4) if need_dgrad else None
+
+    def _geom(self, H, W):
+        s = self.stride
+        if self.padding == "VALID":
+            return (0, 0, (H - self.kh) // s + 1, (W - self.kw) // s + 1)
+        if s == 1:
+            return "SAME"
+        assert self.kh == 1 and self.kw == 1    # the strided 1x1 'same' projections of the entry flow
+        return (0, 0, -(-H // s), -(-W // s))
+
+    def fwd(self, x):
+        self.x, self.in_hw = x, tuple(x.shape[1:3])
+        self.geom = self._geom(*self.in_hw)
+        return ops.conv2d_nhwc(x, self.pack, self.cout, self.kh, self.kw, padding=self.geom,
+                               strides=(self.stride, self.stride), cin=self.cin)
+
+    def bwd(self, dy, grads, leaf="kernel"):
+        cin_pad = (self.cin + 63) // 64 * 64
+        dw = torch.zeros((self.cout, self.kh * self.kw, cin_pad), dtype=torch.float32, device=dy.device)
+        ops.conv2d_wgrad(self.x, dy, self.kh, self.kw, padding=self.geom, strides=(self.stride, self.stride),
+                         cin=self.cin, cout=self.cout, dw=dw)
+        grads[self.name + "/" + leaf] = dw.view(self.cout, self.kh, self.kw, cin_pad)[..., :self.cin].permute(
+            1, 2, 3, 0).contiguous()
+        if self.dpack is None:
+            return None
+        return ops.conv2d_dgrad(dy, self.dpack, self.cin, self.kh, self.kw, self.in_hw, padding=self.geom,
+                                strides=(self.stride, self.stride), cout=self.cout)
+
+
+class Depthwise(object):
+    """Depthwise stage of tf.layers.separable_conv2d; ``w`` = [3,3,C,1] fp32."""
+
+    def __init__(self, name, w, dil=1, relu_in=True):
+        self.name, self.dil, self.relu_in = name, dil, relu_in
+        self.C = w.shape[2]
+        self.w9 = w.reshape(9, self.C).float().contiguous()
+        self.w9_flipped = self.w9.flip(0).contiguous()     # tap (kh,kw) -> (2-kh,2-kw)
+
+    def fwd(self, x):
+        self.x = x
+        return ops.depthwise3x3(x, self.w9, dilation=self.dil, relu_in=self.relu_in)
+
+    def bwd(self, dy, grads):
+        lib = _native.lib()
+        if not hasattr(lib, "xdet_depthwise3x3_wgrad_bf16"):
+            raise _native.NativeLibraryMissing("xdet_depthwise3x3_wgrad_bf16 is staged: build with XDET_BUILD_STAGED=1")
+        lib.xdet_depthwise3x3_wgrad_bf16.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 6 + [ctypes.c_void_p]
+        N, H, W, C = self.x.shape
+        dw = torch.zeros((9, C), dtype=torch.float32, device=dy.device)
+        dy = dy.contiguous()
+        _native.check(lib.xdet_depthwise3x3_wgrad_bf16(self.x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W, C,
+                                                       self.dil, 1 if self.relu_in else 0, _st()))
+        grads[self.name + "/depthwise_kernel"] = dw.reshape(3, 3, C, 1)
+        da = ops.depthwise3x3(dy, self.w9_flipped, dilation=self.dil, relu_in=False)
+        return T.relu_bwd(da, self.x) if self.relu_in else da
+
+
+class BatchNorm(object):
+    """tf.layers.batch_normalization(training=True) (+ ReLU when ``relu``); moving statistics are not updated here."""
+
+    def __init__(self, name, gamma, beta, relu=False):
+        self.name, self.gamma, self.beta, self.relu = name, gamma, beta, relu
+
+    def fwd(self, x):
+        self.x = x
+        self.st = T.bn_train(x, self.gamma, self.beta, BN_EPSILON)
+        return ops.affine_relu(x, self.st.scale, self.st.shift, relu=self.relu)
+
+    def bwd(self, dy, grads):
+        dx, dgamma, dbeta = T.bn_relu_bwd(dy.contiguous(), self.x, self.st, relu=self.relu)
+        grads[self.name + "/gamma"], grads[self.name + "/beta"] = dgamma, dbeta
+        return dx
+
+
+class MaxPool(object):
+    def fwd(self, x):
+        self.in_hw = tuple(x.shape[1:3])
+        y, self.arg = T.maxpool3x3s2_fwd_train(x)
+        return y
+
+    def bwd(self, dy):
+        return T.maxpool3x3s2_bwd(self.arg, dy.contiguous(), self.in_hw)
+
+
+class SepBN(object):
+    def __init__(self, v, name, dil=1, relu_in=True, relu_out=False):
+        self.name = name
+        self.dw = Depthwise(name, v(name + "/depthwise_kernel"), dil, relu_in)
+        self.pw = Conv(name, v(name + "/pointwise_kernel"))
+        self.bn = BatchNorm(name + "_bn", v(name + "_bn/gamma"), v(name + "_bn/beta"), relu_out)
+
+    def fwd(self, x):
+        return self.bn.fwd(self.pw.fwd(self.dw.fwd(x)))
+
+    def bwd(self, dy, grads):
+        return self.dw.bwd(self.pw.bwd(self.bn.bwd(dy, grads), grads, leaf="pointwise_kernel"), grads)
+
+
+class ConvBN(object):
+    def __init__(self, v, conv_name, bn_name, stride, padding, relu, need_dgrad=True):
+        self.conv = Conv(conv_name, v(conv_name + "/kernel"), stride, padding, need_dgrad)
+        self.bn = BatchNorm(bn_name, v(bn_name + "/gamma"), v(bn_name + "/beta"), relu)
+
+    def fwd(self, x):
+        return self.bn.fwd(self.conv.fwd(x))
+
+    def bwd(self, dy, grads):
+        return self.conv.bwd(self.bn.bwd(dy, grads), grads)
+
+
+class XceptionBodyTraining(object):
+    """fwd(images fp32 NCHW) -> (mid [N,h,w,728], out [N,h,w,2048]) NHWC bf16; bwd(d_mid, d_out) -> {name: grad}.
+    ``variables``: {TF variable name without the model scope: fp32 CUDA tensor in TF layout}."""
+
+    def __init__(self, variables):
+        v = variables.__getitem__
+        self.b1c1 = ConvBN(v, "block1_conv1", "block1_conv1_bn", 2, "VALID", True, need_dgrad=False)
+        self.b1c2 = ConvBN(v, "block1_conv2", "block1_conv2_bn", 1, "VALID", True)
+        self.entry = []
+        for blk, idx, first_relu in ((2, 1, False), (3, 2, True), (4, 3, True)):
+            self.entry.append((ConvBN(v, "conv2d_%d" % idx, "batch_normalization_%d" % idx, 2, "SAME", False),
+                               SepBN(v, "block%d_sepconv1" % blk, relu_in=first_relu),
+                               SepBN(v, "block%d_sepconv2" % blk), MaxPool()))
+        self.middle = [[SepBN(v, "block%d_sepconv%d" % (i + 5, j)) for j in (1, 2, 3)] for i in range(8)]
+        self.exit_res = ConvBN(v, "conv2d_4", "batch_normalization_4", 1, "SAME", False)
+        self.b13 = [SepBN(v, "block13_sepconv1"), SepBN(v, "block13_sepconv2")]
+        self.b14 = [SepBN(v, "block14_sepconv1", dil=2, relu_in=False, relu_out=True),
+                    SepBN(v, "block14_sepconv2", dil=2, relu_in=False, relu_out=True)]
+
+    def fwd(self, images):
+        x = T.nchw_f32_to_nhwc_bf16(images.contiguous(), pitch=8)   # 3 channels in rows of 8 (generic strided conv)
+        x = self.b1c2.fwd(self.b1c1.fwd(x))
+        for res, s1, s2, pool in self.entry:
+            x = pool.fwd(s2.fwd(s1.fwd(x))) + res.fwd(x)
+        for blk in self.middle:
+            y = x
+            for s in blk:
+                y = s.fwd(y)
+            x = x + y
+        self.pre_mid = x
+        mid = torch.relu(x)
+        y = self.b13[1].fwd(self.b13[0].fwd(x)) + self.exit_res.fwd(x)
+        return mid, self.b14[1].fwd(self.b14[0].fwd(y))
+
+    def bwd(self, d_mid, d_out):
+        grads = {}
+        d = self.b14[0].bwd(self.b14[1].bwd(d_out, grads), grads)
+        dx = self.b13[0].bwd(self.b13[1].bwd(d, grads), grads) + self.exit_res.bwd(d, grads)
+        dx = dx + T.relu_bwd(d_mid.contiguous(), self.pre_mid)
+        for blk in reversed(self.middle):
+            d = dx
+            for s in reversed(blk):
+                d = s.bwd(d, grads)
+            dx = dx + d
+        for res, s1, s2, pool in reversed(self.entry):
+            dx = s1.bwd(s2.bwd(pool.bwd(dx), grads), grads) + res.bwd(dx, grads)
+        self.b1c1.bwd(self.b1c2.bwd(dx, grads), grads)
+        return grads
