@@ -22,6 +22,14 @@ import torch.nn.functional as F
 from . import net as onet
 
 EPS = onet.EPS_XCEPTION
+# True: round every activation / activation-gradient that crosses a kernel boundary to bf16 (what the CUDA twin,
+# x-detector_b200/net/xception_train_staged.py, stores between launches); weight gradients stay unrounded (fp32 on
+# the device).  Used to CALIBRATE the tolerances of the device-vs-blueprint test, not by the autograd check.
+EMULATE_BF16 = False
+
+
+def _r(t):
+    return t.to(torch.bfloat16).to(t.dtype) if EMULATE_BF16 else t
 
 
 class Conv(object):
@@ -40,14 +48,14 @@ class Conv(object):
             self.pads = (pl, pr, pt, pb)
         self.xp = F.pad(x, self.pads)
         self.wt = w
-        return F.conv2d(self.xp, w, stride=self.stride)
+        return _r(F.conv2d(self.xp, w, stride=self.stride))
 
     def bwd(self, dy, grads):
         dw = torch.nn.grad.conv2d_weight(self.xp, self.wt.shape, dy, stride=self.stride)
         grads[self.name + "/kernel"] = dw.permute(2, 3, 1, 0).contiguous()
         dxp = torch.nn.grad.conv2d_input(self.xp.shape, self.wt, dy, stride=self.stride)
         pl, pr, pt, pb = self.pads
-        return dxp[:, :, pt:dxp.shape[2] - pb, pl:dxp.shape[3] - pr]
+        return _r(dxp[:, :, pt:dxp.shape[2] - pb, pl:dxp.shape[3] - pr])
 
 
 def depthwise_fwd(a, taps, dil):
@@ -67,7 +75,7 @@ class Depthwise(object):
     def fwd(self, x):
         self.x = x
         self.a = torch.relu(x) if self.relu_in else x
-        return depthwise_fwd(self.a, self.taps, self.dil)
+        return _r(depthwise_fwd(self.a, self.taps, self.dil))
 
     def bwd(self, dy, grads):
         d, a = self.dil, self.a
@@ -78,7 +86,7 @@ class Depthwise(object):
             for kw in range(3):   # dW[kh,kw,c] = sum_{n,y,x} a(n, y+(kh-1)d, x+(kw-1)d, c) * dy(n,y,x,c)
                 dw[kh, kw] = (ap[:, :, kh * d:kh * d + H, kw * d:kw * d + W] * dy).sum(dim=(0, 2, 3))
         grads[self.name + "/depthwise_kernel"] = dw.unsqueeze(-1)
-        da = depthwise_fwd(dy, self.taps.flip(0, 1), d)   # the forward kernel on dy with the taps flipped
+        da = _r(depthwise_fwd(dy, self.taps.flip(0, 1), d))   # the forward kernel on dy with the taps flipped
         return da * (self.x > 0).to(da.dtype) if self.relu_in else da
 
 
@@ -95,7 +103,7 @@ class BatchNorm(object):
         self.invstd = 1.0 / torch.sqrt(var + EPS)
         self.xhat = (x - mean.view(sh)) * self.invstd.view(sh)
         self.y = self.xhat * self.gamma.view(sh) + self.beta.view(sh)
-        return torch.relu(self.y) if self.relu else self.y
+        return _r(torch.relu(self.y) if self.relu else self.y)
 
     def bwd(self, dy, grads):
         sh = (1, -1, 1, 1)
@@ -105,7 +113,7 @@ class BatchNorm(object):
         dbeta = dy.sum(dim=(0, 2, 3))
         dgamma = (dy * self.xhat).sum(dim=(0, 2, 3))
         grads[self.name + "/beta"], grads[self.name + "/gamma"] = dbeta, dgamma
-        return (self.gamma * self.invstd).view(sh) / m * (m * dy - dbeta.view(sh) - self.xhat * dgamma.view(sh))
+        return _r((self.gamma * self.invstd).view(sh) / m * (m * dy - dbeta.view(sh) - self.xhat * dgamma.view(sh)))
 
 
 class MaxPool(object):
@@ -181,29 +189,29 @@ class XceptionBodyTape(object):
                     SepBN(v, "block14_sepconv2", dil=2, relu_in=False, relu_out=True)]
 
     def fwd(self, x):
-        x = self.b1c2.fwd(self.b1c1.fwd(x))
+        x = self.b1c2.fwd(self.b1c1.fwd(_r(x)))
         for res, s1, s2, pool in self.entry:
-            x = pool.fwd(s2.fwd(s1.fwd(x))) + res.fwd(x)
+            x = _r(pool.fwd(s2.fwd(s1.fwd(x))) + res.fwd(x))
         for blk in self.middle:
             y = x
             for s in blk:
                 y = s.fwd(y)
-            x = x + y
+            x = _r(x + y)
         self.pre_mid = x
         mid = torch.relu(x)
-        y = self.b13[1].fwd(self.b13[0].fwd(x)) + self.exit_res.fwd(x)
+        y = _r(self.b13[1].fwd(self.b13[0].fwd(x)) + self.exit_res.fwd(x))
         return mid, self.b14[1].fwd(self.b14[0].fwd(y))
 
     def bwd(self, d_mid, d_out):
         grads = {}
         d = self.b14[0].bwd(self.b14[1].bwd(d_out, grads), grads)            # gradient of (block13 + residual)
-        dx = self.b13[0].bwd(self.b13[1].bwd(d, grads), grads) + self.exit_res.bwd(d, grads)
-        dx = dx + d_mid * (self.pre_mid > 0).to(d_mid.dtype)                  # the RPN feature is relu(x)
+        dx = _r(self.b13[0].bwd(self.b13[1].bwd(d, grads), grads) + self.exit_res.bwd(d, grads))
+        dx = _r(dx + d_mid * (self.pre_mid > 0).to(d_mid.dtype))              # the RPN feature is relu(x)
         for blk in reversed(self.middle):
             d = dx
             for s in reversed(blk):
                 d = s.bwd(d, grads)
-            dx = dx + d                                                       # identity shortcut
+            dx = _r(dx + d)                                                   # identity shortcut
         for res, s1, s2, pool in reversed(self.entry):
-            dx = s1.bwd(s2.bwd(pool.bwd(dx), grads), grads) + res.bwd(dx, grads)
+            dx = _r(s1.bwd(s2.bwd(pool.bwd(dx), grads), grads) + res.bwd(dx, grads))
         return self.b1c1.bwd(self.b1c2.bwd(dx, grads), grads), grads

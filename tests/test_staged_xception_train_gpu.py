@@ -1,8 +1,12 @@
 """GPU, STAGED (XDET_BUILD_STAGED=1 XDET_RUN_STAGED=1): training-mode XceptionBody on the CUDA kernels
 (x-detector_b200/net/xception_train_staged.py) against its CPU blueprint (oracle/xception_backward.py, itself equal to
-autograd): forward features and every one of the 154 gradients, on the same name-seeded variables.  bf16 activations
-through ~40 layers: the bar is agreement in direction and scale (cosine > 0.98 per tensor, tighter near the output),
-the exact check of each kernel's arithmetic lives in the per-op tests."""
+autograd): forward features and every one of the 154 gradients, on the same name-seeded variables.
+
+Calibration done on the CPU beforehand (blueprint with EMULATE_BF16 vs the float64 blueprint, same inputs): storing
+activations and activation gradients in bf16 between kernels ALONE moves the gradients of the early layers to a
+cosine of 0.84 against exact arithmetic (0.93 in the exit flow; batch statistics over 2x8x8 values amplify every
+rounding), so the device is compared with the bf16-EMULATING blueprint -- same rounding points, differences left are
+accumulation order and the occasional flipped bf16 tie -- and only loosely with the exact one."""
 import json
 import os
 
@@ -39,21 +43,31 @@ def test_xception_training_backbone_matches_blueprint():
     sd = {n: torch.from_numpy(onet.seeded_variable(scope + n, s)) for n, s in body}
     rs = np.random.RandomState(5)
     images = torch.from_numpy(rs.uniform(-1, 1, (2, 3, 129, 129)).astype(np.float32))
-    # ---- blueprint (float64 CPU) ----
-    tape = xb.XceptionBodyTape({k: v.double() for k, v in sd.items()})
-    with torch.no_grad():
-        mid0, out0 = tape.fwd(images.double())
-        r_mid = torch.from_numpy(rs.standard_normal(tuple(mid0.shape)))
-        r_out = torch.from_numpy(rs.standard_normal(tuple(out0.shape)))
-        _, want = tape.bwd(r_mid, r_out)
+    # ---- blueprint on the CPU: exact, and with bf16 storage between kernels ----
+    def blueprint(emulate, r=None):
+        xb.EMULATE_BF16 = emulate
+        try:
+            tape = xb.XceptionBodyTape({k: v.double() for k, v in sd.items()})
+            with torch.no_grad():
+                m, o = tape.fwd(images.double())
+                if r is None:
+                    r = (torch.from_numpy(rs.standard_normal(tuple(m.shape))).bfloat16().double(),
+                         torch.from_numpy(rs.standard_normal(tuple(o.shape))).bfloat16().double())
+                _, g = tape.bwd(*r)
+        finally:
+            xb.EMULATE_BF16 = False
+        return m, o, g, r
+    mid_x, out_x, exact, (r_mid, r_out) = blueprint(False)
+    mid0, out0, want, _ = blueprint(True, (r_mid, r_out))
     # ---- CUDA ----
     model = xt.XceptionBodyTraining({k: v.cuda() for k, v in sd.items()})
     mid, out = model.fwd(images.cuda())
     to_dev = lambda t: t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()   # noqa: E731
     grads = model.bwd(to_dev(r_mid), to_dev(r_out))
     torch.cuda.synchronize()
-    assert cosine(mid.float().cpu().permute(0, 3, 1, 2), mid0) > 0.995
-    assert cosine(out.float().cpu().permute(0, 3, 1, 2), out0) > 0.995
+    assert cosine(mid.float().cpu().permute(0, 3, 1, 2), mid0) > 0.9995
+    assert cosine(out.float().cpu().permute(0, 3, 1, 2), out0) > 0.9995
+    assert cosine(out.float().cpu().permute(0, 3, 1, 2), out_x) > 0.99
     trainable = {n for n, _ in body if not n.rsplit("/", 1)[-1].startswith("moving_")}
     assert set(grads) == trainable and len(trainable) == 154
     worst = 1.0
@@ -62,7 +76,8 @@ def test_xception_training_backbone_matches_blueprint():
         assert g.shape == want[n].shape and torch.isfinite(g).all(), n
         c = cosine(g, want[n])
         worst = min(worst, c)
-        assert c > (0.995 if n.startswith(("block14", "block13", "conv2d_4", "batch_normalization_4")) else 0.98), (n, c)
+        assert c > (0.999 if n.startswith(("block14", "block13", "conv2d_4", "batch_normalization_4")) else 0.99), (n, c)
         ratio = float(g.double().norm() / (want[n].norm() + 1e-30))
-        assert 0.9 < ratio < 1.1, (n, ratio)
-    assert worst > 0.98
+        assert 0.95 < ratio < 1.05, (n, ratio)
+        assert cosine(g, exact[n]) > 0.75, n          # and in the neighbourhood of the exact gradient
+    assert worst > 0.99
