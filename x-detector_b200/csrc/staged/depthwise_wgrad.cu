@@ -14,9 +14,11 @@
 // of a CTA take different pixels of the same 64-channel chunk, keep 9 fp32x2 partial sums in registers, fold them
 // through shared memory and add ONE value per (tap, channel) and CTA to the fp32 gradient buffer (atomics: the
 // last bits depend on CTA order, like the other weight gradients; DESIGN 7 "determinism").
+#ifndef XDET_EMULATE_ON_CPU   // tests/staged/emulate_depthwise_wgrad.cc supplies host stand-ins instead
 #include <cuda_bf16.h>
 
 #include "../common.cuh"
+#endif
 
 namespace xdet {
 namespace {
@@ -85,22 +87,32 @@ __global__ void __launch_bounds__(kWgThreads) depthwise3x3_wgrad_kernel(
 
 using namespace xdet;
 
+// Grid: blockIdx.x = 64-channel chunk, blockIdx.y = slab of `per` consecutive pixels.  Enough CTAs to fill the chip
+// ~4x over, but at least 64 pixels per warp so that the fold + atomics amortise.  (Plain host arithmetic, kept apart
+// from the launch so that the CPU emulation of tests/staged/ drives the kernel over exactly this decomposition.)
+static void depthwise_wgrad_grid(long long total, int C, int num_sms, int* chunks, int* slabs, int* per) {
+  *chunks = (C + 63) / 64;
+  long long s = (4ll * num_sms + *chunks - 1) / *chunks;
+  const long long max_slabs = (total + 64 * 8 - 1) / (64 * 8);
+  if (s > max_slabs) s = max_slabs;
+  if (s < 1) s = 1;
+  if (s > 65535) s = 65535;
+  *per = (int)((total + s - 1) / s);
+  *slabs = (int)((total + *per - 1) / *per);
+}
+
+#ifndef XDET_EMULATE_ON_CPU
+using namespace xdet;
+
 // d_dw [9, C] fp32 is ACCUMULATED into (the caller zeroes the flat gradient buffer once per step).
 extern "C" int xdet_depthwise3x3_wgrad_bf16(const void* d_x, const void* d_dy, float* d_dw, int N, int H, int W, int C,
                                             int dilation, int relu_in, void* stream) {
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0) return fail(XDET_EINVAL, "depthwise3x3_wgrad: non-positive dimension");
   if (C % 8 != 0) return fail(XDET_EINVAL, "depthwise3x3_wgrad: C (%d) must be a multiple of 8", C);
   if (dilation != 1 && dilation != 2) return fail(XDET_EINVAL, "depthwise3x3_wgrad: dilation must be 1 or 2");
-  const long long total = (long long)N * H * W;
-  const int chunks = (C + 63) / 64;
-  // enough CTAs to fill the chip ~4x over, but at least 64 pixels per warp so that the fold + atomics amortise
-  long long slabs = (4ll * kNumSMs + chunks - 1) / chunks;
-  const long long max_slabs = (total + 64 * kWgWarps - 1) / (64 * kWgWarps);
-  if (slabs > max_slabs) slabs = max_slabs;
-  if (slabs < 1) slabs = 1;
-  if (slabs > 65535) slabs = 65535;
-  const int per = (int)((total + slabs - 1) / slabs);
-  const dim3 grid((unsigned)chunks, (unsigned)((total + per - 1) / per));
+  int chunks, slabs, per;
+  depthwise_wgrad_grid((long long)N * H * W, C, kNumSMs, &chunks, &slabs, &per);
+  const dim3 grid((unsigned)chunks, (unsigned)slabs);
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(d_x);
   const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(d_dy);
   if (dilation == 1)
@@ -109,3 +121,4 @@ extern "C" int xdet_depthwise3x3_wgrad_bf16(const void* d_x, const void* d_dy, f
     depthwise3x3_wgrad_kernel<2><<<grid, kWgThreads, 0, (cudaStream_t)stream>>>(x, dy, d_dw, N, H, W, C, relu_in, per);
   return after_launch("depthwise3x3_wgrad_kernel");
 }
+#endif  // XDET_EMULATE_ON_CPU
