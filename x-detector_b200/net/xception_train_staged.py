@@ -29,6 +29,19 @@ def _st():
     return torch.cuda.current_stream().cuda_stream
 
 
+def depthwise3x3_wgrad(x, dy, dilation, relu_in):
+    """dW [9, C] fp32 of the depthwise 3x3 'same' convolution (csrc/staged/depthwise_wgrad.cu)."""
+    lib = _native.lib()
+    if not hasattr(lib, "xdet_depthwise3x3_wgrad_bf16"):
+        raise _native.NativeLibraryMissing("xdet_depthwise3x3_wgrad_bf16 is staged: build with XDET_BUILD_STAGED=1")
+    lib.xdet_depthwise3x3_wgrad_bf16.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 6 + [ctypes.c_void_p]
+    N, H, W, C = x.shape
+    dw = torch.zeros((9, C), dtype=torch.float32, device=x.device)
+    _native.check(lib.xdet_depthwise3x3_wgrad_bf16(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W, C, dilation,
+                                                   1 if relu_in else 0, _st()))
+    return dw
+
+
 class Conv(object):
     """tf.layers.conv2d without bias on NHWC bf16; ``w`` = TF kernel [kh,kw,cin,cout] fp32."""
 
@@ -81,16 +94,9 @@ class Depthwise(object):
         return ops.depthwise3x3(x, self.w9, dilation=self.dil, relu_in=self.relu_in)
 
     def bwd(self, dy, grads):
-        lib = _native.lib()
-        if not hasattr(lib, "xdet_depthwise3x3_wgrad_bf16"):
-            raise _native.NativeLibraryMissing("xdet_depthwise3x3_wgrad_bf16 is staged: build with XDET_BUILD_STAGED=1")
-        lib.xdet_depthwise3x3_wgrad_bf16.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 6 + [ctypes.c_void_p]
-        N, H, W, C = self.x.shape
-        dw = torch.zeros((9, C), dtype=torch.float32, device=dy.device)
         dy = dy.contiguous()
-        _native.check(lib.xdet_depthwise3x3_wgrad_bf16(self.x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W, C,
-                                                       self.dil, 1 if self.relu_in else 0, _st()))
-        grads[self.name + "/depthwise_kernel"] = dw.reshape(3, 3, C, 1)
+        dw = depthwise3x3_wgrad(self.x, dy, self.dil, self.relu_in)
+        grads[self.name + "/depthwise_kernel"] = dw.reshape(3, 3, self.C, 1)
         da = ops.depthwise3x3(dy, self.w9_flipped, dilation=self.dil, relu_in=False)
         return T.relu_bwd(da, self.x) if self.relu_in else da
 
