@@ -197,3 +197,112 @@ def test_twin_composition_equals_blueprint(monkeypatch):
         assert c > 0.999, (n, c)
         assert abs(float(grads[n].double().norm() / want[n].norm()) - 1.0) < 0.02, n
     print("worst cosine over 154 gradients:", worst)
+
+
+# ---- the registry / optimizer form (TrainableXceptionBody) over the trainer's own parameter classes -------------------
+def fake_bn_train_moving(x, gamma, beta, eps, decay=None, moving_mean=None, moving_var=None):
+    st = fake_bn_train(x, gamma, beta, eps)
+    if moving_mean is not None:   # xdet_bn_finalize: moving <- decay*moving + (1-decay)*batch (unbiased variance)
+        x2 = x.double().reshape(-1, x.shape[-1])
+        moving_mean.mul_(decay).add_((1 - decay) * st.mean.float())
+        moving_var.mul_(decay).add_((1 - decay) * x2.var(0, unbiased=True).float())
+    return st
+
+
+def fake_bn_relu_bwd_into(dy, x, st, relu, grad_view):
+    dx, dgamma, dbeta = fake_bn_relu_bwd(dy, x, st, relu)
+    C = x.shape[-1]
+    grad_view[:C] += dbeta
+    grad_view[C:2 * C] += dgamma
+    return dx
+
+
+def fake_sgd_momentum_conv(dw, w, mom, w_pack, w_dgrad_pack, lr, momentum, wd, grad_scale=1.0, co_off=0, ci_off=0,
+                           fold=False):
+    kh, kw, cin, cout = w.shape
+    g = dw.view(dw.shape[0], kh, kw, dw.shape[-1])[co_off:co_off + cout, :, :, ci_off:ci_off + cin].permute(1, 2, 3, 0)
+    mom.mul_(momentum).add_(g * grad_scale + wd * w)
+    w.sub_(lr * mom)
+    w4 = w.permute(3, 2, 0, 1).double()
+    w_pack.copy_(w4)
+    if w_dgrad_pack is not None:
+        w_dgrad_pack.copy_(torch.flip(w4, dims=(2, 3)).permute(1, 0, 2, 3))
+
+
+def fake_sgd_momentum_vec(g, w, mom, lr, momentum, wd=0.0, grad_scale=1.0):
+    mom.mul_(momentum).add_(g.reshape(w.shape) * grad_scale + wd * w)
+    w.sub_(lr * mom)
+
+
+def test_trainable_form_accumulates_and_updates(monkeypatch):
+    from xdet_b200 import light_head_rfcn_train as lt
+    for mod in (ops, conv_mod):
+        monkeypatch.setattr(mod, "pack_conv_weight", fake_pack_conv_weight)
+        monkeypatch.setattr(mod, "conv2d_nhwc", fake_conv2d_nhwc)
+    monkeypatch.setattr(ops, "conv2d_wgrad", fake_conv2d_wgrad)
+    monkeypatch.setattr(ops, "depthwise3x3", fake_depthwise3x3)
+    monkeypatch.setattr(ops, "affine_relu", fake_affine_relu)
+    monkeypatch.setattr(xt, "depthwise3x3_wgrad", fake_depthwise3x3_wgrad)
+    monkeypatch.setattr(xt, "bn_relu_bwd_into", fake_bn_relu_bwd_into)
+    for name, fn in (("bn_train", fake_bn_train_moving), ("bn_relu_bwd", fake_bn_relu_bwd), ("relu_bwd", fake_relu_bwd),
+                     ("maxpool3x3s2_fwd_train", fake_maxpool_fwd), ("maxpool3x3s2_bwd", fake_maxpool_bwd),
+                     ("nchw_f32_to_nhwc_bf16", fake_nchw_to_nhwc), ("sgd_momentum_conv", fake_sgd_momentum_conv),
+                     ("sgd_momentum_vec", fake_sgd_momentum_vec)):
+        monkeypatch.setattr(T, name, fn)
+
+    meta = json.loads(str(np.load(GOLD)["xc_meta"]))
+    scope = meta["scope"] + "/"
+    heads = tuple(scope + h for h in ("rpn_head", "large_sep_feature", "final_head"))
+    body = [(n[len(scope):], tuple(s)) for n, s in meta["variables"] if n.startswith(scope) and not n.startswith(heads)]
+    all_vars = {n: torch.from_numpy(onet.seeded_variable(scope + n, s)) for n, s in body}
+    masters = {n: t.clone() for n, t in all_vars.items() if not n.rsplit("/", 1)[-1].startswith("moving_")}
+    moving = {n: t.clone() for n, t in all_vars.items() if n.rsplit("/", 1)[-1].startswith("moving_")}
+    rs = np.random.RandomState(9)
+    images = torch.from_numpy(rs.uniform(-1, 1, (2, 3, 65, 81)).astype(np.float32))
+
+    with torch.no_grad():
+        ref = xt.XceptionBodyTraining({n: t.clone() for n, t in masters.items()})      # the standalone twin
+        mid0, out0 = ref.fwd(images)
+        d_mid = torch.from_numpy(rs.standard_normal(tuple(mid0.shape))).to(BF)
+        d_out = torch.from_numpy(rs.standard_normal(tuple(out0.shape))).to(BF)
+        want = ref.bwd(d_mid, d_out)
+
+        reg = lt._Registry("cpu")
+        net = xt.TrainableXceptionBody(masters, moving, reg, lt.ConvParams, lt.VecParam)
+        reg.finalize()
+        assert len(net.convs) == 4 + 2 + 34 and len(net.vecs) == 34 + 40     # convs + pointwise; depthwise + BN pairs
+        mm_before = moving["block5_sepconv1_bn/moving_mean"].clone()
+        mid = net.fwd_mid(images)
+        out = net.fwd_exit()
+        assert torch.equal(mid, mid0) and torch.equal(out, out0)
+        assert net.bwd(d_mid, d_out) == {}                                    # everything went into the flat buffer
+        # ---- gradients in the flat all-reduce buffer == the standalone twin's dict ----
+        for layer in net._layers():
+            if isinstance(layer, xt.Conv):
+                leaf = "pointwise_kernel" if layer.name + "/pointwise_kernel" in masters else "kernel"
+                g = layer.p.dw.view(layer.cout, layer.kh, layer.kw, -1)[..., :layer.cin].permute(1, 2, 3, 0)
+                assert torch.allclose(g, want[layer.name + "/" + leaf], rtol=1e-6, atol=1e-7), layer.name
+            elif isinstance(layer, xt.Depthwise):
+                g = layer.vec.grad[:9 * layer.C].view(3, 3, layer.C, 1)
+                assert torch.allclose(g, want[layer.name + "/depthwise_kernel"], rtol=1e-6, atol=1e-7), layer.name
+            else:
+                C = layer.beta.numel()
+                assert torch.allclose(layer.vec.grad[:C], want[layer.name + "/beta"], rtol=1e-6, atol=1e-7)
+                assert torch.allclose(layer.vec.grad[C:2 * C], want[layer.name + "/gamma"], rtol=1e-6, atol=1e-7)
+        assert float(reg.flat.abs().sum()) > 0
+        # ---- moving statistics followed the batch ----
+        assert not torch.equal(moving["block5_sepconv1_bn/moving_mean"], mm_before)
+        # ---- one optimizer step: L2 on kernels, none on the batch-norm pairs; packs and views follow ----
+        before = {n: t.clone() for n, t in masters.items()}
+        lr, mom, wd = 0.1, 0.9, 1e-2
+        net.update(lr, mom, wd, 1.0)
+        for n in ("block1_conv1/kernel", "block7_sepconv2/pointwise_kernel", "block7_sepconv2/depthwise_kernel",
+                  "conv2d_4/kernel"):
+            assert torch.allclose(masters[n], before[n] - lr * (want[n].float() + wd * before[n]), rtol=1e-5, atol=1e-7), n
+        for n in ("block7_sepconv2_bn/gamma", "batch_normalization_2/beta"):
+            assert torch.allclose(masters[n], before[n] - lr * want[n].float(), rtol=1e-5, atol=1e-7), n
+        reg.flat.zero_()
+        mid1, out1 = net.fwd(images)
+        ref1 = xt.XceptionBodyTraining({n: t.clone() for n, t in masters.items()})   # rebuilt from the updated masters
+        mid2, out2 = ref1.fwd(images)
+        assert torch.equal(mid1, mid2) and torch.equal(out1, out2) and not torch.equal(out1, out0)

@@ -42,6 +42,22 @@ def depthwise3x3_wgrad(x, dy, dilation, relu_in):
     return dw
 
 
+BN_MOMENTUM = 0.99
+
+
+def bn_relu_bwd_into(dy, x, st, relu, grad_view):
+    """xdet_bn_relu_bwd_bf16 with its column sums written straight into ``grad_view`` ([0,C) = dbeta, [C,2C) = dgamma:
+    the (beta, gamma) order of the trainer's VecParam)."""
+    cs = x.shape[-1]
+    assert dy.shape == x.shape and dy.is_contiguous() and grad_view.numel() == 2 * cs
+    dx = torch.empty_like(x)
+    _native.check(_native.lib().xdet_bn_relu_bwd_bf16(dy.data_ptr(), x.data_ptr(), st.scale.data_ptr(),
+                                                      st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
+                                                      st.rows, cs, 1 if relu else 0, None, grad_view.data_ptr(),
+                                                      dx.data_ptr(), _st()))
+    return dx
+
+
 class Conv(object):
     """tf.layers.conv2d without bias on NHWC bf16; ``w`` = TF kernel [kh,kw,cin,cout] fp32."""
 
@@ -68,12 +84,17 @@ class Conv(object):
                                strides=(self.stride, self.stride), cin=self.cin)
 
     def bwd(self, dy, grads, leaf="kernel"):
-        cin_pad = (self.cin + 63) // 64 * 64
-        dw = torch.zeros((self.cout, self.kh * self.kw, cin_pad), dtype=torch.float32, device=dy.device)
+        p = getattr(self, "p", None)     # TrainableXceptionBody: accumulate into the trainer's flat gradient buffer
+        if p is not None:
+            dw = p.dw
+        else:
+            cin_pad = (self.cin + 63) // 64 * 64
+            dw = torch.zeros((self.cout, self.kh * self.kw, cin_pad), dtype=torch.float32, device=dy.device)
         ops.conv2d_wgrad(self.x, dy, self.kh, self.kw, padding=self.geom, strides=(self.stride, self.stride),
                          cin=self.cin, cout=self.cout, dw=dw)
-        grads[self.name + "/" + leaf] = dw.view(self.cout, self.kh, self.kw, cin_pad)[..., :self.cin].permute(
-            1, 2, 3, 0).contiguous()
+        if p is None:
+            grads[self.name + "/" + leaf] = dw.view(self.cout, self.kh, self.kw, -1)[..., :self.cin].permute(
+                1, 2, 3, 0).contiguous()
         if self.dpack is None:
             return None
         return ops.conv2d_dgrad(dy, self.dpack, self.cin, self.kh, self.kw, self.in_hw, padding=self.geom,
@@ -87,7 +108,6 @@ class Depthwise(object):
         self.name, self.dil, self.relu_in = name, dil, relu_in
         self.C = w.shape[2]
         self.w9 = w.reshape(9, self.C).float().contiguous()
-        self.w9_flipped = self.w9.flip(0).contiguous()     # tap (kh,kw) -> (2-kh,2-kw)
 
     def fwd(self, x):
         self.x = x
@@ -96,8 +116,13 @@ class Depthwise(object):
     def bwd(self, dy, grads):
         dy = dy.contiguous()
         dw = depthwise3x3_wgrad(self.x, dy, self.dil, self.relu_in)
-        grads[self.name + "/depthwise_kernel"] = dw.reshape(3, 3, self.C, 1)
-        da = ops.depthwise3x3(dy, self.w9_flipped, dilation=self.dil, relu_in=False)
+        vec = getattr(self, "vec", None)
+        if vec is not None:
+            vec.grad[:9 * self.C] += dw.reshape(-1)
+        else:
+            grads[self.name + "/depthwise_kernel"] = dw.reshape(3, 3, self.C, 1)
+        # tap (kh,kw) -> (2-kh,2-kw); flipped per call: w9 may be a view of a master the optimizer updates
+        da = ops.depthwise3x3(dy, self.w9.flip(0).contiguous(), dilation=self.dil, relu_in=False)
         return T.relu_bwd(da, self.x) if self.relu_in else da
 
 
@@ -109,10 +134,14 @@ class BatchNorm(object):
 
     def fwd(self, x):
         self.x = x
-        self.st = T.bn_train(x, self.gamma, self.beta, BN_EPSILON)
+        moving = getattr(self, "moving", (None, None))   # TrainableXceptionBody: also update the moving statistics
+        self.st = T.bn_train(x, self.gamma, self.beta, BN_EPSILON, None if moving[0] is None else BN_MOMENTUM, *moving)
         return ops.affine_relu(x, self.st.scale, self.st.shift, relu=self.relu)
 
     def bwd(self, dy, grads):
+        vec = getattr(self, "vec", None)
+        if vec is not None:
+            return bn_relu_bwd_into(dy.contiguous(), self.x, self.st, self.relu, vec.grad)
         dx, dgamma, dbeta = T.bn_relu_bwd(dy.contiguous(), self.x, self.st, relu=self.relu)
         grads[self.name + "/gamma"], grads[self.name + "/beta"] = dgamma, dbeta
         return dx
@@ -202,3 +231,81 @@ class XceptionBodyTraining(object):
             dx = s1.bwd(s2.bwd(pool.bwd(dx), grads), grads) + res.bwd(dx, grads)
         self.b1c1.bwd(self.b1c2.bwd(dx, grads), grads)
         return grads
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The same backbone in the form LightHeadTrainer needs (light_head_rfcn_train.py): gradients accumulate into views of
+# the ONE flat all-reduce buffer, every variable owns its momentum slot, the forward is split where the training
+# step forks its second stream (the RPN feature exists after the middle flow; the exit flow runs beside the RPN
+# losses / proposals / RoI targets).
+# ---------------------------------------------------------------------------------------------------------------
+class TrainableXceptionBody(XceptionBodyTraining):
+    """``XceptionBodyTraining`` over the trainer's parameter classes.  ``store_vars``: {name: fp32 master in TF
+    layout} (updated in place by ``update``); ``moving``: {name + '/moving_mean' | '/moving_variance': tensor};
+    ``reg``: the trainer's _Registry (gradient views are carved from its flat buffer at ``reg.finalize()``)."""
+
+    def __init__(self, store_vars, moving, reg, conv_params_cls, vec_param_cls):
+        self.convs, self.vecs = [], []
+        self._reg, self._conv_cls, self._vec_cls, self._moving = reg, conv_params_cls, vec_param_cls, moving
+        self._vars = store_vars
+        XceptionBodyTraining.__init__(self, store_vars)
+        for layer in self._layers():
+            if isinstance(layer, Conv):
+                leaf = "pointwise_kernel" if (layer.name + "/pointwise_kernel") in store_vars else "kernel"
+                key = layer.name + "/" + leaf
+                layer.p = conv_params_cls(reg, [(key, store_vars[key], 0, 0)], layer.kh, layer.kw, layer.cin, layer.cout,
+                                          need_dgrad=layer.dpack is not None)
+                layer.pack, layer.dpack = layer.p.pack, layer.p.dpack     # the packs the optimizer refreshes
+                self.convs.append(layer.p)
+            elif isinstance(layer, Depthwise):
+                layer.master = store_vars[layer.name + "/depthwise_kernel"]
+                layer.w9 = layer.master.view(9, layer.C)                   # a VIEW: follows the optimizer's updates
+                layer.vec = vec_param_cls(reg, [layer.master], decayed=True)
+                self.vecs.append(layer.vec)
+            elif isinstance(layer, BatchNorm):
+                layer.vec = vec_param_cls(reg, [layer.beta, layer.gamma], decayed=False)
+                layer.moving = (moving[layer.name + "/moving_mean"], moving[layer.name + "/moving_variance"])
+                self.vecs.append(layer.vec)
+
+    def _layers(self):
+        blocks = [self.b1c1, self.b1c2] + [b for e in self.entry for b in e[:3]] + [s for m in self.middle for s in m]
+        blocks += [self.exit_res] + self.b13 + self.b14
+        for b in blocks:
+            if isinstance(b, ConvBN):
+                yield b.conv
+                yield b.bn
+            else:
+                yield b.dw
+                yield b.pw
+                yield b.bn
+
+    # ---- forward, split at the RPN feature -------------------------------------------------------------------
+    def fwd_mid(self, images):
+        x = T.nchw_f32_to_nhwc_bf16(images.contiguous(), pitch=8)
+        x = self.b1c2.fwd(self.b1c1.fwd(x))
+        for res, s1, s2, pool in self.entry:
+            x = pool.fwd(s2.fwd(s1.fwd(x))) + res.fwd(x)
+        for blk in self.middle:
+            y = x
+            for s in blk:
+                y = s.fwd(y)
+            x = x + y
+        self.pre_mid = x
+        return torch.relu(x)
+
+    def fwd_exit(self):
+        x = self.pre_mid
+        y = self.b13[1].fwd(self.b13[0].fwd(x)) + self.exit_res.fwd(x)
+        return self.b14[1].fwd(self.b14[0].fwd(y))
+
+    def fwd(self, images):
+        mid = self.fwd_mid(images)
+        return mid, self.fwd_exit()
+
+    def update(self, lr, momentum, weight_decay, grad_scale):
+        """One momentum-SGD step on every variable of the backbone (L2 on everything but the batch-norm pairs, as
+        light_head_rfcn_train.py:420 excludes 'batch_normalization' / '_bn')."""
+        for c in self.convs:
+            c.update(lr, momentum, weight_decay, grad_scale)
+        for v in self.vecs:
+            v.update(lr, momentum, weight_decay, grad_scale)
