@@ -163,3 +163,57 @@ def test_gpu_anchor_encoder_training_targets(cuda):
     assert np.array_equal(bits(rois.cpu().numpy()), bits(G["roi_out"]))
     assert np.array_equal(lab.cpu().numpy(), G["roi_labels"]) and np.array_equal(tgt.cpu().numpy(), G["roi_targets"])
     assert np.array_equal(bits(sc.cpu().numpy()), bits(G["roi_scores"]))
+
+
+def test_anchor_encoder_wrappers_with_stand_in_kernels(monkeypatch):
+    """CPU: the composition logic of AnchorEncoder.encode_all_anchors / ext_encode_rois (argument order, the zero-box
+    padding of the appended ground truth, key slicing, gathers) with the two kernel wrappers replaced by the numpy
+    oracle behind the wrappers' documented contracts -- against the goldens the reference's own AnchorEncoder produced.
+    (Their GPU test is staged; the kernels themselves are validated against the same oracle in test_train_ops_gpu.)"""
+    import torch
+    import xdet_b200  # noqa: F401
+    from oracle import train as ot
+    from xdet_b200.ops import train as T
+    from xdet_b200.preprocessing import anchor_manipulator as am
+
+    def fake_match_encode(boxes, gt, gt_labels, allowed_border, high_thres, low_thres, prior_scaling=(1., 1., 1., 1.),
+                          ref_yxhw=None):
+        assert gt_labels.dtype == torch.int32 and gt.is_contiguous() and boxes.is_contiguous()
+        outs = []
+        for n in range(gt_labels.shape[0]):
+            b = (boxes if boxes.dim() == 2 else boxes[n]).numpy()
+            outs.append(ot.match_encode(b, gt[n].numpy(), gt_labels[n].numpy(), allowed_border, high_thres, low_thres,
+                                        prior_scaling, None if ref_yxhw is None else ref_yxhw.numpy()))
+        return tuple(torch.from_numpy(np.stack([o[i] for o in outs])) for i in range(3))
+
+    def fake_sample_fg_bg(labels, scores, bg_low, exp_fg, total, keys_fg, keys_bg, keys_up):
+        assert keys_fg.shape == labels.shape and keys_up.shape == (labels.shape[0], total)
+        rows = [ot.sample_fg_bg(labels[g].numpy(), None if scores is None else scores[g].numpy(), bg_low, exp_fg, total,
+                                keys_fg[g].numpy(), keys_bg[g].numpy(), keys_up[g].numpy()) for g in range(labels.shape[0])]
+        return (torch.from_numpy(np.stack([r[0] for r in rows]).astype(np.int32)),
+                torch.tensor([r[1] for r in rows], dtype=torch.int32))
+
+    monkeypatch.setattr(T, "match_encode", fake_match_encode)
+    monkeypatch.setattr(T, "sample_fg_bg", fake_sample_fg_bg)
+    cr = am.AnchorCreator([160, 160], layers_shapes=[(10, 10)], anchor_scales=[SCALES], extra_anchor_scales=[EXTRA],
+                          anchor_ratios=[RATIOS], layer_steps=[16])
+    anchors, _ = cr.get_all_anchors()
+    enc = am.AnchorEncoder(anchors, num_classes=21, allowed_borders=[0.], positive_threshold=0.7, ignore_threshold=0.3,
+                           prior_scaling=[1., 1., 1., 1.], rpn_fg_thres=0.5, rpn_bg_high_thres=0.5, rpn_bg_low_thres=0.,
+                           device="cpu")
+    gt, gl = torch.from_numpy(G["tgt_gt"]), torch.from_numpy(G["tgt_gl"])
+    labels, targets, scores, points, n_layers = enc.encode_all_anchors(gl, gt)
+    assert n_layers == 1
+    for n in range(2):
+        assert np.array_equal(labels[0][n].numpy(), G["enc_labels_%d" % n])
+        assert np.array_equal(targets[0][n].numpy(), G["enc_targets_%d" % n])
+        assert np.array_equal(bits(scores[0][n].numpy()), bits(G["enc_scores_%d" % n]))
+        assert np.array_equal(bits(points[0].numpy()), bits(G["enc_points_%d" % n]))
+    one = enc.encode_all_anchors(gl[0], gt[0])                     # the reference's per-image form
+    assert np.array_equal(one[0][0].numpy(), G["enc_labels_0"]) and one[1][0].shape == (2200, 4)
+    keys = {"roi_fg": torch.from_numpy(G["roi_kfg"]), "roi_bg": torch.from_numpy(G["roi_kbg"]),
+            "roi_up": torch.from_numpy(G["roi_kup"])}
+    rois, tgt, lab, sc = enc.ext_encode_rois(torch.from_numpy(G["roi_in"]), gl, gt, 16, 0.25, 0.1, keys=keys)
+    assert np.array_equal(bits(rois.numpy()), bits(G["roi_out"]))
+    assert np.array_equal(lab.numpy(), G["roi_labels"]) and np.array_equal(tgt.numpy(), G["roi_targets"])
+    assert np.array_equal(bits(sc.numpy()), bits(G["roi_scores"]))
