@@ -91,12 +91,10 @@ def event_pair_overhead(torch, n=200):
 
 
 def dist_init(local):
-    """NCCL process group for the ranks torchrun started.  NCCL's own banner ("NCCL version ...") goes to stdout
-    when NCCL_DEBUG=VERSION/INFO is inherited: stdout must carry exactly ONE JSON line, so keep it at WARN."""
+    """NCCL process group for the ranks torchrun started.  NCCL_DEBUG is left as the caller set it (the driver reads
+    the rank lines of NCCL_DEBUG=INFO); NCCL's log goes to stderr so that stdout carries exactly ONE JSON line."""
     import torch
     import torch.distributed as dist
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
-        os.environ["NCCL_DEBUG"] = "WARN"
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 

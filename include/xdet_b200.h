@@ -252,6 +252,57 @@ int xdet_maxpool3x3s2_f32(const float* d_src, float* d_dst, float* d_dst2, const
 int xdet_depthwise3x3_f32(const float* d_src, const float* d_weights, float* d_dst, int N, int H, int W, int C,
                           int dilation, int relu_in, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * fp32-ACCURATE convolution / GEMM on the tcgen05 tensor cores ("f16x2" precision, csrc/conv_gemm_f16x2.cu): the
+ * precision the parity claim (box / score deltas within 1e-4 of the reference's fp32 graph) is benchmarked at.
+ * Replaces the same TensorFlow layers as xdet_conv2d_bf16 (tf.layers.conv2d / dense: net/resnet_v2.py:89-100,
+ * 320-325, net/xception_body.py:224-233,381-400,450-475,540-558), computed to fp32-level error.
+ * Operands are "f16x2 planes": every fp32 value v is two fp16 values hi = fp16(v), lo = fp16((v - hi) * 2^11), stored
+ * as two planes of the same layout (`*_plane` = elements between the planes).  |v| must stay below 65504 (fp16's
+ * range; larger values saturate) -- weights are pre-scaled per output channel by a power of two by the host, the
+ * inverse scale goes into `scale`.
+ * Input  : planes [2][N,H,W,in_cs] fp16 (NHWC, in_cs % 8 == 0), written by xdet_split2_f16 or by the previous
+ *          convolution's epilogue (out_pair / out2_pair).
+ * Weights: planes [2][Cout][KH*KW][ceil(Cin/64)*64] fp16 (tap-major, as xdet_conv2d_bf16).
+ * Output : v = acc*scale[c] + bias[c] (+ residual, fp32, laid out like `out`) (ReLU if relu), where acc is the fp32
+ *          sum over the reduction, accumulated in chunks of <= chunk_kb*64 elements (the tensor core's fp32 accumulator
+ *          truncates; chunk sums are added with round-to-nearest in registers);
+ *          out (fp32, element strides out_s*, NULL = not stored), out_pair (f16x2 planes [2][N*Hout*Wout][pair_cs] of v);
+ *          out2 = ReLU(v*scale2[c] + bias2[c]) (fp32, laid out like `out`) and out2_pair, all optional.
+ * fold_w / in_wp as in xdet_conv_desc (the few-channel stem on a row-padded NHWC8 image). */
+typedef struct {
+  int N, H, W, Cin, in_cs;
+  int Cout, KH, KW, dil_h, dil_w, pad_top, pad_left;
+  int Hout, Wout;
+  int stride_h, stride_w;
+  int fold_w, in_wp;
+  long long in_plane; /* elements between the hi and lo planes of the input */
+  const void* weights;
+  long long w_plane;  /* elements between the hi and lo planes of the weights */
+  const float* scale;
+  const float* bias;
+  int relu;
+  const float* residual;
+  float* out;
+  long long out_sn, out_sy, out_sx, out_sc;
+  void* out_pair;
+  long long pair_plane;
+  int pair_cs;
+  float* out2;
+  const float* scale2;
+  const float* bias2;
+  void* out2_pair;
+  int block_n;  /* 0 = auto; 32, 64 or 128 */
+  int chunk_kb; /* 0 = 12: k-blocks (of 64 reduction elements) per accumulator flush */
+  int max_ctas;
+} xdet_conv_f16x2_desc;
+int xdet_conv2d_f16x2(const void* d_in_pair, const xdet_conv_f16x2_desc* desc, void* stream);
+/* fp32 (element (n,y,x,c) at n*sn + y*sy + x*sx + c*sc) -> f16x2 planes [2][N,H,Wp,cs]: pixel (n,y,x) is written at
+ * ((n*H + y)*Wp + x + x_off)*cs, channels C..cs-1 as zeros; only those pixels are written (a caller that pads rows,
+ * Wp > W, zero-fills the buffer once).  relu != 0 applies ReLU first. */
+int xdet_split2_f16(const float* d_src, long long sn, long long sy, long long sx, long long sc, int N, int H, int W,
+                    int C, void* d_dst, int cs, int Wp, int x_off, long long plane, int relu, void* stream);
+
 /* Input pipeline of the eval / test scripts.
  * Replaces: light_head_preprocess_for_eval / _for_test preprocessing/common_preprocessing.py:383-458 with
  *   resize = WARP_RESIZE (the scripts' default): convert_image_dtype(uint8 -> float32) * 2, tf_image_whitened

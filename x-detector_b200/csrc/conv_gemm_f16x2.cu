@@ -1,0 +1,639 @@
+// fp32-ACCURATE implicit-GEMM convolution / GEMM on the tcgen05 tensor cores ("f16x2" precision).
+//
+// The reference computes every tf.layers.conv2d / dense in fp32 (net/resnet_v2.py:89-100, net/xception_body.py:
+// 224-233,381-400,450-475,540-558) and north_star asks for box / score deltas within 1e-4 of it.  bf16 operands
+// cannot hold that (~1e-2 per stage), so this kernel is the precision the parity claim is benchmarked at.
+//
+//   every fp32 operand v is carried as TWO fp16 values      hi = fp16(v),  lo = fp16((v - hi) * 2^11)
+//   (v = hi + lo*2^-11 to 2^-22 |v|; weights are pre-scaled per output channel by a power of two so that they sit in
+//   fp16's normal range, the inverse scale is folded into the epilogue's `scale` vector), and a product is THREE
+//   tensor-core products into TWO fp32 TMEM accumulators:
+//       acc0 += A_hi * B_hi                     (magnitude 1)
+//       acc1 += A_hi * B_lo + A_lo * B_hi       (magnitude 2^-11 of acc0, carried at 2^11 x its weight)
+//   (the lo*lo term is below 2^-22 of the result and is dropped).  Every fp16 x fp16 product is exact in fp32.
+//   The tensor core's accumulator TRUNCATES, so the error of acc0 grows with the number of accumulation steps:
+//   the reduction is therefore cut into chunks of <= chunk_kb k-blocks (768 reduction elements by default, 48
+//   steps); after each chunk the epilogue warps read both accumulators from TMEM and add  acc0 + acc1 * 2^-11  to
+//   a running fp32 sum held in REGISTERS with round-to-nearest, while the MMA warp already works on the next chunk
+//   in the other TMEM buffer.  One launch per layer, whatever its reduction length.
+//
+// Same structure as conv_gemm.cu (persistent CTAs, warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-9 = epilogue;
+// no im2col: a filter tap is the same 4-D TMA box at shifted coordinates, out-of-bounds zero fill = SAME padding),
+// with these differences: 4 operand tiles per stage (A_hi, A_lo, B_hi, B_lo), the epilogue groups split the tile's
+// COLUMNS (group g owns columns [g*BN/2, (g+1)*BN/2)), outputs are fp32 (any strides: NHWC for the next layer,
+// NCHW for PsRoIAlign) written straight from registers, and the epilogue can also emit the f16x2 split of its
+// outputs so that the next convolution needs no separate split pass.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace xdet {
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 320;     // TMA, MMA, 8 epilogue warps (2 column groups x 4 TMEM quadrants)
+constexpr int kEpiThreads = 256;
+constexpr int kMaxStages = 8;
+constexpr int kMaxBN = 128;
+constexpr float kLoScale = 2048.f;            // 2^11
+constexpr float kLoInv = 1.f / 2048.f;
+constexpr size_t kSmemCapShared = 211 * 1024;
+constexpr size_t kSmemCapAlone = 227 * 1024;
+
+struct PairArgs {
+  int tiles_x, tiles_y, n_tiles_n, total_tiles;
+  int BW, BH;
+  int Hout, Wout, Cout;
+  int taps_w, dil_h, dil_w, pad_top, pad_left, mul_x, mul_y;
+  int k_chunks_per_tap, num_k_blocks, chunk_kb;
+  int BN, stages, tmem_cols;
+  const float* scale;
+  const float* bias;
+  int relu;
+  const float* residual;
+  float* out;
+  long long out_sn, out_sy, out_sx, out_sc;
+  __half* out_pair;      // [2][N*Hout*Wout][pair_cs] or null
+  long long pair_plane;  // elements between the hi and lo planes of out_pair / out2_pair
+  int pair_cs;
+  float* out2;
+  const float* scale2;
+  const float* bias2;
+  __half* out2_pair;
+  int vec_ok;  // fp32 NHWC rows allow float4 access (out_sc == 1, 16-byte aligned pixel strides and bases)
+};
+
+struct TileCoord {
+  int x0, y0, img, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const PairArgs& p, int t) {
+  TileCoord c;
+  const int nt = t % p.n_tiles_n;
+  int mt = t / p.n_tiles_n;
+  c.n0 = nt * p.BN;
+  c.x0 = (mt % p.tiles_x) * p.BW;
+  mt /= p.tiles_x;
+  c.y0 = (mt % p.tiles_y) * p.BH;
+  c.img = mt / p.tiles_y;
+  return c;
+}
+
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// kind::f16 instruction descriptor with fp16 operands (a_format = b_format = 0), fp32 accumulator
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// v -> (hi, lo) of the f16x2 representation; saturating conversions keep out-of-range values finite
+__device__ __forceinline__ void split_f16x2(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+  const float r = __fsub_rn(v, __half2float(hi));  // exact for |v| <= 65504
+  lo = __float2half_rn(fminf(fmaxf(__fmul_rn(r, kLoScale), -65504.f), 65504.f));
+}
+
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+// CG = columns per epilogue group (BN = 2*CG)
+template <int CG>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                       const PairArgs p) {
+  constexpr int BN = 2 * CG;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr uint32_t a_bytes = kBM * kBK * 2;
+  constexpr uint32_t b_bytes = (uint32_t)BN * kBK * 2;
+  constexpr uint32_t b_pad = (b_bytes + 1023u) & ~1023u;
+  constexpr uint32_t stage_bytes = 2 * a_bytes + 2 * b_pad;
+  unsigned char* tiles = smem;
+  float* sbuf = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);  // [4][kMaxBN]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sbuf + 4 * kMaxBN);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full_bar = empty_bar + kMaxStages;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&map_a_hi);
+    ptx::prefetch_tmap(&map_a_lo);
+    ptx::prefetch_tmap(&map_b_hi);
+    ptx::prefetch_tmap(&map_b_lo);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) {
+        ptx::mbar_init(&full_bar[s], 1);
+        ptx::mbar_init(&empty_bar[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        ptx::mbar_init(&tmem_full_bar[s], 1);
+        ptx::mbar_init(&tmem_empty_bar[s], 8);  // one arrival per epilogue warp
+      }
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_ptr, (uint32_t)p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
+
+  const int nchunks = (p.num_k_blocks + p.chunk_kb - 1) / p.chunk_kb;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        const int ax = tc.x0 * p.mul_x - p.pad_left, ay = tc.y0 * p.mul_y - p.pad_top;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          const int tap = kb / p.k_chunks_per_tap, cc = kb - tap * p.k_chunks_per_tap;
+          const int kh = tap / p.taps_w, kw = tap - kh * p.taps_w;
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* s_ahi = tiles + (size_t)stage * stage_bytes;
+          unsigned char* s_alo = s_ahi + a_bytes;
+          unsigned char* s_bhi = s_alo + a_bytes;
+          unsigned char* s_blo = s_bhi + b_pad;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * a_bytes + 2 * b_bytes);
+          const int cx = ax + kw * p.dil_w, cy = ay + kh * p.dil_h;
+          ptx::tma_load_4d(s_ahi, &map_a_hi, &full_bar[stage], cc * kBK, cx, cy, tc.img);
+          ptx::tma_load_4d(s_alo, &map_a_lo, &full_bar[stage], cc * kBK, cx, cy, tc.img);
+          ptx::tma_load_2d(s_bhi, &map_b_hi, &full_bar[stage], kb * kBK, tc.n0);
+          ptx::tma_load_2d(s_blo, &map_b_lo, &full_bar[stage], kb * kBK, tc.n0);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer: one accumulator pair per CHUNK of the reduction =====
+    constexpr uint32_t idesc = make_idesc_f16(kBM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t g = 0;  // running chunk index: TMEM buffer g & 1, barrier parity (g >> 1) & 1
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int kb0 = 0; kb0 < p.num_k_blocks; kb0 += p.chunk_kb, ++g) {
+        const int kb1 = min(kb0 + p.chunk_kb, p.num_k_blocks);
+        const uint32_t buf = g & 1u;
+        ptx::mbar_wait(&tmem_empty_bar[buf], ((g >> 1) & 1u) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d0 = tmem_base + buf * (2u * BN);
+        const uint32_t d1 = d0 + (uint32_t)BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          if (lane == 0) {
+            const uint32_t s_ahi = ptx::smem_u32(tiles + (size_t)stage * stage_bytes);
+            const uint32_t s_alo = s_ahi + a_bytes;
+            const uint32_t s_bhi = s_alo + a_bytes;
+            const uint32_t s_blo = s_bhi + b_pad;
+#pragma unroll
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              const uint64_t dah = ptx::make_smem_desc_sw128(s_ahi + k * kUmmaK * 2);
+              const uint64_t dal = ptx::make_smem_desc_sw128(s_alo + k * kUmmaK * 2);
+              const uint64_t dbh = ptx::make_smem_desc_sw128(s_bhi + k * kUmmaK * 2);
+              const uint64_t dbl = ptx::make_smem_desc_sw128(s_blo + k * kUmmaK * 2);
+              const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+              ptx::mma_bf16_ss(d0, dah, dbh, idesc, acc);
+              ptx::mma_bf16_ss(d1, dah, dbl, idesc, acc);
+              ptx::mma_bf16_ss(d1, dal, dbh, idesc, 1u);
+            }
+            ptx::mma_commit(&empty_bar[stage]);
+            if (kb == kb1 - 1) ptx::mma_commit(&tmem_full_bar[buf]);
+          }
+          __syncwarp();
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5 = column group 0, warps 6..9 = column group 1; TMEM quadrant = warp % 4 =====
+    const int grp = (warp - 2) >> 2;
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;  // row of the tile == TMEM lane
+    const int e = threadIdx.x - 64;  // 0..255 among the epilogue threads
+    uint32_t g = 0;
+    float sum[CG];
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t);
+      // per-tile scale / bias vectors -> shared memory (every epilogue thread is past the previous tile's reads)
+      ptx::named_bar_sync(1, kEpiThreads);
+      for (int i = e; i < BN; i += kEpiThreads) {
+        const int c = tc.n0 + i;
+        const bool ok = c < p.Cout;
+        sbuf[i] = (ok && p.scale) ? __ldg(p.scale + c) : 1.f;
+        sbuf[kMaxBN + i] = (ok && p.bias) ? __ldg(p.bias + c) : 0.f;
+        sbuf[2 * kMaxBN + i] = (ok && p.scale2) ? __ldg(p.scale2 + c) : 1.f;
+        sbuf[3 * kMaxBN + i] = (ok && p.bias2) ? __ldg(p.bias2 + c) : 0.f;
+      }
+      ptx::named_bar_sync(1, kEpiThreads);
+
+      for (int ch = 0; ch < nchunks; ++ch, ++g) {
+        const uint32_t buf = g & 1u;
+        ptx::mbar_wait(&tmem_full_bar[buf], (g >> 1) & 1u);
+        ptx::tc_fence_after();
+        const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (2u * BN) + (uint32_t)(grp * CG);
+#pragma unroll
+        for (int u = 0; u < CG / 16; ++u) {
+          uint32_t r0[16], r1[16];
+          tmem_ld_32x16(t0 + (uint32_t)(u * 16), r0);
+          tmem_ld_32x16(t0 + (uint32_t)(BN + u * 16), r1);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float part = __fmaf_rn(__uint_as_float(r1[j]), kLoInv, __uint_as_float(r0[j]));
+            sum[u * 16 + j] = (ch == 0) ? part : __fadd_rn(sum[u * 16 + j], part);
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
+      }
+
+      // ---- the tile's outputs, straight from registers ----
+      const int py = tc.y0 + m / p.BW, px = tc.x0 + m % p.BW;
+      if (py < p.Hout && px < p.Wout) {
+        const long long pix_off = (long long)tc.img * p.out_sn + (long long)py * p.out_sy + (long long)px * p.out_sx;
+        const long long pix_lin = ((long long)tc.img * p.Hout + py) * p.Wout + px;
+#pragma unroll
+        for (int u = 0; u < CG / 16; ++u) {
+          const int cl = grp * CG + u * 16;  // column inside the tile
+          const int c0 = tc.n0 + cl;         // output channel
+          if (c0 >= p.Cout) continue;
+          const int nv = min(16, p.Cout - c0);
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __fmaf_rn(sum[u * 16 + j], sbuf[cl + j], sbuf[kMaxBN + cl + j]);
+          const bool vec = p.vec_ok && nv == 16;
+          if (p.residual) {
+            const float* rp = p.residual + pix_off + (long long)c0 * p.out_sc;
+            if (vec) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 f = __ldg(reinterpret_cast<const float4*>(rp) + q);
+                v[4 * q] = __fadd_rn(v[4 * q], f.x);
+                v[4 * q + 1] = __fadd_rn(v[4 * q + 1], f.y);
+                v[4 * q + 2] = __fadd_rn(v[4 * q + 2], f.z);
+                v[4 * q + 3] = __fadd_rn(v[4 * q + 3], f.w);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < nv) v[j] = __fadd_rn(v[j], __ldg(rp + (long long)j * p.out_sc));
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (p.out) {
+            float* op = p.out + pix_off + (long long)c0 * p.out_sc;
+            if (vec) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                reinterpret_cast<float4*>(op)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < nv) op[(long long)j * p.out_sc] = v[j];
+            }
+          }
+          if (p.out_pair) {
+            // pair_cs is a multiple of 8 and c0 of 16: whole 16-byte units; channels beyond Cout get zeros
+            __half hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) split_f16x2(j < nv ? v[j] : 0.f, hi[j], lo[j]);
+            __half* hp = p.out_pair + pix_lin * p.pair_cs + c0;
+            __half* lp = hp + p.pair_plane;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              if (c0 + 8 * q < p.pair_cs) {
+                reinterpret_cast<uint4*>(hp)[q] = make_uint4(pack_h2(hi[8 * q], hi[8 * q + 1]), pack_h2(hi[8 * q + 2], hi[8 * q + 3]),
+                                                             pack_h2(hi[8 * q + 4], hi[8 * q + 5]), pack_h2(hi[8 * q + 6], hi[8 * q + 7]));
+                reinterpret_cast<uint4*>(lp)[q] = make_uint4(pack_h2(lo[8 * q], lo[8 * q + 1]), pack_h2(lo[8 * q + 2], lo[8 * q + 3]),
+                                                             pack_h2(lo[8 * q + 4], lo[8 * q + 5]), pack_h2(lo[8 * q + 6], lo[8 * q + 7]));
+              }
+            }
+          }
+          if (p.out2 || p.out2_pair) {
+            float w[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              w[j] = fmaxf(__fmaf_rn(v[j], sbuf[2 * kMaxBN + cl + j], sbuf[3 * kMaxBN + cl + j]), 0.f);
+            if (p.out2) {
+              float* op = p.out2 + pix_off + (long long)c0 * p.out_sc;
+              if (vec) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  reinterpret_cast<float4*>(op)[q] = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (j < nv) op[(long long)j * p.out_sc] = w[j];
+              }
+            }
+            if (p.out2_pair) {
+              __half hi[16], lo[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) split_f16x2(j < nv ? w[j] : 0.f, hi[j], lo[j]);
+              __half* hp = p.out2_pair + pix_lin * p.pair_cs + c0;
+              __half* lp = hp + p.pair_plane;
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                if (c0 + 8 * q < p.pair_cs) {
+                  reinterpret_cast<uint4*>(hp)[q] = make_uint4(pack_h2(hi[8 * q], hi[8 * q + 1]), pack_h2(hi[8 * q + 2], hi[8 * q + 3]),
+                                                               pack_h2(hi[8 * q + 4], hi[8 * q + 5]), pack_h2(hi[8 * q + 6], hi[8 * q + 7]));
+                  reinterpret_cast<uint4*>(lp)[q] = make_uint4(pack_h2(lo[8 * q], lo[8 * q + 1]), pack_h2(lo[8 * q + 2], lo[8 * q + 3]),
+                                                               pack_h2(lo[8 * q + 4], lo[8 * q + 5]), pack_h2(lo[8 * q + 6], lo[8 * q + 7]));
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// fp32 (any layout) -> f16x2 planes [2][N][H][Wp][cs]: pixel (n,y,x) at ((n*H + y)*Wp + x + x_off)*cs.  Only the
+// interior is written (the caller zero-fills padded layouts once).
+__global__ void __launch_bounds__(256) split2_kernel(const float* __restrict__ src, long long sn, long long sy,
+                                                     long long sx, long long sc, int H, int W, int C,
+                                                     __half* __restrict__ dst, int cs, int Wp, int x_off,
+                                                     long long plane, int relu, long long total) {
+  const long long step = (long long)gridDim.x * blockDim.x;
+  const int c8 = cs / 8;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
+    const int cb = (int)(e % c8) * 8;
+    const long long pix = e / c8;
+    const int x = (int)(pix % W);
+    const int y = (int)((pix / W) % H);
+    const long long n = pix / ((long long)W * H);
+    const float* s = src + n * sn + y * sy + x * sx + (long long)cb * sc;
+    __half hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = (cb + j < C) ? __ldg(s + (long long)j * sc) : 0.f;
+      if (relu) v = fmaxf(v, 0.f);
+      split_f16x2(v, hi[j], lo[j]);
+    }
+    __half* d = dst + ((n * H + y) * Wp + x + x_off) * cs + cb;
+    *reinterpret_cast<uint4*>(d) = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
+    *reinterpret_cast<uint4*>(d + plane) = make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7]));
+  }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  });
+  return fn;
+}
+
+int encode_f16(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box, const cuuint32_t* estr = nullptr) {
+  auto fn = encode_fn();
+  if (!fn) return fail(XDET_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+                  box, estr ? estr : ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(XDET_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return XDET_OK;
+}
+
+// N tile: 32 / 64 / 128.  Cost model as in conv_gemm.cu, with three products per k-block and twice the operand bytes.
+int pick_bn(int cout, long long m_tiles, int num_k_blocks) {
+  const int cands[3] = {128, 64, 32};
+  int best = 0;
+  double best_cost = 0;
+  for (int bn : cands) {
+    const long long tiles = m_tiles * ((cout + bn - 1) / bn);
+    const long long waves = (tiles + kNumSMs - 1) / kNumSMs;
+    const double per_kb = std::max(6.0 * bn, (32768.0 + bn * 256.0) / 56.0);
+    const double cost = (double)waves * (num_k_blocks * per_kb + 8.0 * bn + 800.0);
+    if (best == 0 || cost < best_cost * 0.98) {
+      best = bn;
+      best_cost = cost;
+    }
+  }
+  return best;
+}
+
+template <int CG>
+cudaError_t launch(const cudaLaunchConfig_t& cfg, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
+                   const CUtensorMap& b_hi, const CUtensorMap& b_lo, const PairArgs& a) {
+  cudaError_t e = cudaFuncSetAttribute(conv_gemm_f16x2_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  return cudaLaunchKernelEx(&cfg, conv_gemm_f16x2_kernel<CG>, a_hi, a_lo, b_hi, b_lo, a);
+}
+
+}  // namespace
+}  // namespace xdet
+
+using namespace xdet;
+
+extern "C" int xdet_conv2d_f16x2(const void* d_in_pair, const xdet_conv_f16x2_desc* d, void* stream) {
+  if (!d || !d_in_pair) return fail(XDET_EINVAL, "null argument");
+  if (d->N <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0 || d->KH <= 0 || d->KW <= 0)
+    return fail(XDET_EINVAL, "conv2d_f16x2: non-positive dimension");
+  if (d->Hout <= 0 || d->Wout <= 0) return fail(XDET_EINVAL, "conv2d_f16x2: non-positive output size");
+  if (d->in_cs < d->Cin || (d->in_cs % 8) != 0)
+    return fail(XDET_EINVAL, "conv2d_f16x2: input channel stride (%d) must be >= Cin and a multiple of 8", d->in_cs);
+  if ((reinterpret_cast<uintptr_t>(d_in_pair) & 15) || (reinterpret_cast<uintptr_t>(d->weights) & 15) ||
+      (d->in_plane % 8) != 0 || (d->w_plane % 8) != 0)
+    return fail(XDET_EINVAL, "conv2d_f16x2: operand planes must be 16-byte aligned");
+  const int sh = d->stride_h <= 0 ? 1 : d->stride_h, sw = d->stride_w <= 0 ? 1 : d->stride_w;
+  if (sh > 2 || sw > 2) return fail(XDET_EINVAL, "conv2d_f16x2: strides 1 and 2 are supported");
+  const int dil_h = d->dil_h <= 0 ? 1 : d->dil_h, dil_w = d->dil_w <= 0 ? 1 : d->dil_w;
+  const bool fold = d->fold_w != 0;
+  if (fold && (d->KW * d->in_cs > kBK || dil_w != 1 || d->in_wp < (d->Wout - 1) * sw + kBK / d->in_cs))
+    return fail(XDET_EINVAL, "conv2d_f16x2: fold_w needs KW*in_cs <= 64, dil_w == 1 and in_wp >= (Wout-1)*stride_w + 64/in_cs");
+  if (!d->out && !d->out_pair && !d->out2 && !d->out2_pair) return fail(XDET_EINVAL, "conv2d_f16x2: no output");
+  if ((d->out2 || d->out2_pair) && (!d->scale2 || !d->bias2))
+    return fail(XDET_EINVAL, "conv2d_f16x2: second output needs scale2 and bias2");
+  if ((d->out_pair || d->out2_pair) && (d->pair_cs < d->Cout || d->pair_cs % 8 != 0 || d->pair_plane % 8 != 0))
+    return fail(XDET_EINVAL, "conv2d_f16x2: pair_cs must be >= Cout and a multiple of 8");
+
+  int N = d->N, H = d->H, W = d->W, Hout = d->Hout, Wout = d->Wout;
+  long long out_sn = d->out_sn, out_sy = d->out_sy, out_sx = d->out_sx;
+  const bool pointwise = !fold && d->KH == 1 && d->KW == 1 && sh == 1 && sw == 1 && d->pad_top == 0 && d->pad_left == 0 &&
+                         Hout == H && Wout == W;
+  if (pointwise && out_sy == out_sx * W && out_sn == out_sy * H && (long long)N * H * W < (1ll << 31)) {
+    W = Wout = N * H * W;
+    H = Hout = 1;
+    N = 1;
+    out_sy = out_sn = out_sx * W;
+  }
+  const int kcpt = fold ? 1 : (d->Cin + kBK - 1) / kBK;
+  const int taps = fold ? d->KH : d->KH * d->KW;
+  const int ktot = taps * kcpt * kBK;
+
+  PairArgs a{};
+  int BW = 8;
+  while (BW < Wout && BW < kBM) BW <<= 1;
+  a.BW = BW;
+  a.BH = kBM / BW;
+  a.tiles_x = (Wout + a.BW - 1) / a.BW;
+  a.tiles_y = (Hout + a.BH - 1) / a.BH;
+  const long long m_tiles = (long long)a.tiles_x * a.tiles_y * N;
+  a.Hout = Hout;
+  a.Wout = Wout;
+  a.Cout = d->Cout;
+  a.taps_w = fold ? 1 : d->KW;
+  a.dil_h = dil_h;
+  a.dil_w = fold ? 0 : dil_w;
+  a.pad_top = d->pad_top;
+  a.pad_left = fold ? 0 : d->pad_left;
+  a.mul_x = fold ? 1 : sw;
+  a.mul_y = sh;
+  a.k_chunks_per_tap = kcpt;
+  a.num_k_blocks = taps * kcpt;
+  // equal chunks of at most chunk_kb k-blocks (default 12 = 768 reduction elements = 48 accumulation steps)
+  const int max_chunk = d->chunk_kb > 0 ? d->chunk_kb : 12;
+  const int nchunks = (a.num_k_blocks + max_chunk - 1) / max_chunk;
+  a.chunk_kb = (a.num_k_blocks + nchunks - 1) / nchunks;
+
+  int BN = d->block_n > 0 ? d->block_n : pick_bn(d->Cout, m_tiles, a.num_k_blocks);
+  if (BN != 32 && BN != 64 && BN != 128) return fail(XDET_EINVAL, "conv2d_f16x2: block_n must be 32, 64 or 128");
+  const size_t tail = 4 * kMaxBN * sizeof(float) + (2 * kMaxStages + 4) * sizeof(uint64_t) + 64;
+  const size_t cap = d->max_ctas > 0 ? kSmemCapShared : kSmemCapAlone;
+  const size_t stage_bytes = 2 * (size_t)kBM * kBK * 2 + 2 * ((((size_t)BN * kBK * 2) + 1023) & ~(size_t)1023);
+  int stages = (int)((cap - 1024 - tail) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return fail(XDET_EINVAL, "conv2d_f16x2: tile does not fit shared memory");
+  a.BN = BN;
+  a.stages = stages;
+  a.tmem_cols = 4 * BN;  // two buffers x (acc0 + acc1): 128 / 256 / 512 columns
+  a.n_tiles_n = (d->Cout + BN - 1) / BN;
+  const long long total = m_tiles * a.n_tiles_n;
+  if (total >= (1ll << 31)) return fail(XDET_EINVAL, "conv2d_f16x2: too many tiles");
+  a.total_tiles = (int)total;
+  a.scale = d->scale;
+  a.bias = d->bias;
+  a.relu = d->relu;
+  a.residual = d->residual;
+  a.out = d->out;
+  a.out_sn = out_sn;
+  a.out_sy = out_sy;
+  a.out_sx = out_sx;
+  a.out_sc = d->out_sc;
+  a.out_pair = reinterpret_cast<__half*>(d->out_pair);
+  a.pair_plane = d->pair_plane;
+  a.pair_cs = d->pair_cs;
+  a.out2 = d->out2;
+  a.scale2 = d->scale2;
+  a.bias2 = d->bias2;
+  a.out2_pair = reinterpret_cast<__half*>(d->out2_pair);
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  a.vec_ok = (d->out_sc == 1 && out_sx % 4 == 0 && out_sy % 4 == 0 && out_sn % 4 == 0 && al16(d->out) && al16(d->out2) &&
+              al16(d->residual)) ? 1 : 0;
+
+  CUtensorMap map_a[2], map_b[2];
+  for (int pl = 0; pl < 2; ++pl) {
+    const __half* base = reinterpret_cast<const __half*>(d_in_pair) + (size_t)pl * d->in_plane;
+    if (fold) {
+      const cuuint64_t dims[4] = {(cuuint64_t)kBK, (cuuint64_t)Wout, (cuuint64_t)H, (cuuint64_t)N};
+      const cuuint64_t strides[3] = {(cuuint64_t)sw * d->in_cs * 2, (cuuint64_t)d->in_wp * d->in_cs * 2,
+                                     (cuuint64_t)d->in_wp * d->in_cs * 2 * H};
+      const cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)a.BW, (cuuint32_t)(a.BH * sh), 1};
+      const cuuint32_t estr[4] = {1, 1, (cuuint32_t)sh, 1};
+      XDET_TRY(encode_f16(&map_a[pl], base, 4, dims, strides, box, estr));
+    } else {
+      if (a.BW * sw > 256 || a.BH * sh > 256) return fail(XDET_EINVAL, "conv2d_f16x2: strided tile exceeds the TMA box limit");
+      const cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+      const cuuint64_t strides[3] = {(cuuint64_t)d->in_cs * 2, (cuuint64_t)d->in_cs * 2 * W,
+                                     (cuuint64_t)d->in_cs * 2 * W * H};
+      const cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)(a.BW * sw), (cuuint32_t)(a.BH * sh), 1};
+      const cuuint32_t estr[4] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1};
+      XDET_TRY(encode_f16(&map_a[pl], base, 4, dims, strides, box, estr));
+    }
+    const __half* wbase = reinterpret_cast<const __half*>(d->weights) + (size_t)pl * d->w_plane;
+    const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)d->Cout};
+    const cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)BN};
+    XDET_TRY(encode_f16(&map_b[pl], wbase, 2, dims, strides, box));
+  }
+  const size_t smem = (size_t)stages * stage_bytes + tail + 1024;
+  int sms = kNumSMs;
+  if (d->max_ctas > 0 && d->max_ctas < sms) sms = d->max_ctas;
+  const int grid = a.total_tiles < sms ? a.total_tiles : sms;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = d->max_ctas <= 0 ? 1 : 0;
+  cudaError_t le;
+  if (BN == 128) le = launch<64>(cfg, map_a[0], map_a[1], map_b[0], map_b[1], a);
+  else if (BN == 64) le = launch<32>(cfg, map_a[0], map_a[1], map_b[0], map_b[1], a);
+  else le = launch<16>(cfg, map_a[0], map_a[1], map_b[0], map_b[1], a);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return check_cuda(le != cudaSuccess ? le : cudaGetLastError(), "conv_gemm_f16x2_kernel");
+}
+
+extern "C" int xdet_split2_f16(const float* d_src, long long sn, long long sy, long long sx, long long sc, int N, int H,
+                               int W, int C, void* d_dst, int cs, int Wp, int x_off, long long plane, int relu,
+                               void* stream) {
+  if (N < 0 || H < 0 || W < 0 || C <= 0) return fail(XDET_EINVAL, "split2: bad shape");
+  if (cs < C || cs % 8 != 0 || plane % 8 != 0 || Wp < W + x_off || x_off < 0)
+    return fail(XDET_EINVAL, "split2: cs (%d) must be >= C and %% 8 == 0, Wp >= W + x_off", cs);
+  if (reinterpret_cast<uintptr_t>(d_dst) & 15) return fail(XDET_EINVAL, "split2: destination must be 16-byte aligned");
+  const long long total = (long long)N * H * W * (cs / 8);
+  if (total == 0) return XDET_OK;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+  split2_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_src, sn, sy, sx, sc, H, W, C,
+                                                                   reinterpret_cast<__half*>(d_dst), cs, Wp, x_off, plane,
+                                                                   relu, total);
+  return after_launch("split2_kernel");
+}

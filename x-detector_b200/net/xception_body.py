@@ -223,7 +223,7 @@ def get_head(net_input, pooling_op, grid_width, grid_height, loss_func, proposal
         kc, bc = _dense_vars(store, "fc_cls", 2048, num_classes)
         kl, bl = _dense_vars(store, "fc_loc", 2048, 4)
     w1 = _derived(store, ("w", k1[0]), lambda: ops.pack_conv_weight(k1[1].t().reshape(2048, cin, 1, 1)))
-    if ops.conv.PRECISION == "fp32x3":  # parity mode: the pooled features stay fp32 (split inside conv2d_nhwc)
+    if ops.conv.PRECISION in ("f16x2", "fp32x3"):  # fp32 activations: the pooled features are split inside conv2d_nhwc
         h = ops.conv2d_nhwc(feat.reshape(1, 1, N * R, cin), w1, 2048, 1, 1, bias=b1[1], relu=True)
     else:
         pitch = (cin + 7) // 8 * 8  # TMA rows must be 16-byte multiples

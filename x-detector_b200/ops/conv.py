@@ -31,10 +31,15 @@ class ConvDesc(ctypes.Structure):
 
 # Arithmetic of the convolutions / dense layers:
 #   "bf16"   (default, the throughput path) bf16 operands, fp32 accumulate;
-#   "fp32x3" PARITY MODE (csrc/parity_ops.cu): activations stay fp32 between layers and every operand is split
-#            into three bf16 pieces; one convolution over 6*Cin channels sums the six significant cross products
-#            in the fp32 accumulator -> fp32-level error, for the end-to-end 1e-4 parity tests.  ~8x slower.
+#   "f16x2"  fp32-ACCURATE mode (csrc/conv_gemm_f16x2.cu), the precision the parity claim is benchmarked at:
+#            activations stay fp32 between layers; every operand is carried as two fp16 values (hi, lo*2^11), one
+#            kernel launch per layer issues three tensor-core products into two TMEM accumulators and flushes them
+#            into fp32 registers with round-to-nearest every <= 768 reduction elements -> fp32-level error.
+#   "fp32x3" the first parity mode (csrc/parity_ops.cu): three bf16 pieces per operand, one convolution over 6*Cin
+#            channels through the bf16 kernel, long reductions as several launches.  Kept as a second opinion
+#            for the tests; ~20x slower than bf16.
 PRECISION = "bf16"
+PRECISIONS = ("bf16", "f16x2", "fp32x3")
 
 
 class precision(object):
@@ -42,7 +47,7 @@ class precision(object):
     A VariableStore caches packed weights, so use one store (one model object) per precision."""
 
     def __init__(self, mode):
-        assert mode in ("bf16", "fp32x3"), mode
+        assert mode in PRECISIONS, mode
         self.mode = mode
 
     def __enter__(self):
@@ -64,10 +69,112 @@ def split3_values(w):
     return hi, mid, lo
 
 
+class PairWeight(object):
+    """Weights of one convolution / dense layer in "f16x2" precision: fp16 planes [2][Cout][taps*ceil(Cin/64)*64]
+    (hi, lo*2^11) of ``w * 2^e[c]`` -- a per-output-channel power of two that lifts the channel's largest weight into
+    [2^8, 2^9), far from fp16's subnormals -- and ``winv`` = 2^-e[c], which the epilogue's scale vector absorbs
+    (exact).  ``fold_cs``: the fold_w layout [Cout][KH][64] of the few-channel stem."""
+
+    def __init__(self, w_oihw, fold_cs=None):
+        w = w_oihw.float()
+        cout, cin, kh, kw = w.shape
+        amax = w.abs().reshape(cout, -1).amax(dim=1).clamp_min(1e-30)
+        e = torch.floor(8.0 - torch.log2(amax))
+        sc = torch.exp2(e)
+        self.winv = torch.exp2(-e).contiguous()
+        w = w * sc.view(-1, 1, 1, 1)  # exact (power of two)
+        if fold_cs is None:
+            cpad = (cin + 63) // 64 * 64
+            flat = torch.zeros((cout, kh * kw, cpad), dtype=torch.float32, device=w.device)
+            flat[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
+            flat = flat.reshape(cout, kh * kw * cpad)
+        else:
+            assert cin <= fold_cs and kw * fold_cs <= 64
+            flat = torch.zeros((cout, kh, 64), dtype=torch.float32, device=w.device)
+            flat[:, :, :kw * fold_cs].view(cout, kh, kw, fold_cs)[..., :cin] = w.permute(0, 2, 3, 1)
+            flat = flat.reshape(cout, kh * 64)
+        hi = flat.to(torch.float16)
+        lo = ((flat - hi.float()) * 2048.0).to(torch.float16)
+        self.planes = torch.stack([hi, lo]).contiguous()
+        self.cout = cout
+        self._scales = {}
+
+    def data_ptr(self):
+        return self.planes.data_ptr()
+
+    def scale_eff(self, scale):
+        """``scale * winv`` (exact), cached per scale tensor (recomputed if the tensor was written since)."""
+        if scale is None:
+            return self.winv
+        key = scale.data_ptr()
+        hit = self._scales.get(key)
+        if hit is None or hit[0] is not scale or hit[1] != scale._version:
+            hit = (scale, scale._version, (scale.float() * self.winv).contiguous())
+            self._scales[key] = hit
+        return hit[2]
+
+
+class ConvF16x2Desc(ctypes.Structure):
+    _fields_ = [
+        ("N", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int), ("Cin", ctypes.c_int), ("in_cs", ctypes.c_int),
+        ("Cout", ctypes.c_int), ("KH", ctypes.c_int), ("KW", ctypes.c_int), ("dil_h", ctypes.c_int),
+        ("dil_w", ctypes.c_int), ("pad_top", ctypes.c_int), ("pad_left", ctypes.c_int),
+        ("Hout", ctypes.c_int), ("Wout", ctypes.c_int),
+        ("stride_h", ctypes.c_int), ("stride_w", ctypes.c_int), ("fold_w", ctypes.c_int), ("in_wp", ctypes.c_int),
+        ("in_plane", ctypes.c_longlong), ("weights", ctypes.c_void_p), ("w_plane", ctypes.c_longlong),
+        ("scale", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("relu", ctypes.c_int),
+        ("residual", ctypes.c_void_p), ("out", ctypes.c_void_p),
+        ("out_sn", ctypes.c_longlong), ("out_sy", ctypes.c_longlong), ("out_sx", ctypes.c_longlong),
+        ("out_sc", ctypes.c_longlong),
+        ("out_pair", ctypes.c_void_p), ("pair_plane", ctypes.c_longlong), ("pair_cs", ctypes.c_int),
+        ("out2", ctypes.c_void_p), ("scale2", ctypes.c_void_p), ("bias2", ctypes.c_void_p),
+        ("out2_pair", ctypes.c_void_p),
+        ("block_n", ctypes.c_int), ("chunk_kb", ctypes.c_int), ("max_ctas", ctypes.c_int),
+    ]
+
+
+# k-blocks (64 reduction elements each) per accumulator flush of the f16x2 kernel; 0 = the library default (12)
+F16X2_CHUNK_KB = 0
+# the f16x2 epilogue also writes the split planes of its NHWC outputs (the next convolution then needs no split pass)
+F16X2_FUSE_SPLIT = True
+
+
+def split2(x, cin=None, relu=False, pad_w=None):
+    """fp32 [N,H,W,C] (any strides) -> f16x2 planes [2,N,H,Wp,ceil8(C)] fp16: hi = fp16(v), lo = fp16((v-hi)*2^11)
+    (csrc/conv_gemm_f16x2.cu).  ``pad_w`` = (Wp, x_off): row-padded layout for the fold_w stem (zero padding)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+    N, H, W, C = x.shape
+    cin = C if cin is None else cin
+    cs = (cin + 7) // 8 * 8
+    if pad_w is None:
+        Wp, x_off = W, 0
+        out = torch.empty((2, N, H, Wp, cs), dtype=torch.float16, device=x.device)
+    else:
+        Wp, x_off = pad_w
+        out = torch.zeros((2, N, H, Wp, cs), dtype=torch.float16, device=x.device)
+    sn, sy, sx, sc = x.stride()
+    with torch.cuda.device(x.device):
+        rc = _native.lib().xdet_split2_f16(x.data_ptr(), sn, sy, sx, sc, N, H, W, cin, out.data_ptr(), cs, Wp, x_off,
+                                           out.stride(0), 1 if relu else 0, torch.cuda.current_stream().cuda_stream)
+    _native.check(rc)
+    return out
+
+
+def pair_of(x, cin=None):
+    """The f16x2 planes of an fp32 NHWC activation: the ones its producer attached, else a split pass."""
+    p = getattr(x, "_pair", None)
+    if p is not None and p.shape[1:4] == x.shape[0:3]:
+        return p
+    return split2(x, cin)
+
+
+
 def pack_conv_weight(w_oihw):
     """[Cout, Cin, KH, KW] float -> bf16 [Cout, KH*KW*ceil(Cin/64)*64] (tap-major, channels zero-padded).
     In "fp32x3" precision the input-channel axis becomes the six blocks [mid|hi|lo|hi|mid|hi] that pair with the
     activation blocks [mid|lo|hi|mid|hi|hi] written by ``split3``."""
+    if PRECISION == "f16x2":
+        return PairWeight(w_oihw)
     if PRECISION == "fp32x3":
         hi, mid, lo = split3_values(w_oihw)
         w_oihw = torch.cat([mid, hi, lo, hi, mid, hi], dim=1)
@@ -82,6 +189,8 @@ def pack_fold_weight(w_oihw, cs=8):
     """[Cout, Cin<=cs, KH, KW] float -> bf16 [Cout, KH*64] for the fold_w mode: element kw*cs + ci of filter row kh.
     ("fp32x3" precision has no fold mode: the generic split pack is returned and ``conv2d_image_fold`` runs the
     generic strided convolution.)"""
+    if PRECISION == "f16x2":
+        return PairWeight(w_oihw, fold_cs=cs)
     if PRECISION == "fp32x3":
         return pack_conv_weight(w_oihw)
     cout, cin, kh, kw = w_oihw.shape
@@ -172,6 +281,10 @@ def conv2d_nhwc(x, w_packed, cout, kh, kw, *, dilation=(1, 1), padding="SAME", s
                 block_n=0, strides=(1, 1), fold_w=None, skip_out=False, epi_groups=0):
     """x: [N,H,W,C] bf16 (channel stride may be padded: pass the true ``cin``).  Returns the output tensor
     ([N,Ho,Wo,Cout] bf16 for 'nhwc_bf16', [N,Cout,Ho,Wo] fp32 for 'nchw_f32', [N,Ho,Wo,Cout] fp32 for 'nhwc_f32')."""
+    if isinstance(w_packed, PairWeight):
+        return _conv2d_f16x2(x, w_packed, cout, kh, kw, dilation=dilation, padding=padding, scale=scale, bias=bias,
+                             relu=relu, residual=residual, out=out, out_layout=out_layout, out2=out2, scale2=scale2,
+                             bias2=bias2, cin=cin, block_n=block_n, strides=strides, fold_w=fold_w, skip_out=skip_out)
     if x.dtype == torch.float32:  # parity mode: fp32 activations
         return _conv2d_fp32x3(x, w_packed, cout, kh, kw, dilation=dilation, padding=padding, scale=scale, bias=bias,
                               relu=relu, residual=residual, out=out, out_layout=out_layout, out2=out2, scale2=scale2,
@@ -347,6 +460,82 @@ def _conv2d_fp32x3(x, w_packed, cout, kh, kw, *, dilation, padding, scale, bias,
     return y
 
 
+def _conv2d_f16x2(x, w, cout, kh, kw, *, dilation, padding, scale, bias, relu, residual, out, out_layout, out2, scale2,
+                  bias2, cin, block_n, strides, fold_w, skip_out):
+    """``conv2d_nhwc`` in "f16x2" precision.  ``x``: fp32 NHWC activation (its split planes are taken from the
+    producer when attached, else made here), or -- fold_w mode -- the row-padded f16x2 image planes themselves.
+    Outputs are fp32 (the NHWC ones carry their own split planes for the next convolution)."""
+    dh, dw_ = dilation
+    sh, sw = strides
+    if fold_w is not None:
+        planes = x  # [2,N,H,in_wp,8]
+        _, N, H, in_wp, cs = planes.shape
+        W = fold_w[0]
+        cin = cs if cin is None else cin
+    else:
+        assert x.dtype == torch.float32 and x.dim() == 4
+        N, H, W, C = x.shape
+        cin = C if cin is None else cin
+        planes = pair_of(x, cin)
+        cs = planes.shape[-1]
+        in_wp = 0
+    if padding == "SAME":
+        pt, pl = same_pad(H, kh, dh, sh), same_pad(W, kw, dw_, sw)
+        Ho, Wo = -(-H // sh), -(-W // sw)
+    elif padding == "VALID":
+        pt = pl = 0
+        Ho, Wo = (H - (kh - 1) * dh - 1) // sh + 1, (W - (kw - 1) * dw_ - 1) // sw + 1
+    else:
+        pt, pl, Ho, Wo = padding
+    if fold_w is not None:
+        assert pl == fold_w[1], "the materialised left padding must equal the convolution's"
+    dev = planes.device
+    layout = "nhwc_f32" if out_layout == "nhwc_bf16" else out_layout
+    if skip_out:
+        assert out2 is not None and out is None
+    elif out is None:
+        out = torch.empty((N, Ho, Wo, cout) if layout == "nhwc_f32" else (N, cout, Ho, Wo), dtype=torch.float32,
+                          device=dev)
+    geo = out2 if skip_out else out
+    assert geo.dtype == torch.float32
+    if layout == "nchw_f32":
+        sn, sc, sy, sx = geo.stride()
+    else:
+        sn, sy, sx, sc = geo.stride()
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.shape == geo.shape and residual.stride() == geo.stride()
+    if out2 is not None:
+        assert out2.dtype == torch.float32 and out2.stride() == geo.stride()
+    pcs = (cout + 7) // 8 * 8
+    pair = pair2 = None
+    if F16X2_FUSE_SPLIT and layout == "nhwc_f32":
+        if not skip_out:
+            pair = torch.empty((2, N, Ho, Wo, pcs), dtype=torch.float16, device=dev)
+        if out2 is not None:
+            pair2 = torch.empty((2, N, Ho, Wo, pcs), dtype=torch.float16, device=dev)
+    d = ConvF16x2Desc(N, H, W, cin, cs, cout, kh, kw, dh, dw_, pt, pl, Ho, Wo, sh, sw, 0 if fold_w is None else 1, in_wp,
+                      planes.stride(0), w.planes.data_ptr(), w.planes.stride(0), w.scale_eff(scale).data_ptr(),
+                      _ptr(bias), 1 if relu else 0, _ptr(residual), None if skip_out else out.data_ptr(),
+                      sn, sy, sx, sc, _ptr(pair), (pair if pair is not None else pair2).stride(0) if
+                      (pair is not None or pair2 is not None) else 0, pcs, _ptr(out2), _ptr(scale2), _ptr(bias2),
+                      _ptr(pair2), block_n, F16X2_CHUNK_KB, MAX_CTAS)
+    with torch.cuda.device(dev):
+        if PROFILE is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        rc = _native.lib().xdet_conv2d_f16x2(planes.data_ptr(), ctypes.byref(d), torch.cuda.current_stream().cuda_stream)
+        if PROFILE is not None:
+            e1.record()
+            PROFILE.append((e0, e1, 2.0 * N * Ho * Wo * cout * cin * kh * kw, (N, H, W, cin, cout, kh, kw)))
+    _native.check(rc)
+    if pair is not None:
+        out._pair = pair
+    if pair2 is not None:
+        out2._pair = pair2
+    return None if skip_out else out
+
+
+
 def linear(x2d, w_packed, cout, **kw):
     """[M,K] bf16 @ W[cout,K]^T -> [M,cout]: the dense layers of get_head (net/xception_body.py:540-558)."""
     M, K = x2d.shape
@@ -367,6 +556,10 @@ def conv2d_image_fold(image_nchw_f32, w_fold, cout, kh, kw, stride, pad, **kw_ar
                            strides=(stride, stride), cin=C, **kw_args)
     wp = max((Wo - 1) * stride + 8, W + pad)
     wp = (wp + 7) // 8 * 8
+    if isinstance(w_fold, PairWeight):  # row-padded NHWC8 f16x2 planes of the image + the fold_w implicit GEMM
+        x8 = split2(image_nchw_f32.permute(0, 2, 3, 1), cin=C, pad_w=(wp, pad))
+        return conv2d_nhwc(x8, w_fold, cout, kh, kw, padding=(pad, pad, Ho, Wo), strides=(stride, stride), cin=C,
+                           fold_w=(W, pad), **kw_args)
     x8 = image_to_nhwc8(image_nchw_f32, pad, wp)
     return conv2d_nhwc(x8, w_fold, cout, kh, kw, padding=(pad, pad, Ho, Wo), strides=(stride, stride), cin=C,
                        fold_w=(W, pad), **kw_args)
