@@ -293,7 +293,7 @@ typedef struct {
   const float* bias2;
   void* out2_pair;
   int block_n;  /* 0 = auto; 32, 64 or 128 */
-  int chunk_kb; /* 0 = 12: k-blocks (of 64 reduction elements) per accumulator flush */
+  int chunk_kb; /* 0 = 2: k-blocks (of 64 reduction elements) per accumulator flush */
   int max_ctas;
 } xdet_conv_f16x2_desc;
 int xdet_conv2d_f16x2(const void* d_in_pair, const xdet_conv_f16x2_desc* desc, void* stream);
@@ -386,6 +386,13 @@ int xdet_bn_relu_bwd_bf16(const void* d_dy, const void* d_x, const float* d_scal
                           const void* d_add_in, float* d_sums, void* d_dx, void* stream);
 /* dx = dy where y > 0 else 0 (gradient of a ReLU fused into a convolution epilogue); bf16, n elements (n % 8 == 0) */
 int xdet_relu_bwd_bf16(const void* d_dy, const void* d_y, void* d_dx, long long n, void* stream);
+/* Weight gradient of the depthwise 3x3 'SAME' stride-1 convolution (depth multiplier 1, dilation 1 or 2) -- the
+ * depthwise half of tf.layers.separable_conv2d in XceptionBody (net/xception_body.py:224-233), training mode:
+ *   dw[kh*3+kw, c] += sum_{n,y,x} act(x[n, y+(kh-1)*dil, x+(kw-1)*dil, c]) * dy[n,y,x,c],  act = ReLU if relu_in.
+ * x, dy NHWC bf16 (C % 8 == 0); dw [9, C] fp32 is ACCUMULATED into.  The input gradient needs no entry point:
+ * it is xdet_depthwise3x3_bf16 on dy with the taps flipped. */
+int xdet_depthwise3x3_wgrad_bf16(const void* d_x, const void* d_dy, float* d_dw, int N, int H, int W, int C,
+                                 int dilation, int relu_in, void* stream);
 /* fp32 [rows, cols] -> bf16 [rows, dst_pitch] is xdet_f32_to_bf16_rows above */
 int xdet_maxpool3x3s2_bwd_bf16(const void* d_argmax, const void* d_dy, void* d_dx, int N, int H, int W, int C, int Ho,
                                int Wo, int pad_top, int pad_left, void* stream);

@@ -1,4 +1,4 @@
-// CPU EMULATION of the staged CUDA kernel x-detector_b200/csrc/staged/depthwise_wgrad.cu (test infrastructure):
+// CPU EMULATION of the staged CUDA kernel x-detector_b200/csrc/depthwise_wgrad.cu (test infrastructure):
 // the kernel's own source is compiled as host C++ against the few stand-ins below -- thread/block indices as
 // thread-locals, __shared__ as block-wide static storage (one block runs at a time), __syncthreads as a pthread
 // barrier over the block's 256 real threads, atomicAdd under a mutex, bf16 types with round-to-nearest-even
@@ -61,7 +61,7 @@ static inline __nv_bfloat16 float_to_bf16(float f) {  // round to nearest even (
 static inline float2 __bfloat1622float2(__nv_bfloat162 v) { return float2{bf16_to_float(v.x), bf16_to_float(v.y)}; }
 static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 
-#include "../../x-detector_b200/csrc/staged/depthwise_wgrad.cu"
+#include "../../x-detector_b200/csrc/depthwise_wgrad.cu"
 
 using xdet::depthwise3x3_wgrad_kernel;
 

@@ -1,8 +1,5 @@
-"""GPU, STAGED: numerics of the depthwise 3x3 weight-gradient kernel (csrc/staged/depthwise_wgrad.cu) and of the
-'input gradient = forward kernel with flipped taps' identity, against torch autograd in fp64 on the same bf16-rounded
-operands.  Skipped until the kernel is part of libxdet_b200.so (the symbol is looked up at run time)."""
-import ctypes
-
+"""GPU: numerics of the depthwise 3x3 weight-gradient kernel (csrc/depthwise_wgrad.cu) and of the 'input gradient =
+forward kernel with flipped taps' identity, against torch autograd in fp64 on the same bf16-rounded operands."""
 import numpy as np
 import pytest
 import torch
@@ -15,12 +12,7 @@ def lib():
     assert torch.cuda.is_available()
     import xdet_b200  # noqa: F401
     from xdet_b200 import _native
-    lib = _native.lib()
-    if not hasattr(lib, "xdet_depthwise3x3_wgrad_bf16"):
-        pytest.skip("xdet_depthwise3x3_wgrad_bf16 is staged (csrc/staged/), not in the library yet")
-    lib.xdet_depthwise3x3_wgrad_bf16.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 6 + [ctypes.c_void_p]
-    lib.xdet_depthwise3x3_wgrad_bf16.restype = ctypes.c_int
-    return lib
+    return _native.lib()
 
 
 @pytest.mark.parametrize("shape,dil,relu_in", [((2, 19, 23, 72), 1, True), ((1, 50, 50, 728), 1, True),

@@ -136,10 +136,10 @@ def test_training_mode_forward(gold):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("XDET_RUN_STAGED"), reason="staged (XDET_RUN_STAGED=1 runs it): written after the round's GPU budget was spent; un-skip after its first run on a B200")
+@pytest.mark.parametrize("precision", ["f16x2", "fp32x3"])
 @pytest.mark.parametrize("prefix", ["xs", "rs"])
-def test_cuda_parity_mode_matches_reference_builders(gold, prefix):
-    """The CUDA path in fp32x3 parity mode, fed the same name-seeded variables, against the reference's own graph
+def test_cuda_parity_mode_matches_reference_builders(gold, prefix, precision):
+    """The CUDA path in the fp32-accurate precisions, fed the same name-seeded variables, against the reference's own graph
     builders (160x160, both backbones): north_star's 1e-4 on boxes / scores, stage tensors at 1e-4 of their magnitude."""
     import torch
     import xdet_b200  # noqa: F401
@@ -148,7 +148,7 @@ def test_cuda_parity_mode_matches_reference_builders(gold, prefix):
     sd = {name: torch.from_numpy(onet.seeded_variable(name, tuple(shape))) for name, shape in meta["variables"]}
     params = lh.make_params(train_image_size=meta["height"], backbone=meta["backbone"], model_scope=meta["scope"],
                             rpn_pre_nms_top_n=meta["rpn_pre_nms_top_n"], rpn_post_nms_top_n=meta["rpn_post_nms_top_n"],
-                            rpn_nms_thres=meta["rpn_nms_thres"], rpn_min_size=meta["rpn_min_size"], precision="fp32x3")
+                            rpn_nms_thres=meta["rpn_nms_thres"], rpn_min_size=meta["rpn_min_size"], precision=precision)
     model = lh.LightHeadRFCN(params, seed=0, state_dict=sd)
     keys = torch.from_numpy(gold["%s_shuffle_keys" % prefix]).cuda()
     out = model(torch.from_numpy(image(meta)).cuda(), shuffle_keys=keys)

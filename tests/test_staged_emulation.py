@@ -1,4 +1,4 @@
-"""CPU: the staged CUDA kernels (x-detector_b200/csrc/staged/, written without a GPU at hand) executed under a host
+"""CPU: the staged CUDA kernels (x-detector_b200/csrc/, written without a GPU at hand) executed under a host
 emulation -- the kernel's OWN source compiled by g++ against stand-ins for the CUDA built-ins, one real thread per
 CUDA thread, driven over the launcher's own grid decomposition (tests/staged/emulate_*.cc).  Proves the index
 arithmetic, borders, dilation, channel tail, slab split and shared-memory fold before the first GPU run; says nothing

@@ -65,9 +65,13 @@ def test_xception_training_backbone_matches_blueprint():
     to_dev = lambda t: t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()   # noqa: E731
     grads = model.bwd(to_dev(r_mid), to_dev(r_out))
     torch.cuda.synchronize()
-    assert cosine(mid.float().cpu().permute(0, 3, 1, 2), mid0) > 0.9995
-    assert cosine(out.float().cpu().permute(0, 3, 1, 2), out0) > 0.9995
-    assert cosine(out.float().cpu().permute(0, 3, 1, 2), out_x) > 0.99
+    c_mid, c_out = cosine(mid.float().cpu().permute(0, 3, 1, 2), mid0), cosine(out.float().cpu().permute(0, 3, 1, 2), out0)
+    c_outx = cosine(out.float().cpu().permute(0, 3, 1, 2), out_x)
+    print("forward cosines: mid %.6f out %.6f out-vs-exact %.6f (blueprint bf16 vs exact: mid %.6f out %.6f)" % (
+        c_mid, c_out, c_outx, cosine(mid0, mid_x), cosine(out0, out_x)))
+    assert c_mid > 0.9995, c_mid
+    assert c_out > 0.9995, c_out
+    assert c_outx > 0.99, c_outx
     trainable = {n for n, _ in body if not n.rsplit("/", 1)[-1].startswith("moving_")}
     assert set(grads) == trainable and len(trainable) == 154
     worst = 1.0

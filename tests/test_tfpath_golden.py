@@ -136,9 +136,6 @@ def test_gpu_detection_chain_and_matching(cuda):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("XDET_RUN_STAGED"), reason="staged (XDET_RUN_STAGED=1 runs it): AnchorEncoder.encode_all_anchors / ext_encode_rois were added as wrappers over the "
-                         "validated match_encode / sample_fg_bg ops after the round's GPU budget was spent; un-skip "
-                         "after their first run on a B200")
 def test_gpu_anchor_encoder_training_targets(cuda):
     """The reference's method names (preprocessing/anchor_manipulator.py:319-335, :337-432) on the CUDA path against
     the goldens its own AnchorEncoder produced."""
@@ -152,16 +149,19 @@ def test_gpu_anchor_encoder_training_targets(cuda):
     gt, gl = torch.from_numpy(G["tgt_gt"]).cuda(), torch.from_numpy(G["tgt_gl"]).cuda()
     labels, targets, scores, points, n_layers = enc.encode_all_anchors(gl, gt)
     assert n_layers == 1
+    # labels / scores / selections are exact; the encoded targets go through the device's logf (the reference: TF's
+    # CPU log), so they are held to 2e-6 like the kernel's own test (tests/test_train_ops_gpu.py)
     for n in range(2):
         assert np.array_equal(labels[0][n].cpu().numpy(), G["enc_labels_%d" % n])
-        assert np.array_equal(targets[0][n].cpu().numpy(), G["enc_targets_%d" % n])
+        assert np.abs(targets[0][n].cpu().numpy() - G["enc_targets_%d" % n]).max() < 2e-6
         assert np.array_equal(bits(scores[0][n].cpu().numpy()), bits(G["enc_scores_%d" % n]))
         assert np.array_equal(bits(points[0].cpu().numpy()), bits(G["enc_points_%d" % n]))
     keys = {"roi_fg": torch.from_numpy(G["roi_kfg"]).cuda(), "roi_bg": torch.from_numpy(G["roi_kbg"]).cuda(),
             "roi_up": torch.from_numpy(G["roi_kup"]).cuda()}
     rois, tgt, lab, sc = enc.ext_encode_rois(torch.from_numpy(G["roi_in"]).cuda(), gl, gt, 16, 0.25, 0.1, keys=keys)
     assert np.array_equal(bits(rois.cpu().numpy()), bits(G["roi_out"]))
-    assert np.array_equal(lab.cpu().numpy(), G["roi_labels"]) and np.array_equal(tgt.cpu().numpy(), G["roi_targets"])
+    assert np.array_equal(lab.cpu().numpy(), G["roi_labels"])
+    assert np.abs(tgt.cpu().numpy() - G["roi_targets"]).max() < 2e-6
     assert np.array_equal(bits(sc.cpu().numpy()), bits(G["roi_scores"]))
 
 

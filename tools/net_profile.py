@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--list", action="store_true", help="also print every launch of the last step in order")
     ap.add_argument("--train", action="store_true", help="profile the training step instead of inference")
+    ap.add_argument("--precision", default="bf16")
     args = ap.parse_args()
     if args.train:
         from xdet_b200 import light_head_rfcn_train as lt
@@ -31,7 +32,8 @@ def main():
         model = lambda _images, detections=False: trainer.step(*tb)  # noqa: E731
         images = None
     else:
-        params = lh.make_params(train_image_size=args.size, backbone=args.backbone)
+        params = lh.make_params(train_image_size=args.size, backbone=args.backbone, precision=args.precision,
+                                rpn_min_size=16.0 / args.size)
         model = lh.LightHeadRFCN(params, seed=0)
         g = torch.Generator(device="cuda").manual_seed(1)
         images = torch.rand((args.batch, 3, args.size, args.size), generator=g, device="cuda") * 2 - 1

@@ -7,12 +7,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-# XDET_BUILD_STAGED=1: also compile csrc/staged/*.cu (kernels awaiting their first GPU run) into a SEPARATE library,
-# libxdet_b200_staged.so, and load that one -- the default build and library never contain staged code.
-STAGED = os.environ.get("XDET_BUILD_STAGED", "") not in ("", "0")
 # XDET_B200_LIB: load another build of the same library (A/B experiments of tools/); default = the in-tree build
-LIB_PATH = os.environ.get("XDET_B200_LIB") or os.path.join(CSRC, "libxdet_b200_staged.so" if STAGED
-                                                             else "libxdet_b200.so")
+LIB_PATH = os.environ.get("XDET_B200_LIB") or os.path.join(CSRC, "libxdet_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
 NVCC_FLAGS = [
@@ -28,8 +24,7 @@ class NativeLibraryMissing(RuntimeError):
 
 
 def sources():
-    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
-    return srcs + sorted(glob.glob(os.path.join(CSRC, "staged", "*.cu"))) if STAGED else srcs
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
 def build(force=False, verbose=False):
@@ -102,6 +97,7 @@ def _declare_train(lib):
     lib.xdet_col_stats_bf16.argtypes = [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p]
     lib.xdet_bn_finalize.argtypes = [c_void_p] * 3 + [c_ll, c_int, c_float, c_float] + [c_void_p] * 7
     lib.xdet_bn_relu_bwd_bf16.argtypes = [c_void_p] * 6 + [c_ll, c_int, c_int] + [c_void_p] * 4
+    lib.xdet_depthwise3x3_wgrad_bf16.argtypes = [c_void_p] * 3 + [c_int] * 6 + [c_void_p]
     lib.xdet_relu_bwd_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_ll, c_void_p]
     lib.xdet_maxpool3x3s2_bwd_bf16.argtypes = [c_void_p] * 3 + [c_int] * 8 + [c_void_p]
     lib.xdet_nchw_f32_to_nhwc_bf16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]

@@ -1,7 +1,6 @@
-// STAGED FOR ROUND 2 -- NOT part of libxdet_b200.so (the build globs csrc/*.cu only) and NOT yet run on a GPU:
-// it compiles for sm_100a (see staged/README.md) and has a numerics test that is skipped until it is moved into
-// the library.  First missing piece of the Xception TRAINING path (SURVEY 8 row a15 for the reference's own
-// backbone, DESIGN 7 "next steps" item 3).
+// Depthwise 3x3 weight gradient: the kernel the Xception TRAINING path adds to the convolution gradients
+// (SURVEY 8 row a15 for the reference's own backbone).  GPU test: tests/test_depthwise_wgrad_gpu.py; the same source
+// also runs under a host emulation (tests/test_staged_emulation.py).
 //
 // Weight gradient of tf.layers.separable_conv2d's depthwise stage (net/xception_body.py:220-234: 3x3, 'same',
 // stride 1, depth multiplier 1, dilation 1 or 2, input ReLU'd by relu_separable_bn_block):
@@ -17,7 +16,7 @@
 #ifndef XDET_EMULATE_ON_CPU   // tests/staged/emulate_depthwise_wgrad.cc supplies host stand-ins instead
 #include <cuda_bf16.h>
 
-#include "../common.cuh"
+#include "common.cuh"
 #endif
 
 namespace xdet {

@@ -93,7 +93,7 @@ def conv2d_fixed_padding(inputs, filters, kernel_size, strides, data_format, ker
 
 
 def bottleneck_block(inputs, filters, is_training, projection_shortcut, strides, data_format, store=None,
-                     dilation_rate=1, preact=None, next_bn=None, sum_unused=False):
+                     dilation_rate=1, preact=None, next_bn=None, sum_unused=False, next_forms="pair"):
     """Bottleneck block variant for residual networks with BN before convolutions (net/resnet_v2.py:142-184;
     with ``dilation_rate`` > 1 the 3x3 is the dilated SAME conv of xdet_bottleneck_block, net/xdet_body.py:39-81).
 
@@ -111,17 +111,22 @@ def bottleneck_block(inputs, filters, is_training, projection_shortcut, strides,
     k1 = _conv_kernel(store, preact.shape[-1], filters, 1)
     bn2 = _bn(store, filters)
     s2, b2 = store.folded_bn(bn2, _BATCH_NORM_EPSILON)
-    t = _run_conv(store, preact, k1, 1, scale=s2, bias=b2, relu=True)
+    # ("f16x2" precision: the two inner activations are read by convolutions only -> stored as split planes only; the
+    # sum is read as a residual only -> fp32 only)
+    t = _run_conv(store, preact, k1, 1, scale=s2, bias=b2, relu=True, forms="pair")
     k2 = _conv_kernel(store, filters, filters, 3)
     bn3 = _bn(store, filters)
     s3, b3 = store.folded_bn(bn3, _BATCH_NORM_EPSILON)
     t = _run_conv(store, t, k2, strides if dilation_rate == 1 else 1, dilation=dilation_rate, scale=s3, bias=b3,
-                  relu=True)
+                  relu=True, forms="pair")
     k3 = _conv_kernel(store, filters, 4 * filters, 1)
     out2 = None
-    ep = {"residual": shortcut}
+    ep = {"residual": shortcut, "forms": "f32"}
     if next_bn is not None:
         sn, bnb = store.folded_bn(next_bn, _BATCH_NORM_EPSILON)
+        if ops.conv.PRECISION == "f16x2":  # the kernel wrapper allocates the forms that are needed
+            ep.update(out2=True, scale2=sn, bias2=bnb, skip_out=bool(sum_unused), forms2=next_forms)
+            return _run_conv(store, t, k3, 1, **ep)
         out2 = torch.empty_like(shortcut)
         ep.update(out2=out2, scale2=sn, bias2=bnb, skip_out=bool(sum_unused))
     y = _run_conv(store, t, k3, 1, **ep)
@@ -129,17 +134,18 @@ def bottleneck_block(inputs, filters, is_training, projection_shortcut, strides,
 
 
 def block_layer(inputs, filters, block_fn, blocks, strides, is_training, name, data_format, store=None,
-                dilation_rate=1, preact=None, fuse_next=False, sum_unused=False):
+                dilation_rate=1, preact=None, fuse_next=False, sum_unused=False, fused_forms="pair"):
     """Creates one layer of blocks for the ResNet model (net/resnet_v2.py:187-223; dilated form
     net/xdet_body.py:84-121).  Returns the layer output (sum of the last block); with ``fuse_next`` the
     batch-norm that follows this layer in creation order (the next layer's first pre-activation, or a trailing
     batch_norm_relu) is fused into the last convolution and (sum, relu(bn(sum))) is returned; ``sum_unused``
-    then drops the raw sum (None is returned in its place)."""
+    then drops the raw sum (None is returned in its place).  ``fused_forms`` ("f16x2" precision only): the forms of
+    that fused output -- "pair" when only convolutions read it, "both" when it is also a result of the model."""
     filters_out = 4 * filters
 
     def projection_shortcut(x):
         kern = _conv_kernel(store, x.shape[-1], filters_out, 1)
-        return _run_conv(store, x, kern, strides if dilation_rate == 1 else 1)
+        return _run_conv(store, x, kern, strides if dilation_rate == 1 else 1, forms="f32")
 
     x, pre = inputs, preact
     for i in range(blocks):
@@ -148,7 +154,8 @@ def block_layer(inputs, filters, block_fn, blocks, strides, is_training, name, d
         x, pre = block_fn(x, filters, is_training, projection_shortcut if i == 0 else None,
                           strides if i == 0 else 1, data_format, store=store, dilation_rate=dilation_rate, preact=pre,
                           next_bn=_peek_next_bn(store, filters_out) if (not last or fuse_next) else None,
-                          sum_unused=last and fuse_next and sum_unused)
+                          sum_unused=last and fuse_next and sum_unused,
+                          next_forms=fused_forms if last else "pair")
     return (x, pre) if fuse_next else x
 
 
@@ -195,7 +202,7 @@ def stem(image_nchw_f32, store, fuse_next=False):
     key = ("w", kern[0], "fold")
     if key not in store.derived:
         store.derived[key] = ops.pack_fold_weight(kern[1].permute(3, 2, 0, 1))
-    y = ops.conv2d_image_fold(image_nchw_f32.contiguous(), store.derived[key], 64, 7, 7, 2, 3)
+    y = ops.conv2d_image_fold(image_nchw_f32.contiguous(), store.derived[key], 64, 7, 7, 2, 3, forms="f32")
     if not fuse_next:
         return ops.maxpool3x3s2_same(y)
     s1, b1 = store.folded_bn(_peek_next_bn(store, 64, ahead=0), _BATCH_NORM_EPSILON)
@@ -217,11 +224,11 @@ def lighthead_resnet50_body(image_nchw_f32, is_training, store, layers=(3, 4, 6,
                          preact=pre, fuse_next=True, sum_unused=True)
     # after layer 3 the next batch-norm in creation order is the RPN feature's batch_norm_relu
     x, rpn_feat = block_layer(None, 256, bottleneck_block, layers[2], 2, is_training, "block_layer3", df, store,
-                              preact=pre, fuse_next=True)
+                              preact=pre, fuse_next=True, fused_forms="both")
     store.auto_name("batch_normalization")  # consumed by the fused second output above
     if after_rpn_feat is not None:
         after_rpn_feat(rpn_feat)
     _, backbone = block_layer(x, 512, bottleneck_block, layers[3], 1, is_training, "block_layer4", df, store,
-                              dilation_rate=2, fuse_next=True, sum_unused=True)
+                              dilation_rate=2, fuse_next=True, sum_unused=True, fused_forms="both")
     store.auto_name("batch_normalization")
     return rpn_feat, backbone

@@ -70,6 +70,7 @@ def _separable(store, x, name, filters, relu_in, dilation=1, bn_name=None, **epi
     wp = _derived(store, ("w", pw[0]), lambda: ops.pack_conv_weight(pw[1].permute(3, 2, 0, 1)))
     scale, bias = _bn_named(store, bn_name or (name + "_bn"), filters)
     t = ops.depthwise3x3(x, w9, dilation=dilation, relu_in=relu_in)
+    epilogue.setdefault("forms", "f32")  # ("f16x2" precision) the usual reader is the next depthwise kernel
     return ops.conv2d_nhwc(t, wp, filters, 1, 1, scale=scale, bias=bias, cin=cin, **epilogue)
 
 
@@ -91,7 +92,7 @@ def XceptionBody(input_image, num_classes, is_training=False, data_format='chann
     k = _conv_named(store, "block1_conv1", input_image.shape[1], 32, 3)
     wf = _derived(store, ("w", k[0], "fold"), lambda: ops.pack_fold_weight(k[1].permute(3, 2, 0, 1)))
     sc, bi = _bn_named(store, "block1_conv1_bn", 32)
-    x = ops.conv2d_image_fold(input_image.contiguous(), wf, 32, 3, 3, 2, 0, scale=sc, bias=bi, relu=True)
+    x = ops.conv2d_image_fold(input_image.contiguous(), wf, 32, 3, 3, 2, 0, scale=sc, bias=bi, relu=True, forms="pair")
     k = _conv_named(store, "block1_conv2", 32, 64, 3)
     w = _derived(store, ("w", k[0]), lambda: ops.pack_conv_weight(k[1].permute(3, 2, 0, 1)))
     sc, bi = _bn_named(store, "block1_conv2_bn", 64)
@@ -104,7 +105,7 @@ def XceptionBody(input_image, num_classes, is_training=False, data_format='chann
         sc, bi = _bn_named(store, "batch_normalization_%d" % idx, filters)
         N, H, W, _ = x.shape
         return ops.conv2d_nhwc(x, w, filters, 1, 1, padding=(0, 0, -(-H // 2), -(-W // 2)), strides=(2, 2), scale=sc,
-                               bias=bi)
+                               bias=bi, forms="f32")
 
     residual = strided_residual(x, 1, 128)
     x = _separable(store, x, "block2_sepconv1", 128, relu_in=False)  # its input is already ReLU'd (:268)
@@ -129,18 +130,18 @@ def XceptionBody(input_image, num_classes, is_training=False, data_format='chann
             one, zero = _derived(store, ("unit", 728), lambda: (torch.ones(728, device=x.device),
                                                                   torch.zeros(728, device=x.device)))
             x = relu_separable_bn_block(t, 728, prefix + "_sepconv3", is_training, df, store, residual=residual,
-                                        out2=mid_outputs, scale2=one, bias2=zero)
+                                        out2=mid_outputs, scale2=one, bias2=zero, forms="both")
     if after_mid is not None:
         after_mid(mid_outputs)
     # ---- exit flow with the stride removed and dilation 2 in block14 (:337-376) ----
     k = _conv_named(store, "conv2d_4", 728, 1024, 1)
     w = _derived(store, ("w", k[0]), lambda: ops.pack_conv_weight(k[1].permute(3, 2, 0, 1)))
     sc, bi = _bn_named(store, "batch_normalization_4", 1024)
-    residual = ops.conv2d_nhwc(x, w, 1024, 1, 1, scale=sc, bias=bi)
+    residual = ops.conv2d_nhwc(x, w, 1024, 1, 1, scale=sc, bias=bi, forms="f32")
     t = relu_separable_bn_block(x, 728, "block13_sepconv1", is_training, df, store)
     x = relu_separable_bn_block(t, 1024, "block13_sepconv2", is_training, df, store, residual=residual)
     x = _separable(store, x, "block14_sepconv1", 1536, relu_in=False, dilation=2, relu=True)
-    outputs = _separable(store, x, "block14_sepconv2", 2048, relu_in=False, dilation=2, relu=True)
+    outputs = _separable(store, x, "block14_sepconv2", 2048, relu_in=False, dilation=2, relu=True, forms="both")
     return mid_outputs, outputs
 
 
@@ -155,11 +156,11 @@ def get_rpn(net_input, num_anchors, is_training, data_format, var_scope, store=N
         k1, b1 = _conv_vars(store, 512, 2 * num_anchors, 1, 1)
         k2, b2 = _conv_vars(store, 512, 4 * num_anchors, 1, 1)
     w0 = _derived(store, ("w", k0[0]), lambda: ops.pack_conv_weight(k0[1].permute(3, 2, 0, 1)))
-    rpn_relu = ops.conv2d_nhwc(net_input, w0, 512, 3, 3, bias=b0[1], relu=True)
+    rpn_relu = ops.conv2d_nhwc(net_input, w0, 512, 3, 3, bias=b0[1], relu=True, forms="pair")
     w12 = _derived(store, ("w", k1[0], k2[0]),
                    lambda: ops.pack_conv_weight(torch.cat([k1[1], k2[1]], dim=3).permute(3, 2, 0, 1)))
     b12 = _derived(store, ("b", b1[0], b2[0]), lambda: torch.cat([b1[1], b2[1]]).contiguous())
-    return ops.conv2d_nhwc(rpn_relu, w12, 6 * num_anchors, 1, 1, bias=b12, out_layout="nhwc_f32")
+    return ops.conv2d_nhwc(rpn_relu, w12, 6 * num_anchors, 1, 1, bias=b12, out_layout="nhwc_f32", forms="f32")
 
 
 def get_proposals(object_score, bboxes_pred, encode_fn, rpn_pre_nms_top_n, rpn_post_nms_top_n, nms_threshold,
@@ -189,7 +190,7 @@ def large_sep_kernel(net_input, depth_mid, depth_output, is_training, data_forma
     wa = _derived(store, ("w", a0k[0], a1k[0]),
                   lambda: ops.pack_conv_weight(torch.cat([a0k[1], a1k[1]], dim=3).permute(3, 2, 0, 1)))
     ba = _derived(store, ("b", a0b[0], a1b[0]), lambda: torch.cat([a0b[1], a1b[1]]).contiguous())
-    mid = ops.conv2d_nhwc(net_input, wa, 2 * depth_mid, 15, 1, bias=ba)
+    mid = ops.conv2d_nhwc(net_input, wa, 2 * depth_mid, 15, 1, bias=ba, forms="pair")
     wb = _derived(store, ("w", b0k[0], b1k[0]),
                   lambda: ops.pack_conv_weight(torch.cat([b0k[1], b1k[1]], dim=2).permute(3, 2, 0, 1)))
     scale, shift = store.folded_bn(bn, resnet_v2._BATCH_NORM_EPSILON)
@@ -224,7 +225,7 @@ def get_head(net_input, pooling_op, grid_width, grid_height, loss_func, proposal
         kl, bl = _dense_vars(store, "fc_loc", 2048, 4)
     w1 = _derived(store, ("w", k1[0]), lambda: ops.pack_conv_weight(k1[1].t().reshape(2048, cin, 1, 1)))
     if ops.conv.PRECISION in ("f16x2", "fp32x3"):  # fp32 activations: the pooled features are split inside conv2d_nhwc
-        h = ops.conv2d_nhwc(feat.reshape(1, 1, N * R, cin), w1, 2048, 1, 1, bias=b1[1], relu=True)
+        h = ops.conv2d_nhwc(feat.reshape(1, 1, N * R, cin), w1, 2048, 1, 1, bias=b1[1], relu=True, forms="pair")
     else:
         pitch = (cin + 7) // 8 * 8  # TMA rows must be 16-byte multiples
         a = ops.f32_to_bf16_rows(feat, pitch)
@@ -232,7 +233,8 @@ def get_head(net_input, pooling_op, grid_width, grid_height, loss_func, proposal
     w2 = _derived(store, ("w", kc[0], kl[0]),
                   lambda: ops.pack_conv_weight(torch.cat([kc[1], kl[1]], dim=1).t().reshape(num_classes + 4, 2048, 1, 1)))
     b2 = _derived(store, ("b", bc[0], bl[0]), lambda: torch.cat([bc[1], bl[1]]).contiguous())
-    out = ops.conv2d_nhwc(h, w2, num_classes + 4, 1, 1, bias=b2, out_layout="nhwc_f32").reshape(N, R, num_classes + 4)
+    out = ops.conv2d_nhwc(h, w2, num_classes + 4, 1, 1, bias=b2, out_layout="nhwc_f32",
+                          forms="f32").reshape(N, R, num_classes + 4)
     if return_fused:  # also the [N,R,num_classes+4] tensor both results are views of
         return out[..., :num_classes], out[..., num_classes:], out
     return out[..., :num_classes], out[..., num_classes:]

@@ -30,11 +30,8 @@ def _st():
 
 
 def depthwise3x3_wgrad(x, dy, dilation, relu_in):
-    """dW [9, C] fp32 of the depthwise 3x3 'same' convolution (csrc/staged/depthwise_wgrad.cu)."""
+    """dW [9, C] fp32 of the depthwise 3x3 'same' convolution (csrc/depthwise_wgrad.cu)."""
     lib = _native.lib()
-    if not hasattr(lib, "xdet_depthwise3x3_wgrad_bf16"):
-        raise _native.NativeLibraryMissing("xdet_depthwise3x3_wgrad_bf16 is staged: build with XDET_BUILD_STAGED=1")
-    lib.xdet_depthwise3x3_wgrad_bf16.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 6 + [ctypes.c_void_p]
     N, H, W, C = x.shape
     dw = torch.zeros((9, C), dtype=torch.float32, device=x.device)
     _native.check(lib.xdet_depthwise3x3_wgrad_bf16(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W, C, dilation,

@@ -40,6 +40,7 @@ class ConvDesc(ctypes.Structure):
 #            for the tests; ~20x slower than bf16.
 PRECISION = "bf16"
 PRECISIONS = ("bf16", "f16x2", "fp32x3")
+_chunk_cache = {}
 
 
 class precision(object):
@@ -133,7 +134,7 @@ class ConvF16x2Desc(ctypes.Structure):
     ]
 
 
-# k-blocks (64 reduction elements each) per accumulator flush of the f16x2 kernel; 0 = the library default (12)
+# k-blocks (64 reduction elements each) per accumulator flush of the f16x2 kernel; 0 = the library default (2)
 F16X2_CHUNK_KB = 0
 # the f16x2 epilogue also writes the split planes of its NHWC outputs (the next convolution then needs no split pass)
 F16X2_FUSE_SPLIT = True
@@ -150,8 +151,13 @@ def split2(x, cin=None, relu=False, pad_w=None):
         Wp, x_off = W, 0
         out = torch.empty((2, N, H, Wp, cs), dtype=torch.float16, device=x.device)
     else:
+        # the padding is zero-filled ONCE: the buffer is cached per shape and only its interior is rewritten
         Wp, x_off = pad_w
-        out = torch.zeros((2, N, H, Wp, cs), dtype=torch.float16, device=x.device)
+        key = ("padded", N, H, Wp, cs, x_off, W, str(x.device))
+        out = _chunk_cache.get(key)
+        if out is None:
+            out = torch.zeros((2, N, H, Wp, cs), dtype=torch.float16, device=x.device)
+            _chunk_cache[key] = out
     sn, sy, sx, sc = x.stride()
     with torch.cuda.device(x.device):
         rc = _native.lib().xdet_split2_f16(x.data_ptr(), sn, sy, sx, sc, N, H, W, cin, out.data_ptr(), cs, Wp, x_off,
@@ -165,7 +171,21 @@ def pair_of(x, cin=None):
     p = getattr(x, "_pair", None)
     if p is not None and p.shape[1:4] == x.shape[0:3]:
         return p
-    return split2(x, cin)
+    p = split2(x, cin)
+    try:
+        x._pair = p  # a second consumer of the same tensor (projection shortcut + first conv) reuses it
+    except AttributeError:
+        pass
+    return p
+
+
+def pair_only(shape, planes):
+    """Stand-in for an activation that exists only as f16x2 planes (every consumer is a convolution): right shape and
+    dtype for the builders' bookkeeping, no fp32 storage behind it."""
+    t = torch.empty((1,), dtype=torch.float32, device=planes.device).expand(shape)
+    t._pair = planes
+    t._pair_only = True
+    return t
 
 
 
@@ -278,13 +298,16 @@ class cta_limit(object):
 
 def conv2d_nhwc(x, w_packed, cout, kh, kw, *, dilation=(1, 1), padding="SAME", scale=None, bias=None, relu=False,
                 residual=None, out=None, out_layout="nhwc_bf16", out2=None, scale2=None, bias2=None, cin=None,
-                block_n=0, strides=(1, 1), fold_w=None, skip_out=False, epi_groups=0):
+                block_n=0, strides=(1, 1), fold_w=None, skip_out=False, epi_groups=0, forms="both", forms2="both"):
     """x: [N,H,W,C] bf16 (channel stride may be padded: pass the true ``cin``).  Returns the output tensor
-    ([N,Ho,Wo,Cout] bf16 for 'nhwc_bf16', [N,Cout,Ho,Wo] fp32 for 'nchw_f32', [N,Ho,Wo,Cout] fp32 for 'nhwc_f32')."""
+    ([N,Ho,Wo,Cout] bf16 for 'nhwc_bf16', [N,Cout,Ho,Wo] fp32 for 'nchw_f32', [N,Ho,Wo,Cout] fp32 for 'nhwc_f32').
+    ``forms`` / ``forms2`` (read by the "f16x2" precision only): which forms of ``out`` / ``out2`` their consumers need
+    -- "both", "f32" (no convolution reads it: no split planes) or "pair" (only convolutions read it: no fp32 copy)."""
     if isinstance(w_packed, PairWeight):
         return _conv2d_f16x2(x, w_packed, cout, kh, kw, dilation=dilation, padding=padding, scale=scale, bias=bias,
                              relu=relu, residual=residual, out=out, out_layout=out_layout, out2=out2, scale2=scale2,
-                             bias2=bias2, cin=cin, block_n=block_n, strides=strides, fold_w=fold_w, skip_out=skip_out)
+                             bias2=bias2, cin=cin, block_n=block_n, strides=strides, fold_w=fold_w, skip_out=skip_out,
+                             forms=forms, forms2=forms2)
     if x.dtype == torch.float32:  # parity mode: fp32 activations
         return _conv2d_fp32x3(x, w_packed, cout, kh, kw, dilation=dilation, padding=padding, scale=scale, bias=bias,
                               relu=relu, residual=residual, out=out, out_layout=out_layout, out2=out2, scale2=scale2,
@@ -390,7 +413,6 @@ def f32_post(x, residual=None, relu=False, out=None, scale2=None, bias2=None, ou
 # elements (6 * taps * channels): longer reductions run as several launches over channel chunks whose fp32 partial
 # results are added with round-to-nearest by xdet_f32_post.  0 = never chunk.
 PARITY_MAX_K = 768
-_chunk_cache = {}
 
 
 def _weight_chunk(w_packed, cout, taps, cin, c0, c1):
@@ -461,10 +483,11 @@ def _conv2d_fp32x3(x, w_packed, cout, kh, kw, *, dilation, padding, scale, bias,
 
 
 def _conv2d_f16x2(x, w, cout, kh, kw, *, dilation, padding, scale, bias, relu, residual, out, out_layout, out2, scale2,
-                  bias2, cin, block_n, strides, fold_w, skip_out):
+                  bias2, cin, block_n, strides, fold_w, skip_out, forms="both", forms2="both"):
     """``conv2d_nhwc`` in "f16x2" precision.  ``x``: fp32 NHWC activation (its split planes are taken from the
     producer when attached, else made here), or -- fold_w mode -- the row-padded f16x2 image planes themselves.
-    Outputs are fp32 (the NHWC ones carry their own split planes for the next convolution)."""
+    Outputs are fp32 (the NHWC ones carry their own split planes for the next convolution); see ``forms``.
+    ``out2``: a caller-provided fp32 buffer, or True = allocate what ``forms2`` asks for (then (out, out2) is returned)."""
     dh, dw_ = dilation
     sh, sw = strides
     if fold_w is not None:
@@ -490,34 +513,45 @@ def _conv2d_f16x2(x, w, cout, kh, kw, *, dilation, padding, scale, bias, relu, r
     if fold_w is not None:
         assert pl == fold_w[1], "the materialised left padding must equal the convolution's"
     dev = planes.device
-    layout = "nhwc_f32" if out_layout == "nhwc_bf16" else out_layout
+    nhwc = out_layout != "nchw_f32"
+    if not (F16X2_FUSE_SPLIT and nhwc):
+        forms = forms2 = "f32"
+    shape = (N, Ho, Wo, cout) if nhwc else (N, cout, Ho, Wo)
+    want2 = out2 is not None
+    alloc2 = out2 is True
+    if alloc2:
+        out2 = None
     if skip_out:
-        assert out2 is not None and out is None
-    elif out is None:
-        out = torch.empty((N, Ho, Wo, cout) if layout == "nhwc_f32" else (N, cout, Ho, Wo), dtype=torch.float32,
-                          device=dev)
-    geo = out2 if skip_out else out
-    assert geo.dtype == torch.float32
-    if layout == "nchw_f32":
-        sn, sc, sy, sx = geo.stride()
+        assert want2 and out is None
+    # fp32 outputs (caller-provided buffers are always stored in fp32)
+    f32_out = f32_out2 = None
+    if not skip_out and (out is not None or forms != "pair"):
+        f32_out = out if out is not None else torch.empty(shape, dtype=torch.float32, device=dev)
+    if want2 and (out2 is not None or forms2 != "pair"):
+        f32_out2 = out2 if out2 is not None else torch.empty(shape, dtype=torch.float32, device=dev)
+    geo = f32_out if f32_out is not None else (f32_out2 if f32_out2 is not None else residual)
+    if geo is not None and not getattr(geo, "_pair_only", False):
+        st = geo.stride()
     else:
-        sn, sy, sx, sc = geo.stride()
-    if residual is not None:
-        assert residual.dtype == torch.float32 and residual.shape == geo.shape and residual.stride() == geo.stride()
-    if out2 is not None:
-        assert out2.dtype == torch.float32 and out2.stride() == geo.stride()
+        st = (Ho * Wo * cout, Wo * cout, cout, 1)
+    if nhwc:
+        sn, sy, sx, sc = st
+    else:
+        sn, sc, sy, sx = st
+    for t in (residual, f32_out, f32_out2):
+        assert t is None or (t.dtype == torch.float32 and tuple(t.shape) == shape and t.stride() == st and
+                             not getattr(t, "_pair_only", False))
     pcs = (cout + 7) // 8 * 8
     pair = pair2 = None
-    if F16X2_FUSE_SPLIT and layout == "nhwc_f32":
-        if not skip_out:
-            pair = torch.empty((2, N, Ho, Wo, pcs), dtype=torch.float16, device=dev)
-        if out2 is not None:
-            pair2 = torch.empty((2, N, Ho, Wo, pcs), dtype=torch.float16, device=dev)
+    if not skip_out and forms != "f32":
+        pair = torch.empty((2, N, Ho, Wo, pcs), dtype=torch.float16, device=dev)
+    if want2 and forms2 != "f32":
+        pair2 = torch.empty((2, N, Ho, Wo, pcs), dtype=torch.float16, device=dev)
+    some_pair = pair if pair is not None else pair2
     d = ConvF16x2Desc(N, H, W, cin, cs, cout, kh, kw, dh, dw_, pt, pl, Ho, Wo, sh, sw, 0 if fold_w is None else 1, in_wp,
                       planes.stride(0), w.planes.data_ptr(), w.planes.stride(0), w.scale_eff(scale).data_ptr(),
-                      _ptr(bias), 1 if relu else 0, _ptr(residual), None if skip_out else out.data_ptr(),
-                      sn, sy, sx, sc, _ptr(pair), (pair if pair is not None else pair2).stride(0) if
-                      (pair is not None or pair2 is not None) else 0, pcs, _ptr(out2), _ptr(scale2), _ptr(bias2),
+                      _ptr(bias), 1 if relu else 0, _ptr(residual), _ptr(f32_out), sn, sy, sx, sc, _ptr(pair),
+                      0 if some_pair is None else some_pair.stride(0), pcs, _ptr(f32_out2), _ptr(scale2), _ptr(bias2),
                       _ptr(pair2), block_n, F16X2_CHUNK_KB, MAX_CTAS)
     with torch.cuda.device(dev):
         if PROFILE is not None:
@@ -529,11 +563,16 @@ def _conv2d_f16x2(x, w, cout, kh, kw, *, dilation, padding, scale, bias, relu, r
             PROFILE.append((e0, e1, 2.0 * N * Ho * Wo * cout * cin * kh * kw, (N, H, W, cin, cout, kh, kw)))
     _native.check(rc)
     if pair is not None:
-        out._pair = pair
+        if f32_out is None:
+            f32_out = pair_only(shape, pair)
+        else:
+            f32_out._pair = pair
     if pair2 is not None:
-        out2._pair = pair2
-    return None if skip_out else out
-
+        if f32_out2 is None:
+            f32_out2 = pair_only(shape, pair2)
+        else:
+            f32_out2._pair = pair2
+    return (f32_out, f32_out2) if alloc2 else f32_out
 
 
 def linear(x2d, w_packed, cout, **kw):
