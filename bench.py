@@ -113,6 +113,29 @@ def dist_finish(world):
         os._exit(0)
 
 
+def own_context():
+    """Device, process group and measured peaks for the own arm (one process per GPU)."""
+    import torch
+    import torch.distributed as dist
+
+    import xdet_b200  # noqa: F401
+    from xdet_b200 import _native
+
+    world, rank, local = dist_env()
+    assert torch.cuda.is_available(), "bench.py (own arm) needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        dist_init(local)
+    _native.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    return {"world": world, "rank": rank, "local": local, "barrier": barrier, "peaks": load_peaks()}
+
+
 # ==============================================================================================
 # Workload 1 (default): Light-Head R-CNN ResNet-50 inference, batch 8/GPU, 480x480
 # ==============================================================================================
@@ -125,43 +148,37 @@ class LightHeadResnet50:
         rng = np.random.default_rng(1 + 1000 * rank)  # U(-1,1): img*2 - mean/127.5 (common_preprocessing.py:391-392)
         return (rng.random((self.batch, 3, self.size, self.size), dtype=np.float32) * 2 - 1).astype(np.float32)
 
-    def run_own(self, args):
+    # precision of the headline number: the one that holds north_star's 1e-4 against the reference's fp32 graph
+    precision = "f16x2"
+    DTYPES = {"f16x2": "fp32-accurate: 2 x fp16 planes per operand on tcgen05 (kind::f16), fp32 accumulate, chunked "
+                       "round-to-nearest flushes; fp32 activations",
+              "bf16": "bf16 operands and activations, fp32 accumulate"}
+
+    def measure(self, args, precision, ctx, state_dict=None):
+        """One precision of the inference path: device-resident img/s (CUDA-graph replay, CUDA events), end to end
+        with HOST buffers, live per-launch timing of the convolution kernel.  Returns a dict (+ the model)."""
         import torch
         import torch.distributed as dist
 
-        import xdet_b200  # noqa: F401
         from xdet_b200 import _native
         from xdet_b200 import light_head_rfcn_eval as lh
         from xdet_b200.ops import conv as conv_ops
+        world, rank, local, barrier, peaks = ctx["world"], ctx["rank"], ctx["local"], ctx["barrier"], ctx["peaks"]
 
-        world, rank, local = dist_env()
-        assert torch.cuda.is_available(), "bench.py (own arm) needs a GPU; there is no CPU fallback"
-        torch.cuda.set_device(local)
-        if world > 1:
-            dist_init(local)
-        _native.lib()
-        peaks = load_peaks()
-
-        def barrier():
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-
-        params = lh.make_params(train_image_size=self.size, backbone=self.backbone, rpn_min_size=16.0 / self.size)
-        model = lh.LightHeadRFCN(params, seed=0)
+        params = lh.make_params(train_image_size=self.size, backbone=self.backbone, rpn_min_size=16.0 / self.size,
+                                precision=precision)
+        model = lh.LightHeadRFCN(params, seed=0, state_dict=state_dict)
         conv_ops.AUTOTUNE = not args.no_autotune  # one-time tile-shape tuning per layer shape during the eager pass
         imgs_h = torch.from_numpy(self.images(rank)).pin_memory()
         imgs_d = imgs_h.cuda()
-        R = params["rpn_post_nms_top_n"]
         # the step ends with the per-class detections (bboxes_eval): what the reference's eval loop consumes
         ncls, ndet = params["num_classes"] - 1, params["nms_topk"]
         probs_h = torch.empty((self.batch, ncls, ndet), dtype=torch.float32).pin_memory()
         boxes_h = torch.empty((self.batch, ncls, ndet, 4), dtype=torch.float32).pin_memory()
-        del R
         run = lambda x: model(x, detections=True)  # noqa: E731
 
         # ---- build: one eager pass creates the variables / packed weights, then the whole forward is
-        # captured into a CUDA graph (launch-bound otherwise: ~90 kernels per step) ------------------
+        # captured into a CUDA graph (launch-bound otherwise: ~80 kernels per step) ------------------
         static_in = torch.empty_like(imgs_d)
         static_in.copy_(imgs_d)
         out = run(static_in)
@@ -185,8 +202,6 @@ class LightHeadResnet50:
                 graph = None
                 out = run(static_in)
                 torch.cuda.synchronize()
-
-        launches_per_step = None
 
         def step():
             if graph is not None:
@@ -269,7 +284,7 @@ class LightHeadResnet50:
         e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
         clocks = sampler.finish()
 
-        # ---- dominant kernel (conv_gemm_kernel): live per-launch CUDA-event timing, eager pass ------
+        # ---- dominant kernel (the convolution): live per-launch CUDA-event timing, eager pass ------
         # (the GPU first spins in a ~20 ms sleep kernel so that the host runs ahead and every launch is already queued
         # when its start event is reached: the intervals are kernel execution, not launch latency)
         conv_ops.PROFILE = []
@@ -290,42 +305,104 @@ class LightHeadResnet50:
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         step_ms, e2e_ms = float(t[0]), float(t[1])
-        value = world * self.batch / (step_ms * 1e-3)
-        e2e_value = world * self.batch / (e2e_ms * 1e-3)
         achieved = conv_flops / (conv_ms * 1e-3) / 1e12
-        peak = peaks["bf16_tflops_sustained"]
+        # the convolutions were event-timed one by one at boost clocks: the burst cuBLAS figure is the honest peak
+        peak = peaks["bf16_tflops"]
+        products = 3 if precision == "f16x2" else 1
+        kname = "conv_gemm_f16x2_kernel" if precision == "f16x2" else "conv_gemm_kernel"
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
-                    "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM), %d launches per step" % n_conv,
+                    "traffic": None, "peak_source": peaks["source"] + " (burst cuBLAS bf16; fp16 runs at the same rate)",
+                    "kernel": "%s (tcgen05 implicit GEMM), %d launches per step" % (kname, n_conv),
                     "algorithmic_flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms,
                     "kernel_ms_per_step_raw": conv_ms_raw, "event_pair_overhead_ms": ev_over,
                     "kernel_share_of_step": conv_ms / step_ms,
-                    "note": "per-launch CUDA-event times from an eager pass with the launches pre-queued behind a sleep "
-                            "kernel, minus the measured empty event-pair interval per launch (raw sum kept beside it); "
-                            "flops = 2*MACs of every conv/dense layer (bias/BN/ReLU excluded)"}
+                    "tensor_products_per_algorithmic_product": products,
+                    "tensor_pipe_tflops": achieved * products, "tensor_pipe_frac": achieved * products / peak,
+                    "note": "achieved = ALGORITHMIC flops (2*MACs of every conv/dense layer, bias/BN/ReLU excluded) / "
+                            "kernel time; per-launch CUDA-event times from an eager pass with the launches pre-queued "
+                            "behind a sleep kernel, minus the measured empty event-pair interval per launch (raw sum "
+                            "kept beside it)" + ("; the fp32-accurate kernel issues 3 tensor-core products per algorithmic "
+                                                 "product, so its ceiling is peak/3" if products == 3 else "")}
+        return {"precision": precision, "dtype": self.DTYPES[precision], "value": world * self.batch / (step_ms * 1e-3),
+                "ms_per_step": step_ms,
+                "e2e": {"value": world * self.batch / (e2e_ms * 1e-3), "unit": self.unit, "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": int(imgs_h.numel() * 4),
+                        "d2h_bytes_per_step": int(probs_h.numel() * 4 + boxes_h.numel() * 4)},
+                "gpu_launches_per_step": int(launches_per_step), "cuda_graph": graph is not None, "clocks": clocks,
+                "roofline": roofline, "_model": model, "_params": params}
+
+    def parity(self, models, cpu_out, img, keys):
+        """Deltas of each precision against the CPU oracle's outputs on the image the cpu_baseline leg just ran (same
+        variables, same shuffle keys).  Proposals are paired by box (an NMS near-tie flip shifts row positions)."""
+        import torch
+        res = {}
+        pb = np.asarray(cpu_out["proposals_bboxes"], np.float32)[0]
+        for name, model in models.items():
+            out = model(torch.from_numpy(img).cuda(), shuffle_keys=torch.from_numpy(keys).cuda())
+            torch.cuda.synchronize()
+            pa = out["proposals_bboxes"].cpu().numpy()[0]
+            d = np.abs(pa[:, None, :] - pb[None, :, :]).max(axis=-1)
+            j = d.argmin(axis=1)
+            ok = d[np.arange(pa.shape[0]), j] < 1e-4
+            rec = {"rpn_object_score_max_abs": float(np.abs(out["rpn_object_score"].cpu().numpy() - cpu_out["rpn_object_score"]).max()),
+                   "large_sep_feature_max_rel": float(np.abs(out["large_sep_feature"].cpu().numpy() - cpu_out["large_sep_feature"]).max()
+                                                      / np.abs(cpu_out["large_sep_feature"]).max()),
+                   "proposals_paired": int(ok.sum()), "proposals": int(ok.size)}
+            if ok.any():
+                for k, kk in (("head_cls_score", "scores_max_abs"), ("bboxes_predict", "boxes_max_abs")):
+                    a = out[k].float().cpu().numpy().reshape(cpu_out[k].shape)
+                    rec[kk] = float(np.abs(a[np.nonzero(ok)[0]] - cpu_out[k][j[ok]]).max())
+            res[name] = rec
+        return res
+
+    def run_own(self, args):
+        ctx = own_context()
+        world, rank = ctx["world"], ctx["rank"]
+        main = self.measure(args, self.precision, ctx)
+        model, params = main.pop("_model"), main.pop("_params")
+        subs = {}
+        if not args.headline_only:
+            # the same network with bf16 operands (the fast mode: ~1e-2 per stage against the fp32 graph)
+            fast = self.measure(args, "bf16", ctx, state_dict=model.store.state_dict())
+            fast_model = fast.pop("_model")
+            fast.pop("_params")
+            subs["bf16_mode"] = fast
+            if self.size == 480 and self.backbone == "resnet50":
+                subs["psroi"] = PsroiSweepTop().measure(args, ctx)
+                subs["train"] = LightHeadResnet50Train().measure(args, ctx)
 
         cpu = None
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_network_baseline(self, params, model.store.state_dict(), reps=1)
+            cpu, cpu_out, img, keys = cpu_network_baseline(self, params, model.store.state_dict(), reps=1, want_outputs=True)
+            models = {self.precision: model}
+            if "bf16_mode" in subs:
+                models["bf16"] = fast_model
+            par = self.parity(models, cpu_out, img, keys)
+            main_par = par.pop(self.precision)
+            if "bf16_mode" in subs:
+                subs["bf16_mode"]["parity_vs_cpu_oracle"] = par["bf16"]
+        else:
+            main_par = None
 
         if rank == 0:
-            print(json.dumps({
-                "metric": self.metric, "value": value, "unit": self.unit, "n_gpus": world, "steps": args.steps,
-                "warmup": max(3, args.warmup), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": self.dtype, "data": "synthetic",
-                "config": {"workload": self.name, "global_batch": world * self.batch,
-                           "l2": "working set per step (activations ~0.6 GB) exceeds the 126 MB L2",
+            line = {
+                "metric": self.metric, "value": main["value"], "unit": self.unit, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": main["dtype"], "data": "synthetic",
+                "config": {"workload": self.name, "global_batch": world * self.batch, "precision": main["precision"],
+                           "l2": "working set per step (activations > 1 GB) exceeds the 126 MB L2",
                            "sharding": "images partitioned across ranks, no collective (inference)",
-                           "cuda_graph": graph is not None, "conv_autotune": bool(conv_ops.AUTOTUNE),
+                           "cuda_graph": main["cuda_graph"], "conv_autotune": not args.no_autotune,
                            "proposals": "pre_nms_top_n=5000 post_nms_top_n=1000 nms=0.7 (eval flags)",
                            "postprocess": "bboxes_eval on the GPU inside the step: 20 classes x top-400 x NMS 0.3 -> 200"},
-                "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": self.unit, "ms_per_step": e2e_ms,
-                        "h2d_bytes_per_step": int(imgs_h.numel() * 4),
-                        "d2h_bytes_per_step": int(probs_h.numel() * 4 + boxes_h.numel() * 4)},
-                "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
-                "roofline": roofline, "cpu_baseline": cpu,
-            }))
+                "clocks": main["clocks"], "e2e": main["e2e"],
+                "gpu_launches": int(main["gpu_launches_per_step"] * args.steps),
+                "gpu_launches_per_step": main["gpu_launches_per_step"],
+                "roofline": main["roofline"], "cpu_baseline": cpu,
+                "parity_vs_cpu_oracle": main_par,
+            }
+            line.update(subs)
+            print(json.dumps(line))
         dist_finish(world)
 
     def run_reference(self, args):
@@ -352,7 +429,7 @@ class LightHeadResnet50:
         del torch
 
 
-def cpu_network_baseline(wl, params, sd, reps=1, warmup=0):
+def cpu_network_baseline(wl, params, sd, reps=1, warmup=0, want_outputs=False):
     """The reference-semantics CPU path (oracle/net.py, PyTorch CPU fp32 -- TF1 itself is not installable) on a
     bounded sample: ONE 480x480 image per step, all host threads."""
     import torch
@@ -371,8 +448,12 @@ def cpu_network_baseline(wl, params, sd, reps=1, warmup=0):
                create_seed=0)  # creates any missing variable (tiny input), untimed
     from oracle import detections as od
 
+    keys = np.random.default_rng(7).random((1, params["rpn_post_nms_top_n"]), dtype=np.float32)
+    last = {}
+
     def one():
-        o = onet.model(img, sd, params, anchors)
+        o = onet.model(img, sd, params, anchors, shuffle_keys=keys)
+        last["o"] = o
         od.bboxes_eval_select(o["head_cls_score"], o["bboxes_predict"], np.array([0, 0, 1, 1], np.float32),
                               (wl.size, wl.size), params["num_classes"], train_image_size=wl.size)
 
@@ -382,9 +463,10 @@ def cpu_network_baseline(wl, params, sd, reps=1, warmup=0):
     for _ in range(reps):
         one()
     dt = (time.perf_counter() - t0) / reps
-    return {"value": 1.0 / dt, "unit": "images/s", "cores": cores, "kind": "port",
+    base = {"value": 1.0 / dt, "unit": "images/s", "cores": cores, "kind": "port",
             "sample": "1 image of the batch per step (whole graph incl. proposals/NMS, PsRoIAlign C oracle, per-class NMS), "
                       "PyTorch-CPU fp32 restatement, %d threads, %d rep(s)" % (cores, reps)}
+    return (base, last["o"], img, keys) if want_outputs else base
 
 
 # ==============================================================================================
@@ -435,25 +517,13 @@ class PsroiSweepTop:
             "e2e": {"value": base["value"], "unit": self.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
 
-    def run_own(self, args):
+    def measure(self, args, ctx):
         import torch
         import torch.distributed as dist
 
-        import xdet_b200  # noqa: F401
         from xdet_b200 import _native, ops
-
-        world, rank, local = dist_env()
-        assert torch.cuda.is_available(), "bench.py (own arm) needs a GPU; there is no CPU fallback"
-        torch.cuda.set_device(local)
-        if world > 1:
-            dist_init(local)
-        _native.lib()
-        peaks = load_peaks()
-
-        def barrier():
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
+        world, rank, local, barrier, peaks = ctx["world"], ctx["rank"], ctx["local"], ctx["barrier"], ctx["peaks"]
+        steps = max(5, min(args.steps, 20))
 
         x_h, rois_h = self.host_inputs(rank)
         x_pin, rois_pin = torch.from_numpy(x_h).pin_memory(), torch.from_numpy(rois_h).pin_memory()
@@ -473,7 +543,7 @@ class PsroiSweepTop:
         sampler = ClockSampler(local)
         sampler.start()
         launches0 = _native.launch_count()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
         for a, b in ev:
             flush.zero_()  # evict the previous step's output / the map from L2 (not timed)
@@ -496,10 +566,10 @@ class PsroiSweepTop:
             e2e_step()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             e2e_step()
         barrier()
-        e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+        e2e_ms = (time.perf_counter() - t0) / steps * 1e3
         clocks = sampler.finish()
         t = torch.tensor([step_ms, e2e_ms], device="cuda", dtype=torch.float64)
         if world > 1:
@@ -510,25 +580,34 @@ class PsroiSweepTop:
         cpu = None
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             cpu, _ = self.cpu(x_h, rois_h, 3)
-        if rank == 0:
-            print(json.dumps({
-                "metric": self.metric, "value": world * achieved, "unit": self.unit, "n_gpus": world,
-                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": step_ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": self.dtype, "data": "synthetic",
-                "config": {"workload": self.name, "l2": "flushed between timed iterations (256 MB memset)",
-                           "sharding": "independent RoI batches per rank, no collective"},
-                "clocks": clocks,
+        del flush
+        return {"metric": self.metric, "workload": self.name, "value": world * achieved, "unit": self.unit,
+                "steps": steps, "ms_per_step": step_ms, "dtype": self.dtype,
+                "l2": "flushed between timed iterations (256 MB memset)", "clocks": clocks,
                 "e2e": {"value": world * nbytes / (e2e_ms * 1e-3) / 1e9, "unit": self.unit, "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": int(x_h.nbytes + rois_h.nbytes),
                         "d2h_bytes_per_step": int(out_pin.numel() * 4 + idx_pin.numel() * 4)},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
-                             "kernel": "psroi_prep_geom_kernel + psroi_prep_perm_kernel + psroi_fwd_select_kernel<4>",
+                             "kernel": "psroi_prep_geom_kernel + psroi_prep_perm_kernel + psroi_fwd_select_kernel",
                              "algorithmic_bytes_per_launch": nbytes, "kernel_ms": step_ms},
-                "cpu_baseline": cpu,
+                "cpu_baseline": cpu}
+
+    def run_own(self, args):
+        ctx = own_context()
+        m = self.measure(args, ctx)
+        if ctx["rank"] == 0:
+            print(json.dumps({
+                "metric": self.metric, "value": m["value"], "unit": self.unit, "n_gpus": ctx["world"],
+                "steps": m["steps"], "warmup": max(3, args.warmup), "ms_per_step": m["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": self.dtype, "data": "synthetic",
+                "config": {"workload": self.name, "l2": m["l2"],
+                           "sharding": "independent RoI batches per rank, no collective"},
+                "clocks": m["clocks"], "e2e": m["e2e"], "gpu_launches": m["gpu_launches"], "roofline": m["roofline"],
+                "cpu_baseline": m["cpu_baseline"],
             }))
-        dist_finish(world)
+        dist_finish(ctx["world"])
 
 
 class LightHeadResnet50Train:
@@ -538,29 +617,18 @@ class LightHeadResnet50Train:
     metric, unit, dtype = "train_images_per_sec_480x480", "images/s", "bf16"
     batch, size = 8, 480
 
-    def run_own(self, args):
+    backbone = "resnet50"
+
+    def measure(self, args, ctx):
         import torch
         import torch.distributed as dist
 
-        import xdet_b200  # noqa: F401
         from xdet_b200 import _native
         from xdet_b200 import light_head_rfcn_train as lt
         from xdet_b200.ops import conv as conv_ops
+        world, rank, local, barrier, peaks = ctx["world"], ctx["rank"], ctx["local"], ctx["barrier"], ctx["peaks"]
 
-        world, rank, local = dist_env()
-        assert torch.cuda.is_available(), "bench.py (own arm) needs a GPU; there is no CPU fallback"
-        torch.cuda.set_device(local)
-        if world > 1:
-            dist_init(local)
-        _native.lib()
-        peaks = load_peaks()
-
-        def barrier():
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-
-        params = lt.make_params(train_image_size=self.size, batch_size=self.batch)
+        params = lt.make_params(train_image_size=self.size, batch_size=self.batch, backbone=self.backbone)
         trainer = lt.LightHeadTrainer(params, seed=0)  # same seed on every rank: identical initial weights
         images, gt, gl, keys = lt.synthetic_batch(params, self.batch, seed=3 + 1000 * rank, device="cpu")
         host = [images.pin_memory(), gt.pin_memory(), gl.pin_memory()] + [keys[k].pin_memory() for k in sorted(keys)]
@@ -571,8 +639,10 @@ class LightHeadResnet50Train:
             kd = dict(zip(sorted(keys), tensors[3:]))
             return trainer.step(tensors[0], tensors[1], tensors[2], kd)
 
-        l0 = _native.launch_count()
         eager_step = step
+        eager_step(dev)  # first pass: packs, one-time tile-shape tuning
+        torch.cuda.synchronize()
+        l0 = _native.launch_count()
         eager_step(dev)
         torch.cuda.synchronize()
         launches_per_step = _native.launch_count() - l0
@@ -658,31 +728,44 @@ class LightHeadResnet50Train:
         achieved = conv_flops / (conv_ms * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
         h2d = int(sum(t_.numel() * t_.element_size() for t_ in host))
-        if rank == 0:
-            print(json.dumps({
-                "metric": self.metric, "value": world * self.batch / (step_ms * 1e-3), "unit": self.unit, "n_gpus": world,
-                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": step_ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": self.dtype, "data": "synthetic",
-                "config": {"workload": self.name, "global_batch": world * self.batch,
-                           "l2": "working set per step (saved activations ~2 GB) exceeds the 126 MB L2",
-                           "sharding": "images partitioned across ranks; one NCCL all-reduce of the flat fp32 gradient "
-                                       "buffer (%.0f MB) per step" % (trainer.grads.numel() * 4 / 1e6),
-                           "cuda_graph": graph is not None, "conv_autotune": bool(conv_ops.AUTOTUNE),
-                           "flags": "rpn 10000->1800 @0.7, 64 RoIs/img @25% fg, OHEM 32, 256 RPN samples/img, momentum 0.9"},
+        comm = getattr(trainer, "comm_info", lambda: None)()
+        return {"metric": self.metric, "workload": self.name, "value": world * self.batch / (step_ms * 1e-3),
+                "unit": self.unit, "ms_per_step": step_ms, "dtype": self.dtype, "global_batch": world * self.batch,
+                "l2": "working set per step (saved activations ~2 GB) exceeds the 126 MB L2",
+                "sharding": "images partitioned across ranks; NCCL all-reduce (sum) of the flat fp32 gradient buffer "
+                            "(%.0f MB) per step" % (trainer.grads.numel() * 4 / 1e6),
+                "allreduce_bytes_per_step": int(trainer.grads.numel() * 4) if world > 1 else 0, "allreduce": comm,
+                "cuda_graph": graph is not None,
+                "flags": "rpn 10000->1800 @0.7, 64 RoIs/img @25% fg, OHEM 32, 256 RPN samples/img, momentum 0.9",
                 "clocks": clocks,
                 "e2e": {"value": world * self.batch / (e2e_ms * 1e-3), "unit": self.unit, "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},
-                "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
+                "gpu_launches_per_step": int(launches_per_step),
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": achieved / peak, "traffic": None,
                              "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
                              "kernel": "conv_gemm_kernel (forward + input gradients) and conv_wgrad_kernel, %d launches per step" % len(prof),
                              "algorithmic_flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms,
                              "note": "per-launch CUDA-event times of an eager step"},
-                "cpu_baseline": None,
-                "losses": {k: float(out[k]) for k in ("rpn_cross_entropy_loss", "rpn_location_loss", "head_loss")},
+                "losses": {k: float(out[k]) for k in ("rpn_cross_entropy_loss", "rpn_location_loss", "head_loss")}}
+
+    def run_own(self, args):
+        ctx = own_context()
+        m = self.measure(args, ctx)
+        if ctx["rank"] == 0:
+            print(json.dumps({
+                "metric": self.metric, "value": m["value"], "unit": self.unit, "n_gpus": ctx["world"],
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": m["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": self.dtype, "data": "synthetic",
+                "config": {"workload": self.name, "global_batch": m["global_batch"], "l2": m["l2"], "sharding": m["sharding"],
+                           "cuda_graph": m["cuda_graph"], "flags": m["flags"]},
+                "clocks": m["clocks"], "e2e": m["e2e"],
+                "gpu_launches": int(m["gpu_launches_per_step"] * args.steps),
+                "gpu_launches_per_step": m["gpu_launches_per_step"], "roofline": m["roofline"], "cpu_baseline": None,
+                "allreduce": m["allreduce"], "allreduce_bytes_per_step": m["allreduce_bytes_per_step"],
+                "losses": m["losses"],
             }))
-        dist_finish(world)
+        dist_finish(ctx["world"])
 
     def run_reference(self, args):
         world, rank, _ = dist_env()
@@ -719,6 +802,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--headline-only", action="store_true", help="skip the bf16 / psroi / train sub-records")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph replay")
     ap.add_argument("--no-autotune", action="store_true", help="keep the heuristic conv tile shapes (no per-shape tuning)")
     args = ap.parse_args()

@@ -23,7 +23,7 @@ from . import net as onet
 
 EPS = onet.EPS_XCEPTION
 # True: round every activation / activation-gradient that crosses a kernel boundary to bf16 (what the CUDA twin,
-# x-detector_b200/net/xception_train_staged.py, stores between launches); weight gradients stay unrounded (fp32 on
+# x-detector_b200/net/xception_train.py, stores between launches); weight gradients stay unrounded (fp32 on
 # the device).  Used to CALIBRATE the tolerances of the device-vs-blueprint test, not by the autograd check.
 EMULATE_BF16 = False
 

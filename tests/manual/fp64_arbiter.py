@@ -2,13 +2,13 @@
 """Whose rounding is a delta?  Convolution stages of the Light-Head R-CNN forward in float64 on the CPU (the
 oracle's graph, exact for this purpose) against (a) the fp32 CPU oracle and (b) the GPU path in each precision.
 GPU only; developer tool.
-    python tools/fp64_arbiter.py [--backbone resnet50] [--size 480] [--batch 2] [--chunks 1,2,12]"""
+    python tests/manual/fp64_arbiter.py [--backbone resnet50] [--size 480] [--batch 2] [--chunks 1,2,12]"""
 import argparse
 import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402

@@ -2,7 +2,7 @@
 """Error against the fp32 CPU oracle AND throughput of one precision mode of the Light-Head R-CNN forward at a
 BASELINE shape (default: config 2, ResNet-50, 480x480).  GPU only; developer tool (tests/ hold the assertions).
 
-    python tools/parity_bench.py --precision fp32x3 --backbone resnet50 --size 480 --parity-batch 2 --batch 8
+    python tests/manual/parity_bench.py --precision fp32x3 --backbone resnet50 --size 480 --parity-batch 2 --batch 8
 """
 import argparse
 import json
@@ -10,7 +10,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402

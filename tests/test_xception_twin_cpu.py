@@ -1,5 +1,5 @@
 """CPU: the COMPOSITION logic of the staged device-side training backbone
-(x-detector_b200/net/xception_train_staged.py) -- argument orders, geometry tuples, NHWC / packed-gradient layouts,
+(x-detector_b200/net/xception_train.py) -- argument orders, geometry tuples, NHWC / packed-gradient layouts,
 the TF-layout conversions of the returned gradients, the order of the backward walk -- checked before its first GPU
 run by executing it with every kernel wrapper replaced by a float64 torch-CPU stand-in that honours the wrapper's
 documented contract (same signatures, NHWC bf16 tensors in and out, the packed [Cout, kh*kw, cin_pad] weight-gradient
@@ -18,7 +18,7 @@ import xdet_b200  # noqa: F401
 from oracle import net as onet
 from oracle import xception_backward as xb
 from xdet_b200 import ops
-from xdet_b200.net import xception_train_staged as xt
+from xdet_b200.net import xception_train as xt
 from xdet_b200.ops import conv as conv_mod
 from xdet_b200.ops import train as T
 

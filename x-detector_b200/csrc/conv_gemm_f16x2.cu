@@ -539,7 +539,7 @@ extern "C" int xdet_conv2d_f16x2(const void* d_in_pair, const xdet_conv_f16x2_de
   a.k_chunks_per_tap = kcpt;
   a.num_k_blocks = taps * kcpt;
   // equal chunks of at most chunk_kb k-blocks (default 2 = 128 reduction elements = 8 accumulation steps: measured,
-  // tools/fp64_arbiter.py -- the truncation bias is then below the fp32 CPU oracle's own rounding noise)
+  // tests/manual/fp64_arbiter.py -- the truncation bias is then below the fp32 CPU oracle's own rounding noise)
   const int max_chunk = d->chunk_kb > 0 ? d->chunk_kb : 2;
   const int nchunks = (a.num_k_blocks + max_chunk - 1) / max_chunk;
   a.chunk_kb = (a.num_k_blocks + nchunks - 1) / nchunks;

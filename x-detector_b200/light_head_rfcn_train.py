@@ -6,10 +6,14 @@
   (:321-378), proposals (K=10000 -> NMS 0.7 -> 1800) + ``ext_encode_rois`` (64 RoIs/image @ 25 % fg), PsRoIAlign +
   fc head with OHEM (top-32 of the per-RoI loss, get_head net/xception_body.py:504-560), L2 on the non-BN
   variables (:420), backward through everything, momentum-SGD with the piecewise learning rate (:426-441).
-  The backbone is the ResNet-50 v2 light-head composition of BASELINE configs 2/4.
-* Data parallel: images shard across ranks; the only exchange is ONE all-reduce (sum) of the flat fp32 gradient
-  buffer per step (``torch.distributed``: NCCL on GPUs), divided by the world size inside the optimizer kernel.
-  Batch-norm statistics stay local to each rank, exactly like TF tower replication (SURVEY 8 e).
+  Backbones: ``backbone='resnet50'`` = the ResNet-50 v2 light-head composition of BASELINE configs 2/4 (SURVEY 8 a3);
+  ``backbone='xception'`` = the reference's own training backbone (XceptionBody, :289; net/xception_train.py).
+* Data parallel: images shard across ranks; the only exchange is the all-reduce (sum) of the flat fp32 gradient
+  buffer (``torch.distributed``: NCCL on GPUs), divided by the world size inside the optimizer kernel.  The buffer is
+  laid out in forward order, so its tail is complete first in the backward: it is cut into BUCKETS by network stage
+  and each bucket's all-reduce is launched on a communication stream as soon as the last gradient of the stage has
+  been written, overlapping the rest of the backward (SURVEY 8 e).  Batch-norm statistics stay local to each rank,
+  exactly like TF tower replication.
 
 TensorFlow's autodiff is replaced by an explicit backward: every forward layer object below saves what its
 gradient needs and ``bwd`` launches the gradient kernels (``ops.conv2d_wgrad`` / ``ops.conv2d_dgrad`` on the
@@ -87,9 +91,12 @@ class _Registry(object):
         total = sum((n + 3) // 4 * 4 for n, _ in self.requests)
         self.flat = torch.zeros(total, dtype=torch.float32, device=self.device)
         off = 0
+        self.offsets = []  # flat offset of request i (and the total at the end): bucket boundaries are taken from here
         for n, setter in self.requests:
+            self.offsets.append(off)
             setter(self.flat[off:off + n])
             off += (n + 3) // 4 * 4
+        self.offsets.append(off)
 
 
 class ConvParams(object):
@@ -250,8 +257,8 @@ class Bottleneck(object):
 
 
 def allreduce_gradients(flat, group=None):
-    """The ONE exchange of a data-parallel step: sum the flat fp32 gradient buffer over the ranks (NCCL on GPUs,
-    gloo in the CPU tests).  Returns the world size; the optimizer kernels divide by it (grad_scale = 1/world)."""
+    """The exchange of a data-parallel step: sum (a bucket of) the flat fp32 gradient buffer over the ranks (NCCL on
+    GPUs, gloo in the CPU tests).  Returns the world size; the optimizer kernels divide by it (grad_scale = 1/world)."""
     if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
         return 1
     world = torch.distributed.get_world_size(group)
@@ -272,7 +279,9 @@ def shard_batch(global_batch, world, rank):
 class LightHeadTrainer(object):
     def __init__(self, params=None, seed=0, device="cuda", state_dict=None, process_group=None):
         self.params = p = params or make_params()
-        assert p['backbone'] == 'resnet50', "the training step is built for the ResNet-50 composition (config 4)"
+        if p['backbone'] not in ('resnet50', 'xception'):
+            raise ValueError("backbone must be 'resnet50' or 'xception'")
+        self.xception = p['backbone'] == 'xception'
         self.device = torch.device(device)
         self.store = store = VariableStore(device=device, seed=seed, state_dict=state_dict)
         self.pg = process_group
@@ -301,9 +310,57 @@ class LightHeadTrainer(object):
         self.anchors_yxhw = torch.stack([cy, cx, hh, ww], -1).contiguous()
         self.anchors_pt = torch.stack([cy - hh / 2., cx - ww / 2., cy + hh / 2., cx + ww / 2.], -1).contiguous()
         self.side = torch.cuda.Stream(device=self.device)
+        self.comm = torch.cuda.Stream(device=self.device)
+        self.marks = []  # (stage name, index of its first gradient request): where the all-reduce buckets start
         self._build()
         reg.finalize()
         self.grads = reg.flat
+        # buckets in flat (= forward) order: [(name, start, end)]; a stage's bucket is complete when the backward has
+        # passed the stage's first layer
+        starts = [("first", 0)] + [(n, reg.offsets[i]) for n, i in self.marks]
+        self.buckets = [(n, a, (starts[j + 1][1] if j + 1 < len(starts) else reg.offsets[-1]))
+                        for j, (n, a) in enumerate(starts)]
+        self.overlap_allreduce = True
+        self.local_only = False  # tests: keep this rank's own gradient (no exchange)
+        self._pending = None
+
+    # ---- bucketed gradient all-reduce ---------------------------------------------------------------------------
+    def _world(self):
+        if self.local_only or not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            return 1
+        return torch.distributed.get_world_size(self.pg)
+
+    def _stage_done(self, name):
+        """Every gradient of bucket ``name`` (and of all later buckets) has been written on the current stream: start
+        its all-reduce on the communication stream, beside the rest of the backward."""
+        if self._pending is None or not self.overlap_allreduce:
+            return
+        for bname, a, b in self.buckets:
+            if bname == name and bname in self._pending and b > a:
+                self._pending.remove(bname)
+                self.comm.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self.comm):
+                    torch.distributed.all_reduce(self.grads[a:b], op=torch.distributed.ReduceOp.SUM, group=self.pg)
+
+    def _allreduce_finish(self):
+        """The buckets not sent yet (all of them without overlap), then JOIN the communication stream."""
+        world = self._world()
+        if world > 1:
+            if self.overlap_allreduce:
+                for bname, a, b in self.buckets:
+                    if bname in self._pending:
+                        self._stage_done(bname)
+                torch.cuda.current_stream().wait_stream(self.comm)
+            else:
+                allreduce_gradients(self.grads, self.pg)
+        self._pending = None
+        return world
+
+    def comm_info(self):
+        return {"collective": "ncclAllReduce(sum, fp32) per bucket on a communication stream, launched when the "
+                              "stage's last gradient is written (overlaps the rest of the backward)",
+                "overlap": bool(self.overlap_allreduce),
+                "buckets": [{"stage": n, "bytes": int((b - a) * 4)} for n, a, b in reversed(self.buckets)]}
 
     # ---- variable creation in the reference's naming order --------------------------------------------------
     def _conv(self, cin, cout, k, stride=1, dil=1, fold=False, need_dgrad=True, init=None):
@@ -342,19 +399,47 @@ class LightHeadTrainer(object):
         s, p = self.store, self.params
         nc, A = p['num_classes'], self.A
         with s.scope(p['model_scope']):
-            self.stem = self._conv(3, 64, 7, stride=2, fold=True, need_dgrad=False)
-            self.layers = []
-            cin = 64
-            nb = p['resnet_layers']
-            for filters, blocks, stride, dil in ((64, nb[0], 1, 1), (128, nb[1], 2, 1), (256, nb[2], 2, 1), (512, nb[3], 2, 2)):
-                layer = []
-                for i in range(blocks):
-                    layer.append(self._block(cin, filters, i == 0, stride if i == 0 else 1, dil))
-                    cin = 4 * filters
-                self.layers.append(layer)
-                if len(self.layers) == 3:
-                    self.bn_rpn = self._bn(cin)  # batch_norm_relu -> RPN feature (created before block_layer4)
-            self.bn_final = self._bn(cin)
+            if self.xception:
+                # the reference's own training backbone (light_head_rfcn_train.py:289): variables under the reference's
+                # names, gradients / momentum / moving statistics through this trainer's parameter classes
+                from .net import xception_train as xt
+                vars_, moving = {}, {}
+                for kind, name, shape in xt.variable_specs(3):
+                    if kind == "bn":
+                        bn = s.batch_norm(name, shape)
+                        vars_[name + "/gamma"], vars_[name + "/beta"] = bn["gamma"][1], bn["beta"][1]
+                        moving[name + "/moving_mean"], moving[name + "/moving_variance"] = bn["mean"][1], bn["var"][1]
+                    else:
+                        with s.scope(name):
+                            vars_[name + "/" + kind] = s.get(kind, shape, s.glorot_normal)[1]
+                self.body = xt.TrainableXceptionBody(vars_, moving, self.reg, ConvParams, VecParam,
+                                                     key_prefix=p['model_scope'] + "/")
+                self.convs += self.body.convs
+                self.vecs += self.body.vecs
+                self.marks += [("middle", self.body.req_marks["middle"]), ("exit", self.body.req_marks["exit"])]
+                rpn_cin = 728
+            else:
+                self.stem = self._conv(3, 64, 7, stride=2, fold=True, need_dgrad=False)
+                self.layers = []
+                cin = 64
+                nb = p['resnet_layers']
+                for filters, blocks, stride, dil in ((64, nb[0], 1, 1), (128, nb[1], 2, 1), (256, nb[2], 2, 1),
+                                                     (512, nb[3], 2, 2)):
+                    if len(self.layers) >= 2:
+                        self.marks.append(("layer%d" % (len(self.layers) + 1), len(self.reg.requests)))
+                    layer = []
+                    for i in range(blocks):
+                        layer.append(self._block(cin, filters, i == 0, stride if i == 0 else 1, dil))
+                        cin = 4 * filters
+                    self.layers.append(layer)
+                    if len(self.layers) == 3:
+                        self.bn_rpn = self._bn(cin)  # batch_norm_relu -> RPN feature (created before block_layer4)
+                        # (it lands in the layer-3 bucket: its gradient is written right before layer 3's)
+                self.marks.append(("heads", len(self.reg.requests)))
+                self.bn_final = self._bn(cin)
+                rpn_cin = 1024
+            if self.xception:
+                self.marks.append(("heads", len(self.reg.requests)))
 
             def named_conv(kh, kw, cin_, cout_, init=None):
                 name = s.auto_name("conv2d")
@@ -375,10 +460,10 @@ class LightHeadTrainer(object):
                 return fused, views
 
             with s.scope('rpn_head'):
-                k0, b0 = named_conv(3, 3, 1024, 512)
+                k0, b0 = named_conv(3, 3, rpn_cin, 512)
                 k1, b1 = named_conv(1, 1, 512, 2 * A)
                 k2, b2 = named_conv(1, 1, 512, 4 * A)
-            cp0 = ConvParams(self.reg, [(k0[0], k0[1], 0, 0)], 3, 3, 1024, 512)
+            cp0 = ConvParams(self.reg, [(k0[0], k0[1], 0, 0)], 3, 3, rpn_cin, 512)
             cp12 = ConvParams(self.reg, [(k1[0], k1[1], 0, 0), (k2[0], k2[1], 2 * A, 0)], 1, 1, 512, 6 * A)
             self.convs += [cp0, cp12]
             self.rpn_conv = Conv(cp0, bias=self._bias([b0[1]]))
@@ -453,21 +538,29 @@ class LightHeadTrainer(object):
         fm = self.fmap
         self.grads.zero_()
 
+        self._pending = set(n for n, _, _ in self.buckets) if self._world() > 1 else None
+
         # ---------------- forward: backbone ----------------
-        Wimg = images.shape[3]
-        Wo = (Wimg + 6 - 7) // 2 + 1
-        wp = (max((Wo - 1) * 2 + 8, Wimg + 3) + 7) // 8 * 8
-        x8 = ops.image_to_nhwc8(images.contiguous(), 3, wp)
-        Ho = (images.shape[2] + 6 - 7) // 2 + 1
-        self.stem.x = x8
-        y0 = ops.conv2d_nhwc(x8, self.stem.p.pack, 64, 7, 7, padding=(3, 3, Ho, Wo), strides=(2, 2), cin=3,
-                             fold_w=(Wimg, 3))
-        x, pool_arg = T.maxpool3x3s2_fwd_train(y0)
-        for li in range(3):
-            for blk in self.layers[li]:
-                x = blk.fwd(x)
-        x3 = x
-        rpn_feat = self.bn_rpn.fwd(x3)
+        if self.xception:
+            rpn_feat = self.body.fwd_mid(images)
+            fm = rpn_feat.shape[1]
+            assert fm == self.fmap, "the anchors are laid out for a %dx%d map, the backbone produced %dx%d" % (
+                self.fmap, self.fmap, fm, fm)
+        else:
+            Wimg = images.shape[3]
+            Wo = (Wimg + 6 - 7) // 2 + 1
+            wp = (max((Wo - 1) * 2 + 8, Wimg + 3) + 7) // 8 * 8
+            x8 = ops.image_to_nhwc8(images.contiguous(), 3, wp)
+            Ho = (images.shape[2] + 6 - 7) // 2 + 1
+            self.stem.x = x8
+            y0 = ops.conv2d_nhwc(x8, self.stem.p.pack, 64, 7, 7, padding=(3, 3, Ho, Wo), strides=(2, 2), cin=3,
+                                 fold_w=(Wimg, 3))
+            x, pool_arg = T.maxpool3x3s2_fwd_train(y0)
+            for li in range(3):
+                for blk in self.layers[li]:
+                    x = blk.fwd(x)
+            x3 = x
+            rpn_feat = self.bn_rpn.fwd(x3)
         r = self.rpn_conv.fwd(rpn_feat, relu=True)
         rpn_out = self.rpn_out.fwd(r, out_layout="nhwc_f32")  # [N,fm,fm,6A]: logits [0,2A), deltas [2A,6A)
 
@@ -534,9 +627,12 @@ class LightHeadTrainer(object):
         # ---------------- main stream meanwhile: block_layer4, thin feature map ----------------
         conv_ops.MAX_CTAS = 148 - 12
         try:
-            for blk in self.layers[3]:
-                x = blk.fwd(x)
-            backbone = self.bn_final.fwd(x)
+            if self.xception:
+                backbone = self.body.fwd_exit()
+            else:
+                for blk in self.layers[3]:
+                    x = blk.fwd(x)
+                backbone = self.bn_final.fwd(x)
             mid = self.sep_a.fwd(backbone)
             bias_b = self.sep_b_biases[0] + self.sep_b_biases[1]
             # 490 channels live in rows of 496 (16-byte pixel strides for TMA and the vector kernels), zero tail
@@ -601,21 +697,28 @@ class LightHeadTrainer(object):
         # ---- RPN head ----
         dr = T.relu_bwd(self.rpn_out.bwd(d_rpn), r)
         d_rpn_feat = self.rpn_conv.bwd(dr)
-        # ---- backbone ----
-        dx = self.bn_final.bwd(dbackbone)
-        for li in (3, 2, 1, 0):
-            layer = self.layers[li]
-            if li == 2:  # x3 also feeds the RPN feature's batch_norm_relu
-                dx = self.bn_rpn.bwd(d_rpn_feat, add_in=dx)
-            for bi in range(len(layer) - 1, -1, -1):
-                blk = layer[bi]
-                dx = blk.bwd(dx)
-        dy0 = T.maxpool3x3s2_bwd(pool_arg, dx, y0.shape[1:3])
-        ops.conv2d_wgrad(x8, dy0, 7, 7, padding=(3, 3, Ho, Wo), strides=(2, 2), cin=3, cout=64, dw=self.stem.p.dw,
-                         fold_w=(Wimg, 3))
+        # ---- backbone (each stage's gradient bucket goes to the communication stream as soon as it is complete) ----
+        if self.xception:
+            self._stage_done("heads")
+            self.body.bwd(d_rpn_feat, dbackbone, stage_done=self._stage_done)
+        else:
+            dx = self.bn_final.bwd(dbackbone)
+            self._stage_done("heads")
+            for li in (3, 2, 1, 0):
+                layer = self.layers[li]
+                if li == 2:  # x3 also feeds the RPN feature's batch_norm_relu
+                    dx = self.bn_rpn.bwd(d_rpn_feat, add_in=dx)
+                for bi in range(len(layer) - 1, -1, -1):
+                    blk = layer[bi]
+                    dx = blk.bwd(dx)
+                if li >= 2:
+                    self._stage_done("layer%d" % (li + 1))
+            dy0 = T.maxpool3x3s2_bwd(pool_arg, dx, y0.shape[1:3])
+            ops.conv2d_wgrad(x8, dy0, 7, 7, padding=(3, 3, Ho, Wo), strides=(2, 2), cin=3, cout=64, dw=self.stem.p.dw,
+                             fold_w=(Wimg, 3))
 
-        # ================= all-reduce + optimizer =================
-        world = allreduce_gradients(self.grads, self.pg)
+        # ================= all-reduce (remaining buckets, join) + optimizer =================
+        world = self._allreduce_finish()
         if apply_update:
             lr = learning_rate(p, self.global_step)
             gs = 1.0 / world

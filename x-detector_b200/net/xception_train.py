@@ -1,22 +1,18 @@
-"""STAGED (written after the round's GPU minutes were spent; first run pending -- see csrc/staged/README.md):
-training-mode ``XceptionBody`` (net/xception_body.py:220-379 with is_training=True) on the CUDA kernels, forward tape
-+ explicit backward, the device-side twin of the CPU blueprint ``oracle/xception_backward.py`` (which is held to
+"""Training-mode ``XceptionBody`` (net/xception_body.py:220-379 with is_training=True) on the CUDA kernels: forward
+tape + explicit backward, the device-side twin of the CPU blueprint ``oracle/xception_backward.py`` (which is held to
 autograd for all 154 trainable variables).  Same classes, same order of operations; every method is one or two
 kernel launches:
 
-  Conv.bwd        xdet_conv2d_wgrad_bf16 + xdet_conv2d_dgrad_bf16
-  Depthwise.bwd   xdet_depthwise3x3_wgrad_bf16 (csrc/staged/) + the forward kernel on dY with flipped taps
+  Conv.bwd        xdet_conv2d_wgrad_bf16 + the forward kernel on dY with flipped weights (input gradient)
+  Depthwise.bwd   xdet_depthwise3x3_wgrad_bf16 + the forward kernel on dY with flipped taps
                   (+ xdet_relu_bwd_bf16 when the block ReLUs its input)
   BatchNorm       xdet_col_stats / xdet_bn_finalize forward, xdet_bn_relu_bwd_bf16 backward (relu flag 0 / 1)
   MaxPool         xdet_maxpool3x3s2_argmax_bf16 / xdet_maxpool3x3s2_bwd_bf16
 
-Not yet wired into ``LightHeadTrainer`` (whose backbone is the ResNet-50 composition): gradients are returned as a
-dict in TF variable layouts so that the first GPU run can be compared tensor by tensor with the blueprint
-(tests/test_staged_xception_train_gpu.py); fusions (BN into the pointwise epilogue, pool + residual) come after that.
-Needs the staged library: XDET_BUILD_STAGED=1.
+``XceptionBodyTraining`` returns gradients as a dict in TF variable layouts (compared tensor by tensor with the
+blueprint in tests/test_xception_train_gpu.py); ``TrainableXceptionBody`` is the same backbone over
+``LightHeadTrainer``'s parameter classes (flat all-reduce buffer, momentum slots, moving statistics).
 """
-import ctypes
-
 import torch
 
 from .. import _native, ops
@@ -214,16 +210,22 @@ class XceptionBodyTraining(object):
         y = self.b13[1].fwd(self.b13[0].fwd(x)) + self.exit_res.fwd(x)
         return mid, self.b14[1].fwd(self.b14[0].fwd(y))
 
-    def bwd(self, d_mid, d_out):
+    def bwd(self, d_mid, d_out, stage_done=None):
+        """``stage_done(name)`` is called when every gradient of the 'exit' / 'middle' flow has been written (the
+        trainer starts that bucket's all-reduce there)."""
         grads = {}
         d = self.b14[0].bwd(self.b14[1].bwd(d_out, grads), grads)
         dx = self.b13[0].bwd(self.b13[1].bwd(d, grads), grads) + self.exit_res.bwd(d, grads)
+        if stage_done is not None:
+            stage_done("exit")
         dx = dx + T.relu_bwd(d_mid.contiguous(), self.pre_mid)
         for blk in reversed(self.middle):
             d = dx
             for s in reversed(blk):
                 d = s.bwd(d, grads)
             dx = dx + d
+        if stage_done is not None:
+            stage_done("middle")
         for res, s1, s2, pool in reversed(self.entry):
             dx = s1.bwd(s2.bwd(pool.bwd(dx), grads), grads) + res.bwd(dx, grads)
         self.b1c1.bwd(self.b1c2.bwd(dx, grads), grads)
@@ -241,16 +243,24 @@ class TrainableXceptionBody(XceptionBodyTraining):
     layout} (updated in place by ``update``); ``moving``: {name + '/moving_mean' | '/moving_variance': tensor};
     ``reg``: the trainer's _Registry (gradient views are carved from its flat buffer at ``reg.finalize()``)."""
 
-    def __init__(self, store_vars, moving, reg, conv_params_cls, vec_param_cls):
+    def __init__(self, store_vars, moving, reg, conv_params_cls, vec_param_cls, key_prefix=""):
         self.convs, self.vecs = [], []
         self._reg, self._conv_cls, self._vec_cls, self._moving = reg, conv_params_cls, vec_param_cls, moving
         self._vars = store_vars
         XceptionBodyTraining.__init__(self, store_vars)
+        # positions in the registry where the middle and exit flows start (their gradients complete, in backward
+        # order, before the entry flow's: the trainer all-reduces them as separate buckets)
+        self.req_marks = {}
+        first_middle, first_exit = self.middle[0][0].dw, self.exit_res.conv
         for layer in self._layers():
+            if layer is first_middle:
+                self.req_marks["middle"] = len(reg.requests)
+            if layer is first_exit:
+                self.req_marks["exit"] = len(reg.requests)
             if isinstance(layer, Conv):
                 leaf = "pointwise_kernel" if (layer.name + "/pointwise_kernel") in store_vars else "kernel"
                 key = layer.name + "/" + leaf
-                layer.p = conv_params_cls(reg, [(key, store_vars[key], 0, 0)], layer.kh, layer.kw, layer.cin, layer.cout,
+                layer.p = conv_params_cls(reg, [(key_prefix + key, store_vars[key], 0, 0)], layer.kh, layer.kw, layer.cin, layer.cout,
                                           need_dgrad=layer.dpack is not None)
                 layer.pack, layer.dpack = layer.p.pack, layer.p.dpack     # the packs the optimizer refreshes
                 self.convs.append(layer.p)
@@ -306,3 +316,36 @@ class TrainableXceptionBody(XceptionBodyTraining):
             c.update(lr, momentum, weight_decay, grad_scale)
         for v in self.vecs:
             v.update(lr, momentum, weight_decay, grad_scale)
+
+
+def variable_specs(in_channels=3):
+    """(kind, name, shape) of every variable of XceptionBody in the reference's creation order
+    (net/xception_body.py:243-376): kind = 'kernel' | 'depthwise_kernel' | 'pointwise_kernel' | 'bn' (shape = channels)."""
+    out = []
+
+    def conv(name, k, cin, cout, bn_name):
+        out.append(("kernel", name, (k, k, cin, cout)))
+        out.append(("bn", bn_name, cout))
+
+    def sep(name, cin, cout):
+        out.append(("depthwise_kernel", name, (3, 3, cin, 1)))
+        out.append(("pointwise_kernel", name, (1, 1, cin, cout)))
+        out.append(("bn", name + "_bn", cout))
+
+    conv("block1_conv1", 3, in_channels, 32, "block1_conv1_bn")
+    conv("block1_conv2", 3, 32, 64, "block1_conv2_bn")
+    cin = 64
+    for blk, idx, filters in ((2, 1, 128), (3, 2, 256), (4, 3, 728)):
+        conv("conv2d_%d" % idx, 1, cin, filters, "batch_normalization_%d" % idx)
+        sep("block%d_sepconv1" % blk, cin, filters)
+        sep("block%d_sepconv2" % blk, filters, filters)
+        cin = filters
+    for i in range(8):
+        for j in (1, 2, 3):
+            sep("block%d_sepconv%d" % (i + 5, j), 728, 728)
+    conv("conv2d_4", 1, 728, 1024, "batch_normalization_4")
+    sep("block13_sepconv1", 728, 728)
+    sep("block13_sepconv2", 728, 1024)
+    sep("block14_sepconv1", 1024, 1536)
+    sep("block14_sepconv2", 1536, 2048)
+    return out
