@@ -72,6 +72,18 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+def ncu_traffic(precision, kernel_prefix):
+    """DRAM bytes (read + written) per step of the kernels whose name starts with ``kernel_prefix``, from the committed
+    ncu launch list of this workload (profiles/ncu_traffic_<precision>_r2.json, made by tools/ncu_step.py +
+    tools/ncu_traffic.py: cold-cache, serialised launches).  None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic_%s_r2.json" % precision)
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    hits = [v["dram_bytes_per_step"] for k, v in d.items() if k.split("::")[-1].startswith(kernel_prefix)]
+    return float(sum(hits)) if hits else None
+
+
 def dist_env():
     return int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 
@@ -311,7 +323,10 @@ class LightHeadResnet50:
         products = 3 if precision == "f16x2" else 1
         kname = "conv_gemm_f16x2_kernel" if precision == "f16x2" else "conv_gemm_kernel"
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peaks["source"] + " (burst cuBLAS bf16; fp16 runs at the same rate)",
+                    "traffic": ncu_traffic(precision, kname) if (self.size == 480 and self.backbone == "resnet50") else None,
+                    "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of all launches of the kernel in one "
+                                    "step, from the committed ncu launch list (profiles/ncu_traffic_%s_r2.txt)" % precision,
+                    "peak_source": peaks["source"] + " (burst cuBLAS bf16; fp16 runs at the same rate)",
                     "kernel": "%s (tcgen05 implicit GEMM), %d launches per step" % (kname, n_conv),
                     "algorithmic_flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms,
                     "kernel_ms_per_step_raw": conv_ms_raw, "event_pair_overhead_ms": ev_over,

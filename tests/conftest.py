@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the product creates missing batch-norm variables with TensorFlow's defaults (identity); the parity tests want
+    # NON-trivial scale / shift / moving statistics so that a folding or ordering error cannot hide
+    import xdet_b200  # noqa: F401  (import shim -> x-detector_b200/)
+    from xdet_b200.net import variables
+    variables.RANDOMIZE_BN = True
 
 
 @pytest.fixture(scope="session")

@@ -17,6 +17,9 @@ import torch  # noqa: E402
 import xdet_b200  # noqa: F401,E402
 from oracle import net as onet  # noqa: E402
 from xdet_b200 import light_head_rfcn_eval as lh  # noqa: E402
+from xdet_b200.net import variables as _variables  # noqa: E402
+
+_variables.RANDOMIZE_BN = True  # non-trivial batch-norm variables: a folding error cannot hide
 from xdet_b200.ops import conv as conv_ops  # noqa: E402
 
 KEYS = ("rpn_feat_map", "backbone_feat", "large_sep_feature", "rpn_cls", "rpn_box")

@@ -18,6 +18,9 @@ import torch  # noqa: E402
 
 import xdet_b200  # noqa: F401,E402
 from xdet_b200 import light_head_rfcn_eval as lh  # noqa: E402
+from xdet_b200.net import variables as _variables  # noqa: E402
+
+_variables.RANDOMIZE_BN = True  # non-trivial batch-norm variables: a folding error cannot hide
 
 
 def deltas(out, ref):

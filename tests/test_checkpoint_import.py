@@ -173,3 +173,65 @@ def test_reference_named_entry_points(tmp_path):
         flags.model_dir = str(tmp_path / "empty")
         flags.checkpoint_exclude_scopes = "xception_lighthead"
         th.get_init_fn_for_scaffold(flags, names)
+
+
+# ---- second opinions that do not come from this repository -------------------------------------------------------
+def test_crc32c_matches_tensorboards_implementation():
+    """CRC-32C and its TensorFlow mask against the implementation Google ships in TensorBoard's TensorFlow stub (the
+    only TensorFlow-authored code installed here), for the byte-loop and the vectorised large-input paths."""
+    tbs = pytest.importorskip("tensorboard.compat.tensorflow_stub.pywrap_tensorflow")
+    from xdet_b200.utility import tensor_bundle as tb
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 9, 4095, 4096, 70000, 16 * 4096 + 5, 3 * 1024 * 1024 + 77):
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert tb.crc32c(d) == (tbs.crc32c(d) & 0xFFFFFFFF), n
+        assert tb.masked_crc32c(d) == (tbs.masked_crc32c(d) & 0xFFFFFFFF), n
+
+
+def test_entry_protos_parse_with_tensorboards_tensorflow_protos(tmp_path):
+    """The dtype enum and the TensorShapeProto bytes inside every BundleEntryProto written here, parsed by the compiled
+    TensorFlow protobufs TensorBoard ships (types.proto, tensor_shape.proto)."""
+    types_pb2 = pytest.importorskip("tensorboard.compat.proto.types_pb2")
+    shape_pb2 = pytest.importorskip("tensorboard.compat.proto.tensor_shape_pb2")
+    from xdet_b200.utility import tensor_bundle as tb
+    w = tb.TensorBundleWriter(str(tmp_path / "m.ckpt-1"))
+    tensors = {"a/kernel": np.zeros((3, 3, 8, 16), np.float32), "global_step": np.array(7, np.int64),
+               "b/counts": np.arange(5, dtype=np.int32), "c/d": np.ones((2, 0, 4), np.float64)}
+    for k, v in tensors.items():
+        w.add(k, v)
+    w.finish()
+    want = {np.dtype(np.float32): types_pb2.DT_FLOAT, np.dtype(np.int64): types_pb2.DT_INT64,
+            np.dtype(np.int32): types_pb2.DT_INT32, np.dtype(np.float64): types_pb2.DT_DOUBLE}
+    r = tb.TensorBundleReader(str(tmp_path / "m.ckpt-1"))
+    with open(str(tmp_path / "m.ckpt-1.index"), "rb") as f:
+        raw_index = f.read()
+    for name, arr in tensors.items():
+        e = r.entries[name]
+        assert e.dtype == want[arr.dtype] and list(e.shape) == list(arr.shape)
+        assert np.array_equal(r.get_tensor(name), arr)
+        # the shape submessage, byte for byte, is what TensorFlow's own message class serialises
+        proto = shape_pb2.TensorShapeProto()
+        for s in arr.shape:
+            proto.dim.add().size = int(s)
+        assert proto.SerializeToString() in raw_index
+
+
+def test_trainer_checkpoint_roundtrip_through_the_product_writer(tmp_path):
+    """TensorBundleWriter -> TensorBundleReader, the ``checkpoint`` state file and its keep-N pruning."""
+    from xdet_b200.utility import tensor_bundle as tb
+    from xdet_b200.utility import train_helper as th
+    rng = np.random.default_rng(1)
+    for step in (1, 2, 3):
+        w = tb.TensorBundleWriter(str(tmp_path / ("model.ckpt-%d" % step)))
+        ts = {"s/v%03d/kernel" % i: rng.standard_normal((3, 3, i + 1, 2)).astype(np.float32) for i in range(200)}
+        ts["global_step"] = np.array(step, np.int64)
+        for k, v in ts.items():
+            w.add(k, v)
+        w.finish()
+        tb.update_checkpoint_state(str(tmp_path), str(tmp_path / ("model.ckpt-%d" % step)), keep=2)
+    assert th.latest_checkpoint(str(tmp_path)).endswith("model.ckpt-3")
+    assert not (tmp_path / "model.ckpt-1.index").exists() and (tmp_path / "model.ckpt-2.index").exists()
+    r = tb.TensorBundleReader(th.latest_checkpoint(str(tmp_path)))
+    assert set(r.entries) == set(ts) and int(r.get_tensor("global_step")) == 3
+    for k, v in ts.items():
+        assert np.array_equal(r.get_tensor(k), v), k

@@ -185,8 +185,8 @@ class LightHeadRFCN(object):
         self.params = params or make_params()
         self.store = VariableStore(device=device, seed=seed, state_dict=state_dict)
         self.labels = input_pipeline(self.params, device=device)
-
         self._det_consts = {}
+        self._check_restored = False  # from_checkpoint: report variables the checkpoint did not provide
 
     @classmethod
     def from_checkpoint(cls, params=None, checkpoint_path=None, checkpoint_model_scope=None, seed=0, device="cuda"):
@@ -197,7 +197,9 @@ class LightHeadRFCN(object):
         params = params or make_params()
         sd = train_helper.checkpoint_to_state_dict(checkpoint_path or params['checkpoint_path'], params['model_scope'],
                                                    checkpoint_model_scope)
-        return cls(params, seed=seed, device=device, state_dict=sd)
+        model = cls(params, seed=seed, device=device, state_dict=sd)
+        model._check_restored = True
+        return model
 
     def det_consts(self, n, image_shape=None, bbox_img=None, device="cuda"):
         """(bbox_img [n,4], min_size [n]) device tensors for the post-processing; cached, so a CUDA-graph capture of
@@ -220,6 +222,15 @@ class LightHeadRFCN(object):
         with conv_ops.precision(self.params.get('precision', 'bf16')):
             out = lighr_head_model_fn(images, self.labels, "eval", self.params, store=self.store,
                                       shuffle_keys=shuffle_keys)
+        if self._check_restored:
+            self._check_restored = False
+            missing = list(self.store.created)
+            if missing:
+                import warnings
+                stats = [k for k in missing if k.endswith(("moving_mean", "moving_variance", "gamma", "beta"))]
+                warnings.warn("from_checkpoint: %d variable(s) of the model were not in the checkpoint and keep their "
+                              "initial values (%d of them batch-norm scale / shift / moving statistics, initialised to "
+                              "identity), e.g. %s" % (len(missing), len(stats), ", ".join(missing[:4])), RuntimeWarning)
         if detections:
             N, C = images.shape[0], self.params['num_classes']
             ref, min_size = self.det_consts(N, image_shape, bbox_img, images.device)

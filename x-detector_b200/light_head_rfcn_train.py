@@ -356,6 +356,83 @@ class LightHeadTrainer(object):
         self._pending = None
         return world
 
+    # ---- checkpoints (what tf.estimator / tf.train.Saver do around the reference's train_op, :465-505) -------------
+    def trainable_variable_names(self):
+        """TF's TRAINABLE_VARIABLES collection of the graph: every variable but the batch-norm moving statistics."""
+        return [k for k in self.store.vars if not k.rsplit("/", 1)[-1].startswith("moving_")]
+
+    def _momentum_slots(self):
+        """{variable name: its Momentum slot} (``<name>/Momentum`` in a checkpoint, tf.train.MomentumOptimizer)."""
+        slots = {}
+        for cp in self.convs:
+            for (key, _, _, _), m in zip(cp.masters, cp.mom):
+                slots[key] = m
+        owners = []
+        for v in self.vecs:
+            owners += list(zip(v.tensors, v.mom))
+        owners.append((self.sep_b_biases[1], self.sep_b_bias_mom2))
+        for key, var in self.store.vars.items():
+            if key in slots:
+                continue
+            for t, m in owners:  # a fused bias owns one tensor; the named variables are views into it
+                off = (var.data_ptr() - t.data_ptr()) // 4
+                if var.data_ptr() >= t.data_ptr() and off + var.numel() <= t.numel():
+                    slots[key] = m.view(-1)[off:off + var.numel()].view(var.shape)
+                    break
+        return slots
+
+    def save_checkpoint(self, model_dir, keep=5):
+        """Write ``model_dir/model.ckpt-<global_step>`` as a TensorFlow V2 checkpoint: every variable under its TF
+        name, the Momentum slots and ``global_step``; update the ``checkpoint`` state file.  Returns the prefix."""
+        import os
+
+        from .utility import tensor_bundle as tb
+        torch.cuda.synchronize(self.device)
+        prefix = os.path.join(model_dir, "model.ckpt-%d" % self.global_step)
+        w = tb.TensorBundleWriter(prefix)
+        for k, v in self.store.vars.items():
+            w.add(k, v.detach().cpu().numpy())
+        for k, m in self._momentum_slots().items():
+            w.add(k + "/Momentum", m.detach().cpu().numpy())
+        import numpy as np
+        w.add("global_step", np.array(self.global_step, dtype=np.int64))
+        w.finish()
+        tb.update_checkpoint_state(model_dir, prefix, keep=keep)
+        return prefix
+
+    def restore_checkpoint(self, prefix_or_dir):
+        """Resume: variables, Momentum slots and global_step from a checkpoint written by ``save_checkpoint`` (or by the
+        reference's Estimator for the same graph).  The bf16 packs are rebuilt from the restored masters."""
+        from .utility import tensor_bundle as tb
+        from .utility import train_helper as th
+        path = th.resolve_checkpoint_path(prefix_or_dir)
+        if path is None:
+            raise FileNotFoundError("no checkpoint under %s" % prefix_or_dir)
+        r = tb.TensorBundleReader(path)
+        missing = [k for k in self.store.vars if not r.has_tensor(k)]
+        if missing:
+            raise KeyError("checkpoint %s lacks %d variable(s) of the model, e.g. %s" % (path, len(missing), missing[:3]))
+        for k, v in self.store.vars.items():
+            v.copy_(torch.from_numpy(r.get_tensor(k)).to(v.dtype).reshape(v.shape))
+        for k, m in self._momentum_slots().items():
+            if r.has_tensor(k + "/Momentum"):
+                m.copy_(torch.from_numpy(r.get_tensor(k + "/Momentum")).to(m.dtype).reshape(m.shape))
+        if r.has_tensor("global_step"):
+            self.global_step = int(r.get_tensor("global_step"))
+        self.refresh_packs()
+        return path
+
+    def refresh_packs(self):
+        """Re-derive the bf16 forward / input-gradient packs from the fp32 masters (after loading weights): one
+        optimizer update with zero learning rate, zero gradient and zero decay rewrites them and changes nothing else."""
+        self.grads.zero_()
+        saved = [[m.clone() for m in c.mom] for c in self.convs]
+        for c in self.convs:
+            c.update(0.0, 1.0, 0.0, 1.0)
+        for c, ms in zip(self.convs, saved):
+            for m, m0 in zip(c.mom, ms):
+                m.copy_(m0)
+
     def comm_info(self):
         return {"collective": "ncclAllReduce(sum, fp32) per bucket on a communication stream, launched when the "
                               "stage's last gradient is written (overlaps the rest of the backward)",
@@ -611,6 +688,11 @@ class LightHeadTrainer(object):
                 rois_all = torch.cat([props, gt_boxes * (gt_labels > 0).unsqueeze(-1).float()], dim=1).contiguous()
             rlab, rtgt, rsc = T.match_encode(rois_all, gt_boxes, gt_labels, 0.1, p['match_threshold'],
                                              p['neg_threshold_high'])
+            # the reference appends only the VALID ground-truth boxes (tf.boolean_mask, anchor_manipulator.py:345-347);
+            # here the padded slots ride along as zero boxes: mark them 'ignore' so that no threshold setting can ever
+            # sample them (with neg_threshold_low < 0 they would qualify as background)
+            G = gt_labels.shape[1]
+            rlab[:, rlab.shape[1] - G:].masked_fill_(gt_labels <= 0, -1)
             R = p['roi_one_image']
             if 'roi_idx' in inject:
                 roi_idx = inject['roi_idx']
@@ -780,14 +862,45 @@ def arg_parser():
 
 
 def main(argv=None):
+    """The reference's ``main`` (light_head_rfcn_train.py:456-526) on synthetic VOC-shaped tensors: resume from
+    ``--model_dir`` if it holds a checkpoint (what the Estimator does), else the fine-tuning restore of
+    ``get_init_fn_for_scaffold`` from ``--checkpoint_path`` (scope renaming, ``--checkpoint_exclude_scopes``,
+    ``--ignore_missing_vars``), else -- loudly -- random initialisation; a checkpoint is written to ``--model_dir`` every
+    ``--save_checkpoints_secs`` and at the end."""
+    import sys
+    import time
+
+    from .utility import train_helper as th
     args = arg_parser().parse_args(argv)
     params = make_params(**{k: getattr(args, k) for k in _DEFAULTS})
+    flags = types.SimpleNamespace(**params)
     tr = LightHeadTrainer(params)
+    resume = th.latest_checkpoint(flags.model_dir)
+    if resume:
+        print("resuming from %s" % tr.restore_checkpoint(resume))
+    else:
+        init_fn = th.get_init_fn_for_scaffold(flags, tr.trainable_variable_names(),
+                                              shapes={k: tuple(v.shape) for k, v in tr.store.vars.items()})
+        try:
+            sd = init_fn() if init_fn is not None else {}
+        except (FileNotFoundError, OSError) as e:
+            sd = {}
+            sys.stderr.write("WARNING: no checkpoint to fine-tune from (%s): TRAINING FROM RANDOM INITIALISATION\n" % e)
+        for k, v in sd.items():
+            tr.store.vars[k].copy_(torch.as_tensor(v).reshape(tr.store.vars[k].shape))
+        if sd:
+            tr.refresh_packs()
+            print("restored %d variables from the fine-tuning checkpoint" % len(sd))
     batch = synthetic_batch(params, args.batch_size, seed=3)
+    last_save = time.time()
     for i in range(args.steps):
         out = tr.step(*batch)
-        print("step %d  rpn_ce %.4f  rpn_loc %.4f  head %.4f" % (i, float(out['rpn_cross_entropy_loss']),
+        print("step %d  rpn_ce %.4f  rpn_loc %.4f  head %.4f" % (tr.global_step, float(out['rpn_cross_entropy_loss']),
                                                                  float(out['rpn_location_loss']), float(out['head_loss'])))
+        if time.time() - last_save >= flags.save_checkpoints_secs:
+            print("saved %s" % tr.save_checkpoint(flags.model_dir))
+            last_save = time.time()
+    print("saved %s" % tr.save_checkpoint(flags.model_dir))
 
 
 if __name__ == '__main__':

@@ -5,9 +5,13 @@ Variables are fp32 torch tensors keyed by the reference's TF names (``rpn_head/c
 ``batch_normalization_7/moving_variance`` ...), so that a converted TF checkpoint of the reference can be
 dropped in as a state dict.  Kernels keep TF's layouts: conv [KH,KW,Cin,Cout], dense [in,out].
 Missing variables are created with the reference's initialisers (seeded), since no weights exist offline:
-``tf.glorot_normal_initializer`` (net/xception_body.py:25-26), ``tf.variance_scaling_initializer``
-(net/resnet_v2.py:89), zeros for biases; batch-norm statistics are drawn NON-trivially
-(gamma~U(.5,1.5), beta,mean~N(0,.1), var~U(.5,1.5)) so that folding errors would show in parity tests.
+``tf.glorot_normal_initializer`` (net/xception_body.py:25-26) and ``tf.variance_scaling_initializer``
+(net/resnet_v2.py:89) -- both TRUNCATED normals in TF 1.6 (resampled beyond two standard deviations) --, zeros for
+biases, and TensorFlow's batch-norm defaults (gamma = 1, beta = 0, moving_mean = 0, moving_variance = 1): what a
+training or fine-tuning run of the reference starts from (its restore map, utility/train_helper.py, never restores
+moving statistics).  ``randomize_bn=True`` (tests only; tests/conftest.py turns it on through ``RANDOMIZE_BN``) draws
+the batch-norm variables NON-trivially instead (gamma~U(.5,1.5), beta,mean~N(0,.1), var~U(.5,1.5)) so that folding
+errors would show in parity tests.  ``created`` lists the variables that did not come from ``state_dict``.
 
 Derived tensors (packed bf16 GEMM weights, folded batch-norm scale/bias) are cached per name.
 """
@@ -16,9 +20,14 @@ import math
 import torch
 
 
+RANDOMIZE_BN = False  # default of VariableStore(randomize_bn=None); the test suite sets it
+
+
 class VariableStore(object):
-    def __init__(self, device="cuda", seed=0, state_dict=None):
+    def __init__(self, device="cuda", seed=0, state_dict=None, randomize_bn=None):
         self.device = torch.device(device)
+        self.randomize_bn = RANDOMIZE_BN if randomize_bn is None else bool(randomize_bn)
+        self.created = []
         # state_dict: {TF variable name: tensor or numpy array} (e.g. utility.train_helper.load_state_dict of a TF
         # checkpoint); values become fp32 tensors on the device
         self.vars = {} if state_dict is None else {
@@ -60,6 +69,7 @@ class VariableStore(object):
         key = self.full(name)
         if key not in self.vars:
             self.vars[key] = init(shape).to(self.device)
+            self.created.append(key)
         v = self.vars[key]
         if tuple(v.shape) != tuple(shape):
             raise ValueError("variable %s has shape %s, expected %s" % (key, tuple(v.shape), tuple(shape)))
@@ -68,18 +78,23 @@ class VariableStore(object):
     def _normal(self, shape, std):
         return torch.randn(shape, generator=self._gen, dtype=torch.float32) * std
 
+    def _truncated_normal(self, shape, std):
+        """tf.truncated_normal: values beyond two standard deviations are redrawn."""
+        t = torch.empty(shape, dtype=torch.float32)
+        return torch.nn.init.trunc_normal_(t, mean=0.0, std=std, a=-2.0 * std, b=2.0 * std, generator=self._gen)
+
     def glorot_normal(self, shape):
         rf = 1
         for s in shape[:-2]:
             rf *= s
         fan_in, fan_out = shape[-2] * rf, shape[-1] * rf
-        return self._normal(shape, math.sqrt(2.0 / (fan_in + fan_out)))
+        return self._truncated_normal(shape, math.sqrt(2.0 / (fan_in + fan_out)))
 
     def variance_scaling(self, shape):
         rf = 1
         for s in shape[:-2]:
             rf *= s
-        return self._normal(shape, math.sqrt(1.0 / (shape[-2] * rf)))
+        return self._truncated_normal(shape, math.sqrt(1.0 / (shape[-2] * rf)))
 
     def zeros(self, shape):
         return torch.zeros(shape, dtype=torch.float32)
@@ -87,10 +102,16 @@ class VariableStore(object):
     def batch_norm(self, name, channels):
         """-> dict(gamma, beta, moving_mean, moving_variance) keys under ``name``."""
         with self.scope(name):
-            g = self.get("gamma", (channels,), lambda s: torch.rand(s, generator=self._gen) + 0.5)
-            b = self.get("beta", (channels,), lambda s: self._normal(s, 0.1))
-            m = self.get("moving_mean", (channels,), lambda s: self._normal(s, 0.1))
-            v = self.get("moving_variance", (channels,), lambda s: torch.rand(s, generator=self._gen) + 0.5)
+            if self.randomize_bn:
+                g = self.get("gamma", (channels,), lambda s: torch.rand(s, generator=self._gen) + 0.5)
+                b = self.get("beta", (channels,), lambda s: self._normal(s, 0.1))
+                m = self.get("moving_mean", (channels,), lambda s: self._normal(s, 0.1))
+                v = self.get("moving_variance", (channels,), lambda s: torch.rand(s, generator=self._gen) + 0.5)
+            else:  # tf.layers.batch_normalization defaults
+                g = self.get("gamma", (channels,), lambda s: torch.ones(s, dtype=torch.float32))
+                b = self.get("beta", (channels,), self.zeros)
+                m = self.get("moving_mean", (channels,), self.zeros)
+                v = self.get("moving_variance", (channels,), lambda s: torch.ones(s, dtype=torch.float32))
         return {"gamma": g, "beta": b, "mean": m, "var": v}
 
     def folded_bn(self, bn, eps):

@@ -162,6 +162,9 @@ def match_encode(boxes, gt, gt_labels, allowed_border, high_thres, low_thres, pr
     shared = boxes.dim() == 2
     A = boxes.shape[-2]
     dev = gt.device
+    if G == 0:  # a batch without ground-truth slots: everything is background (the reference's tf.argmax would fail)
+        return (torch.zeros((N, A), dtype=torch.int32, device=dev), torch.zeros((N, A, 4), dtype=torch.float32, device=dev),
+                torch.zeros((N, A), dtype=torch.float32, device=dev))
     labels = torch.empty((N, A), dtype=torch.int32, device=dev)
     targets = torch.empty((N, A, 4), dtype=torch.float32, device=dev)
     scores = torch.empty((N, A), dtype=torch.float32, device=dev)
@@ -179,6 +182,10 @@ def sample_fg_bg(labels, scores, bg_low, exp_fg, total, keys_fg, keys_bg, keys_u
     """labels [groups, n] int32 (scores [groups, n] or None) -> (indices [groups, total] int32, counts [groups, 3])."""
     groups, n = labels.shape
     dev = labels.device
+    if total > 4096:
+        raise ValueError("sample_fg_bg draws at most 4096 samples per group (%d asked): the RPN sampler runs over the "
+                         "flattened per-rank batch, batch * rpn_anchors_per_image <= 4096 (16 images at the reference's "
+                         "256); shard larger batches over more ranks" % total)
     out = torch.empty((groups, total), dtype=torch.int32, device=dev)
     counts = torch.empty((groups, 3), dtype=torch.int32, device=dev)
     ws = torch.empty((groups, 2 * n), dtype=torch.int32, device=dev)

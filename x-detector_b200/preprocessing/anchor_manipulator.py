@@ -160,6 +160,9 @@ class AnchorEncoder(object):
                     'roi_up': torch.rand((N, S), device=rois_all.device)}
         lab, tgt, sc = T.match_encode(rois_all, gb, gl, float(allowed_border), self._rpn_fg_thres,
                                       self._rpn_bg_high_thres)
+        # the reference appends only the valid ground-truth boxes (tf.boolean_mask, :345-347); the padded slots ride
+        # along here as zero boxes and are marked 'ignore' so that no threshold setting can sample them
+        lab[:, lab.shape[1] - gl.shape[1]:].masked_fill_(gl <= 0, -1)
         idx, _ = T.sample_fg_bg(lab, sc, float(self._rpn_bg_low_thres), int(round(S * fg_fraction)), S,
                                 keys['roi_fg'], keys['roi_bg'], keys['roi_up'])
         idx = idx.long()
