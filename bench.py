@@ -791,6 +791,13 @@ class LightHeadResnet50Train:
                           "discrete selections injected; it is a parity checker, not a timed arm"}))
 
 
+class LightHeadXceptionTrain(LightHeadResnet50Train):
+    """The reference's own training configuration (light_head_rfcn_train.py:289: XceptionBody), 8 images of 480x480 per
+    GPU."""
+    name = "Light-Head R-CNN Xception training step, batch=8 per GPU, 480x480 synthetic"
+    backbone = "xception"
+
+
 class LightHeadXception800(LightHeadResnet50):
     """BASELINE.json configs[2]: the reference's own backbone (XceptionBody), batch 32, 800x800."""
     name = "Light-Head R-CNN Xception inference, batch=32 per GPU, 800x800 synthetic"
@@ -805,6 +812,7 @@ class LightHeadXception480(LightHeadResnet50):
 
 WORKLOADS = {"lighthead_resnet50": LightHeadResnet50, "lighthead_xception_800": LightHeadXception800,
              "lighthead_xception_480": LightHeadXception480, "lighthead_resnet50_train": LightHeadResnet50Train,
+             "lighthead_xception_train": LightHeadXceptionTrain,
              "psroi_sweep_top": PsroiSweepTop}
 DEFAULT_WORKLOAD = "lighthead_resnet50"
 

@@ -303,6 +303,20 @@ int xdet_conv2d_f16x2(const void* d_in_pair, const xdet_conv_f16x2_desc* desc, v
 int xdet_split2_f16(const float* d_src, long long sn, long long sy, long long sx, long long sc, int N, int H, int W,
                     int C, void* d_dst, int cs, int Wp, int x_off, long long plane, int relu, void* stream);
 
+/* tf.layers.max_pooling2d(3, 2, 'SAME') on NHWC fp32 (C % 8 == 0) for the f16x2 precision: v = window max (+ residual);
+ * any of dst (fp32), dst_pair (f16x2 planes of v), dst2 = ReLU(v*scale2 + bias2) (fp32) and dst2_pair may be NULL.
+ * Replaces tf.layers.max_pooling2d at net/resnet_v2.py:326-328 and net/xception_body.py:272,302,322 together with the
+ * batch_norm_relu / split pass that follows it. */
+int xdet_maxpool3x3s2_f32x(const float* d_src, float* d_dst, void* d_dst_pair, float* d_dst2, void* d_dst2_pair,
+                           const float* d_scale2, const float* d_bias2, const float* d_residual, long long pair_plane,
+                           int N, int H, int W, int C, int Ho, int Wo, int pad_top, int pad_left, void* stream);
+
+/* Depthwise 3x3 'SAME' stride-1 convolution on NHWC fp32 (C % 8 == 0, dilation 1 or 2, optional ReLU on load) for the
+ * f16x2 precision: the depthwise half of tf.layers.separable_conv2d (net/xception_body.py:224-233).  d_dst (fp32)
+ * and / or d_dst_pair (the f16x2 planes the pointwise convolution reads) may be NULL. */
+int xdet_depthwise3x3_f32x(const float* d_src, const float* d_weights, float* d_dst, void* d_dst_pair, long long pair_plane,
+                           int N, int H, int W, int C, int dilation, int relu_in, void* stream);
+
 /* Input pipeline of the eval / test scripts.
  * Replaces: light_head_preprocess_for_eval / _for_test preprocessing/common_preprocessing.py:383-458 with
  *   resize = WARP_RESIZE (the scripts' default): convert_image_dtype(uint8 -> float32) * 2, tf_image_whitened

@@ -219,6 +219,32 @@ def test_elementwise_fp32_forms(xd):
         assert torch.allclose(dw, ref, atol=1e-5)
 
 
+def test_f16x2_elementwise_kernels_match_the_fp32_forms(xd):
+    """The vectorised fp32 depthwise / max-pool kernels of the f16x2 precision (window in registers, fused split planes)
+    against the plain fp32 kernels: same values bit for bit, planes == split2(values)."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    for shape, dil in (((2, 19, 23, 72), 1), ((1, 50, 50, 728), 1), ((2, 10, 12, 1536), 2), ((1, 5, 4, 8), 2)):
+        x = torch.randn(shape, generator=g, device="cuda")
+        w9 = torch.randn((9, shape[-1]), generator=g, device="cuda")
+        for relu_in in (False, True):
+            want = xd.depthwise3x3(x, w9, dilation=dil, relu_in=relu_in)  # default precision: the plain fp32 kernel
+            with xd.precision("f16x2"):
+                both = xd.depthwise3x3(x, w9, dilation=dil, relu_in=relu_in, forms="both")
+                only = xd.depthwise3x3(x, w9, dilation=dil, relu_in=relu_in)
+            assert torch.equal(both, want) and torch.equal(both._pair, xd.split2(want))
+            assert only._pair_only and torch.equal(only._pair, both._pair)
+    x = torch.randn((2, 37, 41, 64), generator=g, device="cuda")
+    res = torch.randn((2, 19, 21, 64), generator=g, device="cuda")
+    sc, bi = torch.rand(64, generator=g, device="cuda") + 0.5, torch.randn(64, generator=g, device="cuda")
+    want, want2 = xd.maxpool3x3s2_same(x, sc, bi, residual=res)
+    with xd.precision("f16x2"):
+        a, b = xd.maxpool3x3s2_same(x, sc, bi, residual=res)
+        n, p = xd.maxpool3x3s2_same(x, sc, bi, residual=res, forms="none", forms2="pair")
+    assert torch.equal(a, want) and torch.equal(b, want2)
+    assert torch.equal(a._pair, xd.split2(want)) and torch.equal(b._pair, xd.split2(want2))
+    assert p._pair_only and torch.equal(p._pair, b._pair) and tuple(n.shape) == tuple(want.shape)
+
+
 def _run(backbone, seed, precision="fp32x3"):
     from xdet_b200 import light_head_rfcn_eval as lh
     params = lh.make_params(train_image_size=160, rpn_pre_nms_top_n=600, rpn_post_nms_top_n=100,

@@ -78,6 +78,8 @@ def _declare(lib):
     lib.xdet_conv2d_f16x2.argtypes = [c_void_p, c_void_p, c_void_p]
     lib.xdet_split2_f16.argtypes = [c_void_p] + [c_ll] * 4 + [c_int] * 4 + [c_void_p, c_int, c_int, c_int, c_ll, c_int,
                                                                             c_void_p]
+    lib.xdet_maxpool3x3s2_f32x.argtypes = [c_void_p] * 8 + [c_ll] + [c_int] * 8 + [c_void_p]
+    lib.xdet_depthwise3x3_f32x.argtypes = [c_void_p] * 4 + [c_ll] + [c_int] * 6 + [c_void_p]
     lib.xdet_f32_post.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_int,
                                   c_void_p]
     lib.xdet_maxpool3x3s2_f32.argtypes = [c_void_p] * 6 + [c_int] * 8 + [c_void_p]

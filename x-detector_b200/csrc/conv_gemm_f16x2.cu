@@ -28,6 +28,7 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <cfloat>
 #include <mutex>
 
 #include "common.cuh"
@@ -426,6 +427,150 @@ __global__ void __launch_bounds__(256) split2_kernel(const float* __restrict__ s
   }
 }
 
+// tf.layers.max_pooling2d(3, 2, 'SAME') on NHWC fp32 (+ residual), 8 channels per thread (two float4 per tap):
+//   v = max over the window (+ residual);  dst = v (fp32, optional), dst_pair = split(v) (optional);
+//   w = ReLU(v*scale2 + bias2):  dst2 (fp32, optional), dst2_pair (optional).
+__global__ void __launch_bounds__(256) maxpool3x3s2_f32x_kernel(
+    const float* __restrict__ src, float* __restrict__ dst, __half* __restrict__ dst_pair, float* __restrict__ dst2,
+    __half* __restrict__ dst2_pair, const float* __restrict__ scale2, const float* __restrict__ bias2,
+    const float* __restrict__ residual, long long plane, int H, int W, int C, int Ho, int Wo, int pad_top, int pad_left,
+    long long total) {
+  const long long step = (long long)gridDim.x * blockDim.x;
+  const int c8 = C / 8;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
+    const int cb = (int)(e % c8) * 8;
+    const long long pix = e / c8;
+    const int xo = (int)(pix % Wo);
+    const int yo = (int)((pix / Wo) % Ho);
+    const long long n = pix / ((long long)Wo * Ho);
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -FLT_MAX;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int yi = yo * 2 + kh - pad_top;
+      if (yi < 0 || yi >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int xi = xo * 2 + kw - pad_left;
+        if (xi < 0 || xi >= W) continue;
+        const float4* p = reinterpret_cast<const float4*>(src + ((n * H + yi) * W + xi) * C + cb);
+        const float4 a = __ldg(p), b = __ldg(p + 1);
+        m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], a.z); m[3] = fmaxf(m[3], a.w);
+        m[4] = fmaxf(m[4], b.x); m[5] = fmaxf(m[5], b.y); m[6] = fmaxf(m[6], b.z); m[7] = fmaxf(m[7], b.w);
+      }
+    }
+    const long long o = pix * C + cb;
+    if (residual) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(residual + o)), b = __ldg(reinterpret_cast<const float4*>(residual + o) + 1);
+      m[0] = __fadd_rn(m[0], a.x); m[1] = __fadd_rn(m[1], a.y); m[2] = __fadd_rn(m[2], a.z); m[3] = __fadd_rn(m[3], a.w);
+      m[4] = __fadd_rn(m[4], b.x); m[5] = __fadd_rn(m[5], b.y); m[6] = __fadd_rn(m[6], b.z); m[7] = __fadd_rn(m[7], b.w);
+    }
+    auto put_pair = [&](__half* base, const float* v) {
+      __half hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split_f16x2(v[j], hi[j], lo[j]);
+      *reinterpret_cast<uint4*>(base + o) = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
+      *reinterpret_cast<uint4*>(base + plane + o) = make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7]));
+    };
+    if (dst) {
+      reinterpret_cast<float4*>(dst + o)[0] = make_float4(m[0], m[1], m[2], m[3]);
+      reinterpret_cast<float4*>(dst + o)[1] = make_float4(m[4], m[5], m[6], m[7]);
+    }
+    if (dst_pair) put_pair(dst_pair, m);
+    if (dst2 || dst2_pair) {
+      float w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = fmaxf(__fadd_rn(__fmul_rn(m[j], __ldg(scale2 + cb + j)), __ldg(bias2 + cb + j)), 0.f);
+      if (dst2) {
+        reinterpret_cast<float4*>(dst2 + o)[0] = make_float4(w[0], w[1], w[2], w[3]);
+        reinterpret_cast<float4*>(dst2 + o)[1] = make_float4(w[4], w[5], w[6], w[7]);
+      }
+      if (dst2_pair) put_pair(dst2_pair, w);
+    }
+  }
+}
+
+// Depthwise 3x3 'SAME' stride-1 convolution in fp32 (depth multiplier 1, dilation D), the depthwise half of
+// tf.layers.separable_conv2d (net/xception_body.py:224-233) for the f16x2 precision.  A thread owns 4 channels of one
+// column and walks a vertical strip of YS output rows with a rolling window of 2D+1 input rows x 3 columns in
+// registers: 3 float4 loads per output row instead of 9.  Taps are summed in (kh, kw) order with fmaf.  The result
+// goes out as fp32 and / or as the f16x2 planes the pointwise convolution reads (its only consumer in XceptionBody).
+template <int D>
+__global__ void __launch_bounds__(256) depthwise3x3_f32x_kernel(const float* __restrict__ src, const float* __restrict__ w9c,
+                                                                float* __restrict__ dst, __half* __restrict__ dst_pair,
+                                                                long long plane, int N, int H, int W, int C, int relu_in,
+                                                                int YS, long long total) {
+  constexpr int R = 2 * D + 1;
+  const int C4 = C / 4;
+  const int HY = (H + YS - 1) / YS;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(e % C4);
+    long long t = e / C4;
+    const int x = (int)(t % W);
+    t /= W;
+    const int ys = (int)(t % HY);
+    const int n = (int)(t / HY);
+    const int y0 = ys * YS, y1 = min(y0 + YS, H);
+    float4 wt[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wt[k] = __ldg(reinterpret_cast<const float4*>(w9c + (long long)k * C) + c4);
+    const float4* img = reinterpret_cast<const float4*>(src) + (long long)n * H * W * C4 + c4;
+    const bool okl = x - D >= 0, okr = x + D < W;
+    auto load_row = [&](int yi, float4 (&r)[3]) {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (yi < 0 || yi >= H) {
+        r[0] = r[1] = r[2] = z;
+        return;
+      }
+      const float4* rp = img + (long long)yi * W * C4;
+      r[0] = okl ? __ldg(rp + (long long)(x - D) * C4) : z;
+      r[1] = __ldg(rp + (long long)x * C4);
+      r[2] = okr ? __ldg(rp + (long long)(x + D) * C4) : z;
+      if (relu_in) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          r[i] = make_float4(fmaxf(r[i].x, 0.f), fmaxf(r[i].y, 0.f), fmaxf(r[i].z, 0.f), fmaxf(r[i].w, 0.f));
+      }
+    };
+    float4 win[R][3];  // input rows y-D .. y+D of the current output row y
+#pragma unroll
+    for (int i = 0; i < R - 1; ++i) load_row(y0 - D + i, win[i + 1]);  // slot i+1: shifted down at the top of the loop
+    for (int y = y0; y < y1; ++y) {
+#pragma unroll
+      for (int i = 0; i < R - 1; ++i) {
+        win[i][0] = win[i + 1][0];
+        win[i][1] = win[i + 1][1];
+        win[i][2] = win[i + 1][2];
+      }
+      load_row(y + D, win[R - 1]);
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float4 v = win[kh * D][kw], k = wt[kh * 3 + kw];
+          a.x = __fmaf_rn(v.x, k.x, a.x);
+          a.y = __fmaf_rn(v.y, k.y, a.y);
+          a.z = __fmaf_rn(v.z, k.z, a.z);
+          a.w = __fmaf_rn(v.w, k.w, a.w);
+        }
+      }
+      const long long o = (((long long)n * H + y) * W + x) * C + (long long)c4 * 4;
+      if (dst) *reinterpret_cast<float4*>(dst + o) = a;
+      if (dst_pair) {
+        __half h0, l0, h1, l1, h2, l2, h3, l3;
+        split_f16x2(a.x, h0, l0);
+        split_f16x2(a.y, h1, l1);
+        split_f16x2(a.z, h2, l2);
+        split_f16x2(a.w, h3, l3);
+        *reinterpret_cast<uint2*>(dst_pair + o) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
+        *reinterpret_cast<uint2*>(dst_pair + plane + o) = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
+      }
+    }
+  }
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   static std::once_flag once;
@@ -648,4 +793,45 @@ extern "C" int xdet_split2_f16(const float* d_src, long long sn, long long sy, l
                                                                    reinterpret_cast<__half*>(d_dst), cs, Wp, x_off, plane,
                                                                    relu, total);
   return after_launch("split2_kernel");
+}
+
+extern "C" int xdet_maxpool3x3s2_f32x(const float* d_src, float* d_dst, void* d_dst_pair, float* d_dst2, void* d_dst2_pair,
+                                      const float* d_scale2, const float* d_bias2, const float* d_residual,
+                                      long long pair_plane, int N, int H, int W, int C, int Ho, int Wo, int pad_top,
+                                      int pad_left, void* stream) {
+  if (N < 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 != 0) return fail(XDET_EINVAL, "maxpool_f32x: C must be a positive multiple of 8");
+  if ((d_dst2 || d_dst2_pair) && (!d_scale2 || !d_bias2)) return fail(XDET_EINVAL, "maxpool_f32x: second output needs scale2 and bias2");
+  if (!d_dst && !d_dst_pair && !d_dst2 && !d_dst2_pair) return fail(XDET_EINVAL, "maxpool_f32x: no output");
+  if ((d_dst_pair || d_dst2_pair) && pair_plane % 8 != 0) return fail(XDET_EINVAL, "maxpool_f32x: pair planes must be 16-byte aligned");
+  const long long total = (long long)N * Ho * Wo * (C / 8);
+  if (total == 0) return XDET_OK;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+  maxpool3x3s2_f32x_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      d_src, d_dst, reinterpret_cast<__half*>(d_dst_pair), d_dst2, reinterpret_cast<__half*>(d_dst2_pair), d_scale2,
+      d_bias2, d_residual, pair_plane, H, W, C, Ho, Wo, pad_top, pad_left, total);
+  return after_launch("maxpool3x3s2_f32x_kernel");
+}
+
+extern "C" int xdet_depthwise3x3_f32x(const float* d_src, const float* d_weights, float* d_dst, void* d_dst_pair,
+                                      long long pair_plane, int N, int H, int W, int C, int dilation, int relu_in,
+                                      void* stream) {
+  if (N < 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 != 0) return fail(XDET_EINVAL, "depthwise_f32x: C must be a positive multiple of 8");
+  if (dilation != 1 && dilation != 2) return fail(XDET_EINVAL, "depthwise_f32x: dilation must be 1 or 2");
+  if (!d_dst && !d_dst_pair) return fail(XDET_EINVAL, "depthwise_f32x: no output");
+  if (d_dst_pair && pair_plane % 8 != 0) return fail(XDET_EINVAL, "depthwise_f32x: pair planes must be 16-byte aligned");
+  if (N == 0) return XDET_OK;
+  // strip height: tall strips amortise the window fill, but keep >= ~8 CTAs per SM in flight
+  int YS = 16;
+  while (YS > 2 && (long long)N * ((H + YS - 1) / YS) * W * (C / 4) < 8ll * kNumSMs * 256) YS /= 2;
+  const long long total = (long long)N * ((H + YS - 1) / YS) * W * (C / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > (1ll << 30)) blocks = 1ll << 30;
+  cudaStream_t st = (cudaStream_t)stream;
+  __half* pp = reinterpret_cast<__half*>(d_dst_pair);
+  if (dilation == 1)
+    depthwise3x3_f32x_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(d_src, d_weights, d_dst, pp, pair_plane, N, H, W, C, relu_in, YS, total);
+  else
+    depthwise3x3_f32x_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(d_src, d_weights, d_dst, pp, pair_plane, N, H, W, C, relu_in, YS, total);
+  return after_launch("depthwise3x3_f32x_kernel");
 }

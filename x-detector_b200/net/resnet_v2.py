@@ -193,7 +193,7 @@ def imagenet_resnet_v2(resnet_size, num_classes, data_format=None, store=None):
     return imagenet_resnet_v2_generator(bottleneck_block, model_params[resnet_size], num_classes, data_format, store)
 
 
-def stem(image_nchw_f32, store, fuse_next=False):
+def stem(image_nchw_f32, store, fuse_next=False, pooled_unused=False):
     """7x7/s2 initial conv with fixed padding + 3x3/s2 SAME max-pool (net/resnet_v2.py:320-328) on the
     fp32 NCHW image the input pipeline delivers; returns NHWC bf16 (with ``fuse_next`` also relu(bn(.)) of the
     first block's batch-norm, computed by the pooling kernel)."""
@@ -206,7 +206,8 @@ def stem(image_nchw_f32, store, fuse_next=False):
     if not fuse_next:
         return ops.maxpool3x3s2_same(y)
     s1, b1 = store.folded_bn(_peek_next_bn(store, 64, ahead=0), _BATCH_NORM_EPSILON)
-    return ops.maxpool3x3s2_same(y, s1, b1)
+    # ("f16x2" precision: the first block has a projection shortcut, so only relu(bn(pooled)) is read, by convolutions)
+    return ops.maxpool3x3s2_same(y, s1, b1, forms="none" if pooled_unused else "both", forms2="pair")
 
 
 def lighthead_resnet50_body(image_nchw_f32, is_training, store, layers=(3, 4, 6, 3), after_rpn_feat=None):
@@ -216,7 +217,7 @@ def lighthead_resnet50_body(image_nchw_f32, is_training, store, layers=(3, 4, 6,
     input; raw sums nobody else reads are never stored.  ``after_rpn_feat(rpn_feature)`` is called as soon as
     the RPN feature exists (the model_fn launches the RPN head and forks the proposal stream there)."""
     df = "channels_last"
-    x, pre = stem(image_nchw_f32, store, fuse_next=True)
+    x, pre = stem(image_nchw_f32, store, fuse_next=True, pooled_unused=True)
     # layers 2 and 3 start with a projection shortcut that reads relu(bn(x)): the raw x of layers 1 and 2 is unused
     _, pre = block_layer(x, 64, bottleneck_block, layers[0], 1, is_training, "block_layer1", df, store, preact=pre,
                          fuse_next=True, sum_unused=True)

@@ -283,6 +283,41 @@ def _autotune(x, d, reps=10):
     return best
 
 
+def _autotune_f16x2(planes, d, reps=10):
+    """Tile width of the f16x2 kernel for one layer shape: the heuristic's choice against N tiles of 32 / 64 / 128,
+    each timed as ``reps`` launches replayed from a CUDA graph (results do not depend on the choice)."""
+    lib = _native.lib()
+    best, best_t = 0, None
+    cur = torch.cuda.current_stream()
+    side = torch.cuda.Stream(device=planes.device)
+    for bn in (0, 128, 64, 32):
+        d.block_n = bn
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            if lib.xdet_conv2d_f16x2(planes.data_ptr(), ctypes.byref(d), side.cuda_stream) != 0:
+                continue
+            side.synchronize()
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    for _ in range(reps):
+                        lib.xdet_conv2d_f16x2(planes.data_ptr(), ctypes.byref(d), torch.cuda.current_stream().cuda_stream)
+                g.replay()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(side)
+                g.replay()
+                e1.record(side)
+                side.synchronize()
+                t = e0.elapsed_time(e1)
+            except RuntimeError:
+                continue
+        if best_t is None or t < best_t * 0.985:  # prefer earlier candidates (the heuristic) on ties
+            best, best_t = bn, t
+    cur.wait_stream(side)
+    d.block_n = 0
+    return best
+
+
 class cta_limit(object):
     def __init__(self, n):
         self.n = n
@@ -554,6 +589,13 @@ def _conv2d_f16x2(x, w, cout, kh, kw, *, dilation, padding, scale, bias, relu, r
                       0 if some_pair is None else some_pair.stride(0), pcs, _ptr(f32_out2), _ptr(scale2), _ptr(bias2),
                       _ptr(pair2), block_n, F16X2_CHUNK_KB, MAX_CTAS)
     with torch.cuda.device(dev):
+        if AUTOTUNE and block_n == 0:
+            key = ("f16x2", N, H, W, cin, cs, cout, kh, kw, dh, dw_, pt, pl, Ho, Wo, sh, sw, fold_w is not None,
+                   residual is not None, f32_out is not None, pair is not None, f32_out2 is not None, pair2 is not None,
+                   nhwc, MAX_CTAS > 0)
+            if key not in _tune_cache and not torch.cuda.is_current_stream_capturing():
+                _tune_cache[key] = _autotune_f16x2(planes, d)
+            d.block_n = _tune_cache.get(key, 0)
         if PROFILE is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()

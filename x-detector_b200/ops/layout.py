@@ -29,12 +29,39 @@ def im2col(x, kh, kw, stride, pad_top, pad_left, Ho, Wo, *, nchw_f32=False, cin=
     return out
 
 
-def maxpool3x3s2_same(x, scale2=None, bias2=None, residual=None):
+def maxpool3x3s2_same(x, scale2=None, bias2=None, residual=None, forms="both", forms2="both"):
     """tf.layers.max_pooling2d(3, 2, 'SAME') on NHWC bf16 (+ ``residual`` added to the pooled value); optionally
-    also returns relu(y*scale2+bias2)."""
+    also returns relu(y*scale2+bias2).  ``forms`` / ``forms2`` ("f16x2" precision only, see ops.conv2d_nhwc): which
+    forms of the two results are stored -- "both", "f32", "pair", or "none" (the pooled value itself is not needed)."""
     N, H, W, C = x.shape
     Ho, Wo = -(-H // 2), -(-W // 2)
     pt, pl = same_pad(H, 3, 1, 2), same_pad(W, 3, 1, 2)
+    from . import conv as _conv
+    if x.dtype == torch.float32 and _conv.PRECISION == "f16x2" and C % 8 == 0:
+        assert x.is_contiguous() and not getattr(x, "_pair_only", False)
+        dev = x.device
+        shape = (N, Ho, Wo, C)
+        want2 = scale2 is not None
+        out = torch.empty(shape, dtype=torch.float32, device=dev) if forms in ("both", "f32") else None
+        pair = torch.empty((2,) + shape, dtype=torch.float16, device=dev) if forms in ("both", "pair") else None
+        out2 = torch.empty(shape, dtype=torch.float32, device=dev) if want2 and forms2 in ("both", "f32") else None
+        pair2 = torch.empty((2,) + shape, dtype=torch.float16, device=dev) if want2 and forms2 in ("both", "pair") else None
+        if residual is not None:
+            assert residual.shape == shape and residual.dtype == torch.float32 and residual.is_contiguous()
+        some = pair if pair is not None else pair2
+        p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        rc = _native.lib().xdet_maxpool3x3s2_f32x(x.data_ptr(), p(out), p(pair), p(out2), p(pair2), p(scale2), p(bias2),
+                                                  p(residual), 0 if some is None else some.stride(0), N, H, W, C, Ho, Wo,
+                                                  pt, pl, _st())
+        _native.check(rc)
+
+        def wrap(f32, pr):
+            if f32 is None:
+                return _conv.pair_only(shape, pr) if pr is not None else torch.empty((1,), device=dev).expand(shape)
+            if pr is not None:
+                f32._pair = pr
+            return f32
+        return (wrap(out, pair), wrap(out2, pair2)) if want2 else wrap(out, pair)
     if x.dtype == torch.float32:  # parity mode (csrc/parity_ops.cu)
         assert x.is_contiguous()
         out = torch.empty((N, Ho, Wo, C), dtype=torch.float32, device=x.device)
@@ -59,9 +86,27 @@ def maxpool3x3s2_same(x, scale2=None, bias2=None, residual=None):
     return (out, out2) if out2 is not None else out
 
 
-def depthwise3x3(x, w9c, dilation=1, relu_in=False):
-    """Depthwise 3x3 SAME conv (depth multiplier 1) on NHWC bf16; ``w9c`` = [9, C] fp32 taps (kh-major)."""
+def depthwise3x3(x, w9c, dilation=1, relu_in=False, forms="pair"):
+    """Depthwise 3x3 SAME conv (depth multiplier 1) on NHWC bf16; ``w9c`` = [9, C] fp32 taps (kh-major).
+    ``forms`` ("f16x2" precision only): the result's forms -- its reader in XceptionBody is the pointwise convolution,
+    so by default only the split planes are written."""
     N, H, W, C = x.shape
+    from . import conv as _conv
+    if x.dtype == torch.float32 and _conv.PRECISION == "f16x2" and C % 8 == 0:
+        assert x.is_contiguous() and not getattr(x, "_pair_only", False)
+        assert w9c.dtype == torch.float32 and w9c.shape == (9, C)
+        out = torch.empty_like(x) if forms in ("both", "f32") else None
+        pair = torch.empty((2, N, H, W, C), dtype=torch.float16, device=x.device) if forms in ("both", "pair") else None
+        rc = _native.lib().xdet_depthwise3x3_f32x(x.data_ptr(), w9c.data_ptr(), None if out is None else out.data_ptr(),
+                                                  None if pair is None else pair.data_ptr(),
+                                                  0 if pair is None else pair.stride(0), N, H, W, C, dilation,
+                                                  1 if relu_in else 0, _st())
+        _native.check(rc)
+        if out is None:
+            return _conv.pair_only((N, H, W, C), pair)
+        if pair is not None:
+            out._pair = pair
+        return out
     if x.dtype == torch.float32:  # parity mode (csrc/parity_ops.cu)
         assert x.is_contiguous() and w9c.dtype == torch.float32 and w9c.shape == (9, C)
         out = torch.empty_like(x)
