@@ -151,6 +151,11 @@ typedef struct {
   int fold_w, in_wp; /* as in xdet_conv_desc (the stem); dw is then [Cout][KH][64] with element kw*in_cs + ci */
 } xdet_wgrad_desc;
 int xdet_conv2d_wgrad_bf16(const void* d_x, const void* d_dy, const xdet_wgrad_desc* desc, void* stream);
+/* The same weight gradient in the fp32-accurate "f16x2" precision (the training parity mode): x and dy are f16x2 planes
+ * ([2][N,H,W,cs] fp16, `*_plane` elements apart, see xdet_conv2d_f16x2); dw += (sum dy*x) * out_scale, where out_scale
+ * undoes a power-of-two scaling the caller applied to dy (loss scaling keeps gradients inside fp16's range). */
+int xdet_conv2d_wgrad_f16x2(const void* d_x_pair, long long x_plane, const void* d_dy_pair, long long dy_plane,
+                            const xdet_wgrad_desc* desc, float out_scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Bandwidth helpers around the tensor-core convolutions (bf16 NHWC tensors).
@@ -400,6 +405,19 @@ int xdet_bn_relu_bwd_bf16(const void* d_dy, const void* d_x, const float* d_scal
                           const void* d_add_in, float* d_sums, void* d_dx, void* stream);
 /* dx = dy where y > 0 else 0 (gradient of a ReLU fused into a convolution epilogue); bf16, n elements (n % 8 == 0) */
 int xdet_relu_bwd_bf16(const void* d_dy, const void* d_y, void* d_dx, long long n, void* stream);
+/* fp32 forms of the kernels above for the fp32-ACCURATE training mode ("f16x2" precision; csrc/train_ops_f32.cu):
+ * deterministic (one owner per channel, fp64 accumulation, no atomics).  xdet_col_stats_f32 overwrites d_sums unless
+ * accumulate != 0; xdet_bn_relu_bwd_f32 overwrites d_sums ([0,C) = sum g, [C,2C) = sum g*xhat). */
+int xdet_col_stats_f32(const float* d_x, long long rows, int C, int cs, int with_squares, int accumulate, float* d_sums,
+                       void* stream);
+int xdet_bn_relu_bwd_f32(const float* d_dy, const float* d_x, const float* d_scale, const float* d_shift,
+                         const float* d_mean, const float* d_invstd, long long rows, int C, int relu,
+                         const float* d_add_in, float* d_sums, float* d_dx, void* stream);
+int xdet_relu_bwd_f32(const float* d_dy, const float* d_y, float* d_dx, long long n, void* stream);
+int xdet_maxpool3x3s2_argmax_f32(const float* d_src, float* d_dst, unsigned char* d_argmax, int N, int H, int W, int C,
+                                 int Ho, int Wo, int pad_top, int pad_left, void* stream);
+int xdet_maxpool3x3s2_bwd_f32(const unsigned char* d_argmax, const float* d_dy, float* d_dx, int N, int H, int W, int C,
+                              int Ho, int Wo, int pad_top, int pad_left, void* stream);
 /* Weight gradient of the depthwise 3x3 'SAME' stride-1 convolution (depth multiplier 1, dilation 1 or 2) -- the
  * depthwise half of tf.layers.separable_conv2d in XceptionBody (net/xception_body.py:224-233), training mode:
  *   dw[kh*3+kw, c] += sum_{n,y,x} act(x[n, y+(kh-1)*dil, x+(kw-1)*dil, c]) * dy[n,y,x,c],  act = ReLU if relu_in.

@@ -25,12 +25,13 @@ class _PsRoi(torch.autograd.Function):
     def forward(ctx, thin, yxhw):
         pooled, index = psroi.psroi_align_fwd(thin.detach().numpy(), yxhw, 7, 7, "max")
         ctx.shape, ctx.yxhw, ctx.index = tuple(thin.shape), yxhw, index
-        return torch.from_numpy(pooled)
+        return torch.from_numpy(pooled).to(thin.dtype)
 
     @staticmethod
     def backward(ctx, g):
-        d = psroi.psroi_align_bwd(ctx.shape, ctx.yxhw, np.ascontiguousarray(g.numpy()), ctx.index, 7, 7, "max")
-        return torch.from_numpy(d), None
+        d = psroi.psroi_align_bwd(ctx.shape, ctx.yxhw, np.ascontiguousarray(g.numpy(), dtype=np.float32), ctx.index, 7, 7,
+                                  "max")
+        return torch.from_numpy(d).to(g.dtype), None
 
 
 def smooth_l1(x):  # modified_smooth_l1, sigma = 1 (:257-275)
@@ -38,8 +39,10 @@ def smooth_l1(x):  # modified_smooth_l1, sigma = 1 (:257-275)
     return torch.where(ax < 1.0, 0.5 * x * x, ax - 0.5)
 
 
-def train_step(images, gt_boxes, gt_labels, sd, params, anchors, inject):
-    """-> (losses dict, grads {variable name: d total_loss_without_L2 / d variable}, intermediates)."""
+def train_step(images, gt_boxes, gt_labels, sd, params, anchors, inject, dtype=torch.float32):
+    """-> (losses dict, grads {variable name: d total_loss_without_L2 / d variable}, intermediates).
+    ``dtype=torch.float64``: the same graph in double precision (PsRoIAlign stays the fp32 C oracle, its output cast up)
+    -- the arbiter that tells whose fp32 rounding a gradient difference is."""
     y, x, h, w = anchors
     fm, A = y.shape[0], h.shape[0]
     cy = np.broadcast_to(y[:, :, None], (fm, fm, A)).reshape(-1).astype(np.float32)
@@ -54,8 +57,9 @@ def train_step(images, gt_boxes, gt_labels, sd, params, anchors, inject):
     nm.leaves = {}
     nm.push(params["model_scope"])
     onet.BN_TRAINING = True
+    prev_dtype, onet.DTYPE = onet.DTYPE, dtype
     try:
-        xin = torch.as_tensor(images).float()
+        xin = torch.as_tensor(images).to(dtype)
         if params.get("backbone", "resnet50") == "xception":  # the reference's own backbone (net/xception_body.py:236-379)
             rpn_feat, backbone = onet.xception_body(xin, nm)
         else:
@@ -108,6 +112,7 @@ def train_step(images, gt_boxes, gt_labels, sd, params, anchors, inject):
         total.backward()
     finally:
         onet.BN_TRAINING = False
+        onet.DTYPE = prev_dtype
     grads = {k_: (v.grad if v.grad is not None else torch.zeros_like(v)) for k_, v in nm.leaves.items()}
     return ({"rpn_cross_entropy_loss": float(rpn_ce.detach()), "rpn_location_loss": float(rpn_loc.detach()),
              "head_loss": float(head.detach())}, grads,

@@ -57,6 +57,8 @@ def _declare(lib):
     lib.xdet_psroi_align_bwd_host.argtypes = [c_void_p] * 4 + [c_int] * 8
     lib.xdet_conv2d_bf16.argtypes = [c_void_p, c_void_p, c_void_p]
     lib.xdet_conv2d_wgrad_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.xdet_conv2d_wgrad_f16x2.argtypes = [c_void_p, ctypes.c_longlong, c_void_p, ctypes.c_longlong, c_void_p, ctypes.c_float,
+                                            c_void_p]
     c_ll, c_float, c_size_t = ctypes.c_longlong, ctypes.c_float, ctypes.c_size_t
     lib.xdet_im2col_bf16.argtypes = [c_void_p, c_int, c_void_p] + [c_int] * 13 + [c_void_p]
     lib.xdet_maxpool3x3s2_bf16.argtypes = [c_void_p] * 5 + [c_int] * 8 + [c_void_p]
@@ -100,6 +102,11 @@ def _declare_train(lib):
     lib.xdet_bn_finalize.argtypes = [c_void_p] * 3 + [c_ll, c_int, c_float, c_float] + [c_void_p] * 7
     lib.xdet_bn_relu_bwd_bf16.argtypes = [c_void_p] * 6 + [c_ll, c_int, c_int] + [c_void_p] * 4
     lib.xdet_depthwise3x3_wgrad_bf16.argtypes = [c_void_p] * 3 + [c_int] * 6 + [c_void_p]
+    lib.xdet_col_stats_f32.argtypes = [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
+    lib.xdet_bn_relu_bwd_f32.argtypes = [c_void_p] * 6 + [c_ll, c_int, c_int] + [c_void_p] * 4
+    lib.xdet_relu_bwd_f32.argtypes = [c_void_p, c_void_p, c_void_p, c_ll, c_void_p]
+    lib.xdet_maxpool3x3s2_argmax_f32.argtypes = [c_void_p] * 3 + [c_int] * 8 + [c_void_p]
+    lib.xdet_maxpool3x3s2_bwd_f32.argtypes = [c_void_p] * 3 + [c_int] * 8 + [c_void_p]
     lib.xdet_relu_bwd_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_ll, c_void_p]
     lib.xdet_maxpool3x3s2_bwd_bf16.argtypes = [c_void_p] * 3 + [c_int] * 8 + [c_void_p]
     lib.xdet_nchw_f32_to_nhwc_bf16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]

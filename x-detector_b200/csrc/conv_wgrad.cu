@@ -16,6 +16,10 @@
 // Work item = (tap, Cout tile, Cin tile, pixel split); persistent CTAs; the fp32 accumulator leaves TMEM through
 // tcgen05.ld and is added to dW with red.global.add.f32 (splits of the same tile meet there; the caller
 // zero-fills dW).  Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue.
+//
+// "f16x2" precision (xdet_conv2d_wgrad_f16x2, the fp32-accurate training mode): both operands arrive as two fp16
+// planes (hi, lo*2^11, csrc/conv_gemm_f16x2.cu); a 16-pixel step is three products into two accumulators
+// (acc0 += dYh*Xh, acc1 += dYh*Xl + dYl*Xh) and the epilogue adds  (acc0 + acc1*2^-11) * out_scale  to dW.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
@@ -42,6 +46,8 @@ struct WgradArgs {
   int splits, items, stages, tmem_cols, overwrite;
   float* dw;
   long long ld_dw;  // taps * cin_pad
+  int pair;         // f16x2 operands: every box is loaded twice (hi plane, lo plane)
+  float out_scale;  // pair mode: factor applied to the result (undoes a power-of-two scaling of dY)
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -56,11 +62,12 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr, 
 
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                  const __grid_constant__ CUtensorMap map_dy_lo, const __grid_constant__ CUtensorMap map_x_lo,
                   const WgradArgs p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t a_bytes = (uint32_t)p.a_boxes * kBoxBytes, b_bytes = (uint32_t)p.b_boxes * kBoxBytes;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t stage_bytes = (a_bytes + b_bytes) * (p.pair ? 2u : 1u);  // pair: [A_hi | B_hi | A_lo | B_lo]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + 8;
   uint64_t* tmem_full_bar = empty_bar + 8;
@@ -71,6 +78,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&map_dy);
     ptx::prefetch_tmap(&map_x);
+    if (p.pair) {
+      ptx::prefetch_tmap(&map_dy_lo);
+      ptx::prefetch_tmap(&map_x_lo);
+    }
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -124,6 +135,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
           const int xx = x0 * p.mul_x + kw * p.dil_w - p.pad_left, yy = y0 * p.mul_y + kh * p.dil_h - p.pad_top;
           for (int b = 0; b < p.b_boxes; ++b)
             ptx::tma_load_4d(sb + (size_t)b * kBoxBytes, &map_x, &full_bar[stage], ci0 + 64 * b, xx, yy, img);
+          if (p.pair) {
+            unsigned char* sal = sb + b_bytes;
+            unsigned char* sbl = sal + a_bytes;
+            for (int a = 0; a < p.a_boxes; ++a)
+              ptx::tma_load_4d(sal + (size_t)a * kBoxBytes, &map_dy_lo, &full_bar[stage], co0 + 64 * a, x0, y0, img);
+            for (int b = 0; b < p.b_boxes; ++b)
+              ptx::tma_load_4d(sbl + (size_t)b * kBoxBytes, &map_x_lo, &full_bar[stage], ci0 + 64 * b, xx, yy, img);
+          }
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -134,7 +153,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
     __syncwarp();
   } else if (warp == 1) {
     // instruction descriptor: D = f32, A = B = bf16, BOTH MN-major (bits 15, 16), N >> 3 at 17, M >> 4 at 24
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+    // (pair mode: fp16 operands, formats 0)
+    const uint32_t fmt = p.pair ? 0u : ((1u << 7) | (1u << 10));
+    const uint32_t idesc = (1u << 4) | fmt | (1u << 15) | (1u << 16) |
                            (static_cast<uint32_t>(p.BN >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0, aphase = 0;
@@ -153,7 +174,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
           for (int k = 0; k < kPix / 16; ++k) {  // 16 pixels = two 8-row groups = 2048 B further down the tile
             const uint64_t da = make_smem_desc_mn_sw128(sa + k * 2048, kBoxBytes);
             const uint64_t db = make_smem_desc_mn_sw128(sb + k * 2048, kBoxBytes);
-            ptx::mma_bf16_ss(tmem_base, da, db, idesc, (pt > pt0 || k > 0) ? 1u : 0u);
+            const uint32_t acc = (pt > pt0 || k > 0) ? 1u : 0u;
+            ptx::mma_bf16_ss(tmem_base, da, db, idesc, acc);
+            if (p.pair) {
+              const uint32_t sal = sb + b_bytes, sbl = sal + a_bytes;
+              const uint64_t dal = make_smem_desc_mn_sw128(sal + k * 2048, kBoxBytes);
+              const uint64_t dbl = make_smem_desc_mn_sw128(sbl + k * 2048, kBoxBytes);
+              ptx::mma_bf16_ss(tmem_base + (uint32_t)p.BN, da, dbl, idesc, acc);
+              ptx::mma_bf16_ss(tmem_base + (uint32_t)p.BN, dal, db, idesc, 1u);
+            }
           }
           ptx::mma_commit(&empty_bar[stage]);
           if (pt == pt1 - 1) ptx::mma_commit(tmem_full_bar);
@@ -183,6 +212,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
       for (int c0 = 0; c0 < ncols; c0 += 32) {
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
+        if (p.pair) {
+          uint32_t r1[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(p.BN + c0), r1);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            r[j] = __float_as_uint(__fmul_rn(__fmaf_rn(__uint_as_float(r1[j]), 1.f / 2048.f, __uint_as_float(r[j])), p.out_scale));
+        }
         ptx::tmem_ld_wait();
         if (co < p.Cout) {  // ncols is a multiple of 64: whole 16-byte groups
           float4* dst = reinterpret_cast<float4*>(row + c0);
@@ -239,7 +276,8 @@ int wg_encode(CUtensorMap* map, const void* base, const cuuint64_t* dims, const 
 
 using namespace xdet;
 
-extern "C" int xdet_conv2d_wgrad_bf16(const void* d_x, const void* d_dy, const xdet_wgrad_desc* d, void* stream) {
+static int launch_wgrad(const void* d_x, const void* d_dy, const xdet_wgrad_desc* d, void* stream, bool pair,
+                        long long x_plane, long long dy_plane, float out_scale) {
   if (!d || !d_x || !d_dy || !d->dw) return fail(XDET_EINVAL, "wgrad: null argument");
   if (d->N <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0 || d->Cout <= 0 || d->KH <= 0 || d->KW <= 0 || d->Hout <= 0 ||
       d->Wout <= 0)
@@ -284,7 +322,9 @@ extern "C" int xdet_conv2d_wgrad_bf16(const void* d_x, const void* d_dy, const x
   a.Cout = d->Cout;
   a.cin_pad = fold ? 64 : (d->Cin + 63) / 64 * 64;
   a.co_tiles = (d->Cout + 127) / 128;
-  a.BN = a.cin_pad >= 256 ? 256 : (a.cin_pad >= 128 ? 128 : 64);
+  a.BN = pair ? 64 : (a.cin_pad >= 256 ? 256 : (a.cin_pad >= 128 ? 128 : 64));  // pair: twice the boxes per stage
+  a.pair = pair ? 1 : 0;
+  a.out_scale = out_scale;
   a.ci_tiles = (a.cin_pad + a.BN - 1) / a.BN;
   a.a_boxes = 2;
   a.b_boxes = a.BN / 64;
@@ -298,43 +338,61 @@ extern "C" int xdet_conv2d_wgrad_bf16(const void* d_x, const void* d_dy, const x
   a.overwrite = 0;  // dw is accumulated into (a caller-zeroed buffer or a partial sum)
   a.splits = splits;
   a.items = units * splits;
-  const size_t stage_bytes = (size_t)(a.a_boxes + a.b_boxes) * kBoxBytes;
+  const size_t stage_bytes = (size_t)(a.a_boxes + a.b_boxes) * kBoxBytes * (pair ? 2 : 1);
   int stages = (int)((227 * 1024 - 1024 - 256) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) return fail(XDET_EINVAL, "wgrad: tile does not fit shared memory");
   a.stages = stages;
-  a.tmem_cols = a.BN < 32 ? 32 : a.BN;  // 64 / 128 / 256: powers of two
+  a.tmem_cols = pair ? 2 * a.BN : (a.BN < 32 ? 32 : a.BN);  // powers of two; pair: acc0 | acc1
   a.dw = d->dw;
   a.ld_dw = (long long)a.taps * a.cin_pad;
 
-  CUtensorMap map_dy, map_x;
-  {
-    const cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)Wout, (cuuint64_t)Hout, (cuuint64_t)N};
-    const cuuint64_t strides[3] = {(cuuint64_t)d->dy_cs * 2, (cuuint64_t)d->dy_cs * 2 * Wout,
-                                   (cuuint64_t)d->dy_cs * 2 * Wout * Hout};
-    const cuuint32_t box[4] = {64, (cuuint32_t)a.BW, (cuuint32_t)a.BH, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    XDET_TRY(wg_encode(&map_dy, d_dy, dims, strides, box, estr));
+  CUtensorMap map_dy[2], map_x[2];
+  for (int pl = 0; pl < (pair ? 2 : 1); ++pl) {
+    const unsigned char* dyb = reinterpret_cast<const unsigned char*>(d_dy) + (size_t)pl * dy_plane * 2;
+    const unsigned char* xb = reinterpret_cast<const unsigned char*>(d_x) + (size_t)pl * x_plane * 2;
+    {
+      const cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)Wout, (cuuint64_t)Hout, (cuuint64_t)N};
+      const cuuint64_t strides[3] = {(cuuint64_t)d->dy_cs * 2, (cuuint64_t)d->dy_cs * 2 * Wout,
+                                     (cuuint64_t)d->dy_cs * 2 * Wout * Hout};
+      const cuuint32_t box[4] = {64, (cuuint32_t)a.BW, (cuuint32_t)a.BH, 1};
+      const cuuint32_t estr[4] = {1, 1, 1, 1};
+      XDET_TRY(wg_encode(&map_dy[pl], dyb, dims, strides, box, estr));
+    }
+    if (fold) {
+      const cuuint64_t dims[4] = {64, (cuuint64_t)Wout, (cuuint64_t)H, (cuuint64_t)N};
+      const cuuint64_t strides[3] = {(cuuint64_t)sw * d->in_cs * 2, (cuuint64_t)d->in_wp * d->in_cs * 2,
+                                     (cuuint64_t)d->in_wp * d->in_cs * 2 * H};
+      const cuuint32_t box[4] = {64, (cuuint32_t)a.BW, (cuuint32_t)(a.BH * sh), 1};
+      const cuuint32_t estr[4] = {1, 1, (cuuint32_t)sh, 1};
+      XDET_TRY(wg_encode(&map_x[pl], xb, dims, strides, box, estr));
+    } else {
+      const cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+      const cuuint64_t strides[3] = {(cuuint64_t)d->in_cs * 2, (cuuint64_t)d->in_cs * 2 * W,
+                                     (cuuint64_t)d->in_cs * 2 * W * H};
+      const cuuint32_t box[4] = {64, (cuuint32_t)(a.BW * sw), (cuuint32_t)(a.BH * sh), 1};
+      const cuuint32_t estr[4] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1};
+      XDET_TRY(wg_encode(&map_x[pl], xb, dims, strides, box, estr));
+    }
   }
-  if (fold) {
-    const cuuint64_t dims[4] = {64, (cuuint64_t)Wout, (cuuint64_t)H, (cuuint64_t)N};
-    const cuuint64_t strides[3] = {(cuuint64_t)sw * d->in_cs * 2, (cuuint64_t)d->in_wp * d->in_cs * 2,
-                                   (cuuint64_t)d->in_wp * d->in_cs * 2 * H};
-    const cuuint32_t box[4] = {64, (cuuint32_t)a.BW, (cuuint32_t)(a.BH * sh), 1};
-    const cuuint32_t estr[4] = {1, 1, (cuuint32_t)sh, 1};
-    XDET_TRY(wg_encode(&map_x, d_x, dims, strides, box, estr));
-  } else {
-    const cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    const cuuint64_t strides[3] = {(cuuint64_t)d->in_cs * 2, (cuuint64_t)d->in_cs * 2 * W,
-                                   (cuuint64_t)d->in_cs * 2 * W * H};
-    const cuuint32_t box[4] = {64, (cuuint32_t)(a.BW * sw), (cuuint32_t)(a.BH * sh), 1};
-    const cuuint32_t estr[4] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1};
-    XDET_TRY(wg_encode(&map_x, d_x, dims, strides, box, estr));
+  if (!pair) {
+    map_dy[1] = map_dy[0];
+    map_x[1] = map_x[0];
   }
   const size_t smem = (size_t)stages * stage_bytes + 256 + 1024;
   XDET_TRY(check_cuda(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
                       "cudaFuncSetAttribute(conv_wgrad)"));
   const int grid = a.items < kNumSMs ? a.items : kNumSMs;
-  conv_wgrad_kernel<<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(map_dy, map_x, a);
+  conv_wgrad_kernel<<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(map_dy[0], map_x[0], map_dy[1], map_x[1], a);
   return after_launch("conv_wgrad_kernel");
+}
+
+extern "C" int xdet_conv2d_wgrad_bf16(const void* d_x, const void* d_dy, const xdet_wgrad_desc* d, void* stream) {
+  return launch_wgrad(d_x, d_dy, d, stream, false, 0, 0, 1.f);
+}
+
+extern "C" int xdet_conv2d_wgrad_f16x2(const void* d_x_pair, long long x_plane, const void* d_dy_pair, long long dy_plane,
+                                       const xdet_wgrad_desc* d, float out_scale, void* stream) {
+  if (x_plane % 8 || dy_plane % 8) return fail(XDET_EINVAL, "wgrad_f16x2: operand planes must be 16-byte aligned");
+  return launch_wgrad(d_x_pair, d_dy_pair, d, stream, true, x_plane, dy_plane, out_scale);
 }

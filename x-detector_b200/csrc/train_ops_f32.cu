@@ -1,0 +1,225 @@
+// fp32 forms of the training-step kernels that are not convolutions, for the fp32-ACCURATE training mode
+// ("f16x2" precision of LightHeadTrainer): the mode in which the explicit backward is held to the autograd oracle at
+// SURVEY 8(d) C4's tolerance (losses 1e-4, gradients 1e-3 relative).  Same contracts as their bf16 namesakes in
+// train_ops.cu / layout_ops.cu (the reference's ops they stand for are named there), fp32 tensors instead of bf16.
+// Written for exactness, not speed: column reductions accumulate in fp64 with ONE owner per channel and a fixed
+// order (deterministic, no atomics); nothing here is on a benchmarked path.
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace xdet {
+namespace {
+
+constexpr int kColCh = 32;     // channels per block
+constexpr int kColLanes = 32;  // row lanes per block
+
+// sums[c] (+)= sum_r x[r, c]   and, with squares, sums[C + c] (+)= sum_r x[r, c]^2.   add == 0: overwrite.
+__global__ void __launch_bounds__(kColCh* kColLanes) col_stats_f32_kernel(const float* __restrict__ x, long long rows,
+                                                                          int C, int cs, int sq, int add,
+                                                                          float* __restrict__ sums) {
+  __shared__ double s_a[kColLanes][kColCh + 1], s_q[kColLanes][kColCh + 1];
+  const int cl = threadIdx.x % kColCh, lane = threadIdx.x / kColCh;
+  const int c = blockIdx.x * kColCh + cl;
+  double a = 0.0, q = 0.0;
+  if (c < C) {
+    for (long long r = lane; r < rows; r += kColLanes) {
+      const double v = (double)__ldg(x + r * cs + c);
+      a += v;
+      if (sq) q += v * v;
+    }
+  }
+  s_a[lane][cl] = a;
+  s_q[lane][cl] = q;
+  __syncthreads();
+  if (lane == 0 && c < C) {
+    double ta = 0.0, tq = 0.0;
+    for (int l = 0; l < kColLanes; ++l) {
+      ta += s_a[l][cl];
+      tq += s_q[l][cl];
+    }
+    sums[c] = (add ? sums[c] : 0.f) + (float)ta;
+    if (sq) sums[C + c] = (add ? sums[C + c] : 0.f) + (float)tq;
+  }
+}
+
+// g = dy * [x*scale+shift > 0 or !relu]; sums[c] = sum g, sums[C + c] = sum g * xhat, xhat = (x - mean) * invstd.
+__global__ void __launch_bounds__(kColCh* kColLanes) bn_bwd_reduce_f32_kernel(
+    const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ scale,
+    const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd, long long rows,
+    int C, int relu, float* __restrict__ sums) {
+  __shared__ double s_a[kColLanes][kColCh + 1], s_b[kColLanes][kColCh + 1];
+  const int cl = threadIdx.x % kColCh, lane = threadIdx.x / kColCh;
+  const int c = blockIdx.x * kColCh + cl;
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    const float sc = scale[c], sh = shift[c], mu = mean[c], is = invstd[c];
+    for (long long r = lane; r < rows; r += kColLanes) {
+      const float xv = __ldg(x + r * C + c);
+      const float g = (!relu || __fmaf_rn(xv, sc, sh) > 0.f) ? __ldg(dy + r * C + c) : 0.f;
+      a += (double)g;
+      b += (double)g * ((double)xv - (double)mu) * (double)is;
+    }
+  }
+  s_a[lane][cl] = a;
+  s_b[lane][cl] = b;
+  __syncthreads();
+  if (lane == 0 && c < C) {
+    double ta = 0.0, tb = 0.0;
+    for (int l = 0; l < kColLanes; ++l) {
+      ta += s_a[l][cl];
+      tb += s_b[l][cl];
+    }
+    sums[c] = (float)ta;
+    sums[C + c] = (float)tb;
+  }
+}
+
+// dx = scale * (g - sum_g/M - xhat * sum_gx/M) (+ add_in)
+__global__ void __launch_bounds__(256) bn_bwd_apply_f32_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                               const float* __restrict__ scale,
+                                                               const float* __restrict__ shift,
+                                                               const float* __restrict__ mean,
+                                                               const float* __restrict__ invstd,
+                                                               const float* __restrict__ sums,
+                                                               const float* __restrict__ add_in, long long rows, int C,
+                                                               int relu, float* __restrict__ dx) {
+  const long long total = rows * C, step = (long long)gridDim.x * blockDim.x;
+  const double inv_m = 1.0 / (double)rows;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
+    const int c = (int)(e % C);
+    const float xv = x[e], sc = scale[c];
+    const float g = (!relu || __fmaf_rn(xv, sc, shift[c]) > 0.f) ? dy[e] : 0.f;
+    const double xhat = ((double)xv - (double)mean[c]) * (double)invstd[c];
+    const double v = (double)sc * ((double)g - (double)sums[c] * inv_m - xhat * (double)sums[C + c] * inv_m);
+    dx[e] = (float)v + (add_in ? add_in[e] : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256) relu_bwd_f32_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                           float* __restrict__ dx, long long n) {
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += step)
+    dx[e] = y[e] > 0.f ? dy[e] : 0.f;
+}
+
+// tf.layers.max_pooling2d(3, 2, 'SAME') with the position (kh*3 + kw) of the FIRST maximum of every window.
+__global__ void __launch_bounds__(256) maxpool_argmax_f32_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                                 unsigned char* __restrict__ arg, int H, int W, int C,
+                                                                 int Ho, int Wo, int pad_top, int pad_left,
+                                                                 long long total) {
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
+    const int c = (int)(e % C);
+    const long long pix = e / C;
+    const int xo = (int)(pix % Wo), yo = (int)((pix / Wo) % Ho);
+    const long long n = pix / ((long long)Wo * Ho);
+    float m = -FLT_MAX;
+    unsigned code = 0;
+    bool any = false;
+    for (int kh = 0; kh < 3; ++kh) {
+      const int yi = yo * 2 + kh - pad_top;
+      if (yi < 0 || yi >= H) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int xi = xo * 2 + kw - pad_left;
+        if (xi < 0 || xi >= W) continue;
+        const float v = __ldg(src + ((n * H + yi) * W + xi) * C + c);
+        if (!any || v > m) {
+          m = v;
+          code = (unsigned)(kh * 3 + kw);
+          any = true;
+        }
+      }
+    }
+    dst[e] = m;
+    arg[e] = (unsigned char)code;
+  }
+}
+
+__global__ void __launch_bounds__(256) maxpool_bwd_f32_kernel(const unsigned char* __restrict__ arg,
+                                                              const float* __restrict__ dy, float* __restrict__ dx, int H,
+                                                              int W, int C, int Ho, int Wo, int pad_top, int pad_left,
+                                                              long long total) {
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
+    const int c = (int)(e % C);
+    long long t = e / C;
+    const int xi = (int)(t % W);
+    t /= W;
+    const int yi = (int)(t % H);
+    const long long n = t / H;
+    float acc = 0.f;
+    const int yo_lo = max(0, (yi + pad_top - 1) / 2), yo_hi = min(Ho - 1, (yi + pad_top) / 2);
+    const int xo_lo = max(0, (xi + pad_left - 1) / 2), xo_hi = min(Wo - 1, (xi + pad_left) / 2);
+    for (int yo = yo_lo; yo <= yo_hi; ++yo) {
+      const int kh = yi - (yo * 2 - pad_top);
+      if (kh < 0 || kh > 2) continue;
+      for (int xo = xo_lo; xo <= xo_hi; ++xo) {
+        const int kw = xi - (xo * 2 - pad_left);
+        if (kw < 0 || kw > 2) continue;
+        const long long o = ((n * Ho + yo) * Wo + xo) * C + c;
+        if (arg[o] == (unsigned char)(kh * 3 + kw)) acc = __fadd_rn(acc, dy[o]);
+      }
+    }
+    dx[e] = acc;
+  }
+}
+
+unsigned blocks256(long long total) {
+  long long b = (total + 255) / 256;
+  const long long cap = (long long)kNumSMs * 32;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace
+}  // namespace xdet
+
+using namespace xdet;
+
+extern "C" int xdet_col_stats_f32(const float* d_x, long long rows, int C, int cs, int with_squares, int accumulate,
+                                  float* d_sums, void* stream) {
+  if (rows <= 0 || C <= 0) return XDET_OK;
+  if (cs < C) return fail(XDET_EINVAL, "col_stats_f32: row pitch below C");
+  col_stats_f32_kernel<<<(C + kColCh - 1) / kColCh, kColCh * kColLanes, 0, (cudaStream_t)stream>>>(
+      d_x, rows, C, cs, with_squares, accumulate, d_sums);
+  return after_launch("col_stats_f32_kernel");
+}
+
+extern "C" int xdet_bn_relu_bwd_f32(const float* d_dy, const float* d_x, const float* d_scale, const float* d_shift,
+                                    const float* d_mean, const float* d_invstd, long long rows, int C, int relu,
+                                    const float* d_add_in, float* d_sums, float* d_dx, void* stream) {
+  if (rows <= 0 || C <= 0) return XDET_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  bn_bwd_reduce_f32_kernel<<<(C + kColCh - 1) / kColCh, kColCh * kColLanes, 0, st>>>(d_dy, d_x, d_scale, d_shift, d_mean,
+                                                                                    d_invstd, rows, C, relu, d_sums);
+  XDET_TRY(after_launch("bn_bwd_reduce_f32_kernel"));
+  bn_bwd_apply_f32_kernel<<<blocks256(rows * C), 256, 0, st>>>(d_dy, d_x, d_scale, d_shift, d_mean, d_invstd, d_sums,
+                                                              d_add_in, rows, C, relu, d_dx);
+  return after_launch("bn_bwd_apply_f32_kernel");
+}
+
+extern "C" int xdet_relu_bwd_f32(const float* d_dy, const float* d_y, float* d_dx, long long n, void* stream) {
+  if (n <= 0) return XDET_OK;
+  relu_bwd_f32_kernel<<<blocks256(n), 256, 0, (cudaStream_t)stream>>>(d_dy, d_y, d_dx, n);
+  return after_launch("relu_bwd_f32_kernel");
+}
+
+extern "C" int xdet_maxpool3x3s2_argmax_f32(const float* d_src, float* d_dst, unsigned char* d_argmax, int N, int H,
+                                            int W, int C, int Ho, int Wo, int pad_top, int pad_left, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0) return fail(XDET_EINVAL, "maxpool_argmax_f32: non-positive dimension");
+  const long long total = (long long)N * Ho * Wo * C;
+  maxpool_argmax_f32_kernel<<<blocks256(total), 256, 0, (cudaStream_t)stream>>>(d_src, d_dst, d_argmax, H, W, C, Ho, Wo,
+                                                                               pad_top, pad_left, total);
+  return after_launch("maxpool_argmax_f32_kernel");
+}
+
+extern "C" int xdet_maxpool3x3s2_bwd_f32(const unsigned char* d_argmax, const float* d_dy, float* d_dx, int N, int H,
+                                         int W, int C, int Ho, int Wo, int pad_top, int pad_left, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0) return fail(XDET_EINVAL, "maxpool_bwd_f32: non-positive dimension");
+  const long long total = (long long)N * H * W * C;
+  maxpool_bwd_f32_kernel<<<blocks256(total), 256, 0, (cudaStream_t)stream>>>(d_argmax, d_dy, d_dx, H, W, C, Ho, Wo,
+                                                                            pad_top, pad_left, total);
+  return after_launch("maxpool_bwd_f32_kernel");
+}

@@ -55,7 +55,15 @@ _DEFAULTS = dict(
     backbone='resnet50',
     # not a reference flag: blocks per block_layer of the ResNet v2 composition (resnet_size 50 = 3,4,6,3)
     resnet_layers=(3, 4, 6, 3),
+    # not a reference flag: 'bf16' = the throughput path (bf16 activations / operands, fp32 accumulate and masters);
+    # 'f16x2' = the fp32-ACCURATE training mode (fp32 activations and gradients, split-operand tensor-core
+    # convolutions for forward / input gradient / weight gradient, fp32 batch-norm / pooling kernels): the mode in
+    # which the explicit backward is held to the autograd oracle at 1e-3 (ResNet-50 composition)
+    precision='bf16',
 )
+# fp32-accurate mode: the backward runs on gradients scaled by 2^12 (exact) so that they sit inside fp16's range when
+# they are split into (hi, lo) planes; the flat gradient buffer is scaled back once at the end
+_LOSS_SCALE = 4096.0
 FLAGS = types.SimpleNamespace(**_DEFAULTS)
 pool_method = 'max'  # light_head_rfcn_train.py:199
 _BN_DECAY, _BN_EPS = 0.997, 1e-5  # net/resnet_v2.py:37-38
@@ -118,11 +126,36 @@ class ConvParams(object):
             self.pack = ops.pack_conv_weight(w)
             self.cin_pad = (cin + 63) // 64 * 64
             shape = (cout, kh * kw, self.cin_pad)
+        self.need_dgrad = need_dgrad
         self.dpack = ops.pack_dgrad_weight(w) if need_dgrad else None
         self.dw = None
+        self.precision = conv_ops.PRECISION
         reg.request(shape[0] * shape[1] * shape[2], lambda v: setattr(self, 'dw', v.view(shape)))
 
+    def _dense(self):
+        w = torch.zeros((self.cout, self.cin, self.kh, self.kw), dtype=torch.float32, device=self.masters[0][1].device)
+        for _, t, co, ci in self.masters:
+            t4 = t if t.dim() == 4 else t.reshape(1, 1, *t.shape)
+            w[co:co + t4.shape[3], ci:ci + t4.shape[2]] = t4.permute(3, 2, 0, 1)
+        return w
+
     def update(self, lr, momentum, wd, gscale):
+        if self.precision == "f16x2":
+            # the optimizer kernel refreshes bf16 packs: give it scratch ones, then re-split the updated masters
+            if not hasattr(self, "_scratch"):
+                cpad = self.cin_pad
+                self._scratch = torch.empty((self.cout, (self.kh if self.fold else self.kh * self.kw) * cpad),
+                                            dtype=torch.bfloat16, device=self.dw.device)
+                copad = (self.cout + 63) // 64 * 64
+                self._dscratch = (torch.empty((self.cin, self.kh * self.kw * copad), dtype=torch.bfloat16,
+                                              device=self.dw.device) if self.need_dgrad else None)
+            for (_, t, co, ci), m in zip(self.masters, self.mom):
+                T.sgd_momentum_conv(self.dw, t, m, self._scratch, self._dscratch, lr, momentum, wd, gscale, co, ci, self.fold)
+            with conv_ops.precision("f16x2"):
+                w = self._dense()
+                self.pack = ops.pack_fold_weight(w) if self.fold else ops.pack_conv_weight(w)
+                self.dpack = ops.pack_dgrad_weight(w) if self.need_dgrad else None
+            return
         for (_, t, co, ci), m in zip(self.masters, self.mom):
             T.sgd_momentum_conv(self.dw, t, m, self.pack, self.dpack, lr, momentum, wd, gscale, co, ci, self.fold)
 
@@ -179,9 +212,7 @@ class Conv(object):
         if self.bias is not None:  # dbias = column sums of dy, accumulated straight into the flat gradient buffer
             dy2 = dy.reshape(-1, dy.shape[-1])
             assert dy2.shape[1] == self.bias.seg, (dy2.shape, self.bias.seg)
-            _native.check(_native.lib().xdet_col_stats_bf16(dy2.data_ptr(), dy2.shape[0], dy2.shape[1], dy2.shape[1], 0,
-                                                            self.bias.grad.data_ptr(),
-                                                            torch.cuda.current_stream().cuda_stream))
+            T.col_sums_into(dy2, self.bias.grad)
         if not need_dx:
             return None
         return ops.conv2d_dgrad(dy, p.dpack, p.cin, p.kh, p.kw, self.in_hw, dilation=(self.dil, self.dil),
@@ -218,15 +249,8 @@ class BNRelu(object):
     def bwd(self, dy, add_in=None):
         cs = self.x.shape[-1]
         assert cs == self.vec.seg and dy.shape == self.x.shape and dy.is_contiguous()
-        dx = torch.empty_like(self.x)
-        st = self.st
         # the kernel's sums ARE the gradient: [0,cs) = dbeta, [cs,2cs) = dgamma, written into the flat buffer
-        _native.check(_native.lib().xdet_bn_relu_bwd_bf16(dy.data_ptr(), self.x.data_ptr(), st.scale.data_ptr(),
-                                                          st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
-                                                          st.rows, cs, 1, None if add_in is None else add_in.data_ptr(),
-                                                          self.vec.grad.data_ptr(), dx.data_ptr(),
-                                                          torch.cuda.current_stream().cuda_stream))
-        return dx
+        return T.bn_relu_bwd_into(dy, self.x, self.st, True, self.vec.grad, add_in)
 
 
 class Bottleneck(object):
@@ -282,6 +306,13 @@ class LightHeadTrainer(object):
         if p['backbone'] not in ('resnet50', 'xception'):
             raise ValueError("backbone must be 'resnet50' or 'xception'")
         self.xception = p['backbone'] == 'xception'
+        self.precision = p.get('precision', 'bf16')
+        if self.precision not in ('bf16', 'f16x2'):
+            raise ValueError("precision must be 'bf16' or 'f16x2'")
+        if self.precision == 'f16x2' and self.xception:
+            raise NotImplementedError("the fp32-accurate training mode is built for the ResNet-50 composition "
+                                      "(BASELINE config 4); XceptionBody trains in bf16")
+        self.f32 = self.precision == 'f16x2'
         self.device = torch.device(device)
         self.store = store = VariableStore(device=device, seed=seed, state_dict=state_dict)
         self.pg = process_group
@@ -312,7 +343,8 @@ class LightHeadTrainer(object):
         self.side = torch.cuda.Stream(device=self.device)
         self.comm = torch.cuda.Stream(device=self.device)
         self.marks = []  # (stage name, index of its first gradient request): where the all-reduce buckets start
-        self._build()
+        with conv_ops.precision(self.precision):
+            self._build()
         reg.finalize()
         self.grads = reg.flat
         # buckets in flat (= forward) order: [(name, start, end)]; a stage's bucket is complete when the backward has
@@ -585,8 +617,12 @@ class LightHeadTrainer(object):
             self.fc2 = Conv(cpf2, bias=self._bias([fused_f2]))
 
     # ---- forward pieces ----------------------------------------------------------------------------------------
+    def _rows(self, feat, pitch):
+        """PsRoIAlign rows for the dense layers: bf16 rows of ``pitch`` channels (fp32 as they are in the f16x2 mode)."""
+        return feat.contiguous() if self.f32 else ops.f32_to_bf16_rows(feat.contiguous(), pitch)
+
     def _head_fwd(self, feat_bf16):
-        """feat [M, 496] bf16 -> (h [1,1,M,2048] bf16 ReLU'd, out [M, nc+4] fp32)."""
+        """feat [M, 496] bf16 (or [M, 490] fp32) -> (h [1,1,M,2048] ReLU'd, out [M, nc+4] fp32)."""
         M = feat_bf16.shape[0]
         h = self.fc1.fwd(feat_bf16.reshape(1, 1, M, -1), relu=True)
         out = self.fc2.fwd(h, out_layout="nhwc_f32")
@@ -609,10 +645,17 @@ class LightHeadTrainer(object):
         'rpn_fg','rpn_bg' [1, N*A_tot], 'rpn_up' [1, N*256], 'prop' [N, 1800], 'roi_fg','roi_bg' [N, 1800+G],
         'roi_up' [N, 64].  ``inject`` (tests): {'rois_all','roi_idx','rpn_idx','ohem_idx'} override the discrete
         selections.  Returns a dict of scalar losses (device tensors) and the selections."""
+        with conv_ops.precision(self.precision):
+            return self._step(images, gt_boxes, gt_labels, keys, apply_update, inject)
+
+    def _step(self, images, gt_boxes, gt_labels, keys, apply_update, inject):
         p, nc, A = self.params, self.params['num_classes'], self.A
         inject = inject or {}
         N = images.shape[0]
         fm = self.fmap
+        # fp32-accurate mode: the backward carries gradients scaled by S (see _LOSS_SCALE); act = activation dtype
+        S = _LOSS_SCALE if self.f32 else 1.0
+        act = torch.float32 if self.f32 else torch.bfloat16
         self.grads.zero_()
 
         self._pending = set(n for n, _, _ in self.buckets) if self._world() > 1 else None
@@ -627,7 +670,10 @@ class LightHeadTrainer(object):
             Wimg = images.shape[3]
             Wo = (Wimg + 6 - 7) // 2 + 1
             wp = (max((Wo - 1) * 2 + 8, Wimg + 3) + 7) // 8 * 8
-            x8 = ops.image_to_nhwc8(images.contiguous(), 3, wp)
+            if self.f32:  # row-padded f16x2 planes of the image (a fresh buffer: the tape keeps it for the weight gradient)
+                x8 = ops.split2(images.permute(0, 2, 3, 1), cin=3, pad_w=(wp, 3)).clone()
+            else:
+                x8 = ops.image_to_nhwc8(images.contiguous(), 3, wp)
             Ho = (images.shape[2] + 6 - 7) // 2 + 1
             self.stem.x = x8
             y0 = ops.conv2d_nhwc(x8, self.stem.p.pack, 64, 7, 7, padding=(3, 3, Ho, Wo), strides=(2, 2), cin=3,
@@ -665,17 +711,18 @@ class LightHeadTrainer(object):
             s_cls, s_loc = cls_all.index_select(0, rpn_idx), loc_all.index_select(0, rpn_idx)
             s_lab = (glabels.reshape(-1).index_select(0, rpn_idx) > 0).to(torch.int32)
             s_tgt = gtargets.reshape(-1, 4).index_select(0, rpn_idx).contiguous()
-            rpn_ce_rows, d_s_cls = T.softmax_ce(s_cls, s_lab, 2, w_all=1.0 / n_rpn)
+            rpn_ce_rows, d_s_cls = T.softmax_ce(s_cls, s_lab, 2, w_all=S / n_rpn)
             posm = s_lab.float()
             npos = posm.sum().clamp(min=1.0)
             row_w = posm / (npos * p['rpn_fg_ratio'])
-            rpn_l1_rows, d_s_loc = T.smooth_l1(s_loc, s_tgt, row_w=row_w, w_all=1.0)
+            rpn_l1_rows, d_s_loc = T.smooth_l1(s_loc, s_tgt, row_w=row_w, w_all=S)
+            # (w_all weights the GRADIENT only: the loss rows are unscaled)
             rpn_ce, rpn_loc = rpn_ce_rows.mean(), rpn_l1_rows.sum()
             # gradient of the RPN losses w.r.t. the head output, scattered back to the dense [N,fm,fm,6A] tensor
             d_cls = torch.zeros_like(cls_all).index_add_(0, rpn_idx, d_s_cls)
             d_loc = torch.zeros_like(loc_all).index_add_(0, rpn_idx, d_s_loc)
             cpitch = (6 * A + 7) // 8 * 8
-            d_rpn = torch.zeros((N, fm, fm, cpitch), dtype=torch.bfloat16, device=self.device)
+            d_rpn = torch.zeros((N, fm, fm, cpitch), dtype=act, device=self.device)
             d_rpn[..., :2 * A] = d_cls.reshape(N, fm, fm, 2 * A)
             d_rpn[..., 2 * A:6 * A] = d_loc.reshape(N, fm, fm, 4 * A)
 
@@ -718,12 +765,15 @@ class LightHeadTrainer(object):
             mid = self.sep_a.fwd(backbone)
             bias_b = self.sep_b_biases[0] + self.sep_b_biases[1]
             # 490 channels live in rows of 496 (16-byte pixel strides for TMA and the vector kernels), zero tail
-            o_buf = torch.zeros((N, fm, fm, 496), dtype=torch.bfloat16, device=self.device)
+            o_buf = torch.zeros((N, fm, fm, 496), dtype=act, device=self.device)
             self.sep_b.fwd(mid, bias_tensor=bias_b, out=o_buf[..., :490])
         finally:
             conv_ops.MAX_CTAS = 0
         st_sep = self.bn_sep.stats(o_buf)
-        thin = T.affine_relu_to_nchw_f32(o_buf, st_sep.scale, st_sep.shift, relu=True, C=490)
+        if self.f32:  # (layout plumbing of the verification mode: NHWC -> the NCHW PsRoIAlign's contract asks for)
+            thin = torch.relu(o_buf[..., :490] * st_sep.scale[:490] + st_sep.shift[:490]).permute(0, 3, 1, 2).contiguous()
+        else:
+            thin = T.affine_relu_to_nchw_f32(o_buf, st_sep.scale, st_sep.shift, relu=True, C=490)
         main.wait_stream(side)  # JOIN
         for t_ in (score, boxes, glabels, gtargets, rpn_idx, d_rpn, rois_all, rlab, rtgt, rsc, roi_idx, rois, roi_tgt,
                    roi_lab, yxhw, rpn_ce, rpn_loc):
@@ -740,7 +790,7 @@ class LightHeadTrainer(object):
             if 'ohem_idx' in inject:
                 sel = inject['ohem_idx']
             else:
-                _, out1 = self._head_fwd(ops.f32_to_bf16_rows(feat, pitch))
+                _, out1 = self._head_fwd(self._rows(feat, pitch))
                 loss1, _ = self._head_loss(out1, lab_flat, tgt_flat, 1.0)
                 sel = torch.topk(loss1.reshape(N, R), k, dim=1).indices  # selection only (tf.nn.top_k, :529)
             # tf.gather(x, select_indices, axis=1) with a [N,k] index: every image gets every image's rows
@@ -751,15 +801,18 @@ class LightHeadTrainer(object):
         else:
             sel, flat_sel, feat2, lab2, tgt2 = None, None, feat, lab_flat, tgt_flat
         M2 = feat2.shape[0]
-        a2 = ops.f32_to_bf16_rows(feat2.contiguous(), pitch)
+        a2 = self._rows(feat2, pitch)
         h2, out2 = self._head_fwd(a2)
-        head_rows, dout2 = self._head_loss(out2, lab2, tgt2, 1.0 / M2)
+        head_rows, dout2 = self._head_loss(out2, lab2, tgt2, S / M2)
         head_loss = head_rows.mean()
 
         # ================= backward =================
         # ---- head ----
         dpitch = (nc + 4 + 7) // 8 * 8
-        d_out_b = ops.f32_to_bf16_rows(dout2, dpitch).reshape(1, 1, M2, dpitch)
+        if self.f32:
+            d_out_b = torch.nn.functional.pad(dout2, (0, dpitch - dout2.shape[1])).reshape(1, 1, M2, dpitch)
+        else:
+            d_out_b = ops.f32_to_bf16_rows(dout2, dpitch).reshape(1, 1, M2, dpitch)
         dh = self.fc2.bwd(d_out_b)
         dh = T.relu_bwd(dh, h2)
         dfeat2 = self.fc1.bwd(dh, dx_layout="nhwc_f32").reshape(M2, cin)
@@ -769,11 +822,13 @@ class LightHeadTrainer(object):
             dfeat = dfeat2
         d_thin = ops.ps_roi_align_grad(thin, yxhw, dfeat.reshape(pooled.shape).contiguous(), pindex, 7, 7, pool_method)
         # ---- thin feature map ----
-        do = self.bn_sep.bwd(T.nchw_f32_to_nhwc_bf16(d_thin, pitch=496))
+        if self.f32:
+            d_o = torch.nn.functional.pad(d_thin.permute(0, 2, 3, 1), (0, 6)).contiguous()
+        else:
+            d_o = T.nchw_f32_to_nhwc_bf16(d_thin, pitch=496)
+        do = self.bn_sep.bwd(d_o)
         # biases of the two 1x15 convs: both get the column sums of `do` (one gradient view, two variables)
-        _native.check(_native.lib().xdet_col_stats_bf16(do.data_ptr(), N * fm * fm, 496, 496, 0,
-                                                        self.sep_b_bias_vec.grad.data_ptr(),
-                                                        torch.cuda.current_stream().cuda_stream))
+        T.col_sums_into(do.reshape(N * fm * fm, 496), self.sep_b_bias_vec.grad)
         dmid = self.sep_b.bwd(do)
         dbackbone = self.sep_a.bwd(dmid)
         # ---- RPN head ----
@@ -800,6 +855,8 @@ class LightHeadTrainer(object):
                              fold_w=(Wimg, 3))
 
         # ================= all-reduce (remaining buckets, join) + optimizer =================
+        if self.f32:
+            self.grads.mul_(1.0 / S)  # exact: S is a power of two (fp32-accurate mode: no bucket has been sent yet)
         world = self._allreduce_finish()
         if apply_update:
             lr = learning_rate(p, self.global_step)

@@ -657,6 +657,9 @@ def conv2d_wgrad(x, dy, kh, kw, *, dilation=(1, 1), padding="SAME", strides=(1, 
                  splits=0, fold_w=None):
     """dW of ``conv2d_nhwc(x, w, ...) -> y`` given ``dy`` (both NHWC bf16): fp32 [Cout, kh*kw, ceil(Cin/64)*64], the
     packed layout of the forward weights.  ``dw`` (zero-filled, or holding a partial sum) is accumulated into."""
+    if dy.dtype == torch.float32:  # the fp32-accurate training mode
+        return _conv2d_wgrad_f16x2(x, dy, kh, kw, dilation=dilation, padding=padding, strides=strides, cin=cin, cout=cout,
+                                   dw=dw, splits=splits, fold_w=fold_w)
     assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and x.is_contiguous() and dy.is_contiguous()
     N, H, W, cs = x.shape
     in_wp = 0
@@ -685,6 +688,49 @@ def conv2d_wgrad(x, dy, kh, kw, *, dilation=(1, 1), padding="SAME", strides=(1, 
             e0.record()
         rc = _native.lib().xdet_conv2d_wgrad_bf16(x.data_ptr(), dy.data_ptr(), ctypes.byref(d),
                                                   torch.cuda.current_stream().cuda_stream)
+        if PROFILE is not None:
+            e1.record()
+            PROFILE.append((e0, e1, 2.0 * N * Ho * Wo * cout * cin * kh * kw, ("wgrad", N, H, W, cin, cout, kh, kw)))
+    _native.check(rc)
+    return dw
+
+
+def _conv2d_wgrad_f16x2(x, dy, kh, kw, *, dilation, padding, strides, cin, cout, dw, splits, fold_w):
+    """``conv2d_wgrad`` in "f16x2" precision: x = fp32 NHWC activation (its split planes attached by the producer, or made
+    here) -- or, fold_w mode, the row-padded image planes themselves; dy = fp32 NHWC [N,Ho,Wo,>=cout]."""
+    if fold_w is not None:
+        xp = x  # [2,N,H,in_wp,8]
+        _, N, H, in_wp, cs = xp.shape
+        W = fold_w[0]
+        cin = cs if cin is None else cin
+    else:
+        N, H, W, C = x.shape
+        cin = C if cin is None else cin
+        xp = pair_of(x, cin)
+        cs, in_wp = xp.shape[-1], 0
+    _, Ho, Wo, dC = dy.shape
+    cout = dC if cout is None else cout
+    dyp = split2(dy)
+    dh, dw_ = dilation
+    sh, sw = strides
+    if padding == "SAME":
+        pt, pl = same_pad(H, kh, dh, sh), same_pad(W, kw, dw_, sw)
+    elif padding == "VALID":
+        pt = pl = 0
+    else:
+        pt, pl = padding[:2]
+    cpad = (cin + 63) // 64 * 64
+    if dw is None:
+        dw = torch.zeros((cout, kh, 64) if fold_w is not None else (cout, kh * kw, cpad), dtype=torch.float32,
+                         device=dy.device)
+    d = WgradDesc(N, H, W, cin, cs, cout, kh, kw, dh, dw_, pt, pl, sh, sw, Ho, Wo, dyp.shape[-1], dw.data_ptr(), splits,
+                  0 if fold_w is None else 1, in_wp)
+    with torch.cuda.device(dy.device):
+        if PROFILE is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        rc = _native.lib().xdet_conv2d_wgrad_f16x2(xp.data_ptr(), xp.stride(0), dyp.data_ptr(), dyp.stride(0),
+                                                   ctypes.byref(d), 1.0, torch.cuda.current_stream().cuda_stream)
         if PROFILE is not None:
             e1.record()
             PROFILE.append((e0, e1, 2.0 * N * Ho * Wo * cout * cin * kh * kw, ("wgrad", N, H, W, cin, cout, kh, kw)))

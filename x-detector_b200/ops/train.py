@@ -18,13 +18,39 @@ def _p(t):
 
 
 def col_stats(x2d, with_squares=True, C=None):
-    """x2d [rows, cs] bf16 -> fp32 [2*C] (sums, sums of squares) or [C]."""
+    """x2d [rows, cs] bf16 (or fp32: the fp32-accurate training mode) -> fp32 [2*C] (sums, sums of squares) or [C]."""
     rows, cs = x2d.shape
     C = cs if C is None else C
     sums = torch.zeros((2 if with_squares else 1) * C, dtype=torch.float32, device=x2d.device)
-    _native.check(_native.lib().xdet_col_stats_bf16(x2d.data_ptr(), rows, C, cs, 1 if with_squares else 0,
-                                                    sums.data_ptr(), _st()))
+    col_sums_into(x2d, sums, with_squares=with_squares, C=C)
     return sums
+
+
+def col_sums_into(x2d, sums, with_squares=False, C=None):
+    """Column sums of x2d [rows, cs] ADDED to ``sums`` (a view of the flat gradient buffer for bias gradients)."""
+    rows, cs = x2d.shape
+    C = cs if C is None else C
+    assert x2d.is_contiguous()
+    if x2d.dtype == torch.float32:
+        _native.check(_native.lib().xdet_col_stats_f32(x2d.data_ptr(), rows, C, cs, 1 if with_squares else 0, 1,
+                                                       sums.data_ptr(), _st()))
+    else:
+        _native.check(_native.lib().xdet_col_stats_bf16(x2d.data_ptr(), rows, C, cs, 1 if with_squares else 0,
+                                                        sums.data_ptr(), _st()))
+
+
+def bn_relu_bwd_into(dy, x, st, relu, sums_view, add_in=None):
+    """Backward of y = [relu](x*scale+shift) with batch statistics; ``sums_view`` ([0,cs) = dbeta, [cs,2cs) = dgamma) is
+    overwritten -- usually a view of the flat gradient buffer.  Returns dx (dtype of x)."""
+    cs = x.shape[-1]
+    assert dy.shape == x.shape and dy.dtype == x.dtype and dy.is_contiguous() and x.is_contiguous()
+    assert sums_view.numel() == 2 * cs and (add_in is None or (add_in.is_contiguous() and add_in.dtype == x.dtype))
+    dx = torch.empty_like(x)
+    fn = _native.lib().xdet_bn_relu_bwd_f32 if x.dtype == torch.float32 else _native.lib().xdet_bn_relu_bwd_bf16
+    _native.check(fn(dy.data_ptr(), x.data_ptr(), st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(),
+                     st.invstd.data_ptr(), st.rows, cs, 1 if relu else 0, _p(add_in), sums_view.data_ptr(),
+                     dx.data_ptr(), _st()))
+    return dx
 
 
 class BNState(object):
@@ -50,21 +76,19 @@ def bn_train(x, gamma, beta, eps, decay=None, moving_mean=None, moving_var=None)
 def bn_relu_bwd(dy, x, st, relu=True, add_in=None):
     """-> (dx bf16 like x, dgamma [C], dbeta [C]) for y = relu(x*scale+shift) with batch statistics."""
     C = x.shape[-1]
-    assert dy.shape == x.shape and dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16
-    assert dy.is_contiguous() and x.is_contiguous() and (add_in is None or add_in.is_contiguous())
     sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
-    dx = torch.empty_like(x)
-    _native.check(_native.lib().xdet_bn_relu_bwd_bf16(dy.data_ptr(), x.data_ptr(), st.scale.data_ptr(),
-                                                      st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
-                                                      st.rows, C, 1 if relu else 0, _p(add_in), sums.data_ptr(),
-                                                      dx.data_ptr(), _st()))
+    dx = bn_relu_bwd_into(dy, x, st, relu, sums, add_in)
     return dx, sums[C:], sums[:C]
 
 
 def relu_bwd(dy, y):
-    assert dy.shape == y.shape and dy.is_contiguous() and y.is_contiguous() and dy.dtype == torch.bfloat16
+    assert dy.shape == y.shape and dy.is_contiguous() and dy.dtype == y.dtype
+    if getattr(y, "_pair_only", False):
+        raise ValueError("relu_bwd needs the fp32 values of y (it was stored as split planes only)")
+    assert y.is_contiguous()
     dx = torch.empty_like(dy)
-    _native.check(_native.lib().xdet_relu_bwd_bf16(dy.data_ptr(), y.data_ptr(), dx.data_ptr(), dy.numel(), _st()))
+    fn = _native.lib().xdet_relu_bwd_f32 if dy.dtype == torch.float32 else _native.lib().xdet_relu_bwd_bf16
+    _native.check(fn(dy.data_ptr(), y.data_ptr(), dx.data_ptr(), dy.numel(), _st()))
     return dx
 
 
@@ -72,10 +96,13 @@ def maxpool3x3s2_fwd_train(x):
     """tf.layers.max_pooling2d(3, 2, 'SAME') on NHWC bf16 -> (pooled, argmax uint8 [N,Ho,Wo,C])."""
     N, H, W, C = x.shape
     Ho, Wo = -(-H // 2), -(-W // 2)
-    out = torch.empty((N, Ho, Wo, C), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty((N, Ho, Wo, C), dtype=x.dtype, device=x.device)
     arg = torch.empty((N, Ho, Wo, C), dtype=torch.uint8, device=x.device)
-    _native.check(_native.lib().xdet_maxpool3x3s2_argmax_bf16(x.data_ptr(), out.data_ptr(), arg.data_ptr(), N, H, W, C, Ho,
-                                                              Wo, same_pad(H, 3, 1, 2), same_pad(W, 3, 1, 2), _st()))
+    fn = (_native.lib().xdet_maxpool3x3s2_argmax_f32 if x.dtype == torch.float32
+          else _native.lib().xdet_maxpool3x3s2_argmax_bf16)
+    assert x.is_contiguous()
+    _native.check(fn(x.data_ptr(), out.data_ptr(), arg.data_ptr(), N, H, W, C, Ho, Wo, same_pad(H, 3, 1, 2),
+                     same_pad(W, 3, 1, 2), _st()))
     return out, arg
 
 
@@ -83,9 +110,11 @@ def maxpool3x3s2_bwd(argmax, dy, in_hw):
     """dx [N,H,W,C] of the pooling above from its recorded argmax."""
     N, Ho, Wo, C = dy.shape
     H, W = in_hw
-    dx = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=dy.device)
-    _native.check(_native.lib().xdet_maxpool3x3s2_bwd_bf16(argmax.data_ptr(), dy.data_ptr(), dx.data_ptr(), N, H, W, C, Ho,
-                                                           Wo, same_pad(H, 3, 1, 2), same_pad(W, 3, 1, 2), _st()))
+    dx = torch.empty((N, H, W, C), dtype=dy.dtype, device=dy.device)
+    fn = _native.lib().xdet_maxpool3x3s2_bwd_f32 if dy.dtype == torch.float32 else _native.lib().xdet_maxpool3x3s2_bwd_bf16
+    assert dy.is_contiguous()
+    _native.check(fn(argmax.data_ptr(), dy.data_ptr(), dx.data_ptr(), N, H, W, C, Ho, Wo, same_pad(H, 3, 1, 2),
+                     same_pad(W, 3, 1, 2), _st()))
     return dx
 
 
