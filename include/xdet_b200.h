@@ -414,6 +414,9 @@ int xdet_bn_relu_bwd_f32(const float* d_dy, const float* d_x, const float* d_sca
                          const float* d_mean, const float* d_invstd, long long rows, int C, int relu,
                          const float* d_add_in, float* d_sums, float* d_dx, void* stream);
 int xdet_relu_bwd_f32(const float* d_dy, const float* d_y, float* d_dx, long long n, void* stream);
+/* dw [9, C] += depthwise 3x3 weight gradient on NHWC fp32 tensors (see xdet_depthwise3x3_wgrad_bf16) */
+int xdet_depthwise3x3_wgrad_f32(const float* d_x, const float* d_dy, float* d_dw, int N, int H, int W, int C,
+                                int dilation, int relu_in, void* stream);
 int xdet_maxpool3x3s2_argmax_f32(const float* d_src, float* d_dst, unsigned char* d_argmax, int N, int H, int W, int C,
                                  int Ho, int Wo, int pad_top, int pad_left, void* stream);
 int xdet_maxpool3x3s2_bwd_f32(const unsigned char* d_argmax, const float* d_dy, float* d_dx, int N, int H, int W, int C,

@@ -202,14 +202,17 @@ def _grad_pairs(tr, grads):
                 yield k, seg[off:off + val.numel()].reshape(val.shape), grads[k].reshape(val.shape)
 
 
-@pytest.mark.parametrize("layers", [(1, 1, 1, 1), (3, 4, 6, 3)])
+@pytest.mark.parametrize("layers", [(1, 1, 1, 1), (3, 4, 6, 3), "xception"])
 def test_fp32_accurate_mode_meets_the_c4_tolerance(layers):
     """"losses within 1e-4 rel, grads within 1e-3 rel (fp32 mode)".  precision='f16x2': fp32 activations
     and gradients, split-operand tensor-core kernels for every convolution's forward, input gradient and weight
     gradient, fp32 batch-norm / pooling kernels -- the explicit backward of LightHeadTrainer against torch autograd
     over the fp32 CPU restatement of the same step (discrete selections injected; they are checked exactly elsewhere).
     Gradients are compared per variable, relative to the variable's gradient norm."""
-    lt, params, tr, sd0, batch, out = _run(layers, precision="f16x2")
+    if layers == "xception":  # the reference's own training backbone (36 convolutions deep)
+        lt, params, tr, sd0, batch, out = _run((3, 4, 6, 3), backbone="xception", precision="f16x2")
+    else:
+        lt, params, tr, sd0, batch, out = _run(layers, precision="f16x2")
     images, gt, gl, keys = batch
     anchors = op.layer_anchors((160, 160), (10, 10), [0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8], [0.1], [1., 2., .5], 16)
     inject = {k: out[k].cpu().numpy() for k in ("rpn_idx", "rois_all", "roi_idx", "ohem_idx")}

@@ -104,6 +104,7 @@ def _declare_train(lib):
     lib.xdet_depthwise3x3_wgrad_bf16.argtypes = [c_void_p] * 3 + [c_int] * 6 + [c_void_p]
     lib.xdet_col_stats_f32.argtypes = [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
     lib.xdet_bn_relu_bwd_f32.argtypes = [c_void_p] * 6 + [c_ll, c_int, c_int] + [c_void_p] * 4
+    lib.xdet_depthwise3x3_wgrad_f32.argtypes = [c_void_p] * 3 + [c_int] * 6 + [c_void_p]
     lib.xdet_relu_bwd_f32.argtypes = [c_void_p, c_void_p, c_void_p, c_ll, c_void_p]
     lib.xdet_maxpool3x3s2_argmax_f32.argtypes = [c_void_p] * 3 + [c_int] * 8 + [c_void_p]
     lib.xdet_maxpool3x3s2_bwd_f32.argtypes = [c_void_p] * 3 + [c_int] * 8 + [c_void_p]

@@ -165,6 +165,52 @@ __global__ void __launch_bounds__(256) maxpool_bwd_f32_kernel(const unsigned cha
   }
 }
 
+// Weight gradient of the depthwise 3x3 'SAME' stride-1 convolution (dilation d): dw[k][c] += sum_pixels act(x[p + tap k]) * dy[p].
+// One block owns 32 channels; 32 pixel lanes accumulate the nine sums in fp64 (fixed order, no atomics).
+__global__ void __launch_bounds__(kColCh* kColLanes) depthwise_wgrad_f32_kernel(const float* __restrict__ x,
+                                                                                const float* __restrict__ dy,
+                                                                                float* __restrict__ dw, int N, int H,
+                                                                                int W, int C, int dil, int relu_in) {
+  __shared__ double s[kColLanes][kColCh + 1];
+  const int cl = threadIdx.x % kColCh, lane = threadIdx.x / kColCh;
+  const int c = blockIdx.x * kColCh + cl;
+  double acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+  if (c < C) {
+    const long long P = (long long)N * H * W;
+    for (long long p = lane; p < P; p += kColLanes) {
+      const int xx = (int)(p % W), yy = (int)((p / W) % H);
+      const long long n = p / ((long long)W * H);
+      const double g = (double)__ldg(dy + p * C + c);
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int yi = yy + (kh - 1) * dil;
+        if (yi < 0 || yi >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int xi = xx + (kw - 1) * dil;
+          if (xi < 0 || xi >= W) continue;
+          float v = __ldg(x + ((n * H + yi) * W + xi) * C + c);
+          if (relu_in) v = fmaxf(v, 0.f);
+          acc[kh * 3 + kw] += (double)v * g;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {  // one tap at a time through the same 8 KB of shared memory
+    s[lane][cl] = acc[k];
+    __syncthreads();
+    if (lane == 0 && c < C) {
+      double t = 0.0;
+      for (int l = 0; l < kColLanes; ++l) t += s[l][cl];
+      dw[(long long)k * C + c] += (float)t;
+    }
+    __syncthreads();
+  }
+}
+
 unsigned blocks256(long long total) {
   long long b = (total + 255) / 256;
   const long long cap = (long long)kNumSMs * 32;
@@ -222,4 +268,13 @@ extern "C" int xdet_maxpool3x3s2_bwd_f32(const unsigned char* d_argmax, const fl
   maxpool_bwd_f32_kernel<<<blocks256(total), 256, 0, (cudaStream_t)stream>>>(d_argmax, d_dy, d_dx, H, W, C, Ho, Wo,
                                                                             pad_top, pad_left, total);
   return after_launch("maxpool_bwd_f32_kernel");
+}
+
+extern "C" int xdet_depthwise3x3_wgrad_f32(const float* d_x, const float* d_dy, float* d_dw, int N, int H, int W, int C,
+                                           int dilation, int relu_in, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0) return fail(XDET_EINVAL, "depthwise3x3_wgrad_f32: non-positive dimension");
+  if (dilation != 1 && dilation != 2) return fail(XDET_EINVAL, "depthwise3x3_wgrad_f32: dilation must be 1 or 2");
+  depthwise_wgrad_f32_kernel<<<(C + kColCh - 1) / kColCh, kColCh * kColLanes, 0, (cudaStream_t)stream>>>(
+      d_x, d_dy, d_dw, N, H, W, C, dilation, relu_in);
+  return after_launch("depthwise_wgrad_f32_kernel");
 }

@@ -58,7 +58,7 @@ _DEFAULTS = dict(
     # not a reference flag: 'bf16' = the throughput path (bf16 activations / operands, fp32 accumulate and masters);
     # 'f16x2' = the fp32-ACCURATE training mode (fp32 activations and gradients, split-operand tensor-core
     # convolutions for forward / input gradient / weight gradient, fp32 batch-norm / pooling kernels): the mode in
-    # which the explicit backward is held to the autograd oracle at 1e-3 (ResNet-50 composition)
+    # which the explicit backward is held to float64 autograd (tests/test_train_step_gpu.py)
     precision='bf16',
 )
 # fp32-accurate mode: the backward runs on gradients scaled by 2^12 (exact) so that they sit inside fp16's range when
@@ -309,9 +309,6 @@ class LightHeadTrainer(object):
         self.precision = p.get('precision', 'bf16')
         if self.precision not in ('bf16', 'f16x2'):
             raise ValueError("precision must be 'bf16' or 'f16x2'")
-        if self.precision == 'f16x2' and self.xception:
-            raise NotImplementedError("the fp32-accurate training mode is built for the ResNet-50 composition "
-                                      "(BASELINE config 4); XceptionBody trains in bf16")
         self.f32 = self.precision == 'f16x2'
         self.device = torch.device(device)
         self.store = store = VariableStore(device=device, seed=seed, state_dict=state_dict)

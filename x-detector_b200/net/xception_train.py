@@ -30,25 +30,27 @@ def depthwise3x3_wgrad(x, dy, dilation, relu_in):
     lib = _native.lib()
     N, H, W, C = x.shape
     dw = torch.zeros((9, C), dtype=torch.float32, device=x.device)
-    _native.check(lib.xdet_depthwise3x3_wgrad_bf16(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W, C, dilation,
-                                                   1 if relu_in else 0, _st()))
+    fn = lib.xdet_depthwise3x3_wgrad_f32 if x.dtype == torch.float32 else lib.xdet_depthwise3x3_wgrad_bf16
+    assert x.dtype == dy.dtype and x.is_contiguous() and dy.is_contiguous()
+    _native.check(fn(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W, C, dilation, 1 if relu_in else 0, _st()))
     return dw
 
 
 BN_MOMENTUM = 0.99
 
 
+def _image_nhwc(images):
+    """fp32 NCHW image -> the NHWC tensor the first convolution reads: bf16 rows of 8 channels, or (fp32-accurate mode)
+    fp32 NHWC as it is."""
+    if ops.conv.PRECISION == "f16x2":
+        return images.permute(0, 2, 3, 1).contiguous()
+    return T.nchw_f32_to_nhwc_bf16(images.contiguous(), pitch=8)
+
+
 def bn_relu_bwd_into(dy, x, st, relu, grad_view):
     """xdet_bn_relu_bwd_bf16 with its column sums written straight into ``grad_view`` ([0,C) = dbeta, [C,2C) = dgamma:
     the (beta, gamma) order of the trainer's VecParam)."""
-    cs = x.shape[-1]
-    assert dy.shape == x.shape and dy.is_contiguous() and grad_view.numel() == 2 * cs
-    dx = torch.empty_like(x)
-    _native.check(_native.lib().xdet_bn_relu_bwd_bf16(dy.data_ptr(), x.data_ptr(), st.scale.data_ptr(),
-                                                      st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
-                                                      st.rows, cs, 1 if relu else 0, None, grad_view.data_ptr(),
-                                                      dx.data_ptr(), _st()))
-    return dx
+    return T.bn_relu_bwd_into(dy, x, st, relu, grad_view)
 
 
 class Conv(object):
@@ -115,7 +117,7 @@ class Depthwise(object):
         else:
             grads[self.name + "/depthwise_kernel"] = dw.reshape(3, 3, self.C, 1)
         # tap (kh,kw) -> (2-kh,2-kw); flipped per call: w9 may be a view of a master the optimizer updates
-        da = ops.depthwise3x3(dy, self.w9.flip(0).contiguous(), dilation=self.dil, relu_in=False)
+        da = ops.depthwise3x3(dy, self.w9.flip(0).contiguous(), dilation=self.dil, relu_in=False, forms="f32")
         return T.relu_bwd(da, self.x) if self.relu_in else da
 
 
@@ -196,7 +198,7 @@ class XceptionBodyTraining(object):
                     SepBN(v, "block14_sepconv2", dil=2, relu_in=False, relu_out=True)]
 
     def fwd(self, images):
-        x = T.nchw_f32_to_nhwc_bf16(images.contiguous(), pitch=8)   # 3 channels in rows of 8 (generic strided conv)
+        x = _image_nhwc(images)   # 3 channels in rows of 8 (generic strided conv)
         x = self.b1c2.fwd(self.b1c1.fwd(x))
         for res, s1, s2, pool in self.entry:
             x = pool.fwd(s2.fwd(s1.fwd(x))) + res.fwd(x)
@@ -288,7 +290,7 @@ class TrainableXceptionBody(XceptionBodyTraining):
 
     # ---- forward, split at the RPN feature -------------------------------------------------------------------
     def fwd_mid(self, images):
-        x = T.nchw_f32_to_nhwc_bf16(images.contiguous(), pitch=8)
+        x = _image_nhwc(images)
         x = self.b1c2.fwd(self.b1c1.fwd(x))
         for res, s1, s2, pool in self.entry:
             x = pool.fwd(s2.fwd(s1.fwd(x))) + res.fwd(x)
