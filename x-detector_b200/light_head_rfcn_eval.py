@@ -39,8 +39,9 @@ _DEFAULTS = dict(
     # not a reference flag: which backbone builder to use ('xception' = the reference's XceptionBody,
     # 'resnet50' = the ResNet-50 v2 light-head composition of BASELINE configs 2/4)
     backbone='resnet50',
-    # not a reference flag: 'bf16' = the throughput path; 'fp32x3' = parity mode (fp32 activations, split-operand
-    # tensor-core convolutions with fp32-level error, ~8x slower; see ops/conv.py and csrc/parity_ops.cu)
+    # not a reference flag: 'f16x2' = the reference's precision (fp32 activations, split-operand tensor-core
+    # convolutions with fp32-level error: within 1e-4 of the fp32 graph end to end; csrc/conv_gemm_f16x2.cu) -- what
+    # bench.py reports; 'bf16' = the fast mode (~1e-2 per stage, 2.2x faster); 'fp32x3' = round 1's parity mode (tests)
     precision='bf16',
 )
 FLAGS = types.SimpleNamespace(**_DEFAULTS)
