@@ -84,7 +84,7 @@ def test_flag_names_and_defaults_match_reference_scripts():
     from xdet_b200 import light_head_rfcn_train as pt
     with open(os.path.join(os.path.dirname(__file__), "golden", "flags_golden.json")) as f:
         gold = json.load(f)
-    for which, mod, extras in (("train", pt, {"backbone", "resnet_layers"}), ("eval", pe, {"backbone", "precision"})):
+    for which, mod, extras in (("train", pt, {"backbone", "resnet_layers", "precision"}), ("eval", pe, {"backbone", "precision"})):
         mine, ref = mod.make_params(), gold[which]
         assert set(mine) - set(ref) == extras, (which, sorted(set(mine) - set(ref)))
         assert set(ref) - set(mine) == set(), (which, sorted(set(ref) - set(mine)))

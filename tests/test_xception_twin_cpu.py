@@ -75,7 +75,7 @@ def fake_conv2d_wgrad(x, dy, kh, kw, *, dilation=(1, 1), padding="SAME", strides
     dw[:, :, :cin] += g.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin).float()
 
 
-def fake_depthwise3x3(x, w9, dilation=1, relu_in=False):
+def fake_depthwise3x3(x, w9, dilation=1, relu_in=False, forms=None):
     assert x.dtype == BF and x.is_contiguous() and w9.shape == (9, x.shape[-1]) and w9.dtype == torch.float32
     a = nchw(x)
     a = torch.relu(a) if relu_in else a
