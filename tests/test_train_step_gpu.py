@@ -259,3 +259,54 @@ def test_fp32_accurate_mode_meets_the_c4_tolerance(layers):
         # this graph (median and worst case within 2x of the fp32 CPU autograd oracle's own distance).
         assert np.median(errs) < 2.0 * np.median(errs32) + 1e-4, (np.median(errs), np.median(errs32))
         assert worst[0][0] < 2.0 * worst32[0][0] + 1e-3, (worst[:3], worst32[:3])
+
+
+# ---- the reference's training call sites, replayed through the reference-named builders ---------------------------
+@pytest.mark.parametrize("backbone", ["xception", "resnet50"])
+def test_reference_named_builders_in_training_mode(backbone):
+    """light_head_rfcn_train.py:289-407 call by call: XceptionBody / get_rpn / large_sep_kernel / get_proposals(encode_fn)
+    / get_head(loss_func, using_ohem) with is_training=True (``store`` = the trainer), then minimize.  Same losses and
+    gradients as ``LightHeadTrainer.step`` on the same batch and selections (fp32-accurate mode: its forward is
+    deterministic); channels_first callers get NCHW views."""
+    import xdet_b200  # noqa: F401
+    from xdet_b200 import light_head_rfcn_train as lt
+    from xdet_b200.net import resnet_v2, xception_body
+    params = lt.make_params(train_image_size=160, batch_size=2, rpn_pre_nms_top_n=600, rpn_post_nms_top_n=200,
+                            rpn_min_size=16.0 / 160, rpn_anchors_per_image=64, roi_one_image=32, ohem_roi_one_image=16,
+                            resnet_layers=(1, 1, 1, 1), backbone=backbone, precision="f16x2")
+    tr = lt.LightHeadTrainer(params, seed=11)
+    images, gt, gl, keys = lt.synthetic_batch(params, 2, seed=5)
+    want = tr.step(images, gt, gl, keys, apply_update=False)
+    torch.cuda.synchronize()
+    want_grads = tr.grads.clone()
+    inj = {k: want[k] for k in ("rpn_idx", "rois_all", "roi_idx", "ohem_idx")}
+    from xdet_b200.ops import conv as conv_ops
+    with conv_ops.precision("f16x2"):
+        tr.begin_step(images, gt, gl, keys, inject=inj)           # the Estimator feeding (features, labels)
+        df = "channels_first"                                     # the reference's default flag (train:93)
+        if backbone == "xception":
+            rpn_feat_map, backbone_feat = xception_body.XceptionBody(images, 21, True, df, store=tr)           # :289
+        else:
+            rpn_feat_map, backbone_feat = resnet_v2.lighthead_resnet50_body(images, True, tr)
+        rpn_out = xception_body.get_rpn(rpn_feat_map, tr.A, True, df, 'rpn_head', store=tr)                     # :291
+        thin = xception_body.large_sep_kernel(backbone_feat, 256, 10 * 7 * 7, True, df, 'large_sep_feature', store=tr)  # :293
+        rpn_ce, rpn_loc = tr.fwd_rpn_losses()                                                                    # :295-378
+        rois, targets, labels, scores = xception_body.get_proposals(
+            tr.t.score, tr.t.boxes, None, params['rpn_pre_nms_top_n'], params['rpn_post_nms_top_n'], params['rpn_nms_thres'],
+            params['rpn_min_size'], True, df, store=tr)                                                         # :381
+        cls_score, bboxes_reg = xception_body.get_head(thin, None, 7, 7, None, rois, 21, True, True,
+                                                       params['ohem_roi_one_image'], df, 'final_head', store=tr)  # :404
+        tr.backward()
+        tr.apply_gradients(apply_update=False)                                                                   # :436-441
+    torch.cuda.synchronize()
+    if backbone == "xception":
+        assert rpn_feat_map.shape[1] == 728 and backbone_feat.shape[1] == 2048      # NCHW views for channels_first
+    assert thin.shape[1] == 490 and rois.shape == (2, 32, 4) and targets.shape == (2, 32, 4) and labels.shape == (2, 32)
+    assert cls_score.shape[1] == 21 and bboxes_reg.shape[1] == 4 and rpn_out.shape[-1] == 6 * tr.A
+    assert float(rpn_ce) == float(want["rpn_cross_entropy_loss"]) and float(rpn_loc) == float(want["rpn_location_loss"])
+    assert float(tr.t.head_loss) == float(want["head_loss"])
+    assert torch.equal(labels, want["roi_labels"]) and torch.equal(rois, want["rois"])
+    rel = float((tr.grads - want_grads).abs().max() / want_grads.abs().max())
+    assert rel < 1e-5, rel   # (weight-gradient pixel splits meet in fp32 atomics: last bits only)
+    with pytest.raises(TypeError):
+        xception_body.get_rpn(rpn_feat_map, tr.A, True, df, 'rpn_head', store=tr.store)   # a VariableStore cannot train

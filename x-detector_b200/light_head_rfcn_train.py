@@ -375,7 +375,7 @@ class LightHeadTrainer(object):
         """The buckets not sent yet (all of them without overlap), then JOIN the communication stream."""
         world = self._world()
         if world > 1:
-            if self.overlap_allreduce:
+            if self.overlap_allreduce and self._pending is not None:
                 for bname, a, b in self.buckets:
                     if bname in self._pending:
                         self._stage_done(bname)
@@ -646,18 +646,55 @@ class LightHeadTrainer(object):
             return self._step(images, gt_boxes, gt_labels, keys, apply_update, inject)
 
     def _step(self, images, gt_boxes, gt_labels, keys, apply_update, inject):
-        p, nc, A = self.params, self.params['num_classes'], self.A
-        inject = inject or {}
-        N = images.shape[0]
-        fm = self.fmap
+        """The step = the pieces below in the order (and on the streams) the trainer wants them.  The reference-named
+        builders (net/xception_body.py with is_training=True) call the same pieces one by one on ONE stream."""
+        self.begin_step(images, gt_boxes, gt_labels, keys, inject)
+        t = self.t
+        rpn_feat = self.fwd_backbone_mid()
+        self.fwd_rpn(rpn_feat)
+        # FORK: RPN losses, proposals and RoI targets on a second stream (the reference pins proposals /
+        # ext_encode_rois to /cpu:0; here they run beside block_layer4 / the exit flow + large_sep_kernel, whose
+        # convolutions leave a few SMs to the one-CTA-per-image kernels meanwhile)
+        main = torch.cuda.current_stream()
+        side = self.side
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self.fwd_rpn_losses()
+            self.fwd_proposals_and_targets()
+        conv_ops.MAX_CTAS = 148 - 12
+        try:
+            backbone = self.fwd_backbone_exit()
+            self.fwd_thin(backbone)
+        finally:
+            conv_ops.MAX_CTAS = 0
+        main.wait_stream(side)  # JOIN
+        for t_ in (t.score, t.boxes, t.glabels, t.gtargets, t.rpn_idx, t.d_rpn, t.rois_all, t.rlab, t.rtgt, t.rsc,
+                   t.roi_idx, t.rois, t.roi_tgt, t.roi_lab, t.yxhw, t.rpn_ce, t.rpn_loc):
+            t_.record_stream(main)
+        self.fwd_head()
+        self.backward()
+        self.apply_gradients(apply_update)
+        return self.outputs()
+
+    # ---- the pieces -------------------------------------------------------------------------------------------
+    def begin_step(self, images, gt_boxes, gt_labels, keys, inject=None):
+        """Start a step: zero the flat gradient buffer, open the tape ``self.t``."""
+        p = self.params
+        t = self.t = types.SimpleNamespace()
+        t.images, t.gt_boxes, t.gt_labels, t.keys, t.inject = images, gt_boxes, gt_labels, keys, (inject or {})
+        t.N = images.shape[0]
         # fp32-accurate mode: the backward carries gradients scaled by S (see _LOSS_SCALE); act = activation dtype
-        S = _LOSS_SCALE if self.f32 else 1.0
-        act = torch.float32 if self.f32 else torch.bfloat16
+        t.S = _LOSS_SCALE if self.f32 else 1.0
+        t.act = torch.float32 if self.f32 else torch.bfloat16
         self.grads.zero_()
+        # (fp32-accurate mode: the buffer is rescaled before it is sent, so its buckets go out together at the end)
+        self._pending = set(n for n, _, _ in self.buckets) if (self._world() > 1 and not self.f32) else None
+        del p
 
-        self._pending = set(n for n, _, _ in self.buckets) if self._world() > 1 else None
-
-        # ---------------- forward: backbone ----------------
+    def fwd_backbone_mid(self):
+        """Backbone up to the RPN feature (XceptionBody's middle flow / block_layer1-3 + batch_norm_relu)."""
+        t = self.t
+        images = t.images
         if self.xception:
             rpn_feat = self.body.fwd_mid(images)
             fm = rpn_feat.shape[1]
@@ -675,113 +712,136 @@ class LightHeadTrainer(object):
             self.stem.x = x8
             y0 = ops.conv2d_nhwc(x8, self.stem.p.pack, 64, 7, 7, padding=(3, 3, Ho, Wo), strides=(2, 2), cin=3,
                                  fold_w=(Wimg, 3))
-            x, pool_arg = T.maxpool3x3s2_fwd_train(y0)
+            x, t.pool_arg = T.maxpool3x3s2_fwd_train(y0)
             for li in range(3):
                 for blk in self.layers[li]:
                     x = blk.fwd(x)
-            x3 = x
-            rpn_feat = self.bn_rpn.fwd(x3)
-        r = self.rpn_conv.fwd(rpn_feat, relu=True)
-        rpn_out = self.rpn_out.fwd(r, out_layout="nhwc_f32")  # [N,fm,fm,6A]: logits [0,2A), deltas [2A,6A)
+            t.x3, t.x8, t.y0_hw, t.stem_geom = x, x8, tuple(y0.shape[1:3]), (Ho, Wo, Wimg)
+            rpn_feat = self.bn_rpn.fwd(x)
+        t.rpn_feat = rpn_feat
+        return rpn_feat
 
-        # ---------------- FORK: RPN losses, proposals and RoI targets on a second stream -----------------------
-        # (the reference pins proposals / ext_encode_rois to /cpu:0; here they run beside block_layer4 +
-        # large_sep_kernel, whose convolutions leave a few SMs to the one-CTA-per-image kernels meanwhile)
-        main = torch.cuda.current_stream()
-        side = self.side
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            score, boxes = ops.rpn_decode(rpn_out, 0, 2 * A, self.enc.device_anchors(0), A)
-            glabels, gtargets, gscores = T.match_encode(self.anchors_pt, gt_boxes, gt_labels, 0.0,
-                                                        p['rpn_match_threshold'], p['rpn_neg_threshold'],
-                                                        ref_yxhw=self.anchors_yxhw)
-            n_rpn = N * p['rpn_anchors_per_image']
-            exp_fg = int(round(n_rpn * p['rpn_fg_ratio']))
-            if 'rpn_idx' in inject:
-                rpn_idx = inject['rpn_idx']
-            else:
-                rpn_idx, _ = T.sample_fg_bg(glabels.reshape(1, -1), None, 0.0, exp_fg, n_rpn, keys['rpn_fg'],
-                                            keys['rpn_bg'], keys['rpn_up'])
-                rpn_idx = rpn_idx.reshape(-1).long()
-            cls_all = rpn_out[..., :2 * A].reshape(-1, 2)   # plumbing: [N*A_tot, 2] copies of the two channel groups
-            loc_all = rpn_out[..., 2 * A:].reshape(-1, 4)
-            s_cls, s_loc = cls_all.index_select(0, rpn_idx), loc_all.index_select(0, rpn_idx)
-            s_lab = (glabels.reshape(-1).index_select(0, rpn_idx) > 0).to(torch.int32)
-            s_tgt = gtargets.reshape(-1, 4).index_select(0, rpn_idx).contiguous()
-            rpn_ce_rows, d_s_cls = T.softmax_ce(s_cls, s_lab, 2, w_all=S / n_rpn)
-            posm = s_lab.float()
-            npos = posm.sum().clamp(min=1.0)
-            row_w = posm / (npos * p['rpn_fg_ratio'])
-            rpn_l1_rows, d_s_loc = T.smooth_l1(s_loc, s_tgt, row_w=row_w, w_all=S)
-            # (w_all weights the GRADIENT only: the loss rows are unscaled)
-            rpn_ce, rpn_loc = rpn_ce_rows.mean(), rpn_l1_rows.sum()
-            # gradient of the RPN losses w.r.t. the head output, scattered back to the dense [N,fm,fm,6A] tensor
-            d_cls = torch.zeros_like(cls_all).index_add_(0, rpn_idx, d_s_cls)
-            d_loc = torch.zeros_like(loc_all).index_add_(0, rpn_idx, d_s_loc)
-            cpitch = (6 * A + 7) // 8 * 8
-            d_rpn = torch.zeros((N, fm, fm, cpitch), dtype=act, device=self.device)
-            d_rpn[..., :2 * A] = d_cls.reshape(N, fm, fm, 2 * A)
-            d_rpn[..., 2 * A:6 * A] = d_loc.reshape(N, fm, fm, 4 * A)
+    def fwd_rpn(self, rpn_feat):
+        """get_rpn (net/xception_body.py:381-400): -> [N,fm,fm,6A] fp32, logits [0,2A), deltas [2A,6A)."""
+        t = self.t
+        t.r = self.rpn_conv.fwd(rpn_feat, relu=True)
+        t.rpn_out = self.rpn_out.fwd(t.r, out_layout="nhwc_f32")
+        return t.rpn_out
 
-            # proposals + RoI targets
-            if 'rois_all' in inject:
-                rois_all = inject['rois_all']
-            else:
-                props, _, _ = ops.rpn_select(score, boxes, p['rpn_pre_nms_top_n'], p['rpn_post_nms_top_n'],
-                                             p['rpn_nms_thres'], p['rpn_min_size'], keys['prop'])
-                rois_all = torch.cat([props, gt_boxes * (gt_labels > 0).unsqueeze(-1).float()], dim=1).contiguous()
-            rlab, rtgt, rsc = T.match_encode(rois_all, gt_boxes, gt_labels, 0.1, p['match_threshold'],
-                                             p['neg_threshold_high'])
-            # the reference appends only the VALID ground-truth boxes (tf.boolean_mask, anchor_manipulator.py:345-347);
-            # here the padded slots ride along as zero boxes: mark them 'ignore' so that no threshold setting can ever
-            # sample them (with neg_threshold_low < 0 they would qualify as background)
-            G = gt_labels.shape[1]
-            rlab[:, rlab.shape[1] - G:].masked_fill_(gt_labels <= 0, -1)
-            R = p['roi_one_image']
-            if 'roi_idx' in inject:
-                roi_idx = inject['roi_idx']
-            else:
-                roi_idx, _ = T.sample_fg_bg(rlab, rsc, p['neg_threshold_low'], int(round(R * p['fg_ratio'])), R,
-                                            keys['roi_fg'], keys['roi_bg'], keys['roi_up'])
-                roi_idx = roi_idx.long()
-            rois = torch.gather(rois_all, 1, roi_idx.unsqueeze(-1).expand(N, R, 4)).contiguous()
-            roi_tgt = torch.gather(rtgt, 1, roi_idx.unsqueeze(-1).expand(N, R, 4)).contiguous()
-            roi_lab = torch.gather(rlab, 1, roi_idx).contiguous()
-            h_, w_ = rois[..., 2] - rois[..., 0], rois[..., 3] - rois[..., 1]
-            yxhw = torch.stack([rois[..., 0] + h_ / 2., rois[..., 1] + w_ / 2., h_, w_], dim=-1).contiguous()  # _point2center
+    def fwd_rpn_losses(self):
+        """Objectness / decode (train:295-319), anchor targets, select_samples (:321-358), the two RPN losses
+        (:361-378) and their gradient with respect to the RPN head's output."""
+        t, p, A = self.t, self.params, self.A
+        N, fm, S, inject, keys = t.N, self.fmap, t.S, t.inject, t.keys
+        rpn_out = t.rpn_out
+        t.score, t.boxes = ops.rpn_decode(rpn_out, 0, 2 * A, self.enc.device_anchors(0), A)
+        t.glabels, t.gtargets, _ = T.match_encode(self.anchors_pt, t.gt_boxes, t.gt_labels, 0.0,
+                                                  p['rpn_match_threshold'], p['rpn_neg_threshold'],
+                                                  ref_yxhw=self.anchors_yxhw)
+        n_rpn = N * p['rpn_anchors_per_image']
+        exp_fg = int(round(n_rpn * p['rpn_fg_ratio']))
+        if 'rpn_idx' in inject:
+            rpn_idx = inject['rpn_idx']
+        else:
+            rpn_idx, _ = T.sample_fg_bg(t.glabels.reshape(1, -1), None, 0.0, exp_fg, n_rpn, keys['rpn_fg'],
+                                        keys['rpn_bg'], keys['rpn_up'])
+            rpn_idx = rpn_idx.reshape(-1).long()
+        cls_all = rpn_out[..., :2 * A].reshape(-1, 2)   # plumbing: [N*A_tot, 2] copies of the two channel groups
+        loc_all = rpn_out[..., 2 * A:].reshape(-1, 4)
+        s_cls, s_loc = cls_all.index_select(0, rpn_idx), loc_all.index_select(0, rpn_idx)
+        s_lab = (t.glabels.reshape(-1).index_select(0, rpn_idx) > 0).to(torch.int32)
+        s_tgt = t.gtargets.reshape(-1, 4).index_select(0, rpn_idx).contiguous()
+        # (w_all weights the GRADIENT only: the loss rows are unscaled)
+        rpn_ce_rows, d_s_cls = T.softmax_ce(s_cls, s_lab, 2, w_all=S / n_rpn)
+        posm = s_lab.float()
+        npos = posm.sum().clamp(min=1.0)
+        row_w = posm / (npos * p['rpn_fg_ratio'])
+        rpn_l1_rows, d_s_loc = T.smooth_l1(s_loc, s_tgt, row_w=row_w, w_all=S)
+        t.rpn_ce, t.rpn_loc, t.rpn_idx = rpn_ce_rows.mean(), rpn_l1_rows.sum(), rpn_idx
+        # gradient of the RPN losses w.r.t. the head output, scattered back to the dense [N,fm,fm,6A] tensor
+        d_cls = torch.zeros_like(cls_all).index_add_(0, rpn_idx, d_s_cls)
+        d_loc = torch.zeros_like(loc_all).index_add_(0, rpn_idx, d_s_loc)
+        cpitch = (6 * A + 7) // 8 * 8
+        d_rpn = torch.zeros((N, fm, fm, cpitch), dtype=t.act, device=self.device)
+        d_rpn[..., :2 * A] = d_cls.reshape(N, fm, fm, 2 * A)
+        d_rpn[..., 2 * A:6 * A] = d_loc.reshape(N, fm, fm, 4 * A)
+        t.d_rpn = d_rpn
+        return t.rpn_ce, t.rpn_loc
 
-        # ---------------- main stream meanwhile: block_layer4, thin feature map ----------------
-        conv_ops.MAX_CTAS = 148 - 12
-        try:
-            if self.xception:
-                backbone = self.body.fwd_exit()
-            else:
-                for blk in self.layers[3]:
-                    x = blk.fwd(x)
-                backbone = self.bn_final.fwd(x)
-            mid = self.sep_a.fwd(backbone)
-            bias_b = self.sep_b_biases[0] + self.sep_b_biases[1]
-            # 490 channels live in rows of 496 (16-byte pixel strides for TMA and the vector kernels), zero tail
-            o_buf = torch.zeros((N, fm, fm, 496), dtype=act, device=self.device)
-            self.sep_b.fwd(mid, bias_tensor=bias_b, out=o_buf[..., :490])
-        finally:
-            conv_ops.MAX_CTAS = 0
+    def fwd_proposals_and_targets(self):
+        """get_proposals in training mode (net/xception_body.py:402-448: clip, top-k, NMS, upsample) + its
+        ``encode_fn`` = ext_encode_rois (append the ground truth, match, sample roi_one_image RoIs per image)."""
+        t, p = self.t, self.params
+        N, inject, keys = t.N, t.inject, t.keys
+        gt_boxes, gt_labels = t.gt_boxes, t.gt_labels
+        if 'rois_all' in inject:
+            rois_all = inject['rois_all']
+        else:
+            props, _, _ = ops.rpn_select(t.score, t.boxes, p['rpn_pre_nms_top_n'], p['rpn_post_nms_top_n'],
+                                         p['rpn_nms_thres'], p['rpn_min_size'], keys['prop'])
+            rois_all = torch.cat([props, gt_boxes * (gt_labels > 0).unsqueeze(-1).float()], dim=1).contiguous()
+        rlab, rtgt, rsc = T.match_encode(rois_all, gt_boxes, gt_labels, 0.1, p['match_threshold'],
+                                         p['neg_threshold_high'])
+        # the reference appends only the VALID ground-truth boxes (tf.boolean_mask, anchor_manipulator.py:345-347);
+        # here the padded slots ride along as zero boxes: mark them 'ignore' so that no threshold setting can ever
+        # sample them (with neg_threshold_low < 0 they would qualify as background)
+        G = gt_labels.shape[1]
+        rlab[:, rlab.shape[1] - G:].masked_fill_(gt_labels <= 0, -1)
+        R = p['roi_one_image']
+        if 'roi_idx' in inject:
+            roi_idx = inject['roi_idx']
+        else:
+            roi_idx, _ = T.sample_fg_bg(rlab, rsc, p['neg_threshold_low'], int(round(R * p['fg_ratio'])), R,
+                                        keys['roi_fg'], keys['roi_bg'], keys['roi_up'])
+            roi_idx = roi_idx.long()
+        rois = torch.gather(rois_all, 1, roi_idx.unsqueeze(-1).expand(N, R, 4)).contiguous()
+        t.roi_tgt = torch.gather(rtgt, 1, roi_idx.unsqueeze(-1).expand(N, R, 4)).contiguous()
+        t.roi_lab = torch.gather(rlab, 1, roi_idx).contiguous()
+        t.roi_sc = torch.gather(rsc, 1, roi_idx).contiguous()
+        h_, w_ = rois[..., 2] - rois[..., 0], rois[..., 3] - rois[..., 1]
+        t.yxhw = torch.stack([rois[..., 0] + h_ / 2., rois[..., 1] + w_ / 2., h_, w_], dim=-1).contiguous()  # _point2center
+        t.rois_all, t.rlab, t.rtgt, t.rsc, t.roi_idx, t.rois = rois_all, rlab, rtgt, rsc, roi_idx, rois
+        return rois, t.roi_tgt, t.roi_lab, t.roi_sc
+
+    def fwd_backbone_exit(self):
+        """The rest of the backbone (XceptionBody's exit flow / block_layer4 + batch_norm_relu) -> [N,fm,fm,2048]."""
+        t = self.t
+        if self.xception:
+            t.backbone = self.body.fwd_exit()
+        else:
+            x = t.x3
+            for blk in self.layers[3]:
+                x = blk.fwd(x)
+            t.backbone = self.bn_final.fwd(x)
+        return t.backbone
+
+    def fwd_thin(self, backbone):
+        """large_sep_kernel (net/xception_body.py:450-475) with batch statistics -> thin feature map, fp32 NCHW."""
+        t = self.t
+        N, fm = t.N, self.fmap
+        mid = self.sep_a.fwd(backbone)
+        bias_b = self.sep_b_biases[0] + self.sep_b_biases[1]
+        # 490 channels live in rows of 496 (16-byte pixel strides for TMA and the vector kernels), zero tail
+        o_buf = torch.zeros((N, fm, fm, 496), dtype=t.act, device=self.device)
+        self.sep_b.fwd(mid, bias_tensor=bias_b, out=o_buf[..., :490])
         st_sep = self.bn_sep.stats(o_buf)
         if self.f32:  # (layout plumbing of the verification mode: NHWC -> the NCHW PsRoIAlign's contract asks for)
-            thin = torch.relu(o_buf[..., :490] * st_sep.scale[:490] + st_sep.shift[:490]).permute(0, 3, 1, 2).contiguous()
+            t.thin = torch.relu(o_buf[..., :490] * st_sep.scale[:490] + st_sep.shift[:490]).permute(0, 3, 1, 2).contiguous()
         else:
-            thin = T.affine_relu_to_nchw_f32(o_buf, st_sep.scale, st_sep.shift, relu=True, C=490)
-        main.wait_stream(side)  # JOIN
-        for t_ in (score, boxes, glabels, gtargets, rpn_idx, d_rpn, rois_all, rlab, rtgt, rsc, roi_idx, rois, roi_tgt,
-                   roi_lab, yxhw, rpn_ce, rpn_loc):
-            t_.record_stream(main)
+            t.thin = T.affine_relu_to_nchw_f32(o_buf, st_sep.scale, st_sep.shift, relu=True, C=490)
+        return t.thin
 
-        # ---------------- forward: PsRoIAlign + head with OHEM ----------------
-        pooled, pindex = ops.ps_roi_align(thin, yxhw, 7, 7, pool_method)
-        feat = pooled.reshape(N * R, -1)
+    def fwd_head(self):
+        """get_head (net/xception_body.py:477-560): PsRoIAlign, fc head, OHEM (no-grad pass, per-RoI loss, top-k,
+        the reference's axis-1 gather), the head loss and its gradient with respect to the head's output."""
+        t, p, nc = self.t, self.params, self.params['num_classes']
+        N, S, inject = t.N, t.S, t.inject
+        R = p['roi_one_image']
+        t.pooled, t.pindex = ops.ps_roi_align(t.thin, t.yxhw, 7, 7, pool_method)
+        feat = t.pooled.reshape(N * R, -1)
         cin = feat.shape[1]
         pitch = (cin + 7) // 8 * 8
-        lab_flat, tgt_flat = roi_lab.reshape(-1), roi_tgt.reshape(-1, 4)
+        lab_flat, tgt_flat = t.roi_lab.reshape(-1), t.roi_tgt.reshape(-1, 4)
         if p['using_ohem']:
             k = min(p['ohem_roi_one_image'], R)
             if 'ohem_idx' in inject:
@@ -793,31 +853,37 @@ class LightHeadTrainer(object):
             # tf.gather(x, select_indices, axis=1) with a [N,k] index: every image gets every image's rows
             flat_sel = (torch.arange(N, device=self.device).view(N, 1, 1) * R + sel.view(1, N, k)).reshape(-1)
             feat2 = feat.index_select(0, flat_sel)
-            lab2 = roi_lab.index_select(1, sel.reshape(-1)).reshape(-1).contiguous()
-            tgt2 = roi_tgt.index_select(1, sel.reshape(-1)).reshape(-1, 4).contiguous()
+            lab2 = t.roi_lab.index_select(1, sel.reshape(-1)).reshape(-1).contiguous()
+            tgt2 = t.roi_tgt.index_select(1, sel.reshape(-1)).reshape(-1, 4).contiguous()
         else:
             sel, flat_sel, feat2, lab2, tgt2 = None, None, feat, lab_flat, tgt_flat
         M2 = feat2.shape[0]
         a2 = self._rows(feat2, pitch)
-        h2, out2 = self._head_fwd(a2)
-        head_rows, dout2 = self._head_loss(out2, lab2, tgt2, S / M2)
-        head_loss = head_rows.mean()
+        t.h2, t.out2 = self._head_fwd(a2)
+        head_rows, t.dout2 = self._head_loss(t.out2, lab2, tgt2, S / M2)
+        t.head_loss = head_rows.mean()
+        t.sel, t.flat_sel, t.feat, t.M2, t.cin = sel, flat_sel, feat, M2, cin
+        return t.out2[:, :nc], t.out2[:, nc:], t.head_loss
 
-        # ================= backward =================
+    def backward(self):
+        """The explicit backward of everything above (TensorFlow: optimizer.compute_gradients, train:436-441)."""
+        t, nc = self.t, self.params['num_classes']
+        N, fm = t.N, self.fmap
         # ---- head ----
         dpitch = (nc + 4 + 7) // 8 * 8
         if self.f32:
-            d_out_b = torch.nn.functional.pad(dout2, (0, dpitch - dout2.shape[1])).reshape(1, 1, M2, dpitch)
+            d_out_b = torch.nn.functional.pad(t.dout2, (0, dpitch - t.dout2.shape[1])).reshape(1, 1, t.M2, dpitch)
         else:
-            d_out_b = ops.f32_to_bf16_rows(dout2, dpitch).reshape(1, 1, M2, dpitch)
+            d_out_b = ops.f32_to_bf16_rows(t.dout2, dpitch).reshape(1, 1, t.M2, dpitch)
         dh = self.fc2.bwd(d_out_b)
-        dh = T.relu_bwd(dh, h2)
-        dfeat2 = self.fc1.bwd(dh, dx_layout="nhwc_f32").reshape(M2, cin)
-        if flat_sel is not None:
-            dfeat = torch.zeros_like(feat).index_add_(0, flat_sel, dfeat2)
+        dh = T.relu_bwd(dh, t.h2)
+        dfeat2 = self.fc1.bwd(dh, dx_layout="nhwc_f32").reshape(t.M2, t.cin)
+        if t.flat_sel is not None:
+            dfeat = torch.zeros_like(t.feat).index_add_(0, t.flat_sel, dfeat2)
         else:
             dfeat = dfeat2
-        d_thin = ops.ps_roi_align_grad(thin, yxhw, dfeat.reshape(pooled.shape).contiguous(), pindex, 7, 7, pool_method)
+        d_thin = ops.ps_roi_align_grad(t.thin, t.yxhw, dfeat.reshape(t.pooled.shape).contiguous(), t.pindex, 7, 7,
+                                       pool_method)
         # ---- thin feature map ----
         if self.f32:
             d_o = torch.nn.functional.pad(d_thin.permute(0, 2, 3, 1), (0, 6)).contiguous()
@@ -829,7 +895,7 @@ class LightHeadTrainer(object):
         dmid = self.sep_b.bwd(do)
         dbackbone = self.sep_a.bwd(dmid)
         # ---- RPN head ----
-        dr = T.relu_bwd(self.rpn_out.bwd(d_rpn), r)
+        dr = T.relu_bwd(self.rpn_out.bwd(t.d_rpn), t.r)
         d_rpn_feat = self.rpn_conv.bwd(dr)
         # ---- backbone (each stage's gradient bucket goes to the communication stream as soon as it is complete) ----
         if self.xception:
@@ -847,13 +913,16 @@ class LightHeadTrainer(object):
                     dx = blk.bwd(dx)
                 if li >= 2:
                     self._stage_done("layer%d" % (li + 1))
-            dy0 = T.maxpool3x3s2_bwd(pool_arg, dx, y0.shape[1:3])
-            ops.conv2d_wgrad(x8, dy0, 7, 7, padding=(3, 3, Ho, Wo), strides=(2, 2), cin=3, cout=64, dw=self.stem.p.dw,
+            Ho, Wo, Wimg = t.stem_geom
+            dy0 = T.maxpool3x3s2_bwd(t.pool_arg, dx, t.y0_hw)
+            ops.conv2d_wgrad(t.x8, dy0, 7, 7, padding=(3, 3, Ho, Wo), strides=(2, 2), cin=3, cout=64, dw=self.stem.p.dw,
                              fold_w=(Wimg, 3))
-
-        # ================= all-reduce (remaining buckets, join) + optimizer =================
         if self.f32:
-            self.grads.mul_(1.0 / S)  # exact: S is a power of two (fp32-accurate mode: no bucket has been sent yet)
+            self.grads.mul_(1.0 / t.S)  # exact: S is a power of two
+
+    def apply_gradients(self, apply_update=True):
+        """All-reduce (the buckets not sent yet, join) + MomentumOptimizer.apply_gradients with the L2 term folded in."""
+        p = self.params
         world = self._allreduce_finish()
         if apply_update:
             lr = learning_rate(p, self.global_step)
@@ -866,10 +935,14 @@ class LightHeadTrainer(object):
             T.sgd_momentum_vec(self.sep_b_bias_vec.grad, self.sep_b_biases[1], self.sep_b_bias_mom2, lr, p['momentum'],
                                p['weight_decay'], gs)
             self.global_step += 1
-        return {'rpn_cross_entropy_loss': rpn_ce, 'rpn_location_loss': rpn_loc, 'head_loss': head_loss,
-                'rpn_idx': rpn_idx, 'rois_all': rois_all, 'roi_idx': roi_idx, 'ohem_idx': sel,
-                'rois': rois, 'roi_labels': roi_lab, 'roi_targets': roi_tgt, 'glabels': glabels,
-                'rpn_out': rpn_out, 'large_sep_feature': thin}
+        return world
+
+    def outputs(self):
+        t = self.t
+        return {'rpn_cross_entropy_loss': t.rpn_ce, 'rpn_location_loss': t.rpn_loc, 'head_loss': t.head_loss,
+                'rpn_idx': t.rpn_idx, 'rois_all': t.rois_all, 'roi_idx': t.roi_idx, 'ohem_idx': t.sel,
+                'rois': t.rois, 'roi_labels': t.roi_lab, 'roi_targets': t.roi_tgt, 'glabels': t.glabels,
+                'rpn_out': t.rpn_out, 'large_sep_feature': t.thin}
 
 
 def synthetic_batch(params, batch, seed, device="cuda", max_gt=6):

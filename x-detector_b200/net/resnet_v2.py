@@ -215,7 +215,17 @@ def lighthead_resnet50_body(image_nchw_f32, is_training, store, layers=(3, 4, 6,
     -> (rpn_feature [N,h,w,1024], backbone_feature [N,h,w,2048]) NHWC bf16, both after batch_norm_relu.
     Every batch_norm_relu between layers is produced by the convolution (or pooling) kernel that writes its
     input; raw sums nobody else reads are never stored.  ``after_rpn_feat(rpn_feature)`` is called as soon as
-    the RPN feature exists (the model_fn launches the RPN head and forks the proposal stream there)."""
+    the RPN feature exists (the model_fn launches the RPN head and forks the proposal stream there).
+    ``is_training=True``: ``store`` = the trainer (see net/xception_body.py, "training mode")."""
+    if is_training:
+        from .xception_body import _trainer
+        tr = _trainer(store, "lighthead_resnet50_body")
+        if tr.xception:
+            raise ValueError("this trainer was built with backbone='xception'")
+        rpn_feat = tr.fwd_backbone_mid()
+        if after_rpn_feat is not None:
+            after_rpn_feat(rpn_feat)
+        return rpn_feat, tr.fwd_backbone_exit()
     df = "channels_last"
     x, pre = stem(image_nchw_f32, store, fuse_next=True, pooled_unused=True)
     # layers 2 and 3 start with a projection shortcut that reads relu(bn(x)): the raw x of layers 1 and 2 is unused

@@ -23,6 +23,31 @@ BN_EPSILON = 0.0001
 BN_MOMENTUM = 0.99
 
 
+# ---- training mode -----------------------------------------------------------------------------------------------
+# With is_training=True the builders below do what they do in the reference's training graph
+# (light_head_rfcn_train.py:289-407): they run their piece of the step in training mode (batch statistics, tape for the
+# explicit backward).  The object that owns the variables, the tape and the gradients is the trainer
+# (light_head_rfcn_train.LightHeadTrainer): pass it as ``store``, open the step with ``trainer.begin_step(images,
+# gt_boxes, gt_labels, keys)`` (the Estimator feeding features / labels), call the builders in the reference's order, and
+# finish with ``trainer.backward(); trainer.apply_gradients()`` (optimizer.minimize).  ``LightHeadTrainer.step`` is the
+# same pieces with the proposal work forked onto a second stream.
+def _trainer(store, what):
+    if store is None or not hasattr(store, "fwd_backbone_mid"):
+        raise TypeError("%s(is_training=True) needs the trainer (light_head_rfcn_train.LightHeadTrainer) as `store`: it "
+                        "owns the variables, the forward tape and the gradient buffer of the training graph" % what)
+    if getattr(store, "t", None) is None:
+        raise RuntimeError("%s(is_training=True): call trainer.begin_step(images, gt_boxes, gt_labels, keys) first" % what)
+    return store
+
+
+def _as_format(x_nhwc, data_format):
+    """Builders hand activations on as NHWC; 'channels_first' callers get the NCHW view of the same memory."""
+    if data_format == "channels_first":
+        return x_nhwc.permute(0, 3, 1, 2)
+    assert data_format == "channels_last", data_format
+    return x_nhwc
+
+
 def _conv_vars(store, cin, filters, kh, kw, init=None, use_bias=True):
     name = store.auto_name("conv2d")
     with store.scope(name):
@@ -85,8 +110,18 @@ def XceptionBody(input_image, num_classes, is_training=False, data_format='chann
     """Xception backbone at stride 16 with the last two separable convs atrous (reference :236-379).
     ``input_image``: fp32 NCHW [N,3,H,W] (what the input pipeline delivers).  Returns
     (mid_outputs [N,h,w,728], outputs [N,h,w,2048]) NHWC bf16, both ReLU'd as in the reference.
-    ``after_mid(mid_outputs)`` is called as soon as the RPN feature exists (the model_fn forks there)."""
-    assert data_format == "channels_last" and not is_training
+    ``after_mid(mid_outputs)`` is called as soon as the RPN feature exists (the model_fn forks there).
+    ``is_training=True`` (``store`` = the trainer): batch statistics, tape; both data formats."""
+    if is_training:
+        tr = _trainer(store, "XceptionBody")
+        if not tr.xception:
+            raise ValueError("this trainer was built with backbone=%r" % tr.params['backbone'])
+        assert input_image is tr.t.images or input_image.data_ptr() == tr.t.images.data_ptr()
+        mid = tr.fwd_backbone_mid()
+        if after_mid is not None:
+            after_mid(mid)
+        return _as_format(mid, data_format), _as_format(tr.fwd_backbone_exit(), data_format)
+    assert data_format == "channels_last"
     df = data_format
     # ---- entry flow: two VALID 3x3 convs (the first strided, on the 3-channel image: fold_w mode) ----
     k = _conv_named(store, "block1_conv1", input_image.shape[1], 32, 3)
@@ -148,7 +183,10 @@ def XceptionBody(input_image, num_classes, is_training=False, data_format='chann
 def get_rpn(net_input, num_anchors, is_training, data_format, var_scope, store=None):
     """3x3 SAME conv -> 512 + bias + ReLU, then two 1x1 convs -> 2A / 4A (+bias) (reference :381-400).
     Returns ONE fp32 NHWC tensor [N,h,w,6A]: class logits in channels [0,2A), box deltas in [2A,6A)
-    (``rpn_cls_score, rpn_bbox_pred`` are its two channel slices)."""
+    (``rpn_cls_score, rpn_bbox_pred`` are its two channel slices).  ``is_training=True``: ``store`` = the trainer."""
+    if is_training:
+        tr = _trainer(store, "get_rpn")
+        return tr.fwd_rpn(tr.t.rpn_feat)
     assert data_format == "channels_last"
     cin = net_input.shape[-1]
     with store.scope(var_scope):
@@ -164,11 +202,16 @@ def get_rpn(net_input, num_anchors, is_training, data_format, var_scope, store=N
 
 
 def get_proposals(object_score, bboxes_pred, encode_fn, rpn_pre_nms_top_n, rpn_post_nms_top_n, nms_threshold,
-                  rpn_min_size, is_training, data_format, shuffle_keys=None):
+                  rpn_min_size, is_training, data_format, shuffle_keys=None, store=None):
     """clip -> filter/top-k -> NMS -> upsample (reference :402-448), on the GPU instead of /cpu:0.
-    object_score [N,A], bboxes_pred [N,A,4].  Inference: returns the proposal boxes [N,post,4]."""
+    object_score [N,A], bboxes_pred [N,A,4].  Inference: returns the proposal boxes [N,post,4].
+    ``is_training=True`` (``store`` = the trainer): also the ``encode_fn`` step (ext_encode_rois with the trainer's
+    thresholds and shuffle keys) -> (proposals_bboxes, proposals_targets, proposals_labels, proposals_scores) (:445-448)."""
     if is_training:
-        raise NotImplementedError("proposal target assignment (ext_encode_rois) is not part of this build")
+        tr = _trainer(store, "get_proposals")
+        if not hasattr(tr.t, "score"):  # objectness / decode / RPN losses of the model_fn (train:295-378)
+            tr.fwd_rpn_losses()
+        return tr.fwd_proposals_and_targets()
     rois, _, _ = ops.rpn_select(object_score, bboxes_pred, rpn_pre_nms_top_n, rpn_post_nms_top_n, nms_threshold,
                                 rpn_min_size, shuffle_keys)
     return rois
@@ -176,8 +219,13 @@ def get_proposals(object_score, bboxes_pred, encode_fn, rpn_pre_nms_top_n, rpn_p
 
 def large_sep_kernel(net_input, depth_mid, depth_output, is_training, data_format, var_scope, store=None):
     """Two branches of (15x1 conv -> depth_mid, 1x15 conv -> depth_output), summed, batch_norm_relu
-    (reference :450-475).  Returns the thin feature map as fp32 NCHW [N,depth_output,h,w]."""
-    assert data_format == "channels_last" and not is_training
+    (reference :450-475).  Returns the thin feature map as fp32 NCHW [N,depth_output,h,w].
+    ``is_training=True``: ``store`` = the trainer (batch statistics for the trailing batch_norm_relu)."""
+    if is_training:
+        tr = _trainer(store, "large_sep_kernel")
+        assert depth_mid == 256 and depth_output == 490, "the trainer is built for the reference's 256 / 10*7*7"
+        return tr.fwd_thin(tr.t.backbone)
+    assert data_format == "channels_last"
     cin = net_input.shape[-1]
     with store.scope(var_scope):
         with store.scope("Branch_0"):
@@ -210,9 +258,16 @@ def get_head(net_input, pooling_op, grid_width, grid_height, loss_func, proposal
              return_fused=False):
     """PS-RoI pooling + fc 2048 (ReLU) + fc_cls / fc_loc (reference :477-560), inference branch.
     net_input: thin feature map, fp32 NCHW (PsRoiAlign's contract).  Returns (cls_score [N,R,num_classes],
-    bboxes_reg [N,R,4]) fp32."""
+    bboxes_reg [N,R,4]) fp32.  ``is_training=True`` (``store`` = the trainer): the training branch with OHEM
+    (:504-533: no-grad pass, per-RoI loss, top-k, the axis-1 gather) -> (cls_score, bboxes_reg) of the selected rows; the
+    head loss (``loss_func`` of the reference = head_loss_func, train:381-399) is ``trainer.t.head_loss``."""
     if is_training or using_ohem:
-        raise NotImplementedError("training / OHEM branch of get_head is not part of this build")
+        tr = _trainer(store, "get_head")
+        if bool(using_ohem) != bool(tr.params['using_ohem']) or (using_ohem and ohem_roi_one_image !=
+                                                                    tr.params['ohem_roi_one_image']):
+            raise ValueError("using_ohem / ohem_roi_one_image differ from the trainer's parameters")
+        cls_score, bboxes_reg, _ = tr.fwd_head()
+        return cls_score, bboxes_reg
     if yxhw_bboxes is None:
         yxhw_bboxes = _point2center(proposals_bboxes)  # fp32 elementwise, same op order as the reference
     psroipooled_rois, _ = pooling_op(net_input, yxhw_bboxes.contiguous(), grid_width, grid_height)
