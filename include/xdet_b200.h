@@ -300,6 +300,8 @@ typedef struct {
   int block_n;  /* 0 = auto; 32, 64 or 128 */
   int chunk_kb; /* 0 = 2: k-blocks (of 64 reduction elements) per accumulator flush */
   int max_ctas;
+  int cluster;  /* 2 = clusters of two CTAs work on two M tiles of one N tile and multicast each other half of the B
+                   tiles (a quarter less operand traffic L2 -> SM); 0 / 1 = independent CTAs */
 } xdet_conv_f16x2_desc;
 int xdet_conv2d_f16x2(const void* d_in_pair, const xdet_conv_f16x2_desc* desc, void* stream);
 /* fp32 (element (n,y,x,c) at n*sn + y*sy + x*sx + c*sc) -> f16x2 planes [2][N,H,Wp,cs]: pixel (n,y,x) is written at

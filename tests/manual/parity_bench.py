@@ -58,13 +58,19 @@ def main():
     ap.add_argument("--no-time", action="store_true")
     ap.add_argument("--out", default=None)
     ap.add_argument("--chunk-kb", type=int, default=0)
+    ap.add_argument("--cluster", type=int, default=1, help="f16x2: 1 = independent CTAs, 2 = 2-CTA clusters everywhere, "
+                    "0 = let the tuner pick per layer (with --autotune)")
+    ap.add_argument("--autotune", action="store_true")
     args = ap.parse_args()
     from xdet_b200.ops import conv as conv_ops
     conv_ops.F16X2_CHUNK_KB = args.chunk_kb
+    conv_ops.F16X2_CLUSTER = args.cluster
+    conv_ops.AUTOTUNE = args.autotune
     params = lh.make_params(train_image_size=args.size, backbone=args.backbone, rpn_min_size=16.0 / args.size,
                             precision=args.precision)
     model = lh.LightHeadRFCN(params, seed=0)
-    rec = {"precision": args.precision, "backbone": args.backbone, "size": args.size}
+    rec = {"precision": args.precision, "backbone": args.backbone, "size": args.size, "cluster": args.cluster,
+           "autotune": args.autotune}
     rng = np.random.default_rng(1)
     imgs = (rng.random((max(args.batch, args.parity_batch), 3, args.size, args.size), dtype=np.float32) * 2 - 1)
     if not args.no_parity:

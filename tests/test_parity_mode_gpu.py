@@ -175,6 +175,42 @@ def test_conv_f16x2_vs_fp64(xd, case):
         assert torch.equal(out2._pair, xd.split2(out2))
 
 
+@pytest.mark.parametrize("case", [
+    dict(n=2, h=21, w=19, cin=64, cout=96, k=3, bn=0),      # 12 M tiles
+    dict(n=1, h=9, w=30, cin=256, cout=256, k=3, bn=128),   # 3 M tiles (odd: the phantom tile of the last pair)
+    dict(n=2, h=30, w=30, cin=1024, cout=256, k=1, bn=128), # flattened 1x1: 15 M tiles, 2 N tiles
+    dict(n=1, h=40, w=40, cin=64, cout=64, k=1, bn=64),
+    dict(n=1, h=12, w=12, cin=128, cout=25, k=1, bn=32),
+])
+def test_conv_f16x2_cluster_mode_is_bit_identical(xd, case):
+    """2-CTA clusters that multicast each other half of the B tiles compute the same products in the same order as
+    independent CTAs: every output (values, second output, split planes) is bit-identical."""
+    from xdet_b200.ops import conv as conv_ops
+    g = torch.Generator(device="cuda").manual_seed(case["cin"] + case["cout"] + case["h"])
+    n, h, w, cin, cout, k = (case[key] for key in ("n", "h", "w", "cin", "cout", "k"))
+    x = torch.randn((n, h, w, cin), generator=g, device="cuda")
+    wt = torch.randn((cout, cin, k, k), generator=g, device="cuda") / (cin * k * k) ** 0.5
+    sc, bi = torch.rand(cout, generator=g, device="cuda") + 0.5, torch.randn(cout, generator=g, device="cuda")
+    s2, b2 = torch.rand(cout, generator=g, device="cuda") + 0.5, torch.randn(cout, generator=g, device="cuda")
+    res = torch.randn((n, h, w, cout), generator=g, device="cuda")
+    outs = []
+    for cl in (1, 2):
+        conv_ops.F16X2_CLUSTER = cl
+        try:
+            with xd.precision("f16x2"):
+                y, y2 = xd.conv2d_nhwc(x, xd.pack_conv_weight(wt), cout, k, k, scale=sc, bias=bi, relu=True, residual=res,
+                                       out2=True, scale2=s2, bias2=b2, block_n=case["bn"])
+            torch.cuda.synchronize()
+        finally:
+            conv_ops.F16X2_CLUSTER = 1
+        outs.append((y, y2))
+    (a, a2), (b, b2_) = outs
+    assert torch.equal(a, b) and torch.equal(a2, b2_)
+    assert torch.equal(a._pair[..., :cout], b._pair[..., :cout]) and torch.equal(a2._pair[..., :cout], b2_._pair[..., :cout])
+    ref = _conv_ref64(x, wt, k, 1, 1, sc, bi, res)
+    assert (b.double().cpu() - ref).abs().max().item() < 2e-6 * max(1.0, ref.abs().max().item())
+
+
 def test_conv_f16x2_layouts_and_stem(xd):
     g = torch.Generator(device="cuda").manual_seed(11)
     with xd.precision("f16x2"):

@@ -69,6 +69,7 @@ struct PairArgs {
   const float* scale2;
   const float* bias2;
   __half* out2_pair;
+  int m_tiles, total_pairs;  // cluster mode: tiles are dealt in pairs of M tiles that share one B tile
   int vec_ok;      // fp32 rows: 2 = 32-byte aligned (256-bit accesses), 1 = 16-byte aligned, 0 = scalar / strided
   int pair_vec32;  // plane rows are 32-byte aligned
 };
@@ -86,6 +87,16 @@ __device__ __forceinline__ TileCoord decode_tile(const PairArgs& p, int t) {
   c.y0 = (mt % p.tiles_y) * p.BH;
   c.img = mt / p.tiles_y;
   return c;
+}
+
+// Cluster mode (2 CTAs): tile pair tp -> N tile tp % n_tiles_n and the M tiles 2*(tp / n_tiles_n) + {0, 1}; CTA `rank`
+// takes the rank-th of them.  An odd M-tile count leaves a phantom second tile: that CTA recomputes the last real
+// tile (identical values, benign duplicate stores) so that the pair stays in lockstep.
+__device__ __forceinline__ int pair_tile(const PairArgs& p, int tp, int rank) {
+  const int nt = tp % p.n_tiles_n;
+  int mt = 2 * (tp / p.n_tiles_n) + rank;
+  if (mt >= p.m_tiles) mt = p.m_tiles - 1;
+  return mt * p.n_tiles_n + nt;
 }
 
 // 32 lanes x 16 consecutive fp32 columns
@@ -173,8 +184,10 @@ __device__ __forceinline__ void store_pair16(__half* hp, long long plane, const 
   }
 }
 
-// CG = columns per epilogue group (BN = 2*CG)
-template <int CG>
+// CG = columns per epilogue group (BN = 2*CG).  CL: the CTAs run as clusters of two that work on two M tiles of the same
+// N tile and fill each other's B tiles -- each loads HALF of B_hi / B_lo and multicasts it to both (a quarter less
+// operand traffic L2 -> SM, which is what bounds the 30^2 / 60^2 layers); a stage is free when BOTH have consumed it.
+template <int CG, bool CL>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                        const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -195,6 +208,12 @@ conv_gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = CL ? (int)ptx::cluster_ctarank() : 0;
+  // the sequence of tiles of this CTA: first, stride, count
+  const int t_first = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_stride = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int t_count = CL ? p.total_pairs : p.total_tiles;
+  auto tile_of = [&](int i) { return CL ? pair_tile(p, i, rank) : i; };
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&map_a_hi);
@@ -206,7 +225,7 @@ conv_gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) {
         ptx::mbar_init(&full_bar[s], 1);
-        ptx::mbar_init(&empty_bar[s], 1);
+        ptx::mbar_init(&empty_bar[s], CL ? 2 : 1);  // cluster: the MMA warps of both CTAs release a stage
       }
       for (int s = 0; s < 2; ++s) {
         ptx::mbar_init(&tmem_full_bar[s], 1);
@@ -219,7 +238,8 @@ conv_gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CL) ptx::cluster_sync();  // the peer's barriers exist before anything is multicast to them
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   ptx::grid_dep_launch_dependents();
@@ -232,8 +252,8 @@ conv_gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(p, t);
+      for (int ti = t_first; ti < t_count; ti += t_stride) {
+        const TileCoord tc = decode_tile(p, tile_of(ti));
         const int ax = tc.x0 * p.mul_x - p.pad_left, ay = tc.y0 * p.mul_y - p.pad_top;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           const int tap = kb / p.k_chunks_per_tap, cc = kb - tap * p.k_chunks_per_tap;
@@ -247,8 +267,16 @@ conv_gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
           const int cx = ax + kw * p.dil_w, cy = ay + kh * p.dil_h;
           ptx::tma_load_4d(s_ahi, &map_a_hi, &full_bar[stage], cc * kBK, cx, cy, tc.img);
           ptx::tma_load_4d(s_alo, &map_a_lo, &full_bar[stage], cc * kBK, cx, cy, tc.img);
-          ptx::tma_load_2d(s_bhi, &map_b_hi, &full_bar[stage], kb * kBK, tc.n0);
-          ptx::tma_load_2d(s_blo, &map_b_lo, &full_bar[stage], kb * kBK, tc.n0);
+          if (CL) {  // my half of the B rows, into both CTAs
+            constexpr uint32_t half = (uint32_t)(BN / 2) * kBK * 2;
+            ptx::tma_load_2d_multicast(s_bhi + rank * half, &map_b_hi, &full_bar[stage], kb * kBK, tc.n0 + rank * (BN / 2),
+                                       (uint16_t)3);
+            ptx::tma_load_2d_multicast(s_blo + rank * half, &map_b_lo, &full_bar[stage], kb * kBK, tc.n0 + rank * (BN / 2),
+                                       (uint16_t)3);
+          } else {
+            ptx::tma_load_2d(s_bhi, &map_b_hi, &full_bar[stage], kb * kBK, tc.n0);
+            ptx::tma_load_2d(s_blo, &map_b_lo, &full_bar[stage], kb * kBK, tc.n0);
+          }
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -263,7 +291,7 @@ conv_gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     int stage = 0;
     uint32_t phase = 0;
     uint32_t g = 0;  // running chunk index: TMEM buffer g & 1, barrier parity (g >> 1) & 1
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    for (int ti = t_first; ti < t_count; ti += t_stride) {
       for (int kb0 = 0; kb0 < p.num_k_blocks; kb0 += p.chunk_kb, ++g) {
         const int kb1 = min(kb0 + p.chunk_kb, p.num_k_blocks);
         const uint32_t buf = g & 1u;
@@ -290,7 +318,8 @@ conv_gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
               ptx::mma_bf16_ss(d1, dah, dbl, idesc, acc);
               ptx::mma_bf16_ss(d1, dal, dbh, idesc, 1u);
             }
-            ptx::mma_commit(&empty_bar[stage]);
+            if (CL) ptx::mma_commit_multicast(&empty_bar[stage], (uint16_t)3);
+            else ptx::mma_commit(&empty_bar[stage]);
             if (kb == kb1 - 1) ptx::mma_commit(&tmem_full_bar[buf]);
           }
           __syncwarp();
@@ -309,8 +338,8 @@ conv_gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
     const int e = threadIdx.x - 64;  // 0..255 among the epilogue threads
     uint32_t g = 0;
     float sum[CG];
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const TileCoord tc = decode_tile(p, t);
+    for (int ti = t_first; ti < t_count; ti += t_stride) {
+      const TileCoord tc = decode_tile(p, tile_of(ti));
       // per-tile scale / bias vectors -> shared memory (every epilogue thread is past the previous tile's reads)
       ptx::named_bar_sync(1, kEpiThreads);
       for (int i = e; i < BN; i += kEpiThreads) {
@@ -323,7 +352,20 @@ conv_gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
       }
       ptx::named_bar_sync(1, kEpiThreads);
 
+      // The residual does not depend on the accumulators: prefetch this thread's row of it BEFORE waiting for the
+      // tile's last chunk, so that its DRAM latency hides behind the MMAs (8 epilogue warps alone cannot keep enough
+      // loads in flight otherwise; holding the row in registers instead spilled and was slower).
+      const int py = tc.y0 + m / p.BW, px = tc.x0 + m % p.BW;
+      const bool row_ok = py < p.Hout && px < p.Wout;
+      const long long pix_off = (long long)tc.img * p.out_sn + (long long)py * p.out_sy + (long long)px * p.out_sx;
+      const bool res_pref = p.residual != nullptr && p.vec_ok == 2 && row_ok && tc.n0 + grp * CG + CG <= p.Cout;
       for (int ch = 0; ch < nchunks; ++ch, ++g) {
+        if (ch == nchunks - 1 && res_pref) {  // pull this thread's residual row towards L2 / L1 (no registers held)
+          const float* rp = p.residual + pix_off + (long long)(tc.n0 + grp * CG) * p.out_sc;
+#pragma unroll
+          for (int q = 0; q < CG / 32 + (CG % 32 ? 1 : 0); ++q)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(rp + 32 * q));
+        }
         const uint32_t buf = g & 1u;
         ptx::mbar_wait(&tmem_full_bar[buf], (g >> 1) & 1u);
         ptx::tc_fence_after();
@@ -346,9 +388,7 @@ conv_gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
       }
 
       // ---- the tile's outputs, straight from registers ----
-      const int py = tc.y0 + m / p.BW, px = tc.x0 + m % p.BW;
-      if (py < p.Hout && px < p.Wout) {
-        const long long pix_off = (long long)tc.img * p.out_sn + (long long)py * p.out_sy + (long long)px * p.out_sx;
+      if (row_ok) {
         const long long pix_lin = ((long long)tc.img * p.Hout + py) * p.Wout + px;
 #pragma unroll
         for (int u = 0; u < CG / 16; ++u) {
@@ -395,7 +435,8 @@ conv_gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gri
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CL) ptx::cluster_sync();  // nobody leaves while the peer may still signal its barriers / fill its tiles
+  else __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
@@ -614,12 +655,12 @@ int pick_bn(int cout, long long m_tiles, int num_k_blocks) {
   return best;
 }
 
-template <int CG>
+template <int CG, bool CL>
 cudaError_t launch(const cudaLaunchConfig_t& cfg, const CUtensorMap& a_hi, const CUtensorMap& a_lo,
                    const CUtensorMap& b_hi, const CUtensorMap& b_lo, const PairArgs& a) {
-  cudaError_t e = cudaFuncSetAttribute(conv_gemm_f16x2_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(conv_gemm_f16x2_kernel<CG, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
-  return cudaLaunchKernelEx(&cfg, conv_gemm_f16x2_kernel<CG>, a_hi, a_lo, b_hi, b_lo, a);
+  return cudaLaunchKernelEx(&cfg, conv_gemm_f16x2_kernel<CG, CL>, a_hi, a_lo, b_hi, b_lo, a);
 }
 
 }  // namespace
@@ -697,6 +738,8 @@ extern "C" int xdet_conv2d_f16x2(const void* d_in_pair, const xdet_conv_f16x2_de
   int stages = (int)((cap - 1024 - tail) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return fail(XDET_EINVAL, "conv2d_f16x2: tile does not fit shared memory");
+  // clusters of two CTAs sharing the B tile: on request (2), never (1); auto (0) = off unless the tuner picks it
+  const bool cluster = d->cluster == 2 && m_tiles >= 2;
   a.BN = BN;
   a.stages = stages;
   a.tmem_cols = 4 * BN;  // two buffers x (acc0 + acc1): 128 / 256 / 512 columns
@@ -753,27 +796,48 @@ extern "C" int xdet_conv2d_f16x2(const void* d_in_pair, const xdet_conv_f16x2_de
     const __half* wbase = reinterpret_cast<const __half*>(d->weights) + (size_t)pl * d->w_plane;
     const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)d->Cout};
     const cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)BN};
+    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)(cluster ? BN / 2 : BN)};  // cluster: each CTA loads half
     XDET_TRY(encode_f16(&map_b[pl], wbase, 2, dims, strides, box));
   }
   const size_t smem = (size_t)stages * stage_bytes + tail + 1024;
   int sms = kNumSMs;
   if (d->max_ctas > 0 && d->max_ctas < sms) sms = d->max_ctas;
-  const int grid = a.total_tiles < sms ? a.total_tiles : sms;
+  sms &= ~1;
+  a.m_tiles = (int)m_tiles;
+  a.total_pairs = (int)((m_tiles + 1) / 2) * a.n_tiles_n;
+  const int grid = cluster ? 2 * (a.total_pairs < sms / 2 ? a.total_pairs : sms / 2)
+                           : (a.total_tiles < sms ? a.total_tiles : sms);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (d->max_ctas <= 0) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = d->max_ctas <= 0 ? 1 : 0;
+  cfg.numAttrs = na;
   cudaError_t le;
-  if (BN == 128) le = launch<64>(cfg, map_a[0], map_a[1], map_b[0], map_b[1], a);
-  else if (BN == 64) le = launch<32>(cfg, map_a[0], map_a[1], map_b[0], map_b[1], a);
-  else le = launch<16>(cfg, map_a[0], map_a[1], map_b[0], map_b[1], a);
+  if (cluster) {
+    if (BN == 128) le = launch<64, true>(cfg, map_a[0], map_a[1], map_b[0], map_b[1], a);
+    else if (BN == 64) le = launch<32, true>(cfg, map_a[0], map_a[1], map_b[0], map_b[1], a);
+    else le = launch<16, true>(cfg, map_a[0], map_a[1], map_b[0], map_b[1], a);
+  } else {
+    if (BN == 128) le = launch<64, false>(cfg, map_a[0], map_a[1], map_b[0], map_b[1], a);
+    else if (BN == 64) le = launch<32, false>(cfg, map_a[0], map_a[1], map_b[0], map_b[1], a);
+    else le = launch<16, false>(cfg, map_a[0], map_a[1], map_b[0], map_b[1], a);
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return check_cuda(le != cudaSuccess ? le : cudaGetLastError(), "conv_gemm_f16x2_kernel");
 }

@@ -130,10 +130,15 @@ class ConvF16x2Desc(ctypes.Structure):
         ("out_pair", ctypes.c_void_p), ("pair_plane", ctypes.c_longlong), ("pair_cs", ctypes.c_int),
         ("out2", ctypes.c_void_p), ("scale2", ctypes.c_void_p), ("bias2", ctypes.c_void_p),
         ("out2_pair", ctypes.c_void_p),
-        ("block_n", ctypes.c_int), ("chunk_kb", ctypes.c_int), ("max_ctas", ctypes.c_int),
+        ("block_n", ctypes.c_int), ("chunk_kb", ctypes.c_int), ("max_ctas", ctypes.c_int), ("cluster", ctypes.c_int),
     ]
 
 
+# 2-CTA clusters that share the B tile (xdet_conv_f16x2_desc.cluster): 1 = never (default), 2 = always, 0 = the tuner
+# decides.  Measured on the benchmarked step: bit-identical results, a quarter less operand traffic, and
+# no gain -- the mid-size layers are bound by latency x bytes in flight (3 stages of 64 KB), not by L2 bandwidth --
+# so it stays off and out of the tuner's candidate list.
+F16X2_CLUSTER = 1
 # k-blocks (64 reduction elements each) per accumulator flush of the f16x2 kernel; 0 = the library default (2)
 F16X2_CHUNK_KB = 0
 # the f16x2 epilogue also writes the split planes of its NHWC outputs (the next convolution then needs no split pass)
@@ -284,14 +289,17 @@ def _autotune(x, d, reps=10):
 
 
 def _autotune_f16x2(planes, d, reps=10):
-    """Tile width of the f16x2 kernel for one layer shape: the heuristic's choice against N tiles of 32 / 64 / 128,
-    each timed as ``reps`` launches replayed from a CUDA graph (results do not depend on the choice)."""
+    """Tile width and cluster mode of the f16x2 kernel for one layer shape: the heuristic's choice against N tiles of
+    32 / 64 / 128, independent CTAs against 2-CTA clusters that share the B tile, each timed as ``reps`` launches
+    replayed from a CUDA graph (results do not depend on the choice: same products, same accumulation order)."""
     lib = _native.lib()
-    best, best_t = 0, None
+    best, best_t = (0, 1), None
     cur = torch.cuda.current_stream()
     side = torch.cuda.Stream(device=planes.device)
-    for bn in (0, 128, 64, 32):
-        d.block_n = bn
+    fixed = d.cluster
+    cands = [(bn, cl) for cl in ((1, 2) if fixed == 0 else (fixed,)) for bn in (0, 128, 64, 32)]
+    for bn, cl in cands:
+        d.block_n, d.cluster = bn, cl
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             if lib.xdet_conv2d_f16x2(planes.data_ptr(), ctypes.byref(d), side.cuda_stream) != 0:
@@ -312,9 +320,9 @@ def _autotune_f16x2(planes, d, reps=10):
             except RuntimeError:
                 continue
         if best_t is None or t < best_t * 0.985:  # prefer earlier candidates (the heuristic) on ties
-            best, best_t = bn, t
+            best, best_t = (bn, cl), t
     cur.wait_stream(side)
-    d.block_n = 0
+    d.block_n, d.cluster = 0, fixed
     return best
 
 
@@ -587,7 +595,7 @@ def _conv2d_f16x2(x, w, cout, kh, kw, *, dilation, padding, scale, bias, relu, r
                       planes.stride(0), w.planes.data_ptr(), w.planes.stride(0), w.scale_eff(scale).data_ptr(),
                       _ptr(bias), 1 if relu else 0, _ptr(residual), _ptr(f32_out), sn, sy, sx, sc, _ptr(pair),
                       0 if some_pair is None else some_pair.stride(0), pcs, _ptr(f32_out2), _ptr(scale2), _ptr(bias2),
-                      _ptr(pair2), block_n, F16X2_CHUNK_KB, MAX_CTAS)
+                      _ptr(pair2), block_n, F16X2_CHUNK_KB, MAX_CTAS, F16X2_CLUSTER)
     with torch.cuda.device(dev):
         if AUTOTUNE and block_n == 0:
             key = ("f16x2", N, H, W, cin, cs, cout, kh, kw, dh, dw_, pt, pl, Ho, Wo, sh, sw, fold_w is not None,
@@ -595,7 +603,7 @@ def _conv2d_f16x2(x, w, cout, kh, kw, *, dilation, padding, scale, bias, relu, r
                    nhwc, MAX_CTAS > 0)
             if key not in _tune_cache and not torch.cuda.is_current_stream_capturing():
                 _tune_cache[key] = _autotune_f16x2(planes, d)
-            d.block_n = _tune_cache.get(key, 0)
+            d.block_n, d.cluster = _tune_cache.get(key, (0, F16X2_CLUSTER))
         if PROFILE is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
