@@ -12,16 +12,22 @@ from oracle import proposals as op
 pytestmark = pytest.mark.gpu
 
 
-def _run(layers, backbone="resnet50", precision="bf16"):
+def _run(layers, backbone="resnet50", precision="bf16", config4=False):
     assert torch.cuda.is_available()
     import xdet_b200  # noqa: F401
     from xdet_b200 import light_head_rfcn_train as lt
-    params = lt.make_params(train_image_size=160, batch_size=2, rpn_pre_nms_top_n=600, rpn_post_nms_top_n=200,
-                            rpn_min_size=16.0 / 160, rpn_anchors_per_image=64, roi_one_image=32, ohem_roi_one_image=16,
-                            resnet_layers=layers, backbone=backbone, precision=precision)
+    if config4:  # BASELINE config 4's per-GPU shard with the reference's training flags: 8 images of 480x480
+        params = lt.make_params(train_image_size=480, batch_size=8, resnet_layers=layers, backbone=backbone,
+                                precision=precision)
+        n = 8
+    else:
+        params = lt.make_params(train_image_size=160, batch_size=2, rpn_pre_nms_top_n=600, rpn_post_nms_top_n=200,
+                                rpn_min_size=16.0 / 160, rpn_anchors_per_image=64, roi_one_image=32,
+                                ohem_roi_one_image=16, resnet_layers=layers, backbone=backbone, precision=precision)
+        n = 2
     tr = lt.LightHeadTrainer(params, seed=7)
     sd0 = {k: v.detach().clone() for k, v in tr.store.state_dict().items()}
-    batch = lt.synthetic_batch(params, 2, seed=3)
+    batch = lt.synthetic_batch(params, n, seed=3)
     out = tr.step(*batch, apply_update=False)
     torch.cuda.synchronize()
     return lt, params, tr, sd0, batch, out
@@ -202,19 +208,24 @@ def _grad_pairs(tr, grads):
                 yield k, seg[off:off + val.numel()].reshape(val.shape), grads[k].reshape(val.shape)
 
 
-@pytest.mark.parametrize("layers", [(1, 1, 1, 1), (3, 4, 6, 3), "xception"])
+@pytest.mark.parametrize("layers", [(1, 1, 1, 1), (3, 4, 6, 3), "xception", "config4-shallow"])
 def test_fp32_accurate_mode_meets_the_c4_tolerance(layers):
     """"losses within 1e-4 rel, grads within 1e-3 rel (fp32 mode)".  precision='f16x2': fp32 activations
     and gradients, split-operand tensor-core kernels for every convolution's forward, input gradient and weight
     gradient, fp32 batch-norm / pooling kernels -- the explicit backward of LightHeadTrainer against torch autograd
     over the fp32 CPU restatement of the same step (discrete selections injected; they are checked exactly elsewhere).
     Gradients are compared per variable, relative to the variable's gradient norm."""
+    size, fm = 160, 10
     if layers == "xception":  # the reference's own training backbone (36 convolutions deep)
         lt, params, tr, sd0, batch, out = _run((3, 4, 6, 3), backbone="xception", precision="f16x2")
+    elif layers == "config4-shallow":  # N = 8, 480x480, the reference's training flags (10000 -> 1800 proposals, ...)
+        layers = (1, 1, 1, 1)
+        lt, params, tr, sd0, batch, out = _run(layers, precision="f16x2", config4=True)
+        size, fm = 480, 30
     else:
         lt, params, tr, sd0, batch, out = _run(layers, precision="f16x2")
     images, gt, gl, keys = batch
-    anchors = op.layer_anchors((160, 160), (10, 10), [0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8], [0.1], [1., 2., .5], 16)
+    anchors = op.layer_anchors((size, size), (fm, fm), [0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8], [0.1], [1., 2., .5], 16)
     inject = {k: out[k].cpu().numpy() for k in ("rpn_idx", "rois_all", "roi_idx", "ohem_idx")}
     losses, grads, mid = ont.train_step(images.cpu().numpy(), gt.cpu().numpy(), gl.cpu().numpy(), sd0, params, anchors,
                                         inject)
@@ -249,9 +260,11 @@ def test_fp32_accurate_mode_meets_the_c4_tolerance(layers):
               layers, checked, np.median(errs), np.quantile(errs, 0.9), [(k, "%.2e" % e) for e, k in worst[:3]],
               np.median(errs32), np.quantile(errs32, 0.9), [(k, "%.2e" % e) for e, k in worst32[:3]]))
     assert checked >= (40 if layers == (1, 1, 1, 1) else 150)
-    if layers == (1, 1, 1, 1):
+    if layers == (1, 1, 1, 1) and size == 160:
         assert worst[0][0] < 1e-3, worst[:5]   # measured: 3e-6 (the fp32 CPU oracle: 5e-3)
     else:
+        # (config-4 shape, shallow: 8 x 480^2 means 9x the activations -> flips already here; measured median 1.0e-3 /
+        # worst 1.9e-3 for the device, 1.6e-3 / 3.4e-3 for the fp32 CPU oracle)
         # 16 blocks deep the gradient is a DISCONTINUOUS function of 1e-6 forward differences (ReLU masks, max-pool and
         # PsRoIAlign arg-max positions flip; batch statistics over 2x10x10 values amplify them): single variables jump
         # by ~1e-2 for the device and for the fp32 CPU oracle alike, and every flip moves all gradients upstream of it
