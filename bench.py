@@ -388,7 +388,7 @@ class LightHeadResnet50:
 
         cpu = None
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            cpu, cpu_out, img, keys = cpu_network_baseline(self, params, model.store.state_dict(), reps=1, want_outputs=True)
+            cpu, cpu_out, img, keys = cpu_network_baseline(self, params, model.store.state_dict(), want_outputs=True)
             models = {self.precision: model}
             if "bf16_mode" in subs:
                 models["bf16"] = fast_model
@@ -444,9 +444,10 @@ class LightHeadResnet50:
         del torch
 
 
-def cpu_network_baseline(wl, params, sd, reps=1, warmup=0, want_outputs=False):
+def cpu_network_baseline(wl, params, sd, reps=None, warmup=1, want_outputs=False, budget_s=10.0):
     """The reference-semantics CPU path (oracle/net.py, PyTorch CPU fp32 -- TF1 itself is not installable) on a
-    bounded sample: ONE 480x480 image per step, all host threads."""
+    bounded sample: ONE image of the batch per repetition, all host threads; ``reps`` repetitions, or (None) as many as
+    fit ~``budget_s`` seconds of CPU work (at least 3, at most 40) after one warm-up."""
     import torch
 
     from oracle import net as onet
@@ -475,8 +476,16 @@ def cpu_network_baseline(wl, params, sd, reps=1, warmup=0, want_outputs=False):
     for _ in range(warmup):
         one()
     t0 = time.perf_counter()
-    for _ in range(reps):
+    done = 0
+    while True:
         one()
+        done += 1
+        if reps is not None:
+            if done >= reps:
+                break
+        elif done >= 40 or (done >= 3 and time.perf_counter() - t0 >= budget_s):
+            break
+    reps = done
     dt = (time.perf_counter() - t0) / reps
     base = {"value": 1.0 / dt, "unit": "images/s", "cores": cores, "kind": "port",
             "sample": "1 image of the batch per step (whole graph incl. proposals/NMS, PsRoIAlign C oracle, per-class NMS), "
@@ -820,7 +829,7 @@ DEFAULT_WORKLOAD = "lighthead_resnet50"
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))

@@ -103,6 +103,8 @@ SHAPES = [
     (1, 98, 50, 37, 33, 7, 7),
     (1, 16, 5, 5, 0, 2, 2),          # empty RoI set
     (1, 49, 30, 30, 1, 7, 7),        # single RoI, bank 1
+    (1, 98, 12, 12, 1100, 7, 7),     # > 1024 RoIs: the backward's thread-per-plane kernel (<= 1024: warp per plane)
+    (8, 490, 30, 30, 64, 7, 7),      # the training step's shape (8 images x 64 sampled RoIs)
 ]
 
 

@@ -933,6 +933,79 @@ __global__ void __launch_bounds__(kBwdThreads) psroi_bwd_kernel(const float* __r
   }
 }
 
+// Max pooling, few RoIs per image (the training step: 64): one WARP per (image, channel) plane.  The expensive part of
+// a contribution -- RoI geometry, the arg-max sample's coordinates, the three fp64 weights -- does not depend on the
+// plane's running sums, so the lanes compute it for different RoIs in parallel and park (cell, value) x 4 taps in
+// shared memory; lane 0 then applies them in the reference's order (RoI index, taps 00 / +row / +col / +row+col), i.e.
+// with exactly the additions of psroi_bwd_kernel, bit for bit -- ~30x less serial work per plane.
+constexpr int kBwdWarps = 4;
+
+__global__ void __launch_bounds__(kBwdWarps * 32) psroi_bwd_max_warp_kernel(const float* __restrict__ rois,
+                                                                            const float* __restrict__ gout,
+                                                                            const int32_t* __restrict__ index,
+                                                                            float* __restrict__ gin, int C, int H, int W,
+                                                                            int R, int gw, int gh, int n_planes) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int HW = H * W;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // per warp: plane accumulator [HW], then the tap list: cell index [R*4] (int, -1 = no cell) and value [R*4]
+  const size_t per_warp = ((size_t)HW + 8 * (size_t)R + 3) / 4 * 4;
+  float* acc = reinterpret_cast<float*>(smem_raw) + (size_t)warp * per_warp;
+  int* cell = reinterpret_cast<int*>(acc + HW);
+  float* val = reinterpret_cast<float*>(cell + 4 * R);
+  const int G = gw * gh, bank = C / G;
+  for (int pl = blockIdx.x * kBwdWarps + warp; pl < n_planes; pl += gridDim.x * kBwdWarps) {
+    const int img = pl / C, c = pl - img * C;
+    const int bin = c / bank, row = bin / gw, col = bin - row * gw;
+    for (int i = lane; i < HW; i += 32) acc[i] = 0.f;
+    for (int r = lane; r < R; r += 32) {
+      int cc[4] = {-1, -1, -1, -1};
+      float vv[4] = {0.f, 0.f, 0.f, 0.f};
+      const RoiGeom g = roi_geometry(rois + ((long long)img * R + r) * 4, H, W, gw, gh);
+      if (g.nh != 0) {
+        const long long o = ((long long)img * R + r) * C + c;
+        const float gv = gout[o];
+        const double dg = (double)gv;
+        const float x0 = __fadd_rn(g.xmin, __fmul_rn(g.bin_w, (float)col));
+        const float y0 = __fadd_rn(g.ymin, __fmul_rn(g.bin_h, (float)row));
+        const int s = index[o];
+        const int hi = s / g.nw, wi = s - hi * g.nw;
+        const float x = sample_coord(x0, g.step_w, wi), y = sample_coord(y0, g.step_h, hi);
+        const int ix = __float2int_rz(x), iy = __float2int_rz(y);
+        const float fx = __fsub_rn(x, (float)ix), fy = __fsub_rn(y, (float)iy);
+        const int ix1 = min(ix + 1, W - 1), iy1 = min(iy + 1, H - 1);
+        const double dfx = (double)fx, dfy = (double)fy;
+        const double ax = __dsub_rn(1.0, dfx), ay = __dsub_rn(1.0, dfy);
+        vv[0] = __double2float_rn(__dmul_rn(__dmul_rn(ax, ay), dg));
+        vv[1] = __double2float_rn(__dmul_rn(__dmul_rn(ax, dfy), dg));
+        vv[2] = __double2float_rn(__dmul_rn(__dmul_rn(dfx, ay), dg));
+        vv[3] = __fmul_rn(__fmul_rn(fx, fy), gv);
+        const bool xin = ix >= 0 && ix < W, yin = iy >= 0 && iy < H;
+        if (xin && yin) cc[0] = iy * W + ix;
+        if (xin) cc[1] = iy1 * W + ix;
+        if (yin) cc[2] = iy * W + ix1;
+        cc[3] = iy1 * W + ix1;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        cell[r * 4 + k] = cc[k];
+        val[r * 4 + k] = vv[k];
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      for (int i = 0; i < 4 * R; ++i) {
+        const int q = cell[i];
+        if (q >= 0) acc[q] = __fadd_rn(acc[q], val[i]);
+      }
+    }
+    __syncwarp();
+    float* out = gin + (long long)pl * HW;
+    for (int i = lane; i < HW; i += 32) out[i] = acc[i];
+    __syncwarp();
+  }
+}
+
 int validate(int N, int C, int H, int W, int R, int gw, int gh) {
   if (N < 0 || C < 0 || H < 0 || W < 0 || R < 0) return fail(XDET_EINVAL, "negative dimension");
   if (gw <= 0 || gh <= 0) return fail(XDET_EINVAL, "Need Attr grid_dim_width/height > 0, got %d x %d", gw, gh);
@@ -1107,6 +1180,22 @@ template <bool kMax>
 static int launch_bwd(const float* rois, const float* gout, const int32_t* idx, float* gin, int N, int C, int H, int W,
                       int R, int gw, int gh, cudaStream_t st) {
   const int HW = H * W;
+  if (kMax && R <= 1024) {  // few RoIs per image: one warp per plane (see psroi_bwd_max_warp_kernel)
+    const size_t per_warp = (((size_t)HW + 8 * (size_t)R + 3) / 4 * 4) * sizeof(float);
+    const size_t smem = per_warp * kBwdWarps;
+    if (smem <= kMaxSmem) {
+      XDET_TRY(check_cuda(cudaFuncSetAttribute(psroi_bwd_max_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)smem), "cudaFuncSetAttribute(psroi_bwd_max_warp)"));
+      const long long n_planes = (long long)N * C;
+      long long blocks = (n_planes + kBwdWarps - 1) / kBwdWarps;
+      if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+      if (n_planes > 0 && n_planes < (1ll << 31)) {
+        psroi_bwd_max_warp_kernel<<<(unsigned)blocks, kBwdWarps * 32, smem, st>>>(rois, gout, idx, gin, C, H, W, R, gw, gh,
+                                                                               (int)n_planes);
+        return after_launch("psroi_bwd_max_warp_kernel");
+      }
+    }
+  }
   const int pitch = (HW % 2 == 0) ? HW + 1 : HW;
   const size_t per_plane = (size_t)(kMax ? 1 : 2) * pitch * sizeof(float);
   int ppc = (int)(kMaxSmem / per_plane);
