@@ -446,6 +446,25 @@ int xdet_sgd_momentum_conv(const float* d_dw, float* d_w, float* d_mom, void* d_
                            void* stream);
 int xdet_sgd_momentum_vec(const float* d_g, float* d_w, float* d_mom, long long n, float lr, float momentum, float wd,
                           float grad_scale, void* stream);
+/* The whole apply_gradients (:436-441) in one launch: a device-resident table of items, one per variable.  A
+ * convolution item is what xdet_sgd_momentum_conv takes (dw / w_pack / w_dgrad_pack already offset to the variable's slice
+ * of a fused pack, regular layout only); a vector item (bias, beta, gamma) has taps == 0 and Cout = its length.  The
+ * caller fills first_block with the running sum of the items' block counts -- tiles_ci * tiles_co * taps 32x32 tiles for
+ * a convolution (tiles_* = ceil(C* / 32)), ceil(Cout / 256) for a vector -- and passes the total. */
+typedef struct xdet_sgd_item {
+  const float* dw;
+  float* w;
+  float* mom;
+  void* w_pack;
+  void* w_dgrad_pack; /* NULL: no input-gradient pack */
+  int Cout, taps, Cin, cin_pad, cout_pad;
+  int tiles_ci, tiles_co;
+  int first_block;
+  float wd;
+  int reserved;
+} xdet_sgd_item;
+int xdet_sgd_momentum_multi(const xdet_sgd_item* d_items, int n_items, int total_blocks, float lr, float momentum,
+                            float grad_scale, void* stream);
 size_t xdet_match_workspace_bytes(int N, int G);
 int xdet_match_encode(const float* d_boxes, long long box_img_stride, const float* d_ref_yxhw, const float* d_gt,
                       const int* d_gt_labels, int N, int A, int G, float allowed_border, float high_thres,

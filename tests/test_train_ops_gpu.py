@@ -183,6 +183,58 @@ def test_sgd_momentum_and_repack(T):
     assert (v - (v0 - 0.1 * gv)).abs().max().item() < 1e-6
 
 
+def test_sgd_multi_matches_the_per_variable_kernels(T):
+    """xdet_sgd_momentum_multi: several convolutions (one a fused pack of two masters at channel offsets, one dense,
+    one without an input-gradient pack) and vectors with different decay in ONE launch = the per-variable launches,
+    bit for bit."""
+    import xdet_b200.ops as ops
+    g = torch.Generator(device="cuda").manual_seed(14)
+    rnd = lambda *s: torch.randn(s, generator=g, device="cuda")  # noqa: E731
+
+    def conv_case(kh, kw, cin, couts, need_d=True):
+        cout = sum(couts)
+        cpad, copad = (cin + 63) // 64 * 64, (cout + 63) // 64 * 64
+        masters, co = [], 0
+        for c in couts:
+            shape = (cin, c) if kh == kw == 1 and len(couts) == 1 and not need_d else (kh, kw, cin, c)
+            masters.append((rnd(*shape) * 0.1, rnd(*shape) * 0.01, co))
+            co += c
+        dw = rnd(cout, kh * kw, cpad)
+        wp = torch.zeros((cout, kh * kw * cpad), dtype=torch.bfloat16, device="cuda")
+        dp = torch.zeros((cin, kh * kw * copad), dtype=torch.bfloat16, device="cuda") if need_d else None
+        return masters, dw, wp, dp
+
+    cases = [conv_case(3, 3, 72, [40]), conv_case(1, 1, 256, [64, 100]), conv_case(1, 1, 130, [50], need_d=False),
+             conv_case(15, 1, 33, [24])]
+    vecs = [(rnd(100), rnd(100), rnd(104), 2e-4), (rnd(2048), rnd(2048), rnd(2048), 0.0), (rnd(7), rnd(7), rnd(8), 0.0)]
+    clone = lambda t: None if t is None else t.clone()  # noqa: E731
+    ref_cases = [([tuple(clone(x) if torch.is_tensor(x) else x for x in m) for m in ms], dw, clone(wp), clone(dp))
+                 for ms, dw, wp, dp in cases]
+    ref_vecs = [(w.clone(), m.clone(), gv, wd) for w, m, gv, wd in vecs]
+    lr, mo, gs = 0.013, 0.9, 0.5
+    for ms, dw, wp, dp in ref_cases:
+        for w, m, co in ms:
+            T.sgd_momentum_conv(dw, w, m, wp, dp, lr, mo, 1e-4, gs, co, 0)
+    for w, m, gv, wd in ref_vecs:
+        T.sgd_momentum_vec(gv[:w.numel()], w, m, lr, mo, wd, gs)
+    plan = T.SgdPlan()
+    for ms, dw, wp, dp in cases:
+        for w, m, co in ms:
+            plan.add_conv(dw, w, m, wp, dp, 1e-4, co, 0)
+    for w, m, gv, wd in vecs:
+        plan.add_vec(gv[:w.numel()], w, m, wd)
+    plan.step(lr, mo, gs)
+    torch.cuda.synchronize()
+    for (ms, _, wp, dp), (rms, _, rwp, rdp) in zip(cases, ref_cases):
+        for (w, m, _), (rw, rm, _) in zip(ms, rms):
+            assert torch.equal(w, rw) and torch.equal(m, rm)
+        assert torch.equal(wp, rwp) and (dp is None or torch.equal(dp, rdp))
+        w4 = torch.cat([(w if w.dim() == 4 else w.reshape(1, 1, *w.shape)) for w, _, _ in ms], dim=3)
+        assert torch.equal(wp, ops.pack_conv_weight(w4.permute(3, 2, 0, 1)))
+    for (w, m, _, _), (rw, rm, _, _) in zip(vecs, ref_vecs):
+        assert torch.equal(w, rw) and torch.equal(m, rm)
+
+
 def test_thin_map_repacks(T):
     g = torch.Generator(device="cuda").manual_seed(5)
     x = torch.randn((2, 490, 30, 30), generator=g, device="cuda")

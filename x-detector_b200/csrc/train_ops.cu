@@ -422,6 +422,66 @@ __global__ void sgd_vec_kernel(const float* __restrict__ g, float* __restrict__ 
   w[i] = wv - lr * a;
 }
 
+// Every variable of the model in ONE launch: a block looks its item up in the table by its block index (the host filled
+// first_block with the running block count) and then does what sgd_conv_tiled_kernel / sgd_vec_kernel do.
+__global__ void __launch_bounds__(256) sgd_multi_kernel(const xdet_sgd_item* __restrict__ items, int n_items, float lr,
+                                                        float momentum, float gscale) {
+  __shared__ float s_g[32][33];
+  __shared__ __nv_bfloat16 s_w[32][34];
+  int lo = 0, hi = n_items - 1;  // last item with first_block <= blockIdx.x
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(&items[mid].first_block) <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const xdet_sgd_item it = items[lo];
+  const int b = (int)blockIdx.x - it.first_block;
+  float* __restrict__ w = it.w;
+  float* __restrict__ mom = it.mom;
+  const float* __restrict__ dw = it.dw;
+  const float wd = it.wd;
+  if (it.taps == 0) {  // a vector (bias / beta / gamma) of Cout elements
+    const int i = b * 256 + threadIdx.x;
+    if (i < it.Cout) {
+      const float wv = w[i];
+      const float a = momentum * mom[i] + dw[i] * gscale + wd * wv;
+      mom[i] = a;
+      w[i] = wv - lr * a;
+    }
+    return;
+  }
+  __nv_bfloat16* __restrict__ wp = reinterpret_cast<__nv_bfloat16*>(it.w_pack);
+  __nv_bfloat16* __restrict__ wd_pack = reinterpret_cast<__nv_bfloat16*>(it.w_dgrad_pack);
+  const int Cout = it.Cout, taps = it.taps, Cin = it.Cin, cin_pad = it.cin_pad, cout_pad = it.cout_pad;
+  const int per_tap = it.tiles_ci * it.tiles_co;
+  const int tap = b / per_tap, r = b - tap * per_tap;
+  const int co0 = (r / it.tiles_ci) * 32, ci0 = (r % it.tiles_ci) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int l = ty; l < 32; l += 8) {
+    const int co = co0 + l, ci = ci0 + tx;
+    s_g[l][tx] = (co < Cout && ci < Cin) ? dw[((long long)co * taps + tap) * cin_pad + ci] : 0.f;
+  }
+  __syncthreads();
+  for (int l = ty; l < 32; l += 8) {
+    const int ci = ci0 + l, co = co0 + tx;
+    if (ci < Cin && co < Cout) {
+      const long long e = ((long long)tap * Cin + ci) * Cout + co;
+      const float wv = w[e];
+      const float a = momentum * mom[e] + (s_g[tx][l] * gscale + wd * wv);
+      mom[e] = a;
+      const float nw = wv - lr * a;
+      w[e] = nw;
+      const __nv_bfloat16 bv = __float2bfloat16_rn(nw);
+      s_w[tx][l] = bv;
+      if (wd_pack) wd_pack[((long long)ci * taps + (taps - 1 - tap)) * cout_pad + co] = bv;
+    }
+  }
+  __syncthreads();
+  for (int l = ty; l < 32; l += 8) {
+    const int co = co0 + l, ci = ci0 + tx;
+    if (co < Cout && ci < Cin) wp[((long long)co * taps + tap) * cin_pad + ci] = s_w[l][tx];
+  }
+}
+
 // ---- target assignment ---------------------------------------------------------------------------------------
 // boxes [N,A,4] (ymin,xmin,ymax,xmax); gt [N,G,4], gt_labels [N,G] (<= 0: padding, ignored).
 __device__ __forceinline__ float iou_ref(const float4 g, const float4 b) {  // iou_matrix, :20-46
@@ -843,6 +903,14 @@ extern "C" int xdet_sgd_momentum_vec(const float* d_g, float* d_w, float* d_mom,
   sgd_vec_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_g, d_w, d_mom, n, lr, momentum, wd,
                                                                                grad_scale);
   return after_launch("sgd_vec_kernel");
+}
+
+extern "C" int xdet_sgd_momentum_multi(const xdet_sgd_item* d_items, int n_items, int total_blocks, float lr,
+                                       float momentum, float grad_scale, void* stream) {
+  if (n_items <= 0 || total_blocks <= 0) return XDET_OK;
+  if (!d_items) return fail(XDET_EINVAL, "sgd_multi: no item table");
+  sgd_multi_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)stream>>>(d_items, n_items, lr, momentum, grad_scale);
+  return after_launch("sgd_multi_kernel");
 }
 
 extern "C" size_t xdet_match_workspace_bytes(int N, int G) { return sizeof(unsigned long long) * (size_t)N * (size_t)G; }

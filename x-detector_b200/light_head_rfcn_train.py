@@ -316,6 +316,7 @@ class LightHeadTrainer(object):
         self.global_step = 0
         self.reg = reg = _Registry(self.device)
         self.convs, self.vecs = [], []
+        self._sgd_plan = None
         size = p['train_image_size']
         self.fmap = size // 16
         creator = anchor_manipulator.AnchorCreator([size] * 2, layers_shapes=[(self.fmap, self.fmap)],
@@ -659,20 +660,26 @@ class LightHeadTrainer(object):
         side = self.side
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            self.fwd_rpn_losses()
+            # first what the head's forward waits for (proposals, RoI targets), then what only the backward needs (anchor
+            # targets, RPN sampling and losses): the second half keeps running beside the head's forward and backward
+            self.fwd_rpn_decode()
             self.fwd_proposals_and_targets()
+            ev_rois = torch.cuda.Event()
+            ev_rois.record(side)
+            self.fwd_rpn_losses()
+            t.ev_rpn = torch.cuda.Event()
+            t.ev_rpn.record(side)
         conv_ops.MAX_CTAS = 148 - 12
         try:
             backbone = self.fwd_backbone_exit()
             self.fwd_thin(backbone)
         finally:
             conv_ops.MAX_CTAS = 0
-        main.wait_stream(side)  # JOIN
-        for t_ in (t.score, t.boxes, t.glabels, t.gtargets, t.rpn_idx, t.d_rpn, t.rois_all, t.rlab, t.rtgt, t.rsc,
-                   t.roi_idx, t.rois, t.roi_tgt, t.roi_lab, t.yxhw, t.rpn_ce, t.rpn_loc):
+        main.wait_event(ev_rois)  # JOIN (proposal half)
+        for t_ in (t.score, t.boxes, t.rois_all, t.rlab, t.rtgt, t.rsc, t.roi_idx, t.rois, t.roi_tgt, t.roi_lab, t.yxhw):
             t_.record_stream(main)
         self.fwd_head()
-        self.backward()
+        self.backward()  # (joins the RPN-loss half where it needs d_rpn)
         self.apply_gradients(apply_update)
         return self.outputs()
 
@@ -728,13 +735,20 @@ class LightHeadTrainer(object):
         t.rpn_out = self.rpn_out.fwd(t.r, out_layout="nhwc_f32")
         return t.rpn_out
 
+    def fwd_rpn_decode(self):
+        """Objectness (softmax[:, -1]) and decode_all_anchors of the RPN head's output (train:295-319)."""
+        t, A = self.t, self.A
+        t.score, t.boxes = ops.rpn_decode(t.rpn_out, 0, 2 * A, self.enc.device_anchors(0), A)
+        return t.score, t.boxes
+
     def fwd_rpn_losses(self):
-        """Objectness / decode (train:295-319), anchor targets, select_samples (:321-358), the two RPN losses
-        (:361-378) and their gradient with respect to the RPN head's output."""
+        """Anchor targets, select_samples (train:321-358), the two RPN losses (:361-378) and their gradient with respect
+        to the RPN head's output."""
         t, p, A = self.t, self.params, self.A
         N, fm, S, inject, keys = t.N, self.fmap, t.S, t.inject, t.keys
         rpn_out = t.rpn_out
-        t.score, t.boxes = ops.rpn_decode(rpn_out, 0, 2 * A, self.enc.device_anchors(0), A)
+        if not hasattr(t, "score"):
+            self.fwd_rpn_decode()
         t.glabels, t.gtargets, _ = T.match_encode(self.anchors_pt, t.gt_boxes, t.gt_labels, 0.0,
                                                   p['rpn_match_threshold'], p['rpn_neg_threshold'],
                                                   ref_yxhw=self.anchors_yxhw)
@@ -774,6 +788,8 @@ class LightHeadTrainer(object):
         t, p = self.t, self.params
         N, inject, keys = t.N, t.inject, t.keys
         gt_boxes, gt_labels = t.gt_boxes, t.gt_labels
+        if not hasattr(t, "score"):
+            self.fwd_rpn_decode()
         if 'rois_all' in inject:
             rois_all = inject['rois_all']
         else:
@@ -895,6 +911,11 @@ class LightHeadTrainer(object):
         dmid = self.sep_b.bwd(do)
         dbackbone = self.sep_a.bwd(dmid)
         # ---- RPN head ----
+        if getattr(t, "ev_rpn", None) is not None:  # JOIN (RPN-loss half of the second stream)
+            main = torch.cuda.current_stream()
+            main.wait_event(t.ev_rpn)
+            for t_ in (t.glabels, t.gtargets, t.rpn_idx, t.d_rpn, t.rpn_ce, t.rpn_loc):
+                t_.record_stream(main)
         dr = T.relu_bwd(self.rpn_out.bwd(t.d_rpn), t.r)
         d_rpn_feat = self.rpn_conv.bwd(dr)
         # ---- backbone (each stage's gradient bucket goes to the communication stream as soon as it is complete) ----
@@ -927,15 +948,37 @@ class LightHeadTrainer(object):
         if apply_update:
             lr = learning_rate(p, self.global_step)
             gs = 1.0 / world
-            for c in self.convs:
-                c.update(lr, p['momentum'], p['weight_decay'], gs)
-            for v in self.vecs:
-                v.update(lr, p['momentum'], p['weight_decay'], gs)
-            # second 1x15 bias: same gradient as the first
-            T.sgd_momentum_vec(self.sep_b_bias_vec.grad, self.sep_b_biases[1], self.sep_b_bias_mom2, lr, p['momentum'],
-                               p['weight_decay'], gs)
+            if self.f32:
+                for c in self.convs:
+                    c.update(lr, p['momentum'], p['weight_decay'], gs)
+                for v in self.vecs:
+                    v.update(lr, p['momentum'], p['weight_decay'], gs)
+                # second 1x15 bias: same gradient as the first
+                T.sgd_momentum_vec(self.sep_b_bias_vec.grad, self.sep_b_biases[1], self.sep_b_bias_mom2, lr,
+                                   p['momentum'], p['weight_decay'], gs)
+            else:
+                # every variable in one launch (the stem's folded layout keeps its own kernel)
+                if self._sgd_plan is None:
+                    self._sgd_plan = self._build_sgd_plan()
+                for c in self.convs:
+                    if c.fold:
+                        c.update(lr, p['momentum'], p['weight_decay'], gs)
+                self._sgd_plan.step(lr, p['momentum'], gs)
             self.global_step += 1
         return world
+
+    def _build_sgd_plan(self):
+        p = self.params
+        plan = T.SgdPlan()
+        for c in self.convs:
+            if not c.fold:
+                for (_, t, co, ci), m in zip(c.masters, c.mom):
+                    plan.add_conv(c.dw, t, m, c.pack, c.dpack, p['weight_decay'], co, ci)
+        for v in self.vecs:
+            for i, (t, m) in enumerate(zip(v.tensors, v.mom)):
+                plan.add_vec(v.grad[i * v.seg:i * v.seg + t.numel()], t, m, p['weight_decay'] if v.decayed else 0.0)
+        plan.add_vec(self.sep_b_bias_vec.grad, self.sep_b_biases[1], self.sep_b_bias_mom2, p['weight_decay'])
+        return plan
 
     def outputs(self):
         t = self.t

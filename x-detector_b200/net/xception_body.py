@@ -209,9 +209,7 @@ def get_proposals(object_score, bboxes_pred, encode_fn, rpn_pre_nms_top_n, rpn_p
     thresholds and shuffle keys) -> (proposals_bboxes, proposals_targets, proposals_labels, proposals_scores) (:445-448)."""
     if is_training:
         tr = _trainer(store, "get_proposals")
-        if not hasattr(tr.t, "score"):  # objectness / decode / RPN losses of the model_fn (train:295-378)
-            tr.fwd_rpn_losses()
-        return tr.fwd_proposals_and_targets()
+        return tr.fwd_proposals_and_targets()  # (runs the model_fn's objectness / decode first if it has not happened)
     rois, _, _ = ops.rpn_select(object_score, bboxes_pred, rpn_pre_nms_top_n, rpn_post_nms_top_n, nms_threshold,
                                 rpn_min_size, shuffle_keys)
     return rois

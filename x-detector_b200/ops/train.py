@@ -183,6 +183,60 @@ def sgd_momentum_vec(g, w, mom, lr, momentum, wd=0.0, grad_scale=1.0):
                                                       momentum, wd, grad_scale, _st()))
 
 
+class SgdItem(ctypes.Structure):
+    """``xdet_sgd_item`` (include/xdet_b200.h)."""
+    _fields_ = [("dw", ctypes.c_void_p), ("w", ctypes.c_void_p), ("mom", ctypes.c_void_p), ("w_pack", ctypes.c_void_p),
+                ("w_dgrad_pack", ctypes.c_void_p), ("Cout", ctypes.c_int), ("taps", ctypes.c_int), ("Cin", ctypes.c_int),
+                ("cin_pad", ctypes.c_int), ("cout_pad", ctypes.c_int), ("tiles_ci", ctypes.c_int),
+                ("tiles_co", ctypes.c_int), ("first_block", ctypes.c_int), ("wd", ctypes.c_float),
+                ("reserved", ctypes.c_int)]
+
+
+class SgdPlan(object):
+    """The item table of ``xdet_sgd_momentum_multi``: add the variables once, ``step`` is one launch.  The table holds raw
+    device pointers: every tensor handed to ``add_*`` must stay allocated (and in place) while the plan is used."""
+
+    def __init__(self):
+        self.items, self.blocks, self.table, self.keep = [], 0, None, []
+
+    def add_conv(self, dw, w, mom, w_pack, w_dgrad_pack, wd, co_off=0, ci_off=0):
+        """Same arguments as ``sgd_momentum_conv`` (regular layout)."""
+        if w.dim() == 2:
+            kh = kw = 1
+            cin, cout = w.shape
+        else:
+            kh, kw, cin, cout = w.shape
+        taps, cin_pad = kh * kw, dw.shape[-1]
+        cout_pad = 0 if w_dgrad_pack is None else w_dgrad_pack.shape[-1] // taps
+        off = co_off * taps * cin_pad + ci_off
+        it = SgdItem(dw.data_ptr() + 4 * off, w.data_ptr(), mom.data_ptr(), w_pack.data_ptr() + 2 * off,
+                     None if w_dgrad_pack is None else w_dgrad_pack.data_ptr() + 2 * (ci_off * taps * cout_pad + co_off),
+                     cout, taps, cin, cin_pad, cout_pad, (cin + 31) // 32, (cout + 31) // 32, self.blocks, wd, 0)
+        assert w.is_contiguous() and mom.is_contiguous() and dw.is_contiguous() and w_pack.dtype == torch.bfloat16
+        self.items.append(it)
+        self.blocks += it.tiles_ci * it.tiles_co * taps
+        self.keep += [dw, w, mom, w_pack, w_dgrad_pack]
+        self.table = None
+
+    def add_vec(self, g, w, mom, wd):
+        n = w.numel()
+        assert g.numel() >= n and w.is_contiguous() and mom.is_contiguous() and g.is_contiguous()
+        self.items.append(SgdItem(g.data_ptr(), w.data_ptr(), mom.data_ptr(), None, None, n, 0, 0, 0, 0, 0, 0,
+                                  self.blocks, wd, 0))
+        self.blocks += (n + 255) // 256
+        self.keep += [g, w, mom]
+        self.table = None
+
+    def step(self, lr, momentum, grad_scale=1.0):
+        if not self.items:
+            return
+        if self.table is None:
+            raw = bytes((SgdItem * len(self.items))(*self.items))
+            self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.keep[0].device)
+        _native.check(_native.lib().xdet_sgd_momentum_multi(self.table.data_ptr(), len(self.items), self.blocks, lr,
+                                                            momentum, grad_scale, _st()))
+
+
 def match_encode(boxes, gt, gt_labels, allowed_border, high_thres, low_thres, prior_scaling=(1., 1., 1., 1.),
                  ref_yxhw=None):
     """boxes [A,4] (shared by all images; pass ref_yxhw [A,4] = the anchors' centre form) or [N,A,4];
