@@ -402,9 +402,18 @@ int xdet_col_stats_bf16(const void* d_x, long long rows, int C, int cs, int with
 int xdet_bn_finalize(const float* d_sums, const float* d_gamma, const float* d_beta, long long rows, int C, float eps,
                      float decay, float* d_moving_mean, float* d_moving_var, float* d_scale, float* d_shift,
                      float* d_mean, float* d_invstd, void* stream);
+/* xdet_col_stats_bf16 (with squares) + xdet_bn_finalize in ONE launch.  d_scratch: xdet_bn_train_scratch_bytes(C) bytes
+ * that are ZERO when the call is issued; the kernel leaves them zero again, so one buffer (sized for the widest layer)
+ * serves every batch-norm issued on the same stream. */
+size_t xdet_bn_train_scratch_bytes(int C);
+int xdet_bn_train_stats_bf16(const void* d_x, long long rows, int C, int cs, const float* d_gamma, const float* d_beta,
+                             float eps, float decay, float* d_moving_mean, float* d_moving_var, float* d_scale,
+                             float* d_shift, float* d_mean, float* d_invstd, void* d_scratch, void* stream);
+/* sums_zeroed != 0: d_sums (2*C floats: dbeta, dgamma) already holds zeros (e.g. a slice of a gradient buffer cleared at
+ * the start of the step) -- the call skips its own memset. */
 int xdet_bn_relu_bwd_bf16(const void* d_dy, const void* d_x, const float* d_scale, const float* d_shift,
                           const float* d_mean, const float* d_invstd, long long rows, int C, int relu,
-                          const void* d_add_in, float* d_sums, void* d_dx, void* stream);
+                          const void* d_add_in, float* d_sums, void* d_dx, int sums_zeroed, void* stream);
 /* dx = dy where y > 0 else 0 (gradient of a ReLU fused into a convolution epilogue); bf16, n elements (n % 8 == 0) */
 int xdet_relu_bwd_bf16(const void* d_dy, const void* d_y, void* d_dx, long long n, void* stream);
 /* fp32 forms of the kernels above for the fp32-ACCURATE training mode ("f16x2" precision; csrc/train_ops_f32.cu):

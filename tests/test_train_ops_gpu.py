@@ -121,6 +121,43 @@ def test_bn_train_forward_backward(T):
     assert (dbeta - br.grad).abs().max().item() < 2e-2 * br.grad.abs().max().item()
 
 
+@pytest.mark.parametrize("rows,C", [(7200, 256), (7200, 2048), (115200, 64), (28800, 496), (37, 8), (5000, 728)])
+def test_bn_train_stats_one_launch_over_a_self_cleaning_scratch(T, rows, C):
+    """xdet_bn_train_stats_bf16 = column statistics + bn_finalize in one launch: against float64 statistics of the same
+    bf16 values; called back to back with different widths on the same scratch (the kernel must hand it back zeroed);
+    the backward's reduce with the raw sum of g*x against the direct sum of g*xhat."""
+    g = torch.Generator(device="cuda").manual_seed(rows + C)
+    for rep in range(3):   # same stream, same scratch, three layers in a row
+        x = (torch.randn((rows, C), generator=g, device="cuda") * (1.0 + rep) + 0.7 * rep).to(torch.bfloat16)
+        gamma = torch.rand(C, generator=g, device="cuda") + 0.5
+        beta = torch.randn(C, generator=g, device="cuda") * 0.2
+        mm, mv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+        st = T.bn_train(x, gamma, beta, 1e-5, 0.997, mm, mv)
+        xd = x.double()
+        mean, var = xd.mean(0), xd.var(0, unbiased=False)
+        inv = 1.0 / torch.sqrt(var + 1e-5)
+        assert (st.mean.double() - mean).abs().max().item() < 2e-5 * (1 + mean.abs().max().item())
+        assert ((st.invstd.double() - inv).abs() / inv).max().item() < 1e-4
+        assert ((st.scale.double() - gamma.double() * inv).abs() / inv).max().item() < 1e-4
+        assert (st.shift.double() - (beta.double() - mean * gamma.double() * inv)).abs().max().item() < 2e-4
+        unb = var * rows / max(rows - 1, 1)
+        assert (mm.double() - 0.003 * mean).abs().max().item() < 1e-6
+        assert (mv.double() - (0.997 + 0.003 * unb)).abs().max().item() < 1e-5 * (1 + unb.max().item())
+        assert int(T._bn_scratch(x.device, C).view(torch.int32).abs().sum()) == 0
+        dy = torch.randn((rows, C), generator=g, device="cuda").to(torch.bfloat16)
+        pre = xd * st.scale.double() + st.shift.double()
+        dy[pre.abs() < 1e-5 * ((xd * st.scale.double()).abs() + st.shift.double().abs())] = 0   # mask a rounding away
+        dx, dgamma, dbeta = T.bn_relu_bwd(dy, x, st, relu=True)
+        mask = (pre > 0).double()
+        gd = dy.double() * mask
+        xhat = (xd - st.mean.double()) * st.invstd.double()
+        ref_b, ref_g = gd.sum(0), (gd * xhat).sum(0)
+        tol = 1e-4 * (gd.abs() * (1 + xhat.abs())).sum(0).max().item()
+        assert (dbeta.double() - ref_b).abs().max().item() < tol and (dgamma.double() - ref_g).abs().max().item() < tol
+        ref_dx = st.scale.double() * (gd - ref_b / rows - xhat * ref_g / rows)
+        assert (dx.double() - ref_dx).abs().max().item() < 0.01 * max(1.0, ref_dx.abs().max().item())
+
+
 def test_maxpool_backward(T):
     import xdet_b200.ops as ops
     g = torch.Generator(device="cuda").manual_seed(2)

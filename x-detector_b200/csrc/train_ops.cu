@@ -54,18 +54,32 @@ __device__ __forceinline__ void block_col_reduce(float (*s)[8], const ColMap& m,
   }
   __syncthreads();
   const int nch = m.cgb * 8;  // channels of this block
+  float t = 0.f, t2 = 0.f;
+  int c = C;
   if ((int)threadIdx.x < nch) {
-    const int cg = threadIdx.x / 8, j = threadIdx.x % 8;
-    const int c = (blockIdx.x * m.cgb + cg) * 8 + j;
+    c = blockIdx.x * nch + threadIdx.x;
     if (c < C) {
-      float t = 0.f, t2 = 0.f;
       for (int r = 0; r < m.rl; ++r) {
-        t += s_a[r * m.cgb + cg][j];
-        if (sq) t2 += s_q[r * m.cgb + cg][j];
+        t += (&s_a[0][0])[r * nch + threadIdx.x];  // = s_a[r*cgb + cg][j] with threadIdx.x = cg*8 + j
+        if (sq) t2 += (&s_q[0][0])[r * nch + threadIdx.x];
       }
-      atomicAdd(sums + c, t);
-      if (sq) atomicAdd(sums + C + c, t2);
     }
+  }
+  // four neighbouring channels leave in ONE 16-byte reduction: the L2 atomic units see a quarter of the operations (with
+  // hundreds of blocks per tensor they, not HBM, bounded the small layers)
+  const float u1 = __shfl_down_sync(0xffffffffu, t, 1), u2 = __shfl_down_sync(0xffffffffu, t, 2),
+              u3 = __shfl_down_sync(0xffffffffu, t, 3);
+  const float v1 = __shfl_down_sync(0xffffffffu, t2, 1), v2 = __shfl_down_sync(0xffffffffu, t2, 2),
+              v3 = __shfl_down_sync(0xffffffffu, t2, 3);
+  if (c >= C) return;
+  if ((reinterpret_cast<uintptr_t>(sums) & 15) == 0) {
+    if ((threadIdx.x & 3) == 0) {  // (C is a multiple of 8: c + 3 < C)
+      atomicAdd(reinterpret_cast<float4*>(sums + c), make_float4(t, u1, u2, u3));
+      if (sq) atomicAdd(reinterpret_cast<float4*>(sums + C + c), make_float4(t2, v1, v2, v3));
+    }
+  } else {
+    atomicAdd(sums + c, t);
+    if (sq) atomicAdd(sums + C + c, t2);
   }
 }
 
@@ -96,19 +110,15 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const __nv_bfloat16* __r
   block_col_reduce(nullptr, m, C, a, q, SQ, sums);
 }
 
-__global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, long long rows, int C, float eps, float decay,
-                                   float* __restrict__ moving_mean, float* __restrict__ moving_var,
-                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
-                                   float* __restrict__ invstd_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double m = (double)sums[c] / (double)rows;
-  double var = (double)sums[C + c] / (double)rows - m * m;  // biased (what normalises the batch)
+__device__ __forceinline__ void bn_finalize_channel(double s0, double s1, int c, const float* gamma, const float* beta,
+                                                    long long rows, float eps, float decay, float* moving_mean,
+                                                    float* moving_var, float* scale, float* shift, float* mean_out,
+                                                    float* invstd_out) {
+  const double m = s0 / (double)rows;
+  double var = s1 / (double)rows - m * m;  // biased (what normalises the batch)
   if (var < 0.0) var = 0.0;
   const double inv = 1.0 / sqrt(var + (double)eps);
-  const float sc = (float)((double)gamma[c] * inv);
-  scale[c] = sc;
+  scale[c] = (float)((double)gamma[c] * inv);
   shift[c] = (float)((double)beta[c] - m * (double)gamma[c] * inv);
   mean_out[c] = (float)m;
   invstd_out[c] = (float)inv;
@@ -119,44 +129,117 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* 
   }
 }
 
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, long long rows, int C, float eps, float decay,
+                                   float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  bn_finalize_channel((double)sums[c], (double)sums[C + c], c, gamma, beta, rows, eps, decay, moving_mean, moving_var,
+                      scale, shift, mean_out, invstd_out);
+}
+
+// Statistics AND bn_finalize in one launch: the block that takes the last ticket finds every partial sum in L2, turns
+// them into scale / shift / mean / invstd (+ the moving averages) and leaves the scratch (sums, ticket) zeroed for the
+// next batch-norm on this stream -- so a layer costs no fill and no second tiny launch.
+__global__ void __launch_bounds__(256) bn_stats_finalize_kernel(
+    const __nv_bfloat16* __restrict__ x, long long rows, int C, int cs, int cgb, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float eps, float decay, float* __restrict__ moving_mean,
+    float* __restrict__ moving_var, float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+    float* __restrict__ invstd_out, float* __restrict__ sums /* [2][C], zero */, unsigned* __restrict__ ticket) {
+  const ColMap m(cgb);
+  float a[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = q[j] = 0.f;
+  if (m.c0 < C) {
+#pragma unroll 4
+    for (long long r = (long long)blockIdx.y * m.rl + m.lane_row; r < rows; r += (long long)gridDim.y * m.rl) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + r * cs + m.c0));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(h[k]);
+        a[2 * k] += f.x;
+        a[2 * k + 1] += f.y;
+        q[2 * k] = fmaf(f.x, f.x, q[2 * k]);
+        q[2 * k + 1] = fmaf(f.y, f.y, q[2 * k + 1]);
+      }
+    }
+  }
+  block_col_reduce(nullptr, m, C, a, q, true, sums);
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1u);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    // (one block serves every channel here: only the cancellation-prone E[x^2] - E[x]^2 is done in double)
+    const double inv_rows = 1.0 / (double)rows;
+    const double md = (double)__ldcg(sums + c) * inv_rows;
+    const double vd = fmax((double)__ldcg(sums + C + c) * inv_rows - md * md, 0.0);
+    const float mean = (float)md, var = (float)vd;
+    const float inv = 1.f / sqrtf(var + eps);
+    const float sc = gamma[c] * inv;
+    scale[c] = sc;
+    shift[c] = beta[c] - mean * sc;
+    mean_out[c] = mean;
+    invstd_out[c] = inv;
+    if (moving_mean) {  // fused batch norm feeds the UNBIASED variance to the moving average
+      const float unb = rows > 1 ? var * ((float)rows / (float)(rows - 1)) : var;
+      moving_mean[c] = moving_mean[c] * decay + (1.f - decay) * mean;
+      moving_var[c] = moving_var[c] * decay + (1.f - decay) * unb;
+    }
+    sums[c] = 0.f;
+    sums[C + c] = 0.f;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
 // g = dy * [x*scale+shift > 0] (ReLU mask recomputed from the saved pre-BN tensor); sums: [0,C) = sum g,
 // [C,2C) = sum g * xhat, xhat = (x - mean) * invstd.
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy,
-                                                            const __nv_bfloat16* __restrict__ x,
-                                                            const float* __restrict__ scale,
-                                                            const float* __restrict__ shift,
-                                                            const float* __restrict__ mean,
-                                                            const float* __restrict__ invstd, long long rows, int C,
-                                                            int relu, int cgb, float* __restrict__ sums) {
+__global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                               const __nv_bfloat16* __restrict__ x,
+                                                               const float* __restrict__ scale,
+                                                               const float* __restrict__ shift,
+                                                               const float* __restrict__ mean,
+                                                               const float* __restrict__ invstd, long long rows, int C,
+                                                               int relu, int cgb, float* __restrict__ sums) {
   const ColMap m(cgb);
-  float a[8], b[8], sc[8], sh[8], mu[8], is[8];
+  float a[8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
   if (m.c0 < C) {
+    {
+      // the loop keeps sum g and sum g*x; xhat = (x - mean)*invstd enters once per thread afterwards
+      float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sc[j] = scale[m.c0 + j];
-      sh[j] = shift[m.c0 + j];
-      mu[j] = mean[m.c0 + j];
-      is[j] = invstd[m.c0 + j];
-    }
+      for (int j = 0; j < 8; ++j) {
+        sc[j] = relu ? scale[m.c0 + j] : 0.f;
+        sh[j] = relu ? shift[m.c0 + j] : 1.f;  // (no ReLU: the mask below is always on)
+      }
 #pragma unroll 4
-    for (long long r = (long long)blockIdx.y * m.rl + m.lane_row; r < rows; r += (long long)gridDim.y * m.rl) {
-      const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + r * C + m.c0));
-      const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x + r * C + m.c0));
-      const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&ud);
-      const __nv_bfloat162* hx = reinterpret_cast<const __nv_bfloat162*>(&ux);
+      for (long long r = (long long)blockIdx.y * m.rl + m.lane_row; r < rows; r += (long long)gridDim.y * m.rl) {
+        const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + r * C + m.c0));
+        const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x + r * C + m.c0));
+        const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&ud);
+        const __nv_bfloat162* hx = reinterpret_cast<const __nv_bfloat162*>(&ux);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 fd = __bfloat1622float2(hd[k]), fx = __bfloat1622float2(hx[k]);
-        const float g0 = (!relu || fmaf(fx.x, sc[2 * k], sh[2 * k]) > 0.f) ? fd.x : 0.f;
-        const float g1 = (!relu || fmaf(fx.y, sc[2 * k + 1], sh[2 * k + 1]) > 0.f) ? fd.y : 0.f;
-        a[2 * k] += g0;
-        a[2 * k + 1] += g1;
-        b[2 * k] = fmaf(g0, (fx.x - mu[2 * k]) * is[2 * k], b[2 * k]);
-        b[2 * k + 1] = fmaf(g1, (fx.y - mu[2 * k + 1]) * is[2 * k + 1], b[2 * k + 1]);
+        for (int k = 0; k < 4; ++k) {
+          const float2 fd = __bfloat1622float2(hd[k]), fx = __bfloat1622float2(hx[k]);
+          const float g0 = (fmaf(fx.x, sc[2 * k], sh[2 * k]) > 0.f) ? fd.x : 0.f;
+          const float g1 = (fmaf(fx.y, sc[2 * k + 1], sh[2 * k + 1]) > 0.f) ? fd.y : 0.f;
+          a[2 * k] += g0;
+          a[2 * k + 1] += g1;
+          b[2 * k] = fmaf(g0, fx.x, b[2 * k]);
+          b[2 * k + 1] = fmaf(g1, fx.y, b[2 * k + 1]);
+        }
       }
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = (b[j] - mean[m.c0 + j] * a[j]) * invstd[m.c0 + j];
   }
   block_col_reduce(nullptr, m, C, a, b, true, sums);
 }
@@ -760,11 +843,13 @@ static int col_cgb(int C) {
   while (g * 2 <= 32 && g * 2 <= C / 8) g *= 2;
   return g;
 }
-static dim3 col_grid(long long rows, int C, int cgb) {
+static dim3 col_grid(long long rows, int C, int cgb, int per_sm = 4, int min_rows = 4) {
+  // one wave: at most per_sm blocks per SM over all channel-group columns, and at least min_rows rows per thread (a
+  // tensor of 7200 rows x 256 channels still spreads over ~225 blocks)
   const int gx = (C / 8 + cgb - 1) / cgb;
   const int rl = 256 / cgb;
-  long long slabs = (rows + (long long)rl * 8 - 1) / ((long long)rl * 8);  // >= 8 rows per thread
-  const long long cap = std::max(1LL, (long long)kNumSMs * 8 / gx);
+  long long slabs = (rows + (long long)rl * min_rows - 1) / ((long long)rl * min_rows);
+  const long long cap = std::max(1LL, (long long)kNumSMs * per_sm / gx);
   if (slabs > cap) slabs = cap;
   if (slabs < 1) slabs = 1;
   return dim3((unsigned)gx, (unsigned)slabs);
@@ -793,13 +878,31 @@ extern "C" int xdet_bn_finalize(const float* d_sums, const float* d_gamma, const
   return after_launch("bn_finalize_kernel");
 }
 
+extern "C" size_t xdet_bn_train_scratch_bytes(int C) { return sizeof(float) * 2 * (size_t)(C > 0 ? C : 0) + 16; }
+
+extern "C" int xdet_bn_train_stats_bf16(const void* d_x, long long rows, int C, int cs, const float* d_gamma,
+                                        const float* d_beta, float eps, float decay, float* d_moving_mean,
+                                        float* d_moving_var, float* d_scale, float* d_shift, float* d_mean,
+                                        float* d_invstd, void* d_scratch, void* stream) {
+  if (rows <= 0 || C <= 0) return fail(XDET_EINVAL, "bn_train_stats: empty");
+  if (C % 8 || cs % 8 || cs < C) return fail(XDET_EINVAL, "bn_train_stats: C and the row pitch must be multiples of 8");
+  if (!d_scratch) return fail(XDET_EINVAL, "bn_train_stats: no scratch");
+  const int cgb = col_cgb(C);
+  const dim3 grid = col_grid(rows, C, cgb, 6);
+  float* sums = reinterpret_cast<float*>(d_scratch);
+  bn_stats_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d_x), rows, C, cs, cgb, d_gamma, d_beta, eps, decay, d_moving_mean,
+      d_moving_var, d_scale, d_shift, d_mean, d_invstd, sums, reinterpret_cast<unsigned*>(sums + 2 * (size_t)C));
+  return after_launch("bn_stats_finalize_kernel");
+}
+
 extern "C" int xdet_bn_relu_bwd_bf16(const void* d_dy, const void* d_x, const float* d_scale, const float* d_shift,
                                      const float* d_mean, const float* d_invstd, long long rows, int C, int relu,
-                                     const void* d_add_in, float* d_sums, void* d_dx, void* stream) {
+                                     const void* d_add_in, float* d_sums, void* d_dx, int sums_zeroed, void* stream) {
   if (rows <= 0 || C <= 0) return XDET_OK;
   if (C % 8) return fail(XDET_EINVAL, "bn_relu_bwd: C must be a multiple of 8");
   cudaStream_t st = (cudaStream_t)stream;
-  XDET_TRY(check_cuda(cudaMemsetAsync(d_sums, 0, sizeof(float) * 2 * C, st), "memset(bn sums)"));
+  if (!sums_zeroed) XDET_TRY(check_cuda(cudaMemsetAsync(d_sums, 0, sizeof(float) * 2 * C, st), "memset(bn sums)"));
   const int cgb = col_cgb(C);
   const dim3 grid = col_grid(rows, C, cgb);
   bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(d_dy),

@@ -250,7 +250,8 @@ class BNRelu(object):
         cs = self.x.shape[-1]
         assert cs == self.vec.seg and dy.shape == self.x.shape and dy.is_contiguous()
         # the kernel's sums ARE the gradient: [0,cs) = dbeta, [cs,2cs) = dgamma, written into the flat buffer
-        return T.bn_relu_bwd_into(dy, self.x, self.st, True, self.vec.grad, add_in)
+        # (begin_step cleared the buffer and this is the view's only writer: no second memset)
+        return T.bn_relu_bwd_into(dy, self.x, self.st, True, self.vec.grad, add_in, sums_zeroed=True)
 
 
 class Bottleneck(object):

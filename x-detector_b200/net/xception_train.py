@@ -49,8 +49,9 @@ def _image_nhwc(images):
 
 def bn_relu_bwd_into(dy, x, st, relu, grad_view):
     """xdet_bn_relu_bwd_bf16 with its column sums written straight into ``grad_view`` ([0,C) = dbeta, [C,2C) = dgamma:
-    the (beta, gamma) order of the trainer's VecParam)."""
-    return T.bn_relu_bwd_into(dy, x, st, relu, grad_view)
+    the (beta, gamma) order of the trainer's VecParam; the flat gradient buffer is cleared when the step begins and this is
+    the view's only writer, so the kernel need not clear it again)."""
+    return T.bn_relu_bwd_into(dy, x, st, relu, grad_view, sums_zeroed=True)
 
 
 class Conv(object):

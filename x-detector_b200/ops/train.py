@@ -39,18 +39,35 @@ def col_sums_into(x2d, sums, with_squares=False, C=None):
                                                         sums.data_ptr(), _st()))
 
 
-def bn_relu_bwd_into(dy, x, st, relu, sums_view, add_in=None):
+def bn_relu_bwd_into(dy, x, st, relu, sums_view, add_in=None, sums_zeroed=False):
     """Backward of y = [relu](x*scale+shift) with batch statistics; ``sums_view`` ([0,cs) = dbeta, [cs,2cs) = dgamma) is
-    overwritten -- usually a view of the flat gradient buffer.  Returns dx (dtype of x)."""
+    overwritten -- usually a view of the flat gradient buffer (``sums_zeroed``: the caller vouches that it holds zeros,
+    the bf16 path then skips its memset).  Returns dx (dtype of x)."""
     cs = x.shape[-1]
     assert dy.shape == x.shape and dy.dtype == x.dtype and dy.is_contiguous() and x.is_contiguous()
     assert sums_view.numel() == 2 * cs and (add_in is None or (add_in.is_contiguous() and add_in.dtype == x.dtype))
     dx = torch.empty_like(x)
-    fn = _native.lib().xdet_bn_relu_bwd_f32 if x.dtype == torch.float32 else _native.lib().xdet_bn_relu_bwd_bf16
-    _native.check(fn(dy.data_ptr(), x.data_ptr(), st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(),
-                     st.invstd.data_ptr(), st.rows, cs, 1 if relu else 0, _p(add_in), sums_view.data_ptr(),
-                     dx.data_ptr(), _st()))
+    args = (dy.data_ptr(), x.data_ptr(), st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(),
+            st.invstd.data_ptr(), st.rows, cs, 1 if relu else 0, _p(add_in), sums_view.data_ptr(), dx.data_ptr())
+    if x.dtype == torch.float32:
+        _native.check(_native.lib().xdet_bn_relu_bwd_f32(*args, _st()))
+    else:
+        _native.check(_native.lib().xdet_bn_relu_bwd_bf16(*args, 1 if sums_zeroed else 0, _st()))
     return dx
+
+
+_BN_SCRATCH = {}
+
+
+def _bn_scratch(device, C):
+    """The zeroed scratch of xdet_bn_train_stats_bf16 for the current stream (the kernel hands it back zeroed; launches
+    on one stream are ordered, so one buffer per stream serves every layer)."""
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    buf = _BN_SCRATCH.get(key)
+    need = _native.lib().xdet_bn_train_scratch_bytes(max(C, 4096))
+    if buf is None or buf.numel() < need:
+        buf = _BN_SCRATCH[key] = torch.zeros(need, dtype=torch.uint8, device=device)
+    return buf
 
 
 class BNState(object):
@@ -62,10 +79,17 @@ def bn_train(x, gamma, beta, eps, decay=None, moving_mean=None, moving_var=None)
     """Batch statistics of x [..., C] bf16 -> BNState (scale/shift normalise with the BATCH mean/variance)."""
     C = x.shape[-1]
     x2 = x.reshape(-1, C)
-    sums = col_stats(x2, True)
     st = BNState()
     st.rows = x2.shape[0]
-    st.scale, st.shift, st.mean, st.invstd = (torch.empty(C, dtype=torch.float32, device=x.device) for _ in range(4))
+    st.scale, st.shift, st.mean, st.invstd = torch.empty((4, C), dtype=torch.float32, device=x.device).unbind(0)
+    if x.dtype == torch.bfloat16:  # statistics + finalize in one launch over a self-cleaning scratch
+        assert x2.is_contiguous()
+        _native.check(_native.lib().xdet_bn_train_stats_bf16(
+            x2.data_ptr(), st.rows, C, C, gamma.data_ptr(), beta.data_ptr(), eps, 0.0 if decay is None else decay,
+            _p(moving_mean), _p(moving_var), st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(),
+            st.invstd.data_ptr(), _bn_scratch(x.device, C).data_ptr(), _st()))
+        return st
+    sums = col_stats(x2, True)
     _native.check(_native.lib().xdet_bn_finalize(sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), st.rows, C, eps,
                                                  0.0 if decay is None else decay, _p(moving_mean), _p(moving_var),
                                                  st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(),
