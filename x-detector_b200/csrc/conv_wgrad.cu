@@ -329,10 +329,23 @@ static int launch_wgrad(const void* d_x, const void* d_dy, const xdet_wgrad_desc
   a.a_boxes = 2;
   a.b_boxes = a.BN / 64;
   const int units = a.taps * a.co_tiles * a.ci_tiles;
-  // pixel splits: just enough to put one item on every SM (each extra split costs a full tile of fp32 atomics),
-  // none when the (tap, Cout tile, Cin tile) units already fill the GPU, and at least 4 pixel tiles per item
-  int splits = d->splits > 0 ? d->splits : (units >= 100 ? 1 : (kNumSMs + units - 1) / units);
-  if (d->splits <= 0 && splits > a.pix_tiles / 4) splits = a.pix_tiles / 4;
+  // pixel splits: the persistent grid runs ceil(items / SMs) rounds of items, an item costs its pixel tiles plus a few
+  // tiles' worth of ramp and fp32 reductions (2 + BN/32) -- take the split count with the cheapest rounds x item product (the
+  // smallest such count: every extra split adds a full tile of atomics).  E.g. 9 taps of a 64 -> 64 3x3: 16 splits =
+  // 144 items in ONE round, where "one item per SM, rounded up" (17 splits, 153 items) ran two.
+  int splits = d->splits;
+  if (splits <= 0) {
+    const int max_splits = std::max(1, std::min(a.pix_tiles / 4, 4 * kNumSMs));
+    long long best_cost = -1;
+    for (int sp = 1; sp <= max_splits; ++sp) {
+      const long long rounds = ((long long)units * sp + kNumSMs - 1) / kNumSMs;
+      const long long cost = rounds * ((a.pix_tiles + sp - 1) / sp + 2 + a.BN / 32);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        splits = sp;
+      }
+    }
+  }
   if (splits > a.pix_tiles) splits = a.pix_tiles;
   if (splits < 1) splits = 1;
   a.overwrite = 0;  // dw is accumulated into (a caller-zeroed buffer or a partial sum)
