@@ -578,20 +578,28 @@ __device__ __forceinline__ float iou_ref(const float4 g, const float4 b) {  // i
 __device__ __forceinline__ bool inside_ok(const float4 b, float border) {
   return b.x >= -border && b.y >= -border && b.z < 1.f + border && b.w < 1.f + border;
 }
-// pass 1: per ground truth the best box (first maximum): 64-bit atomicMax on (iou bits << 32 | ~index)
-__global__ void match_gt_argmax_kernel(const float* __restrict__ boxes, const float* __restrict__ gt,
-                                       const int* __restrict__ gt_labels, int A, int G, float border,
-                                       unsigned long long* __restrict__ best /* [N,G], zero-filled */) {
+// pass 1: per ground truth the best box (first maximum): 64-bit atomicMax on (iou bits << 32 | ~index).  A warp first
+// settles its own maximum (largest overlap, then smallest index) and sends ONE atomic per ground truth: every thread
+// hammering the same G addresses made this the longest kernel of the target assignment.
+__global__ void __launch_bounds__(256) match_gt_argmax_kernel(const float* __restrict__ boxes, long long box_img_stride,
+                                                              const float* __restrict__ gt,
+                                                              const int* __restrict__ gt_labels, int A, int G,
+                                                              float border,
+                                                              unsigned long long* __restrict__ best /* [N,G], zero */) {
   const int img = blockIdx.y;
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= A) return;
-  const float4 b = reinterpret_cast<const float4*>(boxes)[(long long)img * A + a];
-  const bool in = inside_ok(b, border);
+  const bool live = a < A;
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) b = reinterpret_cast<const float4*>(boxes + (long long)img * box_img_stride)[a];
+  const bool in = live && inside_ok(b, border);
   for (int g = 0; g < G; ++g) {
-    if (gt_labels[img * G + g] <= 0) continue;
+    if (gt_labels[img * G + g] <= 0) continue;  // (uniform over the block)
     const float ov = in ? iou_ref(reinterpret_cast<const float4*>(gt)[img * G + g], b) : 0.f;
-    const unsigned long long key = ((unsigned long long)__float_as_uint(ov) << 32) | (0xFFFFFFFFu - (unsigned)a);
-    atomicMax(best + img * G + g, key);
+    const unsigned bits = live ? __float_as_uint(ov) : 0u;  // overlaps are >= 0: their bit patterns order like the values
+    const unsigned top = __reduce_max_sync(0xffffffffu, bits);
+    const unsigned first = __reduce_min_sync(0xffffffffu, (live && bits == top) ? (unsigned)a : 0xFFFFFFFFu);
+    if ((threadIdx.x & 31) == 0 && first != 0xFFFFFFFFu)
+      atomicMax(best + img * G + g, ((unsigned long long)top << 32) | (0xFFFFFFFFu - first));
   }
 }
 // pass 2: do_dual_max_match + encode.  labels_out: matched class (> 0), 0 = background, -1 = ignore.
@@ -1027,19 +1035,10 @@ extern "C" int xdet_match_encode(const float* d_boxes, long long box_img_stride,
   unsigned long long* best = reinterpret_cast<unsigned long long*>(d_workspace);
   XDET_TRY(check_cuda(cudaMemsetAsync(best, 0, sizeof(unsigned long long) * (size_t)N * G, st), "memset(match)"));
   dim3 grid((unsigned)((A + 255) / 256), (unsigned)N);
-  // pass 1 reads boxes with the same per-image stride
-  if (box_img_stride == 0) {
-    // shared boxes: one launch per image keeps the kernel simple (N is small)
-    for (int i = 0; i < N; ++i) {
-      match_gt_argmax_kernel<<<dim3(grid.x, 1), 256, 0, st>>>(d_boxes, d_gt + (long long)i * G * 4, d_gt_labels + (long long)i * G,
-                                                              A, G, allowed_border, best + (long long)i * G);
-      XDET_TRY(after_launch("match_gt_argmax_kernel"));
-    }
-  } else {
-    if (box_img_stride != (long long)A * 4) return fail(XDET_EINVAL, "match_encode: box_img_stride must be 0 or A*4");
-    match_gt_argmax_kernel<<<grid, 256, 0, st>>>(d_boxes, d_gt, d_gt_labels, A, G, allowed_border, best);
-    XDET_TRY(after_launch("match_gt_argmax_kernel"));
-  }
+  if (box_img_stride != 0 && box_img_stride != (long long)A * 4)
+    return fail(XDET_EINVAL, "match_encode: box_img_stride must be 0 or A*4");
+  match_gt_argmax_kernel<<<grid, 256, 0, st>>>(d_boxes, box_img_stride, d_gt, d_gt_labels, A, G, allowed_border, best);
+  XDET_TRY(after_launch("match_gt_argmax_kernel"));
   match_encode_kernel<<<grid, 256, 0, st>>>(d_boxes, box_img_stride, d_ref_yxhw, d_gt, d_gt_labels, best, A, G,
                                             allowed_border, high_thres, low_thres, prior_scaling4[0], prior_scaling4[1],
                                             prior_scaling4[2], prior_scaling4[3], d_labels, d_targets, d_scores);

@@ -340,6 +340,7 @@ class LightHeadTrainer(object):
         self.anchors_yxhw = torch.stack([cy, cx, hh, ww], -1).contiguous()
         self.anchors_pt = torch.stack([cy - hh / 2., cx - ww / 2., cy + hh / 2., cx + ww / 2.], -1).contiguous()
         self.side = torch.cuda.Stream(device=self.device)
+        self.side2 = torch.cuda.Stream(device=self.device)
         self.comm = torch.cuda.Stream(device=self.device)
         self.marks = []  # (stage name, index of its first gradient request): where the all-reduce buckets start
         with conv_ops.precision(self.precision):
@@ -654,33 +655,34 @@ class LightHeadTrainer(object):
         t = self.t
         rpn_feat = self.fwd_backbone_mid()
         self.fwd_rpn(rpn_feat)
-        # FORK: RPN losses, proposals and RoI targets on a second stream (the reference pins proposals /
-        # ext_encode_rois to /cpu:0; here they run beside block_layer4 / the exit flow + large_sep_kernel, whose
-        # convolutions leave a few SMs to the one-CTA-per-image kernels meanwhile)
+        # FORK: proposals + RoI targets on a second stream, anchor targets + RPN losses on a third (the reference pins
+        # proposals / ext_encode_rois to /cpu:0; here they run beside block_layer4 / the exit flow + large_sep_kernel,
+        # whose convolutions leave a few SMs to the one-CTA-per-image kernels meanwhile).  The RPN losses are ready first:
+        # the RPN head's backward fills the time the proposals still need, and only then the head waits for its RoIs.
         main = torch.cuda.current_stream()
-        side = self.side
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            # first what the head's forward waits for (proposals, RoI targets), then what only the backward needs (anchor
-            # targets, RPN sampling and losses): the second half keeps running beside the head's forward and backward
-            self.fwd_rpn_decode()
+        self.fwd_rpn_decode()
+        self.side.wait_stream(main)
+        self.side2.wait_stream(main)
+        with torch.cuda.stream(self.side):
             self.fwd_proposals_and_targets()
             ev_rois = torch.cuda.Event()
-            ev_rois.record(side)
+            ev_rois.record(self.side)
+        with torch.cuda.stream(self.side2):
             self.fwd_rpn_losses()
             t.ev_rpn = torch.cuda.Event()
-            t.ev_rpn.record(side)
+            t.ev_rpn.record(self.side2)
         conv_ops.MAX_CTAS = 148 - 12
         try:
             backbone = self.fwd_backbone_exit()
             self.fwd_thin(backbone)
         finally:
             conv_ops.MAX_CTAS = 0
-        main.wait_event(ev_rois)  # JOIN (proposal half)
-        for t_ in (t.score, t.boxes, t.rois_all, t.rlab, t.rtgt, t.rsc, t.roi_idx, t.rois, t.roi_tgt, t.roi_lab, t.yxhw):
+        self.backward_rpn_head()   # JOIN (RPN-loss stream)
+        main.wait_event(ev_rois)   # JOIN (proposal stream)
+        for t_ in (t.rois_all, t.rlab, t.rtgt, t.rsc, t.roi_idx, t.rois, t.roi_tgt, t.roi_lab, t.yxhw):
             t_.record_stream(main)
         self.fwd_head()
-        self.backward()  # (joins the RPN-loss half where it needs d_rpn)
+        self.backward()
         self.apply_gradients(apply_update)
         return self.outputs()
 
@@ -882,6 +884,19 @@ class LightHeadTrainer(object):
         t.sel, t.flat_sel, t.feat, t.M2, t.cin = sel, flat_sel, feat, M2, cin
         return t.out2[:, :nc], t.out2[:, nc:], t.head_loss
 
+    def backward_rpn_head(self):
+        """Backward of the RPN head from the gradient of its two losses: needs only ``fwd_rpn_losses`` (not the proposals
+        or the head), so the step runs it early; leaves the gradient with respect to the RPN feature in ``t.d_rpn_feat``."""
+        t = self.t
+        if getattr(t, "ev_rpn", None) is not None:  # the losses were computed on another stream
+            main = torch.cuda.current_stream()
+            main.wait_event(t.ev_rpn)
+            for t_ in (t.glabels, t.gtargets, t.rpn_idx, t.d_rpn, t.rpn_ce, t.rpn_loc):
+                t_.record_stream(main)
+        dr = T.relu_bwd(self.rpn_out.bwd(t.d_rpn), t.r)
+        t.d_rpn_feat = self.rpn_conv.bwd(dr)
+        return t.d_rpn_feat
+
     def backward(self):
         """The explicit backward of everything above (TensorFlow: optimizer.compute_gradients, train:436-441)."""
         t, nc = self.t, self.params['num_classes']
@@ -911,14 +926,10 @@ class LightHeadTrainer(object):
         T.col_sums_into(do.reshape(N * fm * fm, 496), self.sep_b_bias_vec.grad)
         dmid = self.sep_b.bwd(do)
         dbackbone = self.sep_a.bwd(dmid)
-        # ---- RPN head ----
-        if getattr(t, "ev_rpn", None) is not None:  # JOIN (RPN-loss half of the second stream)
-            main = torch.cuda.current_stream()
-            main.wait_event(t.ev_rpn)
-            for t_ in (t.glabels, t.gtargets, t.rpn_idx, t.d_rpn, t.rpn_ce, t.rpn_loc):
-                t_.record_stream(main)
-        dr = T.relu_bwd(self.rpn_out.bwd(t.d_rpn), t.r)
-        d_rpn_feat = self.rpn_conv.bwd(dr)
+        # ---- RPN head (unless the step already ran it while it waited for the proposals) ----
+        if getattr(t, "d_rpn_feat", None) is None:
+            self.backward_rpn_head()
+        d_rpn_feat = t.d_rpn_feat
         # ---- backbone (each stage's gradient bucket goes to the communication stream as soon as it is complete) ----
         if self.xception:
             self._stage_done("heads")
