@@ -127,6 +127,8 @@ typedef struct {
   int block_n;  /* 0 = auto; otherwise the N tile (multiple of 16, <= 256; of 64 for bf16 NHWC outputs) */
   int epi_groups; /* 0 = auto; 1 or 2 epilogue warpgroups (tuning / tests) */
   int max_ctas; /* 0 = one persistent CTA per SM; otherwise an upper bound (leaves SMs to a concurrent stream) */
+  float* stats; /* NULL, or [2][Cout] fp32 the kernel ADDS the column sums and sums of squares of the stored bf16 `out`
+                   to (training: the statistics of the batch-norm that reads `out`; Cout % 8 == 0, 16-byte aligned) */
 } xdet_conv_desc;
 int xdet_conv2d_bf16(const void* d_in, const xdet_conv_desc* desc, void* stream);
 /* Convolutions are launched with programmatic stream serialization (their prologue overlaps the predecessor's tail;
@@ -409,6 +411,12 @@ size_t xdet_bn_train_scratch_bytes(int C);
 int xdet_bn_train_stats_bf16(const void* d_x, long long rows, int C, int cs, const float* d_gamma, const float* d_beta,
                              float eps, float decay, float* d_moving_mean, float* d_moving_var, float* d_scale,
                              float* d_shift, float* d_mean, float* d_invstd, void* d_scratch, void* stream);
+/* bn_finalize + affine (+ReLU) in one launch, from statistics some producer already accumulated (xdet_conv_desc.stats):
+ * every block derives scale/shift of its channels from d_sums ([0,C) sums, [C,2C) sums of squares over `rows` rows);
+ * the first row of blocks also writes d_scale/d_shift/d_mean/d_invstd (what the backward reads) and the moving averages. */
+int xdet_bn_train_apply_bf16(const void* d_x, void* d_y, long long rows, int C, const float* d_sums, const float* d_gamma,
+                             const float* d_beta, float eps, float decay, float* d_moving_mean, float* d_moving_var,
+                             float* d_scale, float* d_shift, float* d_mean, float* d_invstd, int relu, void* stream);
 /* sums_zeroed != 0: d_sums (2*C floats: dbeta, dgamma) already holds zeros (e.g. a slice of a gradient buffer cleared at
  * the start of the step) -- the call skips its own memset. */
 int xdet_bn_relu_bwd_bf16(const void* d_dy, const void* d_x, const float* d_scale, const float* d_shift,

@@ -158,6 +158,57 @@ def test_bn_train_stats_one_launch_over_a_self_cleaning_scratch(T, rows, C):
         assert (dx.double() - ref_dx).abs().max().item() < 0.01 * max(1.0, ref_dx.abs().max().item())
 
 
+@pytest.mark.parametrize("case", [
+    # N, H, W, cin, cout, k, stride, dil, residual
+    (8, 30, 30, 256, 1024, 1, 1, 1, True),     # flattened 1x1 with the residual epilogue, 4 N tiles of 256
+    (2, 120, 120, 64, 64, 3, 1, 1, False),     # wide rows: 120 of 128 tile columns are inside the image
+    (3, 61, 45, 128, 136, 3, 2, 1, False),     # ragged tiles in both directions, a partial channel chunk, stride 2
+    (8, 30, 30, 512, 512, 3, 1, 2, False),     # the dilated block_layer4 shape
+    (4, 30, 30, 2048, 512, 1, 1, 1, False),
+])
+def test_conv_epilogue_batch_statistics(T, case):
+    """conv2d_nhwc(stats=...): the epilogue's per-channel sums / sums of squares of the STORED bf16 output (rows outside
+    the image and channels outside Cout excluded, statistics added to what the buffer holds), then bn_train_apply against
+    the standalone statistics kernel + affine_relu on the same tensor."""
+    import xdet_b200.ops as ops
+    N, H, W, cin, cout, k, stride, dil, with_res = case
+    g = torch.Generator(device="cuda").manual_seed(cin + cout)
+    x = torch.randn((N, H, W, cin), generator=g, device="cuda").to(torch.bfloat16)
+    w = torch.randn((cout, cin, k, k), generator=g, device="cuda") * (1.0 / (cin * k * k) ** 0.5)
+    wp = ops.pack_conv_weight(w)
+    bias = torch.randn(cout, generator=g, device="cuda") * 0.3
+    Ho, Wo = -(-H // stride), -(-W // stride)
+    res = torch.randn((N, Ho, Wo, cout), generator=g, device="cuda").to(torch.bfloat16) if with_res else None
+    pre = torch.full((2 * cout,), 0.5, device="cuda")     # the kernel ADDS
+    sums = pre.clone()
+    y = ops.conv2d_nhwc(x, wp, cout, k, k, dilation=(dil, dil), strides=(stride, stride), bias=bias, residual=res,
+                        stats=sums)
+    y_plain = ops.conv2d_nhwc(x, wp, cout, k, k, dilation=(dil, dil), strides=(stride, stride), bias=bias, residual=res)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_plain)
+    yd = y.double().reshape(-1, cout)
+    ref = torch.cat([yd.sum(0), (yd * yd).sum(0)]) + 0.5
+    scale = torch.cat([yd.abs().sum(0), (yd * yd).sum(0)]) + 1.0
+    assert ((sums.double() - ref).abs() / scale).max().item() < 2e-6
+    gamma = torch.rand(cout, generator=g, device="cuda") + 0.5
+    beta = torch.randn(cout, generator=g, device="cuda") * 0.2
+    mm, mv = torch.zeros(cout, device="cuda"), torch.ones(cout, device="cuda")
+    mm2, mv2 = mm.clone(), mv.clone()
+    z, st = T.bn_train_apply(y, sums - pre, gamma, beta, 1e-5, 0.997, mm, mv, relu=True)
+    st0 = T.bn_train(y, gamma, beta, 1e-5, 0.997, mm2, mv2)
+    z0 = ops.affine_relu(y, st0.scale, st0.shift, relu=True)
+    torch.cuda.synchronize()
+    assert st.rows == st0.rows
+    for a, b in ((st.mean, st0.mean), (st.invstd, st0.invstd), (st.scale, st0.scale), (st.shift, st0.shift), (mm, mm2),
+                 (mv, mv2)):
+        assert ((a - b).abs() / (1e-3 + b.abs())).max().item() < 2e-4
+    assert (z.float() - z0.float()).abs().max().item() <= 0.02 * max(1.0, z0.float().abs().max().item())
+    # and bit for bit when fed the very same sums
+    sums2 = T.col_stats(y.reshape(-1, cout), True)
+    z2, st2 = T.bn_train_apply(y, sums2, gamma, beta, 1e-5)
+    assert torch.equal(z2, ops.affine_relu(y, st2.scale, st2.shift, relu=True))
+
+
 def test_maxpool_backward(T):
     import xdet_b200.ops as ops
     g = torch.Generator(device="cuda").manual_seed(2)

@@ -101,6 +101,8 @@ def _declare_train(lib):
     lib.xdet_col_stats_bf16.argtypes = [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p]
     lib.xdet_bn_finalize.argtypes = [c_void_p] * 3 + [c_ll, c_int, c_float, c_float] + [c_void_p] * 7
     lib.xdet_bn_relu_bwd_bf16.argtypes = [c_void_p] * 6 + [c_ll, c_int, c_int] + [c_void_p] * 3 + [c_int, c_void_p]
+    lib.xdet_bn_train_apply_bf16.argtypes = [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_float,
+                                             c_float] + [c_void_p] * 6 + [c_int, c_void_p]
     lib.xdet_bn_train_scratch_bytes.restype = c_size_t
     lib.xdet_bn_train_scratch_bytes.argtypes = [c_int]
     lib.xdet_bn_train_stats_bf16.argtypes = [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_float, c_float] + \

@@ -74,6 +74,8 @@ struct ConvGemmArgs {
   long long out_sn, out_sy, out_sx, out_sc;
   const float* scale2;
   const float* bias2;
+  float* stats;    // [2][Cout] sums / sums of squares of the stored bf16 outputs (NULL: off)
+  int stats_cols;  // Cout rounded up to 64: length of one of the CTA's two shared-memory accumulators
 };
 
 struct TileCoord {
@@ -116,8 +118,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
   uint64_t* res_full_bar = tmem_empty_bar + 2;       // [2 groups][kMaxSlots]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full_bar + 2 * kMaxSlots);
+  // statistics (p.stats): [2 groups][4 warps][8 units][16] partials of the chunk in flight, then the groups' accumulators
+  // [2 groups][2][stats_cols] (16-byte aligned: see `tail`)
+  float* s_part = reinterpret_cast<float*>(tmem_ptr + 16);
+  float* s_stats = s_part + 2 * 4 * 8 * 16;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.stats)
+    for (int i = threadIdx.x; i < 4 * p.stats_cols; i += kGemmThreads) s_stats[i] = 0.f;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&map_a);
@@ -363,6 +371,62 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               issue_residual(q + 2);
             }
           }
+          if (p.stats) {
+            // Batch-norm statistics of what was just stored (the bf16 values, as the next layer reads them): the staged
+            // 128 x 64 tile is re-read column-wise -- thread = (16-byte unit u of 8 channels, row group rg), rows
+            // rg, rg+16, ... -- reduced over the warp's four row groups by shuffles and added to the CTA's accumulators.
+            // (The slot is not rewritten before every thread of the group has passed the next chunk's barrier.)
+            const int u = e & 7, rg = e >> 3;
+            const int bw_shift = __ffs(p.BW) - 1;
+            float sa[8], sq[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) sa[jj] = sq[jj] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int r = rg + 16 * k;
+              const bool ok = (tc.y0 + (r >> bw_shift) < p.Hout) && (tc.x0 + (r & (p.BW - 1)) < p.Wout);
+              if (ok) {
+                const uint4 w4 = *reinterpret_cast<const uint4*>(obuf + (size_t)r * 128 + ((uint32_t)(u ^ (r & 7)) << 4));
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w4);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                  const float2 f = __bfloat1622float2(h[jj]);
+                  sa[2 * jj] += f.x;
+                  sa[2 * jj + 1] += f.y;
+                  sq[2 * jj] = fmaf(f.x, f.x, sq[2 * jj]);
+                  sq[2 * jj + 1] = fmaf(f.y, f.y, sq[2 * jj + 1]);
+                }
+              }
+            }
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              sa[jj] += __shfl_xor_sync(0xffffffffu, sa[jj], 8);
+              sq[jj] += __shfl_xor_sync(0xffffffffu, sq[jj], 8);
+              sa[jj] += __shfl_xor_sync(0xffffffffu, sa[jj], 16);
+              sq[jj] += __shfl_xor_sync(0xffffffffu, sq[jj], 16);
+            }
+            // the four warps' partials meet in shared memory (plain stores: shared-memory float atomics are CAS loops);
+            // after the barrier thread e owns value e & 15 (8 sums, 8 squares) of unit e >> 4 and adds it to the GROUP's
+            // accumulator -- the only writer of that element, since a group works through its chunks one at a time
+            float* part = s_part + grp * (4 * 8 * 16);
+            if (lane < 8) {
+              float4* dst = reinterpret_cast<float4*>(part + ((warp & 3) * 8 + u) * 16);
+              dst[0] = make_float4(sa[0], sa[1], sa[2], sa[3]);
+              dst[1] = make_float4(sa[4], sa[5], sa[6], sa[7]);
+              dst[2] = make_float4(sq[0], sq[1], sq[2], sq[3]);
+              dst[3] = make_float4(sq[4], sq[5], sq[6], sq[7]);
+            }
+            ptx::named_bar_sync(bar_id, kEpiThreads);
+            {
+              const int uu = e >> 4, kk = e & 15;
+              const int c = tc.n0 + col0 + uu * 8 + (kk & 7);
+              if (c < p.Cout) {
+                const float v = part[(0 * 8 + uu) * 16 + kk] + part[(1 * 8 + uu) * 16 + kk] +
+                                part[(2 * 8 + uu) * 16 + kk] + part[(3 * 8 + uu) * 16 + kk];
+                s_stats[(grp * 2 + (kk >> 3)) * p.stats_cols + c] += v;
+              }
+            }
+          }
         }
         if (!released) release_tmem();  // no chunk of this tile (or only skipped ones) was this group's
       } else {
@@ -407,6 +471,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (as == 0) aphase ^= 1;
     }
     if (p.tma_epilogue && leader) ptx::bulk_wait_all();  // staging tiles must outlive their stores
+    if (p.stats) {
+      // every epilogue warp of the CTA has added its last chunk: the groups' accumulators are summed and leave as one
+      // reduction per element (a 148th of what per-tile atomics would send to the same few cache lines)
+      ptx::named_bar_sync(5u, (uint32_t)(kEpiThreads * p.epi_groups));
+      const int ei = grp * kEpiThreads + e, nthr = kEpiThreads * p.epi_groups;
+      for (int i = ei * 4; i < 2 * p.Cout; i += nthr * 4) {  // (Cout % 8 == 0: a group of four never straddles the halves)
+        const int h = i >= p.Cout ? 1 : 0, c = i - h * p.Cout;
+        float4 v = *reinterpret_cast<const float4*>(s_stats + h * p.stats_cols + c);
+        if (p.epi_groups == 2) {
+          const float4 w = *reinterpret_cast<const float4*>(s_stats + (2 + h) * p.stats_cols + c);
+          v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+        if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
+          asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.stats + i), "f"(v.x), "f"(v.y),
+                       "f"(v.z), "f"(v.w)
+                       : "memory");
+      }
+    }
   }
 
   ptx::tc_fence_before();
@@ -555,7 +637,15 @@ extern "C" int xdet_conv2d_bf16(const void* d_in, const xdet_conv_desc* d, void*
   if (d->epi_groups == 1 || d->epi_groups == 2) a.epi_groups = a.tma_epilogue ? d->epi_groups : 1;
   a.n_slots = a.tma_epilogue ? (a.has_res ? 3 : 2) : 0;
   a.n_out2 = a.has_out2 ? (a.has_res ? 1 : 2) : 0;
-  const size_t tail = 2 * 4 * kMaxBN * sizeof(float) + (2 * kMaxStages + 4 + 2 * kMaxSlots) * sizeof(uint64_t) + 64;
+  const int stats_cols = d->stats ? (d->Cout + 63) / 64 * 64 : 0;
+  if (d->stats) {
+    if (!a.tma_epilogue || a.skip_out)
+      return fail(XDET_EINVAL, "conv2d: statistics need a stored bf16 NHWC `out`");
+    if (d->Cout % 8 || d->Cout > 2048 || (reinterpret_cast<uintptr_t>(d->stats) & 15))
+      return fail(XDET_EINVAL, "conv2d: statistics need Cout %% 8 == 0, Cout <= 2048 and a 16-byte aligned buffer");
+  }
+  const size_t tail = 2 * 4 * kMaxBN * sizeof(float) + (2 * kMaxStages + 4 + 2 * kMaxSlots) * sizeof(uint64_t) + 64 +
+                      (d->stats ? (2 * 4 * 8 * 16 + 4 * (size_t)stats_cols) * sizeof(float) : 0);
   int BN = d->block_n > 0 ? d->block_n : pick_block_n(d->Cout, m_tiles, a.num_k_blocks, a.tma_epilogue != 0);
   if (BN % 16 != 0 || BN < 16 || BN > kMaxBN) return fail(XDET_EINVAL, "conv2d: block_n must be a multiple of 16 in [16,256]");
   if (a.tma_epilogue && BN % 64 != 0) return fail(XDET_EINVAL, "conv2d: block_n must be a multiple of 64 for bf16 NHWC outputs");
@@ -597,6 +687,8 @@ extern "C" int xdet_conv2d_bf16(const void* d_in, const xdet_conv_desc* d, void*
   a.out_sc = d->out_sc;
   a.scale2 = d->scale2;
   a.bias2 = d->bias2;
+  a.stats = d->stats;
+  a.stats_cols = stats_cols;
 
   CUtensorMap map_a, map_b, map_out, map_res, map_out2;
   if (fold) {

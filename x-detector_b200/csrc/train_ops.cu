@@ -198,6 +198,73 @@ __global__ void __launch_bounds__(256) bn_stats_finalize_kernel(
   if (threadIdx.x == 0) *ticket = 0u;
 }
 
+// bn_finalize + normalise (+ReLU) in one launch when the statistics already exist (the producing convolution's epilogue
+// accumulated them): every thread derives scale / shift of its 8 channels from the sums; the first row of blocks also
+// stores them (with mean / invstd: what the backward reads) and advances the moving averages.
+__global__ void __launch_bounds__(256) bn_apply_finalize_kernel(
+    const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long rows, int C, int cgb,
+    const float* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+    float decay, float* __restrict__ moving_mean, float* __restrict__ moving_var, float* __restrict__ scale_out,
+    float* __restrict__ shift_out, float* __restrict__ mean_out, float* __restrict__ invstd_out, int relu) {
+  const ColMap m(cgb);
+  // the first row lane of the block finalizes the block's channels once and shares them (every thread repeating the
+  // divisions and square roots cost more than the normalisation itself on the small layers)
+  __shared__ float s_sc[256], s_sh[256];
+  if (m.lane_row == 0 && m.c0 < C) {
+    const float inv_rows = 1.f / (float)rows;
+    const bool writer = blockIdx.y == 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // fp32 throughout: E[x^2] - E[x]^2 with the product exact inside the fma
+      const int c = m.c0 + j;
+      const float mean = sums[c] * inv_rows;
+      const float var = fmaxf(fmaf(-mean, mean, sums[C + c] * inv_rows), 0.f);
+      const float inv = 1.f / sqrtf(var + eps);
+      const float scj = gamma[c] * inv, shj = beta[c] - mean * scj;
+      s_sc[m.cg * 8 + j] = scj;
+      s_sh[m.cg * 8 + j] = shj;
+      if (writer) {
+        scale_out[c] = scj;
+        shift_out[c] = shj;
+        mean_out[c] = mean;
+        invstd_out[c] = inv;
+        if (moving_mean) {  // fused batch norm feeds the UNBIASED variance to the moving average
+          const float unb = rows > 1 ? var * ((float)rows / (float)(rows - 1)) : var;
+          moving_mean[c] = moving_mean[c] * decay + (1.f - decay) * mean;
+          moving_var[c] = moving_var[c] * decay + (1.f - decay) * unb;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (m.c0 >= C) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = s_sc[m.cg * 8 + j];
+    sh[j] = s_sh[m.cg * 8 + j];
+  }
+#pragma unroll 4
+  for (long long r = (long long)blockIdx.y * m.rl + m.lane_row; r < rows; r += (long long)gridDim.y * m.rl) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + r * C + m.c0));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    uint4 o;
+    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 f = __bfloat1622float2(h[q]);
+      float a = fmaf(f.x, sc[2 * q], sh[2 * q]);
+      float b = fmaf(f.y, sc[2 * q + 1], sh[2 * q + 1]);
+      if (relu) {
+        a = fmaxf(a, 0.f);
+        b = fmaxf(b, 0.f);
+      }
+      ho[q] = __floats2bfloat162_rn(a, b);
+    }
+    *reinterpret_cast<uint4*>(y + r * C + m.c0) = o;
+  }
+}
+
 // g = dy * [x*scale+shift > 0] (ReLU mask recomputed from the saved pre-BN tensor); sums: [0,C) = sum g,
 // [C,2C) = sum g * xhat, xhat = (x - mean) * invstd.
 __global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy,
@@ -902,6 +969,20 @@ extern "C" int xdet_bn_train_stats_bf16(const void* d_x, long long rows, int C, 
       reinterpret_cast<const __nv_bfloat16*>(d_x), rows, C, cs, cgb, d_gamma, d_beta, eps, decay, d_moving_mean,
       d_moving_var, d_scale, d_shift, d_mean, d_invstd, sums, reinterpret_cast<unsigned*>(sums + 2 * (size_t)C));
   return after_launch("bn_stats_finalize_kernel");
+}
+
+extern "C" int xdet_bn_train_apply_bf16(const void* d_x, void* d_y, long long rows, int C, const float* d_sums,
+                                        const float* d_gamma, const float* d_beta, float eps, float decay,
+                                        float* d_moving_mean, float* d_moving_var, float* d_scale, float* d_shift,
+                                        float* d_mean, float* d_invstd, int relu, void* stream) {
+  if (rows <= 0 || C <= 0) return fail(XDET_EINVAL, "bn_train_apply: empty");
+  if (C % 8) return fail(XDET_EINVAL, "bn_train_apply: C must be a multiple of 8");
+  const int cgb = col_cgb(C);
+  const dim3 grid = col_grid(rows, C, cgb, 8, 4);
+  bn_apply_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d_x), reinterpret_cast<__nv_bfloat16*>(d_y), rows, C, cgb, d_sums, d_gamma,
+      d_beta, eps, decay, d_moving_mean, d_moving_var, d_scale, d_shift, d_mean, d_invstd, relu);
+  return after_launch("bn_apply_finalize_kernel");
 }
 
 extern "C" int xdet_bn_relu_bwd_bf16(const void* d_dy, const void* d_x, const float* d_scale, const float* d_shift,

@@ -63,6 +63,7 @@ _DEFAULTS = dict(
 )
 # fp32-accurate mode: the backward runs on gradients scaled by 2^12 (exact) so that they sit inside fp16's range when
 # they are split into (hi, lo) planes; the flat gradient buffer is scaled back once at the end
+FUSE_BN_STATS = True   # batch statistics from the producing convolution's epilogue (bf16 precision)
 _LOSS_SCALE = 4096.0
 FLAGS = types.SimpleNamespace(**_DEFAULTS)
 pool_method = 'max'  # light_head_rfcn_train.py:199
@@ -181,7 +182,33 @@ class VecParam(object):
 # ---------------------------------------------------------------------------------------------------------------
 # layers with explicit backward
 # ---------------------------------------------------------------------------------------------------------------
+class _StatsArena(object):
+    """Per-step fp32 scratch for the batch statistics the convolutions' epilogues accumulate (conv2d_nhwc(stats=...)): one
+    buffer cleared once when the step begins, slots handed out in call order (the first step sizes it)."""
+
+    def __init__(self, device):
+        self.device, self.buf, self.pos, self.need = device, None, 0, 0
+
+    def begin(self):
+        if self.need and (self.buf is None or self.buf.numel() < self.need):
+            self.buf = torch.zeros(self.need, dtype=torch.float32, device=self.device)
+        elif self.buf is not None:
+            self.buf.zero_()
+        self.pos = 0
+
+    def take(self, n):
+        if self.buf is not None and self.pos + n <= self.buf.numel():
+            v = self.buf[self.pos:self.pos + n]
+        else:
+            v = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.pos += n
+        self.need = max(self.need, self.pos)
+        return v
+
+
 class Conv(object):
+    arena = None   # the trainer's _StatsArena (set per layer by LightHeadTrainer._conv)
+
     def __init__(self, params, stride=1, dilation=1, padding="SAME", bias=None):
         self.p, self.stride, self.dil, self.padding, self.bias = params, stride, dilation, padding, bias
 
@@ -194,14 +221,22 @@ class Conv(object):
             return (pad, pad, (H + 2 * pad - p.kh) // s + 1, (W + 2 * pad - p.kw) // s + 1)
         return self.padding
 
-    def fwd(self, x, bias_tensor=None, **epilogue):
+    def fwd(self, x, bias_tensor=None, bn_stats=False, **epilogue):
+        """``bn_stats``: the output feeds a training-mode batch-norm -- let the kernel's epilogue accumulate its batch
+        statistics (bf16 precision; the sums ride on the output tensor as ``_bn_sums`` for BNRelu.fwd)."""
         p = self.p
         self.x = x
         self.in_hw = x.shape[1:3]
         self.geom = self._geom(*self.in_hw)
         b = bias_tensor if bias_tensor is not None else (self.bias.tensors[0] if self.bias is not None else None)
+        sums = None
+        if bn_stats and FUSE_BN_STATS and self.arena is not None and x.dtype == torch.bfloat16 and p.cout % 8 == 0:
+            sums = self.arena.take(2 * p.cout)
+            epilogue["stats"] = sums
         self.y = ops.conv2d_nhwc(x, p.pack, p.cout, p.kh, p.kw, dilation=(self.dil, self.dil), padding=self.geom,
                                  strides=(self.stride, self.stride), cin=p.cin, bias=b, **epilogue)
+        if sums is not None:
+            self.y._bn_sums = sums
         return self.y
 
     def bwd(self, dy, need_dx=True, dx_residual=None, dx_layout="nhwc_bf16"):
@@ -243,6 +278,13 @@ class BNRelu(object):
         return self.st
 
     def fwd(self, x):
+        sums = getattr(x, "_bn_sums", None)
+        beta, gamma = self.vec.tensors
+        if sums is not None and x.dtype == torch.bfloat16 and x.shape[-1] == beta.numel():
+            # the producing convolution already summed the batch: finalize + normalise + ReLU in one launch
+            self.x = x
+            y, self.st = T.bn_train_apply(x, sums, gamma, beta, self.eps, self.decay, self.moving[0], self.moving[1])
+            return y
         st = self.stats(x)
         return ops.affine_relu(x, st.scale, st.shift, relu=True)
 
@@ -263,9 +305,9 @@ class Bottleneck(object):
     def fwd(self, x):
         a = self.bn1.fwd(x)
         sc = self.proj.fwd(a) if self.proj is not None else x
-        b = self.bn2.fwd(self.c1.fwd(a))
-        c = self.bn3.fwd(self.c2.fwd(b))
-        return self.c3.fwd(c, residual=sc)
+        b = self.bn2.fwd(self.c1.fwd(a, bn_stats=True))
+        c = self.bn3.fwd(self.c2.fwd(b, bn_stats=True))
+        return self.c3.fwd(c, residual=sc, bn_stats=True)   # (the next block's / stage's batch-norm reads the sum)
 
     def bwd(self, dy, extra_dx=None):
         """dy: gradient of the block output.  Returns the gradient of the block input (+ ``extra_dx``)."""
@@ -318,6 +360,7 @@ class LightHeadTrainer(object):
         self.reg = reg = _Registry(self.device)
         self.convs, self.vecs = [], []
         self._sgd_plan = None
+        self.arena = _StatsArena(self.device)
         size = p['train_image_size']
         self.fmap = size // 16
         creator = anchor_manipulator.AnchorCreator([size] * 2, layers_shapes=[(self.fmap, self.fmap)],
@@ -480,7 +523,9 @@ class LightHeadTrainer(object):
         cp = ConvParams(self.reg, [(key, t, 0, 0)], k, k, cin, cout, fold=fold, need_dgrad=need_dgrad)
         self.convs.append(cp)
         padding = "SAME" if stride == 1 else "FIXED"
-        return Conv(cp, stride=stride, dilation=dil, padding=padding)
+        c = Conv(cp, stride=stride, dilation=dil, padding=padding)
+        c.arena = self.arena
+        return c
 
     def _bn(self, channels, name=None):
         s = self.store
@@ -697,6 +742,7 @@ class LightHeadTrainer(object):
         t.S = _LOSS_SCALE if self.f32 else 1.0
         t.act = torch.float32 if self.f32 else torch.bfloat16
         self.grads.zero_()
+        self.arena.begin()
         # (fp32-accurate mode: the buffer is rescaled before it is sent, so its buckets go out together at the end)
         self._pending = set(n for n, _, _ in self.buckets) if (self._world() > 1 and not self.f32) else None
         del p

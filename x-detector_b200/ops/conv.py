@@ -25,7 +25,7 @@ class ConvDesc(ctypes.Structure):
         ("out_sn", ctypes.c_longlong), ("out_sy", ctypes.c_longlong), ("out_sx", ctypes.c_longlong),
         ("out_sc", ctypes.c_longlong),
         ("out2", ctypes.c_void_p), ("scale2", ctypes.c_void_p), ("bias2", ctypes.c_void_p), ("block_n", ctypes.c_int),
-        ("epi_groups", ctypes.c_int), ("max_ctas", ctypes.c_int),
+        ("epi_groups", ctypes.c_int), ("max_ctas", ctypes.c_int), ("stats", ctypes.c_void_p),
     ]
 
 
@@ -341,11 +341,16 @@ class cta_limit(object):
 
 def conv2d_nhwc(x, w_packed, cout, kh, kw, *, dilation=(1, 1), padding="SAME", scale=None, bias=None, relu=False,
                 residual=None, out=None, out_layout="nhwc_bf16", out2=None, scale2=None, bias2=None, cin=None,
-                block_n=0, strides=(1, 1), fold_w=None, skip_out=False, epi_groups=0, forms="both", forms2="both"):
+                block_n=0, strides=(1, 1), fold_w=None, skip_out=False, epi_groups=0, forms="both", forms2="both",
+                stats=None):
     """x: [N,H,W,C] bf16 (channel stride may be padded: pass the true ``cin``).  Returns the output tensor
     ([N,Ho,Wo,Cout] bf16 for 'nhwc_bf16', [N,Cout,Ho,Wo] fp32 for 'nchw_f32', [N,Ho,Wo,Cout] fp32 for 'nhwc_f32').
     ``forms`` / ``forms2`` (read by the "f16x2" precision only): which forms of ``out`` / ``out2`` their consumers need
-    -- "both", "f32" (no convolution reads it: no split planes) or "pair" (only convolutions read it: no fp32 copy)."""
+    -- "both", "f32" (no convolution reads it: no split planes) or "pair" (only convolutions read it: no fp32 copy).
+    ``stats`` (bf16 precision, bf16 NHWC output): fp32 [2*cout] the kernel ADDS the per-channel sums and sums of squares of
+    the stored output to -- the batch statistics of the batch-norm that reads it (ops.train.bn_train_apply)."""
+    if stats is not None and (isinstance(w_packed, PairWeight) or x.dtype != torch.bfloat16):
+        raise ValueError("conv2d_nhwc(stats=...) is a bf16-precision feature")
     if isinstance(w_packed, PairWeight):
         return _conv2d_f16x2(x, w_packed, cout, kh, kw, dilation=dilation, padding=padding, scale=scale, bias=bias,
                              relu=relu, residual=residual, out=out, out_layout=out_layout, out2=out2, scale2=scale2,
@@ -397,13 +402,19 @@ def conv2d_nhwc(x, w_packed, cout, kh, kw, *, dilation=(1, 1), padding="SAME", s
                  w_packed.data_ptr(), _ptr(scale), _ptr(bias),
                  1 if relu else 0, _ptr(residual), None if skip_out else out.data_ptr(),
                  0 if out.dtype == torch.bfloat16 else 1, sn, sy, sx, sc, _ptr(out2), _ptr(scale2), _ptr(bias2),
-                 block_n, epi_groups, MAX_CTAS)
+                 block_n, epi_groups, MAX_CTAS, _ptr(stats))
+    if stats is not None:
+        assert stats.dtype == torch.float32 and stats.numel() == 2 * cout and stats.is_contiguous()
     with torch.cuda.device(dev):
         if AUTOTUNE and block_n == 0 and epi_groups == 0:
             key = (N, H, W, cin, cs, cout, kh, kw, dh, dw, pt, pl, Ho, Wo, sh, sw, fold_w is not None, bool(relu),
-                   residual is not None, out2 is not None, bool(skip_out), out_layout, MAX_CTAS > 0)
+                   residual is not None, out2 is not None, bool(skip_out), out_layout, MAX_CTAS > 0, stats is not None)
             if key not in _tune_cache and not torch.cuda.is_current_stream_capturing():
+                if stats is not None:  # (the timing runs add to a scratch copy, not to the caller's statistics)
+                    scratch = torch.zeros_like(stats)
+                    d.stats = scratch.data_ptr()
                 _tune_cache[key] = _autotune(x, d)
+                d.stats = _ptr(stats)
             d.block_n, d.epi_groups = _tune_cache.get(key, (0, 0))
         if PROFILE is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -97,6 +97,23 @@ def bn_train(x, gamma, beta, eps, decay=None, moving_mean=None, moving_var=None)
     return st
 
 
+def bn_train_apply(x, sums, gamma, beta, eps, decay=None, moving_mean=None, moving_var=None, relu=True):
+    """Batch-norm (+ReLU) of x [..., C] bf16 from statistics that already exist -- ``sums`` fp32 [2*C] (sums, sums of
+    squares over all rows), accumulated by the convolution that produced x (``conv2d_nhwc(stats=...)``): bn_finalize and
+    the normalisation in one launch.  Returns (y, BNState)."""
+    C = x.shape[-1]
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and sums.numel() == 2 * C and sums.dtype == torch.float32
+    st = BNState()
+    st.rows = x.numel() // C
+    st.scale, st.shift, st.mean, st.invstd = torch.empty((4, C), dtype=torch.float32, device=x.device).unbind(0)
+    y = torch.empty_like(x)
+    _native.check(_native.lib().xdet_bn_train_apply_bf16(
+        x.data_ptr(), y.data_ptr(), st.rows, C, sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps,
+        0.0 if decay is None else decay, _p(moving_mean), _p(moving_var), st.scale.data_ptr(), st.shift.data_ptr(),
+        st.mean.data_ptr(), st.invstd.data_ptr(), 1 if relu else 0, _st()))
+    return y, st
+
+
 def bn_relu_bwd(dy, x, st, relu=True, add_in=None):
     """-> (dx bf16 like x, dgamma [C], dbeta [C]) for y = relu(x*scale+shift) with batch statistics."""
     C = x.shape[-1]
