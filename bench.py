@@ -689,16 +689,18 @@ class LightHeadResnet50Train:
                     gout = eager_step(static)
                 torch.cuda.synchronize()
             except Exception as e:
-                sys.stderr.write("CUDA graph capture failed (%s: %s); timing eager launches\n" % (type(e).__name__, e))
+                import traceback
+                sys.stderr.write("CUDA graph capture failed (%s: %s); timing eager launches\n%s" %
+                                 (type(e).__name__, e, traceback.format_exc()))
                 graph = None
                 torch.cuda.synchronize()
 
         def step(tensors):
-            if graph is None:
-                return eager_step(tensors)
-            if tensors is not static:
+            if tensors is not static:  # (pinned host tensors of the end-to-end leg: H2D into the step's input buffers)
                 for s_, d_ in zip(static, tensors):
                     s_.copy_(d_, non_blocking=True)
+            if graph is None:
+                return eager_step(static)
             graph.replay()
             return gout
 

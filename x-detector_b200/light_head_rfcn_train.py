@@ -63,6 +63,7 @@ _DEFAULTS = dict(
 )
 # fp32-accurate mode: the backward runs on gradients scaled by 2^12 (exact) so that they sit inside fp16's range when
 # they are split into (hi, lo) planes; the flat gradient buffer is scaled back once at the end
+WGRAD_STREAM = True    # weight gradients on their own stream beside the input-gradient chain (bf16 precision)
 FUSE_BN_STATS = True   # batch statistics from the producing convolution's epilogue (bf16 precision)
 _LOSS_SCALE = 4096.0
 FLAGS = types.SimpleNamespace(**_DEFAULTS)
@@ -208,6 +209,7 @@ class _StatsArena(object):
 
 class Conv(object):
     arena = None   # the trainer's _StatsArena (set per layer by LightHeadTrainer._conv)
+    wg_stream = None   # set per layer by the trainer: the stream the weight gradients run on
 
     def __init__(self, params, stride=1, dilation=1, padding="SAME", bias=None):
         self.p, self.stride, self.dil, self.padding, self.bias = params, stride, dilation, padding, bias
@@ -242,12 +244,26 @@ class Conv(object):
     def bwd(self, dy, need_dx=True, dx_residual=None, dx_layout="nhwc_bf16"):
         """dy: NHWC bf16 (channel pitch a multiple of 8, >= cout).  Accumulates dW (and dbias); returns dX."""
         p = self.p
-        ops.conv2d_wgrad(self.x, dy, p.kh, p.kw, dilation=(self.dil, self.dil), padding=self.geom,
-                         strides=(self.stride, self.stride), cin=p.cin, cout=p.cout, dw=p.dw)
-        if self.bias is not None:  # dbias = column sums of dy, accumulated straight into the flat gradient buffer
-            dy2 = dy.reshape(-1, dy.shape[-1])
-            assert dy2.shape[1] == self.bias.seg, (dy2.shape, self.bias.seg)
-            T.col_sums_into(dy2, self.bias.grad)
+
+        def weight_side():
+            ops.conv2d_wgrad(self.x, dy, p.kh, p.kw, dilation=(self.dil, self.dil), padding=self.geom,
+                             strides=(self.stride, self.stride), cin=p.cin, cout=p.cout, dw=p.dw)
+            if self.bias is not None:  # dbias = column sums of dy, accumulated straight into the flat gradient buffer
+                dy2 = dy.reshape(-1, dy.shape[-1])
+                assert dy2.shape[1] == self.bias.seg, (dy2.shape, self.bias.seg)
+                T.col_sums_into(dy2, self.bias.grad)
+
+        wg = self.wg_stream
+        if wg is not None and need_dx and dy.dtype == torch.bfloat16:
+            # nothing downstream of this layer's backward reads dW: the weight gradient runs on its own stream beside
+            # the input-gradient chain (joined before the stage's bucket is sent / the optimizer runs)
+            wg.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(wg):
+                weight_side()
+            dy.record_stream(wg)
+            wg.xdet_forked = True   # (the trainer joins the stream only if something ran on it this step)
+        else:
+            weight_side()
         if not need_dx:
             return None
         return ops.conv2d_dgrad(dy, p.dpack, p.cin, p.kh, p.kw, self.in_hw, dilation=(self.dil, self.dil),
@@ -361,6 +377,7 @@ class LightHeadTrainer(object):
         self.convs, self.vecs = [], []
         self._sgd_plan = None
         self.arena = _StatsArena(self.device)
+        self.wg_stream = torch.cuda.Stream(device=self.device) if (WGRAD_STREAM and not self.f32) else None
         size = p['train_image_size']
         self.fmap = size // 16
         creator = anchor_manipulator.AnchorCreator([size] * 2, layers_shapes=[(self.fmap, self.fmap)],
@@ -414,6 +431,8 @@ class LightHeadTrainer(object):
             if bname == name and bname in self._pending and b > a:
                 self._pending.remove(bname)
                 self.comm.wait_stream(torch.cuda.current_stream())
+                if self.wg_stream is not None and getattr(self.wg_stream, "xdet_forked", False):
+                    self.comm.wait_stream(self.wg_stream)
                 with torch.cuda.stream(self.comm):
                     torch.distributed.all_reduce(self.grads[a:b], op=torch.distributed.ReduceOp.SUM, group=self.pg)
 
@@ -525,6 +544,7 @@ class LightHeadTrainer(object):
         padding = "SAME" if stride == 1 else "FIXED"
         c = Conv(cp, stride=stride, dilation=dil, padding=padding)
         c.arena = self.arena
+        c.wg_stream = self.wg_stream
         return c
 
     def _bn(self, channels, name=None):
@@ -660,6 +680,8 @@ class LightHeadTrainer(object):
             self.fc1 = Conv(cpf1, bias=self._bias([f1b[1]]))
             fused_f2, _ = fuse_bias([fcb, flb])
             self.fc2 = Conv(cpf2, bias=self._bias([fused_f2]))
+            for c in (self.rpn_conv, self.rpn_out, self.sep_a, self.sep_b, self.fc1, self.fc2):
+                c.wg_stream = self.wg_stream
 
     # ---- forward pieces ----------------------------------------------------------------------------------------
     def _rows(self, feat, pitch):
@@ -996,6 +1018,9 @@ class LightHeadTrainer(object):
             dy0 = T.maxpool3x3s2_bwd(t.pool_arg, dx, t.y0_hw)
             ops.conv2d_wgrad(t.x8, dy0, 7, 7, padding=(3, 3, Ho, Wo), strides=(2, 2), cin=3, cout=64, dw=self.stem.p.dw,
                              fold_w=(Wimg, 3))
+        if self.wg_stream is not None and getattr(self.wg_stream, "xdet_forked", False):
+            torch.cuda.current_stream().wait_stream(self.wg_stream)   # JOIN (weight-gradient stream)
+            self.wg_stream.xdet_forked = False
         if self.f32:
             self.grads.mul_(1.0 / t.S)  # exact: S is a power of two
 
