@@ -587,7 +587,9 @@ class LightHeadTrainer(object):
                         with s.scope(name):
                             vars_[name + "/" + kind] = s.get(kind, shape, s.glorot_normal)[1]
                 self.body = xt.TrainableXceptionBody(vars_, moving, self.reg, ConvParams, VecParam,
-                                                     key_prefix=p['model_scope'] + "/")
+                                                     key_prefix=p['model_scope'] + "/", wg_stream=None)
+                # (measured: the separable blocks' pointwise weight gradients beside the depthwise kernels of the chain
+                # LOSE 7 % -- 528 -> 490 img/s --, so the body keeps them in line; the heads' use the second stream)
                 self.convs += self.body.convs
                 self.vecs += self.body.vecs
                 self.marks += [("middle", self.body.req_marks["middle"]), ("exit", self.body.req_marks["exit"])]

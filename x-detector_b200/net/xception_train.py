@@ -86,8 +86,17 @@ class Conv(object):
         else:
             cin_pad = (self.cin + 63) // 64 * 64
             dw = torch.zeros((self.cout, self.kh * self.kw, cin_pad), dtype=torch.float32, device=dy.device)
-        ops.conv2d_wgrad(self.x, dy, self.kh, self.kw, padding=self.geom, strides=(self.stride, self.stride),
-                         cin=self.cin, cout=self.cout, dw=dw)
+        wg = getattr(self, "wg_stream", None)   # the trainer's weight-gradient stream (joined by LightHeadTrainer.backward)
+        if wg is not None and p is not None and self.dpack is not None and dy.dtype == torch.bfloat16:
+            wg.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(wg):
+                ops.conv2d_wgrad(self.x, dy, self.kh, self.kw, padding=self.geom, strides=(self.stride, self.stride),
+                                 cin=self.cin, cout=self.cout, dw=dw)
+            dy.record_stream(wg)
+            wg.xdet_forked = True
+        else:
+            ops.conv2d_wgrad(self.x, dy, self.kh, self.kw, padding=self.geom, strides=(self.stride, self.stride),
+                             cin=self.cin, cout=self.cout, dw=dw)
         if p is None:
             grads[self.name + "/" + leaf] = dw.view(self.cout, self.kh, self.kw, -1)[..., :self.cin].permute(
                 1, 2, 3, 0).contiguous()
@@ -246,7 +255,7 @@ class TrainableXceptionBody(XceptionBodyTraining):
     layout} (updated in place by ``update``); ``moving``: {name + '/moving_mean' | '/moving_variance': tensor};
     ``reg``: the trainer's _Registry (gradient views are carved from its flat buffer at ``reg.finalize()``)."""
 
-    def __init__(self, store_vars, moving, reg, conv_params_cls, vec_param_cls, key_prefix=""):
+    def __init__(self, store_vars, moving, reg, conv_params_cls, vec_param_cls, key_prefix="", wg_stream=None):
         self.convs, self.vecs = [], []
         self._reg, self._conv_cls, self._vec_cls, self._moving = reg, conv_params_cls, vec_param_cls, moving
         self._vars = store_vars
@@ -266,6 +275,7 @@ class TrainableXceptionBody(XceptionBodyTraining):
                 layer.p = conv_params_cls(reg, [(key_prefix + key, store_vars[key], 0, 0)], layer.kh, layer.kw, layer.cin, layer.cout,
                                           need_dgrad=layer.dpack is not None)
                 layer.pack, layer.dpack = layer.p.pack, layer.p.dpack     # the packs the optimizer refreshes
+                layer.wg_stream = wg_stream
                 self.convs.append(layer.p)
             elif isinstance(layer, Depthwise):
                 layer.master = store_vars[layer.name + "/depthwise_kernel"]
