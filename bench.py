@@ -840,6 +840,12 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph replay")
     ap.add_argument("--no-autotune", action="store_true", help="keep the heuristic conv tile shapes (no per-shape tuning)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: Python's prints keep the real stdout, while file descriptor 1 -- where C code
+    # writes (NCCL prints its version banner there whatever NCCL_DEBUG_FILE says) -- is pointed at stderr
+    sys.stdout.flush()
+    real_out = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_out, "w", buffering=1)
     wl = WORKLOADS[args.workload]()
     if args.impl == "reference":
         wl.run_reference(args)
