@@ -16,7 +16,14 @@ def lib():
 
 
 @pytest.mark.parametrize("shape,dil,relu_in", [((2, 19, 23, 72), 1, True), ((1, 50, 50, 728), 1, True),
-                                               ((3, 10, 12, 1536), 2, False), ((1, 5, 4, 8), 2, True)])
+                                               ((3, 10, 12, 1536), 2, False), ((1, 5, 4, 8), 2, True),
+                                               # the row-sliding kernel's corners: widths around the ring length (3 / 5),
+                                               # rows split over several warps per CTA, the training shapes
+                                               ((2, 7, 3, 16), 1, False), ((2, 7, 4, 136), 1, True),
+                                               ((1, 9, 5, 24), 2, True), ((1, 9, 6, 264), 2, False),
+                                               ((1, 3, 2, 8), 1, True),       # W <= 2*dil: the pixel-strided fallback
+                                               ((8, 30, 30, 728), 1, True), ((2, 120, 120, 128), 1, False),
+                                               ((8, 30, 30, 1024), 2, True)])
 def test_depthwise_wgrad_and_flipped_dgrad(lib, shape, dil, relu_in):
     from xdet_b200 import _native, ops
     N, H, W, C = shape

@@ -26,7 +26,7 @@ def main():
     args = ap.parse_args()
     if args.train:
         from xdet_b200 import light_head_rfcn_train as lt
-        tparams = lt.make_params(train_image_size=args.size, batch_size=args.batch)
+        tparams = lt.make_params(train_image_size=args.size, batch_size=args.batch, backbone=args.backbone)
         trainer = lt.LightHeadTrainer(tparams, seed=0)
         tb = lt.synthetic_batch(tparams, args.batch, seed=3)
         model = lambda _images, detections=False: trainer.step(*tb)  # noqa: E731
