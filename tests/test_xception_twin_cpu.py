@@ -82,7 +82,10 @@ def fake_depthwise3x3(x, w9, dilation=1, relu_in=False, forms=None):
     return nhwc_bf16(xb.depthwise_fwd(a, w9.double().reshape(3, 3, -1), dilation))
 
 
-def fake_depthwise3x3_wgrad(x, dy, dilation, relu_in):
+def fake_depthwise3x3_wgrad(x, dy, dilation, relu_in, out=None):
+    if out is not None:   # the device kernel ACCUMULATES into a view of the flat gradient buffer
+        out += fake_depthwise3x3_wgrad(x, dy, dilation, relu_in).reshape(-1)
+        return out
     a, g, d = nchw(x), nchw(dy), dilation
     a = torch.relu(a) if relu_in else a
     H, W = a.shape[2:]

@@ -24,6 +24,7 @@ axis=1)`` (net/xception_body.py:533) applies EVERY image's top-k index row to EV
 N*N*k RoI rows and the loss is their mean.
 """
 import math
+import os
 import types
 
 import torch
@@ -63,6 +64,7 @@ _DEFAULTS = dict(
 )
 # fp32-accurate mode: the backward runs on gradients scaled by 2^12 (exact) so that they sit inside fp16's range when
 # they are split into (hi, lo) planes; the flat gradient buffer is scaled back once at the end
+XCEPTION_BODY_WGRAD_STREAM = os.environ.get("XDET_XBODY_WG", "1") == "1"   # (measured both ways, see _build)
 WGRAD_STREAM = True    # weight gradients on their own stream beside the input-gradient chain (bf16 precision)
 FUSE_BN_STATS = True   # batch statistics from the producing convolution's epilogue (bf16 precision)
 _LOSS_SCALE = 4096.0
@@ -587,9 +589,11 @@ class LightHeadTrainer(object):
                         with s.scope(name):
                             vars_[name + "/" + kind] = s.get(kind, shape, s.glorot_normal)[1]
                 self.body = xt.TrainableXceptionBody(vars_, moving, self.reg, ConvParams, VecParam,
-                                                     key_prefix=p['model_scope'] + "/", wg_stream=None)
-                # (measured: the separable blocks' pointwise weight gradients beside the depthwise kernels of the chain
-                # LOSE 7 % -- 528 -> 490 img/s --, so the body keeps them in line; the heads' use the second stream)
+                                                     key_prefix=p['model_scope'] + "/",
+                                                     wg_stream=self.wg_stream if XCEPTION_BODY_WGRAD_STREAM else None,
+                                                     arena=self.arena if FUSE_BN_STATS else None)
+                # (measured: with the first depthwise weight-gradient kernel -- 163 us per layer -- the pointwise weight
+                # gradients beside the chain LOST 7 %; with the row-sliding one they gain 3 %: 740 -> 760 img/s)
                 self.convs += self.body.convs
                 self.vecs += self.body.vecs
                 self.marks += [("middle", self.body.req_marks["middle"]), ("exit", self.body.req_marks["exit"])]

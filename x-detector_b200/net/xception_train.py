@@ -25,11 +25,16 @@ def _st():
     return torch.cuda.current_stream().cuda_stream
 
 
-def depthwise3x3_wgrad(x, dy, dilation, relu_in):
-    """dW [9, C] fp32 of the depthwise 3x3 'same' convolution (csrc/depthwise_wgrad.cu)."""
+def depthwise3x3_wgrad(x, dy, dilation, relu_in, out=None):
+    """dW [9, C] fp32 of the depthwise 3x3 'same' convolution (csrc/depthwise_wgrad.cu).  ``out``: 9*C fp32 elements the
+    kernel ADDS the gradient to (a view of the trainer's flat gradient buffer: no temporary, no separate add)."""
     lib = _native.lib()
     N, H, W, C = x.shape
-    dw = torch.zeros((9, C), dtype=torch.float32, device=x.device)
+    if out is not None:
+        assert out.dtype == torch.float32 and out.numel() == 9 * C and out.is_contiguous()
+        dw = out
+    else:
+        dw = torch.zeros((9, C), dtype=torch.float32, device=x.device)
     fn = lib.xdet_depthwise3x3_wgrad_f32 if x.dtype == torch.float32 else lib.xdet_depthwise3x3_wgrad_bf16
     assert x.dtype == dy.dtype and x.is_contiguous() and dy.is_contiguous()
     _native.check(fn(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W, C, dilation, 1 if relu_in else 0, _st()))
@@ -76,8 +81,16 @@ class Conv(object):
     def fwd(self, x):
         self.x, self.in_hw = x, tuple(x.shape[1:3])
         self.geom = self._geom(*self.in_hw)
-        return ops.conv2d_nhwc(x, self.pack, self.cout, self.kh, self.kw, padding=self.geom,
-                               strides=(self.stride, self.stride), cin=self.cin)
+        # every convolution of the body feeds a batch-norm: under the trainer (bf16 precision) the kernel's epilogue
+        # accumulates that layer's batch statistics (they ride on the output tensor as ``_bn_sums``)
+        arena, sums = getattr(self, "arena", None), None
+        if arena is not None and x.dtype == torch.bfloat16 and self.cout % 8 == 0 and ops.conv.PRECISION == "bf16":
+            sums = arena.take(2 * self.cout)
+        y = ops.conv2d_nhwc(x, self.pack, self.cout, self.kh, self.kw, padding=self.geom,
+                            strides=(self.stride, self.stride), cin=self.cin, **({} if sums is None else {"stats": sums}))
+        if sums is not None:
+            y._bn_sums = sums
+        return y
 
     def bwd(self, dy, grads, leaf="kernel"):
         p = getattr(self, "p", None)     # TrainableXceptionBody: accumulate into the trainer's flat gradient buffer
@@ -120,11 +133,11 @@ class Depthwise(object):
 
     def bwd(self, dy, grads):
         dy = dy.contiguous()
-        dw = depthwise3x3_wgrad(self.x, dy, self.dil, self.relu_in)
         vec = getattr(self, "vec", None)
         if vec is not None:
-            vec.grad[:9 * self.C] += dw.reshape(-1)
+            depthwise3x3_wgrad(self.x, dy, self.dil, self.relu_in, out=vec.grad[:9 * self.C])
         else:
+            dw = depthwise3x3_wgrad(self.x, dy, self.dil, self.relu_in)
             grads[self.name + "/depthwise_kernel"] = dw.reshape(3, 3, self.C, 1)
         # tap (kh,kw) -> (2-kh,2-kw); flipped per call: w9 may be a view of a master the optimizer updates
         da = ops.depthwise3x3(dy, self.w9.flip(0).contiguous(), dilation=self.dil, relu_in=False, forms="f32")
@@ -140,6 +153,11 @@ class BatchNorm(object):
     def fwd(self, x):
         self.x = x
         moving = getattr(self, "moving", (None, None))   # TrainableXceptionBody: also update the moving statistics
+        sums = getattr(x, "_bn_sums", None)
+        if sums is not None and x.dtype == torch.bfloat16 and x.shape[-1] == self.gamma.numel():
+            y, self.st = T.bn_train_apply(x, sums, self.gamma, self.beta, BN_EPSILON,
+                                          None if moving[0] is None else BN_MOMENTUM, *moving, relu=self.relu)
+            return y
         self.st = T.bn_train(x, self.gamma, self.beta, BN_EPSILON, None if moving[0] is None else BN_MOMENTUM, *moving)
         return ops.affine_relu(x, self.st.scale, self.st.shift, relu=self.relu)
 
@@ -255,7 +273,8 @@ class TrainableXceptionBody(XceptionBodyTraining):
     layout} (updated in place by ``update``); ``moving``: {name + '/moving_mean' | '/moving_variance': tensor};
     ``reg``: the trainer's _Registry (gradient views are carved from its flat buffer at ``reg.finalize()``)."""
 
-    def __init__(self, store_vars, moving, reg, conv_params_cls, vec_param_cls, key_prefix="", wg_stream=None):
+    def __init__(self, store_vars, moving, reg, conv_params_cls, vec_param_cls, key_prefix="", wg_stream=None,
+                 arena=None):
         self.convs, self.vecs = [], []
         self._reg, self._conv_cls, self._vec_cls, self._moving = reg, conv_params_cls, vec_param_cls, moving
         self._vars = store_vars
@@ -276,6 +295,7 @@ class TrainableXceptionBody(XceptionBodyTraining):
                                           need_dgrad=layer.dpack is not None)
                 layer.pack, layer.dpack = layer.p.pack, layer.p.dpack     # the packs the optimizer refreshes
                 layer.wg_stream = wg_stream
+                layer.arena = arena
                 self.convs.append(layer.p)
             elif isinstance(layer, Depthwise):
                 layer.master = store_vars[layer.name + "/depthwise_kernel"]
