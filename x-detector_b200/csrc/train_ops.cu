@@ -377,28 +377,35 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const unsigned char* _
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    // windows (yo, xo) with yo*2 - pad_top <= yi <= yo*2 - pad_top + 2
+    // windows (yo, xo) with yo*2 - pad_top <= yi <= yo*2 - pad_top + 2: at most two per axis.  All (<= 4) candidates
+    // are loaded unconditionally from clamped positions and masked afterwards, so that the eight loads leave together
+    // (a `continue` per window made every load wait for the one before it).
     const int yo_lo = max(0, (yi + pad_top - 1) / 2), yo_hi = min(Ho - 1, (yi + pad_top) / 2);
     const int xo_lo = max(0, (xi + pad_left - 1) / 2), xo_hi = min(Wo - 1, (xi + pad_left) / 2);
-    for (int yo = yo_lo; yo <= yo_hi; ++yo) {
-      const int kh = yi - (yo * 2 - pad_top);
-      if (kh < 0 || kh > 2) continue;
-      for (int xo = xo_lo; xo <= xo_hi; ++xo) {
-        const int kw = xi - (xo * 2 - pad_left);
-        if (kw < 0 || kw > 2) continue;
-        const unsigned code = (unsigned)(kh * 3 + kw);
-        const long long o = (((long long)n * Ho + yo) * Wo + xo) * C8 + c8;
-        const uint2 a = __ldg(reinterpret_cast<const uint2*>(argmax) + o);
-        const uint4 d = __ldg(reinterpret_cast<const uint4*>(dy) + o);
-        const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&d);
+    uint2 am[4];
+    uint4 dv[4];
+    unsigned code[4];
+    bool ok[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 f = __bfloat1622float2(hd[q]);
-          const unsigned w = (q < 2) ? a.x : a.y;
-          const unsigned a0 = (w >> ((2 * q & 3) * 8)) & 255u, a1 = (w >> (((2 * q + 1) & 3) * 8)) & 255u;
-          if (a0 == code) acc[2 * q] += f.x;
-          if (a1 == code) acc[2 * q + 1] += f.y;
-        }
+    for (int w = 0; w < 4; ++w) {
+      const int yo = yo_lo + (w >> 1), xo = xo_lo + (w & 1);
+      const int kh = yi - (yo * 2 - pad_top), kw = xi - (xo * 2 - pad_left);
+      ok[w] = yo <= yo_hi && xo <= xo_hi && kh >= 0 && kh <= 2 && kw >= 0 && kw <= 2;
+      code[w] = (unsigned)(kh * 3 + kw);
+      const long long o = (((long long)n * Ho + min(yo, Ho - 1)) * Wo + min(xo, Wo - 1)) * C8 + c8;
+      am[w] = __ldg(reinterpret_cast<const uint2*>(argmax) + o);
+      dv[w] = __ldg(reinterpret_cast<const uint4*>(dy) + o);
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&dv[w]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(hd[q]);
+        const unsigned wd = (q < 2) ? am[w].x : am[w].y;
+        const unsigned a0 = (wd >> ((2 * q & 3) * 8)) & 255u, a1 = (wd >> (((2 * q + 1) & 3) * 8)) & 255u;
+        if (ok[w] && a0 == code[w]) acc[2 * q] += f.x;
+        if (ok[w] && a1 == code[w]) acc[2 * q + 1] += f.y;
       }
     }
     uint4 o4;
