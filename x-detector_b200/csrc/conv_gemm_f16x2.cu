@@ -487,18 +487,28 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_f32x_kernel(
     float m[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) m[j] = -FLT_MAX;
+    // all nine taps are loaded from clamped positions first and masked afterwards: a `continue` per tap made every load
+    // wait for the maximum over the one before it (nine dependent round trips per output)
+    float4 ta[9], tb[9];
+    bool ok[9];
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int yi = yo * 2 + kh - pad_top;
-      if (yi < 0 || yi >= H) continue;
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
         const int xi = xo * 2 + kw - pad_left;
-        if (xi < 0 || xi >= W) continue;
-        const float4* p = reinterpret_cast<const float4*>(src + ((n * H + yi) * W + xi) * C + cb);
-        const float4 a = __ldg(p), b = __ldg(p + 1);
-        m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], a.z); m[3] = fmaxf(m[3], a.w);
-        m[4] = fmaxf(m[4], b.x); m[5] = fmaxf(m[5], b.y); m[6] = fmaxf(m[6], b.z); m[7] = fmaxf(m[7], b.w);
+        ok[kh * 3 + kw] = yi >= 0 && yi < H && xi >= 0 && xi < W;
+        const int yc = min(max(yi, 0), H - 1), xc = min(max(xi, 0), W - 1);
+        const float4* p = reinterpret_cast<const float4*>(src + ((n * H + yc) * W + xc) * C + cb);
+        ta[kh * 3 + kw] = __ldg(p);
+        tb[kh * 3 + kw] = __ldg(p + 1);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      if (ok[t]) {
+        m[0] = fmaxf(m[0], ta[t].x); m[1] = fmaxf(m[1], ta[t].y); m[2] = fmaxf(m[2], ta[t].z); m[3] = fmaxf(m[3], ta[t].w);
+        m[4] = fmaxf(m[4], tb[t].x); m[5] = fmaxf(m[5], tb[t].y); m[6] = fmaxf(m[6], tb[t].z); m[7] = fmaxf(m[7], tb[t].w);
       }
     }
     const long long o = pix * C + cb;
