@@ -765,17 +765,29 @@ __device__ void select_smallest(const float* __restrict__ keys, int n, int k, in
   if (tid == 0) {
     *s_prefix = 0ull;
     *s_remaining = k;
+    *s_count = 0;  // (doubles as the "resolved far enough" flag of the pass loop)
   }
   __syncthreads();
+  // Radix select from the top byte down, but only until the candidates fit the sort buffer: after a pass, G keys lie
+  // above the threshold bucket (all selected) and E inside it; once G + E <= P the bucket's keys are simply sorted
+  // along.  With 150 000 anchors that is 2 passes over the keys instead of 8.  Four independent loads per thread and
+  // iteration (clamped index, masked afterwards) keep the memory pipe busy.
+  constexpr int U = 4;
   for (int pass = 0; pass < 8; ++pass) {
     const int shift = 56 - 8 * pass;
     for (int i = tid; i < 256; i += kSampThreads) hist[i] = 0;
     __syncthreads();
     const unsigned long long prefix = *s_prefix;
-    for (int i = tid; i < n; i += kSampThreads) {
-      const unsigned long long kk = key64(i);
-      const bool match = (pass == 0) || ((kk >> (shift + 8)) == (prefix >> (shift + 8)));
-      if (match) atomicAdd(&hist[(unsigned)(kk >> shift) & 255u], 1u);
+    for (int i0 = tid; i0 < n; i0 += U * kSampThreads) {
+      unsigned long long kk[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) kk[u] = key64(min(i0 + u * kSampThreads, n - 1));
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool in = i0 + u * kSampThreads < n;
+        const bool match = (pass == 0) || ((kk[u] >> (shift + 8)) == (prefix >> (shift + 8)));
+        if (in && match) atomicAdd(&hist[(unsigned)(kk[u] >> shift) & 255u], 1u);
+      }
     }
     __syncthreads();
     if (tid == 0) {
@@ -787,16 +799,24 @@ __device__ void select_smallest(const float* __restrict__ keys, int n, int k, in
       }
       *s_prefix = prefix | ((unsigned long long)b << shift);
       *s_remaining = rem;
+      if ((k - rem) + (int)hist[b] <= P) *s_count = 1;
     }
     __syncthreads();
+    const int done = *s_count;
+    __syncthreads();
+    if (done) break;
   }
-  const unsigned long long thr = *s_prefix;
+  const unsigned long long thr = *s_prefix;  // (low bits zero when the loop left early: the whole bucket qualifies)
   if (tid == 0) *s_count = 0;
   for (int i = tid; i < P; i += kSampThreads) sk[i] = 0ull;
   __syncthreads();
-  for (int i = tid; i < n; i += kSampThreads) {
-    const unsigned long long kk = key64(i);
-    if (kk >= thr) sk[atomicAdd(s_count, 1)] = kk;
+  for (int i0 = tid; i0 < n; i0 += U * kSampThreads) {
+    unsigned long long kk[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) kk[u] = key64(min(i0 + u * kSampThreads, n - 1));
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (i0 + u * kSampThreads < n && kk[u] >= thr) sk[atomicAdd(s_count, 1)] = kk[u];
   }
   __syncthreads();
   for (int size = 2; size <= P; size <<= 1) {
@@ -830,7 +850,7 @@ __global__ void __launch_bounds__(kSampThreads) sample_fg_bg_kernel(
   __shared__ unsigned int hist[256];
   __shared__ unsigned long long s_prefix;
   __shared__ int s_remaining, s_count;
-  __shared__ int s_pos[kSampThreads + 1], s_neg[kSampThreads + 1];
+  __shared__ int s_pos[65], s_neg[65];
   const int grp = blockIdx.x, tid = threadIdx.x;
   labels += (long long)grp * n;
   if (scores) scores += (long long)grp * n;
@@ -841,36 +861,56 @@ __global__ void __launch_bounds__(kSampThreads) sample_fg_bg_kernel(
   int* neg_list = pos_list + n;
   out += (long long)grp * total;
 
-  // ordered compaction of positives / negatives
-  const int chunk = (n + kSampThreads - 1) / kSampThreads;
-  const int i0 = min(n, tid * chunk), i1 = min(n, i0 + chunk);
-  int cp = 0, cn = 0;
-  for (int i = i0; i < i1; ++i) {
-    const int l = labels[i];
-    cp += l > 0;
-    cn += (l == 0) && (!scores || scores[i] > bg_low);
-  }
-  s_pos[tid + 1] = cp;
-  s_neg[tid + 1] = cn;
-  __syncthreads();
-  if (tid == 0) {
-    s_pos[0] = s_neg[0] = 0;
-    for (int t = 1; t <= kSampThreads; ++t) {
-      s_pos[t] += s_pos[t - 1];
-      s_neg[t] += s_neg[t - 1];
-    }
-  }
-  __syncthreads();
+  // ordered compaction of positives / negatives: coalesced tiles of 1024 labels (the next tile's loads are issued before
+  // the current one is placed), ranks inside a warp by ballot + popc, the 32 warp totals scanned by warp 0
   {
-    int op = s_pos[tid], on = s_neg[tid];
-    for (int i = i0; i < i1; ++i) {
-      const int l = labels[i];
-      if (l > 0) pos_list[op++] = i;
-      if ((l == 0) && (!scores || scores[i] > bg_low)) neg_list[on++] = i;
+    const int lane = tid & 31, warp = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    if (tid == 0) s_pos[64] = s_neg[64] = 0;  // running totals; [0,32) / [32,64): per-warp offsets of even / odd tiles
+    int l_next = tid < n ? labels[tid] : -1;
+    float s_next = (scores && tid < n) ? scores[tid] : 0.f;
+    __syncthreads();
+    int par = 0;
+    for (int t0 = 0; t0 < n; t0 += kSampThreads, par ^= 32) {
+      const int i = t0 + tid, l = l_next;
+      const float sc = s_next;
+      const int inx = i + kSampThreads;
+      l_next = inx < n ? labels[inx] : -1;
+      s_next = (scores && inx < n) ? scores[inx] : 0.f;
+      const bool isp = l > 0, isn = (l == 0) && (!scores || sc > bg_low);
+      const unsigned bp = __ballot_sync(0xffffffffu, isp), bn = __ballot_sync(0xffffffffu, isn);
+      if (lane == 0) {
+        s_pos[par + warp] = __popc(bp);
+        s_neg[par + warp] = __popc(bn);
+      }
+      __syncthreads();
+      if (warp == 0) {  // exclusive scan of the warp totals, offset by the running totals
+        int vp = s_pos[par + lane], vn = s_neg[par + lane];
+        int ip = vp, in_ = vn;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, ip, d), un = __shfl_up_sync(0xffffffffu, in_, d);
+          if (lane >= d) {
+            ip += up;
+            in_ += un;
+          }
+        }
+        const int bp0 = s_pos[64], bn0 = s_neg[64];
+        s_pos[par + lane] = bp0 + ip - vp;
+        s_neg[par + lane] = bn0 + in_ - vn;
+        if (lane == 31) {
+          s_pos[64] = bp0 + ip;
+          s_neg[64] = bn0 + in_;
+        }
+      }
+      __syncthreads();
+      if (isp) pos_list[s_pos[par + warp] + __popc(bp & lt)] = i;
+      if (isn) neg_list[s_neg[par + warp] + __popc(bn & lt)] = i;
+      // (the next tile writes the OTHER half of the offset arrays; its first barrier orders it after these reads)
     }
+    __syncthreads();
   }
-  __syncthreads();
-  const int n_pos = s_pos[kSampThreads], n_neg = s_neg[kSampThreads];
+  const int n_pos = s_pos[64], n_neg = s_neg[64];
   int n_fg;
   if (n_pos < exp_fg) {
     n_fg = n_pos;
