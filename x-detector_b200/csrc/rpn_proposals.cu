@@ -134,16 +134,28 @@ __global__ void __launch_bounds__(kSelThreads) rpn_topk_kernel(const float* __re
       if (tid == 0) {
         s_prefix = 0ull;
         s_remaining = keff;
+        s_count = 0;  // (doubles as the "resolved far enough" flag of the pass loop)
       }
+      __syncthreads();
+      // from the top byte down, but only until the candidates fit the sort buffer: after a pass G keys lie above the
+      // threshold bucket (all selected) and E inside it; once G + E <= P the bucket is simply sorted along (its surplus
+      // lands behind position keff).  Typically one or two passes instead of eight; four loads in flight per thread.
+      constexpr int U = 4;
       for (int pass = 0; pass < 8; ++pass) {
         const int shift = 56 - 8 * pass;
         for (int i = tid; i < 256; i += nthr) hist[i] = 0;
         __syncthreads();
         const unsigned long long prefix = s_prefix;
-        for (int i = tid; i < A_tot; i += nthr) {
-          const unsigned long long k = keys[i];
-          const bool match = (pass == 0) || ((k >> (shift + 8)) == (prefix >> (shift + 8)));
-          if (match && k != 0ull) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
+        for (int i0 = tid; i0 < A_tot; i0 += U * nthr) {
+          unsigned long long kk[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) kk[u] = keys[min(i0 + u * nthr, A_tot - 1)];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const unsigned long long k = kk[u];
+            const bool match = (pass == 0) || ((k >> (shift + 8)) == (prefix >> (shift + 8)));
+            if (i0 + u * nthr < A_tot && match && k != 0ull) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
+          }
         }
         __syncthreads();
         if (tid == 0) {
@@ -155,10 +167,15 @@ __global__ void __launch_bounds__(kSelThreads) rpn_topk_kernel(const float* __re
           }
           s_prefix = prefix | ((unsigned long long)b << shift);
           s_remaining = rem;
+          if ((keff - rem) + (int)hist[b] <= P) s_count = 1;
         }
         __syncthreads();
+        const int done = s_count;
+        __syncthreads();
+        if (done) break;
       }
-      thr = s_prefix;
+      thr = s_prefix;  // (low bits zero when the loop left early: the whole bucket qualifies)
+      if (thr == 0ull) thr = 1ull;  // never the filtered-out keys
     }
 
     // compact the selected keys into shared memory, pad with zeros
