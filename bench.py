@@ -719,18 +719,56 @@ class LightHeadResnet50Train:
         barrier()
         step_ms = e0.elapsed_time(e1) / args.steps
 
-        def e2e_step():
-            o = step(host)  # pinned host tensors -> H2D copies into the step's input buffers
-            losses_h.copy_(torch.stack([o["rpn_cross_entropy_loss"], o["rpn_location_loss"], o["head_loss"]]),
-                           non_blocking=True)
+        # ---- end to end with HOST buffers, every step: H2D of the batch (images, boxes, labels, shuffle keys), D2H of
+        # the three losses.  Double-buffered like the inference arm: step i+1's batch travels host->device on a copy
+        # stream while step i computes; the host reads the losses of step i-1 before it enqueues step i+1.
+        stage = [[torch.empty_like(t) for t in static] for _ in range(2)]
+        loss_d = [torch.empty(3, dtype=torch.float32, device="cuda") for _ in range(2)]
+        loss_hh = [losses_h, torch.empty_like(losses_h).pin_memory()]
+        cur = torch.cuda.current_stream()
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+        ev_loss = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+
+        def upload(b):
+            for s_, h_ in zip(stage[b], host):
+                s_.copy_(h_, non_blocking=True)
+
+        def e2e_run(n):
+            with torch.cuda.stream(s_in):
+                upload(0)
+                ev_in[0].record(s_in)
+            for i in range(n):
+                b = i & 1
+                if i + 1 < n:
+                    with torch.cuda.stream(s_in):
+                        if i >= 1:
+                            s_in.wait_event(ev_free[b ^ 1])
+                        upload(b ^ 1)
+                        ev_in[b ^ 1].record(s_in)
+                cur.wait_event(ev_in[b])
+                for s_, d_ in zip(static, stage[b]):
+                    s_.copy_(d_, non_blocking=True)  # device -> device into the step's (graph-captured) input buffers
+                ev_free[b].record(cur)
+                o = step(static)
+                if i >= 2:
+                    cur.wait_event(ev_done[b])
+                torch.stack([o["rpn_cross_entropy_loss"], o["rpn_location_loss"], o["head_loss"]], out=loss_d[b])
+                ev_loss[b].record(cur)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_loss[b])
+                    loss_hh[b].copy_(loss_d[b], non_blocking=True)
+                    ev_done[b].record(s_out)
+                if i >= 1:
+                    ev_done[b ^ 1].synchronize()  # the host has the losses of step i-1
             torch.cuda.synchronize()
 
-        for _ in range(2):
-            e2e_step()
+        e2e_run(3)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
+        e2e_run(args.steps)
         barrier()
         e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
         clocks = sampler.finish()
