@@ -49,6 +49,8 @@ def _image_nhwc(images):
     fp32 NHWC as it is."""
     if ops.conv.PRECISION == "f16x2":
         return images.permute(0, 2, 3, 1).contiguous()
+    if images.is_cuda and images.shape[1] <= 8 and images.dtype == torch.float32:   # (the stem's coalesced repack)
+        return ops.image_to_nhwc8(images.contiguous(), 0, images.shape[3])
     return T.nchw_f32_to_nhwc_bf16(images.contiguous(), pitch=8)
 
 
