@@ -325,6 +325,9 @@ int xdet_maxpool3x3s2_f32x(const float* d_src, float* d_dst, void* d_dst_pair, f
  * and / or d_dst_pair (the f16x2 planes the pointwise convolution reads) may be NULL. */
 int xdet_depthwise3x3_f32x(const float* d_src, const float* d_weights, float* d_dst, void* d_dst_pair, long long pair_plane,
                            int N, int H, int W, int C, int dilation, int relu_in, void* stream);
+/* xdet_depthwise3x3_f32x has two implementations with identical results: TMA-staged tiles (default) and a register-window
+ * kernel; 0 selects the second (tests compare the two, tools time them). */
+void xdet_set_depthwise_f32_tma(int enabled);
 
 /* Input pipeline of the eval / test scripts.
  * Replaces: light_head_preprocess_for_eval / _for_test preprocessing/common_preprocessing.py:383-458 with

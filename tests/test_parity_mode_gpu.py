@@ -259,7 +259,11 @@ def test_f16x2_elementwise_kernels_match_the_fp32_forms(xd):
     """The vectorised fp32 depthwise / max-pool kernels of the f16x2 precision (window in registers, fused split planes)
     against the plain fp32 kernels: same values bit for bit, planes == split2(values)."""
     g = torch.Generator(device="cuda").manual_seed(9)
-    for shape, dil in (((2, 19, 23, 72), 1), ((1, 50, 50, 728), 1), ((2, 10, 12, 1536), 2), ((1, 5, 4, 8), 2)):
+    from xdet_b200 import _native
+    for shape, dil in (((2, 19, 23, 72), 1), ((1, 50, 50, 728), 1), ((2, 10, 12, 1536), 2), ((1, 5, 4, 8), 2),
+                       # tile corners of the TMA-staged kernel: exact multiples of the 8 x 16 x 32 tile, one past them,
+                       # more tiles than CTAs (the stages wrap), a channel tail inside the last 32-channel box
+                       ((2, 8, 16, 32), 1), ((3, 33, 47, 136), 1), ((1, 9, 17, 40), 2), ((6, 64, 80, 264), 1)):
         x = torch.randn(shape, generator=g, device="cuda")
         w9 = torch.randn((9, shape[-1]), generator=g, device="cuda")
         for relu_in in (False, True):
@@ -267,8 +271,14 @@ def test_f16x2_elementwise_kernels_match_the_fp32_forms(xd):
             with xd.precision("f16x2"):
                 both = xd.depthwise3x3(x, w9, dilation=dil, relu_in=relu_in, forms="both")
                 only = xd.depthwise3x3(x, w9, dilation=dil, relu_in=relu_in)
+                _native.lib().xdet_set_depthwise_f32_tma(0)      # the register-window implementation of the same entry
+                try:
+                    regs = xd.depthwise3x3(x, w9, dilation=dil, relu_in=relu_in, forms="both")
+                finally:
+                    _native.lib().xdet_set_depthwise_f32_tma(1)
             assert torch.equal(both, want) and torch.equal(both._pair, xd.split2(want))
             assert only._pair_only and torch.equal(only._pair, both._pair)
+            assert torch.equal(regs, want) and torch.equal(regs._pair, both._pair)
     x = torch.randn((2, 37, 41, 64), generator=g, device="cuda")
     res = torch.randn((2, 19, 21, 64), generator=g, device="cuda")
     sc, bi = torch.rand(64, generator=g, device="cuda") + 0.5, torch.randn(64, generator=g, device="cuda")

@@ -123,6 +123,8 @@ def _declare_train(lib):
     lib.xdet_smooth_l1.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_float, c_ll, c_void_p, c_void_p, c_int, c_void_p]
     lib.xdet_sgd_momentum_conv.argtypes = [c_void_p] * 5 + [c_int] * 9 + [c_float] * 4 + [c_void_p]
     lib.xdet_sgd_momentum_vec.argtypes = [c_void_p] * 3 + [c_ll] + [c_float] * 4 + [c_void_p]
+    lib.xdet_set_depthwise_f32_tma.argtypes = [c_int]
+    lib.xdet_set_depthwise_f32_tma.restype = None
     lib.xdet_sgd_momentum_multi.argtypes = [c_void_p, c_int, c_int, c_float, c_float, c_float, c_void_p]
     lib.xdet_match_workspace_bytes.argtypes = [c_int, c_int]
     lib.xdet_match_workspace_bytes.restype = c_size_t

@@ -622,6 +622,109 @@ __global__ void __launch_bounds__(256) depthwise3x3_f32x_kernel(const float* __r
   }
 }
 
+// The same depthwise convolution with the input staged by TMA (what the Xception paths run): a persistent CTA walks
+// tiles of TH x TW pixels x 32 channels; one 4-D box {32 ch, TW+2D, TH+2D, 1} per tile lands in shared memory with the
+// halo and TMA's zero fill outside the image (= 'SAME' padding), kDwStages tiles ahead of the arithmetic.  The register
+// kernel above keeps its in-flight loads in registers -- 3 x 16 B per thread at 25 % occupancy, ~24 KB per SM, which by
+// Little's law is ~2.6 TB/s of requests against a 3x re-read of every input --; here the in-flight bytes live in shared
+// memory (3 boxes, ~70 KB per SM) and the halo costs 1.4x.  A thread owns one float4 of channels for 4 pixels of the
+// tile; a quarter-warp reads 128 contiguous bytes of one pixel (no bank conflicts).  Same taps, same fmaf order.
+constexpr int kDwTH = 8, kDwTW = 16, kDwCB = 32, kDwStages = 4, kDwThreads = 256;
+
+struct DwTile {
+  int n, y0, x0, c0;
+};
+
+template <int D>
+__global__ void __launch_bounds__(kDwThreads, 2) depthwise3x3_f32_tma_kernel(
+    const __grid_constant__ CUtensorMap map_src, const float* __restrict__ w9c, float* __restrict__ dst,
+    __half* __restrict__ dst_pair, long long plane, int N, int H, int W, int C, int relu_in, int tiles_x, int tiles_y,
+    int tiles_c, int total_tiles) {
+  constexpr int HW_ = kDwTW + 2 * D, HH_ = kDwTH + 2 * D;
+  constexpr uint32_t kBox = (uint32_t)HW_ * HH_ * kDwCB * 4;
+  extern __shared__ unsigned char dw_smem_raw[];
+  unsigned char* smem = dw_smem_raw + ((128u - (ptx::smem_u32(dw_smem_raw) & 127u)) & 127u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)kDwStages * kBox);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    ptx::prefetch_tmap(&map_src);
+    for (int s_ = 0; s_ < kDwStages; ++s_) ptx::mbar_init(&full_bar[s_], 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  auto decode = [&](int t) {
+    DwTile d;
+    d.c0 = (t % tiles_c) * kDwCB;
+    t /= tiles_c;
+    d.x0 = (t % tiles_x) * kDwTW;
+    t /= tiles_x;
+    d.y0 = (t % tiles_y) * kDwTH;
+    d.n = t / tiles_y;
+    return d;
+  };
+  auto issue = [&](int t, int stage) {
+    const DwTile d = decode(t);
+    ptx::mbar_arrive_expect_tx(&full_bar[stage], kBox);
+    ptx::tma_load_4d(smem + (size_t)stage * kBox, &map_src, &full_bar[stage], d.c0, d.x0 - D, d.y0 - D, d.n);
+  };
+  const int first = blockIdx.x, stride = gridDim.x;
+  if (tid == 0)
+    for (int s_ = 0; s_ < kDwStages - 1; ++s_)
+      if (first + s_ * stride < total_tiles) issue(first + s_ * stride, s_);
+
+  const int cv = tid & 7, p0 = tid >> 3;  // float4 of channels inside the 32-channel box; first of this thread's 4 pixels
+  int it = 0;
+  for (int t = first; t < total_tiles; t += stride, ++it) {
+    const int stage = it % kDwStages;
+    // the stage that tile it + kDwStages - 1 will use was read in iteration it - 1: every thread is past it (barrier below)
+    if (tid == 0) {
+      const int tn = t + (kDwStages - 1) * stride;
+      if (tn < total_tiles) issue(tn, (it + kDwStages - 1) % kDwStages);
+    }
+    const DwTile d = decode(t);
+    const int c = d.c0 + cv * 4;
+    float4 wt[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+      wt[k] = c < C ? __ldg(reinterpret_cast<const float4*>(w9c + (long long)k * C + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ptx::mbar_wait(&full_bar[stage], (uint32_t)(it / kDwStages) & 1u);
+    const float4* tile = reinterpret_cast<const float4*>(smem + (size_t)stage * kBox);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int pix = p0 + 32 * q, py = pix / kDwTW, px = pix % kDwTW;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          float4 v = tile[((py + kh * D) * HW_ + (px + kw * D)) * (kDwCB / 4) + cv];
+          if (relu_in) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+          const float4 k = wt[kh * 3 + kw];
+          a.x = __fmaf_rn(v.x, k.x, a.x);
+          a.y = __fmaf_rn(v.y, k.y, a.y);
+          a.z = __fmaf_rn(v.z, k.z, a.z);
+          a.w = __fmaf_rn(v.w, k.w, a.w);
+        }
+      }
+      const int y = d.y0 + py, x = d.x0 + px;
+      if (y < H && x < W && c < C) {
+        const long long o = (((long long)d.n * H + y) * W + x) * C + c;
+        if (dst) *reinterpret_cast<float4*>(dst + o) = a;
+        if (dst_pair) {
+          __half h0, l0, h1, l1, h2, l2, h3, l3;
+          split_f16x2(a.x, h0, l0);
+          split_f16x2(a.y, h1, l1);
+          split_f16x2(a.z, h2, l2);
+          split_f16x2(a.w, h3, l3);
+          *reinterpret_cast<uint2*>(dst_pair + o) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
+          *reinterpret_cast<uint2*>(dst_pair + plane + o) = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
+        }
+      }
+    }
+    __syncthreads();  // every thread has read this stage: it may be refilled (by the issue at the top of the next turn)
+  }
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   static std::once_flag once;
@@ -887,6 +990,10 @@ extern "C" int xdet_maxpool3x3s2_f32x(const float* d_src, float* d_dst, void* d_
   return after_launch("maxpool3x3s2_f32x_kernel");
 }
 
+static int g_dw_tma = 1;
+// 0: the register-window kernel (kept as the second implementation the tests compare against), 1: the TMA-staged one
+extern "C" void xdet_set_depthwise_f32_tma(int enabled) { g_dw_tma = enabled ? 1 : 0; }
+
 extern "C" int xdet_depthwise3x3_f32x(const float* d_src, const float* d_weights, float* d_dst, void* d_dst_pair,
                                       long long pair_plane, int N, int H, int W, int C, int dilation, int relu_in,
                                       void* stream) {
@@ -895,14 +1002,48 @@ extern "C" int xdet_depthwise3x3_f32x(const float* d_src, const float* d_weights
   if (!d_dst && !d_dst_pair) return fail(XDET_EINVAL, "depthwise_f32x: no output");
   if (d_dst_pair && pair_plane % 8 != 0) return fail(XDET_EINVAL, "depthwise_f32x: pair planes must be 16-byte aligned");
   if (N == 0) return XDET_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  __half* pp = reinterpret_cast<__half*>(d_dst_pair);
+  if ((reinterpret_cast<uintptr_t>(d_src) & 15) == 0 && C % 4 == 0 && W >= 4 && H >= 4 && g_dw_tma) {
+    // TMA-staged kernel: fp32 tensor map {C, W, H, N}, box {32, TW+2D, TH+2D, 1}, no swizzle, zero fill outside
+    auto fn = encode_fn();
+    if (!fn) return fail(XDET_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    CUtensorMap map;
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)C * 4 * W, (cuuint64_t)C * 4 * W * H};
+    const cuuint32_t box[4] = {(cuuint32_t)kDwCB, (cuuint32_t)(kDwTW + 2 * dilation), (cuuint32_t)(kDwTH + 2 * dilation), 1};
+    const cuuint32_t ones[4] = {1, 1, 1, 1};
+    CUresult r = fn(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d_src), dims, strides, box, ones,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(XDET_ECUDA, "cuTensorMapEncodeTiled(depthwise) failed with CUresult %d", (int)r);
+    const int tiles_x = (W + kDwTW - 1) / kDwTW, tiles_y = (H + kDwTH - 1) / kDwTH, tiles_c = (C + kDwCB - 1) / kDwCB;
+    const long long total_t = (long long)N * tiles_y * tiles_x * tiles_c;
+    if (total_t < (1ll << 31)) {
+      const size_t box_bytes = (size_t)(kDwTW + 2 * dilation) * (kDwTH + 2 * dilation) * kDwCB * 4;
+      const size_t smem = kDwStages * box_bytes + kDwStages * sizeof(uint64_t) + 128;
+      const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+      const int grid = (int)std::min<long long>(total_t, (long long)kNumSMs * per_sm);
+      if (dilation == 1) {
+        XDET_TRY(check_cuda(cudaFuncSetAttribute(depthwise3x3_f32_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem), "cudaFuncSetAttribute(depthwise tma)"));
+        depthwise3x3_f32_tma_kernel<1><<<grid, kDwThreads, smem, st>>>(map, d_weights, d_dst, pp, pair_plane, N, H, W, C,
+                                                                      relu_in, tiles_x, tiles_y, tiles_c, (int)total_t);
+      } else {
+        XDET_TRY(check_cuda(cudaFuncSetAttribute(depthwise3x3_f32_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem), "cudaFuncSetAttribute(depthwise tma)"));
+        depthwise3x3_f32_tma_kernel<2><<<grid, kDwThreads, smem, st>>>(map, d_weights, d_dst, pp, pair_plane, N, H, W, C,
+                                                                      relu_in, tiles_x, tiles_y, tiles_c, (int)total_t);
+      }
+      return after_launch("depthwise3x3_f32_tma_kernel");
+    }
+  }
   // strip height: tall strips amortise the window fill, but keep >= ~8 CTAs per SM in flight
   int YS = 16;
   while (YS > 2 && (long long)N * ((H + YS - 1) / YS) * W * (C / 4) < 8ll * kNumSMs * 256) YS /= 2;
   const long long total = (long long)N * ((H + YS - 1) / YS) * W * (C / 4);
   long long blocks = (total + 255) / 256;
   if (blocks > (1ll << 30)) blocks = 1ll << 30;
-  cudaStream_t st = (cudaStream_t)stream;
-  __half* pp = reinterpret_cast<__half*>(d_dst_pair);
   if (dilation == 1)
     depthwise3x3_f32x_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(d_src, d_weights, d_dst, pp, pair_plane, N, H, W, C, relu_in, YS, total);
   else
