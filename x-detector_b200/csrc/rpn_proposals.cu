@@ -303,19 +303,29 @@ __global__ void __launch_bounds__(kSelThreads) nms_scan_kernel(
   const int nworkers = nthr - 32;
   __shared__ unsigned long long s_surv2[2];
   int nk = 0;  // every thread tracks the kept count in a register
-  unsigned long long d0 = 0ull, d1 = 0ull;
+  unsigned long long d0 = 0ull, d1 = 0ull, e0 = 0ull, e1 = 0ull;  // diagonal words / words of the NEXT column of block cb
   if (warp_id == 0) {
     d0 = lane_id < K ? m[(long long)lane_id * words] : 0ull;
     d1 = lane_id + 32 < K ? m[(long long)(lane_id + 32) * words] : 0ull;
+    if (words > 1) {
+      e0 = lane_id < K ? m[(long long)lane_id * words + 1] : 0ull;
+      e1 = lane_id + 32 < K ? m[(long long)(lane_id + 32) * words + 1] : 0ull;
+    }
   }
   for (int cb = 0; cb < words && nk < out_size; ++cb) {
     if (warp_id == 0) {
-      // prefetch the next block's diagonal words
-      unsigned long long n0 = 0ull, n1 = 0ull;
+      // prefetch the next block's diagonal words AND its rows' words of the column after it (the survivors among them
+      // are OR-ed into removed[cb + 2] in the next iteration: fetched for all 64 rows now, the load no longer waits for
+      // the sequential resolution that decides which of them count)
+      unsigned long long n0 = 0ull, n1 = 0ull, f0 = 0ull, f1 = 0ull;
       if (cb + 1 < words) {
         const int r0 = (cb + 1) * 64 + lane_id, r1 = r0 + 32;
         if (r0 < K) n0 = m[(long long)r0 * words + cb + 1];
         if (r1 < K) n1 = m[(long long)r1 * words + cb + 1];
+        if (cb + 2 < words) {
+          if (r0 < K) f0 = m[(long long)r0 * words + cb + 2];
+          if (r1 < K) f1 = m[(long long)r1 * words + cb + 2];
+        }
       }
       unsigned long long rem = removed[cb], surv = 0ull;
       int k = nk;
@@ -335,7 +345,7 @@ __global__ void __launch_bounds__(kSelThreads) nms_scan_kernel(
         const int j = lane_id + 32 * h;
         if ((surv >> j) & 1ull) {
           kept[nk + __popcll(surv & ((1ull << j) - 1ull))] = cb * 64 + j;
-          if (cb + 1 < words) next_word |= m[(long long)(cb * 64 + j) * words + cb + 1];
+          next_word |= (h == 0 ? e0 : e1);  // (prefetched one iteration ago; 0 beyond the last column)
         }
       }
       const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)(next_word & 0xffffffffull));
@@ -347,6 +357,8 @@ __global__ void __launch_bounds__(kSelThreads) nms_scan_kernel(
       }
       d0 = n0;
       d1 = n1;
+      e0 = f0;
+      e1 = f1;
     } else if (cb >= 1) {
       const int pb = cb - 1;  // block whose survivors' rows are applied to the columns >= pb + 2
       const unsigned long long surv = s_surv2[pb & 1];
