@@ -330,13 +330,15 @@ __global__ void __launch_bounds__(kSelThreads) nms_scan_kernel(
       unsigned long long rem = removed[cb], surv = 0ull;
       int k = nk;
       const int n_in = min(64, K - cb * 64);
-      for (int j = 0; j < n_in && k < out_size; ++j) {
+      if (n_in < 64) rem |= ~0ull << n_in;  // positions past the list can never survive
+      // jump from survivor to survivor (the lowest clear bit of `rem`): a block with a dozen survivors costs a dozen
+      // shuffle steps, not 64 -- this loop is the serial spine of the whole scan
+      while (k < out_size && rem != ~0ull) {
+        const int j = __ffsll((long long)~rem) - 1;
         const unsigned long long dj = __shfl_sync(0xffffffffu, j < 32 ? d0 : d1, j & 31);
-        if (!((rem >> j) & 1ull)) {
-          surv |= (1ull << j);
-          ++k;
-          rem |= dj;
-        }
+        surv |= (1ull << j);
+        ++k;
+        rem |= dj | ((2ull << j) - 1ull);  // its victims (later positions) and everything up to itself
       }
       // survivors' positions in the kept list, and their words of column cb+1
       unsigned long long next_word = 0ull;
