@@ -806,7 +806,11 @@ class LightHeadResnet50Train:
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},
                 "gpu_launches_per_step": int(launches_per_step),
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                             "frac": achieved / peak, "traffic": None,
+                             "frac": achieved / peak,
+                             "traffic": ncu_traffic("train" if self.backbone == "resnet50" else "xception_train", "conv_"),
+                             "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the convolution kernels "
+                                             "(forward, input and weight gradients) in one step, from the committed ncu "
+                                             "launch list (profiles/ncu_traffic_train_r2.txt)",
                              "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
                              "kernel": "conv_gemm_kernel (forward + input gradients) and conv_wgrad_kernel, %d launches per step" % len(prof),
                              "algorithmic_flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms,
