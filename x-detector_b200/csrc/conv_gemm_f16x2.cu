@@ -446,6 +446,7 @@ __global__ void __launch_bounds__(256) split2_kernel(const float* __restrict__ s
                                                      long long sx, long long sc, int H, int W, int C,
                                                      __half* __restrict__ dst, int cs, int Wp, int x_off,
                                                      long long plane, int relu, long long total) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL-launched convolution may come up behind us
   const long long step = (long long)gridDim.x * blockDim.x;
   const int c8 = cs / 8;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
@@ -476,6 +477,7 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_f32x_kernel(
     __half* __restrict__ dst2_pair, const float* __restrict__ scale2, const float* __restrict__ bias2,
     const float* __restrict__ residual, long long plane, int H, int W, int C, int Ho, int Wo, int pad_top, int pad_left,
     long long total) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL-launched convolution may come up behind us
   const long long step = (long long)gridDim.x * blockDim.x;
   const int c8 = C / 8;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
@@ -552,6 +554,7 @@ __global__ void __launch_bounds__(256) depthwise3x3_f32x_kernel(const float* __r
                                                                 float* __restrict__ dst, __half* __restrict__ dst_pair,
                                                                 long long plane, int N, int H, int W, int C, int relu_in,
                                                                 int YS, long long total) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL-launched convolution may come up behind us
   constexpr int R = 2 * D + 1;
   const int C4 = C / 4;
   const int HY = (H + YS - 1) / YS;
@@ -640,6 +643,7 @@ __global__ void __launch_bounds__(kDwThreads, 2) depthwise3x3_f32_tma_kernel(
     const __grid_constant__ CUtensorMap map_src, const float* __restrict__ w9c, float* __restrict__ dst,
     __half* __restrict__ dst_pair, long long plane, int N, int H, int W, int C, int relu_in, int tiles_x, int tiles_y,
     int tiles_c, int total_tiles) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL-launched convolution may come up behind us
   constexpr int HW_ = kDwTW + 2 * D, HH_ = kDwTH + 2 * D;
   constexpr uint32_t kBox = (uint32_t)HW_ * HH_ * kDwCB * 4;
   extern __shared__ unsigned char dw_smem_raw[];

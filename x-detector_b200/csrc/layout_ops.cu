@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* 
                                                            unsigned char* __restrict__ argmax, int N, int H,
                                                            int W, int C, int Ho, int Wo, int pad_top, int pad_left,
                                                            long long total_vec) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL-launched convolution may come up behind us
   const int C8 = C / 8;
   const long long step = (long long)gridDim.x * blockDim.x;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total_vec; e += step) {
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(256) affine_relu_kernel(const __nv_bfloat16* _
                                                           const float* __restrict__ scale,
                                                           const float* __restrict__ bias, int C, int relu, int cgb,
                                                           long long rows) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL-launched convolution may come up behind us
   const int rl = 256 / cgb;
   const int cg = threadIdx.x % cgb, lane_row = threadIdx.x / cgb;
   const int c0 = (blockIdx.x * cgb + cg) * 8;
@@ -206,6 +208,7 @@ __global__ void __launch_bounds__(256) affine_relu_kernel(const __nv_bfloat16* _
 __global__ void __launch_bounds__(256) f32_to_bf16_rows_kernel(const float* __restrict__ src,
                                                                __nv_bfloat16* __restrict__ dst, long long rows,
                                                                int cols, int dst_pitch) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL-launched convolution may come up behind us
   const long long total = rows * dst_pitch;
   const long long step = (long long)gridDim.x * blockDim.x;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
@@ -226,6 +229,7 @@ __global__ void __launch_bounds__(256, 3) depthwise3x3_kernel(const __nv_bfloat1
                                                            const float* __restrict__ w /* [9][C] */,
                                                            __nv_bfloat16* __restrict__ dst, int N, int H, int W, int C,
                                                            int relu_in, long long total) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL-launched convolution may come up behind us
   constexpr int WIN = PX + 2 * DIL;
   const int C2 = C / 2;
   const int WX = (W + PX - 1) / PX;
@@ -316,6 +320,7 @@ __global__ void __launch_bounds__(256, 2) depthwise3x3_rows_kernel(const __nv_bf
                                                                    const float* __restrict__ w /* [9][C] */,
                                                                    __nv_bfloat16* __restrict__ dst, int N, int H, int W,
                                                                    int C, int relu_in, int YS, long long total) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL-launched convolution may come up behind us
   constexpr int WIN = PX + 2;
   constexpr int RS = D + 1;  // ring slots: D rows in flight + the one being consumed
   __shared__ uint2 ring[RS * WIN * 256];
@@ -468,6 +473,7 @@ __global__ void __launch_bounds__(256, 2) depthwise3x3_rows_kernel(const __nv_bf
 __global__ void __launch_bounds__(256) image_to_nhwc8_kernel(const float* __restrict__ src,
                                                              __nv_bfloat16* __restrict__ dst, int N, int C, int H,
                                                              int W, int Wp, int pad_left, long long total) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL-launched convolution may come up behind us
   const long long step = (long long)gridDim.x * blockDim.x;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
     const int xp = (int)(e % Wp);

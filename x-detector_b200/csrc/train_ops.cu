@@ -206,6 +206,9 @@ __global__ void __launch_bounds__(256) bn_apply_finalize_kernel(
     const float* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
     float decay, float* __restrict__ moving_mean, float* __restrict__ moving_var, float* __restrict__ scale_out,
     float* __restrict__ shift_out, float* __restrict__ mean_out, float* __restrict__ invstd_out, int relu) {
+  // (the convolution that follows is launched with programmatic stream serialization: let its CTAs come up -- barriers,
+  // TMEM, tensor maps -- while this kernel runs; it still waits for this grid's completion before it reads anything)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const ColMap m(cgb);
   // the first row lane of the block finalizes the block's channels once and shares them (every thread repeating the
   // divisions and square roots cost more than the normalisation itself on the small layers)
@@ -322,6 +325,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
                                                            const float* __restrict__ sums,
                                                            const __nv_bfloat16* __restrict__ add_in, long long rows,
                                                            int C, int relu, int cgb, __nv_bfloat16* __restrict__ dx) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // (see bn_apply_finalize_kernel)
   const ColMap m(cgb);
   if (m.c0 >= C) return;
   const float inv_m = 1.f / (float)rows;
@@ -418,6 +422,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const unsigned char* _
 
 __global__ void relu_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, uint4* __restrict__ dx,
                                 long long n8) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL-launched convolution may come up behind us
   const long long step = (long long)gridDim.x * blockDim.x;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n8; e += step) {
     const uint4 d = __ldg(dy + e), v = __ldg(y + e);
