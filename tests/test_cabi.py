@@ -96,3 +96,32 @@ def test_product_fails_loudly_without_the_cuda_library(tmp_path):
     env = dict(os.environ, XDET_B200_LIB=str(tmp_path / "absent" / "libxdet_b200.so"))
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "LOUD" in r.stdout, r.stdout + r.stderr
+
+
+def test_ctypes_structures_match_the_header(tmp_path):
+    """The Python side fills the descriptor structs of include/xdet_b200.h through ctypes mirrors: size and the offset of
+    every field must equal what the C compiler lays out (a silent drift would corrupt every launch)."""
+    import subprocess
+    import xdet_b200  # noqa: F401
+    from xdet_b200.ops import conv, train
+    pairs = [("xdet_conv_desc", conv.ConvDesc), ("xdet_conv_f16x2_desc", conv.ConvF16x2Desc),
+             ("xdet_wgrad_desc", conv.WgradDesc), ("xdet_sgd_item", train.SgdItem)]
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "xdet_b200.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        lines.append('  printf("%s %%zu", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('  printf(" %%zu", offsetof(%s, %s));' % (cname, fname))
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    assert len(out) == len(pairs)
+    for line, (cname, cls) in zip(out, pairs):
+        tok = line.split()
+        assert tok[0] == cname
+        assert int(tok[1]) == ctypes.sizeof(cls), (cname, tok[1], ctypes.sizeof(cls))
+        offs = [int(t) for t in tok[2:]]
+        assert offs == [getattr(cls, f).offset for f, _ in cls._fields_], cname
